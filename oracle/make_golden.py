@@ -1,0 +1,222 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (and the installed torchvision CPU
+NMS it depends on) on seeded synthetic inputs.  Run in the build container only:
+
+    python oracle/make_golden.py
+
+Inputs are regenerated from ``vision_conglomerate_b200.synth`` seeds by the tests; each fixture stores
+the generation parameters, a checksum of the inputs and the reference's outputs.
+TEST INFRASTRUCTURE -- never imported by the product.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torchvision
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness  # noqa: E402
+from vision_conglomerate_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def digest(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t).tobytes())
+    return h.hexdigest()[:16]
+
+
+def save(name, **kw):
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **kw)
+    print("wrote", name, {k: (v.shape if hasattr(v, "shape") else v) for k, v in kw.items()})
+
+
+DECODE_CASES = {
+    # name: (B, H, W, C, dist, seed, og_size)
+    "dec_sq64": (2, 64, 64, 80, "N", 11, None),
+    "dec_rect_rescale": (2, 96, 64, 3, "N", 12, (120, 100)),
+    "dec_rect_norescale": (1, 96, 64, 3, "N", 13, (96, 100)),   # `and` guard at detection.py:76 -> no rescale
+    "dec_T128": (3, 128, 128, 80, "TP", 7, None),
+}
+
+POST_CASES = {
+    # name: (decode case, iou, score_thr, box_allowance, tracked)
+    "post_sq64": ("dec_sq64", 0.65, 0.3, 4, None),
+    "post_sq64_lowthr": ("dec_sq64", 0.35, 0.001, None, None),
+    "post_T128_tracked": ("dec_T128", 0.35, 0.3, 4, (1, 4, 7, 16, 17)),
+    "post_T128": ("dec_T128", 0.65, 0.001, 4, None),
+}
+
+
+def gen_decode_post(ns):
+    decoded = {}
+    for name, (B, H, W, C, dist, seed, og) in DECODE_CASES.items():
+        raws = synth.raw_head_outputs(B, H, W, C, dist, seed)
+        anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+        preds = ref_harness.ref_decode_inference(raws, anc, H, W, og, C)
+        decoded[name] = (preds, C)
+        # training-mode decode of the sm scale as well
+        m = ns.DecodeOnly(C)
+        with torch.no_grad():
+            tr = m._get_scale_pred(raws[0].clone(), anc[0], input_shape=(H, W), inference=False)
+        save(name, params=np.array([B, H, W, C, seed, -1 if og is None else og[0], -1 if og is None else og[1]]),
+             dist=np.array(dist), in_digest=np.array(digest(*raws)),
+             boxes=preds[..., C + 1:C + 5].numpy(), logits_digest=np.array(digest(preds[..., :C + 1].contiguous())),
+             train_sm_boxes=tr[..., C + 1:C + 5].numpy())
+    for name, (dname, iou, thr, allow, tracked) in POST_CASES.items():
+        preds, C = decoded[dname]
+        cap = ref_harness.ref_post_process(preds, C, iou, thr, allow, tracked)
+        B = preds.shape[0]
+        # post_process_preds gives the drawing code one array per surviving image, in image order,
+        # skipping images left empty (inference_det.py:100-112).  Recover the image id from the NMS capture.
+        keep = cap["keep"]
+        sc = cap["scores"][keep]
+        m = sc > thr
+        simg = cap["idxs"][keep][m]
+        per = cap["per_image"]
+        save(name, decode_case=np.array(dname), iou=np.array(iou), thr=np.array(thr),
+             allow=np.array(-1 if allow is None else allow),
+             tracked=np.array(tracked if tracked else [], dtype=np.int64),
+             nms_keep=keep.numpy(), nms_scores_digest=np.array(digest(cap["scores"])),
+             xyxy=cap["boxes"].numpy() if cap["boxes"].numel() < 200000 else cap["boxes"][keep].numpy(),
+             scores_kept=sc.numpy(), kept_img=simg.numpy(),
+             n_images=np.array(len(per)),
+             per_image=np.concatenate(per, 0) if per else np.zeros((0, 6), np.float32),
+             per_image_counts=np.array([p.shape[0] for p in per], dtype=np.int64))
+
+
+def gen_nms():
+    cases = {}
+    b, s, g = synth.nms_boxes(3000, 4, seed=3)
+    cases["rand"] = (b, s, g, 0.5)
+    b, s, g = synth.nms_boxes(3000, 5, seed=4, ties=True)
+    cases["ties"] = (b, s, g, 0.5)
+    b, s, g = synth.nms_boxes(2000, 1, seed=5, extent=100.0)
+    cases["dense1"] = (b, s, g, 0.65)
+    # hand-made: IoU exactly 0.5 against thr 0.5 and 0.5-1e-12; zero-area; negative extent; 3-way tie
+    hb = torch.tensor([[0, 0, 2, 1], [1, 0, 3, 1],  # inter 1, union 3 -> 1/3
+                       [0, 0, 2, 2], [0, 0, 2, 1],  # inter 2, union 4 -> exactly 0.5
+                       [5, 5, 5, 5], [5, 5, 5, 5],  # zero area: 0/0 NaN never suppresses
+                       [9, 9, 8, 8], [8, 8, 9, 9],  # negative extent
+                       [20, 20, 30, 30], [20, 20, 30, 30], [20, 20, 30, 30]], dtype=torch.float32)
+    hs = torch.tensor([0.9, 0.8, 0.7, 0.6, 0.5, 0.5, 0.4, 0.3, 0.2, 0.2, 0.2])
+    hg = torch.zeros(11, dtype=torch.int64)
+    cases["hand_thr05"] = (hb, hs, hg, 0.5)
+    cases["hand_thr05m"] = (hb, hs, hg, 0.5 - 1e-12)
+    cases["hand_thr0"] = (hb, hs, hg, 0.0)
+    out = {}
+    for name, (b, s, g, thr) in cases.items():
+        keep = torchvision.ops.boxes._batched_nms_vanilla(b, s, g, thr)
+        keep2 = torchvision.ops.batched_nms(b, s, g, thr) if b.numel() > 4000 else keep
+        assert sorted(keep.tolist()) == sorted(keep2.tolist())
+        out[name + "_boxes"] = b.numpy()
+        out[name + "_scores"] = s.numpy()
+        out[name + "_idxs"] = g.numpy()
+        out[name + "_thr"] = np.array(thr)
+        out[name + "_keep"] = keep.numpy()
+    save("nms", **out)
+
+
+ASSIGN_CASES = {
+    # name: (targets factory, list of fmap shapes)
+    "c1": (lambda: synth.targets(2, 20, 80, 0, fixed=False), [(80, 80), (40, 40), (20, 20)]),
+    "b8g100": (lambda: synth.targets(8, 100, 80, 0), [(80, 80), (40, 40), (20, 20)]),
+    "adv": (lambda: synth.adversarial_targets(2, 80), [(80, 80), (40, 40), (20, 20), (12, 8)]),
+    "empty": (lambda: torch.zeros(0, 6), [(20, 20)]),
+}
+
+
+def gen_assign(ns):
+    out = {}
+    for name, (mk, fmaps) in ASSIGN_CASES.items():
+        t = mk()
+        out[name + "_in_digest"] = np.array(digest(t))
+        for (ny, nx) in fmaps:
+            for sc in synth.SCALES:
+                anc = synth.anchors_tensor(sc)
+                idx, cls, a, box, _, _ = ns.DetectionDataset.build_target_by_scale(t.clone(), (ny, nx), anc, 4.0, 0.5)
+                k = f"{name}_{ny}x{nx}_{sc}"
+                out[k + "_idx"] = torch.stack(idx, 0).numpy() if cls.numel() else np.zeros((4, 0), np.int64)
+                out[k + "_cls"] = cls.numpy()
+                out[k + "_anc"] = a.numpy().reshape(-1, 2)
+                out[k + "_box"] = box.numpy().reshape(-1, 4)
+    save("assign", **out)
+
+
+def gen_ciou(ns):
+    g = torch.Generator().manual_seed(21)
+    M = 512
+    p = torch.cat([torch.rand(M, 2, generator=g) * 1.5 - 0.25, torch.rand(M, 2, generator=g) * 6 + 0.05], 1)
+    t = torch.cat([torch.rand(M, 2, generator=g), torch.rand(M, 2, generator=g) * 6 + 0.05], 1)
+    p[:8] = t[:8]                      # identical boxes
+    p[8:16, 2:] = t[8:16, 2:]          # same size, shifted
+    p.requires_grad_(True)
+    c = ns.DetectionLoss.compute_ciou(p, t)
+    w = torch.linspace(0.5, 1.5, M)
+    (c * w).sum().backward()
+    save("ciou", p=p.detach().numpy(), t=t.numpy(), ciou=c.detach().numpy(), w=w.numpy(), grad=p.grad.numpy())
+
+
+LOSS_CASES = {
+    # name: (B, H, W, C, G, fixed, targets seed, preds seed)
+    "loss_sq64": (2, 64, 64, 80, 6, False, 0, 1),
+    "loss_collide": (2, 64, 64, 80, 40, True, 2, 3),     # 40 gt on 8x8/4x4/2x2 maps: heavy duplicate cells
+    "loss_c3_rect": (3, 96, 64, 3, 10, True, 4, 5),
+    "loss_empty": (2, 64, 64, 80, 0, True, 0, 1),
+    "loss_c1_640": (2, 640, 640, 80, 20, False, 0, 1),
+}
+
+
+def gen_loss(ns):
+    torch.set_num_threads(1)  # the reference's duplicate-index scatter is racy with more
+    for name, (B, H, W, C, G, fixed, ts, ps) in LOSS_CASES.items():
+        t = synth.targets(B, G, C, ts, fixed) if G > 0 else torch.zeros(0, 6)
+        preds = [p.requires_grad_(True) for p in synth.train_preds(B, H, W, C, ps)]
+        loss_mod = ns.DetectionLoss(ns.FakeModel(C, synth.ANCHORS), **synth.LOSS_CONFIG)
+        loss, metrics = loss_mod(tuple(preds), t.clone())
+        loss.backward()
+        kw = dict(params=np.array([B, H, W, C, G, int(fixed), ts, ps]), in_digest=np.array(digest(t, *preds)),
+                  loss=np.array(loss.item(), np.float64),
+                  metric_keys=np.array(list(metrics.keys())),
+                  metric_vals=np.array([float(v) for v in metrics.values()], np.float64))
+        big = preds[0].numel() > 400000
+        for sc, p in zip(synth.SCALES, preds):
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            if big:  # keep the fixture small: objectness plane checksums + sparse box/class grads
+                kw["grad_" + sc + "_obj_sum"] = np.array(g[..., 0].double().sum().item())
+                kw["grad_" + sc + "_abs_sum"] = np.array(g.double().abs().sum().item())
+                nz = (g[..., 1:].abs().sum(-1) > 0).nonzero()
+                sel = nz[:: max(1, nz.shape[0] // 64)]
+                kw["grad_" + sc + "_rows_idx"] = sel.numpy()
+                kw["grad_" + sc + "_rows"] = g[sel[:, 0], sel[:, 1], sel[:, 2], sel[:, 3]].numpy()
+            else:
+                kw["grad_" + sc] = g.numpy()
+        save(name, **kw)
+
+
+def gen_ratio(ns):
+    g = torch.Generator().manual_seed(31)
+    wh = 0.01 + 0.5 * torch.rand(1000, 2, generator=g)
+    anc = torch.tensor(sum((synth.ANCHORS[s] for s in synth.SCALES), []), dtype=torch.float32)
+    s1 = ns.make_anchors.ratio_metrics(anc, wh, 4.0)
+    s2 = ns.make_anchors.ratio_metrics_w_extras(anc, wh, 4.0)
+    s3 = ns.make_anchors.ratio_metrics_w_extras(anc, wh * 3.0, 2.0)
+    save("ratio", wh=wh.numpy(), anchors=anc.numpy(), score=np.array(s1), extras=np.array(s2), extras_x3_t2=np.array(s3))
+
+
+if __name__ == "__main__":
+    ns = ref_harness.load()
+    gen_decode_post(ns)
+    gen_nms()
+    gen_assign(ns)
+    gen_ciou(ns)
+    gen_loss(ns)
+    gen_ratio(ns)
+    print("torch", torch.__version__, "torchvision", torchvision.__version__)

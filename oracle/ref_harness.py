@@ -1,0 +1,147 @@
+"""Import the *unmodified* reference from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` to generate the committed
+fixtures under ``tests/golden/`` and by the ``-m "not gpu"`` tests that diff the
+oracle against the live reference when it is present.  The GPU box has no
+/root/reference: nothing that runs there imports this module.
+
+Recipe from SURVEY.md Appendix B: the reference imports ``supervision`` at module
+top (utils/utils.py:11, inference_det.py:12), which is not installed, so a stub
+module is registered first.  ``DetectionLoss`` only needs ``model.{sm,md,lg}_anchors``
+and ``model.num_classes`` (modules/detection_loss.py:91-93,141) -> ``FakeModel``.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+REF = os.environ.get("BOXGEOM_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REF, "modules", "detection_loss.py"))
+
+
+_mods = None
+
+
+def load():
+    """Returns a namespace with DetectionNet, DetectionLoss, DetectionDataset, inference_det,
+    make_anchors, utils and FakeModel."""
+    global _mods
+    if _mods is not None:
+        return _mods
+    if not available():
+        raise RuntimeError("reference not present at %s" % REF)
+    import torch
+    import torch.nn as nn
+
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if "supervision" not in sys.modules:
+        sv = types.ModuleType("supervision")
+        sv.Detections = type("Detections", (), {})
+        sv.ByteTrack = type("ByteTrack", (), {"__init__": lambda s, *a, **k: None})
+        sys.modules["supervision"] = sv
+    from modules.detection import DetectionNet
+    from modules.detection_loss import DetectionLoss
+    from dataset.detection_dataset import DetectionDataset
+    import inference_det
+    from utils import make_anchors, utils as ref_utils
+
+    inference_det.device = "cpu"  # module-global only defined under __main__ (inference_det.py:108 vs :318)
+
+    class FakeModel(nn.Module):
+        def __init__(self, num_classes, anchors):
+            super().__init__()
+            self.num_classes, self.num_keypoints = num_classes, 0
+            for k in ("sm", "md", "lg"):
+                setattr(self, k + "_anchors", nn.Parameter(torch.tensor(anchors[k], dtype=torch.float32)))
+
+    class DecodeOnly:
+        """Carries just what DetectionNet._get_scale_pred / _bbox_to_size / _make_2dgrid read from self."""
+        num_keypoints = None
+
+        def __init__(self, num_classes):
+            self.num_classes = num_classes
+
+        _get_scale_pred = DetectionNet._get_scale_pred
+        _bbox_to_size = DetectionNet._bbox_to_size
+        _make_2dgrid = DetectionNet._make_2dgrid
+
+    ns = types.SimpleNamespace(DetectionNet=DetectionNet, DetectionLoss=DetectionLoss,
+                               DetectionDataset=DetectionDataset, inference_det=inference_det,
+                               make_anchors=make_anchors, utils=ref_utils, FakeModel=FakeModel,
+                               DecodeOnly=DecodeOnly)
+    _mods = ns
+    return ns
+
+
+def ref_decode_inference(raws, anchors3, H, W, og_size=None, num_classes=80):
+    """Runs the reference's own _get_scale_pred x3, the rescale guard and the reshape/cat of
+    DetectionNet.forward (modules/detection.py:69-91) starting from the three head outputs."""
+    import torch
+    ns = load()
+    m = ns.DecodeOnly(num_classes)
+    with torch.no_grad():
+        ps = [m._get_scale_pred(r.clone(), a, input_shape=(H, W), inference=True) for r, a in zip(raws, anchors3)]
+        if (og_size is not None) and (og_size[0] != H and og_size[1] != W):
+            _from = torch.tensor([W, H, W, H])
+            _to = torch.tensor([og_size[1], og_size[0], og_size[1], og_size[0]])
+            ps = [m._bbox_to_size(p, _from, _to) for p in ps]
+        B = raws[0].shape[0]
+        D = raws[0].shape[-1]
+        ps = [p.reshape(B, -1, D) for p in ps]
+        return torch.cat(ps, dim=1).flatten(start_dim=1, end_dim=-2)
+
+
+def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_allowance=None, tracked_classes=None):
+    """Calls the reference's post_process_preds unmodified and captures (a) the arguments and result of
+    its torchvision.ops.batched_nms call and (b) the per-image box arrays it hands to the drawing code
+    (after the score threshold and the tracked-class filter)."""
+    import numpy as np
+    import torch
+    import torchvision
+    ns = load()
+    inf = ns.inference_det
+    cap = {"per_image": []}
+    real_nms = torchvision.ops.batched_nms
+
+    def spy_nms(boxes, scores, idxs, iou_threshold):
+        keep = real_nms(boxes, scores, idxs, iou_threshold)
+        cap.update(boxes=boxes.clone(), scores=scores.clone(), idxs=idxs.clone(), keep=keep.clone())
+        return keep
+
+    def spy_apply(img, boxes, **kw):
+        cap["per_image"].append(np.array(boxes, copy=True))
+        return img
+
+    class _NullImg:
+        @staticmethod
+        def fromarray(a):
+            class _I:
+                def save(self, f):
+                    pass
+            return _I()
+
+    old = (torchvision.ops.batched_nms, inf.apply_bboxes, inf.Image, inf.STORAGE_PATH)
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    try:
+        torchvision.ops.batched_nms = spy_nms
+        inf.apply_bboxes = spy_apply
+        inf.Image = _NullImg
+        inf.STORAGE_PATH = tmp
+        B = preds.shape[0]
+        imgs = torch.zeros(B, 3, 8, 8, dtype=torch.uint8)
+        with torch.no_grad():
+            inf.post_process_preds(imgs, preds.clone(), num_classes, iou_threshold=iou_threshold,
+                                   score_threshold=score_threshold, box_allowance=box_allowance,
+                                   tracked_classes=list(tracked_classes) if tracked_classes else None)
+    finally:
+        torchvision.ops.batched_nms, inf.apply_bboxes, inf.Image, inf.STORAGE_PATH = old
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return cap

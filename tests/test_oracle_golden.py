@@ -1,0 +1,139 @@
+"""CPU suite: the oracle (oracle/boxgeom_oracle.c) against the committed golden fixtures, which are
+outputs of the unmodified reference / torchvision-CPU (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from vision_conglomerate_b200 import synth
+from tests.util import assert_close, canon, digest, golden, rows_canon
+
+DEC = ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"]
+
+
+def _decode_inputs(g):
+    B, H, W, C, seed, og0, og1 = (int(v) for v in g["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(g["dist"]), seed)
+    assert digest(*raws) == str(g["in_digest"]), "synthetic generator drifted from the fixture"
+    og = None if og0 < 0 else (og0, og1)
+    return raws, B, H, W, C, og
+
+
+@pytest.mark.parametrize("name", DEC)
+def test_decode(name):
+    g = golden(name)
+    raws, B, H, W, C, og = _decode_inputs(g)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = O.decode_inference(raws, anc, H, W, og)
+    assert_close(preds[..., C + 1:], g["boxes"], rtol=1e-5, atol=1e-5, what="decoded boxes")
+    assert digest(np.ascontiguousarray(preds[..., :C + 1])) == str(g["logits_digest"])  # logits pass through bit-exact
+    tr = O.decode_scale(raws[0], anc[0], H, W, inference=False)
+    assert_close(tr[..., C + 1:], g["train_sm_boxes"], rtol=1e-5, atol=1e-6, what="training decode")
+
+
+@pytest.mark.parametrize("name", ["post_sq64", "post_sq64_lowthr", "post_T128_tracked", "post_T128"])
+def test_post_process(name):
+    g = golden(name)
+    gd = golden(str(g["decode_case"]))
+    raws, B, H, W, C, og = _decode_inputs(gd)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = O.decode_inference(raws, anc, H, W, og)
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    # NMS stage alone, fed the reference's own fp32 boxes: bit-exact keep list
+    N = preds.shape[1]
+    score, cls, xyxy = O.score_xyxy(preds, allow or 0.0)
+    assert_close(xyxy, g["xyxy"], rtol=1e-5, atol=1e-4, what="xyxy")
+    sample = np.repeat(np.arange(B, dtype=np.int64), N)
+    keep_ref = g["nms_keep"]
+    keep = O.batched_nms(g["xyxy"], score, sample, float(g["iou"]))
+    # scores come from our sigmoid; identical ordering is expected unless two scores sit within an ulp
+    assert np.array_equal(np.sort(keep), np.sort(keep_ref))
+    out = O.post_process(preds, float(g["iou"]), float(g["thr"]), allow, tracked)
+    counts = g["per_image_counts"]
+    assert out["pred_boxes"].shape[0] == counts.sum()
+    # per image, score-descending: compare against what the reference handed to its drawing code
+    ref_rows = g["per_image"]
+    got = out["pred_boxes"]
+    ref_img = np.repeat(np.arange(len(counts)), counts)
+    got_img = np.unique(out["sample_idxs"], return_inverse=True)[1] if len(got) else out["sample_idxs"]
+    got, ref_rows = rows_canon(got, got_img), rows_canon(ref_rows, ref_img)
+    assert_close(got, ref_rows, rtol=1e-5, atol=1e-4, what="pred_boxes")
+    assert np.array_equal(got[:, 1], ref_rows[:, 1])  # class ids exact
+
+
+@pytest.mark.parametrize("case", ["rand", "ties", "dense1", "hand_thr05", "hand_thr05m", "hand_thr0"])
+def test_nms(case):
+    g = golden("nms")
+    b, s, i, thr = g[case + "_boxes"], g[case + "_scores"], g[case + "_idxs"], float(g[case + "_thr"])
+    keep = O.batched_nms(b, s, i, thr)
+    assert np.array_equal(keep, canon(g[case + "_keep"], s))
+    assert np.all(np.diff(s[keep]) <= 0)
+
+
+def test_nms_live_torchvision():
+    import torchvision
+    b, s, i = synth.nms_boxes(5000, 7, seed=9)
+    ref = torchvision.ops.boxes._batched_nms_vanilla(b, s, i, 0.45).numpy()
+    assert np.array_equal(O.batched_nms(b, s, i, 0.45), canon(ref, s.numpy()))
+    ref1 = torchvision.ops.nms(b, s, 0.3).numpy()
+    assert np.array_equal(O.nms(b, s, 0.3), ref1)
+
+
+def _assign_cases():
+    g = golden("assign")
+    keys = sorted(k[:-4] for k in g.files if k.endswith("_idx"))
+    return keys
+
+
+@pytest.mark.parametrize("key", _assign_cases())
+def test_assign(key):
+    g = golden("assign")
+    name, fm, sc = key.rsplit("_", 2)
+    ny, nx = (int(v) for v in fm.split("x"))
+    t = {"c1": lambda: synth.targets(2, 20, 80, 0, fixed=False), "b8g100": lambda: synth.targets(8, 100, 80, 0),
+         "adv": lambda: synth.adversarial_targets(2, 80), "empty": lambda: torch.zeros(0, 6)}[name]()
+    assert digest(t) == str(g[name + "_in_digest"])
+    idx, cls, anc, box = O.build_target_by_scale(t, (ny, nx), synth.anchors_tensor(sc), 4.0, 0.5)
+    assert np.array_equal(np.stack(idx, 0), g[key + "_idx"])          # indices: bit- and order-exact
+    assert np.array_equal(cls, g[key + "_cls"])
+    assert np.array_equal(anc, g[key + "_anc"])                       # fp32 outputs are bit-reproducible too
+    assert np.array_equal(box, g[key + "_box"])
+
+
+def test_ciou():
+    g = golden("ciou")
+    c, grad = O.compute_ciou(g["p"], g["t"], with_grad=True)
+    assert_close(c, g["ciou"], rtol=1e-5, atol=1e-6, what="ciou")
+    assert_close(grad * g["w"][:, None], g["grad"], rtol=1e-4, atol=1e-5, what="ciou grad")
+
+
+@pytest.mark.parametrize("name", ["loss_sq64", "loss_collide", "loss_c3_rect", "loss_empty", "loss_c1_640"])
+def test_loss(name):
+    g = golden(name)
+    B, H, W, C, G, fixed, ts, ps = (int(v) for v in g["params"])
+    t = synth.targets(B, G, C, ts, bool(fixed)) if G > 0 else torch.zeros(0, 6)
+    preds = synth.train_preds(B, H, W, C, ps)
+    assert digest(t, *preds) == str(g["in_digest"])
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    loss, metrics, grads, Ms = O.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_grad=True)
+    assert_close(loss, float(g["loss"]), rtol=1e-5, atol=0, what="loss")
+    ref_m = dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"]))
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for sc, gr in zip(synth.SCALES, grads):
+        if "grad_" + sc in g.files:
+            assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
+        else:
+            assert_close(gr[..., 0].astype(np.float64).sum(), float(g["grad_" + sc + "_obj_sum"]), rtol=1e-4, atol=1e-7)
+            assert_close(np.abs(gr.astype(np.float64)).sum(), float(g["grad_" + sc + "_abs_sum"]), rtol=1e-4)
+            ix = g["grad_" + sc + "_rows_idx"]
+            assert_close(gr[ix[:, 0], ix[:, 1], ix[:, 2], ix[:, 3]], g["grad_" + sc + "_rows"], rtol=1e-4, atol=1e-7)
+
+
+def test_ratio_metrics():
+    g = golden("ratio")
+    s = O.ratio_metrics(g["anchors"], g["wh"], 4.0)
+    assert_close(s[0], float(g["score"]), rtol=1e-5)
+    assert_close(np.array(s), g["extras"], rtol=1e-5)
+    assert_close(np.array(O.ratio_metrics(g["anchors"], g["wh"] * 3.0, 2.0)), g["extras_x3_t2"], rtol=1e-5)

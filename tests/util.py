@@ -1,0 +1,48 @@
+"""Shared helpers for the parity tests."""
+import hashlib
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+
+
+def digest(*tensors) -> str:
+    h = hashlib.sha256()
+    for t in tensors:
+        h.update(np.ascontiguousarray(t.detach().cpu().numpy() if hasattr(t, "detach") else t).tobytes())
+    return h.hexdigest()[:16]
+
+
+def canon(keep, scores):
+    """(score desc, index asc) canonical order of a keep list."""
+    keep = np.asarray(keep, dtype=np.int64)
+    s = np.asarray(scores, dtype=np.float32)[keep].astype(np.float64)
+    return keep[np.lexsort((keep, -s))]
+
+
+def assert_close(a, b, rtol=1e-5, atol=1e-6, what=""):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    if a.size == 0:
+        return
+    err = np.abs(a - b)
+    tol = atol + rtol * np.abs(b)
+    bad = ~((err <= tol) | (np.isnan(a) & np.isnan(b)))
+    assert not bad.any(), f"{what}: {bad.sum()} / {a.size} outside rtol={rtol} atol={atol}; max err {np.nanmax(err):.3e}"
+
+
+def rows_canon(rows, img):
+    """Order [K,6] (score, cls, x1,y1,x2,y2) rows by image, score descending, then the remaining columns
+    (the reference's order inside equal-score runs is arbitrary -- SURVEY A.4)."""
+    rows = np.asarray(rows)
+    if rows.shape[0] == 0:
+        return rows
+    r = rows.astype(np.float64)
+    order = np.lexsort((r[:, 5], r[:, 4], r[:, 3], r[:, 2], r[:, 1], -r[:, 0], np.asarray(img)))
+    return rows[order]
