@@ -1,0 +1,173 @@
+/*
+ * boxgeom.h -- C ABI of libboxgeom.so, the B200 (sm_100a) implementation of the
+ * box-geometry hot path of ches-001/vision-conglomerate.
+ *
+ * The reference is pure Python and has no FFI of its own: its "plugin boundary"
+ * is five Python call sites.  Each entry point below names the
+ * reference routine it replaces (paths relative to the reference root); the
+ * Python shim in vision_conglomerate_b200/ binds these with ctypes and re-creates
+ * the reference signatures on top.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the comment says "host";
+ *  - the library never allocates or frees device memory and keeps no state
+ *    between calls: inputs, outputs and the scratch `workspace` are owned by the
+ *    caller (query the size with the matching *_workspace_bytes function);
+ *  - all work is enqueued on `stream` (a cudaStream_t passed as void*); no call
+ *    synchronises with the host.  Data-dependent result sizes are written to
+ *    device memory (`out_counts`), to be read by the caller after its own sync;
+ *  - return value: BG_OK or an error code (see bg_strerror); never throws;
+ *  - fp32 arithmetic follows the reference's CPU operation order without FMA
+ *    contraction; integer outputs are bit-exact with the reference.
+ */
+#ifndef BOXGEOM_H_
+#define BOXGEOM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BG_OK 0
+#define BG_ERR_INVALID 1   /* bad argument (null pointer, negative size, unsupported shape) */
+#define BG_ERR_WORKSPACE 2 /* workspace too small for this call */
+#define BG_ERR_LAUNCH 3    /* CUDA reported an error while enqueueing */
+
+/* bits of the device-side status word (out_counts[1]) */
+#define BG_STATUS_GROUP_RANGE 1 /* batched_nms: max(idxs)-min(idxs) exceeds max_groups */
+#define BG_STATUS_MASK_SPACE 2  /* suppression-mask scratch exhausted: retry with a larger workspace */
+
+#define BG_MAX_ANCHORS 8
+#define BG_MAX_TRACKED 64
+
+const char *bg_strerror(int code);
+int bg_version(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+uint64_t bg_launch_count(void);
+/* sizeof(bg_detect_params) / sizeof(bg_loss_params) as compiled, so a binding can verify its struct layout */
+size_t bg_sizeof_detect_params(void);
+size_t bg_sizeof_loss_params(void);
+
+/* ------------------------------------------------------------------ B4
+ * torchvision.ops.batched_nms(boxes, scores, idxs, iou_threshold), the call at
+ * inference_det.py:77-82 / inference_seg.py:85-90.  Greedy NMS independently per
+ * distinct idxs value (the `_batched_nms_vanilla` semantics every BASELINE
+ * configuration takes), IoU test bit-identical to torchvision's CPU kernel.
+ *   boxes [n,4] f32 xyxy, scores [n] f32, idxs [n] i64.
+ *   out_keep [n] i64: kept indices, score-descending, index-ascending inside
+ *                     equal scores (torchvision's order inside ties is arbitrary);
+ *   out_counts [2] i32: [0] = number kept, [1] = status bits.
+ *   max_groups bounds max(idxs)-min(idxs)+1 (sizes the per-group tables).
+ */
+size_t bg_batched_nms_workspace_bytes(int64_t n, int64_t max_groups, size_t mask_bytes);
+int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs, int64_t n,
+                   double iou_threshold, int64_t max_groups, int64_t *out_keep, int32_t *out_counts,
+                   void *workspace, size_t workspace_bytes, size_t mask_bytes, void *stream);
+
+/* ------------------------------------------------------------------ B5
+ * Fused replacement of DetectionNet.forward(inference=True) from the three head
+ * outputs on (modules/detection.py:69-91,98-190) followed by
+ * inference_det.post_process_preds lines 57-97 and the tracked-class filter at
+ * :107-109: decode, score, strict score threshold, per-image NMS, row assembly.
+ */
+typedef struct {
+    int32_t B, C, na;           /* batch, classes, anchors per cell */
+    int32_t H, W;               /* network input size (x.shape[2:]) */
+    int32_t og_H, og_W;         /* original frame size; <= 0 means og_size=None */
+    int32_t ny[3], nx[3];       /* feature-map shape per scale (sm, md, lg) */
+    float anchors[3][BG_MAX_ANCHORS][2]; /* normalised (w,h) per scale, read from the model at call time */
+    float box_allowance;        /* added to w and h before xyxy (inference_det.py:73-74); 0 = None */
+    float score_threshold;      /* rows with score > threshold survive (strict, :84) */
+    double iou_threshold;
+    int32_t n_tracked;          /* 0 = no class filter */
+    int32_t tracked[BG_MAX_TRACKED];
+    int32_t order;              /* 0: image-major, score-descending inside an image; 1: globally score-descending (reference row order) */
+    int32_t variant;            /* decode kernel: 0 auto, 1 plain vector loads, 2 TMA bulk pipeline */
+} bg_detect_params;
+
+size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);
+/*   raw_* [B,ny,nx,na,5+C] f32 contiguous, channels [obj, cls*C, tx,ty,tw,th] (common.py:912-931)
+ *   out_boxes [B*N,6] f32 = (score, class, x1,y1,x2,y2)           (inference_det.py:93-97)
+ *   out_img   [B*N] i64   = image index of each row               (sample_idxs, :87)
+ *   out_keep  [B*N] i64   = flat candidate index b*N + i of each row (keep_idxs after the threshold)
+ *   out_counts [2+2*B] i32: [0] rows written, [1] status bits, [2+b] rows of image b,
+ *                           [2+B+b] candidates of image b that passed the score threshold
+ */
+int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *p /*host*/,
+              float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
+              size_t workspace_bytes, size_t mask_bytes, void *stream);
+
+/* Profiling hook for bench.py: when both are non-NULL, the next bg_detect call records `start`/`stop`
+ * (cudaEvent_t) on its stream immediately around the decode+filter kernel, then clears the hook. */
+void bg_profile_events(void *start, void *stop);
+
+/* DetectionNet._get_scale_pred (modules/detection.py:98-173) for one scale, optionally followed by
+ * _bbox_to_size (:175-190): writes the decoded tensor, same shape as raw.  inference = 0 gives the
+ * training-mode decode (xy = 2s-0.5, wh = (2s)^2 only). */
+int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
+                    const float *anchors /*host [na,2]*/, int32_t H, int32_t W, int32_t inference, int32_t og_H,
+                    int32_t og_W, void *stream);
+
+/* ------------------------------------------------------------------ B1
+ * DetectionDataset.build_target_by_scale (dataset/detection_dataset.py:90-246), detection branch.
+ *   targets [nt,6] f32 (img, cls, x, y, w, h); anchors host [na,2] normalised.
+ *   out_idx4 [4,cap] i64 rows = batch_idx, grid_j, grid_i, anchor_idx; out_cls [cap] i64;
+ *   out_anchor [cap,2] f32 (grid units); out_box [cap,4] f32; cap = 5*na*nt.
+ *   out_count [1] i32 = M.  Output order: (offset k, anchor a, target t) lexicographic.
+ */
+size_t bg_assign_workspace_bytes(int64_t nt, int32_t na);
+int bg_assign_targets(const float *targets, int64_t nt, int32_t ny, int32_t nx, const float *anchors /*host*/,
+                      int32_t na, float anchor_t, float edge_t, int64_t *out_idx4, int64_t *out_cls,
+                      float *out_anchor, float *out_box, int64_t cap, int32_t *out_count, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ B2
+ * DetectionLoss.compute_ciou (modules/detection_loss.py:229-264), element-wise [M,4] x [M,4] -> [M].
+ * bg_ciou_bwd: grad_p[m,:] = grad_out[m] * d ciou / d preds_xywh (alpha held constant, :261-262). */
+int bg_ciou_fwd(const float *preds_xywh, const float *targets_xywh, int64_t M, float eps, float *out, void *stream);
+int bg_ciou_bwd(const float *preds_xywh, const float *targets_xywh, const float *grad_out, int64_t M, float eps,
+                float *grad_p, void *stream);
+
+/* ------------------------------------------------------------------ B3
+ * DetectionLoss.forward (modules/detection_loss.py:84-226) for the default configuration
+ * (BCEWithLogits, no focal loss, no keypoints): target assignment, matched-row gather, CIoU,
+ * "last match wins" objectness targets, dense objectness BCE, class BCE and the per-class
+ * confusion counters behind the sklearn metrics, for all three scales in one call.
+ */
+typedef struct {
+    int32_t B, C, na;
+    int32_t ny[3], nx[3];
+    float anchors[3][BG_MAX_ANCHORS][2];
+    float anchor_t, edge_t, label_smoothing;
+    float box_w, conf_w, class_w;
+    float scale_w[3];
+    int64_t nt;
+} bg_loss_params;
+
+size_t bg_loss_workspace_bytes(const bg_loss_params *p /*host*/);
+/*   preds_* [B,ny,nx,na,5+C] f32 (training-mode decoded); targets [nt,6] f32.
+ *   out_scalars [3,8] f64 per scale: lbox, lconf, lcls (NaN->0 applied), mean_ciou, avg_pos_conf,
+ *                 avg_neg_conf, M, n_neg;   out_hist [3,3,C] i64: tp, n_true, n_pred per class.
+ *   The workspace keeps what bg_loss_bwd needs (matches, CIoU, objectness targets).
+ */
+int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const float *targets,
+                const bg_loss_params *p /*host*/, double *out_scalars, int64_t *out_hist, void *workspace,
+                size_t workspace_bytes, void *stream);
+/*   grad_* [same shape as preds_*]: d(grad_out * loss)/d preds, loss as combined at :107-110. */
+int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const bg_loss_params *p /*host*/,
+                float grad_out, float *grad_sm, float *grad_md, float *grad_lg, void *workspace,
+                size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ a13
+ * utils/make_anchors.py:14-39 ratio_metrics / ratio_metrics_w_extras.
+ *   wh [n,2] f32, anchors host [k,2]; out3 [3] f64 = sum(v*m), sum(m), n  (score = out[0]/n, bpr = out[1]/n, aat = out[1]).
+ */
+int bg_ratio_metrics(const float *wh, int64_t n, const float *anchors /*host*/, int32_t k, float threshold,
+                     double *out3, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOXGEOM_H_ */

@@ -1,0 +1,279 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the Python shim over the C ABI, against the
+CPU oracle on the same seeded inputs and against the committed golden fixtures (reference outputs).
+
+Bars: integer / index outputs bit-exact; fp32 outputs rtol 1e-5 (atol stated per test)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from vision_conglomerate_b200 import synth
+from tests.util import assert_close, canon, digest, golden, rows_canon
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vision_conglomerate_b200 import ops as _ops
+    return _ops
+
+
+def dev(t):
+    return t.cuda() if isinstance(t, torch.Tensor) else torch.as_tensor(t).cuda()
+
+
+# ------------------------------------------------------------------------------------------ NMS (B4)
+@pytest.mark.parametrize("case", ["rand", "ties", "dense1", "hand_thr05", "hand_thr05m", "hand_thr0"])
+def test_nms_golden(ops, case):
+    """Identical fp32 inputs -> keep list bit-exact with torchvision-CPU (the reference's NMS)."""
+    g = golden("nms")
+    b, s, i, thr = g[case + "_boxes"], g[case + "_scores"], g[case + "_idxs"], float(g[case + "_thr"])
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), thr).cpu().numpy()
+    assert np.array_equal(keep, canon(g[case + "_keep"], s))
+
+
+@pytest.mark.parametrize("n,groups,thr,ties", [(1, 1, 0.5, False), (2, 2, 0.5, False), (63, 1, 0.3, False),
+                                               (64, 1, 0.3, True), (65, 3, 0.7, False), (4097, 2, 0.5, True),
+                                               (20000, 8, 0.45, False), (30000, 1, 0.6, False),
+                                               (50000, 700, 0.5, True)])
+def test_nms_oracle(ops, n, groups, thr, ties):
+    b, s, i = synth.nms_boxes(n, groups, seed=n, ties=ties)
+    i = i * 3 - 7  # arbitrary (negative, gapped) group ids
+    ref = O.batched_nms(b, s, i, thr)
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), thr).cpu().numpy()
+    assert np.array_equal(keep, ref)
+
+
+def test_nms_empty_and_props(ops):
+    e = ops.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), 0.5)
+    assert e.numel() == 0 and e.dtype == torch.int64
+    b, s, i = synth.nms_boxes(8000, 4, seed=77)
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), 0.5)
+    # idempotence: NMS of the survivors keeps every survivor, in the same order
+    again = ops.batched_nms(dev(b)[keep], dev(s)[keep], dev(i)[keep], 0.5)
+    assert torch.equal(again, torch.arange(keep.numel(), device="cuda"))
+    assert bool((s.cuda()[keep][1:] <= s.cuda()[keep][:-1]).all())
+    with pytest.raises(RuntimeError):
+        ops.batched_nms(b, s, i, 0.5)  # CPU tensors are refused: no fallback
+
+
+def test_nms_live_torchvision_cpu(ops):
+    """torchvision is installed on the box: cross-check against its CPU kernel directly."""
+    import torchvision
+    b, s, i = synth.nms_boxes(12000, 5, seed=123)
+    ref = torchvision.ops.boxes._batched_nms_vanilla(b, s, i, 0.55).numpy()
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), 0.55).cpu().numpy()
+    assert np.array_equal(keep, canon(ref, s.numpy()))
+
+
+# ------------------------------------------------------------------------- decode + NMS (B5, a1-a8)
+def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order="image", max_mismatch=0):
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = O.decode_inference(raws, anc, H, W, og)
+    ref = O.post_process(preds, iou, thr, allow, tracked)
+    det = ops.detect([dev(r) for r in raws], anc, (H, W), C, og_size=og, iou_threshold=iou, score_threshold=thr,
+                     box_allowance=allow, tracked_classes=tracked, order=order, variant=variant)
+    keep = det.keep_idxs.cpu().numpy()
+    rows = det.pred_boxes.cpu().numpy()
+    img = det.sample_idxs.cpu().numpy()
+    N = preds.shape[1]
+    assert np.array_equal(img, keep // N)
+    assert int(det.counts.sum()) == keep.shape[0]
+    miss = np.setxor1d(keep, ref["keep"])
+    assert miss.size <= max_mismatch, f"{miss.size} keep mismatches (allowed {max_mismatch})"
+    if order == "global":
+        assert np.all(np.diff(rows[:, 0]) <= 0)
+    else:
+        assert np.all(np.diff(img) >= 0)
+        for b in np.unique(img):
+            assert np.all(np.diff(rows[img == b, 0]) <= 0)
+    if miss.size == 0:
+        a = rows_canon(rows, img)
+        r = rows_canon(ref["pred_boxes"], ref["sample_idxs"])
+        assert_close(a, r, rtol=1e-5, atol=2e-5 * max(H, W), what="pred_boxes")
+        assert np.array_equal(a[:, 1], r[:, 1])
+    return det, ref
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", ["post_sq64", "post_sq64_lowthr", "post_T128_tracked", "post_T128"])
+def test_detect_golden(ops, name, variant):
+    """Fused decode+NMS against what the unmodified reference handed to its drawing code."""
+    g = golden(name)
+    gd = golden(str(g["decode_case"]))
+    B, H, W, C, seed, og0, og1 = (int(v) for v in gd["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(gd["dist"]), seed)
+    og = None if og0 < 0 else (og0, og1)
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    det, _ = _detect_vs_oracle(ops, raws, H, W, C, og, float(g["iou"]), float(g["thr"]), allow, tracked, variant)
+    counts = g["per_image_counts"]
+    ref_rows = rows_canon(g["per_image"], np.repeat(np.arange(len(counts)), counts))
+    got_img = np.unique(det.sample_idxs.cpu().numpy(), return_inverse=True)[1]
+    got = rows_canon(det.pred_boxes.cpu().numpy(), got_img)
+    assert_close(got, ref_rows, rtol=1e-5, atol=2e-5 * max(H, W), what="rows vs reference")
+    assert np.array_equal(got[:, 1], ref_rows[:, 1])
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,H,W,C,dist,og,iou,thr,allow,tracked,order", [
+    (2, 96, 64, 3, "N", (120, 100), 0.5, 0.2, 4, None, "image"),        # non-square, rescale, even row length (D=8)
+    (1, 96, 64, 3, "N", (96, 100), 0.5, 0.2, None, None, "global"),     # `and` guard: no rescale
+    (4, 320, 320, 80, "T", None, 0.65, 0.001, 4, None, "image"),
+    (3, 320, 320, 80, "R", None, 0.65, 0.001, 4, None, "global"),       # every candidate survives (K = 6300)
+    (5, 160, 160, 7, "N", None, 0.35, 0.3, 4, (1, 4), "image"),         # D = 12, ragged tiles, class filter
+    (2, 640, 640, 80, "TP", (720, 1280), 0.35, 0.3, 4, (1, 4, 7, 16, 17), "image"),  # config 5 shape
+])
+def test_detect_oracle(ops, variant, B, H, W, C, dist, og, iou, thr, allow, tracked, order):
+    raws = synth.raw_head_outputs(B, H, W, C, dist, seed=7)
+    K = synth.candidates_per_image(H, W) * B
+    _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order, max_mismatch=max(0, K // 5000))
+
+
+def test_detect_config2_full_size(ops):
+    """BASELINE config 2 (B=64, 640^2, conf 0.001, IoU 0.65, dist T): oracle parity on 4 images, and
+    size-independent properties on the whole batch."""
+    B, H, W, C = 64, 640, 640, 80
+    raws = synth.raw_head_outputs(B, H, W, C, "T", seed=7)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    graws = [dev(r) for r in raws]
+    det = ops.detect(graws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4)
+    N = synth.candidates_per_image(H, W)
+    keep = det.keep_idxs.cpu().numpy()
+    sub = [0, 1, 31, 63]
+    preds = O.decode_inference([r[sub] for r in raws], anc, H, W, None)
+    ref = O.post_process(preds, 0.65, 0.001, 4, None)
+    for j, b in enumerate(sub):
+        got = np.sort(keep[(keep // N) == b] - b * N)
+        exp = np.sort(ref["keep"][(ref["keep"] // N) == j] - j * N)
+        assert np.setxor1d(got, exp).size <= 1, f"image {b}"
+    # both decode variants and both row orders agree exactly
+    det1 = ops.detect(graws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, variant=1,
+                      order="global")
+    assert np.array_equal(np.sort(det1.keep_idxs.cpu().numpy()), np.sort(keep))
+    assert bool((det1.pred_boxes[1:, 0] <= det1.pred_boxes[:-1, 0]).all())
+    # idempotence: batched NMS over the kept boxes, grouped by image, keeps all of them
+    again = ops.batched_nms(det.pred_boxes[:, 2:6].contiguous(), det.pred_boxes[:, 0].contiguous(), det.sample_idxs, 0.65)
+    assert again.numel() == keep.shape[0]
+    assert int(det.counts.sum()) == keep.shape[0] and int(det.candidates.min()) > 0
+
+
+@pytest.mark.parametrize("name", ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"])
+def test_decode_scale_golden(ops, name):
+    g = golden(name)
+    B, H, W, C, seed, og0, og1 = (int(v) for v in g["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(g["dist"]), seed)
+    og = None if og0 < 0 else (og0, og1)
+    outs = [ops.decode_scale(dev(r), synth.anchors_tensor(s), (H, W), True, og).cpu().reshape(B, -1, C + 5)
+            for r, s in zip(raws, synth.SCALES)]
+    preds = torch.cat(outs, 1).numpy()
+    assert_close(preds[..., C + 1:], g["boxes"], rtol=1e-5, atol=2e-5 * max(H, W), what="decoded boxes")
+    assert digest(np.ascontiguousarray(preds[..., :C + 1])) == str(g["logits_digest"])
+    tr = ops.decode_scale(dev(raws[0]), synth.anchors_tensor("sm"), (H, W), False).cpu().numpy()
+    assert_close(tr[..., C + 1:], g["train_sm_boxes"], rtol=1e-5, atol=1e-6, what="training decode")
+
+
+# -------------------------------------------------------------------------- target assignment (B1)
+def _assign_check(ops, t, ny, nx, sc):
+    anc = synth.anchors_tensor(sc)
+    ref = O.build_target_by_scale(t, (ny, nx), anc, 4.0, 0.5)
+    idx, cls, a, box, m, k = ops.build_target_by_scale(dev(t), (ny, nx), anc.cuda(), 4.0, 0.5)
+    assert m is None and k is None
+    assert all(x.dtype == torch.int64 for x in idx) and cls.dtype == torch.int64
+    assert np.array_equal(torch.stack(idx, 0).cpu().numpy(), np.stack(ref[0], 0))
+    assert np.array_equal(cls.cpu().numpy(), ref[1])
+    assert np.array_equal(a.cpu().numpy(), ref[2])
+    assert np.array_equal(box.cpu().numpy(), ref[3])
+    return cls.numel()
+
+
+@pytest.mark.parametrize("name", ["c1", "b8g100", "adv", "empty"])
+def test_assign_golden(ops, name):
+    g = golden("assign")
+    t = {"c1": lambda: synth.targets(2, 20, 80, 0, fixed=False), "b8g100": lambda: synth.targets(8, 100, 80, 0),
+         "adv": lambda: synth.adversarial_targets(2, 80), "empty": lambda: torch.zeros(0, 6)}[name]()
+    for key in sorted(k[:-4] for k in g.files if k.endswith("_idx") and k.startswith(name + "_")):
+        _, fm, sc = key.rsplit("_", 2)
+        ny, nx = (int(v) for v in fm.split("x"))
+        idx, cls, a, box, _, _ = ops.build_target_by_scale(dev(t), (ny, nx), synth.anchors_tensor(sc), 4.0, 0.5)
+        got = torch.stack(idx, 0).cpu().numpy() if cls.numel() else np.zeros((4, 0), np.int64)
+        assert np.array_equal(got, g[key + "_idx"]), key
+        assert np.array_equal(cls.cpu().numpy(), g[key + "_cls"])
+        assert np.array_equal(a.cpu().numpy().reshape(-1, 2), g[key + "_anc"])
+        assert np.array_equal(box.cpu().numpy().reshape(-1, 4), g[key + "_box"])
+
+
+def test_assign_config3_and_4(ops):
+    t3 = synth.targets(256, 100, 80, 0)          # config 3: nt = 25 600
+    total = sum(_assign_check(ops, t3, s, s, sc) for s, sc in zip((80, 40, 20), synth.SCALES))
+    assert total > 400000
+    t4 = synth.targets(32, 300, 80, 0)           # config 4: 1280^2, 300 gt / image
+    for s, sc in zip((160, 80, 40), synth.SCALES):
+        _assign_check(ops, t4, s, s, sc)
+
+
+# -------------------------------------------------------------------------------------- CIoU (B2)
+def test_ciou(ops):
+    g = golden("ciou")
+    p = dev(g["p"]).requires_grad_(True)
+    c = ops.compute_ciou(p, dev(g["t"]))
+    (c * dev(g["w"])).sum().backward()
+    assert_close(c.detach().cpu().numpy(), g["ciou"], rtol=1e-5, atol=1e-6, what="ciou vs reference")
+    assert_close(p.grad.cpu().numpy(), g["grad"], rtol=1e-4, atol=1e-5, what="ciou grad vs reference autograd")
+    oc, og = O.compute_ciou(g["p"], g["t"], with_grad=True)
+    assert_close(c.detach().cpu().numpy(), oc, rtol=1e-5, atol=1e-6, what="ciou vs oracle")
+
+
+# -------------------------------------------------------------------------------------- loss (B3)
+def _loss_case(ops, B, H, W, C, t, preds, rtol_grad=1e-4):
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    gp = [dev(p).requires_grad_(True) for p in preds]
+    loss, metrics = ops.detection_loss(gp, dev(t) if t.numel() else torch.zeros(0, 6).cuda(), anc, synth.LOSS_CONFIG)
+    loss.backward()
+    return loss, metrics, [p.grad.cpu().numpy() for p in gp]
+
+
+@pytest.mark.parametrize("name", ["loss_sq64", "loss_collide", "loss_c3_rect", "loss_empty", "loss_c1_640"])
+def test_loss_golden(ops, name):
+    g = golden(name)
+    B, H, W, C, G, fixed, ts, ps = (int(v) for v in g["params"])
+    t = synth.targets(B, G, C, ts, bool(fixed)) if G > 0 else torch.zeros(0, 6)
+    preds = synth.train_preds(B, H, W, C, ps)
+    loss, metrics, grads = _loss_case(ops, B, H, W, C, t, preds)
+    assert_close(float(loss), float(g["loss"]), rtol=1e-5, atol=0, what="loss vs reference")
+    ref_m = dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"]))
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for sc, gr in zip(synth.SCALES, grads):
+        if "grad_" + sc in g.files:
+            assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
+        else:
+            assert_close(gr[..., 0].astype(np.float64).sum(), float(g["grad_" + sc + "_obj_sum"]), rtol=1e-4, atol=1e-7)
+            assert_close(np.abs(gr.astype(np.float64)).sum(), float(g["grad_" + sc + "_abs_sum"]), rtol=1e-4)
+            ix = g["grad_" + sc + "_rows_idx"]
+            assert_close(gr[ix[:, 0], ix[:, 1], ix[:, 2], ix[:, 3]], g["grad_" + sc + "_rows"], rtol=1e-4, atol=1e-7)
+
+
+def test_loss_config3_shard(ops):
+    """Config 3 per-GPU shard at P=8 (B=32, 100 gt/img) against the oracle, incl. the dense gradient."""
+    B, H, W, C = 32, 640, 640, 80
+    t = synth.targets(B, 100, C, 0)
+    preds = synth.train_preds(B, H, W, C, 1)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    ref_loss, ref_m, ref_g, Ms = O.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_grad=True)
+    loss, metrics, grads = _loss_case(ops, B, H, W, C, t, preds)
+    assert_close(float(loss), ref_loss, rtol=1e-5, what="loss")
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for a, b in zip(grads, ref_g):
+        assert_close(a, b, rtol=1e-4, atol=1e-9, what="grad")
+
+
+# ------------------------------------------------------------------------------ anchor metrics (a13)
+def test_ratio_metrics(ops):
+    g = golden("ratio")
+    s = ops.ratio_metrics_w_extras(g["anchors"], dev(g["wh"]), 4.0)
+    assert_close(np.array(s), g["extras"], rtol=1e-5)
+    assert_close(ops.ratio_metrics(g["anchors"], dev(g["wh"]), 4.0), float(g["score"]), rtol=1e-5)
+    assert_close(np.array(ops.ratio_metrics_w_extras(g["anchors"], dev(g["wh"]) * 3.0, 2.0)), g["extras_x3_t2"], rtol=1e-5)

@@ -1,0 +1,78 @@
+// Shared device/host helpers for libboxgeom (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/boxgeom.h"
+
+namespace bg {
+
+extern unsigned long long g_launches;  // host-side count of kernels enqueued by this library
+
+#define BG_LAUNCH_CHECK()                                   \
+    do {                                                    \
+        ++::bg::g_launches;                                 \
+        if (cudaPeekAtLastError() != cudaSuccess) {         \
+            (void)cudaGetLastError();                       \
+            return BG_ERR_LAUNCH;                           \
+        }                                                   \
+    } while (0)
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline u32 next_pow2(u32 x)
+{
+    if (x <= 1) return 1;
+    --x;
+    x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16;
+    return x + 1;
+}
+
+// fp32 -> u32 whose unsigned order equals the float order (-0 canonicalised to +0).
+__device__ __forceinline__ u32 orderable(float f)
+{
+    if (f == 0.0f) f = 0.0f;
+    u32 u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(u32 u)
+{
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+// sort key: ascending u64 order == (score descending, id ascending)
+__device__ __forceinline__ u64 make_key(float score, u32 id) { return ((u64)(~orderable(score)) << 32) | id; }
+__device__ __forceinline__ float key_score(u64 k) { return from_orderable(~(u32)(k >> 32)); }
+__device__ __forceinline__ u32 key_id(u64 k) { return (u32)k; }
+
+// sigmoid with IEEE divide and the accurate expf (parity tolerance is rtol 1e-5 against ATen's CPU sigmoid)
+__device__ __forceinline__ float sigmoid_acc(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+__device__ __forceinline__ u32 lanemask_lt()
+{
+    u32 m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Threshold constants for the exact IoU test (see nms.cu: iou_suppresses).
+struct IouThr {
+    float tdn;  // largest float <= the double threshold: (double)q > thr  <=>  q > tdn for every float q
+    float lo, hi;  // guard band around tdn for the division-free fast path
+    int fast_ok;   // guard band valid (tdn is a positive normal number)
+    int zero_suppresses;  // 0.0 > thr: non-overlapping pairs suppress too (negative thresholds)
+};
+IouThr make_iou_thr(double thr);
+
+}  // namespace bg

@@ -1,0 +1,42 @@
+// Segmented greedy-NMS engine shared by bg_batched_nms (generic groups) and bg_detect (one segment
+// per image).  See nms.cu for the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace bg {
+
+struct SegHdr {  // lives at the start of the workspace; (re)initialised by the first kernel of every call
+    int S;       // number of segments
+    int status;  // BG_STATUS_* bits
+    unsigned item_ctr;     // tile scheduler of the mask kernel
+    unsigned reduce_done;  // "last CTA" ticket of the reduce kernel
+    long long gmin, gmax;  // batched_nms: range of idxs
+    long long total_out;
+    long long pad[3];
+};
+
+struct SegNms {
+    SegHdr *hdr;
+    int *seg_count;         // [S_max]   candidates per segment
+    long long *seg_off;     // [S_max+1] element offset of the segment in keys / sorted_* / emit_* (room for next_pow2(count))
+    int *tile_prefix;       // [S_max+1] exclusive prefix of ceil(count/64); also the word offset into keepbits
+    long long *mask_off;    // [S_max+1] exclusive prefix of count*ceil(count/64) (u64 words)
+    int *emit_count;        // [S_max]   rows emitted per segment (after NMS and the class filter)
+    long long *out_prefix;  // [S_max+1]
+    u64 *keys;              // (score desc, id asc) keys, sorted in place per segment
+    float4 *sorted_box;     // boxes gathered into sorted order
+    float *sorted_area;     // (x2-x1)*(y2-y1), pre-rounded like torchvision's CPU kernel
+    u64 *keepbits;          // kept bitmap in sorted order, word offset tile_prefix[s]
+    u64 *mask;              // suppression bit matrix, per segment column-tile-major: word(ct,row) at mask_off[s] + ct*K + row
+    long long mask_words;   // capacity of mask
+    u32 *emit_pos;          // sorted position of each emitted row (compact per segment, at seg_off)
+    u64 *emit_key;          // its key
+    const float4 *boxes;    // source boxes; box of (segment s, id) is boxes[s*box_seg_stride + id]
+    long long box_seg_stride;
+    const int *cls;         // optional class of (s, id) at the same index, for the tracked-class filter
+    int n_tracked;
+    int tracked[BG_MAX_TRACKED];
+    IouThr thr;
+};
+
+}  // namespace bg

@@ -1,0 +1,445 @@
+// Training side: YOLOv5-style target assignment (ordered compaction), element-wise CIoU with its
+// analytic gradient, the fused detection loss (forward + backward) and the anchor-fit metrics.
+//
+// Reference semantics: dataset/detection_dataset.py:90-246,
+// modules/detection_loss.py:125-264, utils/make_anchors.py:14-39.
+#pragma once
+#include "common.cuh"
+
+namespace bg {
+
+// ------------------------------------------------------------------------------------------------
+// target assignment
+// ------------------------------------------------------------------------------------------------
+struct AssignK {
+    const float *targets;  // [nt,6]
+    long long nt;
+    int ny, nx, na;
+    float fnx, fny;
+    float aw[BG_MAX_ANCHORS], ah[BG_MAX_ANCHORS];  // anchors in grid units: anchor * (nx, ny)   (:183)
+    float anchor_t, edge_t;
+    long long ncand;       // 5*na*nt
+    int *block_counts;     // [nblocks]
+    // outputs (any may be null)
+    long long *idx4;       // [4,cap]
+    long long *cls64;      // [cap]
+    float *anchor;         // [cap,2]
+    float *box;            // [cap,4]
+    long long cap;
+    int *count;            // [1] M
+    // packed outputs for the fused loss (any may be null)
+    int *cell;             // [cap] ((b*ny+gj)*nx+gi)*na+a
+    int *cls32;            // [cap]
+};
+
+constexpr int ASSIGN_THREADS = 1024;
+
+struct AssignOut { int b, gj, gi, a, cls; float aw, ah, bx, by, bw, bh; };
+
+__device__ __forceinline__ float torch_remainder1(float x)
+{
+    float r = fmodf(x, 1.0f);
+    if (r != 0.0f && r < 0.0f) r += 1.0f;
+    return r;
+}
+
+// candidate c = (k*na + a)*nt + t; returns whether it is emitted and, if so, its outputs
+__device__ __forceinline__ bool assign_eval(const AssignK &k, long long c, AssignOut &o)
+{
+    const long long t = c % k.nt;
+    const int ka = (int)(c / k.nt);
+    const int a = ka % k.na, kk = ka / k.na;
+    const float *tg = k.targets + 6 * t;
+    const float gx = __fmul_rn(tg[2], k.fnx), gy = __fmul_rn(tg[3], k.fny);
+    const float gw = __fmul_rn(tg[4], k.fnx), gh = __fmul_rn(tg[5], k.fny);
+    const float rw = __fdiv_rn(gw, k.aw[a]), rh = __fdiv_rn(gh, k.ah[a]);
+    const float irw = __fdiv_rn(1.0f, rw), irh = __fdiv_rn(1.0f, rh);
+    const float m = fmaxf(fmaxf(rw, irw), fmaxf(rh, irh));
+    if (!(m < k.anchor_t)) return false;
+    float ox = 0.f, oy = 0.f;
+    bool sel = true;
+    if (kk == 1) { sel = (torch_remainder1(gx) < k.edge_t) && (gx > 1.0f); ox = k.edge_t; }
+    else if (kk == 2) { sel = (torch_remainder1(gy) < k.edge_t) && (gy > 1.0f); oy = k.edge_t; }
+    else if (kk == 3) { const float ix = __fsub_rn(k.fnx, gx); sel = (torch_remainder1(ix) < k.edge_t) && (ix > 1.0f); ox = -k.edge_t; }
+    else if (kk == 4) { const float iy = __fsub_rn(k.fny, gy); sel = (torch_remainder1(iy) < k.edge_t) && (iy > 1.0f); oy = -k.edge_t; }
+    if (!sel) return false;
+    long long gi = (long long)__fsub_rn(gx, ox), gj = (long long)__fsub_rn(gy, oy);  // .long() truncates (:231)
+    gi = gi < 0 ? 0 : (gi > k.nx - 1 ? k.nx - 1 : gi);
+    gj = gj < 0 ? 0 : (gj > k.ny - 1 ? k.ny - 1 : gj);
+    o.b = (int)(long long)tg[0];
+    o.cls = (int)(long long)tg[1];
+    o.gi = (int)gi; o.gj = (int)gj; o.a = a;
+    o.aw = k.aw[a]; o.ah = k.ah[a];
+    o.bx = __fsub_rn(gx, (float)gi); o.by = __fsub_rn(gy, (float)gj);  // clamped cell (aliasing at :232-237)
+    o.bw = gw; o.bh = gh;
+    return true;
+}
+
+__device__ __forceinline__ int block_count_flags(bool f, int *s_w /*[32]*/)
+{
+    const u32 b = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
+    __syncthreads();
+    int tot = 0;
+    if (threadIdx.x < 32) {
+        int v = (threadIdx.x < (int)(blockDim.x >> 5)) ? s_w[threadIdx.x] : 0;
+        tot = warp_sum(v);
+    }
+    return tot;  // valid in warp 0
+}
+
+__global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(AssignK k)
+{
+    __shared__ int s_w[32];
+    const long long c = (long long)blockIdx.x * ASSIGN_THREADS + threadIdx.x;
+    AssignOut o;
+    const bool f = (c < k.ncand) && assign_eval(k, c, o);
+    const int tot = block_count_flags(f, s_w);
+    if (threadIdx.x == 0) k.block_counts[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(AssignK k)
+{
+    __shared__ int s_w[32];
+    __shared__ long long s_base;
+    // offset of this block = sum of the counts of all earlier blocks (fixed order -> deterministic)
+    long long part = 0;
+    for (int j = threadIdx.x; j < (int)blockIdx.x; j += ASSIGN_THREADS) part += k.block_counts[j];
+    part = warp_sum(part);
+    __shared__ long long s_p[32];
+    if ((threadIdx.x & 31) == 0) s_p[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        long long v = s_p[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) s_base = v;
+    }
+    __syncthreads();
+    const long long c = (long long)blockIdx.x * ASSIGN_THREADS + threadIdx.x;
+    AssignOut o;
+    const bool f = (c < k.ncand) && assign_eval(k, c, o);
+    const u32 bal = __ballot_sync(0xffffffffu, f);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int q = 0; q < ASSIGN_THREADS / 32; ++q) {
+        const int v = s_w[q];
+        if (q < wid) woff += v;
+        tot += v;
+    }
+    if (f) {
+        const long long m = s_base + woff + __popc(bal & lanemask_lt());
+        if (m < k.cap) {
+            if (k.idx4) {
+                k.idx4[0 * k.cap + m] = o.b; k.idx4[1 * k.cap + m] = o.gj;
+                k.idx4[2 * k.cap + m] = o.gi; k.idx4[3 * k.cap + m] = o.a;
+            }
+            if (k.cls64) k.cls64[m] = o.cls;
+            if (k.anchor) { k.anchor[2 * m] = o.aw; k.anchor[2 * m + 1] = o.ah; }
+            if (k.box) { float4 *bp = reinterpret_cast<float4 *>(k.box) + m; *bp = make_float4(o.bx, o.by, o.bw, o.bh); }
+            if (k.cell) k.cell[m] = ((o.b * k.ny + o.gj) * k.nx + o.gi) * k.na + o.a;
+            if (k.cls32) k.cls32[m] = o.cls;
+        }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *k.count = (int)(s_base + tot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CIoU (modules/detection_loss.py:229-264): fp32 forward in the reference's operation order; the
+// gradient w.r.t. the prediction (alpha constant) is evaluated in double from the same quantities.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], float e, double *g /*4 or null*/)
+{
+    const float pw = p[2], ph = p[3], tw = t[2], th = t[3];
+    const float px1 = __fsub_rn(p[0], __fdiv_rn(pw, 2.0f)), py1 = __fsub_rn(p[1], __fdiv_rn(ph, 2.0f));
+    const float px2 = __fadd_rn(px1, pw), py2 = __fadd_rn(py1, ph);
+    const float tx1 = __fsub_rn(t[0], __fdiv_rn(tw, 2.0f)), ty1 = __fsub_rn(t[1], __fdiv_rn(th, 2.0f));
+    const float tx2 = __fadd_rn(tx1, tw), ty2 = __fadd_rn(ty1, th);
+    const float iw_raw = __fsub_rn(fminf(px2, tx2), fmaxf(px1, tx1));
+    const float ih_raw = __fsub_rn(fminf(py2, ty2), fmaxf(py1, ty1));
+    const float iw = iw_raw < 0.f ? 0.f : iw_raw, ih = ih_raw < 0.f ? 0.f : ih_raw;
+    const float inter = __fmul_rn(iw, ih);
+    const float uni = __fsub_rn(__fadd_rn(__fmul_rn(pw, ph), __fmul_rn(tw, th)), inter);
+    const float iou = __fdiv_rn(inter, __fadd_rn(uni, e));
+    const float cw = __fsub_rn(fmaxf(px2, tx2), fminf(px1, tx1));
+    const float ch = __fsub_rn(fmaxf(py2, ty2), fminf(py1, ty1));
+    const float c2 = __fadd_rn(__fadd_rn(__fmul_rn(cw, cw), __fmul_rn(ch, ch)), e);
+    const float k4pi2 = 0.40528473456935105f;  // float32(4 / pi^2)
+    const float dat = __fsub_rn(atanf(__fdiv_rn(tw, th)), atanf(__fdiv_rn(pw, ph)));
+    const float v = __fmul_rn(k4pi2, __fmul_rn(dat, dat));
+    const float dx = __fsub_rn(p[0], t[0]), dy = __fsub_rn(p[1], t[1]);
+    const float rho2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    const float a = __fdiv_rn(v, __fadd_rn(__fsub_rn(v, iou), __fadd_rn(1.0f, e)));
+    const float ciou = __fsub_rn(iou, __fadd_rn(__fdiv_rn(rho2, c2), __fmul_rn(a, v)));
+    if (g) {
+        const double dpx1[4] = {1, 0, -0.5, 0}, dpx2[4] = {1, 0, 0.5, 0};
+        const double dpy1[4] = {0, 1, 0, -0.5}, dpy2[4] = {0, 1, 0, 0.5};
+        const bool iw_pos = iw_raw >= 0.f, ih_pos = ih_raw >= 0.f;  // clamp passes the gradient at equality
+        // torch.min / torch.max split the gradient evenly on exact ties
+        const double s_minx2 = px2 < tx2 ? 1.0 : (px2 == tx2 ? 0.5 : 0.0), s_maxx1 = px1 > tx1 ? 1.0 : (px1 == tx1 ? 0.5 : 0.0);
+        const double s_miny2 = py2 < ty2 ? 1.0 : (py2 == ty2 ? 0.5 : 0.0), s_maxy1 = py1 > ty1 ? 1.0 : (py1 == ty1 ? 0.5 : 0.0);
+        const double s_maxx2 = px2 > tx2 ? 1.0 : (px2 == tx2 ? 0.5 : 0.0), s_minx1 = px1 < tx1 ? 1.0 : (px1 == tx1 ? 0.5 : 0.0);
+        const double s_maxy2 = py2 > ty2 ? 1.0 : (py2 == ty2 ? 0.5 : 0.0), s_miny1 = py1 < ty1 ? 1.0 : (py1 == ty1 ? 0.5 : 0.0);
+        const double den = (double)uni + (double)e;
+        const double r = (double)pw / (double)ph;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double diw = iw_pos ? (s_minx2 * dpx2[q] - s_maxx1 * dpx1[q]) : 0.0;
+            const double dih = ih_pos ? (s_miny2 * dpy2[q] - s_maxy1 * dpy1[q]) : 0.0;
+            const double dinter = diw * ih + iw * dih;
+            const double dpwph = (q == 2 ? (double)ph : 0.0) + (q == 3 ? (double)pw : 0.0);
+            const double duni = dpwph - dinter;
+            const double diou = dinter / den - (double)inter * duni / (den * den);
+            const double dcw = s_maxx2 * dpx2[q] - s_minx1 * dpx1[q];
+            const double dch = s_maxy2 * dpy2[q] - s_miny1 * dpy1[q];
+            const double dc2 = 2.0 * cw * dcw + 2.0 * ch * dch;
+            const double drho2 = (q == 0 ? 2.0 * dx : 0.0) + (q == 1 ? 2.0 * dy : 0.0);
+            const double dr = (q == 2 ? 1.0 / (double)ph : 0.0) + (q == 3 ? -(double)pw / ((double)ph * ph) : 0.0);
+            const double dv = (double)k4pi2 * 2.0 * (double)dat * (-(dr / (1.0 + r * r)));
+            const double av = (q >= 2) ? (double)a * dv : 0.0;  // v depends on (w,h) only: a NaN alpha never reaches x,y
+            g[q] = diou - (drho2 / c2 - (double)rho2 * dc2 / ((double)c2 * c2) + av);
+        }
+    }
+    return ciou;
+}
+
+__global__ void ciou_fwd_kernel(const float *p, const float *t, long long M, float e, float *out)
+{
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float4 pp = reinterpret_cast<const float4 *>(p)[m], tt = reinterpret_cast<const float4 *>(t)[m];
+    const float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ta[4] = {tt.x, tt.y, tt.z, tt.w};
+    out[m] = ciou_eval(pa, ta, e, nullptr);
+}
+
+__global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go, long long M, float e, float *gp)
+{
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float4 pp = reinterpret_cast<const float4 *>(p)[m], tt = reinterpret_cast<const float4 *>(t)[m];
+    const float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ta[4] = {tt.x, tt.y, tt.z, tt.w};
+    double g[4];
+    ciou_eval(pa, ta, e, g);
+    const double s = go[m];
+    reinterpret_cast<float4 *>(gp)[m] = make_float4((float)(s * g[0]), (float)(s * g[1]), (float)(s * g[2]), (float)(s * g[3]));
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused detection loss, one scale
+// ------------------------------------------------------------------------------------------------
+struct LossScaleK {
+    const float *preds;  // [B,ny,nx,na,D]
+    float *grad;         // same shape (backward only)
+    long long cells;     // B*ny*nx*na
+    int C, D;
+    const int *M;        // device count from the assignment
+    const int *cell;     // [cap]
+    const int *cls;      // [cap]
+    const float *anchor; // [cap,2]
+    const float *box;    // [cap,4]
+    float *ciou;         // [cap]
+    int *winner;         // [cells] index of the last match that targets the cell, -1 if none
+    double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
+    double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
+    long long *hist;     // [3,C]
+    double *scalars;     // [8]
+    float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
+    double w_box, w_conf, w_cls;  // term weight * scale weight * upstream gradient (backward)
+    int nblk_match, nblk_dense;
+};
+
+__device__ __forceinline__ float bce_logits(float x, float t)
+{
+    // ATen binary_cross_entropy_with_logits: (1 - t) * x - log_sigmoid(x)
+    const float ls = __fsub_rn(fminf(x, 0.0f), log1pf(expf(-fabsf(x))));
+    return __fsub_rn(__fmul_rn(__fsub_rn(1.0f, t), x), ls);
+}
+
+constexpr int LOSS_THREADS = 256;
+
+// one warp per match: gather the row, CIoU, class BCE, confusion counters, "last match wins" ticket
+__global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(LossScaleK k)
+{
+    __shared__ double s_red[LOSS_THREADS / 32][4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int M = *k.M;
+    const long long warp0 = (long long)blockIdx.x * (LOSS_THREADS / 32) + wid;
+    const long long nwarps = (long long)gridDim.x * (LOSS_THREADS / 32);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (long long m = warp0; m < M; m += nwarps) {
+        const int cell = k.cell[m];
+        const int tc = k.cls[m];
+        const float *row = k.preds + (long long)cell * k.D;
+        float bsum = 0.f, best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < k.C; c += 32) {
+            const float x = __ldg(row + 1 + c);
+            bsum += bce_logits(x, c == tc ? k.cp : k.cn);
+            if (x > best) { best = x; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            const float p[4] = {__ldg(row + k.C + 1), __ldg(row + k.C + 2),
+                                __fmul_rn(__ldg(row + k.C + 3), k.anchor[2 * m]),
+                                __fmul_rn(__ldg(row + k.C + 4), k.anchor[2 * m + 1])};
+            const float4 tb = reinterpret_cast<const float4 *>(k.box)[m];
+            const float t[4] = {tb.x, tb.y, tb.z, tb.w};
+            const float ci = ciou_eval(p, t, 1e-7f, nullptr);
+            k.ciou[m] = ci;
+            atomicMax(&k.winner[cell], (int)m);
+            a0 += (double)__fsub_rn(1.0f, ci);
+            a1 += (double)ci;
+            a2 += (double)sigmoid_acc(__ldg(row));
+            a3 += (double)bsum;
+            atomicAdd((unsigned long long *)&k.hist[0 * k.C + tc], (unsigned long long)(bi == tc));
+            atomicAdd((unsigned long long *)&k.hist[1 * k.C + tc], 1ull);
+            atomicAdd((unsigned long long *)&k.hist[2 * k.C + bi], 1ull);
+        }
+    }
+    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; s_red[wid][3] = a3; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
+        k.part_match[(long long)blockIdx.x * 4 + threadIdx.x] = s;
+    }
+}
+
+// dense objectness BCE over every cell
+__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(LossScaleK k)
+{
+    __shared__ double s_red[LOSS_THREADS / 32][3];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < k.cells;
+         c += (long long)gridDim.x * LOSS_THREADS) {
+        const float x = __ldg(k.preds + c * k.D);
+        const int w = k.winner[c];
+        const float t = w >= 0 ? k.ciou[w] : 0.0f;
+        a0 += (double)bce_logits(x, t);
+        if (t == 0.0f) { a1 += (double)sigmoid_acc(x); a2 += 1.0; }
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
+        k.part_dense[(long long)blockIdx.x * 3 + threadIdx.x] = s;
+    }
+}
+
+// fixed-order final reduction -> scalars[8]
+__global__ void __launch_bounds__(256) loss_finalize_kernel(LossScaleK k)
+{
+    __shared__ double s_red[8][7];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = threadIdx.x; b < k.nblk_match; b += 256)
+        for (int q = 0; q < 4; ++q) v[q] += k.part_match[(long long)b * 4 + q];
+    for (int b = threadIdx.x; b < k.nblk_dense; b += 256)
+        for (int q = 0; q < 3; ++q) v[4 + q] += k.part_dense[(long long)b * 3 + q];
+    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0) for (int q = 0; q < 7; ++q) s_red[wid][q] = v[q];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s[7];
+        for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[w][q]; }
+        const double M = (double)*k.M;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        k.scalars[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
+        k.scalars[1] = s[4] / (double)k.cells;
+        k.scalars[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
+        k.scalars[3] = M > 0 ? s[1] / M : nan;
+        k.scalars[4] = M > 0 ? s[2] / M : nan;
+        k.scalars[5] = s[6] > 0 ? s[5] / s[6] : nan;
+        k.scalars[6] = M;
+        k.scalars[7] = s[6];
+    }
+}
+
+// backward 1/2: dense write of the gradient tensor (objectness channel everywhere, zeros elsewhere)
+__global__ void __launch_bounds__(256) loss_bwd_dense_kernel(LossScaleK k)
+{
+    const long long total = k.cells * k.D;
+    const double sc = k.w_conf / (double)k.cells;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+        const long long c = e / k.D;
+        float g = 0.0f;
+        if (e - c * k.D == 0) {
+            const float x = __ldg(k.preds + e);
+            const int w = k.winner[c];
+            const float t = w >= 0 ? k.ciou[w] : 0.0f;
+            g = (float)(sc * ((double)sigmoid_acc(x) - (double)t));
+        }
+        k.grad[e] = g;
+    }
+}
+
+// backward 2/2: matched rows -- class and box channels; duplicate matches of a cell accumulate
+__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_match_kernel(LossScaleK k)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int M = *k.M;
+    if (M <= 0) return;
+    const long long warp0 = (long long)blockIdx.x * (LOSS_THREADS / 32) + wid;
+    const long long nwarps = (long long)gridDim.x * (LOSS_THREADS / 32);
+    const double sc_cls = k.w_cls / ((double)M * (double)k.C);
+    const double sc_box = -k.w_box / (double)M;
+    for (long long m = warp0; m < M; m += nwarps) {
+        const int cell = k.cell[m];
+        const int tc = k.cls[m];
+        const float *row = k.preds + (long long)cell * k.D;
+        float *grow = k.grad + (long long)cell * k.D;
+        for (int c = lane; c < k.C; c += 32) {
+            const float x = __ldg(row + 1 + c);
+            const double t = (c == tc) ? (double)k.cp : (double)k.cn;
+            atomicAdd(grow + 1 + c, (float)(sc_cls * ((double)sigmoid_acc(x) - t)));
+        }
+        if (lane == 0) {
+            const float aw = k.anchor[2 * m], ah = k.anchor[2 * m + 1];
+            const float p[4] = {__ldg(row + k.C + 1), __ldg(row + k.C + 2), __fmul_rn(__ldg(row + k.C + 3), aw),
+                                __fmul_rn(__ldg(row + k.C + 4), ah)};
+            const float4 tb = reinterpret_cast<const float4 *>(k.box)[m];
+            const float t[4] = {tb.x, tb.y, tb.z, tb.w};
+            double g[4];
+            ciou_eval(p, t, 1e-7f, g);
+            atomicAdd(grow + k.C + 1, (float)(sc_box * g[0]));
+            atomicAdd(grow + k.C + 2, (float)(sc_box * g[1]));
+            atomicAdd(grow + k.C + 3, (float)(sc_box * g[2] * (double)aw));
+            atomicAdd(grow + k.C + 4, (float)(sc_box * g[3] * (double)ah));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// anchor-fit metrics (utils/make_anchors.py:14-39)
+// ------------------------------------------------------------------------------------------------
+struct RatioK { const float *wh; long long n; int k; float aw[32], ah[32]; float inv_thr; double *out; };
+
+__global__ void __launch_bounds__(256) ratio_metrics_kernel(RatioK k)
+{
+    double s0 = 0, s1 = 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < k.n; i += (long long)gridDim.x * 256) {
+        const float w = k.wh[2 * i], h = k.wh[2 * i + 1];
+        float best = -INFINITY;
+        for (int j = 0; j < k.k; ++j) {
+            const float r0 = __fdiv_rn(w, k.aw[j]), r1 = __fdiv_rn(h, k.ah[j]);
+            const float v = fminf(fminf(r0, __fdiv_rn(1.0f, r0)), fminf(r1, __fdiv_rn(1.0f, r1)));
+            best = fmaxf(best, v);
+        }
+        if (best > k.inv_thr) { s0 += (double)best; s1 += 1.0; }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(k.out, s0); atomicAdd(k.out + 1, s1); }
+    if (blockIdx.x == 0 && threadIdx.x == 0) k.out[2] = (double)k.n;
+}
+
+}  // namespace bg

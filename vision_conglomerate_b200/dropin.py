@@ -1,0 +1,137 @@
+"""Drop-in installation under the reference's own Python call sites.
+
+The reference has no plugin registry: ``train_det.py`` / ``inference_det.py`` reach the hot path through
+attribute look-ups resolved at call time (``DetectionDataset.build_target_by_scale``,
+``DetectionLoss.compute_ciou`` / ``forward``, ``torchvision.ops.batched_nms``,
+``DetectionNet._get_scale_pred``).  :func:`install` re-points those attributes at the CUDA operators,
+keeping every signature and return contract, so the host scripts run unmodified.
+
+Variants that are out of scope for the CUDA path (segmentation ``overlap_masks``, keypoint columns,
+focal loss) are delegated to the reference's *own original callable*, which is saved at install time --
+never to a re-implementation of ours.  CPU tensors are refused: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import ops
+
+_saved: Dict[str, Any] = {}
+
+
+def _is_cuda_f32(t) -> bool:
+    return isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32
+
+
+def _need_cuda(t, what: str) -> None:
+    if not _is_cuda_f32(t):
+        raise RuntimeError(f"{what}: vision_conglomerate_b200 is installed and only handles CUDA fp32 tensors "
+                           "(no CPU fallback); call uninstall() to get the reference implementation back")
+
+
+# ------------------------------------------------------------------------------------------------ B1
+def _make_build_target_by_scale(orig):
+    def build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold: float = 4.0,
+                              edge_threshold: float = 0.5, overlap_masks: Optional[bool] = None,
+                              batch_size: Optional[int] = None):
+        # segmentation / keypoint variants stay on the reference's implementation (detection_dataset.py:132-172)
+        if overlap_masks is not None or (isinstance(targets, torch.Tensor) and targets.dim() == 2 and targets.shape[1] > 6):
+            return orig(targets, fmap_shape, anchors, anchor_threshold, edge_threshold, overlap_masks, batch_size)
+        _need_cuda(targets, "build_target_by_scale")
+        return ops.build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold, edge_threshold)
+    return build_target_by_scale
+
+
+# ------------------------------------------------------------------------------------------------ B2
+def _make_compute_ciou(orig):
+    def compute_ciou(preds_xywh, targets_xywh, e: float = 1e-7):
+        if preds_xywh.shape != targets_xywh.shape:  # broadcasting form, unused by the repo (detection_loss.py:231-234)
+            return orig(preds_xywh, targets_xywh, e)
+        _need_cuda(preds_xywh, "compute_ciou")
+        return ops.compute_ciou(preds_xywh, targets_xywh.to(preds_xywh.dtype), e)
+    return compute_ciou
+
+
+# ------------------------------------------------------------------------------------------------ B3
+def _make_loss_forward(orig):
+    def forward(self, preds, targets):
+        model = self.model
+        out_of_scope = (
+            (self.alpha and self.gamma)                       # FocalLoss configured (detection_loss.py:74-76)
+            or bool(getattr(model, "num_keypoints", None))    # keypoint branch (:147-173)
+            or hasattr(model, "proto_seg_module")             # segmentation model
+            or len(preds) != 3
+            or (isinstance(targets, torch.Tensor) and targets.dim() == 2 and targets.shape[1] > 6)
+            or type(self).loss_fn is not _saved.get("DetectionLoss.loss_fn", type(self).loss_fn)
+        )
+        if out_of_scope:
+            return orig(self, preds, targets)
+        for p in preds:
+            _need_cuda(p, "DetectionLoss.forward")
+        cfg = dict(anchor_t=self.anchor_t, edge_t=self.edge_t, box_w=self.box_w, conf_w=self.conf_w,
+                   class_w=self.class_w, label_smoothing=self.label_smoothing, scale_w=self.scale_w,
+                   batch_scale_loss=self.batch_scale_loss)
+        # anchors are read from the module at call time: they live in the state dict (detection.py:36-38)
+        anchors3 = [model.sm_anchors.data, model.md_anchors.data, model.lg_anchors.data]
+        return ops.detection_loss(preds, targets.to(preds[0].device, torch.float32), anchors3, cfg)
+    return forward
+
+
+# ------------------------------------------------------------------------------------------------ B4
+def _make_batched_nms(orig):
+    def batched_nms(boxes, scores, idxs, iou_threshold):
+        _need_cuda(boxes, "batched_nms")
+        return ops.batched_nms(boxes, scores.float(), idxs.to(torch.int64), float(iou_threshold))
+    return batched_nms
+
+
+# ------------------------------------------------------------------------------------------------ B5
+def _make_get_scale_pred(orig):
+    def _get_scale_pred(self, scale_pred, anchors, input_shape, inference: bool = False):
+        if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
+            return orig(self, scale_pred, anchors, input_shape, inference)
+        if scale_pred.requires_grad and torch.is_grad_enabled():
+            # training: the decode must stay differentiable; the fused CUDA decode is inference-only
+            return orig(self, scale_pred, anchors, input_shape, inference)
+        _need_cuda(scale_pred, "_get_scale_pred")
+        return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), inference)
+    return _get_scale_pred
+
+
+def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True) -> None:
+    """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
+    imported in your process (any subset); ``torchvision_ops=True`` also replaces
+    ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time)."""
+    from . import _lib
+    _lib.lib()  # fail loudly now if the extension is not built
+    if DetectionDataset is not None and "build_target_by_scale" not in _saved:
+        _saved["build_target_by_scale"] = (DetectionDataset, DetectionDataset.__dict__["build_target_by_scale"])
+        DetectionDataset.build_target_by_scale = staticmethod(
+            _make_build_target_by_scale(DetectionDataset.build_target_by_scale))
+    if DetectionLoss is not None and "compute_ciou" not in _saved:
+        _saved["compute_ciou"] = (DetectionLoss, DetectionLoss.__dict__["compute_ciou"])
+        _saved["forward"] = (DetectionLoss, DetectionLoss.__dict__["forward"])
+        _saved["DetectionLoss.loss_fn"] = DetectionLoss.__dict__["loss_fn"]
+        DetectionLoss.compute_ciou = staticmethod(_make_compute_ciou(DetectionLoss.compute_ciou))
+        DetectionLoss.forward = _make_loss_forward(DetectionLoss.__dict__["forward"])
+    if DetectionNet is not None and "_get_scale_pred" not in _saved:
+        _saved["_get_scale_pred"] = (DetectionNet, DetectionNet.__dict__["_get_scale_pred"])
+        DetectionNet._get_scale_pred = _make_get_scale_pred(DetectionNet.__dict__["_get_scale_pred"])
+    if torchvision_ops and "batched_nms" not in _saved:
+        import torchvision
+        _saved["batched_nms"] = (torchvision.ops, torchvision.ops.batched_nms)
+        torchvision.ops.batched_nms = _make_batched_nms(torchvision.ops.batched_nms)
+
+
+def uninstall() -> None:
+    for name in ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "batched_nms"):
+        if name in _saved:
+            owner, orig = _saved.pop(name)
+            setattr(owner, name, orig)
+    _saved.pop("DetectionLoss.loss_fn", None)
+
+
+def installed() -> Dict[str, bool]:
+    return {k: (k in _saved) for k in ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "batched_nms")}

@@ -1,0 +1,424 @@
+"""Torch-facing operators over libboxgeom.so.
+
+PyTorch is plumbing here: it owns device memory (inputs, outputs, workspaces come from the caching
+allocator) and supplies the CUDA stream; all arithmetic happens in the hand-written sm_100a kernels.
+Every operator rejects CPU / non-fp32 tensors -- there is no fallback path.
+
+Each function cites the reference routine whose call signature it mirrors (paths relative to the
+reference root).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import DetectParams, LossParams, check
+
+_ws: Dict[Tuple[int, str], torch.Tensor] = {}
+_pinned: Dict[Tuple[int, str], torch.Tensor] = {}
+_mask_budget: Dict[Tuple[int, str], int] = {}
+DEFAULT_MASK_BYTES = 64 << 20
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _workspace(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind)
+    t = _ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        _ws[key] = t
+    return t
+
+
+def _pinned_i32(dev: torch.device, kind: str, n: int) -> torch.Tensor:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), kind)
+    t = _pinned.get(key)
+    if t is None or t.numel() < n:
+        t = torch.empty(int(n), dtype=torch.int32).pin_memory()
+        _pinned[key] = t
+    return t
+
+
+def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: the box-geometry kernels need a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _anchors_host(anchors) -> List[List[float]]:
+    if isinstance(anchors, torch.Tensor):
+        return anchors.detach().to("cpu", torch.float32).reshape(-1, 2).tolist()
+    return torch.tensor(anchors, dtype=torch.float32).reshape(-1, 2).tolist()
+
+
+def _anchor_array(anchors) -> "C.Array":
+    a = _anchors_host(anchors)
+    arr = (C.c_float * (2 * len(a)))()
+    for i, (w, h) in enumerate(a):
+        arr[2 * i] = w
+        arr[2 * i + 1] = h
+    return arr
+
+
+def _read_counts(dev_counts: torch.Tensor, kind: str) -> torch.Tensor:
+    """One device->host copy + one stream sync: the only host-visible sync of an operator."""
+    host = _pinned_i32(dev_counts.device, kind, dev_counts.numel())[: dev_counts.numel()]
+    host.copy_(dev_counts, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host
+
+
+# ---------------------------------------------------------------------------------------------- B4
+def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, iou_threshold: float,
+                max_groups: int = 1 << 16) -> torch.Tensor:
+    """Drop-in for ``torchvision.ops.batched_nms`` as called at inference_det.py:77-82: greedy NMS per
+    distinct ``idxs`` value, int64 keep indices, score-descending (index-ascending inside equal scores)."""
+    boxes = _req(boxes, "boxes").reshape(-1, 4)
+    scores = _req(scores, "scores").reshape(-1)
+    idxs = _req(idxs, "idxs", torch.int64).reshape(-1)
+    n = scores.numel()
+    dev = boxes.device
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    keep = torch.empty(n, dtype=torch.int64, device=dev)
+    counts = torch.empty(2, dtype=torch.int32, device=dev)
+    key = (dev.index, "gnms")
+    mask_bytes = _mask_budget.get(key, DEFAULT_MASK_BYTES)
+    while True:
+        ws = _workspace(dev, "gnms", L.bg_batched_nms_workspace_bytes(n, max_groups, mask_bytes))
+        check(L.bg_batched_nms(boxes.data_ptr(), scores.data_ptr(), idxs.data_ptr(), n, float(iou_threshold),
+                               max_groups, keep.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), mask_bytes,
+                               _stream()), "bg_batched_nms")
+        h = _read_counts(counts, "gnms")
+        status = int(h[1])
+        if status & _lib.STATUS_GROUP_RANGE:
+            if max_groups >= (1 << 24):
+                raise RuntimeError("batched_nms: idxs span more than 2^24 distinct values")
+            max_groups = min(max_groups << 4, 1 << 24)
+            continue
+        if status & _lib.STATUS_MASK_SPACE:
+            worst = n * ((n + 63) // 64) * 8
+            if mask_bytes >= worst:
+                raise RuntimeError("batched_nms: suppression-mask workspace exhausted")
+            mask_bytes = min(worst, mask_bytes * 8)
+            _mask_budget[key] = mask_bytes
+            continue
+        return keep[: int(h[0])]
+
+
+# ---------------------------------------------------------------------------------------------- B5
+@dataclass
+class Detections:
+    """Result of :func:`detect`.  ``pred_boxes[:, :] = (score, class, x1, y1, x2, y2)`` (inference_det.py:93-97),
+    ``sample_idxs`` the image of each row (:87), ``keep_idxs`` its flat candidate index ``b*N + i``,
+    ``counts[b]`` rows of image b (rows are image-major unless ``order='global'``), ``candidates[b]`` how many
+    candidates of image b cleared the score threshold."""
+    pred_boxes: torch.Tensor
+    sample_idxs: torch.Tensor
+    keep_idxs: torch.Tensor
+    counts: torch.Tensor
+    candidates: torch.Tensor
+
+
+class DetectPlan:
+    """Parameters, output buffers and workspace of one fused decode+NMS configuration, reusable across
+    batches of the same shape.  ``enqueue`` launches the kernels on the current stream without any host
+    synchronisation; ``result`` performs the single device->host read the reference signature forces."""
+
+    def __init__(self, shapes: Sequence[Tuple[int, ...]], anchors3: Sequence, input_shape: Tuple[int, int],
+                 num_classes: int, device: torch.device, og_size: Optional[Tuple[int, int]] = None,
+                 iou_threshold: float = 0.5, score_threshold: float = 0.1, box_allowance: Optional[float] = None,
+                 tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0):
+        if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
+            raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
+        B, _, _, na, D = shapes[0]
+        if D != num_classes + 5:
+            raise RuntimeError("detect: the keypoint / mask-coefficient variants are out of scope for the fused path")
+        p = DetectParams()
+        p.B, p.C, p.na = B, num_classes, na
+        p.H, p.W = int(input_shape[0]), int(input_shape[1])
+        p.og_H, p.og_W = (int(og_size[0]), int(og_size[1])) if og_size is not None else (-1, -1)
+        for s, sh in enumerate(shapes):
+            if sh[0] != B or sh[3] != na or sh[4] != D:
+                raise RuntimeError("detect: inconsistent head output shapes")
+            p.ny[s], p.nx[s] = sh[1], sh[2]
+            for a, (w, h) in enumerate(_anchors_host(anchors3[s])):
+                p.anchors[s][a][0] = w
+                p.anchors[s][a][1] = h
+        p.box_allowance = float(box_allowance) if box_allowance else 0.0
+        p.score_threshold = float(score_threshold)
+        p.iou_threshold = float(iou_threshold)
+        tracked = list(tracked_classes) if tracked_classes else []
+        if len(tracked) > _lib.BG_MAX_TRACKED:
+            raise RuntimeError("detect: at most %d tracked classes" % _lib.BG_MAX_TRACKED)
+        p.n_tracked = len(tracked)
+        for i, c in enumerate(tracked):
+            p.tracked[i] = int(c)
+        p.order = 1 if order == "global" else 0
+        p.variant = int(variant)
+        self.params, self.B, self.dev = p, B, device
+        self.N = sum(sh[1] * sh[2] * na for sh in shapes)
+        self.shapes = [tuple(sh) for sh in shapes]
+        n = B * self.N
+        self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
+        self.out_img = torch.empty(n, dtype=torch.int64, device=device)
+        self.out_keep = torch.empty(n, dtype=torch.int64, device=device)
+        self.counts = torch.empty(2 + 2 * B, dtype=torch.int32, device=device)
+        self.key = (device.index, "detect")
+        self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
+
+    def enqueue(self, raws: Sequence[torch.Tensor]) -> None:
+        L = _lib.lib()
+        p = self.params
+        self.raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
+        if [tuple(r.shape) for r in self.raws] != self.shapes:
+            raise RuntimeError("detect: head output shapes differ from the plan")
+        self.mask_bytes = _mask_budget.get(self.key, DEFAULT_MASK_BYTES)
+        need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
+        if need == 0:
+            raise RuntimeError("detect: invalid parameters")
+        ws = _workspace(self.dev, "detect", need)
+        check(L.bg_detect(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(), C.byref(p),
+                          self.out_boxes.data_ptr(), self.out_img.data_ptr(), self.out_keep.data_ptr(),
+                          self.counts.data_ptr(), ws.data_ptr(), ws.numel(), self.mask_bytes, _stream()), "bg_detect")
+
+    def result(self) -> Detections:
+        B = self.B
+        while True:
+            h = _read_counts(self.counts, "detect")
+            if int(h[1]) & _lib.STATUS_MASK_SPACE:
+                # the per-image survivor counts are known now: size the bit matrix exactly and run again
+                cand = h[2 + B: 2 + 2 * B].to(torch.int64)
+                exact = int((cand * ((cand + 63) // 64)).sum()) * 8
+                if exact <= self.mask_bytes:
+                    raise RuntimeError("detect: suppression-mask workspace exhausted")
+                _mask_budget[self.key] = exact + (exact >> 3)
+                self.enqueue(self.raws)
+                continue
+            k = int(h[0])
+            return Detections(self.out_boxes[:k], self.out_img[:k], self.out_keep[:k], h[2: 2 + B].clone(),
+                              h[2 + B: 2 + 2 * B].clone())
+
+
+def detect(raws: Sequence[torch.Tensor], anchors3: Sequence, input_shape: Tuple[int, int], num_classes: int,
+           og_size: Optional[Tuple[int, int]] = None, iou_threshold: float = 0.5, score_threshold: float = 0.1,
+           box_allowance: Optional[float] = None, tracked_classes: Optional[Sequence[int]] = None,
+           order: str = "image", variant: int = 0) -> Detections:
+    """Fused ``DetectionNet.forward(inference=True)`` tail (modules/detection.py:69-91) +
+    ``post_process_preds`` lines 57-97 and the class filter at :107-109, from the three raw head outputs
+    ``[B, ny, nx, na, 5+C]``.  The returned tensors are views of buffers owned by the plan of this call."""
+    raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
+    plan = DetectPlan([tuple(r.shape) for r in raws], anchors3, input_shape, num_classes, raws[0].device, og_size,
+                      iou_threshold, score_threshold, box_allowance, tracked_classes, order, variant)
+    plan.enqueue(raws)
+    return plan.result()
+
+
+def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int], inference: bool = False,
+                 og_size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+    """``DetectionNet._get_scale_pred`` (modules/detection.py:98-173), optionally followed by
+    ``_bbox_to_size`` (:175-190, guard of :76 applied inside)."""
+    x = _req(scale_pred, "scale_pred")
+    B, ny, nx, na, D = x.shape
+    out = torch.empty_like(x)
+    og = (int(og_size[0]), int(og_size[1])) if og_size is not None else (-1, -1)
+    check(_lib.lib().bg_decode_scale(x.data_ptr(), out.data_ptr(), B, ny, nx, na, D - 5, _anchor_array(anchors),
+                                     int(input_shape[0]), int(input_shape[1]), int(bool(inference)), og[0], og[1],
+                                     _stream()), "bg_decode_scale")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- B1
+def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_threshold: float = 4.0,
+                          edge_threshold: float = 0.5):
+    """``DetectionDataset.build_target_by_scale`` (dataset/detection_dataset.py:90-246), detection branch.
+    Returns ``(indices, classes, anchors, boxes, None, None)`` exactly like the reference."""
+    t = _req(targets, "targets")
+    if t.dim() != 2 or t.shape[1] != 6:
+        raise RuntimeError("build_target_by_scale: keypoint columns are out of scope for the CUDA path")
+    dev = t.device
+    nt = t.shape[0]
+    ny, nx = (int(v) for v in (fmap_shape.tolist() if isinstance(fmap_shape, torch.Tensor) else fmap_shape))
+    anc = _anchors_host(anchors)
+    na = len(anc)
+    cap = max(5 * na * nt, 1)
+    idx4 = torch.empty(4, cap, dtype=torch.int64, device=dev)
+    cls = torch.empty(cap, dtype=torch.int64, device=dev)
+    anc_out = torch.empty(cap, 2, dtype=torch.float32, device=dev)
+    box = torch.empty(cap, 4, dtype=torch.float32, device=dev)
+    count = torch.empty(2, dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    ws = _workspace(dev, "assign", max(L.bg_assign_workspace_bytes(nt, na), 256))
+    check(L.bg_assign_targets(t.data_ptr(), nt, ny, nx, _anchor_array(anc), na, float(anchor_threshold),
+                              float(edge_threshold), idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
+                              box.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "bg_assign_targets")
+    M = int(_read_counts(count[:1], "assign")[0])
+    indices = [idx4[k, :M] for k in range(4)]
+    return indices, cls[:M], anc_out[:M], box[:M], None, None
+
+
+# ---------------------------------------------------------------------------------------------- B2
+class _CIoU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, t, e):
+        p32, t32 = _req(p, "preds_xywh").reshape(-1, 4), _req(t, "targets_xywh").reshape(-1, 4)
+        out = torch.empty(p32.shape[0], dtype=torch.float32, device=p32.device)
+        check(_lib.lib().bg_ciou_fwd(p32.data_ptr(), t32.data_ptr(), p32.shape[0], float(e), out.data_ptr(), _stream()),
+              "bg_ciou_fwd")
+        ctx.save_for_backward(p32, t32)
+        ctx.e = float(e)
+        ctx.shape = p.shape
+        return out.reshape(p.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, go):
+        p32, t32 = ctx.saved_tensors
+        go = go.contiguous().reshape(-1).float()
+        gp = torch.empty_like(p32)
+        check(_lib.lib().bg_ciou_bwd(p32.data_ptr(), t32.data_ptr(), go.data_ptr(), p32.shape[0], ctx.e, gp.data_ptr(),
+                                     _stream()), "bg_ciou_bwd")
+        return gp.reshape(ctx.shape), None, None
+
+
+def compute_ciou(preds_xywh: torch.Tensor, targets_xywh: torch.Tensor, e: float = 1e-7) -> torch.Tensor:
+    """``DetectionLoss.compute_ciou`` (modules/detection_loss.py:229-264), element-wise form, differentiable
+    w.r.t. ``preds_xywh`` (alpha held constant as under the reference's ``no_grad``)."""
+    if preds_xywh.shape != targets_xywh.shape:
+        raise RuntimeError("compute_ciou: the broadcasting form (preds.ndim == targets.ndim + 1) is unused by the "
+                           "reference and not provided")
+    return _CIoU.apply(preds_xywh, targets_xywh, e)
+
+
+# ---------------------------------------------------------------------------------------------- B3
+METRIC_KEYS = ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy", "f1", "precision",
+               "recall")
+
+
+def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
+    p = LossParams()
+    B, _, _, na, D = preds3[0].shape
+    p.B, p.C, p.na = B, D - 5, na
+    for s, x in enumerate(preds3):
+        p.ny[s], p.nx[s] = x.shape[1], x.shape[2]
+        for a, (w, h) in enumerate(_anchors_host(anchors3[s])):
+            p.anchors[s][a][0] = w
+            p.anchors[s][a][1] = h
+    p.anchor_t, p.edge_t = float(cfg.get("anchor_t", 4.0)), float(cfg.get("edge_t", 0.5))
+    p.label_smoothing = float(cfg.get("label_smoothing", 0.0))
+    p.box_w, p.conf_w, p.class_w = float(cfg.get("box_w", 1.0)), float(cfg.get("conf_w", 1.0)), float(cfg.get("class_w", 1.0))
+    sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
+    for s in range(3):
+        p.scale_w[s] = float(sw[s])
+    p.nt = targets.shape[0]
+    return p
+
+
+class _DetLoss(torch.autograd.Function):
+    """Forward: assignment + gather + CIoU + objectness/class BCE for the three scales, no host sync.
+    Backward: dense ``grad_preds`` written once per scale."""
+
+    @staticmethod
+    def forward(ctx, sm, md, lg, targets, params: LossParams, scalars, hist):
+        L = _lib.lib()
+        dev = sm.device
+        ws = _workspace(dev, "loss", L.bg_loss_workspace_bytes(C.byref(params)))
+        check(L.bg_loss_fwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), targets.data_ptr() if targets.numel() else None,
+                            C.byref(params), scalars.data_ptr(), hist.data_ptr(), ws.data_ptr(), ws.numel(),
+                            _stream()), "bg_loss_fwd")
+        ctx.save_for_backward(sm, md, lg)
+        ctx.params, ctx.ws = params, ws
+        sw = torch.tensor([params.scale_w[0], params.scale_w[1], params.scale_w[2]], dtype=torch.float64, device=dev)
+        tw = torch.tensor([params.box_w, params.conf_w, params.class_w], dtype=torch.float64, device=dev)
+        per_term = (scalars[:, :3] * sw[:, None]).sum(0)  # lbox, lconf, lcls weighted over scales (:107-109)
+        return (per_term * tw).sum().float()               # :110
+
+    @staticmethod
+    def backward(ctx, go):
+        sm, md, lg = ctx.saved_tensors
+        L = _lib.lib()
+        grads = [torch.empty_like(x) for x in (sm, md, lg)]
+        # the upstream gradient is a scalar; reading it costs one sync (loss.backward() passes 1.0)
+        g = float(go)
+        check(L.bg_loss_bwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), C.byref(ctx.params), g, grads[0].data_ptr(),
+                            grads[1].data_ptr(), grads[2].data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()),
+              "bg_loss_bwd")
+        return grads[0], grads[1], grads[2], None, None, None, None
+
+
+def _macro_metrics(hist: torch.Tensor, M: int) -> Dict[str, float]:
+    """sklearn accuracy / macro f1, precision, recall (modules/detection_loss.py:198-206) from the per-class
+    (tp, n_true, n_pred) counters -- finished on the host in float64."""
+    nan = float("nan")
+    if M == 0:
+        return dict(accuracy=nan, f1=nan, precision=nan, recall=nan)
+    tp, nt, npred = (hist[i].double() for i in range(3))
+    lab = (nt + npred) > 0
+    prec = torch.where(npred > 0, tp / npred.clamp(min=1), torch.zeros_like(tp))[lab]
+    rec = torch.where(nt > 0, tp / nt.clamp(min=1), torch.zeros_like(tp))[lab]
+    f1 = (2 * tp / (nt + npred).clamp(min=1))[lab]
+    return dict(accuracy=float(tp.sum() / M), f1=float(f1.mean()), precision=float(prec.mean()), recall=float(rec.mean()))
+
+
+def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchors3: Sequence, cfg: dict,
+                   with_metrics: bool = True):
+    """``DetectionLoss.forward`` (modules/detection_loss.py:84-122) for the default configuration.
+    Returns ``(loss, metrics_dict)``; ``loss`` is a 0-d tensor attached to autograd through ``preds3``."""
+    preds3 = [_req(x, f"preds[{i}]") for i, x in enumerate(preds3)]
+    targets = _req(targets, "targets")
+    if targets.dim() != 2 or targets.shape[1] != 6:
+        raise RuntimeError("detection_loss: keypoint targets are out of scope for the CUDA path")
+    dev = preds3[0].device
+    params = _loss_params(preds3, targets, anchors3, cfg)
+    Cc = params.C
+    scalars = torch.empty(3, 8, dtype=torch.float64, device=dev)
+    hist = torch.empty(3, 3, Cc, dtype=torch.int64, device=dev)
+    loss = _DetLoss.apply(preds3[0], preds3[1], preds3[2], targets, params, scalars, hist)
+    if cfg.get("batch_scale_loss"):
+        loss = loss * preds3[-1].shape[0]
+    if not with_metrics:
+        return loss, {}
+    # one D2H copy for everything the reference fetches with ~28 .item() calls
+    host = torch.cat([scalars.reshape(-1), hist.reshape(-1).double(), loss.detach().double().reshape(1)]).cpu()
+    sc = host[:24].reshape(3, 8)
+    hh = host[24:24 + 9 * Cc].reshape(3, 3, Cc).long()
+    rows = []
+    for s in range(3):
+        M = int(sc[s, 6])
+        m = dict(mean_ciou=float(sc[s, 3]), conf_loss=float(sc[s, 1]), avg_pos_conf=float(sc[s, 4]),
+                 avg_neg_conf=float(sc[s, 5]), class_loss=float(sc[s, 2]) if M else float("nan"))
+        m.update(_macro_metrics(hh[s], M))
+        rows.append(m)
+    metrics = {"aggregate_loss": float(host[-1])}
+    for k in METRIC_KEYS:
+        vals = [r[k] for r in rows if r[k] == r[k]]  # pandas column mean skips NaN (:117-121)
+        metrics[k] = sum(vals) / len(vals) if vals else float("nan")
+    return loss, metrics
+
+
+# ---------------------------------------------------------------------------------------------- a13
+def ratio_metrics_w_extras(anchors, wh_data: torch.Tensor, threshold: float = 4.0) -> Tuple[float, float, float]:
+    """``utils/make_anchors.py:27-39``: (score, best-possible-recall, anchors-above-threshold)."""
+    wh = _req(wh_data, "wh_data").reshape(-1, 2)
+    anc = _anchors_host(anchors)
+    out = torch.empty(3, dtype=torch.float64, device=wh.device)
+    check(_lib.lib().bg_ratio_metrics(wh.data_ptr(), wh.shape[0], _anchor_array(anc), len(anc), float(threshold),
+                                      out.data_ptr(), _stream()), "bg_ratio_metrics")
+    s, m, n = out.cpu().tolist()
+    nan = float("nan")
+    return (s / n if n else nan, m / n if n else nan, m)
+
+
+def ratio_metrics(anchors, wh_data: torch.Tensor, threshold: float = 4.0) -> float:
+    """``utils/make_anchors.py:14-25``."""
+    return ratio_metrics_w_extras(anchors, wh_data, threshold)[0]
