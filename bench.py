@@ -174,6 +174,9 @@ def run_ours(args):
     K = args.steps
     ev_k = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for a, b in ev_k:  # torch creates the cudaEvent lazily: record once so the handle exists
+        a.record()
+        b.record()
     barrier()
     launches0 = _lib.launch_count()
     with ClockSampler(local) as clk:

@@ -133,7 +133,7 @@ def nms_boxes(n: int, groups: int, seed: int = 3, extent: float = 640.0, ties: b
     scores = torch.rand(n, generator=g)
     if ties:
         scores = (scores * 16).floor() / 16  # heavy score ties
-        boxes[n // 2:] = boxes[: n - n // 2]   # exact duplicate boxes
+        boxes[n // 2:] = boxes[: n - n // 2].clone()   # exact duplicate boxes
     idxs = torch.randint(0, groups, (n,), generator=g, dtype=torch.int64)
     return boxes, scores.contiguous(), idxs
 
