@@ -10,7 +10,7 @@ timeout 300 $CMD > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?" >> gpurun_out/stages.txt
 timeout 300 $CMD > gpurun_out/plain2.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"decode_filter|nms_mask|nms_reduce|seg_sort|detect_output" -s 25 -c 5 -o gpurun_out/prof_r1 -f $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"decode_filter|nms_mask|nms_pairs|nms_reduce|seg_sort|detect_output|seg_tables" -s 42 -c 7 -o gpurun_out/prof_r1 -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?" >> gpurun_out/stages.txt
 cat gpurun_out/stages.txt
 tail -n 3 gpurun_out/pytest_gpu.log

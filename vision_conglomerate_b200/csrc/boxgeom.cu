@@ -62,12 +62,18 @@ static void carve_seg(Bump &b, SegNms &p, long long S_max, long long elems, size
     p.seg_off = b.take<long long>(S_max + 1);
     p.tile_prefix = b.take<int>(S_max + 1);
     p.mask_off = b.take<long long>(S_max + 1);
+    p.item_prefix = b.take<int>(S_max + 1);
     p.emit_count = b.take<int>(S_max);
     p.out_prefix = b.take<long long>(S_max + 1);
     p.keys = b.take<u64>(elems);
     p.sorted_box = b.take<float4>(elems);
     p.sorted_area = b.take<float>(elems);
+    p.bkeys = b.take<u64>(elems);
+    p.bbox = b.take<float4>(elems);
+    p.barea = b.take<float>(elems);
     p.keepbits = b.take<u64>(elems / 64 + S_max + 1);
+    p.ew32 = b.take<u32>(2 * (elems / 64 + S_max + 1));
+    p.rank32 = b.take<u32>(2 * (elems / 64 + S_max + 1));
     p.emit_pos = b.take<u32>(elems);
     p.emit_key = b.take<u64>(elems);
     p.mask = b.take<u64>(mask_bytes / 8);
@@ -166,6 +172,7 @@ int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs,
     p.cls = nullptr;
     p.n_tracked = 0;
     p.thr = make_iou_thr(iou_threshold);
+    segnms_configure(p);
     const int sms = num_sms();
     const int gs = sms * 8;
     const long long *gidx = reinterpret_cast<const long long *>(idxs);
@@ -182,8 +189,8 @@ int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs,
     const int S_launch = (int)(max_groups < n ? max_groups : n);
     int rc = segnms_run(p, S_launch, out_counts, 0, sms, st);
     if (rc != BG_OK) return rc;
-    int go = S_launch < 1 ? 1 : (S_launch > sms * 8 ? sms * 8 : S_launch);
-    gnms_output_kernel<<<go, 256, 0, st>>>(p, reinterpret_cast<long long *>(out_keep));
+    const int go = S_launch < 1 ? 1 : (S_launch > 4096 ? 4096 : S_launch);
+    gnms_output_kernel<<<dim3(S_launch > 256 ? 1 : 8, go), 256, 0, st>>>(p, reinterpret_cast<long long *>(out_keep));
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -213,6 +220,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     p.n_tracked = pp->n_tracked;
     for (int i = 0; i < pp->n_tracked; ++i) p.tracked[i] = pp->tracked[i];
     p.thr = make_iou_thr(pp->iou_threshold);
+    segnms_configure(p);
 
     DetectK k;
     memset(&k, 0, sizeof(k));
@@ -254,24 +262,27 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     if (variant == 2 && !aligned) return BG_ERR_INVALID;
     if (variant == 2) {
         TileMap tm;
-        int TR = (int)((200 * 1024) / ((size_t)TMA_STAGES * k.D * 4));
-        TR = TR > TMA_THREADS ? TMA_THREADS : (TR / 4) * 4;
+        int TR = (int)(TMA_TILE_BYTES / ((size_t)k.D * 4));
+        TR = TR > TMA_THREADS ? TMA_THREADS : (TR / 4) * 4;  // multiple of 4 rows keeps every full tile 16-byte sized
         if (TR < 4) variant = 1;
         else {
             tm.TR = TR;
             tm.total = 0;
             for (int s = 0; s < 3; ++s) { tm.tiles[s] = (int)((k.sc[s].rows + TR - 1) / TR); tm.total += tm.tiles[s]; }
-            const size_t smem = (size_t)TMA_STAGES * TR * k.D * 4;
-            static size_t smem_set = 0;
-            if (smem > smem_set) {
-                if (cudaFuncSetAttribute(decode_filter_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            const size_t smem = (size_t)TR * k.D * 4;
+            static bool attr_set = false;
+            if (!attr_set) {
+                if (cudaFuncSetAttribute(decode_filter_tma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_TILE_BYTES) != cudaSuccess ||
+                    cudaFuncSetAttribute(decode_filter_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_TILE_BYTES) != cudaSuccess) {
                     (void)cudaGetLastError();
                     return BG_ERR_LAUNCH;
                 }
-                smem_set = smem;
+                attr_set = true;
             }
-            const int grid = tm.total < sms ? tm.total : sms;
-            decode_filter_tma_kernel<<<grid, TMA_THREADS, smem, st>>>(k, tm);
+            const int cap = sms * TMA_CTAS_PER_SM;
+            const int grid = tm.total < cap ? tm.total : cap;
+            if (k.C == 80) decode_filter_tma_kernel<80><<<grid, TMA_THREADS, smem, st>>>(k, tm);
+            else decode_filter_tma_kernel<0><<<grid, TMA_THREADS, smem, st>>>(k, tm);
             BG_LAUNCH_CHECK();
         }
     }
@@ -282,8 +293,8 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     if (prof) { cudaEventRecord(g_prof_stop, st); g_prof_start = g_prof_stop = nullptr; }
     int rc = segnms_run(p, pp->B, out_counts, 1, sms, st);
     if (rc != BG_OK) return rc;
-    const int go = pp->B < sms * 4 ? pp->B : sms * 4;
-    detect_output_kernel<<<go, 256, 0, st>>>(p, k, pp->order, out_boxes, reinterpret_cast<long long *>(out_img),
+    const int go = pp->B < 4096 ? pp->B : 4096;
+    detect_output_kernel<<<dim3(pp->B > 256 ? 1 : 8, go), 256, 0, st>>>(p, k, pp->order, out_boxes, reinterpret_cast<long long *>(out_img),
                                              reinterpret_cast<long long *>(out_keep), out_counts);
     BG_LAUNCH_CHECK();
     return BG_OK;

@@ -156,12 +156,16 @@ __global__ void __launch_bounds__(256) decode_filter_warp_kernel(DetectK k)
 }
 
 // ---------------------------------------------------------------------------------------------
-// variant 2: persistent CTAs, TMA bulk copies (cp.async.bulk + mbarrier) into a multi-stage
-// shared-memory ring; one thread per candidate row reads its row from shared memory (row stride
-// D = 5+C words: conflict-free when D is odd, e.g. 85).
+// variant 2: persistent CTAs, several per SM, each streaming tiles of TR candidate rows into shared
+// memory with one TMA bulk copy (cp.async.bulk + mbarrier) per tile.  Phase 1: one thread per row
+// takes the class maximum and the score from shared memory (row stride D = 5+C words: conflict-free
+// when D is odd, e.g. 85) and the survivors of the threshold are compacted into a small list;
+// phase 2: one thread per *survivor* finds the class id, decodes the box and writes the candidate.
+// The co-resident CTAs of an SM overlap each other's copy latency (4 x 43.5 KB in flight per SM).
 // ---------------------------------------------------------------------------------------------
-constexpr int TMA_STAGES = 4;
 constexpr int TMA_THREADS = 128;
+constexpr int TMA_CTAS_PER_SM = 4;
+constexpr int TMA_TILE_BYTES = 44 * 1024;
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
@@ -205,87 +209,119 @@ __device__ __forceinline__ void tile_locate(const DetectK &k, const TileMap &tm,
     rows = rem < tm.TR ? (int)rem : tm.TR;
 }
 
-__global__ void __launch_bounds__(TMA_THREADS, 1) decode_filter_tma_kernel(DetectK k, TileMap tm)
+struct Surv { int row; float score, wm, pm; };
+
+template <int CT>  // compile-time class count (fully unrolled row scan); 0 = take it from the parameters
+__global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS_PER_SM) decode_filter_tma_kernel(DetectK k, TileMap tm)
 {
     extern __shared__ __align__(128) unsigned char tma_smem[];
-    __shared__ __align__(8) u64 full_bar[TMA_STAGES];
-    const int D = k.D, C = k.C;
-    const u32 stage_bytes = (u32)tm.TR * D * 4;  // multiple of 16 (TR % 4 == 0)
+    __shared__ __align__(8) u64 full_bar;
+    __shared__ Surv s_surv[TMA_THREADS];
+    __shared__ int s_n;
+    const int C = CT ? CT : k.C;
+    const int D = C + 5;
+    float *tile = reinterpret_cast<float *>(tma_smem);
     const int tid = threadIdx.x, lane = tid & 31;
 
     if (tid == 0) {
-        for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full_bar[s], 1);
+        mbar_init(&full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_n = 0;
     }
     __syncthreads();
 
-    auto issue = [&](int tile, int stage) {
+    u32 parity = 0;
+    for (int t = blockIdx.x; t < tm.total; t += gridDim.x) {
         int si, rows;
         long long row0;
-        tile_locate(k, tm, tile, si, row0, rows);
-        const u32 bytes = ((u32)rows * D * 4) & ~15u;
-        mbar_expect_tx(&full_bar[stage], bytes);
-        if (bytes) bulk_g2s(tma_smem + (size_t)stage * stage_bytes, k.sc[si].raw + row0 * D, bytes, &full_bar[stage]);
-    };
-    if (tid == 0)
-        for (int s = 0; s < TMA_STAGES; ++s) {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < tm.total) issue(tile, s);
+        tile_locate(k, tm, t, si, row0, rows);
+        const ScaleDesc &s = k.sc[si];
+        const float *src = s.raw + row0 * D;
+        const int nfl = rows * D;
+        if ((nfl & 3) == 0) {  // the tile is a whole number of 16-byte units: one bulk copy
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile buffer
+                mbar_expect_tx(&full_bar, (u32)nfl * 4);
+                bulk_g2s(tile, src, (u32)nfl * 4, &full_bar);
+            }
+            mbar_wait(&full_bar, parity);
+            parity ^= 1;
+        } else {  // ragged last tile of a scale: plain coalesced loads
+            for (int i = tid; i < nfl; i += TMA_THREADS) tile[i] = __ldg(src + i);
+            __syncthreads();
         }
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x, ++it) {
-        const int stage = it % TMA_STAGES;
-        const u32 parity = (it / TMA_STAGES) & 1;
-        int si, rows;
-        long long row0;
-        tile_locate(k, tm, tile, si, row0, rows);
-        const ScaleDesc &s = k.sc[si];
-        mbar_wait(&full_bar[stage], parity);
-        const float *sr = reinterpret_cast<const float *>(tma_smem + (size_t)stage * stage_bytes) + tid * D;
-        const int n_bulk = (int)((((u32)rows * D * 4) & ~15u) >> 2);  // floats that arrived through the bulk copy
-        const float *gr = s.raw + (row0 + tid) * D;                   // the last <4 floats of a ragged tile come from global
-        bool alive = tid < rows;
+        // phase 1: one thread per row -- class maximum, score, threshold
+        bool alive = false;
         float score = 0.f, wm = -INFINITY, pm = 0.f;
-        const bool ragged = alive && ((tid + 1) * D > n_bulk);
-        auto ld = [&](int e) -> float { return (ragged && tid * D + e >= n_bulk) ? __ldg(gr + e) : sr[e]; };
-        if (alive) {
-#pragma unroll 8
-            for (int c = 1; c <= C; ++c) wm = fmaxf(wm, ld(c));
+        if (tid < rows) {
+            const float *sr = tile + tid * D;
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            if (CT) {
+#pragma unroll
+                for (int c = 0; c + 3 < CT; c += 4) {
+                    m0 = fmaxf(m0, sr[1 + c]); m1 = fmaxf(m1, sr[2 + c]);
+                    m2 = fmaxf(m2, sr[3 + c]); m3 = fmaxf(m3, sr[4 + c]);
+                }
+#pragma unroll
+                for (int c = CT & ~3; c < CT; ++c) m0 = fmaxf(m0, sr[1 + c]);
+            } else {
+                int c = 0;
+                for (; c + 3 < C; c += 4) {
+                    m0 = fmaxf(m0, sr[1 + c]); m1 = fmaxf(m1, sr[2 + c]);
+                    m2 = fmaxf(m2, sr[3 + c]); m3 = fmaxf(m3, sr[4 + c]);
+                }
+                for (; c < C; ++c) m0 = fmaxf(m0, sr[1 + c]);
+            }
+            wm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
             pm = sigmoid_acc(wm);
-            score = __fmul_rn(pm, sigmoid_acc(ld(0)));
+            score = __fmul_rn(pm, sigmoid_acc(sr[0]));
             alive = score > k.score_thr;
         }
-        const u32 amask = __ballot_sync(0xffffffffu, alive);
-        if (alive) {
-            int ci = 0;
-            const float win = tie_window(pm);
-            for (int c = 1; c <= C; ++c) {
-                const float v = ld(c);
-                if (v == wm || (v >= wm - win && sigmoid_acc(v) == pm)) { ci = c - 1; break; }
-            }
-            int b, x, y, a, idx;
-            row_coords(s, k.na, row0 + tid, b, x, y, a, idx);
-            const float4 bx = decode_xyxy(k, s, ld(C + 1), ld(C + 2), ld(C + 3), ld(C + 4), x, y, a);
-            // warp-aggregated slot allocation, one atomic per (warp, image)
-            const u32 peers = __match_any_sync(amask, b);
-            const int leader = __ffs(peers) - 1;
+        {   // compact the survivors of this tile (order inside the list is irrelevant)
+            const u32 am = __ballot_sync(0xffffffffu, alive);
             int base = 0;
-            if (lane == leader) base = atomicAdd(&k.seg_count[b], __popc(peers));
-            base = __shfl_sync(peers, base, leader);
-            const int slot = base + __popc(peers & lanemask_lt());
-            k.keys[k.seg_off[b] + slot] = make_key(score, (u32)idx);
-            k.box_dense[(long long)b * k.N + idx] = bx;
-            k.cls_dense[(long long)b * k.N + idx] = ci;
+            if (am) {
+                const int leader = __ffs(am) - 1;
+                if (lane == leader) base = atomicAdd(&s_n, __popc(am));
+                base = __shfl_sync(0xffffffffu, base, leader);
+            }
+            if (alive) s_surv[base + __popc(am & lanemask_lt())] = Surv{tid, score, wm, pm};
         }
-        __syncthreads();  // every consumer is done with this stage
-        if (tid == 0) {
-            const int next = tile + TMA_STAGES * gridDim.x;
-            if (next < tm.total) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue(next, stage);
+        __syncthreads();
+        const int n = s_n;
+
+        // phase 2: one thread per survivor -- class id, box decode, per-image slot, writes
+        for (int q0 = 0; q0 < n; q0 += TMA_THREADS) {
+            const int q = q0 + tid;
+            const bool act = q < n;
+            const u32 amask = __ballot_sync(0xffffffffu, act);
+            if (act) {
+                const Surv sv = s_surv[q];
+                const float *sr = tile + sv.row * D;
+                int ci = 0;
+                const float lo = sv.wm - tie_window(sv.pm);
+                for (int c = 0; c < C; ++c) {
+                    const float v = sr[1 + c];
+                    if (v >= lo && (v == sv.wm || sigmoid_acc(v) == sv.pm)) { ci = c; break; }
+                }
+                int b, x, y, a, idx;
+                row_coords(s, k.na, row0 + sv.row, b, x, y, a, idx);
+                const float4 bx = decode_xyxy(k, s, sr[C + 1], sr[C + 2], sr[C + 3], sr[C + 4], x, y, a);
+                // warp-aggregated slot allocation, one atomic per (warp, image)
+                const u32 peers = __match_any_sync(amask, b);
+                const int leader = __ffs(peers) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&k.seg_count[b], __popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const int slot = base + __popc(peers & lanemask_lt());
+                k.keys[k.seg_off[b] + slot] = make_key(sv.score, (u32)idx);
+                k.box_dense[(long long)b * k.N + idx] = bx;
+                k.cls_dense[(long long)b * k.N + idx] = ci;
             }
         }
+        __syncthreads();  // the tile buffer and the survivor list are free again
+        if (tid == 0) s_n = 0;  // ordered before the next phase 1 by the mbarrier (release/acquire) or the barrier above
     }
 }
 
@@ -297,12 +333,12 @@ __global__ void __launch_bounds__(256) detect_output_kernel(SegNms p, DetectK k,
                                                             int32_t *out_counts)
 {
     const int S = k.B;
-    for (int seg = blockIdx.x; seg < S; seg += gridDim.x) {
+    for (int seg = blockIdx.y; seg < S; seg += gridDim.y) {
         const int cnt = p.emit_count[seg];
         const long long off = p.seg_off[seg];
         const long long base = p.out_prefix[seg];
-        if (threadIdx.x == 0) out_counts[2 + S + seg] = p.seg_count[seg];
-        for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) out_counts[2 + S + seg] = p.seg_count[seg];
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt; r += gridDim.x * blockDim.x) {
             const u64 key = p.emit_key[off + r];
             const u32 pos = p.emit_pos[off + r];
             const u32 id = key_id(key);

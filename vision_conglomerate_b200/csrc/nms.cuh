@@ -1,5 +1,5 @@
 // Segmented greedy-NMS engine shared by bg_batched_nms (generic groups) and bg_detect (one segment
-// per image).  See nms.cu for the kernels.
+// per image).  Kernels are in nms_kernels.cuh (single translation unit: boxgeom.cu).
 #pragma once
 #include "common.cuh"
 
@@ -8,7 +8,7 @@ namespace bg {
 struct SegHdr {  // lives at the start of the workspace; (re)initialised by the first kernel of every call
     int S;       // number of segments
     int status;  // BG_STATUS_* bits
-    unsigned item_ctr;     // tile scheduler of the mask kernel
+    unsigned item_ctr;     // work-item scheduler of the pair / mask kernel
     unsigned reduce_done;  // "last CTA" ticket of the reduce kernel
     long long gmin, gmax;  // batched_nms: range of idxs
     long long total_out;
@@ -18,18 +18,24 @@ struct SegHdr {  // lives at the start of the workspace; (re)initialised by the 
 struct SegNms {
     SegHdr *hdr;
     int *seg_count;         // [S_max]   candidates per segment
-    long long *seg_off;     // [S_max+1] element offset of the segment in keys / sorted_* / emit_* (room for next_pow2(count))
+    long long *seg_off;     // [S_max+1] element offset of the segment in keys / sorted_* / b* / emit_* (room for next_pow2(count))
     int *tile_prefix;       // [S_max+1] exclusive prefix of ceil(count/64); also the word offset into keepbits
     long long *mask_off;    // [S_max+1] exclusive prefix of count*ceil(count/64) (u64 words)
+    int *item_prefix;       // [S_max+1] exclusive prefix of the pair-kernel work items
     int *emit_count;        // [S_max]   rows emitted per segment (after NMS and the class filter)
     long long *out_prefix;  // [S_max+1]
     u64 *keys;              // (score desc, id asc) keys, sorted in place per segment
-    float4 *sorted_box;     // boxes gathered into sorted order
+    float4 *sorted_box;     // boxes gathered into score order
     float *sorted_area;     // (x2-x1)*(y2-y1), pre-rounded like torchvision's CPU kernel
-    u64 *keepbits;          // kept bitmap in sorted order, word offset tile_prefix[s]
+    u64 *bkeys;             // (size bin << 32 | score-order position), sorted per segment: the "bin order"
+    float4 *bbox;           // boxes in bin order
+    float *barea;
+    u64 *keepbits;          // kept bitmap in score order, word offset tile_prefix[s]
+    u32 *ew32;              // emitted bitmap (32-bit words), offset 2*tile_prefix[s]
+    u32 *rank32;            // exclusive rank of each 32-bit word of ew32
     u64 *mask;              // suppression bit matrix, per segment column-tile-major: word(ct,row) at mask_off[s] + ct*K + row
     long long mask_words;   // capacity of mask
-    u32 *emit_pos;          // sorted position of each emitted row (compact per segment, at seg_off)
+    u32 *emit_pos;          // score-order position of each emitted row (compact per segment, at seg_off)
     u64 *emit_key;          // its key
     const float4 *boxes;    // source boxes; box of (segment s, id) is boxes[s*box_seg_stride + id]
     long long box_seg_stride;
@@ -37,6 +43,9 @@ struct SegNms {
     int n_tracked;
     int tracked[BG_MAX_TRACKED];
     IouThr thr;
+    int sparse;             // 1: size-binned pair kernel over a zeroed matrix; 0: dense tiled kernel
+    int nb;                 // bins per axis
+    float inv_delta;        // 1 / (bin width in log2 units)
 };
 
 }  // namespace bg
