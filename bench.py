@@ -39,6 +39,17 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel, per launch, from the committed
+    `ncu --set full` capture (profiles/traffic.json); None until a capture of the current kernel exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["decode_filter_kernel"]["dram_bytes_per_launch"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
 
@@ -196,6 +207,23 @@ def run_ours(args):
             torch.cuda.synchronize()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # stage breakdown of the per-image NMS kernel (one extra untimed step with the %globaltimer hook armed)
+    nms_stages = None
+    try:
+        ns = int(L.bg_profile_stamps_per_image())
+        stamps = torch.zeros(B, ns, dtype=torch.int64, device=devc)
+        L.bg_profile_stamps(stamps.data_ptr())
+        plan.enqueue(raws_d)
+        torch.cuda.synchronize()
+        L.bg_profile_stamps(None)
+        st = stamps.cpu().double()
+        if float(st[:, 7].min()) > 0:
+            names = ["load_slots", "grid_bucket", "pair_tests", "resolve", "sort", "rank+lookback", "write_rows"]
+            nms_stages = {n: float((st[:, i + 1] - st[:, i]).mean()) / 1e3 for i, n in enumerate(names)}
+            nms_stages["kernel_span_us"] = float(st[:, 7].max() - st[:, 0].min()) / 1e3
+            nms_stages["per_image_mean_us"] = float((st[:, 7] - st[:, 0]).mean()) / 1e3
+    except Exception as e:  # noqa: BLE001
+        nms_stages = {"error": repr(e)}
     t = torch.tensor([ms], dtype=torch.float64, device=devc)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -248,13 +276,13 @@ def run_ours(args):
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": int(plan.input_bytes), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "decode_filter_tma_kernel" if args.variant != 1 else "decode_filter_warp_kernel",
+        "roofline": {"bound": "hbm", "kernel": "decode_filter_kernel<80> (%s tile loads)" % ("plain" if args.variant == 1 else "TMA bulk"),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                     "traffic": _ncu_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "whole_step_frac": (alg_bytes / (ms_max / K * 1e-3) / 1e9) / peak},
         "detail": {"kept_rows_per_step": kept_rows, "survivors_per_image": survivors,
-                   "launches_per_step": launches_per_step},
+                   "launches_per_step": launches_per_step, "image_nms_kernel_stages_us": nms_stages},
     }
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1

@@ -38,6 +38,7 @@ extern "C" {
 /* bits of the device-side status word (out_counts[1]) */
 #define BG_STATUS_GROUP_RANGE 1 /* batched_nms: max(idxs)-min(idxs) exceeds max_groups */
 #define BG_STATUS_MASK_SPACE 2  /* suppression-mask scratch exhausted: retry with a larger workspace */
+#define BG_STATUS_NEED_GENERAL 4 /* bg_detect, per-image NMS path: an image has too many survivors or overlaps; retry with nms_path = 1 */
 
 #define BG_MAX_ANCHORS 8
 #define BG_MAX_TRACKED 64
@@ -84,7 +85,8 @@ typedef struct {
     int32_t n_tracked;          /* 0 = no class filter */
     int32_t tracked[BG_MAX_TRACKED];
     int32_t order;              /* 0: image-major, score-descending inside an image; 1: globally score-descending (reference row order) */
-    int32_t variant;            /* decode kernel: 0 auto, 1 plain vector loads, 2 TMA bulk pipeline */
+    int32_t variant;            /* decode kernel tile loads: 0 auto, 1 plain loads, 2 TMA bulk pipeline (needs 16-byte aligned inputs) */
+    int32_t nms_path;           /* 0 auto (one CTA per image when the threshold allows), 1 general segmented engine, 2 per-image only */
 } bg_detect_params;
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);
@@ -102,6 +104,10 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
 /* Profiling hook for bench.py: when both are non-NULL, the next bg_detect call records `start`/`stop`
  * (cudaEvent_t) on its stream immediately around the decode+filter kernel, then clears the hook. */
 void bg_profile_events(void *start, void *stop);
+/* Profiling hook: while `dev_buf` ([B, bg_profile_stamps_per_image()] u64, device) is non-NULL, the per-image NMS
+ * kernel of bg_detect writes the %globaltimer value (ns) at each of its stage boundaries for every image. */
+void bg_profile_stamps(void *dev_buf);
+int bg_profile_stamps_per_image(void);
 
 /* DetectionNet._get_scale_pred (modules/detection.py:98-173) for one scale, optionally followed by
  * _bbox_to_size (:175-190): writes the decoded tensor, same shape as raw.  inference = 0 gives the
@@ -147,18 +153,21 @@ typedef struct {
 } bg_loss_params;
 
 size_t bg_loss_workspace_bytes(const bg_loss_params *p /*host*/);
-/*   preds_* [B,ny,nx,na,5+C] f32 (training-mode decoded); targets [nt,6] f32.
+/*   preds_* [B,ny,nx,na,5+C] f32 (training-mode decoded, 16-byte aligned); targets [nt,6] f32.
  *   out_scalars [3,8] f64 per scale: lbox, lconf, lcls (NaN->0 applied), mean_ciou, avg_pos_conf,
- *                 avg_neg_conf, M, n_neg;   out_hist [3,3,C] i64: tp, n_true, n_pred per class.
- *   The workspace keeps what bg_loss_bwd needs (matches, CIoU, objectness targets).
+ *                 avg_neg_conf, M, n_neg;   out_hist [3,3,C] i64: tp, n_true, n_pred per class;
+ *   out_loss [1] f32: box_w*sum_s(scale_w*lbox) + conf_w*... + class_w*...  (:107-110).
+ *   The workspace keeps what bg_loss_bwd needs (matches, CIoU gradients, objectness residuals).
  */
 int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const float *targets,
-                const bg_loss_params *p /*host*/, double *out_scalars, int64_t *out_hist, void *workspace,
-                size_t workspace_bytes, void *stream);
-/*   grad_* [same shape as preds_*]: d(grad_out * loss)/d preds, loss as combined at :107-110. */
+                const bg_loss_params *p /*host*/, double *out_scalars, int64_t *out_hist, float *out_loss,
+                void *workspace, size_t workspace_bytes, void *stream);
+/*   grad_* [same shape as preds_*]: d(grad_out * loss)/d preds, every element written.  The upstream
+ *   gradient is read from device memory (grad_out_dev [1] f32) when non-NULL -- no host sync in
+ *   loss.backward() -- else grad_out_host is used. */
 int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const bg_loss_params *p /*host*/,
-                float grad_out, float *grad_sm, float *grad_md, float *grad_lg, void *workspace,
-                size_t workspace_bytes, void *stream);
+                const float *grad_out_dev, float grad_out_host, float *grad_sm, float *grad_md, float *grad_lg,
+                void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------ a13
  * utils/make_anchors.py:14-39 ratio_metrics / ratio_metrics_w_extras.

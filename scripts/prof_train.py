@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Profiling driver for the training side (config 3 shard): N iterations of the fused detection loss
+forward + backward through the public operator.  Run plain for CUDA-event timings, or under
+`ncu --metrics gpu__time_duration.sum` for the per-kernel launch list."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from vision_conglomerate_b200 import ops, synth  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--gt", type=int, default=100)
+ap.add_argument("--size", type=int, default=640)
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+B, S, C = a.batch, a.size, 80
+t = synth.targets(B, a.gt, C, 0).to(dev)
+g = torch.Generator(device=dev).manual_seed(1)
+preds = [torch.randn(B, ny, nx, 3, 5 + C, generator=g, device=dev).requires_grad_(True) for ny, nx in synth.fmap_shapes(S, S)]
+anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+
+
+def step():
+    for p in preds:
+        p.grad = None
+    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False)
+    loss.backward()
+    return loss
+
+
+for _ in range(a.warmup):
+    step()
+torch.cuda.synchronize()
+e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+e[0].record()
+for _ in range(a.iters):
+    for p in preds:
+        p.grad = None
+    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False)
+e[1].record()
+for _ in range(a.iters):
+    step()
+e[2].record()
+torch.cuda.synchronize()
+fwd = e[0].elapsed_time(e[1]) / a.iters
+both = e[1].elapsed_time(e[2]) / a.iters
+print("train B=%d gt=%d S=%d: fwd %.3f ms, fwd+bwd %.3f ms (%.0f img/s), loss %.6f" % (B, a.gt, S, fwd, both, B / both * 1e3, float(loss)))

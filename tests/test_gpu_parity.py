@@ -68,12 +68,13 @@ def test_nms_live_torchvision_cpu(ops):
 
 
 # ------------------------------------------------------------------------- decode + NMS (B5, a1-a8)
-def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order="image", max_mismatch=0):
+def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order="image", max_mismatch=0,
+                      nms_path="auto"):
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
     preds = O.decode_inference(raws, anc, H, W, og)
     ref = O.post_process(preds, iou, thr, allow, tracked)
     det = ops.detect([dev(r) for r in raws], anc, (H, W), C, og_size=og, iou_threshold=iou, score_threshold=thr,
-                     box_allowance=allow, tracked_classes=tracked, order=order, variant=variant)
+                     box_allowance=allow, tracked_classes=tracked, order=order, variant=variant, nms_path=nms_path)
     keep = det.keep_idxs.cpu().numpy()
     rows = det.pred_boxes.cpu().numpy()
     img = det.sample_idxs.cpu().numpy()
@@ -116,19 +117,37 @@ def test_detect_golden(ops, name, variant):
     assert np.array_equal(got[:, 1], ref_rows[:, 1])
 
 
+@pytest.mark.parametrize("nms_path", ["auto", "general"])
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,W,C,dist,og,iou,thr,allow,tracked,order", [
     (2, 96, 64, 3, "N", (120, 100), 0.5, 0.2, 4, None, "image"),        # non-square, rescale, even row length (D=8)
     (1, 96, 64, 3, "N", (96, 100), 0.5, 0.2, None, None, "global"),     # `and` guard: no rescale
     (4, 320, 320, 80, "T", None, 0.65, 0.001, 4, None, "image"),
-    (3, 320, 320, 80, "R", None, 0.65, 0.001, 4, None, "global"),       # every candidate survives (K = 6300)
+    (4, 320, 320, 80, "T", None, 0.65, 0.001, 4, None, "global"),
+    (3, 320, 320, 80, "R", None, 0.65, 0.001, 4, None, "global"),       # every candidate survives (K = 6300 > per-image cap)
+    (2, 160, 160, 80, "R", None, 0.65, 0.001, 4, None, "image"),        # K = 1575, every box overlaps its neighbours
     (5, 160, 160, 7, "N", None, 0.35, 0.3, 4, (1, 4), "image"),         # D = 12, ragged tiles, class filter
+    (3, 256, 256, 5, "N", None, 0.2, 0.05, 4, None, "image"),           # low IoU threshold: long suppression chains
     (2, 640, 640, 80, "TP", (720, 1280), 0.35, 0.3, 4, (1, 4, 7, 16, 17), "image"),  # config 5 shape
 ])
-def test_detect_oracle(ops, variant, B, H, W, C, dist, og, iou, thr, allow, tracked, order):
+def test_detect_oracle(ops, variant, nms_path, B, H, W, C, dist, og, iou, thr, allow, tracked, order):
     raws = synth.raw_head_outputs(B, H, W, C, dist, seed=7)
     K = synth.candidates_per_image(H, W) * B
-    _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order, max_mismatch=max(0, K // 5000))
+    _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order, max_mismatch=max(0, K // 5000),
+                      nms_path=nms_path)
+
+
+def test_detect_paths_agree_exactly(ops):
+    """The one-CTA-per-image NMS and the general segmented engine produce identical rows (bitwise)."""
+    B, H, W, C = 8, 640, 640, 80
+    raws = [dev(r) for r in synth.raw_head_outputs(B, H, W, C, "T", seed=11)]
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    for iou in (0.65, 0.3, 0.1):
+        a = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="auto")
+        a = [t.clone() for t in (a.pred_boxes, a.sample_idxs, a.keep_idxs, a.counts)]
+        g = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="general")
+        for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
+            assert torch.equal(x, y), iou
 
 
 def test_detect_config2_full_size(ops):

@@ -17,10 +17,12 @@ BG_MAX_ANCHORS = 8
 BG_MAX_TRACKED = 64
 STATUS_GROUP_RANGE = 1
 STATUS_MASK_SPACE = 2
+STATUS_NEED_GENERAL = 4
 
 # every symbol include/boxgeom.h declares (tests check that the library exports each of them)
 SYMBOLS = (
     "bg_strerror", "bg_version", "bg_launch_count", "bg_sizeof_detect_params", "bg_sizeof_loss_params", "bg_profile_events",
+    "bg_profile_stamps", "bg_profile_stamps_per_image",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
     "bg_detect_workspace_bytes", "bg_detect", "bg_decode_scale",
     "bg_assign_workspace_bytes", "bg_assign_targets",
@@ -44,6 +46,7 @@ class DetectParams(C.Structure):
         ("tracked", C.c_int32 * BG_MAX_TRACKED),
         ("order", C.c_int32),
         ("variant", C.c_int32),
+        ("nms_path", C.c_int32),
     ]
 
 
@@ -92,6 +95,9 @@ def lib() -> C.CDLL:
         raise RuntimeError("libboxgeom.so: parameter struct layout differs from the ctypes binding (stale build?)")
     L.bg_profile_events.argtypes = [vp, vp]
     L.bg_profile_events.restype = None
+    L.bg_profile_stamps.argtypes = [vp]
+    L.bg_profile_stamps.restype = None
+    L.bg_profile_stamps_per_image.restype = C.c_int
     L.bg_batched_nms_workspace_bytes.argtypes = [i64, i64, sz]
     L.bg_batched_nms_workspace_bytes.restype = sz
     L.bg_batched_nms.argtypes = [vp, vp, vp, i64, f64, i64, vp, vp, vp, sz, sz, vp]
@@ -106,8 +112,8 @@ def lib() -> C.CDLL:
     L.bg_ciou_bwd.argtypes = [vp, vp, vp, i64, f32, vp, vp]
     L.bg_loss_workspace_bytes.argtypes = [C.POINTER(LossParams)]
     L.bg_loss_workspace_bytes.restype = sz
-    L.bg_loss_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(LossParams), vp, vp, vp, sz, vp]
-    L.bg_loss_bwd.argtypes = [vp, vp, vp, C.POINTER(LossParams), f32, vp, vp, vp, vp, sz, vp]
+    L.bg_loss_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(LossParams), vp, vp, vp, vp, sz, vp]
+    L.bg_loss_bwd.argtypes = [vp, vp, vp, C.POINTER(LossParams), vp, f32, vp, vp, vp, vp, sz, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_decode_scale", "bg_assign_targets", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_ratio_metrics"):

@@ -7,12 +7,14 @@
 #include "common.cuh"
 #include "nms_kernels.cuh"
 #include "detect_kernels.cuh"
+#include "imgnms_kernels.cuh"
 #include "train_kernels.cuh"
 
 namespace bg {
 
 unsigned long long g_launches = 0;
 static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static unsigned long long *g_prof_stamps = nullptr;
 
 IouThr make_iou_thr(double thr)
 {
@@ -91,15 +93,51 @@ static size_t gnms_carve(unsigned char *base, long long n, long long max_groups,
     return align_up(b.off, 256);
 }
 
-struct DetWs { SegNms p; float4 *box_dense; int *cls_dense; long long stride; };
-static size_t det_carve(unsigned char *base, int B, long long N, size_t mask_bytes, DetWs &w)
+struct DetWs {
+    // decode stage (both NMS paths): per-tile survivor slots
+    int *tile_count;
+    u64 *slot_keys;
+    float4 *box_slots;
+    int *cls_slots;
+    // per-image NMS path
+    FusedHdr *hdr;
+    u64 *chain;
+    long long *f_seg_off;
+    int *f_emit_count;
+    int *cand_count;
+    u64 *f_emit_key;      // globally ordered output only
+    float4 *f_emit_box;
+    int *f_emit_cls;
+    // general path: boxes / classes by candidate index + the segmented engine
+    float4 *box_dense;
+    int *cls_dense;
+    SegNms p;
+    long long stride;
+};
+static size_t det_carve(unsigned char *base, int B, long long N, int tiles_per_image, bool general, bool global_order,
+                        size_t mask_bytes, DetWs &w)
 {
     Bump b{base, 0};
-    memset(&w.p, 0, sizeof(w.p));
+    memset(&w, 0, sizeof(w));
+    w.tile_count = b.take<int>((size_t)B * tiles_per_image);
+    w.slot_keys = b.take<u64>((size_t)B * N);
+    w.box_slots = b.take<float4>((size_t)B * N);
+    w.cls_slots = b.take<int>((size_t)B * N);
+    w.hdr = b.take<FusedHdr>(1);
+    w.chain = b.take<u64>((size_t)B + 1);
+    w.f_seg_off = b.take<long long>((size_t)B + 1);
+    w.f_emit_count = b.take<int>(B);
+    w.cand_count = b.take<int>(B);
     w.stride = (long long)next_pow2((u32)N);
-    carve_seg(b, w.p, B, (long long)B * w.stride, mask_bytes);
-    w.box_dense = b.take<float4>((size_t)B * N);
-    w.cls_dense = b.take<int>((size_t)B * N);
+    if (general) {
+        w.box_dense = b.take<float4>((size_t)B * N);
+        w.cls_dense = b.take<int>((size_t)B * N);
+        carve_seg(b, w.p, B, (long long)B * w.stride, mask_bytes);
+    } else if (global_order) {
+        w.f_emit_key = b.take<u64>((size_t)B * N);
+        w.f_emit_box = b.take<float4>((size_t)B * N);
+        w.f_emit_cls = b.take<int>((size_t)B * N);
+    }
     return align_up(b.off, 256);
 }
 
@@ -118,6 +156,41 @@ static bool det_valid(const bg_detect_params *p)
         if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
     const long long N = det_candidates(p);
     return N > 0 && N < (1ll << 31) && (long long)p->B * N < (1ll << 31);
+}
+
+static TilePlan det_tile_plan(const bg_detect_params *p)
+{
+    TilePlan tp;
+    const int D = p->C + 5;
+    int TR = (int)(DEC_TILE_BYTES / ((size_t)D * 4));
+    TR = TR > DEC_THREADS ? DEC_THREADS : (TR / 4) * 4;  // multiple of 4 rows keeps every full tile 16-byte sized
+    if (TR < 4) TR = 4;
+    tp.TR = TR;
+    tp.tpi_total = 0;
+    for (int s = 0; s < 3; ++s) {
+        const long long cells_na = (long long)p->ny[s] * p->nx[s] * p->na;
+        tp.tpi[s] = (int)((cells_na + TR - 1) / TR);
+        tp.tpi_total += tp.tpi[s];
+    }
+    tp.total = p->B * tp.tpi_total;
+    return tp;
+}
+
+// 1 = general segmented engine, 0 = one CTA per image (needs a positive threshold for the reach bound and
+// a tile list that fits the kernel's shared-memory prefix table)
+static int det_nms_path(const bg_detect_params *p, const TilePlan &tp)
+{
+    if (p->nms_path == 1) return 1;
+    const IouThr t = make_iou_thr(p->iou_threshold);
+    const bool ok = t.fast_ok && !t.zero_suppresses && t.tdn >= 0.05f && t.tdn < 1.0f && tp.tpi_total < INMS_MAXT &&
+                    det_candidates(p) <= INMS_MAX_N && p->C <= 65535;
+    if (p->nms_path == 2) return ok ? 0 : -1;
+    return ok ? 0 : 1;
+}
+
+static bool det_plan_valid(const bg_detect_params *p, const TilePlan &tp)
+{
+    return (size_t)tp.TR * (p->C + 5) * 4 <= (size_t)DEC_TILE_BYTES && (long long)p->B * tp.tpi_total < (1ll << 31);
 }
 
 }  // namespace bg
@@ -141,6 +214,8 @@ int bg_version(void) { return 100; }
 
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
+void bg_profile_stamps(void *dev_buf) { g_prof_stamps = (unsigned long long *)dev_buf; }
+int bg_profile_stamps_per_image(void) { return INMS_STAMPS; }
 size_t bg_sizeof_detect_params(void) { return sizeof(bg_detect_params); }
 size_t bg_sizeof_loss_params(void) { return sizeof(bg_loss_params); }
 
@@ -199,8 +274,11 @@ int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs,
 size_t bg_detect_workspace_bytes(const bg_detect_params *p, size_t mask_bytes)
 {
     if (!det_valid(p)) return 0;
+    const TilePlan tp = det_tile_plan(p);
+    const int path = det_nms_path(p, tp);
+    if (path < 0 || !det_plan_valid(p, tp)) return 0;
     DetWs w;
-    return det_carve(nullptr, p->B, det_candidates(p), mask_bytes, w);
+    return det_carve(nullptr, p->B, det_candidates(p), tp.tpi_total, path == 1, p->order != 0, mask_bytes, w);
 }
 
 int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *pp,
@@ -211,16 +289,12 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     if (!det_valid(pp) || !raw_sm || !raw_md || !raw_lg || !out_boxes || !out_img || !out_keep || !out_counts || !workspace)
         return BG_ERR_INVALID;
     const long long N = det_candidates(pp);
+    const TilePlan tp = det_tile_plan(pp);
+    const int path = det_nms_path(pp, tp);
+    if (path < 0 || !det_plan_valid(pp, tp)) return BG_ERR_INVALID;
     DetWs w;
-    if (det_carve((unsigned char *)workspace, pp->B, N, mask_bytes, w) > workspace_bytes) return BG_ERR_WORKSPACE;
-    SegNms &p = w.p;
-    p.boxes = w.box_dense;
-    p.box_seg_stride = N;
-    p.cls = w.cls_dense;
-    p.n_tracked = pp->n_tracked;
-    for (int i = 0; i < pp->n_tracked; ++i) p.tracked[i] = pp->tracked[i];
-    p.thr = make_iou_thr(pp->iou_threshold);
-    segnms_configure(p);
+    if (det_carve((unsigned char *)workspace, pp->B, N, tp.tpi_total, path == 1, pp->order != 0, mask_bytes, w) > workspace_bytes)
+        return BG_ERR_WORKSPACE;
 
     DetectK k;
     memset(&k, 0, sizeof(k));
@@ -248,54 +322,85 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     k.use_allowance = pp->box_allowance != 0.0f;
     k.allowance = pp->box_allowance;
     k.score_thr = pp->score_threshold;
-    k.seg_count = p.seg_count; k.seg_off = p.seg_off; k.keys = p.keys;
+    k.keys = w.slot_keys; k.box_slots = w.box_slots; k.cls_slots = w.cls_slots;
     k.box_dense = w.box_dense; k.cls_dense = w.cls_dense;
 
     const int sms = num_sms();
-    detect_init_kernel<<<(pp->B + 1 + 255) / 256, 256, 0, st>>>(p, pp->B, w.stride, out_counts);
-    BG_LAUNCH_CHECK();
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(decode_filter_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(decode_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(image_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return BG_ERR_LAUNCH;
+        }
+        attr_set = true;
+    }
 
+    // ---- decode + score filter: variant 1 forces plain loads, variant 2 insists on the TMA pipeline ----
+    if (pp->variant == 2 && !aligned) return BG_ERR_INVALID;
+    DecodeOut o;
+    o.tile_count = w.tile_count; o.hdr = w.hdr; o.chain = w.chain; o.seg_off = w.f_seg_off;
+    o.force_plain = (pp->variant == 1 || !aligned) ? 1 : 0;
     const bool prof = g_prof_start && g_prof_stop;
     if (prof) cudaEventRecord(g_prof_start, st);
-    int variant = pp->variant;
-    if (variant == 0) variant = aligned ? 2 : 1;
-    if (variant == 2 && !aligned) return BG_ERR_INVALID;
-    if (variant == 2) {
-        TileMap tm;
-        int TR = (int)(TMA_TILE_BYTES / ((size_t)k.D * 4));
-        TR = TR > TMA_THREADS ? TMA_THREADS : (TR / 4) * 4;  // multiple of 4 rows keeps every full tile 16-byte sized
-        if (TR < 4) variant = 1;
-        else {
-            tm.TR = TR;
-            tm.total = 0;
-            for (int s = 0; s < 3; ++s) { tm.tiles[s] = (int)((k.sc[s].rows + TR - 1) / TR); tm.total += tm.tiles[s]; }
-            const size_t smem = (size_t)TR * k.D * 4;
-            static bool attr_set = false;
-            if (!attr_set) {
-                if (cudaFuncSetAttribute(decode_filter_tma_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_TILE_BYTES) != cudaSuccess ||
-                    cudaFuncSetAttribute(decode_filter_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_TILE_BYTES) != cudaSuccess) {
-                    (void)cudaGetLastError();
-                    return BG_ERR_LAUNCH;
-                }
-                attr_set = true;
-            }
-            const int cap = sms * TMA_CTAS_PER_SM;
-            const int grid = tm.total < cap ? tm.total : cap;
-            if (k.C == 80) decode_filter_tma_kernel<80><<<grid, TMA_THREADS, smem, st>>>(k, tm);
-            else decode_filter_tma_kernel<0><<<grid, TMA_THREADS, smem, st>>>(k, tm);
-            BG_LAUNCH_CHECK();
-        }
-    }
-    if (variant == 1) {
-        decode_filter_warp_kernel<<<sms * 8, 256, 0, st>>>(k);
+    {
+        const int cap = sms * DEC_CTAS_PER_SM;
+        const int grid = tp.total < cap ? tp.total : cap;
+        const size_t smem = (size_t)DEC_STAGES * tp.TR * k.D * 4;
+        if (k.C == 80) decode_filter_kernel<80><<<grid, DEC_THREADS, smem, st>>>(k, tp, o);
+        else decode_filter_kernel<0><<<grid, DEC_THREADS, smem, st>>>(k, tp, o);
         BG_LAUNCH_CHECK();
     }
     if (prof) { cudaEventRecord(g_prof_stop, st); g_prof_start = g_prof_stop = nullptr; }
+
+    if (path == 0) {
+        // ---- one CTA per image: sort, grid-pruned pair tests, greedy resolution, rows ----
+        ImgNmsK q;
+        memset(&q, 0, sizeof(q));
+        q.B = pp->B; q.N = (int)N; q.TR = tp.TR; q.tpi_total = tp.tpi_total;
+        for (int s = 0; s < 3; ++s) { q.tpi[s] = tp.tpi[s]; q.img_off[s] = k.sc[s].img_off; }
+        q.tile_count = w.tile_count; q.keys = w.slot_keys; q.box_slots = w.box_slots; q.cls_slots = w.cls_slots;
+        q.thr = make_iou_thr(pp->iou_threshold);
+        q.reach = (1.0f - q.thr.tdn) / q.thr.tdn * 1.01f + 0.01f;
+        q.n_tracked = pp->n_tracked;
+        for (int i = 0; i < pp->n_tracked; ++i) q.tracked[i] = pp->tracked[i];
+        q.hdr = w.hdr; q.chain = w.chain; q.order = pp->order;
+        q.emit_key = w.f_emit_key; q.emit_box = w.f_emit_box; q.emit_cls = w.f_emit_cls;
+        q.emit_count = w.f_emit_count; q.cand_count = w.cand_count;
+        q.out_boxes = out_boxes; q.out_img = reinterpret_cast<long long *>(out_img);
+        q.out_keep = reinterpret_cast<long long *>(out_keep); q.out_counts = out_counts;
+        q.stamps = g_prof_stamps;
+        image_nms_kernel<<<pp->B, INMS_THREADS, sizeof(ImgNmsSmem), st>>>(q);
+        BG_LAUNCH_CHECK();
+        if (pp->order) {
+            SegNms v;
+            memset(&v, 0, sizeof(v));
+            v.emit_count = w.f_emit_count; v.emit_key = w.f_emit_key; v.seg_off = w.f_seg_off; v.box_seg_stride = N;
+            const int go = pp->B < 4096 ? pp->B : 4096;
+            detect_output_kernel<<<dim3(pp->B > 256 ? 1 : 8, go), 256, 0, st>>>(v, k, 1, nullptr, w.f_emit_box, w.f_emit_cls, out_boxes, reinterpret_cast<long long *>(out_img),
+                                                                           reinterpret_cast<long long *>(out_keep), out_counts);
+            BG_LAUNCH_CHECK();
+        }
+        return BG_OK;
+    }
+
+    // ---- general path: segmented engine over the compacted survivor lists ----
+    SegNms &p = w.p;
+    p.boxes = w.box_dense;
+    p.box_seg_stride = N;
+    p.cls = w.cls_dense;
+    p.n_tracked = pp->n_tracked;
+    for (int i = 0; i < pp->n_tracked; ++i) p.tracked[i] = pp->tracked[i];
+    p.thr = make_iou_thr(pp->iou_threshold);
+    segnms_configure(p);
+    detect_compact_kernel<<<pp->B < 2 * sms ? pp->B : 2 * sms, 1024, 0, st>>>(p, k, tp, w.tile_count, w.stride, out_counts);
+    BG_LAUNCH_CHECK();
     int rc = segnms_run(p, pp->B, out_counts, 1, sms, st);
     if (rc != BG_OK) return rc;
     const int go = pp->B < 4096 ? pp->B : 4096;
-    detect_output_kernel<<<dim3(pp->B > 256 ? 1 : 8, go), 256, 0, st>>>(p, k, pp->order, out_boxes, reinterpret_cast<long long *>(out_img),
-                                             reinterpret_cast<long long *>(out_keep), out_counts);
+    detect_output_kernel<<<dim3(pp->B > 256 ? 1 : 8, go), 256, 0, st>>>(p, k, pp->order, p.seg_count, nullptr, nullptr, out_boxes, reinterpret_cast<long long *>(out_img),
+                                                                   reinterpret_cast<long long *>(out_keep), out_counts);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -334,16 +439,19 @@ static void assign_fill(AssignK &k, const float *targets, long long nt, int ny, 
     k.ncand = 5ll * na * nt;
 }
 
-static int assign_launch(AssignK &k, cudaStream_t st)
+// `n` scales (all with the same target list, hence the same candidate count) in one pair of launches
+static int assign_launch(Assign3K &kk, int n, cudaStream_t st)
 {
+    const AssignK &k = kk.a[0];
     if (k.nt == 0) {
-        if (cudaMemsetAsync(k.count, 0, sizeof(int), st) != cudaSuccess) return BG_ERR_LAUNCH;
+        for (int s = 0; s < n; ++s)
+            if (cudaMemsetAsync(kk.a[s].count, 0, sizeof(int), st) != cudaSuccess) return BG_ERR_LAUNCH;
         return BG_OK;
     }
     const int nblk = (int)((k.ncand + ASSIGN_THREADS - 1) / ASSIGN_THREADS);
-    assign_count_kernel<<<nblk, ASSIGN_THREADS, 0, st>>>(k);
+    assign_count_kernel<<<dim3(nblk, n), ASSIGN_THREADS, 0, st>>>(kk);
     BG_LAUNCH_CHECK();
-    assign_emit_kernel<<<nblk, ASSIGN_THREADS, 0, st>>>(k);
+    assign_emit_kernel<<<dim3(nblk, n), ASSIGN_THREADS, 0, st>>>(kk);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -366,13 +474,15 @@ int bg_assign_targets(const float *targets, int64_t nt, int32_t ny, int32_t nx, 
         return BG_ERR_INVALID;
     if (out_box && (((uintptr_t)out_box & 15) != 0)) return BG_ERR_INVALID;
     if (workspace_bytes < bg_assign_workspace_bytes(nt, na)) return BG_ERR_WORKSPACE;
-    AssignK k;
+    Assign3K kk;
+    AssignK &k = kk.a[0];
     assign_fill(k, targets, nt, ny, nx, anchors, na, anchor_t, edge_t);
     k.block_counts = (int *)workspace;
     k.idx4 = reinterpret_cast<long long *>(out_idx4);
     k.cls64 = reinterpret_cast<long long *>(out_cls);
     k.anchor = out_anchor; k.box = out_box; k.cap = cap; k.count = out_count;
-    return assign_launch(k, (cudaStream_t)stream);
+    kk.a[1] = kk.a[2] = k;
+    return assign_launch(kk, 1, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------ B2
@@ -400,23 +510,25 @@ int bg_ciou_bwd(const float *p, const float *t, const float *go, int64_t M, floa
 namespace {
 struct LossWs {
     int *block_counts[3];
-    int *M[3];
+    int *M;               // [3]
     int *cell[3];
     int *cls[3];
     float *anchor[3];
     float *box[3];
     float *ciou[3];
-    int *winner[3];
+    float4 *gbox[3];
+    int *winner;          // all scales, contiguous (one memset)
+    float *gobj;          // all scales, contiguous
     double *part_match[3];
     double *part_dense[3];
     long long cap;
-    long long cells[3];
+    long long cells[3], cell_off[3], cells_total;
     int nblk_match, nblk_dense;
 };
 
 bool loss_valid(const bg_loss_params *p)
 {
-    if (!p || p->B <= 0 || p->C <= 0 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->nt < 0) return false;
+    if (!p || p->B <= 0 || p->C <= 0 || p->C > 4096 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->nt < 0) return false;
     if (5ll * p->na * p->nt >= (1ll << 31)) return false;
     for (int s = 0; s < 3; ++s) {
         if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
@@ -432,35 +544,50 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     const int sms = num_sms();
     w.cap = 5ll * p->na * p->nt;
     if (w.cap < 1) w.cap = 1;
-    w.nblk_match = sms * 8;
+    w.nblk_match = sms * 4;
     w.nblk_dense = sms * 8;
     const size_t nblk_assign = (size_t)((w.cap + ASSIGN_THREADS - 1) / ASSIGN_THREADS + 1);
+    w.cells_total = 0;
     for (int s = 0; s < 3; ++s) {
         w.cells[s] = (long long)p->B * p->ny[s] * p->nx[s] * p->na;
+        w.cell_off[s] = w.cells_total;
+        w.cells_total += w.cells[s];
+    }
+    w.M = b.take<int>(4);
+    w.winner = b.take<int>(w.cells_total);
+    w.gobj = b.take<float>(w.cells_total);
+    for (int s = 0; s < 3; ++s) {
         w.block_counts[s] = b.take<int>(nblk_assign);
-        w.M[s] = b.take<int>(1);
         w.cell[s] = b.take<int>(w.cap);
         w.cls[s] = b.take<int>(w.cap);
         w.anchor[s] = b.take<float>(2 * w.cap);
         w.box[s] = b.take<float>(4 * w.cap);
         w.ciou[s] = b.take<float>(w.cap);
-        w.winner[s] = b.take<int>(w.cells[s]);
+        w.gbox[s] = b.take<float4>(w.cap);
         w.part_match[s] = b.take<double>((size_t)w.nblk_match * 4);
         w.part_dense[s] = b.take<double>((size_t)w.nblk_dense * 3);
     }
     return align_up(b.off, 256);
 }
 
-void loss_fill(LossScaleK &k, const bg_loss_params *p, const LossWs &w, int s, const float *preds, float *grad)
+void loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const float *const preds[3], float *const grads[3])
 {
     memset(&k, 0, sizeof(k));
-    k.preds = preds; k.grad = grad; k.cells = w.cells[s]; k.C = p->C; k.D = p->C + 5;
-    k.M = w.M[s]; k.cell = w.cell[s]; k.cls = w.cls[s]; k.anchor = w.anchor[s]; k.box = w.box[s];
-    k.ciou = w.ciou[s]; k.winner = w.winner[s]; k.part_match = w.part_match[s]; k.part_dense = w.part_dense[s];
-    k.cn = 0.5f * p->label_smoothing;  // python: cn = 0.5*ls (double), written into an fp32 tensor
+    k.C = p->C; k.D = p->C + 5;
+    // python: cn = 0.5 * label_smoothing, cp = 1 - cn in double, written into fp32 tensors (detection_loss.py:191-195)
     k.cn = (float)(0.5 * (double)p->label_smoothing);
     k.cp = (float)(1.0 - 0.5 * (double)p->label_smoothing);
     k.nblk_match = w.nblk_match; k.nblk_dense = w.nblk_dense;
+    k.box_w = p->box_w; k.conf_w = p->conf_w; k.class_w = p->class_w;
+    for (int s = 0; s < 3; ++s) {
+        LossScale &S = k.s[s];
+        S.preds = preds[s]; S.grad = grads ? grads[s] : nullptr; S.cells = w.cells[s];
+        S.M = w.M + s; S.cell = w.cell[s]; S.cls = w.cls[s]; S.anchor = w.anchor[s]; S.box = w.box[s];
+        S.ciou = w.ciou[s]; S.gbox = w.gbox[s];
+        S.winner = w.winner + w.cell_off[s]; S.gobj = w.gobj + w.cell_off[s];
+        S.part_match = w.part_match[s]; S.part_dense = w.part_dense[s];
+        S.scale_w = p->scale_w[s];
+    }
 }
 }  // namespace
 
@@ -472,65 +599,67 @@ size_t bg_loss_workspace_bytes(const bg_loss_params *p)
 }
 
 int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const float *targets,
-                const bg_loss_params *p, double *out_scalars, int64_t *out_hist, void *workspace,
+                const bg_loss_params *p, double *out_scalars, int64_t *out_hist, float *out_loss, void *workspace,
                 size_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!loss_valid(p) || !preds_sm || !preds_md || !preds_lg || !out_scalars || !out_hist || !workspace) return BG_ERR_INVALID;
+    if (!loss_valid(p) || !preds_sm || !preds_md || !preds_lg || !out_scalars || !out_hist || !out_loss || !workspace)
+        return BG_ERR_INVALID;
     if (p->nt > 0 && !targets) return BG_ERR_INVALID;
+    if (((uintptr_t)preds_sm | (uintptr_t)preds_md | (uintptr_t)preds_lg) & 15) return BG_ERR_INVALID;
     LossWs w;
     if (loss_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
     const float *preds[3] = {preds_sm, preds_md, preds_lg};
     if (cudaMemsetAsync(out_hist, 0, sizeof(int64_t) * 9 * (size_t)p->C, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (cudaMemsetAsync(w.winner, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    Assign3K a3;
     for (int s = 0; s < 3; ++s) {
-        AssignK a;
+        AssignK &a = a3.a[s];
         float anc[2 * BG_MAX_ANCHORS];
         for (int q = 0; q < p->na; ++q) { anc[2 * q] = p->anchors[s][q][0]; anc[2 * q + 1] = p->anchors[s][q][1]; }
         assign_fill(a, targets, p->nt, p->ny[s], p->nx[s], anc, p->na, p->anchor_t, p->edge_t);
         a.block_counts = w.block_counts[s];
         a.anchor = w.anchor[s]; a.box = w.box[s]; a.cell = w.cell[s]; a.cls32 = w.cls[s];
-        a.cap = w.cap; a.count = w.M[s];
-        int rc = assign_launch(a, st);
-        if (rc != BG_OK) return rc;
-        if (cudaMemsetAsync(w.winner[s], 0xff, sizeof(int) * (size_t)w.cells[s], st) != cudaSuccess) return BG_ERR_LAUNCH;
-        LossScaleK k;
-        loss_fill(k, p, w, s, preds[s], nullptr);
-        k.hist = reinterpret_cast<long long *>(out_hist) + (size_t)s * 3 * p->C;
-        k.scalars = out_scalars + 8 * s;
-        loss_match_kernel<<<w.nblk_match, LOSS_THREADS, 0, st>>>(k);
-        BG_LAUNCH_CHECK();
-        loss_dense_kernel<<<w.nblk_dense, LOSS_THREADS, 0, st>>>(k);
-        BG_LAUNCH_CHECK();
-        loss_finalize_kernel<<<1, 256, 0, st>>>(k);
-        BG_LAUNCH_CHECK();
+        a.cap = w.cap; a.count = w.M + s;
     }
+    int rc = assign_launch(a3, 3, st);
+    if (rc != BG_OK) return rc;
+    Loss3K k;
+    loss_fill(k, p, w, preds, nullptr);
+    for (int s = 0; s < 3; ++s) k.s[s].hist = reinterpret_cast<long long *>(out_hist) + (size_t)s * 3 * p->C;
+    k.scalars = out_scalars;
+    k.loss_out = out_loss;
+    loss_match_kernel<<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
+    BG_LAUNCH_CHECK();
+    loss_dense_kernel<<<dim3(w.nblk_dense, 3), LOSS_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    loss_finalize_kernel<<<1, 256, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
     return BG_OK;
 }
 
 int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const bg_loss_params *p,
-                float grad_out, float *grad_sm, float *grad_md, float *grad_lg, void *workspace,
-                size_t workspace_bytes, void *stream)
+                const float *grad_out_dev, float grad_out_host, float *grad_sm, float *grad_md, float *grad_lg,
+                void *workspace, size_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!loss_valid(p) || !preds_sm || !preds_md || !preds_lg || !grad_sm || !grad_md || !grad_lg || !workspace)
+        return BG_ERR_INVALID;
+    if (((uintptr_t)preds_sm | (uintptr_t)preds_md | (uintptr_t)preds_lg | (uintptr_t)grad_sm | (uintptr_t)grad_md | (uintptr_t)grad_lg) & 15)
         return BG_ERR_INVALID;
     LossWs w;
     if (loss_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
     const float *preds[3] = {preds_sm, preds_md, preds_lg};
     float *grads[3] = {grad_sm, grad_md, grad_lg};
+    Loss3K k;
+    loss_fill(k, p, w, preds, grads);
+    k.go_dev = grad_out_dev;
+    k.go_host = grad_out_host;
     const int sms = num_sms();
-    for (int s = 0; s < 3; ++s) {
-        LossScaleK k;
-        loss_fill(k, p, w, s, preds[s], grads[s]);
-        const double sw = (double)p->scale_w[s] * (double)grad_out;
-        k.w_box = (double)p->box_w * sw;
-        k.w_conf = (double)p->conf_w * sw;
-        k.w_cls = (double)p->class_w * sw;
-        loss_bwd_dense_kernel<<<sms * 16, 256, 0, st>>>(k);
-        BG_LAUNCH_CHECK();
-        loss_bwd_match_kernel<<<sms * 8, LOSS_THREADS, 0, st>>>(k);
-        BG_LAUNCH_CHECK();
-    }
+    loss_bwd_dense_kernel<<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    loss_bwd_dup_kernel<<<dim3(sms * 2, 3), LOSS_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
     return BG_OK;
 }
 

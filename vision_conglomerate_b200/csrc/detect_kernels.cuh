@@ -28,12 +28,14 @@ struct DetectK {
     int use_allowance;
     float allowance;
     float score_thr;
-    // outputs of the filter stage
-    int *seg_count;          // [B] survivors per image (atomic slots)
-    const long long *seg_off;
-    u64 *keys;
-    float4 *box_dense;       // [B*N] xyxy of survivors, at b*N + idx
-    int *cls_dense;          // [B*N]
+    // outputs of the filter stage (see decode_filter_kernel): the survivors of a tile sit, in candidate order,
+    // in the tile's own slots b*N + (first candidate of the tile) + j
+    u64 *keys;               // [B*N] sort keys (score desc, candidate index asc)
+    float4 *box_slots;       // [B*N] xyxy
+    int *cls_slots;          // [B*N] class id
+    // general NMS path only: the same data addressed by candidate index b*N + idx (filled by detect_compact_kernel)
+    float4 *box_dense;
+    int *cls_dense;
 };
 
 // Decode one candidate's box to xyxy (image or original-frame pixels).
@@ -64,108 +66,46 @@ __device__ __forceinline__ float4 decode_xyxy(const DetectK &k, const ScaleDesc 
 // cannot share its sigmoid (ulp(p) <= 1.2e-7*p and sigmoid' = p(1-p)); p == 1 gives an infinite window.
 __device__ __forceinline__ float tie_window(float pm) { return __fdividef(5e-7f, 1.0f - pm); }
 
-__device__ __forceinline__ void row_coords(const ScaleDesc &s, int na, long long row, int &b, int &x, int &y, int &a,
-                                           int &idx)
+// ---------------------------------------------------------------------------------------------
+// tile plan: the three head tensors are cut into tiles of TR candidate rows that never straddle an
+// image; tile t = b * tpi_total + r, r running over (scale, tile inside the image's slice).
+// ---------------------------------------------------------------------------------------------
+struct TilePlan {
+    int TR;          // rows per tile (multiple of 4, <= DEC_THREADS)
+    int tpi[3];      // tiles per image on each scale
+    int tpi_total;   // tiles per image
+    int total;       // B * tpi_total
+};
+
+__host__ __device__ inline void tile_locate(const DetectK &k, const TilePlan &tp, int t, int &b, int &si, int &lrow0,
+                                            int &rows)
 {
-    b = (int)(row / s.cells_na);
-    const int rl = (int)(row - (long long)b * s.cells_na);
-    a = rl % na;
-    const int cell = rl / na;
-    x = cell % s.nx;
-    y = cell / s.nx;
-    idx = s.img_off + rl;
+    b = t / tp.tpi_total;
+    int r = t - b * tp.tpi_total;
+    si = 0;
+    if (r >= tp.tpi[0]) { r -= tp.tpi[0]; si = 1; if (r >= tp.tpi[1]) { r -= tp.tpi[1]; si = 2; } }
+    lrow0 = r * tp.TR;
+    const int rem = k.sc[si].cells_na - lrow0;
+    rows = rem < tp.TR ? rem : tp.TR;
 }
 
 // ---------------------------------------------------------------------------------------------
-// init: header, per-image counters and fixed segment offsets
+// decode + score + threshold + per-tile compaction.
+// Persistent CTAs (DEC_CTAS_PER_SM per SM), each owning a ring of DEC_STAGES shared-memory tile
+// buffers filled by TMA bulk copies (cp.async.bulk + mbarrier): while a tile is being processed the
+// next DEC_STAGES-1 tiles of the CTA are already in flight, so every SM keeps >= 2 x 43.5 KB of
+// reads outstanding (HBM latency x bandwidth needs ~45 KB per SM).
+//   phase 1  one thread per row: class maximum and score from shared memory (row stride D = 5+C
+//            words, conflict-free when D is odd), strict threshold, survivors listed in smem;
+//   phase 2a one warp per survivor: class id (first index whose sigmoid equals the maximum sigmoid);
+//   phase 2b one thread per survivor: box decode, coalesced writes.
+// Survivors of tile t go to the tile's own slots (b*N + first candidate of the tile + j, candidate order)
+// and their count to tile_count[t]: no global atomics, nothing to zero between calls.
 // ---------------------------------------------------------------------------------------------
-__global__ void detect_init_kernel(SegNms p, int B, long long seg_stride, int32_t *out_counts)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        SegHdr h;
-        h.S = B; h.status = 0; h.item_ctr = 0; h.reduce_done = 0; h.gmin = 0; h.gmax = 0; h.total_out = 0;
-        h.pad[0] = h.pad[1] = h.pad[2] = 0;
-        *p.hdr = h;
-        out_counts[0] = 0;
-        out_counts[1] = 0;
-    }
-    if (i < B) p.seg_count[i] = 0;
-    if (i <= B) p.seg_off[i] = (long long)i * seg_stride;
-}
-
-// ---------------------------------------------------------------------------------------------
-// variant 1: one warp per candidate row, plain coalesced loads
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) decode_filter_warp_kernel(DetectK k)
-{
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long total = k.sc[0].rows + k.sc[1].rows + k.sc[2].rows;
-    const int C = k.C, D = k.D;
-    for (long long g = warp; g < total; g += nwarps) {
-        int si = 0;
-        long long row = g;
-        if (row >= k.sc[0].rows) { row -= k.sc[0].rows; si = 1; }
-        if (si == 1 && row >= k.sc[1].rows) { row -= k.sc[1].rows; si = 2; }
-        const ScaleDesc &s = k.sc[si];
-        const float *rp = s.raw + row * D;
-        float m = -INFINITY;
-        float obj = 0.f, t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-        for (int e = lane; e < D; e += 32) {
-            const float v = __ldg(rp + e);
-            if (e == 0) obj = v;
-            else if (e <= C) m = fmaxf(m, v);
-            else if (e == C + 1) t0 = v;
-            else if (e == C + 2) t1 = v;
-            else if (e == C + 3) t2 = v;
-            else t3 = v;
-        }
-        // max logit across the warp (sigmoid is monotone: max_c sig(cls_c) == sig(max_c cls_c))
-        float wm = m;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        obj = __shfl_sync(0xffffffffu, obj, 0);
-        const float pm = sigmoid_acc(wm);
-        const float score = __fmul_rn(pm, sigmoid_acc(obj));
-        if (!(score > k.score_thr)) continue;  // warp-uniform
-        // class id = first index whose sigmoid equals the maximum sigmoid (torch argmax over probabilities)
-        int ci = 0x7fffffff;
-        const float win = tie_window(pm);
-        for (int e = 1 + lane; e <= C; e += 32) {
-            const float v = __ldg(rp + e);
-            if (v == wm || (v >= wm - win && sigmoid_acc(v) == pm)) { ci = min(ci, e - 1); }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ci = min(ci, __shfl_xor_sync(0xffffffffu, ci, o));
-        t0 = __shfl_sync(0xffffffffu, t0, (C + 1) & 31);
-        t1 = __shfl_sync(0xffffffffu, t1, (C + 2) & 31);
-        t2 = __shfl_sync(0xffffffffu, t2, (C + 3) & 31);
-        t3 = __shfl_sync(0xffffffffu, t3, (C + 4) & 31);
-        if (lane == 0) {
-            int b, x, y, a, idx;
-            row_coords(s, k.na, row, b, x, y, a, idx);
-            const float4 bx = decode_xyxy(k, s, t0, t1, t2, t3, x, y, a);
-            const int slot = atomicAdd(&k.seg_count[b], 1);
-            k.keys[k.seg_off[b] + slot] = make_key(score, (u32)idx);
-            k.box_dense[(long long)b * k.N + idx] = bx;
-            k.cls_dense[(long long)b * k.N + idx] = ci;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// variant 2: persistent CTAs, several per SM, each streaming tiles of TR candidate rows into shared
-// memory with one TMA bulk copy (cp.async.bulk + mbarrier) per tile.  Phase 1: one thread per row
-// takes the class maximum and the score from shared memory (row stride D = 5+C words: conflict-free
-// when D is odd, e.g. 85) and the survivors of the threshold are compacted into a small list;
-// phase 2: one thread per *survivor* finds the class id, decodes the box and writes the candidate.
-// The co-resident CTAs of an SM overlap each other's copy latency (4 x 43.5 KB in flight per SM).
-// ---------------------------------------------------------------------------------------------
-constexpr int TMA_THREADS = 128;
-constexpr int TMA_CTAS_PER_SM = 4;
-constexpr int TMA_TILE_BYTES = 44 * 1024;
+constexpr int DEC_THREADS = 128;
+constexpr int DEC_STAGES = 2;
+constexpr int DEC_CTAS_PER_SM = 2;
+constexpr int DEC_TILE_BYTES = 43520;  // 128 rows x 85 floats
 
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
@@ -195,59 +135,88 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, u32 bytes, 
                  : "memory");
 }
 
-struct TileMap { int tiles[3]; int total; int TR; };
+struct Surv { int row; float score, wm, pm; int ci; };
 
-__device__ __forceinline__ void tile_locate(const DetectK &k, const TileMap &tm, int tile, int &si, long long &row0,
-                                            int &rows)
-{
-    si = 0;
-    int t = tile;
-    if (t >= tm.tiles[0]) { t -= tm.tiles[0]; si = 1; }
-    if (si == 1 && t >= tm.tiles[1]) { t -= tm.tiles[1]; si = 2; }
-    row0 = (long long)t * tm.TR;
-    const long long rem = k.sc[si].rows - row0;
-    rows = rem < tm.TR ? (int)rem : tm.TR;
-}
+struct FusedHdr {            // scratch of the fused path, (re)initialised by the decode kernel of every call
+    unsigned ticket;         // image scheduler of image_nms_kernel
+    unsigned done;           // images finished
+    int status;              // BG_STATUS_* bits
+    int pad;
+};
+// per-image words of the output-offset look-back chain (word 0 = prefix 0, word b+1 = image b)
+constexpr u64 CHAIN_PREFIX = 1ull << 63;  // value = rows emitted by images <= b
+constexpr u64 CHAIN_AGG = 1ull << 62;     // value = rows emitted by image b alone
+constexpr u64 CHAIN_VALUE = (1ull << 62) - 1;
 
-struct Surv { int row; float score, wm, pm; };
+struct DecodeOut {
+    int *tile_count;         // [B * tpi_total]
+    FusedHdr *hdr;
+    u64 *chain;              // [B+1] look-back words
+    long long *seg_off;      // [B+1] b*N (row offset of the image's emit list)
+    int force_plain;         // 1: never use TMA (unaligned inputs, variant 1)
+};
 
 template <int CT>  // compile-time class count (fully unrolled row scan); 0 = take it from the parameters
-__global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS_PER_SM) decode_filter_tma_kernel(DetectK k, TileMap tm)
+__global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_kernel(DetectK k, TilePlan tp, DecodeOut o)
 {
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    __shared__ __align__(8) u64 full_bar;
-    __shared__ Surv s_surv[TMA_THREADS];
-    __shared__ int s_n;
+    extern __shared__ __align__(128) unsigned char dec_smem[];
+    __shared__ __align__(8) u64 full_bar[DEC_STAGES];
+    __shared__ Surv s_surv[DEC_THREADS];
+    __shared__ int s_wcnt[DEC_THREADS / 32];
     const int C = CT ? CT : k.C;
     const int D = C + 5;
-    float *tile = reinterpret_cast<float *>(tma_smem);
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int stage_floats = tp.TR * D;
+    float *ring = reinterpret_cast<float *>(dec_smem);
+
+    // scratch of the per-image NMS kernel that follows in the stream
+    if (blockIdx.x == 0) {
+        if (tid == 0) { o.hdr->ticket = 0; o.hdr->done = 0; o.hdr->status = 0; o.hdr->pad = 0; }
+        for (int b = tid; b <= k.B; b += DEC_THREADS) {
+            o.chain[b] = (b == 0) ? CHAIN_PREFIX : 0ull;
+            o.seg_off[b] = (long long)b * k.N;
+        }
+    }
+
+    auto tile_src = [&](int t, int &b, int &si, int &lrow0, int &rows) -> const float * {
+        tile_locate(k, tp, t, b, si, lrow0, rows);
+        return k.sc[si].raw + ((long long)b * k.sc[si].cells_na + lrow0) * D;
+    };
+    auto tma_ok = [&](const float *src, int rows) -> bool {
+        return !o.force_plain && (((rows * D) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    };
 
     if (tid == 0) {
-        mbar_init(&full_bar, 1);
+        for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_n = 0;
+        for (int s = 0; s < DEC_STAGES; ++s) {  // prologue: fill the ring
+            const int t = blockIdx.x + s * gridDim.x;
+            if (t < tp.total) {
+                int b, si, lrow0, rows;
+                const float *src = tile_src(t, b, si, lrow0, rows);
+                if (tma_ok(src, rows)) {
+                    mbar_expect_tx(&full_bar[s], (u32)(rows * D) * 4);
+                    bulk_g2s(ring + (size_t)s * stage_floats, src, (u32)(rows * D) * 4, &full_bar[s]);
+                }
+            }
+        }
     }
     __syncthreads();
 
-    u32 parity = 0;
-    for (int t = blockIdx.x; t < tm.total; t += gridDim.x) {
-        int si, rows;
-        long long row0;
-        tile_locate(k, tm, t, si, row0, rows);
+    u32 phases = 0;  // bit s = parity the next wait on stage s expects
+    int it = 0;
+    for (int t = blockIdx.x; t < tp.total; t += gridDim.x, ++it) {
+        const int stage = it % DEC_STAGES;
+        float *tile = ring + (size_t)stage * stage_floats;
+        int b, si, lrow0, rows;
+        const float *src = tile_src(t, b, si, lrow0, rows);
         const ScaleDesc &s = k.sc[si];
-        const float *src = s.raw + row0 * D;
-        const int nfl = rows * D;
-        if ((nfl & 3) == 0) {  // the tile is a whole number of 16-byte units: one bulk copy
-            if (tid == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the tile buffer
-                mbar_expect_tx(&full_bar, (u32)nfl * 4);
-                bulk_g2s(tile, src, (u32)nfl * 4, &full_bar);
-            }
-            mbar_wait(&full_bar, parity);
-            parity ^= 1;
-        } else {  // ragged last tile of a scale: plain coalesced loads
-            for (int i = tid; i < nfl; i += TMA_THREADS) tile[i] = __ldg(src + i);
+        if (tma_ok(src, rows)) {
+            mbar_wait(&full_bar[stage], (phases >> stage) & 1u);
+            phases ^= 1u << stage;
+        } else {  // ragged / unaligned tile: plain coalesced loads
+            const int nfl = rows * D;
+            for (int i = tid; i < nfl; i += DEC_THREADS) tile[i] = __ldg(src + i);
             __syncthreads();
         }
 
@@ -278,79 +247,174 @@ __global__ void __launch_bounds__(TMA_THREADS, TMA_CTAS_PER_SM) decode_filter_tm
             score = __fmul_rn(pm, sigmoid_acc(sr[0]));
             alive = score > k.score_thr;
         }
-        {   // compact the survivors of this tile (order inside the list is irrelevant)
-            const u32 am = __ballot_sync(0xffffffffu, alive);
-            int base = 0;
-            if (am) {
-                const int leader = __ffs(am) - 1;
-                if (lane == leader) base = atomicAdd(&s_n, __popc(am));
-                base = __shfl_sync(0xffffffffu, base, leader);
+        // list the survivors of this tile in row order (warp ballots + a prefix over the four warps), so that
+        // slot order == candidate order and ties in score keep torchvision's lower-index-first rule downstream
+        const u32 am = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) s_wcnt[wid] = __popc(am);
+        __syncthreads();
+        int base = 0, n = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < DEC_THREADS / 32; ++w2) {
+            const int c = s_wcnt[w2];
+            if (w2 < wid) base += c;
+            n += c;
+        }
+        if (alive) s_surv[base + __popc(am & lanemask_lt())] = Surv{tid, score, wm, pm, 0};
+        __syncthreads();
+
+        // phase 2a: one warp per survivor -- class id = first index whose sigmoid equals the maximum sigmoid
+        for (int q = wid; q < n; q += DEC_THREADS / 32) {
+            const float swm = s_surv[q].wm, spm = s_surv[q].pm;
+            const float *sr = tile + s_surv[q].row * D + 1;
+            const float lo = swm - tie_window(spm);
+            int ci = 0;
+            for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                bool hit = false;
+                if (c < C) {
+                    const float v = sr[c];
+                    hit = v >= lo && (v == swm || sigmoid_acc(v) == spm);
+                }
+                const u32 hm = __ballot_sync(0xffffffffu, hit);
+                if (hm) { ci = c0 + __ffs(hm) - 1; break; }
             }
-            if (alive) s_surv[base + __popc(am & lanemask_lt())] = Surv{tid, score, wm, pm};
+            if (lane == 0) s_surv[q].ci = ci;
         }
         __syncthreads();
-        const int n = s_n;
 
-        // phase 2: one thread per survivor -- class id, box decode, per-image slot, writes
-        for (int q0 = 0; q0 < n; q0 += TMA_THREADS) {
-            const int q = q0 + tid;
-            const bool act = q < n;
-            const u32 amask = __ballot_sync(0xffffffffu, act);
-            if (act) {
-                const Surv sv = s_surv[q];
-                const float *sr = tile + sv.row * D;
-                int ci = 0;
-                const float lo = sv.wm - tie_window(sv.pm);
-                for (int c = 0; c < C; ++c) {
-                    const float v = sr[1 + c];
-                    if (v >= lo && (v == sv.wm || sigmoid_acc(v) == sv.pm)) { ci = c; break; }
-                }
-                int b, x, y, a, idx;
-                row_coords(s, k.na, row0 + sv.row, b, x, y, a, idx);
-                const float4 bx = decode_xyxy(k, s, sr[C + 1], sr[C + 2], sr[C + 3], sr[C + 4], x, y, a);
-                // warp-aggregated slot allocation, one atomic per (warp, image)
-                const u32 peers = __match_any_sync(amask, b);
-                const int leader = __ffs(peers) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(&k.seg_count[b], __popc(peers));
-                base = __shfl_sync(peers, base, leader);
-                const int slot = base + __popc(peers & lanemask_lt());
-                k.keys[k.seg_off[b] + slot] = make_key(sv.score, (u32)idx);
-                k.box_dense[(long long)b * k.N + idx] = bx;
-                k.cls_dense[(long long)b * k.N + idx] = ci;
-            }
+        // phase 2b: one thread per survivor -- box decode and writes
+        if (tid == 0) o.tile_count[t] = n;
+        if (tid < n) {
+            const Surv sv = s_surv[tid];
+            const float *sr = tile + sv.row * D;
+            const int rl = lrow0 + sv.row;
+            const int a = rl % k.na, cell = rl / k.na;
+            const int x = cell % s.nx, y = cell / s.nx;
+            const int idx = s.img_off + rl;
+            const float4 bx = decode_xyxy(k, s, sr[C + 1], sr[C + 2], sr[C + 3], sr[C + 4], x, y, a);
+            const long long slot = (long long)b * k.N + s.img_off + lrow0 + tid;
+            k.keys[slot] = make_key(sv.score, (u32)idx);
+            k.box_slots[slot] = bx;
+            k.cls_slots[slot] = sv.ci;
         }
         __syncthreads();  // the tile buffer and the survivor list are free again
-        if (tid == 0) s_n = 0;  // ordered before the next phase 1 by the mbarrier (release/acquire) or the barrier above
+
+        if (tid == 0) {   // refill this stage with the tile DEC_STAGES iterations ahead
+            const int tn = t + DEC_STAGES * gridDim.x;
+            if (tn < tp.total) {
+                int b2, si2, l2, r2;
+                const float *src2 = tile_src(tn, b2, si2, l2, r2);
+                if (tma_ok(src2, r2)) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer above
+                    mbar_expect_tx(&full_bar[stage], (u32)(r2 * D) * 4);
+                    bulk_g2s(tile, src2, (u32)(r2 * D) * 4, &full_bar[stage]);
+                }
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// row assembly after NMS: pred_boxes = [score, class, x1,y1,x2,y2], sample index, flat keep index
+// row assembly after NMS from the per-image emit lists (general NMS path, and the globally ordered
+// output of the fused path): pred_boxes = [score, class, x1,y1,x2,y2], sample index, flat keep index
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) detect_output_kernel(SegNms p, DetectK k, int order, float *out_boxes,
-                                                            long long *out_img, long long *out_keep,
+__global__ void __launch_bounds__(256) detect_output_kernel(SegNms p, DetectK k, int order, const int *cand_count,
+                                                            const float4 *emit_box, const int *emit_cls,
+                                                            float *out_boxes, long long *out_img, long long *out_keep,
                                                             int32_t *out_counts)
 {
     const int S = k.B;
     for (int seg = blockIdx.y; seg < S; seg += gridDim.y) {
         const int cnt = p.emit_count[seg];
         const long long off = p.seg_off[seg];
-        const long long base = p.out_prefix[seg];
-        if (threadIdx.x == 0 && blockIdx.x == 0) out_counts[2 + S + seg] = p.seg_count[seg];
+        const long long base = order ? 0 : p.out_prefix[seg];
+        if (cand_count && threadIdx.x == 0 && blockIdx.x == 0) out_counts[2 + S + seg] = cand_count[seg];
         for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt; r += gridDim.x * blockDim.x) {
             const u64 key = p.emit_key[off + r];
-            const u32 pos = p.emit_pos[off + r];
             const u32 id = key_id(key);
-            const float4 b = p.sorted_box[off + pos];
+            // box / class of the row: emit-list aligned (per-image NMS path) or by candidate index (general path)
+            const float4 b = emit_box ? emit_box[off + r] : k.box_dense[(long long)seg * k.N + id];
+            const int cl = emit_cls ? emit_cls[off + r] : k.cls_dense[(long long)seg * k.N + id];
             const long long dst = order ? segnms_global_rank(p, S, seg, r, key) : base + r;
             float *o = out_boxes + dst * 6;
             o[0] = key_score(key);
-            o[1] = (float)k.cls_dense[(long long)seg * k.N + id];
+            o[1] = (float)cl;
             o[2] = b.x; o[3] = b.y; o[4] = b.z; o[5] = b.w;
             out_img[dst] = seg;
             out_keep[dst] = (long long)seg * k.N + id;
         }
+    }
+}
+
+// general NMS path: gather the tile slots of every image into the segment layout of the segmented NMS
+// engine (keys of image b compacted at seg_off[b] = b * seg_stride) and initialise its header.
+__global__ void __launch_bounds__(1024) detect_compact_kernel(SegNms p, DetectK k, TilePlan tp, const int *tile_count,
+                                                              long long seg_stride, int32_t *out_counts)
+{
+    __shared__ int s_pref[1025];
+    __shared__ int s_wsum[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (blockIdx.x == 0 && tid == 0) {
+        SegHdr h;
+        h.S = k.B; h.status = 0; h.item_ctr = 0; h.reduce_done = 0; h.gmin = 0; h.gmax = 0; h.total_out = 0;
+        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        *p.hdr = h;
+        out_counts[0] = 0;
+        out_counts[1] = 0;
+    }
+    if (blockIdx.x == 0)
+        for (int b = tid; b <= k.B; b += 1024) p.seg_off[b] = (long long)b * seg_stride;
+    for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
+        if (tid == 0) s_carry = 0;
+        __syncthreads();
+        u64 *dst = p.keys + (long long)b * seg_stride;
+        for (int r0 = 0; r0 < tp.tpi_total; r0 += 1024) {
+            const int r = r0 + tid;
+            const int c = (r < tp.tpi_total) ? tile_count[(long long)b * tp.tpi_total + r] : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                int w = s_wsum[lane], winc = w;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, winc, o);
+                    if (lane >= o) winc += u;
+                }
+                s_wsum[lane] = winc - w;
+            }
+            __syncthreads();
+            const int carry = s_carry;
+            s_pref[tid] = carry + s_wsum[wid] + inc - c;
+            if (tid == 1023) s_pref[1024] = carry + s_wsum[wid] + inc;
+            __syncthreads();
+            // one warp per tile: coalesced copy of its slots
+            const int nt = min(1024, tp.tpi_total - r0);
+            for (int q = wid; q < nt; q += 32) {
+                const int rr = r0 + q;
+                int si = 0, lr = rr;
+                if (lr >= tp.tpi[0]) { lr -= tp.tpi[0]; si = 1; if (lr >= tp.tpi[1]) { lr -= tp.tpi[1]; si = 2; } }
+                const long long src = (long long)b * k.N + k.sc[si].img_off + (long long)lr * tp.TR;
+                const int o0 = s_pref[q], cnt = s_pref[q + 1] - o0;
+                for (int j = lane; j < cnt; j += 32) {
+                    const u64 key = k.keys[src + j];
+                    dst[o0 + j] = key;
+                    k.box_dense[(long long)b * k.N + key_id(key)] = k.box_slots[src + j];
+                    k.cls_dense[(long long)b * k.N + key_id(key)] = k.cls_slots[src + j];
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_carry = s_pref[1024];
+            __syncthreads();
+        }
+        if (tid == 0) p.seg_count[b] = s_carry;
+        __syncthreads();
     }
 }
 

@@ -1,0 +1,468 @@
+// Per-image greedy NMS in one CTA (the NMS stage of the fused detect path).
+//
+// One CTA of 1024 threads owns one image and keeps everything in shared memory.  Survivors are numbered
+// p = 0..K-1 in candidate order (the order of the decode kernel's tile slots):
+//   1. load keys, boxes and classes from the tile slots (coalesced; prefix over the tile counts);
+//   2. bucket the box centres on a uniform grid (counting sort), bounds from a block reduction;
+//   3. pair tests.  IoU > t needs |dcx| < (1-t)/t * w and |dcy| < (1-t)/t * h for EITHER box of the pair
+//      (DESIGN.md has the derivation), so a box only meets the boxes of the grid cells inside that reach.
+//      The work is cut into (box, grid row) items spread evenly over the threads -- a tall box has hundreds
+//      of cells in reach, a small one a handful.  The lower-numbered box of a pair owns the test; the exact
+//      fp32 IoU decision is iou_suppresses() of the segmented engine.  A hit becomes an edge from the box
+//      that comes first in score order to the other one;
+//   4. greedy resolution by rounds over the edge list: a box is suppressed once a kept earlier neighbour is
+//      known, kept once all its earlier neighbours are known to be suppressed -- the fixed point is exactly
+//      the sequential greedy scan;
+//   5. bitonic sort of the keys (score desc, candidate index asc -- torchvision's stable order);
+//   6. class filter, ranks, output offset by decoupled look-back over the images, rows.
+// Images with more than INMS_CAP survivors or more than INMS_ECAP overlapping pairs are left to the general
+// segmented engine: the kernel raises BG_STATUS_NEED_GENERAL and the caller re-enqueues in general mode.
+#pragma once
+#include "detect_kernels.cuh"
+
+namespace bg {
+
+constexpr int INMS_THREADS = 1024;
+constexpr int INMS_CAP = 4096;       // survivors per image held in shared memory
+constexpr int INMS_PBITS = 12;       // bits of p inside the sort key
+constexpr int INMS_ECAP = 16384;     // overlap edges per image
+constexpr int INMS_MAXT = 1024;      // tiles per image
+constexpr int INMS_GMAX = 64;        // grid cells per axis
+constexpr int INMS_ITEMS = 8192;     // (box, grid row) work items per pass
+constexpr int INMS_MAX_N = 1 << (32 - INMS_PBITS);  // candidates per image (key = score | idx | p)
+
+struct ImgNmsK {
+    int B, N, TR, tpi_total;
+    int tpi[3], img_off[3];
+    const int *tile_count;
+    const u64 *keys;           // tile slots
+    const float4 *box_slots;
+    const int *cls_slots;
+    IouThr thr;
+    float reach;               // (1-t)/t plus margin
+    int n_tracked;
+    int tracked[BG_MAX_TRACKED];
+    FusedHdr *hdr;
+    u64 *chain;
+    int order;                 // 0: rows written here, image-major; 1: emit lists only (rows by detect_output_kernel)
+    u64 *emit_key;             // [B*N] order 1: kept keys of image b at b*N in score order, with their boxes / classes
+    float4 *emit_box;
+    int *emit_cls;
+    int *emit_count;           // [B]
+    int *cand_count;           // [B]
+    float *out_boxes;
+    long long *out_img, *out_keep;
+    int32_t *out_counts;
+    unsigned long long *stamps;  // optional [B, INMS_STAMPS] globaltimer (ns) at the stage boundaries (profiling hook)
+};
+constexpr int INMS_STAMPS = 10;
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define INMS_STAMP(i) do { if (k.stamps && tid == 0) k.stamps[(long long)b * INMS_STAMPS + (i)] = globaltimer_ns(); } while (0)
+
+struct ImgNmsSmem {
+    u64 keys[INMS_CAP];                          // (~score | idx | p); indexed by p until the sort
+    float4 box[INMS_CAP];                        // by p
+    u32 edges[INMS_ECAP];                        // (from << 16) | to, in p numbers
+    int cell_start[INMS_GMAX * INMS_GMAX + 1];
+    union {
+        int tile_pref[INMS_MAXT + 1];            // stage 1
+        unsigned short cellord[INMS_CAP];        // stage 2..3: box numbers in cell order
+    };
+    union {
+        struct { unsigned short cell_of[INMS_CAP], rank_in_cell[INMS_CAP]; };  // stage 2
+        unsigned short item_owner[INMS_ITEMS];                                 // stage 3
+    };
+    union {
+        unsigned char item_row[INMS_ITEMS];                                    // stage 3
+        struct { unsigned char state[INMS_CAP], blocked[INMS_CAP]; };          // stage 4..6: 0 undecided, 1 kept, 2 suppressed
+    };
+    unsigned short cls[INMS_CAP];                // by p
+    int wsum[33];
+    float red[4][32];
+    int n_edges;
+    int img;
+    long long base;
+};
+static_assert(INMS_ITEMS * sizeof(unsigned short) == 2 * INMS_CAP * sizeof(unsigned short), "item_owner aliases cell_of + rank_in_cell");
+static_assert(sizeof(ImgNmsSmem) <= 227 * 1024, "per-image NMS state must fit one SM's shared memory");
+
+__device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, int &total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        const int w = wsum[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += u;
+        }
+        wsum[lane] = winc - w;
+        if (lane == 31) wsum[32] = winc;
+    }
+    __syncthreads();
+    const int r = wsum[wid] + inc - v;
+    total = wsum[32];
+    __syncthreads();
+    return r;
+}
+
+// ascending bitonic sort of s[0..P) (P a power of two, 64 <= P <= 4096) by 1024 threads; strides below 64
+// stay inside one warp's 64-element window and only need a warp barrier
+__device__ __forceinline__ void inms_sort(u64 *s, int P)
+{
+    const int tid = threadIdx.x;
+    const int half = P >> 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < half; t += INMS_THREADS) {
+                const int i = 2 * t - (t & (j - 1));
+                const int l = i + j;
+                const bool asc = ((i & k) == 0);
+                const u64 a = s[i], b = s[l];
+                if ((a > b) == asc) { s[i] = b; s[l] = a; }
+            }
+            if (j > 32) __syncthreads(); else __syncwarp();
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ bool inms_tracked(const ImgNmsK &k, int c)
+{
+    for (int i = 0; i < k.n_tracked; ++i)
+        if (k.tracked[i] == c) return true;
+    return false;
+}
+
+struct InmsGrid {
+    float mnx, mny, invx, invy, pad, reach;
+    int G;
+    __device__ __forceinline__ int cx(float x) const { return (int)fminf(fmaxf(floorf(__fmul_rn(__fsub_rn(x, mnx), invx)), 0.0f), (float)(G - 1)); }
+    __device__ __forceinline__ int cy(float y) const { return (int)fminf(fmaxf(floorf(__fmul_rn(__fsub_rn(y, mny), invy)), 0.0f), (float)(G - 1)); }
+};
+
+__device__ __forceinline__ bool inms_box_valid(const float4 bx, float &w, float &h, float &cx, float &cy)
+{
+    w = __fsub_rn(bx.z, bx.x); h = __fsub_rn(bx.w, bx.y);
+    cx = 0.5f * bx.x + 0.5f * bx.z; cy = 0.5f * bx.y + 0.5f * bx.w;
+    // boxes without a positive finite extent have IoU 0 or NaN with everything: they never suppress nor get suppressed
+    return (w > 0.0f) && (h > 0.0f) && (w < INFINITY) && (h < INFINITY) && (fabsf(cx) < INFINITY) && (fabsf(cy) < INFINITY);
+}
+
+__global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
+{
+    extern __shared__ __align__(16) unsigned char inms_raw[];
+    ImgNmsSmem &S = *reinterpret_cast<ImgNmsSmem *>(inms_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    if (tid == 0) S.img = (int)atomicAdd(&k.hdr->ticket, 1u);  // dynamic image order: predecessors are running or done
+    __syncthreads();
+    const int b = S.img;
+    if (b >= k.B) return;
+    const long long ibase = (long long)b * k.N;
+    INMS_STAMP(0);
+
+    // ---- 1. tile counts -> prefix; keys, boxes, classes into shared memory (slot order = candidate order) ----
+    int K;
+    {
+        const int c = (tid < k.tpi_total) ? k.tile_count[(long long)b * k.tpi_total + tid] : 0;
+        const int ex = inms_block_excl_scan(c, S.wsum, K);
+        if (tid <= k.tpi_total) S.tile_pref[tid] = ex;  // tid == tpi_total holds the total (c = 0 there)
+        if (tid == 0) S.n_edges = 0;
+    }
+    __syncthreads();
+    bool over = K > INMS_CAP;
+    if (over) K = 0;  // this image is left to the general path; it still takes part in the look-back chain
+    float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+    for (int j = tid; j < K; j += INMS_THREADS) {
+        int lo = 0, hi = k.tpi_total;  // largest tile with tile_pref[tile] <= j
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (S.tile_pref[mid] <= j) lo = mid; else hi = mid;
+        }
+        int si = 0, lr = lo;
+        if (lr >= k.tpi[0]) { lr -= k.tpi[0]; si = 1; if (lr >= k.tpi[1]) { lr -= k.tpi[1]; si = 2; } }
+        const long long slot = ibase + k.img_off[si] + (long long)lr * k.TR + (j - S.tile_pref[lo]);
+        const u64 key = k.keys[slot];
+        const float4 bx = k.box_slots[slot];
+        const int cl = k.cls_slots[slot];
+        S.keys[j] = (key & 0xffffffff00000000ull) | ((u64)key_id(key) << INMS_PBITS) | (u64)j;
+        S.box[j] = bx;
+        S.cls[j] = (unsigned short)cl;
+        float w, h, cx, cy;
+        if (inms_box_valid(bx, w, h, cx, cy)) { mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy); }
+    }
+    INMS_STAMP(1);
+
+    // ---- 2. grid over the valid centres, counting sort by cell --------------------------------------------------
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0) { S.red[0][wid] = mnx; S.red[1][wid] = mxx; S.red[2][wid] = mny; S.red[3][wid] = mxy; }
+    __syncthreads();  // also: every thread is done with tile_pref (aliases cellord)
+    mnx = S.red[0][lane]; mxx = S.red[1][lane]; mny = S.red[2][lane]; mxy = S.red[3][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    // about two boxes per cell; the cell of a centre is a monotone function of the coordinate, so a conservative
+    // coordinate interval maps to a conservative cell interval
+    InmsGrid gr;
+    gr.G = 1;
+    while (gr.G < INMS_GMAX && 2 * (gr.G + 1) * (gr.G + 1) <= K) ++gr.G;
+    gr.mnx = mnx; gr.mny = mny;
+    gr.invx = (mxx > mnx) ? (float)gr.G / (mxx - mnx) : 0.0f;
+    gr.invy = (mxy > mny) ? (float)gr.G / (mxy - mny) : 0.0f;
+    gr.pad = 1e-6f * fmaxf(fmaxf(fabsf(mnx), fabsf(mxx)), fmaxf(fabsf(mny), fabsf(mxy)));  // fp32 rounding of the centres
+    gr.reach = k.reach;
+    const int G = gr.G, ncell = G * G;
+    for (int c = tid; c <= ncell; c += INMS_THREADS) S.cell_start[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < K; i += INMS_THREADS) {
+        float w, h, cx, cy;
+        unsigned short cell = 0xffff;
+        if (inms_box_valid(S.box[i], w, h, cx, cy)) {
+            cell = (unsigned short)(gr.cy(cy) * G + gr.cx(cx));
+            S.rank_in_cell[i] = (unsigned short)atomicAdd(&S.cell_start[cell], 1);
+        }
+        S.cell_of[i] = cell;
+    }
+    __syncthreads();
+    {   // exclusive scan of the cell counts (4 consecutive cells per thread)
+        const int c0 = tid * 4;
+        int v[4], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { v[q] = (c0 + q < ncell) ? S.cell_start[c0 + q] : 0; sum += v[q]; }
+        int tot;
+        int ex = inms_block_excl_scan(sum, S.wsum, tot);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { if (c0 + q < ncell) S.cell_start[c0 + q] = ex; ex += v[q]; }
+        if (tid == 0) S.cell_start[ncell] = tot;
+    }
+    __syncthreads();
+    for (int i = tid; i < K; i += INMS_THREADS) {
+        const unsigned short cell = S.cell_of[i];
+        if (cell != 0xffff) S.cellord[S.cell_start[cell] + S.rank_in_cell[i]] = (unsigned short)i;
+    }
+    // rows of the grid inside the reach of my four boxes (thread t owns boxes 4t..4t+3) -> work items
+    int y0[4], nrow[4], items = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = tid * 4 + q;
+        y0[q] = 0; nrow[q] = 0;
+        float w, h, cx, cy;
+        if (i < K && inms_box_valid(S.box[i], w, h, cx, cy)) {
+            const float ry = gr.reach * h + gr.pad;
+            y0[q] = gr.cy(cy - ry);
+            nrow[q] = gr.cy(cy + ry) - y0[q] + 1;
+        }
+        items += nrow[q];
+    }
+    int T;
+    const int item0 = inms_block_excl_scan(items, S.wsum, T);  // (its barriers also publish cellord)
+    INMS_STAMP(2);
+
+    // ---- 3. pair tests, item-parallel ------------------------------------------------------------------------
+    const IouThr thr = k.thr;
+    for (int c0 = 0; c0 < T; c0 += INMS_ITEMS) {
+        {   // publish the items of this pass
+            int it = item0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                for (int r = 0; r < nrow[q]; ++r, ++it) {
+                    const int rel = it - c0;
+                    if (rel >= 0 && rel < INMS_ITEMS) {
+                        S.item_owner[rel] = (unsigned short)(tid * 4 + q);
+                        S.item_row[rel] = (unsigned char)(y0[q] + r);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const int nit = min(INMS_ITEMS, T - c0);
+        for (int it = tid; it < nit; it += INMS_THREADS) {
+            const int i = S.item_owner[it];
+            const int gy = S.item_row[it];
+            const float4 a = S.box[i];
+            const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
+            const float aa = __fmul_rn(w, h);
+            const float cx = 0.5f * a.x + 0.5f * a.z;
+            const float rx = gr.reach * w + gr.pad;
+            const int x0 = gr.cx(cx - rx), x1 = gr.cx(cx + rx);
+            const int qa = S.cell_start[gy * G + x0], qb = S.cell_start[gy * G + x1 + 1];
+            for (int q = qa; q < qb; q += 4) {
+                int jj[4];
+                float4 cb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) jj[u] = (q + u < qb) ? (int)S.cellord[q + u] : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) cb[u] = S.box[jj[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (jj[u] <= i) continue;  // the lower-numbered box of a pair owns the test (padding reads as 0)
+                    const float4 c = cb[u];
+                    const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+                    if (iou_suppresses(a, aa, c, ac, thr)) {
+                        const int e = atomicAdd(&S.n_edges, 1);
+                        if (e < INMS_ECAP) {
+                            const bool i_first = S.keys[i] < S.keys[jj[u]];  // earlier in (score desc, index asc) order
+                            S.edges[e] = i_first ? (((u32)i << 16) | (u32)jj[u]) : (((u32)jj[u] << 16) | (u32)i);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    int ne = S.n_edges;
+    if (ne > INMS_ECAP) { over = true; ne = 0; K = 0; }
+    INMS_STAMP(3);
+
+    // ---- 4. greedy resolution by rounds -------------------------------------------------------------------------------
+    for (int i = tid; i < INMS_CAP; i += INMS_THREADS) { S.state[i] = 0; S.blocked[i] = 0; }  // (aliases item_row)
+    __syncthreads();
+    while (true) {
+        for (int e = tid; e < ne; e += INMS_THREADS) {
+            const u32 ed = S.edges[e];
+            const int i = (int)(ed >> 16), j = (int)(ed & 0xffffu);
+            if (S.state[j] == 0) {
+                const unsigned char si = S.state[i];
+                if (si == 1) S.state[j] = 2;
+                else if (si == 0) S.blocked[j] = 1;
+            }
+        }
+        __syncthreads();
+        int pending = 0;
+        for (int j = tid; j < K; j += INMS_THREADS) {
+            if (S.state[j] == 0) {
+                if (S.blocked[j]) { S.blocked[j] = 0; pending = 1; }
+                else S.state[j] = 1;
+            }
+        }
+        if (!__syncthreads_or(pending)) break;
+    }
+    INMS_STAMP(4);
+
+    // ---- 5. sort ------------------------------------------------------------------------------------------------------
+    int P = 64;
+    while (P < K) P <<= 1;
+    for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
+    __syncthreads();
+    inms_sort(S.keys, P);
+    INMS_STAMP(5);
+
+    // ---- 6. emission ---------------------------------------------------------------------------------------------------
+    // thread t owns the 4 consecutive score positions 4t..4t+3, so ranks follow the score order
+    int flags = 0, cnt = 0;
+    u64 mykeys[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = tid * 4 + q;
+        mykeys[q] = 0;
+        if (i < K) {
+            const u64 key = S.keys[i];
+            const int p = (int)(key & (INMS_CAP - 1));
+            if (S.state[p] == 1 && (k.n_tracked == 0 || inms_tracked(k, S.cls[p]))) {
+                mykeys[q] = key;
+                flags |= 1 << q;
+                ++cnt;
+            }
+        }
+    }
+    int total;
+    int rank = inms_block_excl_scan(cnt, S.wsum, total);
+    // rows of image b start after the rows of images < b: decoupled look-back over the per-image words
+    // (CHAIN_AGG | own count, later CHAIN_PREFIX | inclusive prefix); predecessors hold earlier tickets, so
+    // they are running or done and the wait cannot deadlock
+    if (wid == 0) {
+        if (lane == 0) {
+            ((volatile u64 *)k.chain)[b + 1] = CHAIN_AGG | (u64)total;
+            k.emit_count[b] = total;
+            k.cand_count[b] = over ? (INMS_CAP + 1) : K;
+            k.out_counts[2 + b] = total;
+            k.out_counts[2 + k.B + b] = over ? (INMS_CAP + 1) : K;
+            if (over) atomicOr(&k.hdr->status, BG_STATUS_NEED_GENERAL);
+        }
+        long long base = 0;
+        int hi = b;  // words 1..b belong to images 0..b-1; word 0 is the constant prefix 0
+        while (true) {
+            const int j = hi - lane;  // word index, newest first
+            u64 v = CHAIN_PREFIX;     // lanes past word 0 read as "prefix 0"
+            if (j >= 0) {
+                do { v = ((volatile u64 *)k.chain)[j]; } while (!(v & (CHAIN_AGG | CHAIN_PREFIX)));
+            }
+            const u32 pm = __ballot_sync(0xffffffffu, (v & CHAIN_PREFIX) != 0);
+            const int stop = pm ? (__ffs(pm) - 1) : 32;  // nearest word that already holds an inclusive prefix
+            long long part = (lane <= stop) ? (long long)(v & CHAIN_VALUE) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            base += part;
+            if (pm) break;
+            hi -= 32;
+        }
+        if (lane == 0) {
+            S.base = base;
+            ((volatile u64 *)k.chain)[b + 1] = CHAIN_PREFIX | (u64)(base + total);
+        }
+    }
+    __syncthreads();
+    INMS_STAMP(6);
+    const long long base = S.base;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!((flags >> q) & 1)) continue;
+        const u64 key = mykeys[q];
+        const int p = (int)(key & (INMS_CAP - 1));
+        const u32 id = (u32)((key & 0xffffffffull) >> INMS_PBITS);
+        const float score = from_orderable(~(u32)(key >> 32));
+        const float4 bx = S.box[p];
+        if (k.order == 0) {
+            const long long dst = base + rank;
+            float2 *o = reinterpret_cast<float2 *>(k.out_boxes + dst * 6);  // rows are 24 bytes: 8-byte aligned
+            o[0] = make_float2(score, (float)S.cls[p]);
+            o[1] = make_float2(bx.x, bx.y);
+            o[2] = make_float2(bx.z, bx.w);
+            k.out_img[dst] = b;
+            k.out_keep[dst] = ibase + id;
+        } else {
+            k.emit_key[ibase + rank] = (key & 0xffffffff00000000ull) | (u64)id;
+            k.emit_box[ibase + rank] = bx;
+            k.emit_cls[ibase + rank] = (int)S.cls[p];
+        }
+        ++rank;
+    }
+    INMS_STAMP(7);
+
+    // last image to finish: totals and status
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned d = atomicAdd(&k.hdr->done, 1u);
+        if (d == (unsigned)k.B - 1) {
+            __threadfence();
+            const u64 v = *((volatile u64 *)(k.chain + k.B));
+            k.out_counts[0] = (int)(v & CHAIN_VALUE);
+            k.out_counts[1] = *((volatile int *)&k.hdr->status);
+        }
+    }
+}
+
+}  // namespace bg

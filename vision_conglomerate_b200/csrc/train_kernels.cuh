@@ -33,6 +33,7 @@ struct AssignK {
 };
 
 constexpr int ASSIGN_THREADS = 1024;
+struct Assign3K { AssignK a[3]; };  // one launch covers up to three scales: blockIdx.y selects the entry
 
 struct AssignOut { int b, gj, gi, a, cls; float aw, ah, bx, by, bw, bh; };
 
@@ -88,8 +89,9 @@ __device__ __forceinline__ int block_count_flags(bool f, int *s_w /*[32]*/)
     return tot;  // valid in warp 0
 }
 
-__global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(AssignK k)
+__global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(Assign3K kk)
 {
+    const AssignK &k = kk.a[blockIdx.y];
     __shared__ int s_w[32];
     const long long c = (long long)blockIdx.x * ASSIGN_THREADS + threadIdx.x;
     AssignOut o;
@@ -98,8 +100,9 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(AssignK k)
     if (threadIdx.x == 0) k.block_counts[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(AssignK k)
+__global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(Assign3K kk)
 {
+    const AssignK &k = kk.a[blockIdx.y];
     __shared__ int s_w[32];
     __shared__ long long s_base;
     // offset of this block = sum of the counts of all earlier blocks (fixed order -> deterministic)
@@ -226,27 +229,47 @@ __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go,
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused detection loss, one scale
+// fused detection loss: every kernel covers the three scales (blockIdx.y)
+//   forward : loss_match_kernel  pass A, one thread per match   : gather, CIoU and its gradient, "last match
+//                                                                  wins" ticket (atomicMax of the match index)
+//                                pass B, eight lanes per match  : class BCE, argmax, confusion counters
+//             loss_dense_kernel  one thread per cell            : objectness BCE against the winner's CIoU;
+//                                                                  keeps sigmoid(x) - t for the backward
+//             loss_finalize_kernel                              : fixed-order reduction, scalars, total loss
+//   backward: loss_bwd_dense_kernel one 16-byte store per four gradient elements: objectness everywhere,
+//                                   class / box channels of a matched row from the row's LAST match
+//             loss_bwd_dup_kernel   earlier matches of a cell that was matched more than once accumulate
+//                                   with atomics (gather backward = index_put(accumulate=True))
 // ------------------------------------------------------------------------------------------------
-struct LossScaleK {
+struct LossScale {
     const float *preds;  // [B,ny,nx,na,D]
     float *grad;         // same shape (backward only)
     long long cells;     // B*ny*nx*na
-    int C, D;
     const int *M;        // device count from the assignment
     const int *cell;     // [cap]
     const int *cls;      // [cap]
     const float *anchor; // [cap,2]
     const float *box;    // [cap,4]
     float *ciou;         // [cap]
+    float4 *gbox;        // [cap] d ciou / d (x, y, w_raw, h_raw) of the matched prediction
     int *winner;         // [cells] index of the last match that targets the cell, -1 if none
+    float *gobj;         // [cells] sigmoid(obj) - t_conf
     double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
     double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
     long long *hist;     // [3,C]
-    double *scalars;     // [8]
+    double scale_w;
+};
+
+struct Loss3K {
+    LossScale s[3];
+    int C, D;
     float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
-    double w_box, w_conf, w_cls;  // term weight * scale weight * upstream gradient (backward)
     int nblk_match, nblk_dense;
+    double box_w, conf_w, class_w;
+    double *scalars;     // [3,8]
+    float *loss_out;     // [1] total loss (modules/detection_loss.py:107-110)
+    const float *go_dev; // backward: upstream gradient on the device (or null -> go_host)
+    float go_host;
 };
 
 __device__ __forceinline__ float bce_logits(float x, float t)
@@ -258,73 +281,100 @@ __device__ __forceinline__ float bce_logits(float x, float t)
 
 constexpr int LOSS_THREADS = 256;
 
-// one warp per match: gather the row, CIoU, class BCE, confusion counters, "last match wins" ticket
-__global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(LossScaleK k)
+__global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
 {
+    extern __shared__ int s_hist[];  // [3,C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int M = *k.M;
-    const long long warp0 = (long long)blockIdx.x * (LOSS_THREADS / 32) + wid;
-    const long long nwarps = (long long)gridDim.x * (LOSS_THREADS / 32);
+    const LossScale &S = k.s[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int M = *S.M;
+    const int C = k.C, D = k.D;
+    for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+
+    // pass A: one thread per match
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (long long m = warp0; m < M; m += nwarps) {
-        const int cell = k.cell[m];
-        const int tc = k.cls[m];
-        const float *row = k.preds + (long long)cell * k.D;
+    for (long long m = (long long)blockIdx.x * LOSS_THREADS + tid; m < M; m += (long long)gridDim.x * LOSS_THREADS) {
+        const int cell = S.cell[m];
+        const float *row = S.preds + (long long)cell * D;
+        const float aw = S.anchor[2 * m], ah = S.anchor[2 * m + 1];
+        const float p[4] = {__ldg(row + C + 1), __ldg(row + C + 2), __fmul_rn(__ldg(row + C + 3), aw),
+                            __fmul_rn(__ldg(row + C + 4), ah)};
+        const float obj = __ldg(row);
+        const float4 tb = reinterpret_cast<const float4 *>(S.box)[m];
+        const float t[4] = {tb.x, tb.y, tb.z, tb.w};
+        double g[4];
+        const float ci = ciou_eval(p, t, 1e-7f, g);
+        S.ciou[m] = ci;
+        S.gbox[m] = make_float4((float)g[0], (float)g[1], (float)(g[2] * (double)aw), (float)(g[3] * (double)ah));
+        atomicMax(&S.winner[cell], (int)m);
+        a0 += (double)__fsub_rn(1.0f, ci);
+        a1 += (double)ci;
+        a2 += (double)sigmoid_acc(obj);
+    }
+
+    // pass B: eight lanes per match (four matches per warp in flight)
+    const int gl = lane & 7;
+    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
+         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
+        const long long m = mb + (lane >> 3);
+        const bool valid = m < M;
         float bsum = 0.f, best = -INFINITY;
-        int bi = 0x7fffffff;
-        for (int c = lane; c < k.C; c += 32) {
-            const float x = __ldg(row + 1 + c);
-            bsum += bce_logits(x, c == tc ? k.cp : k.cn);
-            if (x > best) { best = x; bi = c; }
+        int bi = 0x7fffffff, tc = -1;
+        if (valid) {
+            tc = S.cls[m];
+            const float *row = S.preds + (long long)S.cell[m] * D + 1;
+            for (int c = gl; c < C; c += 8) {
+                const float x = __ldg(row + c);
+                bsum += bce_logits(x, c == tc ? k.cp : k.cn);
+                if (x > best) { best = x; bi = c; }
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 4; o > 0; o >>= 1) {
             bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
             const float ob = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
         }
-        if (lane == 0) {
-            const float p[4] = {__ldg(row + k.C + 1), __ldg(row + k.C + 2),
-                                __fmul_rn(__ldg(row + k.C + 3), k.anchor[2 * m]),
-                                __fmul_rn(__ldg(row + k.C + 4), k.anchor[2 * m + 1])};
-            const float4 tb = reinterpret_cast<const float4 *>(k.box)[m];
-            const float t[4] = {tb.x, tb.y, tb.z, tb.w};
-            const float ci = ciou_eval(p, t, 1e-7f, nullptr);
-            k.ciou[m] = ci;
-            atomicMax(&k.winner[cell], (int)m);
-            a0 += (double)__fsub_rn(1.0f, ci);
-            a1 += (double)ci;
-            a2 += (double)sigmoid_acc(__ldg(row));
+        if (valid && gl == 0) {
             a3 += (double)bsum;
-            atomicAdd((unsigned long long *)&k.hist[0 * k.C + tc], (unsigned long long)(bi == tc));
-            atomicAdd((unsigned long long *)&k.hist[1 * k.C + tc], 1ull);
-            atomicAdd((unsigned long long *)&k.hist[2 * k.C + bi], 1ull);
+            if (bi == tc) atomicAdd(&s_hist[tc], 1);
+            atomicAdd(&s_hist[C + tc], 1);
+            if (bi >= 0 && bi < C) atomicAdd(&s_hist[2 * C + bi], 1);
         }
     }
+
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
     if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; s_red[wid][3] = a3; }
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (tid < 4) {
         double s = 0;
-        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
-        k.part_match[(long long)blockIdx.x * 4 + threadIdx.x] = s;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][tid];
+        S.part_match[(long long)blockIdx.x * 4 + tid] = s;
+    }
+    for (int i = tid; i < 3 * C; i += LOSS_THREADS) {
+        const int v = s_hist[i];
+        if (v) atomicAdd((unsigned long long *)&S.hist[i], (unsigned long long)v);
     }
 }
 
 // dense objectness BCE over every cell
-__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(LossScaleK k)
+__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
 {
     __shared__ double s_red[LOSS_THREADS / 32][3];
+    const LossScale &S = k.s[blockIdx.y];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
-    for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < k.cells;
+    for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < S.cells;
          c += (long long)gridDim.x * LOSS_THREADS) {
-        const float x = __ldg(k.preds + c * k.D);
-        const int w = k.winner[c];
-        const float t = w >= 0 ? k.ciou[w] : 0.0f;
+        const float x = __ldg(S.preds + c * k.D);
+        const int w = S.winner[c];
+        const float t = w >= 0 ? S.ciou[w] : 0.0f;
+        const float sg = sigmoid_acc(x);
         a0 += (double)bce_logits(x, t);
-        if (t == 0.0f) { a1 += (double)sigmoid_acc(x); a2 += 1.0; }
+        if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
+        S.gobj[c] = __fsub_rn(sg, t);
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
@@ -332,89 +382,160 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(LossScaleK k)
     if (threadIdx.x < 3) {
         double s = 0;
         for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
-        k.part_dense[(long long)blockIdx.x * 3 + threadIdx.x] = s;
+        S.part_dense[(long long)blockIdx.x * 3 + threadIdx.x] = s;
     }
 }
 
-// fixed-order final reduction -> scalars[8]
-__global__ void __launch_bounds__(256) loss_finalize_kernel(LossScaleK k)
+// fixed-order final reduction -> scalars[3,8] and the combined loss
+__global__ void __launch_bounds__(256) loss_finalize_kernel(Loss3K k)
 {
     __shared__ double s_red[8][7];
+    __shared__ double s_terms[3][3];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int b = threadIdx.x; b < k.nblk_match; b += 256)
-        for (int q = 0; q < 4; ++q) v[q] += k.part_match[(long long)b * 4 + q];
-    for (int b = threadIdx.x; b < k.nblk_dense; b += 256)
-        for (int q = 0; q < 3; ++q) v[4 + q] += k.part_dense[(long long)b * 3 + q];
-    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
-    if (lane == 0) for (int q = 0; q < 7; ++q) s_red[wid][q] = v[q];
-    __syncthreads();
+    for (int sc = 0; sc < 3; ++sc) {
+        const LossScale &S = k.s[sc];
+        double v[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int b = threadIdx.x; b < k.nblk_match; b += 256)
+            for (int q = 0; q < 4; ++q) v[q] += S.part_match[(long long)b * 4 + q];
+        for (int b = threadIdx.x; b < k.nblk_dense; b += 256)
+            for (int q = 0; q < 3; ++q) v[4 + q] += S.part_dense[(long long)b * 3 + q];
+        for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+        if (lane == 0) for (int q = 0; q < 7; ++q) s_red[wid][q] = v[q];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s[7];
+            for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[w][q]; }
+            const double M = (double)*S.M;
+            const double nan = __longlong_as_double(0x7ff8000000000000LL);
+            double *o = k.scalars + 8 * sc;
+            o[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
+            o[1] = s[4] / (double)S.cells;
+            o[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
+            o[3] = M > 0 ? s[1] / M : nan;
+            o[4] = M > 0 ? s[2] / M : nan;
+            o[5] = s[6] > 0 ? s[5] / s[6] : nan;
+            o[6] = M;
+            o[7] = s[6];
+            s_terms[sc][0] = S.scale_w * o[0]; s_terms[sc][1] = S.scale_w * o[1]; s_terms[sc][2] = S.scale_w * o[2];
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
-        double s[7];
-        for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[w][q]; }
-        const double M = (double)*k.M;
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        k.scalars[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
-        k.scalars[1] = s[4] / (double)k.cells;
-        k.scalars[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
-        k.scalars[3] = M > 0 ? s[1] / M : nan;
-        k.scalars[4] = M > 0 ? s[2] / M : nan;
-        k.scalars[5] = s[6] > 0 ? s[5] / s[6] : nan;
-        k.scalars[6] = M;
-        k.scalars[7] = s[6];
+        const double lbox = s_terms[0][0] + s_terms[1][0] + s_terms[2][0];
+        const double lconf = s_terms[0][1] + s_terms[1][1] + s_terms[2][1];
+        const double lcls = s_terms[0][2] + s_terms[1][2] + s_terms[2][2];
+        *k.loss_out = (float)(k.box_w * lbox + k.conf_w * lconf + k.class_w * lcls);
     }
 }
 
-// backward 1/2: dense write of the gradient tensor (objectness channel everywhere, zeros elsewhere)
-__global__ void __launch_bounds__(256) loss_bwd_dense_kernel(LossScaleK k)
+struct BwdScales { double conf, cls, box; };
+__device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale &S)
 {
-    const long long total = k.cells * k.D;
-    const double sc = k.w_conf / (double)k.cells;
-    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-        const long long c = e / k.D;
-        float g = 0.0f;
-        if (e - c * k.D == 0) {
-            const float x = __ldg(k.preds + e);
-            const int w = k.winner[c];
-            const float t = w >= 0 ? k.ciou[w] : 0.0f;
-            g = (float)(sc * ((double)sigmoid_acc(x) - (double)t));
+    const double go = (double)(k.go_dev ? *k.go_dev : k.go_host) * S.scale_w;
+    const int M = *S.M;
+    BwdScales r;
+    r.conf = k.conf_w * go / (double)S.cells;
+    r.cls = M > 0 ? k.class_w * go / ((double)M * (double)k.C) : 0.0;
+    r.box = M > 0 ? -k.box_w * go / (double)M : 0.0;
+    return r;
+}
+
+// gradient of element (row, col); m = winner of the row (-1: unmatched), x = the prediction at (row, col)
+__device__ __forceinline__ float bwd_elem(const Loss3K &k, const LossScale &S, const BwdScales &sc, long long row, int col,
+                                          int m, float x)
+{
+    if (col == 0) return (float)(sc.conf * (double)S.gobj[row]);
+    if (m < 0) return 0.0f;
+    if (col <= k.C) {
+        const double t = (col - 1 == S.cls[m]) ? (double)k.cp : (double)k.cn;
+        return (float)(sc.cls * ((double)sigmoid_acc(x) - t));
+    }
+    const float *g = reinterpret_cast<const float *>(S.gbox + m);
+    return (float)(sc.box * (double)g[col - k.C - 1]);
+}
+
+constexpr int BWD_THREADS = 256;
+constexpr int BWD_F4_PER_THREAD = 8;
+
+__global__ void __launch_bounds__(BWD_THREADS) loss_bwd_dense_kernel(Loss3K k)
+{
+    const LossScale &S = k.s[blockIdx.y];
+    const BwdScales sc = bwd_scales(k, S);
+    const u32 D = (u32)k.D;
+    const long long total = S.cells * (long long)D;
+    const long long nf4 = total >> 2;
+    constexpr int CH = BWD_THREADS * BWD_F4_PER_THREAD;
+    float4 *g4 = reinterpret_cast<float4 *>(S.grad);
+    const float4 *p4 = reinterpret_cast<const float4 *>(S.preds);
+    for (long long f0 = (long long)blockIdx.x * CH; f0 < nf4; f0 += (long long)gridDim.x * CH) {
+        const long long row0 = (4 * f0) / D;
+        const u32 rem0 = (u32)(4 * f0 - row0 * D);
+#pragma unroll 2
+        for (int i = 0; i < BWD_F4_PER_THREAD; ++i) {
+            const u32 lf = (u32)i * BWD_THREADS + threadIdx.x;
+            const long long f = f0 + lf;
+            if (f >= nf4) break;
+            const u32 e = rem0 + 4 * lf;
+            const u32 q = e / D, r = e - q * D;
+            const long long row = row0 + q;
+            const bool two = r + 3 >= D && row + 1 < S.cells;  // the four elements straddle a row boundary
+            const int mA = S.winner[row];
+            const int mB = two ? S.winner[row + 1] : -1;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (mA < 0 && mB < 0) {
+                if (r == 0) v[0] = (float)(sc.conf * (double)S.gobj[row]);
+                else if (two) {
+                    const float go1 = (float)(sc.conf * (double)S.gobj[row + 1]);
+                    const u32 pos = D - r;  // 1..3
+                    v[1] = pos == 1 ? go1 : 0.f; v[2] = pos == 2 ? go1 : 0.f; v[3] = pos == 3 ? go1 : 0.f;
+                }
+            } else {
+                const float4 x4 = __ldg(p4 + f);
+                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const u32 col = r + j;
+                    if (col < D) v[j] = bwd_elem(k, S, sc, row, (int)col, mA, x[j]);
+                    else if (row + 1 < S.cells) v[j] = bwd_elem(k, S, sc, row + 1, (int)(col - D), mB, x[j]);
+                }
+            }
+            g4[f] = make_float4(v[0], v[1], v[2], v[3]);
         }
-        k.grad[e] = g;
+    }
+    // the last total % 4 elements (only when cells * D is not a multiple of four)
+    if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
+        const long long e = (nf4 << 2) + threadIdx.x;
+        const long long row = e / D;
+        const int col = (int)(e - row * D);
+        S.grad[e] = bwd_elem(k, S, sc, row, col, S.winner[row], S.preds[e]);
     }
 }
 
-// backward 2/2: matched rows -- class and box channels; duplicate matches of a cell accumulate
-__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_match_kernel(LossScaleK k)
+// matches that are not the last match of their cell add their class / box gradients to the row
+__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_dup_kernel(Loss3K k)
 {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int M = *k.M;
+    const LossScale &S = k.s[blockIdx.y];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gl = lane & 7;
+    const int M = *S.M;
     if (M <= 0) return;
-    const long long warp0 = (long long)blockIdx.x * (LOSS_THREADS / 32) + wid;
-    const long long nwarps = (long long)gridDim.x * (LOSS_THREADS / 32);
-    const double sc_cls = k.w_cls / ((double)M * (double)k.C);
-    const double sc_box = -k.w_box / (double)M;
-    for (long long m = warp0; m < M; m += nwarps) {
-        const int cell = k.cell[m];
-        const int tc = k.cls[m];
-        const float *row = k.preds + (long long)cell * k.D;
-        float *grow = k.grad + (long long)cell * k.D;
-        for (int c = lane; c < k.C; c += 32) {
-            const float x = __ldg(row + 1 + c);
+    const BwdScales sc = bwd_scales(k, S);
+    const int C = k.C, D = k.D;
+    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
+         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
+        const long long m = mb + (lane >> 3);
+        if (m >= M) continue;
+        const int cell = S.cell[m];
+        if (S.winner[cell] == (int)m) continue;  // written by the dense kernel
+        const int tc = S.cls[m];
+        const float *row = S.preds + (long long)cell * D;
+        float *grow = S.grad + (long long)cell * D;
+        for (int c = gl; c < C; c += 8) {
             const double t = (c == tc) ? (double)k.cp : (double)k.cn;
-            atomicAdd(grow + 1 + c, (float)(sc_cls * ((double)sigmoid_acc(x) - t)));
+            atomicAdd(grow + 1 + c, (float)(sc.cls * ((double)sigmoid_acc(__ldg(row + 1 + c)) - t)));
         }
-        if (lane == 0) {
-            const float aw = k.anchor[2 * m], ah = k.anchor[2 * m + 1];
-            const float p[4] = {__ldg(row + k.C + 1), __ldg(row + k.C + 2), __fmul_rn(__ldg(row + k.C + 3), aw),
-                                __fmul_rn(__ldg(row + k.C + 4), ah)};
-            const float4 tb = reinterpret_cast<const float4 *>(k.box)[m];
-            const float t[4] = {tb.x, tb.y, tb.z, tb.w};
-            double g[4];
-            ciou_eval(p, t, 1e-7f, g);
-            atomicAdd(grow + k.C + 1, (float)(sc_box * g[0]));
-            atomicAdd(grow + k.C + 2, (float)(sc_box * g[1]));
-            atomicAdd(grow + k.C + 3, (float)(sc_box * g[2] * (double)aw));
-            atomicAdd(grow + k.C + 4, (float)(sc_box * g[3] * (double)ah));
+        if (gl < 4) {
+            const float *g = reinterpret_cast<const float *>(S.gbox + m);
+            atomicAdd(grow + C + 1 + gl, (float)(sc.box * (double)g[gl]));
         }
     }
 }

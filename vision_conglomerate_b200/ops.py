@@ -22,6 +22,10 @@ _ws: Dict[Tuple[int, str], torch.Tensor] = {}
 _pinned: Dict[Tuple[int, str], torch.Tensor] = {}
 _mask_budget: Dict[Tuple[int, str], int] = {}
 DEFAULT_MASK_BYTES = 64 << 20
+# bg_detect NMS path remembered per (device, batch, candidates, thresholds): 0 = one CTA per image (default),
+# 1 = general segmented engine (images with many survivors), 3 = general for good (overlap-edge overflow)
+_nms_path_hint: Dict[Tuple, int] = {}
+PER_IMAGE_NMS_CAP = 4096  # INMS_CAP of csrc/imgnms_kernels.cuh
 
 
 def _stream() -> int:
@@ -138,7 +142,8 @@ class DetectPlan:
     def __init__(self, shapes: Sequence[Tuple[int, ...]], anchors3: Sequence, input_shape: Tuple[int, int],
                  num_classes: int, device: torch.device, og_size: Optional[Tuple[int, int]] = None,
                  iou_threshold: float = 0.5, score_threshold: float = 0.1, box_allowance: Optional[float] = None,
-                 tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0):
+                 tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0,
+                 nms_path: str = "auto"):
         if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
             raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
         B, _, _, na, D = shapes[0]
@@ -168,6 +173,8 @@ class DetectPlan:
         p.variant = int(variant)
         self.params, self.B, self.dev = p, B, device
         self.N = sum(sh[1] * sh[2] * na for sh in shapes)
+        self.hint_key = (device.index, B, self.N, p.iou_threshold, p.score_threshold)
+        p.nms_path = 1 if (nms_path == "general" or _nms_path_hint.get(self.hint_key, 0)) else 0
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
         self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
@@ -196,6 +203,17 @@ class DetectPlan:
         B = self.B
         while True:
             h = _read_counts(self.counts, "detect")
+            if int(h[1]) & _lib.STATUS_NEED_GENERAL:
+                # an image exceeded what the one-CTA-per-image NMS holds: run again through the general engine
+                # and remember it (survivor overflow is re-evaluated from the counts, edge overflow is kept)
+                many = int(h[2 + B: 2 + 2 * B].max()) > PER_IMAGE_NMS_CAP
+                _nms_path_hint[self.hint_key] = 1 if many else 3
+                self.params.nms_path = 1
+                self.enqueue(self.raws)
+                continue
+            if self.params.nms_path == 1 and _nms_path_hint.get(self.hint_key) == 1 \
+                    and int(h[2 + B: 2 + 2 * B].max()) <= PER_IMAGE_NMS_CAP // 2:
+                _nms_path_hint.pop(self.hint_key, None)  # sparse again: the next plan starts on the per-image path
             if int(h[1]) & _lib.STATUS_MASK_SPACE:
                 # the per-image survivor counts are known now: size the bit matrix exactly and run again
                 cand = h[2 + B: 2 + 2 * B].to(torch.int64)
@@ -213,13 +231,13 @@ class DetectPlan:
 def detect(raws: Sequence[torch.Tensor], anchors3: Sequence, input_shape: Tuple[int, int], num_classes: int,
            og_size: Optional[Tuple[int, int]] = None, iou_threshold: float = 0.5, score_threshold: float = 0.1,
            box_allowance: Optional[float] = None, tracked_classes: Optional[Sequence[int]] = None,
-           order: str = "image", variant: int = 0) -> Detections:
+           order: str = "image", variant: int = 0, nms_path: str = "auto") -> Detections:
     """Fused ``DetectionNet.forward(inference=True)`` tail (modules/detection.py:69-91) +
     ``post_process_preds`` lines 57-97 and the class filter at :107-109, from the three raw head outputs
     ``[B, ny, nx, na, 5+C]``.  The returned tensors are views of buffers owned by the plan of this call."""
     raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
     plan = DetectPlan([tuple(r.shape) for r in raws], anchors3, input_shape, num_classes, raws[0].device, og_size,
-                      iou_threshold, score_threshold, box_allowance, tracked_classes, order, variant)
+                      iou_threshold, score_threshold, box_allowance, tracked_classes, order, variant, nms_path)
     plan.enqueue(raws)
     return plan.result()
 
@@ -325,34 +343,32 @@ def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
 
 
 class _DetLoss(torch.autograd.Function):
-    """Forward: assignment + gather + CIoU + objectness/class BCE for the three scales, no host sync.
-    Backward: dense ``grad_preds`` written once per scale."""
+    """Forward: assignment + gather + CIoU + objectness/class BCE for the three scales and the combined loss,
+    all on the device, no host sync.  Backward: dense ``grad_preds`` written once per scale; the upstream
+    gradient stays on the device."""
 
     @staticmethod
     def forward(ctx, sm, md, lg, targets, params: LossParams, scalars, hist):
         L = _lib.lib()
         dev = sm.device
         ws = _workspace(dev, "loss", L.bg_loss_workspace_bytes(C.byref(params)))
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
         check(L.bg_loss_fwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), targets.data_ptr() if targets.numel() else None,
-                            C.byref(params), scalars.data_ptr(), hist.data_ptr(), ws.data_ptr(), ws.numel(),
-                            _stream()), "bg_loss_fwd")
+                            C.byref(params), scalars.data_ptr(), hist.data_ptr(), loss.data_ptr(), ws.data_ptr(),
+                            ws.numel(), _stream()), "bg_loss_fwd")
         ctx.save_for_backward(sm, md, lg)
         ctx.params, ctx.ws = params, ws
-        sw = torch.tensor([params.scale_w[0], params.scale_w[1], params.scale_w[2]], dtype=torch.float64, device=dev)
-        tw = torch.tensor([params.box_w, params.conf_w, params.class_w], dtype=torch.float64, device=dev)
-        per_term = (scalars[:, :3] * sw[:, None]).sum(0)  # lbox, lconf, lcls weighted over scales (:107-109)
-        return (per_term * tw).sum().float()               # :110
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, go):
         sm, md, lg = ctx.saved_tensors
         L = _lib.lib()
         grads = [torch.empty_like(x) for x in (sm, md, lg)]
-        # the upstream gradient is a scalar; reading it costs one sync (loss.backward() passes 1.0)
-        g = float(go)
-        check(L.bg_loss_bwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), C.byref(ctx.params), g, grads[0].data_ptr(),
-                            grads[1].data_ptr(), grads[2].data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(), _stream()),
-              "bg_loss_bwd")
+        go = go.detach().to(torch.float32).contiguous()
+        check(L.bg_loss_bwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), C.byref(ctx.params), go.data_ptr(), 1.0,
+                            grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ctx.ws.data_ptr(),
+                            ctx.ws.numel(), _stream()), "bg_loss_bwd")
         return grads[0], grads[1], grads[2], None, None, None, None
 
 
