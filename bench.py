@@ -193,10 +193,15 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(K):
-            L.bg_profile_events(ev_k[i][0].cuda_event, ev_k[i][1].cuda_event)
             plan.enqueue(raws_d)
         e1.record()
         launches = _lib.launch_count() - launches0  # kernels of ours enqueued inside the timed region
+        barrier()
+        # second pass, untimed as a whole: the same K steps with CUDA events recorded immediately around the
+        # decode+filter kernel on its stream (the roofline numerator's duration)
+        for i in range(K):
+            L.bg_profile_events(ev_k[i][0].cuda_event, ev_k[i][1].cuda_event)
+            plan.enqueue(raws_d)
         barrier()
         L.bg_profile_events(None, None)
         # the timed region lasts milliseconds; keep the same load running ~0.5 s more (untimed) so the

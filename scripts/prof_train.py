@@ -17,7 +17,18 @@ ap.add_argument("--gt", type=int, default=100)
 ap.add_argument("--size", type=int, default=640)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--l2-fetch", type=int, default=0, help="experiment: cudaLimitMaxL2FetchGranularity in bytes (32/64/128)")
 a = ap.parse_args()
+if a.l2_fetch:
+    import ctypes
+    torch.cuda.init()
+    rt = ctypes.CDLL("libcudart.so.12")
+    cur = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(cur), 5)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(a.l2_fetch))  # cudaLimitMaxL2FetchGranularity = 0x05
+    new = ctypes.c_size_t(0)
+    rt.cudaDeviceGetLimit(ctypes.byref(new), 5)
+    print("L2 fetch granularity: was %d, set rc=%d, now %d" % (cur.value, rc, new.value))
 dev = torch.device("cuda", 0)
 B, S, C = a.batch, a.size, 80
 t = synth.targets(B, a.gt, C, 0).to(dev)

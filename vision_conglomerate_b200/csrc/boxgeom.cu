@@ -633,7 +633,7 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
     BG_LAUNCH_CHECK();
     loss_dense_kernel<<<dim3(w.nblk_dense, 3), LOSS_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 256, 0, st>>>(k);
+    loss_finalize_kernel<<<1, 768, 0, st>>>(k);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -656,9 +656,10 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
     k.go_dev = grad_out_dev;
     k.go_host = grad_out_host;
     const int sms = num_sms();
-    loss_bwd_dense_kernel<<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
+    if (k.D == 85) loss_bwd_dense_kernel<85><<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
+    else loss_bwd_dense_kernel<0><<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
-    loss_bwd_dup_kernel<<<dim3(sms * 2, 3), LOSS_THREADS, 0, st>>>(k);
+    loss_bwd_dup_kernel<<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }

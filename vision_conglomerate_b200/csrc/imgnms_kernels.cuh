@@ -90,6 +90,7 @@ struct ImgNmsSmem {
     long long base;
 };
 static_assert(INMS_ITEMS * sizeof(unsigned short) == 2 * INMS_CAP * sizeof(unsigned short), "item_owner aliases cell_of + rank_in_cell");
+static_assert(INMS_CAP == 4 * INMS_THREADS, "the register sort holds at most four keys per thread");
 static_assert(sizeof(ImgNmsSmem) <= 227 * 1024, "per-image NMS state must fit one SM's shared memory");
 
 __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, int &total)
@@ -121,25 +122,65 @@ __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, i
     return r;
 }
 
-// ascending bitonic sort of s[0..P) (P a power of two, 64 <= P <= 4096) by 1024 threads; strides below 64
-// stay inside one warp's 64-element window and only need a warp barrier
-__device__ __forceinline__ void inms_sort(u64 *s, int P)
+// Ascending bitonic sort of s[0..P), P = E * 1024 keys (callers pad with ~0), by 1024 threads.  Thread t holds
+// the E consecutive keys t*E..t*E+E-1 in registers: strides below E are register compare-exchanges, strides
+// below 32*E are warp shuffles with lane ^ (j/E), and only the larger strides go through shared memory
+// (staged key-index-major, s[e*1024 + t], so the exchange reads are conflict-free).
+template <int E>
+__device__ __forceinline__ void inms_sort_reg(u64 *s)
 {
-    const int tid = threadIdx.x;
-    const int half = P >> 1;
+    const int t = threadIdx.x;
+    constexpr int P = E * INMS_THREADS;
+    u64 v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = s[t * E + e];
+    __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < half; t += INMS_THREADS) {
-                const int i = 2 * t - (t & (j - 1));
-                const int l = i + j;
-                const bool asc = ((i & k) == 0);
-                const u64 a = s[i], b = s[l];
-                if ((a > b) == asc) { s[i] = b; s[l] = a; }
+            if (j >= 32 * E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) s[e * INMS_THREADS + t] = v[e];
+                __syncthreads();
+                const int pt = t ^ (j / E);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const u64 o = s[e * INMS_THREADS + pt];
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
+                }
+                __syncthreads();
+            } else if (j >= E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const u64 o = __shfl_xor_sync(0xffffffffu, v[e], j / E);
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
+                }
+            } else {
+                // register compare-exchange; j is 1 (E >= 2) or 2 (E == 4): static indices keep v[] in registers
+#pragma unroll
+                for (int jj = 1; jj < E; jj <<= 1) {
+                    if (jj != j) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if ((e & jj) == 0) {
+                            const int i = t * E + e;
+                            const bool up = (i & k) == 0;
+                            const u64 a = v[e], c = v[e | jj];
+                            const bool sw = (a > c) == up;
+                            v[e] = sw ? c : a;
+                            v[e | jj] = sw ? a : c;
+                        }
+                    }
+                }
             }
-            if (j > 32) __syncthreads(); else __syncwarp();
         }
-        __syncthreads();
     }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[t * E + e] = v[e];
+    __syncthreads();
 }
 
 __device__ __forceinline__ bool inms_tracked(const ImgNmsK &k, int c)
@@ -262,7 +303,10 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         const unsigned short cell = S.cell_of[i];
         if (cell != 0xffff) S.cellord[S.cell_start[cell] + S.rank_in_cell[i]] = (unsigned short)i;
     }
-    // rows of the grid inside the reach of my four boxes (thread t owns boxes 4t..4t+3) -> work items
+    // Work items = (box, grid row) for the rows from the box's own row down to the end of its reach: a pair in
+    // different cells is tested by the box whose cell comes first in row-major order, a pair inside one cell
+    // by the lower-numbered box (each box of a pair lies in the other's reach, so either side finds it).
+    // Thread t owns boxes 4t..4t+3.
     int y0[4], nrow[4], items = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -271,7 +315,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         float w, h, cx, cy;
         if (i < K && inms_box_valid(S.box[i], w, h, cx, cy)) {
             const float ry = gr.reach * h + gr.pad;
-            y0[q] = gr.cy(cy - ry);
+            y0[q] = gr.cy(cy);
             nrow[q] = gr.cy(cy + ry) - y0[q] + 1;
         }
         items += nrow[q];
@@ -304,23 +348,30 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
             const float4 a = S.box[i];
             const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
             const float aa = __fmul_rn(w, h);
-            const float cx = 0.5f * a.x + 0.5f * a.z;
+            const float cx = 0.5f * a.x + 0.5f * a.z, cy = 0.5f * a.y + 0.5f * a.w;
             const float rx = gr.reach * w + gr.pad;
-            const int x0 = gr.cx(cx - rx), x1 = gr.cx(cx + rx);
+            const int ax = gr.cx(cx), ay = gr.cy(cy);
+            const bool own_row = gy == ay;
+            const int x0 = own_row ? ax : gr.cx(cx - rx), x1 = gr.cx(cx + rx);
             const int qa = S.cell_start[gy * G + x0], qb = S.cell_start[gy * G + x1 + 1];
+            const int q_own = own_row ? S.cell_start[gy * G + ax + 1] : qa;  // entries below q_own share my cell
+            // IoU > t needs both extent ratios above t: cheap conservative reject (1 % slack covers the fp32 rounding)
+            const float wlo = 0.99f * thr.tdn * w, hlo = 0.99f * thr.tdn * h;
+            const float wsc = 0.99f * thr.tdn, w_me = w, h_me = h;
             for (int q = qa; q < qb; q += 4) {
                 int jj[4];
                 float4 cb[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) jj[u] = (q + u < qb) ? (int)S.cellord[q + u] : 0;
+                for (int u = 0; u < 4; ++u) jj[u] = (q + u < qb) ? (int)S.cellord[q + u] : -1;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) cb[u] = S.box[jj[u]];
+                for (int u = 0; u < 4; ++u) cb[u] = S.box[jj[u] < 0 ? 0 : jj[u]];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (jj[u] <= i) continue;  // the lower-numbered box of a pair owns the test (padding reads as 0)
+                    if (jj[u] < 0 || (q + u < q_own && jj[u] <= i)) continue;
                     const float4 c = cb[u];
-                    const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
-                    if (iou_suppresses(a, aa, c, ac, thr)) {
+                    const float wc = __fsub_rn(c.z, c.x), hc = __fsub_rn(c.w, c.y);
+                    if (wc < wlo || hc < hlo || wsc * wc > w_me || wsc * hc > h_me) continue;
+                    if (iou_suppresses(a, aa, c, __fmul_rn(wc, hc), thr)) {
                         const int e = atomicAdd(&S.n_edges, 1);
                         if (e < INMS_ECAP) {
                             const bool i_first = S.keys[i] < S.keys[jj[u]];  // earlier in (score desc, index asc) order
@@ -362,11 +413,12 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     INMS_STAMP(4);
 
     // ---- 5. sort ------------------------------------------------------------------------------------------------------
-    int P = 64;
-    while (P < K) P <<= 1;
+    const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
     for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
     __syncthreads();
-    inms_sort(S.keys, P);
+    if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
+    else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
+    else inms_sort_reg<4>(S.keys);
     INMS_STAMP(5);
 
     // ---- 6. emission ---------------------------------------------------------------------------------------------------

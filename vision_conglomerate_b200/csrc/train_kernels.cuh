@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(Assign3K kk
 // CIoU (modules/detection_loss.py:229-264): fp32 forward in the reference's operation order; the
 // gradient w.r.t. the prediction (alpha constant) is evaluated in double from the same quantities.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], float e, double *g /*4 or null*/)
+template <typename G>  // G = double (stand-alone bg_ciou_bwd) or float (fused loss: rtol 1e-4 against fp32 autograd)
+__device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], float e, G *g /*4 or null*/)
 {
     const float pw = p[2], ph = p[3], tw = t[2], th = t[3];
     const float px1 = __fsub_rn(p[0], __fdiv_rn(pw, 2.0f)), py1 = __fsub_rn(p[1], __fdiv_rn(ph, 2.0f));
@@ -176,32 +177,32 @@ __device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], f
     const float a = __fdiv_rn(v, __fadd_rn(__fsub_rn(v, iou), __fadd_rn(1.0f, e)));
     const float ciou = __fsub_rn(iou, __fadd_rn(__fdiv_rn(rho2, c2), __fmul_rn(a, v)));
     if (g) {
-        const double dpx1[4] = {1, 0, -0.5, 0}, dpx2[4] = {1, 0, 0.5, 0};
-        const double dpy1[4] = {0, 1, 0, -0.5}, dpy2[4] = {0, 1, 0, 0.5};
+        const G dpx1[4] = {1, 0, -0.5, 0}, dpx2[4] = {1, 0, 0.5, 0};
+        const G dpy1[4] = {0, 1, 0, -0.5}, dpy2[4] = {0, 1, 0, 0.5};
         const bool iw_pos = iw_raw >= 0.f, ih_pos = ih_raw >= 0.f;  // clamp passes the gradient at equality
         // torch.min / torch.max split the gradient evenly on exact ties
-        const double s_minx2 = px2 < tx2 ? 1.0 : (px2 == tx2 ? 0.5 : 0.0), s_maxx1 = px1 > tx1 ? 1.0 : (px1 == tx1 ? 0.5 : 0.0);
-        const double s_miny2 = py2 < ty2 ? 1.0 : (py2 == ty2 ? 0.5 : 0.0), s_maxy1 = py1 > ty1 ? 1.0 : (py1 == ty1 ? 0.5 : 0.0);
-        const double s_maxx2 = px2 > tx2 ? 1.0 : (px2 == tx2 ? 0.5 : 0.0), s_minx1 = px1 < tx1 ? 1.0 : (px1 == tx1 ? 0.5 : 0.0);
-        const double s_maxy2 = py2 > ty2 ? 1.0 : (py2 == ty2 ? 0.5 : 0.0), s_miny1 = py1 < ty1 ? 1.0 : (py1 == ty1 ? 0.5 : 0.0);
-        const double den = (double)uni + (double)e;
-        const double r = (double)pw / (double)ph;
+        const G s_minx2 = px2 < tx2 ? (G)1 : (px2 == tx2 ? (G)0.5 : (G)0), s_maxx1 = px1 > tx1 ? (G)1 : (px1 == tx1 ? (G)0.5 : (G)0);
+        const G s_miny2 = py2 < ty2 ? (G)1 : (py2 == ty2 ? (G)0.5 : (G)0), s_maxy1 = py1 > ty1 ? (G)1 : (py1 == ty1 ? (G)0.5 : (G)0);
+        const G s_maxx2 = px2 > tx2 ? (G)1 : (px2 == tx2 ? (G)0.5 : (G)0), s_minx1 = px1 < tx1 ? (G)1 : (px1 == tx1 ? (G)0.5 : (G)0);
+        const G s_maxy2 = py2 > ty2 ? (G)1 : (py2 == ty2 ? (G)0.5 : (G)0), s_miny1 = py1 < ty1 ? (G)1 : (py1 == ty1 ? (G)0.5 : (G)0);
+        const G den = (G)uni + (G)e;
+        const G r = (G)pw / (G)ph;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double diw = iw_pos ? (s_minx2 * dpx2[q] - s_maxx1 * dpx1[q]) : 0.0;
-            const double dih = ih_pos ? (s_miny2 * dpy2[q] - s_maxy1 * dpy1[q]) : 0.0;
-            const double dinter = diw * ih + iw * dih;
-            const double dpwph = (q == 2 ? (double)ph : 0.0) + (q == 3 ? (double)pw : 0.0);
-            const double duni = dpwph - dinter;
-            const double diou = dinter / den - (double)inter * duni / (den * den);
-            const double dcw = s_maxx2 * dpx2[q] - s_minx1 * dpx1[q];
-            const double dch = s_maxy2 * dpy2[q] - s_miny1 * dpy1[q];
-            const double dc2 = 2.0 * cw * dcw + 2.0 * ch * dch;
-            const double drho2 = (q == 0 ? 2.0 * dx : 0.0) + (q == 1 ? 2.0 * dy : 0.0);
-            const double dr = (q == 2 ? 1.0 / (double)ph : 0.0) + (q == 3 ? -(double)pw / ((double)ph * ph) : 0.0);
-            const double dv = (double)k4pi2 * 2.0 * (double)dat * (-(dr / (1.0 + r * r)));
-            const double av = (q >= 2) ? (double)a * dv : 0.0;  // v depends on (w,h) only: a NaN alpha never reaches x,y
-            g[q] = diou - (drho2 / c2 - (double)rho2 * dc2 / ((double)c2 * c2) + av);
+            const G diw = iw_pos ? (s_minx2 * dpx2[q] - s_maxx1 * dpx1[q]) : (G)0;
+            const G dih = ih_pos ? (s_miny2 * dpy2[q] - s_maxy1 * dpy1[q]) : (G)0;
+            const G dinter = diw * ih + iw * dih;
+            const G dpwph = (q == 2 ? (G)ph : (G)0) + (q == 3 ? (G)pw : (G)0);
+            const G duni = dpwph - dinter;
+            const G diou = dinter / den - (G)inter * duni / (den * den);
+            const G dcw = s_maxx2 * dpx2[q] - s_minx1 * dpx1[q];
+            const G dch = s_maxy2 * dpy2[q] - s_miny1 * dpy1[q];
+            const G dc2 = (G)2 * cw * dcw + (G)2 * ch * dch;
+            const G drho2 = (q == 0 ? (G)2 * dx : (G)0) + (q == 1 ? (G)2 * dy : (G)0);
+            const G dr = (q == 2 ? (G)1 / (G)ph : (G)0) + (q == 3 ? -(G)pw / ((G)ph * ph) : (G)0);
+            const G dv = (G)k4pi2 * (G)2 * (G)dat * (-(dr / ((G)1 + r * r)));
+            const G av = (q >= 2) ? (G)a * dv : (G)0;  // v depends on (w,h) only: a NaN alpha never reaches x,y
+            g[q] = diou - (drho2 / c2 - (G)rho2 * dc2 / ((G)c2 * c2) + av);
         }
     }
     return ciou;
@@ -213,7 +214,7 @@ __global__ void ciou_fwd_kernel(const float *p, const float *t, long long M, flo
     if (m >= M) return;
     const float4 pp = reinterpret_cast<const float4 *>(p)[m], tt = reinterpret_cast<const float4 *>(t)[m];
     const float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ta[4] = {tt.x, tt.y, tt.z, tt.w};
-    out[m] = ciou_eval(pa, ta, e, nullptr);
+    out[m] = ciou_eval<double>(pa, ta, e, nullptr);
 }
 
 __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go, long long M, float e, float *gp)
@@ -223,7 +224,7 @@ __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go,
     const float4 pp = reinterpret_cast<const float4 *>(p)[m], tt = reinterpret_cast<const float4 *>(t)[m];
     const float pa[4] = {pp.x, pp.y, pp.z, pp.w}, ta[4] = {tt.x, tt.y, tt.z, tt.w};
     double g[4];
-    ciou_eval(pa, ta, e, g);
+    ciou_eval<double>(pa, ta, e, g);
     const double s = go[m];
     reinterpret_cast<float4 *>(gp)[m] = make_float4((float)(s * g[0]), (float)(s * g[1]), (float)(s * g[2]), (float)(s * g[3]));
 }
@@ -279,6 +280,15 @@ __device__ __forceinline__ float bce_logits(float x, float t)
     return __fsub_rn(__fmul_rn(__fsub_rn(1.0f, t), x), ls);
 }
 
+// class-term variant on the fast exp / log units: |error| < 3e-7 per element against bce_logits(), far inside
+// the rtol 1e-5 bar of a mean over M*C terms (the objectness term keeps the accurate form)
+__device__ __forceinline__ float bce_logits_fast(float x, float t)
+{
+    const float ls = fminf(x, 0.0f) - __logf(1.0f + __expf(-fabsf(x)));
+    return (1.0f - t) * x - ls;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
 constexpr int LOSS_THREADS = 256;
 
 __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
@@ -303,10 +313,10 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
         const float obj = __ldg(row);
         const float4 tb = reinterpret_cast<const float4 *>(S.box)[m];
         const float t[4] = {tb.x, tb.y, tb.z, tb.w};
-        double g[4];
-        const float ci = ciou_eval(p, t, 1e-7f, g);
+        float g[4];
+        const float ci = ciou_eval<float>(p, t, 1e-7f, g);
         S.ciou[m] = ci;
-        S.gbox[m] = make_float4((float)g[0], (float)g[1], (float)(g[2] * (double)aw), (float)(g[3] * (double)ah));
+        S.gbox[m] = make_float4(g[0], g[1], g[2] * aw, g[3] * ah);
         atomicMax(&S.winner[cell], (int)m);
         a0 += (double)__fsub_rn(1.0f, ci);
         a1 += (double)ci;
@@ -326,7 +336,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
             const float *row = S.preds + (long long)S.cell[m] * D + 1;
             for (int c = gl; c < C; c += 8) {
                 const float x = __ldg(row + c);
-                bsum += bce_logits(x, c == tc ? k.cp : k.cn);
+                bsum += bce_logits_fast(x, c == tc ? k.cp : k.cn);
                 if (x > best) { best = x; bi = c; }
             }
         }
@@ -386,40 +396,39 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
     }
 }
 
-// fixed-order final reduction -> scalars[3,8] and the combined loss
-__global__ void __launch_bounds__(256) loss_finalize_kernel(Loss3K k)
+// fixed-order final reduction -> scalars[3,8] and the combined loss; 768 threads, 256 per scale
+__global__ void __launch_bounds__(768) loss_finalize_kernel(Loss3K k)
 {
-    __shared__ double s_red[8][7];
+    __shared__ double s_red[3][8][7];
     __shared__ double s_terms[3][3];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int sc = 0; sc < 3; ++sc) {
-        const LossScale &S = k.s[sc];
-        double v[7] = {0, 0, 0, 0, 0, 0, 0};
-        for (int b = threadIdx.x; b < k.nblk_match; b += 256)
-            for (int q = 0; q < 4; ++q) v[q] += S.part_match[(long long)b * 4 + q];
-        for (int b = threadIdx.x; b < k.nblk_dense; b += 256)
-            for (int q = 0; q < 3; ++q) v[4 + q] += S.part_dense[(long long)b * 3 + q];
-        for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
-        if (lane == 0) for (int q = 0; q < 7; ++q) s_red[wid][q] = v[q];
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s[7];
-            for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[w][q]; }
-            const double M = (double)*S.M;
-            const double nan = __longlong_as_double(0x7ff8000000000000LL);
-            double *o = k.scalars + 8 * sc;
-            o[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
-            o[1] = s[4] / (double)S.cells;
-            o[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
-            o[3] = M > 0 ? s[1] / M : nan;
-            o[4] = M > 0 ? s[2] / M : nan;
-            o[5] = s[6] > 0 ? s[5] / s[6] : nan;
-            o[6] = M;
-            o[7] = s[6];
-            s_terms[sc][0] = S.scale_w * o[0]; s_terms[sc][1] = S.scale_w * o[1]; s_terms[sc][2] = S.scale_w * o[2];
-        }
-        __syncthreads();
+    const int sc = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int lane = t & 31, wid = t >> 5;
+    const LossScale &S = k.s[sc];
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = t; b < k.nblk_match; b += 256)
+        for (int q = 0; q < 4; ++q) v[q] += S.part_match[(long long)b * 4 + q];
+    for (int b = t; b < k.nblk_dense; b += 256)
+        for (int q = 0; q < 3; ++q) v[4 + q] += S.part_dense[(long long)b * 3 + q];
+    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0) for (int q = 0; q < 7; ++q) s_red[sc][wid][q] = v[q];
+    __syncthreads();
+    if (t == 0) {
+        double s[7];
+        for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[sc][w][q]; }
+        const double M = (double)*S.M;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        double *o = k.scalars + 8 * sc;
+        o[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
+        o[1] = s[4] / (double)S.cells;
+        o[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
+        o[3] = M > 0 ? s[1] / M : nan;
+        o[4] = M > 0 ? s[2] / M : nan;
+        o[5] = s[6] > 0 ? s[5] / s[6] : nan;
+        o[6] = M;
+        o[7] = s[6];
+        s_terms[sc][0] = S.scale_w * o[0]; s_terms[sc][1] = S.scale_w * o[1]; s_terms[sc][2] = S.scale_w * o[2];
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
         const double lbox = s_terms[0][0] + s_terms[1][0] + s_terms[2][0];
         const double lconf = s_terms[0][1] + s_terms[1][1] + s_terms[2][1];
@@ -428,114 +437,123 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(Loss3K k)
     }
 }
 
-struct BwdScales { double conf, cls, box; };
+struct BwdScales { float conf, cls, box; };
 __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale &S)
 {
     const double go = (double)(k.go_dev ? *k.go_dev : k.go_host) * S.scale_w;
     const int M = *S.M;
     BwdScales r;
-    r.conf = k.conf_w * go / (double)S.cells;
-    r.cls = M > 0 ? k.class_w * go / ((double)M * (double)k.C) : 0.0;
-    r.box = M > 0 ? -k.box_w * go / (double)M : 0.0;
+    r.conf = (float)(k.conf_w * go / (double)S.cells);
+    r.cls = M > 0 ? (float)(k.class_w * go / ((double)M * (double)k.C)) : 0.0f;
+    r.box = M > 0 ? (float)(-k.box_w * go / (double)M) : 0.0f;
     return r;
 }
 
-// gradient of element (row, col); m = winner of the row (-1: unmatched), x = the prediction at (row, col)
-__device__ __forceinline__ float bwd_elem(const Loss3K &k, const LossScale &S, const BwdScales &sc, long long row, int col,
-                                          int m, float x)
+// class / box gradient of element (col >= 1) of a row whose last match is m; x = the prediction there
+__device__ __forceinline__ float bwd_match_elem(const Loss3K &k, const LossScale &S, const BwdScales &sc, int col, int m, float x)
 {
-    if (col == 0) return (float)(sc.conf * (double)S.gobj[row]);
-    if (m < 0) return 0.0f;
-    if (col <= k.C) {
-        const double t = (col - 1 == S.cls[m]) ? (double)k.cp : (double)k.cn;
-        return (float)(sc.cls * ((double)sigmoid_acc(x) - t));
-    }
-    const float *g = reinterpret_cast<const float *>(S.gbox + m);
-    return (float)(sc.box * (double)g[col - k.C - 1]);
+    if (col <= k.C) return sc.cls * (sigmoid_fast(x) - ((col - 1 == S.cls[m]) ? k.cp : k.cn));
+    return sc.box * reinterpret_cast<const float *>(S.gbox + m)[col - k.C - 1];
 }
 
+// One warp per chunk of 32 rows (32*D elements, 16-byte aligned because 32*D*4 is): the lanes first fetch the
+// chunk's winners and objectness residuals (one coalesced load each), then stream the chunk out as float4
+// stores; which row an element belongs to is index arithmetic, its row data comes from the owning lane by shuffle.
 constexpr int BWD_THREADS = 256;
-constexpr int BWD_F4_PER_THREAD = 8;
 
+template <int DT>  // compile-time row length (division by a constant); 0 = runtime
 __global__ void __launch_bounds__(BWD_THREADS) loss_bwd_dense_kernel(Loss3K k)
 {
     const LossScale &S = k.s[blockIdx.y];
     const BwdScales sc = bwd_scales(k, S);
-    const u32 D = (u32)k.D;
-    const long long total = S.cells * (long long)D;
-    const long long nf4 = total >> 2;
-    constexpr int CH = BWD_THREADS * BWD_F4_PER_THREAD;
-    float4 *g4 = reinterpret_cast<float4 *>(S.grad);
-    const float4 *p4 = reinterpret_cast<const float4 *>(S.preds);
-    for (long long f0 = (long long)blockIdx.x * CH; f0 < nf4; f0 += (long long)gridDim.x * CH) {
-        const long long row0 = (4 * f0) / D;
-        const u32 rem0 = (u32)(4 * f0 - row0 * D);
-#pragma unroll 2
-        for (int i = 0; i < BWD_F4_PER_THREAD; ++i) {
-            const u32 lf = (u32)i * BWD_THREADS + threadIdx.x;
-            const long long f = f0 + lf;
-            if (f >= nf4) break;
-            const u32 e = rem0 + 4 * lf;
-            const u32 q = e / D, r = e - q * D;
-            const long long row = row0 + q;
-            const bool two = r + 3 >= D && row + 1 < S.cells;  // the four elements straddle a row boundary
-            const int mA = S.winner[row];
-            const int mB = two ? S.winner[row + 1] : -1;
+    const u32 D = DT ? (u32)DT : (u32)k.D;
+    const int lane = threadIdx.x & 31;
+    const long long nchunks = (S.cells + 31) >> 5;
+    const long long gw = (long long)blockIdx.x * (BWD_THREADS / 32) + (threadIdx.x >> 5);
+    const long long nw = (long long)gridDim.x * (BWD_THREADS / 32);
+    for (long long ch = gw; ch < nchunks; ch += nw) {
+        const long long row0 = ch << 5;
+        const int nrows = (int)min((long long)32, S.cells - row0);
+        const int win = lane < nrows ? S.winner[row0 + lane] : -1;
+        const float go = lane < nrows ? sc.conf * S.gobj[row0 + lane] : 0.0f;
+        const bool any = __ballot_sync(0xffffffffu, win >= 0) != 0;
+        const long long e0 = row0 * D;
+        float4 *g4 = reinterpret_cast<float4 *>(S.grad + e0);
+        const float4 *p4 = reinterpret_cast<const float4 *>(S.preds + e0);
+        const u32 nelem = (u32)nrows * D, nf4 = nelem >> 2;
+        for (u32 f0 = 0; f0 < nf4; f0 += 32) {
+            const u32 f = f0 + lane;
+            const u32 e = 4 * f;
+            const u32 q = e / D, r = e - q * D;         // first element: row q of the chunk, column r
+            const bool straddle = r + 3 >= D;           // columns r..D-1 of row q, then 0.. of row q+1
+            const u32 qo = (r == 0) ? q : q + 1;        // the row whose objectness column may sit in this vector
+            const float gobj = __shfl_sync(0xffffffffu, go, qo & 31);
             float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (mA < 0 && mB < 0) {
-                if (r == 0) v[0] = (float)(sc.conf * (double)S.gobj[row]);
-                else if (two) {
-                    const float go1 = (float)(sc.conf * (double)S.gobj[row + 1]);
-                    const u32 pos = D - r;  // 1..3
-                    v[1] = pos == 1 ? go1 : 0.f; v[2] = pos == 2 ? go1 : 0.f; v[3] = pos == 3 ? go1 : 0.f;
-                }
-            } else {
-                const float4 x4 = __ldg(p4 + f);
-                const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+            if (r == 0) v[0] = gobj;
+            else if (straddle) {
+                const u32 pos = D - r;
+                v[1] = pos == 1 ? gobj : 0.f; v[2] = pos == 2 ? gobj : 0.f; v[3] = pos == 3 ? gobj : 0.f;
+            }
+            if (any) {
+                const int mA = __shfl_sync(0xffffffffu, win, q & 31);
+                const int mB = __shfl_sync(0xffffffffu, win, (q + 1) & 31);
+                if (f < nf4 && (mA >= 0 || (straddle && mB >= 0))) {
+                    const float4 x4 = __ldg(p4 + f);
+                    const float x[4] = {x4.x, x4.y, x4.z, x4.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const u32 col = r + j;
-                    if (col < D) v[j] = bwd_elem(k, S, sc, row, (int)col, mA, x[j]);
-                    else if (row + 1 < S.cells) v[j] = bwd_elem(k, S, sc, row + 1, (int)(col - D), mB, x[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        const u32 col = r + j;
+                        if (col < D) { if (col > 0 && mA >= 0) v[j] = bwd_match_elem(k, S, sc, (int)col, mA, x[j]); }
+                        else if (col > D && mB >= 0) v[j] = bwd_match_elem(k, S, sc, (int)(col - D), mB, x[j]);
+                    }
                 }
             }
-            g4[f] = make_float4(v[0], v[1], v[2], v[3]);
+            if (f < nf4) g4[f] = make_float4(v[0], v[1], v[2], v[3]);
         }
-    }
-    // the last total % 4 elements (only when cells * D is not a multiple of four)
-    if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
-        const long long e = (nf4 << 2) + threadIdx.x;
-        const long long row = e / D;
-        const int col = (int)(e - row * D);
-        S.grad[e] = bwd_elem(k, S, sc, row, col, S.winner[row], S.preds[e]);
+        // the last nelem % 4 elements (only in the final chunk, when cells * D is not a multiple of four)
+        const u32 tail = nelem & 3;
+        if (lane < tail) {
+            const u32 e = (nf4 << 2) + lane;
+            const u32 q = e / D, col = e - q * D;
+            const int m = S.winner[row0 + q];
+            float v = 0.f;
+            if (col == 0) v = sc.conf * S.gobj[row0 + q];
+            else if (m >= 0) v = bwd_match_elem(k, S, sc, (int)col, m, S.preds[e0 + e]);
+            S.grad[e0 + e] = v;
+        }
     }
 }
 
 // matches that are not the last match of their cell add their class / box gradients to the row
+// (gather backward = index_put(accumulate=True)); one thread per match finds them, the warp then works
+// through its finds together
 __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_dup_kernel(Loss3K k)
 {
     const LossScale &S = k.s[blockIdx.y];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gl = lane & 7;
+    const int lane = threadIdx.x & 31;
     const int M = *S.M;
     if (M <= 0) return;
     const BwdScales sc = bwd_scales(k, S);
     const int C = k.C, D = k.D;
-    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
-         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
-        const long long m = mb + (lane >> 3);
-        if (m >= M) continue;
-        const int cell = S.cell[m];
-        if (S.winner[cell] == (int)m) continue;  // written by the dense kernel
-        const int tc = S.cls[m];
-        const float *row = S.preds + (long long)cell * D;
-        float *grow = S.grad + (long long)cell * D;
-        for (int c = gl; c < C; c += 8) {
-            const double t = (c == tc) ? (double)k.cp : (double)k.cn;
-            atomicAdd(grow + 1 + c, (float)(sc.cls * ((double)sigmoid_acc(__ldg(row + 1 + c)) - t)));
+    for (long long m0 = ((long long)blockIdx.x * LOSS_THREADS + threadIdx.x) - lane; m0 < M; m0 += (long long)gridDim.x * LOSS_THREADS) {
+        const long long m = m0 + lane;
+        int cell = -1;
+        if (m < M) {
+            cell = S.cell[m];
+            if (S.winner[cell] == (int)m) cell = -1;  // the last match of a cell was written by the dense kernel
         }
-        if (gl < 4) {
-            const float *g = reinterpret_cast<const float *>(S.gbox + m);
-            atomicAdd(grow + C + 1 + gl, (float)(sc.box * (double)g[gl]));
+        u32 todo = __ballot_sync(0xffffffffu, cell >= 0);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int c2 = __shfl_sync(0xffffffffu, cell, src);
+            const long long mm = m0 + src;
+            const int tc = S.cls[mm];
+            const float *row = S.preds + (long long)c2 * D;
+            float *grow = S.grad + (long long)c2 * D;
+            for (int c = lane; c < C; c += 32)
+                atomicAdd(grow + 1 + c, sc.cls * (sigmoid_fast(__ldg(row + 1 + c)) - ((c == tc) ? k.cp : k.cn)));
+            if (lane < 4) atomicAdd(grow + C + 1 + lane, sc.box * reinterpret_cast<const float *>(S.gbox + mm)[lane]);
         }
     }
 }
