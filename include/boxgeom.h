@@ -86,7 +86,8 @@ typedef struct {
     int32_t tracked[BG_MAX_TRACKED];
     int32_t order;              /* 0: image-major, score-descending inside an image; 1: globally score-descending (reference row order) */
     int32_t variant;            /* decode kernel tile loads: 0 auto, 1 plain loads, 2 TMA bulk pipeline (needs 16-byte aligned inputs) */
-    int32_t nms_path;           /* 0 auto (one CTA per image when the threshold allows), 1 general segmented engine, 2 per-image only */
+    int32_t nms_path;           /* 0 auto (per-image CTAs when the threshold allows), 1 general segmented engine,
+                                 * 2 per-image only, 3 per-image only with one CTA per image (no helper CTA) */
 } bg_detect_params;
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);

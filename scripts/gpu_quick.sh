@@ -1,9 +1,10 @@
 #!/bin/bash
-# quick GPU pass: parity suite, bench line, training timings (default and with 32-byte L2 fetch granularity)
+# quick GPU pass: parity suite, bench line (PDL on / off), training timings
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -n 3 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_quick.log 2>&1; echo "bench rc=$?"
 tail -n 1 gpurun_out/bench_quick.log
+BG_PDL=0 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_nopdl.log 2>&1; echo "bench nopdl rc=$?"
+tail -n 1 gpurun_out/bench_nopdl.log | cut -c1-220
 timeout 300 python scripts/prof_train.py > gpurun_out/train_plain.log 2>&1; tail -n 1 gpurun_out/train_plain.log
-timeout 300 python scripts/prof_train.py --l2-fetch 32 > gpurun_out/train_l2_32.log 2>&1; tail -n 2 gpurun_out/train_l2_32.log

@@ -117,7 +117,7 @@ def test_detect_golden(ops, name, variant):
     assert np.array_equal(got[:, 1], ref_rows[:, 1])
 
 
-@pytest.mark.parametrize("nms_path", ["auto", "general"])
+@pytest.mark.parametrize("nms_path", ["auto", "general", "per_image_single"])
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,W,C,dist,og,iou,thr,allow,tracked,order", [
     (2, 96, 64, 3, "N", (120, 100), 0.5, 0.2, 4, None, "image"),        # non-square, rescale, even row length (D=8)
@@ -145,9 +145,10 @@ def test_detect_paths_agree_exactly(ops):
     for iou in (0.65, 0.3, 0.1):
         a = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="auto")
         a = [t.clone() for t in (a.pred_boxes, a.sample_idxs, a.keep_idxs, a.counts)]
-        g = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="general")
-        for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
-            assert torch.equal(x, y), iou
+        for path in ("general", "per_image_single"):
+            g = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path=path)
+            for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
+                assert torch.equal(x, y), (iou, path)
 
 
 def test_detect_config2_full_size(ops):

@@ -2,6 +2,7 @@
 // Single translation unit (the kernels live in the *_kernels.cuh headers), built for sm_100a only:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -105,6 +106,9 @@ struct DetWs {
     long long *f_seg_off;
     int *f_emit_count;
     int *cand_count;
+    u32 *gflag;           // split mode hand-over (helper CTA -> main CTA)
+    u32 *gedges;
+    u64 *gsorted;
     u64 *f_emit_key;      // globally ordered output only
     float4 *f_emit_box;
     int *f_emit_cls;
@@ -128,6 +132,11 @@ static size_t det_carve(unsigned char *base, int B, long long N, int tiles_per_i
     w.f_seg_off = b.take<long long>((size_t)B + 1);
     w.f_emit_count = b.take<int>(B);
     w.cand_count = b.take<int>(B);
+    w.gflag = b.take<u32>(2 * (size_t)B);
+    if (!general) {
+        w.gedges = b.take<u32>((size_t)B * INMS_HCAP);
+        w.gsorted = b.take<u64>((size_t)B * INMS_CAP);
+    }
     w.stride = (long long)next_pow2((u32)N);
     if (general) {
         w.box_dense = b.take<float4>((size_t)B * N);
@@ -184,7 +193,7 @@ static int det_nms_path(const bg_detect_params *p, const TilePlan &tp)
     const IouThr t = make_iou_thr(p->iou_threshold);
     const bool ok = t.fast_ok && !t.zero_suppresses && t.tdn >= 0.05f && t.tdn < 1.0f && tp.tpi_total < INMS_MAXT &&
                     det_candidates(p) <= INMS_MAX_N && p->C <= 65535;
-    if (p->nms_path == 2) return ok ? 0 : -1;
+    if (p->nms_path == 2 || p->nms_path == 3) return ok ? 0 : -1;
     return ok ? 0 : 1;
 }
 
@@ -342,6 +351,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     DecodeOut o;
     o.tile_count = w.tile_count; o.hdr = w.hdr; o.chain = w.chain; o.seg_off = w.f_seg_off;
     o.force_plain = (pp->variant == 1 || !aligned) ? 1 : 0;
+    o.gflag = w.gflag;
     const bool prof = g_prof_start && g_prof_stop;
     if (prof) cudaEventRecord(g_prof_start, st);
     {
@@ -371,8 +381,24 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
         q.out_boxes = out_boxes; q.out_img = reinterpret_cast<long long *>(out_img);
         q.out_keep = reinterpret_cast<long long *>(out_keep); q.out_counts = out_counts;
         q.stamps = g_prof_stamps;
-        image_nms_kernel<<<pp->B, INMS_THREADS, sizeof(ImgNmsSmem), st>>>(q);
-        BG_LAUNCH_CHECK();
+        {   // two CTAs per image (helper + main) while every CTA of the grid can be resident at once
+            static const int split_env = []() { const char *e = getenv("BG_NMS_SPLIT"); return e ? atoi(e) : -1; }();
+            q.split = pp->nms_path == 3 ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
+        }
+        q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted;
+        {   // programmatic dependent launch: the CTAs become resident while the decode kernel drains
+            static const bool pdl = []() { const char *e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3(pp->B * (q.split ? 2 : 1)); cfg.blockDim = dim3(INMS_THREADS);
+            cfg.dynamicSmemBytes = sizeof(ImgNmsSmem); cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+            if (cudaLaunchKernelEx(&cfg, image_nms_kernel, q) != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
+            ++g_launches;
+        }
         if (pp->order) {
             SegNms v;
             memset(&v, 0, sizeof(v));

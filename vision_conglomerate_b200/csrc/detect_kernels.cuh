@@ -57,7 +57,8 @@ __device__ __forceinline__ float4 decode_xyxy(const DetectK &k, const ScaleDesc 
         bh = __fmul_rn(__fdiv_rn(bh, k.fH), k.fH0);
     }
     if (k.use_allowance) { bw = __fadd_rn(bw, k.allowance); bh = __fadd_rn(bh, k.allowance); }
-    const float x1 = __fsub_rn(bx, __fdiv_rn(bw, 2.0f)), y1 = __fsub_rn(by, __fdiv_rn(bh, 2.0f));
+    // w / 2 == w * 0.5 exactly (power-of-two scaling)
+    const float x1 = __fsub_rn(bx, __fmul_rn(bw, 0.5f)), y1 = __fsub_rn(by, __fmul_rn(bh, 0.5f));
     return make_float4(x1, y1, __fadd_rn(x1, bw), __fadd_rn(y1, bh));
 }
 
@@ -154,6 +155,7 @@ struct DecodeOut {
     u64 *chain;              // [B+1] look-back words
     long long *seg_off;      // [B+1] b*N (row offset of the image's emit list)
     int force_plain;         // 1: never use TMA (unaligned inputs, variant 1)
+    u32 *gflag;              // [2B] helper -> main flags of the split per-image NMS (zeroed here)
 };
 
 template <int CT>  // compile-time class count (fully unrolled row scan); 0 = take it from the parameters
@@ -169,6 +171,8 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
     const int stage_floats = tp.TR * D;
     float *ring = reinterpret_cast<float *>(dec_smem);
 
+    // let the dependent per-image NMS kernel be scheduled as SMs free up (it waits for this grid to finish)
+    cudaTriggerProgrammaticLaunchCompletion();
     // scratch of the per-image NMS kernel that follows in the stream
     if (blockIdx.x == 0) {
         if (tid == 0) { o.hdr->ticket = 0; o.hdr->done = 0; o.hdr->status = 0; o.hdr->pad = 0; }
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
             o.chain[b] = (b == 0) ? CHAIN_PREFIX : 0ull;
             o.seg_off[b] = (long long)b * k.N;
         }
+        for (int i = tid; i < 2 * k.B; i += DEC_THREADS) o.gflag[i] = 0u;
     }
 
     auto tile_src = [&](int t, int &b, int &si, int &lrow0, int &rows) -> const float * {

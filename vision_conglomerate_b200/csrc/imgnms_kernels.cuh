@@ -25,11 +25,13 @@ namespace bg {
 constexpr int INMS_THREADS = 1024;
 constexpr int INMS_CAP = 4096;       // survivors per image held in shared memory
 constexpr int INMS_PBITS = 12;       // bits of p inside the sort key
-constexpr int INMS_ECAP = 16384;     // overlap edges per image
+constexpr int INMS_ECAP = 12288;     // overlap edges per image
 constexpr int INMS_MAXT = 1024;      // tiles per image
 constexpr int INMS_GMAX = 64;        // grid cells per axis
 constexpr int INMS_ITEMS = 8192;     // (box, grid row) work items per pass
 constexpr int INMS_MAX_N = 1 << (32 - INMS_PBITS);  // candidates per image (key = score | idx | p)
+constexpr int INMS_HCAP = 4096;      // edges a helper CTA may hand over
+constexpr int INMS_HELPER_SHARE_32 = 7;  // the helper takes 7/32 of the pair-test items (it also does the sort)
 
 struct ImgNmsK {
     int B, N, TR, tpi_total;
@@ -54,6 +56,11 @@ struct ImgNmsK {
     long long *out_img, *out_keep;
     int32_t *out_counts;
     unsigned long long *stamps;  // optional [B, INMS_STAMPS] globaltimer (ns) at the stage boundaries (profiling hook)
+    // split mode (two CTAs per image when the GPU has room): the helper tests a share of the pairs and sorts the keys
+    int split;
+    u32 *gflag;                // [B,2] helper -> main: edge count + 1, sorted keys ready
+    u32 *gedges;               // [B, INMS_HCAP]
+    u64 *gsorted;              // [B, INMS_CAP]
 };
 constexpr int INMS_STAMPS = 10;
 
@@ -63,7 +70,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-#define INMS_STAMP(i) do { if (k.stamps && tid == 0) k.stamps[(long long)b * INMS_STAMPS + (i)] = globaltimer_ns(); } while (0)
+#define INMS_STAMP(i) do { if (k.stamps && tid == 0 && role == 1) k.stamps[(long long)b * INMS_STAMPS + (i)] = globaltimer_ns(); } while (0)
 
 struct ImgNmsSmem {
     u64 keys[INMS_CAP];                          // (~score | idx | p); indexed by p until the sort
@@ -83,6 +90,7 @@ struct ImgNmsSmem {
         struct { unsigned char state[INMS_CAP], blocked[INMS_CAP]; };          // stage 4..6: 0 undecided, 1 kept, 2 suppressed
     };
     unsigned short cls[INMS_CAP];                // by p
+    u32 whc[INMS_CAP];                           // stage 3: (w, h) of the boxes in cell order, truncated to bf16 pairs
     int wsum[33];
     float red[4][32];
     int n_edges;
@@ -211,9 +219,15 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     ImgNmsSmem &S = *reinterpret_cast<ImgNmsSmem *>(inms_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
-    if (tid == 0) S.img = (int)atomicAdd(&k.hdr->ticket, 1u);  // dynamic image order: predecessors are running or done
+    // launched with programmatic stream serialization: the CTA may become resident while the decode kernel
+    // drains; everything it reads is produced by that kernel, so wait for it here
+    cudaGridDependencySynchronize();
+    if (tid == 0) S.img = (int)atomicAdd(&k.hdr->ticket, 1u);  // dynamic order: whoever a CTA waits for holds an earlier ticket
     __syncthreads();
-    const int b = S.img;
+    // split mode: tickets 2b (helper: a share of the pair tests, then the sort) and 2b+1 (main: everything else).
+    // The main CTA waits for its helper and for the main CTAs of earlier images only -- all earlier tickets.
+    const int b = k.split ? (S.img >> 1) : S.img;
+    const int role = k.split ? (S.img & 1) : 1;
     if (b >= k.B) return;
     const long long ibase = (long long)b * k.N;
     INMS_STAMP(0);
@@ -301,7 +315,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     __syncthreads();
     for (int i = tid; i < K; i += INMS_THREADS) {
         const unsigned short cell = S.cell_of[i];
-        if (cell != 0xffff) S.cellord[S.cell_start[cell] + S.rank_in_cell[i]] = (unsigned short)i;
+        if (cell != 0xffff) {
+            const int pos = S.cell_start[cell] + S.rank_in_cell[i];
+            const float4 bx = S.box[i];
+            S.cellord[pos] = (unsigned short)i;
+            // extents rounded toward zero to bf16: stored <= true < stored * (1 + 2^-7)
+            S.whc[pos] = (__float_as_uint(__fsub_rn(bx.z, bx.x)) >> 16) | (__float_as_uint(__fsub_rn(bx.w, bx.y)) & 0xffff0000u);
+        }
     }
     // Work items = (box, grid row) for the rows from the box's own row down to the end of its reach: a pair in
     // different cells is tested by the box whose cell comes first in row-major order, a pair inside one cell
@@ -326,14 +346,17 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
 
     // ---- 3. pair tests, item-parallel ------------------------------------------------------------------------
     const IouThr thr = k.thr;
-    for (int c0 = 0; c0 < T; c0 += INMS_ITEMS) {
+    const int T_helper = k.split ? (int)(((long long)T * INMS_HELPER_SHARE_32) >> 5) : 0;
+    const int it_lo = role == 1 ? T_helper : 0, it_hi = role == 1 ? T : T_helper;
+    for (int c0 = it_lo; c0 < it_hi; c0 += INMS_ITEMS) {
+        const int nit = min(INMS_ITEMS, it_hi - c0);
         {   // publish the items of this pass
             int it = item0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 for (int r = 0; r < nrow[q]; ++r, ++it) {
                     const int rel = it - c0;
-                    if (rel >= 0 && rel < INMS_ITEMS) {
+                    if (rel >= 0 && rel < nit) {
                         S.item_owner[rel] = (unsigned short)(tid * 4 + q);
                         S.item_row[rel] = (unsigned char)(y0[q] + r);
                     }
@@ -341,7 +364,6 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
             }
         }
         __syncthreads();
-        const int nit = min(INMS_ITEMS, T - c0);
         for (int it = tid; it < nit; it += INMS_THREADS) {
             const int i = S.item_owner[it];
             const int gy = S.item_row[it];
@@ -355,27 +377,27 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
             const int x0 = own_row ? ax : gr.cx(cx - rx), x1 = gr.cx(cx + rx);
             const int qa = S.cell_start[gy * G + x0], qb = S.cell_start[gy * G + x1 + 1];
             const int q_own = own_row ? S.cell_start[gy * G + ax + 1] : qa;  // entries below q_own share my cell
-            // IoU > t needs both extent ratios above t: cheap conservative reject (1 % slack covers the fp32 rounding)
-            const float wlo = 0.99f * thr.tdn * w, hlo = 0.99f * thr.tdn * h;
-            const float wsc = 0.99f * thr.tdn, w_me = w, h_me = h;
+            // IoU > t needs both extent ratios above t.  Conservative reject on the bf16 extents kept in cell
+            // order (1 % slack for the fp32 rounding of the exact test, 2^-7 for the truncation), so most
+            // entries cost one 4-byte load and never touch the partner's box.
+            const float wlo = 0.99f * thr.tdn * w, hlo = 0.99f * thr.tdn * h, tsc = 0.99f * thr.tdn;
             for (int q = qa; q < qb; q += 4) {
-                int jj[4];
-                float4 cb[4];
+                u32 wh[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) jj[u] = (q + u < qb) ? (int)S.cellord[q + u] : -1;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) cb[u] = S.box[jj[u] < 0 ? 0 : jj[u]];
+                for (int u = 0; u < 4; ++u) wh[u] = (q + u < qb) ? S.whc[q + u] : 0u;  // padding: zero extents, rejected
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (jj[u] < 0 || (q + u < q_own && jj[u] <= i)) continue;
-                    const float4 c = cb[u];
-                    const float wc = __fsub_rn(c.z, c.x), hc = __fsub_rn(c.w, c.y);
-                    if (wc < wlo || hc < hlo || wsc * wc > w_me || wsc * hc > h_me) continue;
-                    if (iou_suppresses(a, aa, c, __fmul_rn(wc, hc), thr)) {
+                    const float wt = __uint_as_float(wh[u] << 16), ht = __uint_as_float(wh[u] & 0xffff0000u);
+                    if (wt * 1.008f < wlo || ht * 1.008f < hlo || tsc * wt > w || tsc * ht > h) continue;
+                    const int j = S.cellord[q + u];
+                    if (q + u < q_own && j <= i) continue;  // same cell: the lower-numbered box owns the test
+                    const float4 c = S.box[j];
+                    const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
+                    if (iou_suppresses(a, aa, c, ac, thr)) {
                         const int e = atomicAdd(&S.n_edges, 1);
                         if (e < INMS_ECAP) {
-                            const bool i_first = S.keys[i] < S.keys[jj[u]];  // earlier in (score desc, index asc) order
-                            S.edges[e] = i_first ? (((u32)i << 16) | (u32)jj[u]) : (((u32)jj[u] << 16) | (u32)i);
+                            const bool i_first = S.keys[i] < S.keys[j];  // earlier in (score desc, index asc) order
+                            S.edges[e] = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
                         }
                     }
                 }
@@ -384,6 +406,46 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         __syncthreads();
     }
     int ne = S.n_edges;
+    if (role == 0) {
+        // ---- helper: hand the edges over, sort the keys, hand them over, done ----
+        u32 *ge = k.gedges + (long long)b * INMS_HCAP;
+        const bool hover = ne > INMS_HCAP;
+        if (!hover) for (int e = tid; e < ne; e += INMS_THREADS) ge[e] = S.edges[e];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ((volatile u32 *)k.gflag)[2 * b] = hover ? 0xffffffffu : (u32)ne + 1u;
+        const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
+        for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
+        __syncthreads();
+        if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
+        else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
+        else inms_sort_reg<4>(S.keys);
+        u64 *gs = k.gsorted + (long long)b * INMS_CAP;
+        for (int j = tid; j < K; j += INMS_THREADS) gs[j] = S.keys[j];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) ((volatile u32 *)k.gflag)[2 * b + 1] = 1u;
+        return;
+    }
+    if (k.split) {   // main: append the helper's edges
+        if (tid == 0) {
+            u32 v;
+            do { v = ((volatile u32 *)k.gflag)[2 * b]; } while (v == 0u);
+            S.img = (int)v;
+        }
+        __syncthreads();
+        const u32 hv = (u32)S.img;
+        __threadfence();
+        if (hv == 0xffffffffu) ne = INMS_ECAP + 1;
+        else {
+            const int nh = (int)hv - 1;
+            const u32 *ge = k.gedges + (long long)b * INMS_HCAP;
+            if (ne <= INMS_ECAP && ne + nh <= INMS_ECAP)
+                for (int e = tid; e < nh; e += INMS_THREADS) S.edges[ne + e] = __ldcg(ge + e);
+            ne += nh;
+        }
+        __syncthreads();
+    }
     if (ne > INMS_ECAP) { over = true; ne = 0; K = 0; }
     INMS_STAMP(3);
 
@@ -413,12 +475,21 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     INMS_STAMP(4);
 
     // ---- 5. sort ------------------------------------------------------------------------------------------------------
-    const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
-    for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
-    __syncthreads();
-    if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
-    else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
-    else inms_sort_reg<4>(S.keys);
+    if (k.split) {   // the helper sorted the keys meanwhile
+        if (tid == 0) { while (((volatile u32 *)k.gflag)[2 * b + 1] == 0u) { } }
+        __syncthreads();
+        __threadfence();
+        const u64 *gs = k.gsorted + (long long)b * INMS_CAP;
+        for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = __ldcg(gs + j);
+        __syncthreads();
+    } else {
+        const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
+        for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
+        __syncthreads();
+        if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
+        else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
+        else inms_sort_reg<4>(S.keys);
+    }
     INMS_STAMP(5);
 
     // ---- 6. emission ---------------------------------------------------------------------------------------------------

@@ -174,7 +174,8 @@ class DetectPlan:
         self.params, self.B, self.dev = p, B, device
         self.N = sum(sh[1] * sh[2] * na for sh in shapes)
         self.hint_key = (device.index, B, self.N, p.iou_threshold, p.score_threshold)
-        p.nms_path = 1 if (nms_path == "general" or _nms_path_hint.get(self.hint_key, 0)) else 0
+        p.nms_path = 1 if (nms_path == "general" or _nms_path_hint.get(self.hint_key, 0)) else \
+            {"per_image": 2, "per_image_single": 3}.get(nms_path, 0)
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
         self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
