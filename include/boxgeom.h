@@ -109,6 +109,10 @@ void bg_profile_events(void *start, void *stop);
  * kernel of bg_detect writes the %globaltimer value (ns) at each of its stage boundaries for every image. */
 void bg_profile_stamps(void *dev_buf);
 int bg_profile_stamps_per_image(void);
+/* Profiling hook: while `dev_buf` ([1024, 8] u64, device) is non-NULL, thread 0 of every CTA of the decode kernel of
+ * bg_detect accumulates the SM clock cycles it spends in each of its 8 phases (wait, phase 1, barrier, list,
+ * phase 2a, barrier + phase 2b, barrier, refill). */
+void bg_profile_decode_cycles(void *dev_buf);
 
 /* DetectionNet._get_scale_pred (modules/detection.py:98-173) for one scale, optionally followed by
  * _bbox_to_size (:175-190): writes the decoded tensor, same shape as raw.  inference = 0 gives the

@@ -22,7 +22,7 @@ STATUS_NEED_GENERAL = 4
 # every symbol include/boxgeom.h declares (tests check that the library exports each of them)
 SYMBOLS = (
     "bg_strerror", "bg_version", "bg_launch_count", "bg_sizeof_detect_params", "bg_sizeof_loss_params", "bg_profile_events",
-    "bg_profile_stamps", "bg_profile_stamps_per_image",
+    "bg_profile_stamps", "bg_profile_stamps_per_image", "bg_profile_decode_cycles",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
     "bg_detect_workspace_bytes", "bg_detect", "bg_decode_scale",
     "bg_assign_workspace_bytes", "bg_assign_targets",
@@ -98,6 +98,8 @@ def lib() -> C.CDLL:
     L.bg_profile_stamps.argtypes = [vp]
     L.bg_profile_stamps.restype = None
     L.bg_profile_stamps_per_image.restype = C.c_int
+    L.bg_profile_decode_cycles.argtypes = [vp]
+    L.bg_profile_decode_cycles.restype = None
     L.bg_batched_nms_workspace_bytes.argtypes = [i64, i64, sz]
     L.bg_batched_nms_workspace_bytes.restype = sz
     L.bg_batched_nms.argtypes = [vp, vp, vp, i64, f64, i64, vp, vp, vp, sz, sz, vp]

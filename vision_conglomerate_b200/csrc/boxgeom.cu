@@ -15,7 +15,7 @@ namespace bg {
 
 unsigned long long g_launches = 0;
 static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
-static unsigned long long *g_prof_stamps = nullptr;
+static unsigned long long *g_prof_stamps = nullptr, *g_prof_cycles = nullptr;
 
 IouThr make_iou_thr(double thr)
 {
@@ -224,6 +224,7 @@ int bg_version(void) { return 100; }
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
 void bg_profile_stamps(void *dev_buf) { g_prof_stamps = (unsigned long long *)dev_buf; }
+void bg_profile_decode_cycles(void *dev_buf) { g_prof_cycles = (unsigned long long *)dev_buf; }
 int bg_profile_stamps_per_image(void) { return INMS_STAMPS; }
 size_t bg_sizeof_detect_params(void) { return sizeof(bg_detect_params); }
 size_t bg_sizeof_loss_params(void) { return sizeof(bg_loss_params); }
@@ -352,6 +353,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     o.tile_count = w.tile_count; o.hdr = w.hdr; o.chain = w.chain; o.seg_off = w.f_seg_off;
     o.force_plain = (pp->variant == 1 || !aligned) ? 1 : 0;
     o.gflag = w.gflag;
+    o.cycles = g_prof_cycles;
     const bool prof = g_prof_start && g_prof_stop;
     if (prof) cudaEventRecord(g_prof_start, st);
     {

@@ -78,11 +78,10 @@ struct TilePlan {
     int total;       // B * tpi_total
 };
 
-__host__ __device__ inline void tile_locate(const DetectK &k, const TilePlan &tp, int t, int &b, int &si, int &lrow0,
-                                            int &rows)
+// (b, r) = (image, tile inside the image) of tile t = b * tpi_total + r; the kernel advances them incrementally
+__host__ __device__ inline void tile_locate(const DetectK &k, const TilePlan &tp, int b, int r, int &si, int &lrow0, int &rows)
 {
-    b = t / tp.tpi_total;
-    int r = t - b * tp.tpi_total;
+    (void)b;
     si = 0;
     if (r >= tp.tpi[0]) { r -= tp.tpi[0]; si = 1; if (r >= tp.tpi[1]) { r -= tp.tpi[1]; si = 2; } }
     lrow0 = r * tp.TR;
@@ -156,6 +155,7 @@ struct DecodeOut {
     long long *seg_off;      // [B+1] b*N (row offset of the image's emit list)
     int force_plain;         // 1: never use TMA (unaligned inputs, variant 1)
     u32 *gflag;              // [2B] helper -> main flags of the split per-image NMS (zeroed here)
+    unsigned long long *cycles;  // optional profiling hook: [gridDim.x, 8] SM clock cycles thread 0 spent per phase
 };
 
 template <int CT>  // compile-time class count (fully unrolled row scan); 0 = take it from the parameters
@@ -183,10 +183,13 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         for (int i = tid; i < 2 * k.B; i += DEC_THREADS) o.gflag[i] = 0u;
     }
 
-    auto tile_src = [&](int t, int &b, int &si, int &lrow0, int &rows) -> const float * {
-        tile_locate(k, tp, t, b, si, lrow0, rows);
+    auto tile_src = [&](int b, int r, int &si, int &lrow0, int &rows) -> const float * {
+        tile_locate(k, tp, b, r, si, lrow0, rows);
         return k.sc[si].raw + ((long long)b * k.sc[si].cells_na + lrow0) * D;
     };
+    // a CTA steps its tile number by gridDim.x: (image, tile in image) advance without divisions
+    const int step_b = (int)gridDim.x / tp.tpi_total, step_r = (int)gridDim.x - step_b * tp.tpi_total;
+    auto advance = [&](int &b, int &r) { b += step_b; r += step_r; if (r >= tp.tpi_total) { r -= tp.tpi_total; ++b; } };
     auto tma_ok = [&](const float *src, int rows) -> bool {
         return !o.force_plain && (((rows * D) & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     };
@@ -194,27 +197,36 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
     if (tid == 0) {
         for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int pb = (int)blockIdx.x / tp.tpi_total, pr = (int)blockIdx.x - pb * tp.tpi_total;
         for (int s = 0; s < DEC_STAGES; ++s) {  // prologue: fill the ring
-            const int t = blockIdx.x + s * gridDim.x;
-            if (t < tp.total) {
-                int b, si, lrow0, rows;
-                const float *src = tile_src(t, b, si, lrow0, rows);
+            if (pb < k.B) {
+                int si, lrow0, rows;
+                const float *src = tile_src(pb, pr, si, lrow0, rows);
                 if (tma_ok(src, rows)) {
                     mbar_expect_tx(&full_bar[s], (u32)(rows * D) * 4);
                     bulk_g2s(ring + (size_t)s * stage_floats, src, (u32)(rows * D) * 4, &full_bar[s]);
                 }
             }
+            advance(pb, pr);
         }
     }
     __syncthreads();
 
     u32 phases = 0;  // bit s = parity the next wait on stage s expects
     int it = 0;
-    for (int t = blockIdx.x; t < tp.total; t += gridDim.x, ++it) {
+    long long cyc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c_prev = 0;
+    const bool prof = o.cycles != nullptr && tid == 0;
+#define DEC_MARK(i) do { if (prof) { const long long c_now = clock64(); cyc[i] += c_now - c_prev; c_prev = c_now; } } while (0)
+    if (prof) c_prev = clock64();
+    int b = (int)blockIdx.x / tp.tpi_total, tr = (int)blockIdx.x - b * tp.tpi_total;  // this tile
+    int nb = b, nr = tr;                                                             // the tile DEC_STAGES steps ahead
+    for (int s = 0; s < DEC_STAGES; ++s) advance(nb, nr);
+    for (; b < k.B; advance(b, tr), advance(nb, nr), ++it) {
+        const int t = b * tp.tpi_total + tr;
         const int stage = it % DEC_STAGES;
         float *tile = ring + (size_t)stage * stage_floats;
-        int b, si, lrow0, rows;
-        const float *src = tile_src(t, b, si, lrow0, rows);
+        int si, lrow0, rows;
+        const float *src = tile_src(b, tr, si, lrow0, rows);
         const ScaleDesc &s = k.sc[si];
         if (tma_ok(src, rows)) {
             mbar_wait(&full_bar[stage], (phases >> stage) & 1u);
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
             __syncthreads();
         }
 
+        DEC_MARK(0);  // tile location + wait for the tile
         // phase 1: one thread per row -- class maximum, score, threshold
         bool alive = false;
         float score = 0.f, wm = -INFINITY, pm = 0.f;
@@ -254,9 +267,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         }
         // list the survivors of this tile in row order (warp ballots + a prefix over the four warps), so that
         // slot order == candidate order and ties in score keep torchvision's lower-index-first rule downstream
+        DEC_MARK(1);  // phase 1
         const u32 am = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) s_wcnt[wid] = __popc(am);
         __syncthreads();
+        DEC_MARK(2);  // barrier: slowest warp of phase 1
         int base = 0, n = 0;
 #pragma unroll
         for (int w2 = 0; w2 < DEC_THREADS / 32; ++w2) {
@@ -266,25 +281,38 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         }
         if (alive) s_surv[base + __popc(am & lanemask_lt())] = Surv{tid, score, wm, pm, 0};
         __syncthreads();
+        DEC_MARK(3);  // survivor list
 
-        // phase 2a: one warp per survivor -- class id = first index whose sigmoid equals the maximum sigmoid
+        // phase 2a: one warp per survivor -- class id = first index whose sigmoid equals the maximum sigmoid.
+        // A logit equal to the maximum always qualifies; a smaller one only inside the tie window (rare), and
+        // only then is its sigmoid evaluated.
         for (int q = wid; q < n; q += DEC_THREADS / 32) {
             const float swm = s_surv[q].wm, spm = s_surv[q].pm;
             const float *sr = tile + s_surv[q].row * D + 1;
             const float lo = swm - tie_window(spm);
-            int ci = 0;
-            for (int c0 = 0; c0 < C; c0 += 32) {
-                const int c = c0 + lane;
-                bool hit = false;
-                if (c < C) {
-                    const float v = sr[c];
-                    hit = v >= lo && (v == swm || sigmoid_acc(v) == spm);
+            int ci = 0x7fffffff;
+            for (int c0 = 0; c0 < C; c0 += 96) {
+                float v[3];
+                u32 hit[3], near[3];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) { const int c = c0 + 32 * u + lane; v[u] = c < C ? sr[c] : -INFINITY; }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    hit[u] = __ballot_sync(0xffffffffu, v[u] == swm);
+                    near[u] = __ballot_sync(0xffffffffu, v[u] >= lo && v[u] < swm);
                 }
-                const u32 hm = __ballot_sync(0xffffffffu, hit);
-                if (hm) { ci = c0 + __ffs(hm) - 1; break; }
+                if (near[0] | near[1] | near[2]) {  // warp-uniform
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        hit[u] |= __ballot_sync(0xffffffffu, v[u] >= lo && v[u] < swm && sigmoid_acc(v[u]) == spm);
+                }
+#pragma unroll
+                for (int u = 2; u >= 0; --u) if (hit[u]) ci = c0 + 32 * u + __ffs(hit[u]) - 1;
+                if (ci != 0x7fffffff) break;
             }
-            if (lane == 0) s_surv[q].ci = ci;
+            if (lane == 0) s_surv[q].ci = ci == 0x7fffffff ? 0 : ci;
         }
+        DEC_MARK(4);  // phase 2a (this warp)
         __syncthreads();
 
         // phase 2b: one thread per survivor -- box decode and writes
@@ -302,21 +330,26 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
             k.box_slots[slot] = bx;
             k.cls_slots[slot] = sv.ci;
         }
+        DEC_MARK(5);  // barrier after 2a + phase 2b (this thread)
         __syncthreads();  // the tile buffer and the survivor list are free again
+        DEC_MARK(6);  // barrier: slowest thread of phase 2b
 
         if (tid == 0) {   // refill this stage with the tile DEC_STAGES iterations ahead
-            const int tn = t + DEC_STAGES * gridDim.x;
-            if (tn < tp.total) {
-                int b2, si2, l2, r2;
-                const float *src2 = tile_src(tn, b2, si2, l2, r2);
+            if (nb < k.B) {
+                int si2, l2, r2;
+                const float *src2 = tile_src(nb, nr, si2, l2, r2);
                 if (tma_ok(src2, r2)) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer above
+                    // the generic-proxy reads of this buffer are ordered before the copy by the barrier above (write
+                    // after read needs no proxy fence; only generic writes must be fenced before an async-proxy access)
                     mbar_expect_tx(&full_bar[stage], (u32)(r2 * D) * 4);
                     bulk_g2s(tile, src2, (u32)(r2 * D) * 4, &full_bar[stage]);
                 }
             }
         }
+        DEC_MARK(7);  // refill
     }
+    if (prof) for (int i = 0; i < 8; ++i) o.cycles[(long long)blockIdx.x * 8 + i] = (unsigned long long)cyc[i];
+#undef DEC_MARK
 }
 
 // ---------------------------------------------------------------------------------------------
