@@ -545,7 +545,8 @@ struct LossWs {
     float *box[3];
     float *ciou[3];
     float4 *gbox[3];
-    int *winner;          // all scales, contiguous (one memset)
+    int *head;            // all scales, contiguous (one memset)
+    int *next[3];
     float *gobj;          // all scales, contiguous
     double *part_match[3];
     double *part_dense[3];
@@ -572,7 +573,7 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     const int sms = num_sms();
     w.cap = 5ll * p->na * p->nt;
     if (w.cap < 1) w.cap = 1;
-    w.nblk_match = sms * 4;
+    w.nblk_match = sms * 8;
     w.nblk_dense = sms * 8;
     const size_t nblk_assign = (size_t)((w.cap + ASSIGN_THREADS - 1) / ASSIGN_THREADS + 1);
     w.cells_total = 0;
@@ -582,7 +583,7 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
         w.cells_total += w.cells[s];
     }
     w.M = b.take<int>(4);
-    w.winner = b.take<int>(w.cells_total);
+    w.head = b.take<int>(w.cells_total);
     w.gobj = b.take<float>(w.cells_total);
     for (int s = 0; s < 3; ++s) {
         w.block_counts[s] = b.take<int>(nblk_assign);
@@ -592,6 +593,7 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
         w.box[s] = b.take<float>(4 * w.cap);
         w.ciou[s] = b.take<float>(w.cap);
         w.gbox[s] = b.take<float4>(w.cap);
+        w.next[s] = b.take<int>(w.cap);
         w.part_match[s] = b.take<double>((size_t)w.nblk_match * 4);
         w.part_dense[s] = b.take<double>((size_t)w.nblk_dense * 3);
     }
@@ -612,7 +614,7 @@ void loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const float 
         S.preds = preds[s]; S.grad = grads ? grads[s] : nullptr; S.cells = w.cells[s];
         S.M = w.M + s; S.cell = w.cell[s]; S.cls = w.cls[s]; S.anchor = w.anchor[s]; S.box = w.box[s];
         S.ciou = w.ciou[s]; S.gbox = w.gbox[s];
-        S.winner = w.winner + w.cell_off[s]; S.gobj = w.gobj + w.cell_off[s];
+        S.head = w.head + w.cell_off[s]; S.next = w.next[s]; S.gobj = w.gobj + w.cell_off[s];
         S.part_match = w.part_match[s]; S.part_dense = w.part_dense[s];
         S.scale_w = p->scale_w[s];
     }
@@ -639,7 +641,7 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
     if (loss_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
     const float *preds[3] = {preds_sm, preds_md, preds_lg};
     if (cudaMemsetAsync(out_hist, 0, sizeof(int64_t) * 9 * (size_t)p->C, st) != cudaSuccess) return BG_ERR_LAUNCH;
-    if (cudaMemsetAsync(w.winner, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (cudaMemsetAsync(w.head, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
     Assign3K a3;
     for (int s = 0; s < 3; ++s) {
         AssignK &a = a3.a[s];
@@ -684,10 +686,22 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
     k.go_dev = grad_out_dev;
     k.go_host = grad_out_host;
     const int sms = num_sms();
-    if (k.D == 85) loss_bwd_dense_kernel<85><<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
-    else loss_bwd_dense_kernel<0><<<dim3(sms * 8, 3), BWD_THREADS, 0, st>>>(k);
-    BG_LAUNCH_CHECK();
-    loss_bwd_dup_kernel<<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
+    {
+        const size_t smem = (size_t)BWD_WARPS * 2 * 32 * k.D * sizeof(float);
+        if (smem > 200 * 1024) return BG_ERR_INVALID;  // rows longer than ~780 floats do not fit the chunk images
+        static size_t attr_smem = 0;
+        if (smem > attr_smem) {
+            if (cudaFuncSetAttribute(loss_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return BG_ERR_LAUNCH;
+            }
+            attr_smem = smem;
+        }
+        const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+        loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
+        BG_LAUNCH_CHECK();
+    }
+    loss_bwd_rows_kernel<<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }

@@ -231,16 +231,15 @@ __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go,
 
 // ------------------------------------------------------------------------------------------------
 // fused detection loss: every kernel covers the three scales (blockIdx.y)
-//   forward : loss_match_kernel  pass A, one thread per match   : gather, CIoU and its gradient, "last match
-//                                                                  wins" ticket (atomicMax of the match index)
+//   forward : loss_match_kernel  pass A, one thread per match   : gather, CIoU and its gradient, link the match
+//                                                                  into its cell's list (atomicExch on the head)
 //                                pass B, eight lanes per match  : class BCE, argmax, confusion counters
 //             loss_dense_kernel  one thread per cell            : objectness BCE against the winner's CIoU;
 //                                                                  keeps sigmoid(x) - t for the backward
 //             loss_finalize_kernel                              : fixed-order reduction, scalars, total loss
-//   backward: loss_bwd_dense_kernel one 16-byte store per four gradient elements: objectness everywhere,
-//                                   class / box channels of a matched row from the row's LAST match
-//             loss_bwd_dup_kernel   earlier matches of a cell that was matched more than once accumulate
-//                                   with atomics (gather backward = index_put(accumulate=True))
+//   backward: loss_bwd_stream_kernel  zeros + the objectness column, one 16-byte store per four elements
+//             loss_bwd_rows_kernel    class / box columns of the matched rows, summed over the cell's match list
+//                                     (gather backward = index_put(accumulate=True)); no atomics
 // ------------------------------------------------------------------------------------------------
 struct LossScale {
     const float *preds;  // [B,ny,nx,na,D]
@@ -253,7 +252,8 @@ struct LossScale {
     const float *box;    // [cap,4]
     float *ciou;         // [cap]
     float4 *gbox;        // [cap] d ciou / d (x, y, w_raw, h_raw) of the matched prediction
-    int *winner;         // [cells] index of the last match that targets the cell, -1 if none
+    int *head;           // [cells] most recently linked match of the cell (-1: none); list through next[]
+    int *next;           // [cap] previous match of the same cell, -1 at the end of the list
     float *gobj;         // [cells] sigmoid(obj) - t_conf
     double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
     double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
@@ -290,6 +290,7 @@ __device__ __forceinline__ float bce_logits_fast(float x, float t)
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 constexpr int LOSS_THREADS = 256;
+constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
 
 __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
 {
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
     for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
     __syncthreads();
 
-    // pass A: one thread per match
+    // pass A: one thread per match -- gather, CIoU and its gradient, link the match into its cell's list
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (long long m = (long long)blockIdx.x * LOSS_THREADS + tid; m < M; m += (long long)gridDim.x * LOSS_THREADS) {
         const int cell = S.cell[m];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
         const float ci = ciou_eval<float>(p, t, 1e-7f, g);
         S.ciou[m] = ci;
         S.gbox[m] = make_float4(g[0], g[1], g[2] * aw, g[3] * ah);
-        atomicMax(&S.winner[cell], (int)m);
+        S.next[m] = atomicExch(&S.head[cell], (int)m);
         a0 += (double)__fsub_rn(1.0f, ci);
         a1 += (double)ci;
         a2 += (double)sigmoid_acc(obj);
@@ -334,10 +335,18 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
         if (valid) {
             tc = S.cls[m];
             const float *row = S.preds + (long long)S.cell[m] * D + 1;
-            for (int c = gl; c < C; c += 8) {
-                const float x = __ldg(row + c);
-                bsum += bce_logits_fast(x, c == tc ? k.cp : k.cn);
-                if (x > best) { best = x; bi = c; }
+            for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
+                float x[ROWS_UNROLL];
+#pragma unroll
+                for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = c < C ? __ldg(row + c) : -INFINITY; }
+#pragma unroll
+                for (int u = 0; u < ROWS_UNROLL; ++u) {
+                    const int c = cb + 8 * u + gl;
+                    if (c < C) {
+                        bsum += bce_logits_fast(x[u], c == tc ? k.cp : k.cn);
+                        if (x[u] > best) { best = x[u]; bi = c; }
+                    }
+                }
             }
         }
 #pragma unroll
@@ -369,6 +378,15 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
     }
 }
 
+// One float every D*4 bytes: ask L2 for 64-byte fills instead of the default (measured on B200 for a 340-byte
+// stride: 89 instead of 122 bytes of DRAM time per element, scripts/micro/write_stride.cu)
+__device__ __forceinline__ float ld_stride_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // dense objectness BCE over every cell
 __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
 {
@@ -378,8 +396,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
     double a0 = 0, a1 = 0, a2 = 0;
     for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < S.cells;
          c += (long long)gridDim.x * LOSS_THREADS) {
-        const float x = __ldg(S.preds + c * k.D);
-        const int w = S.winner[c];
+        const float x = ld_stride_f32(S.preds + c * k.D);
+        int w = S.head[c];  // "last match wins": the highest match index of the cell's list
+        for (int j = w; j >= 0; j = S.next[j]) w = j > w ? j : w;
         const float t = w >= 0 ? S.ciou[w] : 0.0f;
         const float sg = sigmoid_acc(x);
         a0 += (double)bce_logits(x, t);
@@ -449,112 +468,131 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
     return r;
 }
 
-// class / box gradient of element (col >= 1) of a row whose last match is m; x = the prediction there
-__device__ __forceinline__ float bwd_match_elem(const Loss3K &k, const LossScale &S, const BwdScales &sc, int col, int m, float x)
-{
-    if (col <= k.C) return sc.cls * (sigmoid_fast(x) - ((col - 1 == S.cls[m]) ? k.cp : k.cn));
-    return sc.box * reinterpret_cast<const float *>(S.gbox + m)[col - k.C - 1];
-}
-
-// One warp per chunk of 32 rows (32*D elements, 16-byte aligned because 32*D*4 is): the lanes first fetch the
-// chunk's winners and objectness residuals (one coalesced load each), then stream the chunk out as float4
-// stores; which row an element belongs to is index arithmetic, its row data comes from the owning lane by shuffle.
+// grad_preds is zeros, one objectness value per row, and the class / box columns of the matched rows (6 % of
+// the rows).  Two kernels, no atomics, both with every warp of the machine busy:
+//
+// loss_bwd_stream_kernel: written the way a memset would be.  Every warp owns two shared-memory images of a
+//   32-row chunk (32*D floats, zero-filled once); per chunk it drops the 32 objectness values into column 0 of
+//   the rows (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and hands the
+//   image to the TMA store engine (cp.async.bulk.global.shared::cta: ONE instruction per 32*D*4-byte chunk),
+//   alternating between its two images so the next chunk is prepared while the copy drains.
+// loss_bwd_rows_kernel: eight lanes per match; the most recently linked match of a cell (head of its list) owns
+//   the row, walks the list (gather backward = index_put(accumulate=True): every match of the cell contributes)
+//   and rewrites the row's class / box columns:
+//   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
 constexpr int BWD_THREADS = 256;
 
-template <int DT>  // compile-time row length (division by a constant); 0 = runtime
-__global__ void __launch_bounds__(BWD_THREADS) loss_bwd_dense_kernel(Loss3K k)
+constexpr int BWD_WARPS = 4;  // warps per CTA of the streaming kernel (each owns two chunk images)
+
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes)
 {
-    const LossScale &S = k.s[blockIdx.y];
-    const BwdScales sc = bwd_scales(k, S);
-    const u32 D = DT ? (u32)DT : (u32)k.D;
-    const int lane = threadIdx.x & 31;
-    const long long nchunks = (S.cells + 31) >> 5;
-    const long long gw = (long long)blockIdx.x * (BWD_THREADS / 32) + (threadIdx.x >> 5);
-    const long long nw = (long long)gridDim.x * (BWD_THREADS / 32);
-    for (long long ch = gw; ch < nchunks; ch += nw) {
-        const long long row0 = ch << 5;
-        const int nrows = (int)min((long long)32, S.cells - row0);
-        const int win = lane < nrows ? S.winner[row0 + lane] : -1;
-        const float go = lane < nrows ? sc.conf * S.gobj[row0 + lane] : 0.0f;
-        const bool any = __ballot_sync(0xffffffffu, win >= 0) != 0;
-        const long long e0 = row0 * D;
-        float4 *g4 = reinterpret_cast<float4 *>(S.grad + e0);
-        const float4 *p4 = reinterpret_cast<const float4 *>(S.preds + e0);
-        const u32 nelem = (u32)nrows * D, nf4 = nelem >> 2;
-        for (u32 f0 = 0; f0 < nf4; f0 += 32) {
-            const u32 f = f0 + lane;
-            const u32 e = 4 * f;
-            const u32 q = e / D, r = e - q * D;         // first element: row q of the chunk, column r
-            const bool straddle = r + 3 >= D;           // columns r..D-1 of row q, then 0.. of row q+1
-            const u32 qo = (r == 0) ? q : q + 1;        // the row whose objectness column may sit in this vector
-            const float gobj = __shfl_sync(0xffffffffu, go, qo & 31);
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (r == 0) v[0] = gobj;
-            else if (straddle) {
-                const u32 pos = D - r;
-                v[1] = pos == 1 ? gobj : 0.f; v[2] = pos == 2 ? gobj : 0.f; v[3] = pos == 3 ? gobj : 0.f;
-            }
-            if (any) {
-                const int mA = __shfl_sync(0xffffffffu, win, q & 31);
-                const int mB = __shfl_sync(0xffffffffu, win, (q + 1) & 31);
-                if (f < nf4 && (mA >= 0 || (straddle && mB >= 0))) {
-                    const float4 x4 = __ldg(p4 + f);
-                    const float x[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const u32 col = r + j;
-                        if (col < D) { if (col > 0 && mA >= 0) v[j] = bwd_match_elem(k, S, sc, (int)col, mA, x[j]); }
-                        else if (col > D && mB >= 0) v[j] = bwd_match_elem(k, S, sc, (int)(col - D), mB, x[j]);
-                    }
-                }
-            }
-            if (f < nf4) g4[f] = make_float4(v[0], v[1], v[2], v[3]);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((u32)__cvta_generic_to_shared(src)), "r"(bytes)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
+{
+    extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][2][32*D]
+    const int D = k.D;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int chunk_floats = 32 * D;
+    float *img0 = bwd_smem + (size_t)(2 * wid) * chunk_floats;
+    for (int i = lane; i < 2 * chunk_floats; i += 32) img0[i] = 0.f;  // both images; only column 0 of a row ever changes
+    __syncwarp();
+
+    long long nch[3], tot = 0;
+    for (int s = 0; s < 3; ++s) { nch[s] = k.s[s].cells >> 5; tot += nch[s]; }  // full chunks; remainders below
+    const float cf0 = bwd_scales(k, k.s[0]).conf, cf1 = bwd_scales(k, k.s[1]).conf, cf2 = bwd_scales(k, k.s[2]).conf;
+    const long long gw = (long long)blockIdx.x * BWD_WARPS + wid, nw = (long long)gridDim.x * BWD_WARPS;
+
+    auto locate = [&](long long g, int &si, long long &row0) {
+        si = 0;
+        long long ch = g;
+        if (ch >= nch[0]) { ch -= nch[0]; si = 1; if (ch >= nch[1]) { ch -= nch[1]; si = 2; } }
+        row0 = ch << 5;
+    };
+    int si = 0; long long row0 = 0;
+    float gobj_n = 0.f;
+    if (gw < tot) { locate(gw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }
+    int it = 0;
+    for (long long g = gw; g < tot; g += nw, ++it) {
+        float *dst = k.s[si].grad + row0 * D;
+        const float go = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gobj_n;
+        if (g + nw < tot) { locate(g + nw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }  // prefetch
+        float *im = img0 + (size_t)(it & 1) * chunk_floats;
+        // the bulk store issued from this image two chunks ago must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        im[lane * D] = go;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane's value -> visible to the bulk copy
+        __syncwarp();
+        if (lane == 0) {
+            bulk_s2g(dst, im, (u32)chunk_floats * 4);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
-        // the last nelem % 4 elements (only in the final chunk, when cells * D is not a multiple of four)
-        const u32 tail = nelem & 3;
-        if (lane < tail) {
-            const u32 e = (nf4 << 2) + lane;
-            const u32 q = e / D, col = e - q * D;
-            const int m = S.winner[row0 + q];
-            float v = 0.f;
-            if (col == 0) v = sc.conf * S.gobj[row0 + q];
-            else if (m >= 0) v = bwd_match_elem(k, S, sc, (int)col, m, S.preds[e0 + e]);
-            S.grad[e0 + e] = v;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+
+    // rows beyond the last full chunk of a scale (cells not a multiple of 32): plain stores by one CTA
+    if (blockIdx.x == 0) {
+        for (int s = 0; s < 3; ++s) {
+            const LossScale &S = k.s[s];
+            const float cf = s == 0 ? cf0 : (s == 1 ? cf1 : cf2);
+            for (long long row = (S.cells & ~31LL) + wid; row < S.cells; row += BWD_WARPS)
+                for (int col = lane; col < D; col += 32) S.grad[row * D + col] = col == 0 ? cf * S.gobj[row] : 0.f;
         }
     }
 }
 
-// matches that are not the last match of their cell add their class / box gradients to the row
-// (gather backward = index_put(accumulate=True)); one thread per match finds them, the warp then works
-// through its finds together
-__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_dup_kernel(Loss3K k)
+__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
 {
     const LossScale &S = k.s[blockIdx.y];
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gl = lane & 7;
     const int M = *S.M;
     if (M <= 0) return;
     const BwdScales sc = bwd_scales(k, S);
     const int C = k.C, D = k.D;
-    for (long long m0 = ((long long)blockIdx.x * LOSS_THREADS + threadIdx.x) - lane; m0 < M; m0 += (long long)gridDim.x * LOSS_THREADS) {
-        const long long m = m0 + lane;
-        int cell = -1;
-        if (m < M) {
-            cell = S.cell[m];
-            if (S.winner[cell] == (int)m) cell = -1;  // the last match of a cell was written by the dense kernel
+    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
+         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
+        const long long m = mb + (lane >> 3);
+        if (m >= M) continue;
+        const int cell = S.cell[m];
+        if (S.head[cell] != (int)m) continue;  // another match of the cell owns the row
+        int n = 0, c1 = -1, c2 = -1;
+        float gb[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = (int)m; j >= 0; j = S.next[j]) {
+            const float4 gq = S.gbox[j];
+            gb[0] += gq.x; gb[1] += gq.y; gb[2] += gq.z; gb[3] += gq.w;
+            if (n == 0) c1 = S.cls[j]; else if (n == 1) c2 = S.cls[j];
+            ++n;
         }
-        u32 todo = __ballot_sync(0xffffffffu, cell >= 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int c2 = __shfl_sync(0xffffffffu, cell, src);
-            const long long mm = m0 + src;
-            const int tc = S.cls[mm];
-            const float *row = S.preds + (long long)c2 * D;
-            float *grow = S.grad + (long long)c2 * D;
-            for (int c = lane; c < C; c += 32)
-                atomicAdd(grow + 1 + c, sc.cls * (sigmoid_fast(__ldg(row + 1 + c)) - ((c == tc) ? k.cp : k.cn)));
-            if (lane < 4) atomicAdd(grow + C + 1 + lane, sc.box * reinterpret_cast<const float *>(S.gbox + mm)[lane]);
+        const float *xrow = S.preds + (long long)cell * D;
+        float *grow = S.grad + (long long)cell * D;
+        // cls*(n*(sg - cn) - (cp - cn)*hits) = ka*sg - kb - kc*hits
+        const float ka = sc.cls * (float)n, kb = ka * k.cn, kc = sc.cls * (k.cp - k.cn);
+        for (int cb = 1; cb <= C; cb += 8 * ROWS_UNROLL) {
+            float x[ROWS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < ROWS_UNROLL; ++u) {  // all loads of the batch in flight before the first store
+                const int col = cb + 8 * u + gl;
+                x[u] = col <= C ? __ldg(xrow + col) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < ROWS_UNROLL; ++u) {
+                const int col = cb + 8 * u + gl;
+                if (col > C) continue;
+                const float sg = sigmoid_fast(x[u]);
+                const int c = col - 1;
+                float v;
+                if (n <= 2) v = (ka * sg - kb) - ((c == c1 ? kc : 0.f) + (c == c2 ? kc : 0.f));
+                else {  // three or more matches on one cell: walk the list
+                    v = 0.f;
+                    for (int j = (int)m; j >= 0; j = S.next[j]) v += sc.cls * (sg - ((c == S.cls[j]) ? k.cp : k.cn));
+                }
+                grow[col] = v;
+            }
         }
+        if (gl < 4) grow[C + 1 + gl] = sc.box * (gl == 0 ? gb[0] : gl == 1 ? gb[1] : gl == 2 ? gb[2] : gb[3]);
     }
 }
 
