@@ -134,6 +134,21 @@ int bg_assign_targets(const float *targets, int64_t nt, int32_t ny, int32_t nx, 
                       float *out_anchor, float *out_box, int64_t cap, int32_t *out_count, void *workspace,
                       size_t workspace_bytes, void *stream);
 
+/* The segmentation / keypoint variants of the same routine (detection_dataset.py:132-172,239-245):
+ *   targets [nt, row_stride] with row_stride = 6 + 3*num_keypoints; the extra columns are returned per match in
+ *   out_kpts [cap, row_stride-6] (the reference's `keypoints`).
+ *   tmask_mode 0: none; 1: overlap_masks=False (mask index = the target's position); 2: overlap_masks=True
+ *   (1 + position inside the image's block, blocks laid out by the per-image counts for ids 0..batch_size-1);
+ *   out_tmask [cap] i64 (the reference's `tmask_idx`).
+ *   out_count [2] i32: [0] = M, [1] = 1 if the per-image counts do not add up to nt (the reference raises).
+ */
+size_t bg_assign_ex_workspace_bytes(int64_t nt, int32_t na, int32_t batch_size);
+int bg_assign_targets_ex(const float *targets, int64_t nt, int32_t row_stride, int32_t ny, int32_t nx,
+                         const float *anchors /*host*/, int32_t na, float anchor_t, float edge_t, int32_t tmask_mode,
+                         int32_t batch_size, int64_t *out_idx4, int64_t *out_cls, float *out_anchor, float *out_box,
+                         int64_t *out_tmask, float *out_kpts, int64_t cap, int32_t *out_count, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
 /* ------------------------------------------------------------------ B2
  * DetectionLoss.compute_ciou (modules/detection_loss.py:229-264), element-wise [M,4] x [M,4] -> [M].
  * bg_ciou_bwd: grad_p[m,:] = grad_out[m] * d ciou / d preds_xywh (alpha held constant, :261-262). */

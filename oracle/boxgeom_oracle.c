@@ -218,9 +218,9 @@ BGO_API int64_t bgo_batched_nms(const float *boxes, const float *scores, const i
  * out_idx4: [4, cap] rows = batch_idx, grid_j, grid_i, anchor_idx (int64);
  * returns M.  cap must be >= 5*na*nt.
  */
-BGO_API int64_t bgo_assign(const float *targets, int64_t nt, int ny, int nx, const float *anchors,
-                           int na, float anchor_t, float edge_t, int64_t cap, int64_t *out_idx4,
-                           int64_t *out_cls, float *out_anchor, float *out_box)
+static int64_t bgo_assign_impl(const float *targets, int64_t nt, int stride, int ny, int nx, const float *anchors,
+                               int na, float anchor_t, float edge_t, int64_t cap, int64_t *out_idx4,
+                               int64_t *out_cls, float *out_anchor, float *out_box, int64_t *out_t)
 {
     static const float offx[5] = {0.f, 1.f, 0.f, -1.f, 0.f};
     static const float offy[5] = {0.f, 0.f, 1.f, 0.f, -1.f};
@@ -231,7 +231,7 @@ BGO_API int64_t bgo_assign(const float *targets, int64_t nt, int ny, int nx, con
         for (int a = 0; a < na; ++a) {
             const float aw = anchors[2 * a] * fnx, ah = anchors[2 * a + 1] * fny; /* :183 */
             for (int64_t t = 0; t < nt; ++t) {
-                const float *tg = targets + 6 * t;
+                const float *tg = targets + (int64_t)stride * t;
                 const float gx = tg[2] * fnx, gy = tg[3] * fny, gw = tg[4] * fnx, gh = tg[5] * fny; /* :184 */
                 const float rw = gw / aw, rh = gh / ah;                                              /* :190 */
                 const float irw = 1.0f / rw, irh = 1.0f / rh;
@@ -262,11 +262,29 @@ BGO_API int64_t bgo_assign(const float *targets, int64_t nt, int ny, int nx, con
                 out_box[4 * M + 0] = gx - (float)gi; /* clamped gi,gj (aliasing) :237 */
                 out_box[4 * M + 1] = gy - (float)gj;
                 out_box[4 * M + 2] = gw; out_box[4 * M + 3] = gh;
+                if (out_t) out_t[M] = t;
                 ++M;
             }
         }
     }
     return M;
+}
+
+BGO_API int64_t bgo_assign(const float *targets, int64_t nt, int ny, int nx, const float *anchors,
+                           int na, float anchor_t, float edge_t, int64_t cap, int64_t *out_idx4,
+                           int64_t *out_cls, float *out_anchor, float *out_box)
+{
+    return bgo_assign_impl(targets, nt, 6, ny, nx, anchors, na, anchor_t, edge_t, cap, out_idx4, out_cls, out_anchor, out_box, NULL);
+}
+
+/* Segmentation / keypoint variants (detection_dataset.py:127-172,239-245): rows of `stride` floats, the extra
+ * columns ride along unchanged (gain 1, :173-176); out_t [cap] = source target of every match, from which the
+ * caller derives tmask_idx (:132-170) and the keypoint rows (:244). */
+BGO_API int64_t bgo_assign_ex(const float *targets, int64_t nt, int stride, int ny, int nx, const float *anchors,
+                              int na, float anchor_t, float edge_t, int64_t cap, int64_t *out_idx4,
+                              int64_t *out_cls, float *out_anchor, float *out_box, int64_t *out_t)
+{
+    return bgo_assign_impl(targets, nt, stride, ny, nx, anchors, na, anchor_t, edge_t, cap, out_idx4, out_cls, out_anchor, out_box, out_t);
 }
 
 /* ------------------------------------------------------------------- CIoU

@@ -150,6 +150,31 @@ def gen_assign(ns):
     save("assign", **out)
 
 
+def gen_assign_variants(ns):
+    """Segmentation (overlap_masks) and keypoint-column variants of build_target_by_scale."""
+    out = {}
+    cases = {
+        "seg_overlap": (synth.targets(4, 12, 80, 3, fixed=False), True, 4),
+        "seg_plain": (synth.targets(4, 12, 80, 3, fixed=False), False, None),
+        "kpt": (synth.keypoint_targets(3, 10, 2), None, None),
+        "kpt_seg_overlap": (synth.keypoint_targets(3, 10, 2), True, 3),
+    }
+    for name, (t, overlap, bs) in cases.items():
+        for (ny, nx), sc in zip(((16, 16), (8, 8), (4, 4)), synth.SCALES):
+            anc = synth.anchors_tensor(sc)
+            idx, cls, a, box, tm, kp = ns.DetectionDataset.build_target_by_scale(t.clone(), (ny, nx), anc, 4.0, 0.5, overlap, bs)
+            k = f"{name}_{sc}"
+            out[k + "_idx"] = torch.stack(idx, 0).numpy() if cls.numel() else np.zeros((4, 0), np.int64)
+            out[k + "_cls"] = cls.numpy()
+            out[k + "_anc"] = a.numpy().reshape(-1, 2)
+            out[k + "_box"] = box.numpy().reshape(-1, 4)
+            if tm is not None:
+                out[k + "_tmask"] = tm.numpy()
+            if kp is not None:
+                out[k + "_kpts"] = kp.numpy()
+    save("assign_variants", **out)
+
+
 def gen_ciou(ns):
     g = torch.Generator().manual_seed(21)
     M = 512
@@ -216,6 +241,7 @@ if __name__ == "__main__":
     gen_decode_post(ns)
     gen_nms()
     gen_assign(ns)
+    gen_assign_variants(ns)
     gen_ciou(ns)
     gen_loss(ns)
     gen_ratio(ns)

@@ -51,6 +51,9 @@ def lib() -> C.CDLL:
         L.bgo_assign.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, f32p, C.c_int, C.c_float, C.c_float, C.c_int64,
                                  i64p, i64p, f32p, f32p]
         L.bgo_assign.restype = C.c_int64
+        L.bgo_assign_ex.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_float, C.c_float, C.c_int64,
+                                    i64p, i64p, f32p, f32p, i64p]
+        L.bgo_assign_ex.restype = C.c_int64
         L.bgo_ciou.argtypes = [f32p, f32p, C.c_int64, C.c_float, f32p, f32p]
         L.bgo_ciou.restype = None
         L.bgo_loss_scale.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i64p, C.c_int64, i64p, f32p,
@@ -171,6 +174,41 @@ def build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold: float 
                          _p(box, C.c_float))
     assert M >= 0
     return [idx4[k, :M].copy() for k in range(4)], cls[:M].copy(), anc[:M].copy(), box[:M].copy()
+
+
+def build_target_by_scale_ex(targets, fmap_shape, anchors, anchor_threshold: float = 4.0, edge_threshold: float = 0.5,
+                             overlap_masks: Optional[bool] = None, batch_size: Optional[int] = None):
+    """dataset/detection_dataset.py:90-246 including the segmentation (``overlap_masks``) and keypoint-column
+    variants.  Returns (indices, classes, anchors, boxes, tmask_idx or None, keypoints or None)."""
+    targets, anchors = _np(targets, np.float32), _np(anchors, np.float32)
+    targets = targets.reshape(-1, targets.shape[-1] if targets.ndim == 2 else 6)
+    nt, stride, na = targets.shape[0], targets.shape[1], anchors.shape[0]
+    ny, nx = int(fmap_shape[0]), int(fmap_shape[1])
+    cap = max(5 * na * nt, 1)
+    idx4 = np.empty((4, cap), np.int64)
+    cls = np.empty(cap, np.int64)
+    anc = np.empty((cap, 2), np.float32)
+    box = np.empty((cap, 4), np.float32)
+    src = np.empty(cap, np.int64)
+    M = lib().bgo_assign_ex(_p(targets, C.c_float), nt, stride, ny, nx, _p(anchors, C.c_float), na, float(anchor_threshold),
+                            float(edge_threshold), cap, _p(idx4, C.c_int64), _p(cls, C.c_int64), _p(anc, C.c_float),
+                            _p(box, C.c_float), _p(src, C.c_int64))
+    assert M >= 0
+    src = src[:M]
+    tmask = None
+    if overlap_masks is not None:
+        if overlap_masks:  # :146-157: 1 + position inside the image's block, blocks sized by the per-image counts
+            if not batch_size:
+                raise ValueError("batch_size is required when overlap_mask is set to True")
+            per_t = np.concatenate([np.arange(int((targets[:, 0] == i).sum())) + 1 for i in range(batch_size)]) \
+                if nt else np.zeros(0, np.int64)
+            if per_t.shape[0] != nt:
+                raise ValueError("per-image target counts do not add up to the number of targets")
+        else:              # :170: the target's own position
+            per_t = np.arange(nt)
+        tmask = per_t[src].astype(np.int64)
+    kpts = targets[src, 6:].copy() if stride > 6 else None
+    return [idx4[k, :M].copy() for k in range(4)], cls[:M].copy(), anc[:M].copy(), box[:M].copy(), tmask, kpts
 
 
 def compute_ciou(p, t, e: float = 1e-7, with_grad: bool = False):

@@ -99,10 +99,12 @@ def test_dropin_keeps_reference_signatures():
             ns.DetectionDataset.build_target_by_scale(synth.targets(1, 3), (20, 20), synth.anchors_tensor("lg"))
         with pytest.raises(RuntimeError, match="CUDA"):
             torchvision.ops.batched_nms(*synth.nms_boxes(10, 2), 0.5)
-        # out-of-scope variants are delegated to the reference's original callable
-        t = synth.targets(2, 3)
-        out = ns.DetectionDataset.build_target_by_scale(t, (20, 20), synth.anchors_tensor("lg"), overlap_masks=False)
-        assert out[4] is not None
+        # the segmentation / keypoint variants of build_target_by_scale run on the CUDA kernel too: CPU refused
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns.DetectionDataset.build_target_by_scale(synth.targets(2, 3), (20, 20), synth.anchors_tensor("lg"), overlap_masks=False)
+        # out-of-scope variants are delegated to the reference's original callable (broadcasting CIoU form)
+        p4 = torch.rand(2, 5, 4) + 0.1
+        assert ns.DetectionLoss.compute_ciou(p4, p4[:, 0]).shape[:2] == (2, 5)
     finally:
         dropin.uninstall()
     assert not any(dropin.installed().values())

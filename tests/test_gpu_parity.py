@@ -8,7 +8,7 @@ import torch
 
 from oracle import oracle as O
 from vision_conglomerate_b200 import synth
-from tests.util import assert_close, canon, digest, golden, rows_canon
+from tests.util import ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon
 
 pytestmark = pytest.mark.gpu
 
@@ -222,6 +222,31 @@ def test_assign_golden(ops, name):
         assert np.array_equal(cls.cpu().numpy(), g[key + "_cls"])
         assert np.array_equal(a.cpu().numpy().reshape(-1, 2), g[key + "_anc"])
         assert np.array_equal(box.cpu().numpy().reshape(-1, 4), g[key + "_box"])
+
+
+@pytest.mark.parametrize("name", ASSIGN_VARIANTS)
+def test_assign_variants_golden(ops, name):
+    """Segmentation (overlap_masks) and keypoint-column variants: bit-exact with the reference's outputs."""
+    g = golden("assign_variants")
+    t, overlap, bs = assign_variant_case(name)
+    for (ny, nx), sc in zip(((16, 16), (8, 8), (4, 4)), synth.SCALES):
+        idx, cls, a, box, tm, kp = ops.build_target_by_scale(dev(t), (ny, nx), synth.anchors_tensor(sc), 4.0, 0.5, overlap, bs)
+        k = f"{name}_{sc}"
+        assert np.array_equal(torch.stack(idx, 0).cpu().numpy(), g[k + "_idx"]) and np.array_equal(cls.cpu().numpy(), g[k + "_cls"])
+        assert np.array_equal(a.cpu().numpy(), g[k + "_anc"]) and np.array_equal(box.cpu().numpy(), g[k + "_box"])
+        assert (tm is None) == (k + "_tmask" not in g.files) and (kp is None) == (k + "_kpts" not in g.files)
+        if tm is not None:
+            assert tm.dtype == torch.int64 and np.array_equal(tm.cpu().numpy(), g[k + "_tmask"])
+        if kp is not None:
+            assert np.array_equal(kp.cpu().numpy(), g[k + "_kpts"])
+
+
+def test_assign_variants_errors(ops):
+    t = synth.targets(2, 5, 80, 0)
+    with pytest.raises(ValueError):   # the reference's own error: overlap_masks=True needs batch_size
+        ops.build_target_by_scale(dev(t), (8, 8), synth.anchors_tensor("md"), 4.0, 0.5, True, None)
+    with pytest.raises(RuntimeError):  # image ids outside 0..batch_size-1: the reference's torch.cat raises
+        ops.build_target_by_scale(dev(t), (8, 8), synth.anchors_tensor("md"), 4.0, 0.5, True, 1)
 
 
 def test_assign_config3_and_4(ops):

@@ -6,7 +6,7 @@ import torch
 
 from oracle import oracle as O
 from vision_conglomerate_b200 import synth
-from tests.util import assert_close, canon, digest, golden, rows_canon
+from tests.util import ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon
 
 DEC = ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"]
 
@@ -99,6 +99,23 @@ def test_assign(key):
     assert np.array_equal(cls, g[key + "_cls"])
     assert np.array_equal(anc, g[key + "_anc"])                       # fp32 outputs are bit-reproducible too
     assert np.array_equal(box, g[key + "_box"])
+
+
+@pytest.mark.parametrize("name", ASSIGN_VARIANTS)
+def test_assign_variants(name):
+    """Segmentation (overlap_masks) and keypoint-column variants against the reference's outputs."""
+    g = golden("assign_variants")
+    t, overlap, bs = assign_variant_case(name)
+    for (ny, nx), sc in zip(((16, 16), (8, 8), (4, 4)), synth.SCALES):
+        idx, cls, anc, box, tm, kp = O.build_target_by_scale_ex(t, (ny, nx), synth.anchors_tensor(sc), 4.0, 0.5, overlap, bs)
+        k = f"{name}_{sc}"
+        assert np.array_equal(np.stack(idx, 0), g[k + "_idx"]) and np.array_equal(cls, g[k + "_cls"])
+        assert np.array_equal(anc, g[k + "_anc"]) and np.array_equal(box, g[k + "_box"])
+        assert (tm is None) == (k + "_tmask" not in g.files) and (kp is None) == (k + "_kpts" not in g.files)
+        if tm is not None:
+            assert np.array_equal(tm, g[k + "_tmask"])
+        if kp is not None:
+            assert np.array_equal(kp, g[k + "_kpts"])
 
 
 def test_ciou():

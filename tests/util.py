@@ -46,3 +46,17 @@ def rows_canon(rows, img):
     r = rows.astype(np.float64)
     order = np.lexsort((r[:, 5], r[:, 4], r[:, 3], r[:, 2], r[:, 1], -r[:, 0], np.asarray(img)))
     return rows[order]
+
+
+def assign_variant_case(name):
+    """(targets, overlap_masks, batch_size) of a tests/golden/assign_variants.npz case (oracle/make_golden.py)."""
+    from vision_conglomerate_b200 import synth
+    return {
+        "seg_overlap": lambda: (synth.targets(4, 12, 80, 3, fixed=False), True, 4),
+        "seg_plain": lambda: (synth.targets(4, 12, 80, 3, fixed=False), False, None),
+        "kpt": lambda: (synth.keypoint_targets(3, 10, 2), None, None),
+        "kpt_seg_overlap": lambda: (synth.keypoint_targets(3, 10, 2), True, 3),
+    }[name]()
+
+
+ASSIGN_VARIANTS = ("seg_overlap", "seg_plain", "kpt", "kpt_seg_overlap")

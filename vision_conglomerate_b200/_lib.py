@@ -25,7 +25,7 @@ SYMBOLS = (
     "bg_profile_stamps", "bg_profile_stamps_per_image", "bg_profile_decode_cycles",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
     "bg_detect_workspace_bytes", "bg_detect", "bg_decode_scale",
-    "bg_assign_workspace_bytes", "bg_assign_targets",
+    "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd",
     "bg_ratio_metrics",
@@ -110,6 +110,10 @@ def lib() -> C.CDLL:
     L.bg_assign_workspace_bytes.argtypes = [i64, i32]
     L.bg_assign_workspace_bytes.restype = sz
     L.bg_assign_targets.argtypes = [vp, i64, i32, i32, C.POINTER(f32), i32, f32, f32, vp, vp, vp, vp, i64, vp, vp, sz, vp]
+    L.bg_assign_ex_workspace_bytes.argtypes = [i64, i32, i32]
+    L.bg_assign_ex_workspace_bytes.restype = sz
+    L.bg_assign_targets_ex.argtypes = [vp, i64, i32, i32, i32, C.POINTER(f32), i32, f32, f32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp,
+                                       vp, sz, vp]
     L.bg_ciou_fwd.argtypes = [vp, vp, i64, f32, vp, vp]
     L.bg_ciou_bwd.argtypes = [vp, vp, vp, i64, f32, vp, vp]
     L.bg_loss_workspace_bytes.argtypes = [C.POINTER(LossParams)]
@@ -117,7 +121,7 @@ def lib() -> C.CDLL:
     L.bg_loss_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(LossParams), vp, vp, vp, vp, sz, vp]
     L.bg_loss_bwd.argtypes = [vp, vp, vp, C.POINTER(LossParams), vp, f32, vp, vp, vp, vp, sz, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
-    for name in ("bg_batched_nms", "bg_detect", "bg_decode_scale", "bg_assign_targets", "bg_ciou_fwd", "bg_ciou_bwd",
+    for name in ("bg_batched_nms", "bg_detect", "bg_decode_scale", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_ratio_metrics"):
         getattr(L, name).restype = C.c_int
     _lib = L

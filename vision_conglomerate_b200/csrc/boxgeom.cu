@@ -94,6 +94,8 @@ static size_t gnms_carve(unsigned char *base, long long n, long long max_groups,
     return align_up(b.off, 256);
 }
 
+constexpr int DET_SPILL_EDGES = 1 << 17;  // overlap edges per image that may spill past the shared-memory list
+
 struct DetWs {
     // decode stage (both NMS paths): per-tile survivor slots
     int *tile_count;
@@ -108,6 +110,7 @@ struct DetWs {
     int *cand_count;
     u32 *gflag;           // split mode hand-over (helper CTA -> main CTA)
     u32 *gedges;
+    u32 *gspill;
     u64 *gsorted;
     u64 *f_emit_key;      // globally ordered output only
     float4 *f_emit_box;
@@ -132,9 +135,10 @@ static size_t det_carve(unsigned char *base, int B, long long N, int tiles_per_i
     w.f_seg_off = b.take<long long>((size_t)B + 1);
     w.f_emit_count = b.take<int>(B);
     w.cand_count = b.take<int>(B);
-    w.gflag = b.take<u32>(2 * (size_t)B);
+    w.gflag = b.take<u32>(4 * (size_t)B);
     if (!general) {
         w.gedges = b.take<u32>((size_t)B * INMS_HCAP);
+        w.gspill = b.take<u32>((size_t)B * DET_SPILL_EDGES);
         w.gsorted = b.take<u64>((size_t)B * INMS_CAP);
     }
     w.stride = (long long)next_pow2((u32)N);
@@ -387,7 +391,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
             static const int split_env = []() { const char *e = getenv("BG_NMS_SPLIT"); return e ? atoi(e) : -1; }();
             q.split = pp->nms_path == 3 ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
         }
-        q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted;
+        q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted; q.gspill = w.gspill; q.gcap = DET_SPILL_EDGES;
         {   // programmatic dependent launch: the CTAs become resident while the decode kernel drains
             static const bool pdl = []() { const char *e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
             cudaLaunchConfig_t cfg;
@@ -460,7 +464,7 @@ static void assign_fill(AssignK &k, const float *targets, long long nt, int ny, 
                         float anchor_t, float edge_t)
 {
     memset(&k, 0, sizeof(k));
-    k.targets = targets; k.nt = nt; k.ny = ny; k.nx = nx; k.na = na;
+    k.targets = targets; k.row_stride = 6; k.nt = nt; k.ny = ny; k.nx = nx; k.na = na;
     k.fnx = (float)nx; k.fny = (float)ny;
     for (int a = 0; a < na; ++a) { k.aw[a] = anchors[2 * a] * (float)nx; k.ah[a] = anchors[2 * a + 1] * (float)ny; }
     k.anchor_t = anchor_t; k.edge_t = edge_t;
@@ -489,6 +493,53 @@ size_t bg_assign_workspace_bytes(int64_t nt, int32_t na)
     if (nt < 0 || na <= 0) return 0;
     const long long ncand = 5ll * na * nt;
     return align_up((size_t)((ncand + ASSIGN_THREADS - 1) / ASSIGN_THREADS + 1) * sizeof(int), 256);
+}
+
+size_t bg_assign_ex_workspace_bytes(int64_t nt, int32_t na, int32_t batch_size)
+{
+    if (nt < 0 || na <= 0 || batch_size < 0) return 0;
+    return bg_assign_workspace_bytes(nt, na) + align_up((size_t)(nt + 1) * sizeof(int), 256) +
+           align_up((size_t)(batch_size + 2) * sizeof(int), 256) + 256;
+}
+
+int bg_assign_targets_ex(const float *targets, int64_t nt, int32_t row_stride, int32_t ny, int32_t nx, const float *anchors,
+                         int32_t na, float anchor_t, float edge_t, int32_t tmask_mode, int32_t batch_size,
+                         int64_t *out_idx4, int64_t *out_cls, float *out_anchor, float *out_box, int64_t *out_tmask,
+                         float *out_kpts, int64_t cap, int32_t *out_count, void *workspace, size_t workspace_bytes,
+                         void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nt < 0 || ny <= 0 || nx <= 0 || na <= 0 || na > BG_MAX_ANCHORS || !anchors || !out_count || row_stride < 6) return BG_ERR_INVALID;
+    if (tmask_mode < 0 || tmask_mode > 2 || (tmask_mode == 2 && batch_size <= 0) || batch_size < 0) return BG_ERR_INVALID;
+    if (5ll * na * nt >= (1ll << 31)) return BG_ERR_INVALID;
+    if (nt > 0 && (!targets || !out_idx4 || !out_cls || !out_anchor || !out_box || !workspace || cap < 5ll * na * nt))
+        return BG_ERR_INVALID;
+    if (nt > 0 && ((tmask_mode && !out_tmask) || (row_stride > 6 && !out_kpts))) return BG_ERR_INVALID;
+    if (out_box && (((uintptr_t)out_box & 15) != 0)) return BG_ERR_INVALID;
+    if (workspace_bytes < bg_assign_ex_workspace_bytes(nt, na, batch_size)) return BG_ERR_WORKSPACE;
+    if (cudaMemsetAsync(out_count, 0, 2 * sizeof(int32_t), st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (nt == 0) return BG_OK;
+    unsigned char *wsp = (unsigned char *)workspace;
+    int *block_counts = (int *)wsp; wsp += bg_assign_workspace_bytes(nt, na);
+    int *tmask_of_target = (int *)wsp; wsp += align_up((size_t)(nt + 1) * sizeof(int), 256);
+    int *block_start = (int *)wsp;
+    Assign3K kk;
+    AssignK &k = kk.a[0];
+    assign_fill(k, targets, nt, ny, nx, anchors, na, anchor_t, edge_t);
+    k.row_stride = row_stride;
+    k.block_counts = block_counts;
+    k.idx4 = reinterpret_cast<long long *>(out_idx4);
+    k.cls64 = reinterpret_cast<long long *>(out_cls);
+    k.anchor = out_anchor; k.box = out_box; k.cap = cap; k.count = out_count;
+    if (tmask_mode) {
+        assign_tmask_kernel<<<1, 1024, 0, st>>>(targets, row_stride, nt, tmask_mode == 2, batch_size, tmask_of_target, block_start, out_count + 1);
+        BG_LAUNCH_CHECK();
+        k.tmask_of_target = tmask_of_target;
+        k.tmask64 = reinterpret_cast<long long *>(out_tmask);
+    }
+    if (row_stride > 6) k.kpts = out_kpts;
+    kk.a[1] = kk.a[2] = k;
+    return assign_launch(kk, 1, st);
 }
 
 int bg_assign_targets(const float *targets, int64_t nt, int32_t ny, int32_t nx, const float *anchors, int32_t na,

@@ -154,7 +154,7 @@ struct DecodeOut {
     u64 *chain;              // [B+1] look-back words
     long long *seg_off;      // [B+1] b*N (row offset of the image's emit list)
     int force_plain;         // 1: never use TMA (unaligned inputs, variant 1)
-    u32 *gflag;              // [2B] helper -> main flags of the split per-image NMS (zeroed here)
+    u32 *gflag;              // [4B] hand-over flags and spill counters of the per-image NMS (zeroed here)
     unsigned long long *cycles;  // optional profiling hook: [gridDim.x, 8] SM clock cycles thread 0 spent per phase
 };
 
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
             o.chain[b] = (b == 0) ? CHAIN_PREFIX : 0ull;
             o.seg_off[b] = (long long)b * k.N;
         }
-        for (int i = tid; i < 2 * k.B; i += DEC_THREADS) o.gflag[i] = 0u;
+        for (int i = tid; i < 4 * k.B; i += DEC_THREADS) o.gflag[i] = 0u;
     }
 
     auto tile_src = [&](int b, int r, int &si, int &lrow0, int &rows) -> const float * {

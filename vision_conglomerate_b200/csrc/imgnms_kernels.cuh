@@ -15,8 +15,9 @@
 //      the sequential greedy scan;
 //   5. bitonic sort of the keys (score desc, candidate index asc -- torchvision's stable order);
 //   6. class filter, ranks, output offset by decoupled look-back over the images, rows.
-// Images with more than INMS_CAP survivors or more than INMS_ECAP overlapping pairs are left to the general
-// segmented engine: the kernel raises BG_STATUS_NEED_GENERAL and the caller re-enqueues in general mode.
+// Overlap edges beyond the shared-memory list spill to a per-image list in global memory (L2 resident).  Images
+// with more than INMS_CAP survivors, or more edges than the spill list holds, are left to the general segmented
+// engine: the kernel raises BG_STATUS_NEED_GENERAL and the caller re-enqueues in general mode.
 #pragma once
 #include "detect_kernels.cuh"
 
@@ -30,7 +31,7 @@ constexpr int INMS_MAXT = 1024;      // tiles per image
 constexpr int INMS_GMAX = 64;        // grid cells per axis
 constexpr int INMS_ITEMS = 8192;     // (box, grid row) work items per pass
 constexpr int INMS_MAX_N = 1 << (32 - INMS_PBITS);  // candidates per image (key = score | idx | p)
-constexpr int INMS_HCAP = 4096;      // edges a helper CTA may hand over
+constexpr int INMS_HCAP = INMS_ECAP;  // edges a helper CTA hands over from its shared-memory list
 constexpr int INMS_HELPER_SHARE_32 = 7;  // the helper takes 7/32 of the pair-test items (it also does the sort)
 
 struct ImgNmsK {
@@ -58,8 +59,10 @@ struct ImgNmsK {
     unsigned long long *stamps;  // optional [B, INMS_STAMPS] globaltimer (ns) at the stage boundaries (profiling hook)
     // split mode (two CTAs per image when the GPU has room): the helper tests a share of the pairs and sorts the keys
     int split;
-    u32 *gflag;                // [B,2] helper -> main: edge count + 1, sorted keys ready
-    u32 *gedges;               // [B, INMS_HCAP]
+    u32 *gflag;                // [B,4]: helper -> main edge count + 1, sorted keys ready, spilled-edge counter, pad
+    u32 *gedges;               // [B, INMS_HCAP] the helper's shared-memory edge list
+    u32 *gspill;               // [B, gcap] edges that did not fit a CTA's shared-memory list (main and helper)
+    int gcap;
     u64 *gsorted;              // [B, INMS_CAP]
 };
 constexpr int INMS_STAMPS = 10;
@@ -394,10 +397,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
                     const float4 c = S.box[j];
                     const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
                     if (iou_suppresses(a, aa, c, ac, thr)) {
+                        const bool i_first = S.keys[i] < S.keys[j];  // earlier in (score desc, index asc) order
+                        const u32 ed = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
                         const int e = atomicAdd(&S.n_edges, 1);
-                        if (e < INMS_ECAP) {
-                            const bool i_first = S.keys[i] < S.keys[j];  // earlier in (score desc, index asc) order
-                            S.edges[e] = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
+                        if (e < INMS_ECAP) S.edges[e] = ed;
+                        else {  // shared-memory list full: spill to the image's global list
+                            const u32 o = atomicAdd(&k.gflag[4 * b + 2], 1u);
+                            if (o < (u32)k.gcap) k.gspill[(long long)b * k.gcap + o] = ed;
                         }
                     }
                 }
@@ -405,15 +411,14 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         }
         __syncthreads();
     }
-    int ne = S.n_edges;
+    int ne = min(S.n_edges, INMS_ECAP);  // edges in this CTA's shared-memory list (the rest were spilled)
     if (role == 0) {
         // ---- helper: hand the edges over, sort the keys, hand them over, done ----
         u32 *ge = k.gedges + (long long)b * INMS_HCAP;
-        const bool hover = ne > INMS_HCAP;
-        if (!hover) for (int e = tid; e < ne; e += INMS_THREADS) ge[e] = S.edges[e];
+        for (int e = tid; e < ne; e += INMS_THREADS) ge[e] = S.edges[e];
         __threadfence();
         __syncthreads();
-        if (tid == 0) ((volatile u32 *)k.gflag)[2 * b] = hover ? 0xffffffffu : (u32)ne + 1u;
+        if (tid == 0) ((volatile u32 *)k.gflag)[4 * b] = (u32)ne + 1u;
         const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
         for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
         __syncthreads();
@@ -424,44 +429,42 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         for (int j = tid; j < K; j += INMS_THREADS) gs[j] = S.keys[j];
         __threadfence();
         __syncthreads();
-        if (tid == 0) ((volatile u32 *)k.gflag)[2 * b + 1] = 1u;
+        if (tid == 0) ((volatile u32 *)k.gflag)[4 * b + 1] = 1u;
         return;
     }
-    if (k.split) {   // main: append the helper's edges
+    int nh = 0;  // edges in the helper's list
+    if (k.split) {
         if (tid == 0) {
             u32 v;
-            do { v = ((volatile u32 *)k.gflag)[2 * b]; } while (v == 0u);
-            S.img = (int)v;
+            do { v = ((volatile u32 *)k.gflag)[4 * b]; } while (v == 0u);
+            S.img = (int)v - 1;
         }
         __syncthreads();
-        const u32 hv = (u32)S.img;
+        nh = S.img;
         __threadfence();
-        if (hv == 0xffffffffu) ne = INMS_ECAP + 1;
-        else {
-            const int nh = (int)hv - 1;
-            const u32 *ge = k.gedges + (long long)b * INMS_HCAP;
-            if (ne <= INMS_ECAP && ne + nh <= INMS_ECAP)
-                for (int e = tid; e < nh; e += INMS_THREADS) S.edges[ne + e] = __ldcg(ge + e);
-            ne += nh;
-        }
-        __syncthreads();
     }
-    if (ne > INMS_ECAP) { over = true; ne = 0; K = 0; }
+    __syncthreads();  // (also: this CTA's own spills are complete)
+    int nsp = (int)min(((volatile u32 *)k.gflag)[4 * b + 2], 0x7fffffffu);  // spilled edges, main's and the helper's
+    if (nsp > k.gcap) { over = true; ne = nh = nsp = 0; K = 0; }
+    const u32 *ge = k.gedges + (long long)b * INMS_HCAP;
+    const u32 *gsp = k.gspill + (long long)b * k.gcap;
     INMS_STAMP(3);
 
     // ---- 4. greedy resolution by rounds -------------------------------------------------------------------------------
     for (int i = tid; i < INMS_CAP; i += INMS_THREADS) { S.state[i] = 0; S.blocked[i] = 0; }  // (aliases item_row)
     __syncthreads();
-    while (true) {
-        for (int e = tid; e < ne; e += INMS_THREADS) {
-            const u32 ed = S.edges[e];
-            const int i = (int)(ed >> 16), j = (int)(ed & 0xffffu);
-            if (S.state[j] == 0) {
-                const unsigned char si = S.state[i];
-                if (si == 1) S.state[j] = 2;
-                else if (si == 0) S.blocked[j] = 1;
-            }
+    auto relax = [&](u32 ed) {
+        const int i = (int)(ed >> 16), j = (int)(ed & 0xffffu);
+        if (S.state[j] == 0) {
+            const unsigned char si = S.state[i];
+            if (si == 1) S.state[j] = 2;
+            else if (si == 0) S.blocked[j] = 1;
         }
+    };
+    while (true) {
+        for (int e = tid; e < ne; e += INMS_THREADS) relax(S.edges[e]);
+        for (int e = tid; e < nh; e += INMS_THREADS) relax(__ldcg(ge + e));
+        for (int e = tid; e < nsp; e += INMS_THREADS) relax(__ldcg(gsp + e));
         __syncthreads();
         int pending = 0;
         for (int j = tid; j < K; j += INMS_THREADS) {
@@ -476,7 +479,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
 
     // ---- 5. sort ------------------------------------------------------------------------------------------------------
     if (k.split) {   // the helper sorted the keys meanwhile
-        if (tid == 0) { while (((volatile u32 *)k.gflag)[2 * b + 1] == 0u) { } }
+        if (tid == 0) { while (((volatile u32 *)k.gflag)[4 * b + 1] == 0u) { } }
         __syncthreads();
         __threadfence();
         const u64 *gs = k.gsorted + (long long)b * INMS_CAP;

@@ -12,7 +12,8 @@ namespace bg {
 // target assignment
 // ------------------------------------------------------------------------------------------------
 struct AssignK {
-    const float *targets;  // [nt,6]
+    const float *targets;  // [nt, row_stride]: (img, cls, x, y, w, h, keypoint columns...)
+    int row_stride;        // 6 + number of keypoint columns
     long long nt;
     int ny, nx, na;
     float fnx, fny;
@@ -30,12 +31,16 @@ struct AssignK {
     // packed outputs for the fused loss (any may be null)
     int *cell;             // [cap] ((b*ny+gj)*nx+gi)*na+a
     int *cls32;            // [cap]
+    // segmentation / keypoint variants (detection_dataset.py:132-172,239-245); null = detection branch
+    const int *tmask_of_target;  // [nt] mask index of every target (see assign_tmask_kernel)
+    long long *tmask64;          // [cap]
+    float *kpts;                 // [cap, row_stride-6]
 };
 
 constexpr int ASSIGN_THREADS = 1024;
 struct Assign3K { AssignK a[3]; };  // one launch covers up to three scales: blockIdx.y selects the entry
 
-struct AssignOut { int b, gj, gi, a, cls; float aw, ah, bx, by, bw, bh; };
+struct AssignOut { int b, gj, gi, a, cls; long long t; float aw, ah, bx, by, bw, bh; };
 
 __device__ __forceinline__ float torch_remainder1(float x)
 {
@@ -50,7 +55,7 @@ __device__ __forceinline__ bool assign_eval(const AssignK &k, long long c, Assig
     const long long t = c % k.nt;
     const int ka = (int)(c / k.nt);
     const int a = ka % k.na, kk = ka / k.na;
-    const float *tg = k.targets + 6 * t;
+    const float *tg = k.targets + (long long)k.row_stride * t;
     const float gx = __fmul_rn(tg[2], k.fnx), gy = __fmul_rn(tg[3], k.fny);
     const float gw = __fmul_rn(tg[4], k.fnx), gh = __fmul_rn(tg[5], k.fny);
     const float rw = __fdiv_rn(gw, k.aw[a]), rh = __fdiv_rn(gh, k.ah[a]);
@@ -67,6 +72,7 @@ __device__ __forceinline__ bool assign_eval(const AssignK &k, long long c, Assig
     long long gi = (long long)__fsub_rn(gx, ox), gj = (long long)__fsub_rn(gy, oy);  // .long() truncates (:231)
     gi = gi < 0 ? 0 : (gi > k.nx - 1 ? k.nx - 1 : gi);
     gj = gj < 0 ? 0 : (gj > k.ny - 1 ? k.ny - 1 : gj);
+    o.t = t;
     o.b = (int)(long long)tg[0];
     o.cls = (int)(long long)tg[1];
     o.gi = (int)gi; o.gj = (int)gj; o.a = a;
@@ -87,6 +93,44 @@ __device__ __forceinline__ int block_count_flags(bool f, int *s_w /*[32]*/)
         tot = warp_sum(v);
     }
     return tot;  // valid in warp 0
+}
+
+// Mask index of every target (detection_dataset.py:132-170).  overlap = 0: the target's own position.
+// overlap = 1: masks of one image are merged into one plane, the index is 1 + the position inside the image's
+// block, the blocks being laid out by the per-image counts for image ids 0..batch_size-1 in order (which is the
+// targets' own order when they are sorted by image, as collate_fn produces them).  status[0] is set to 1 when the
+// counts do not add up to nt (the reference's torch.cat would raise).
+__global__ void __launch_bounds__(1024) assign_tmask_kernel(const float *targets, int row_stride, long long nt, int overlap,
+                                                             int batch_size, int *tmask_of_target, int *block_start /*[batch_size+1]*/,
+                                                             int *status)
+{
+    if (!overlap) {
+        for (long long t = threadIdx.x; t < nt; t += 1024) tmask_of_target[t] = (int)t;
+        if (threadIdx.x == 0) status[0] = 0;
+        return;
+    }
+    for (int i = threadIdx.x; i <= batch_size; i += 1024) block_start[i] = 0;
+    __syncthreads();
+    for (long long t = threadIdx.x; t < nt; t += 1024) {
+        const float fi = targets[(long long)row_stride * t];
+        const int i = (int)fi;
+        if (i >= 0 && i < batch_size && (float)i == fi) atomicAdd(&block_start[i + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // batch_size is small: a serial prefix is fine
+        int run = 0;
+        for (int i = 1; i <= batch_size; ++i) { run += block_start[i]; block_start[i] = run; }
+        status[0] = (run == nt) ? 0 : 1;
+    }
+    __syncthreads();
+    for (long long p = threadIdx.x; p < nt; p += 1024) {
+        int lo = 0, hi = batch_size;  // largest block with block_start[block] <= p
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (block_start[mid] <= p) lo = mid; else hi = mid;
+        }
+        tmask_of_target[p] = (int)(p - block_start[lo]) + 1;
+    }
 }
 
 __global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(Assign3K kk)
@@ -143,6 +187,12 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(Assign3K kk
             if (k.box) { float4 *bp = reinterpret_cast<float4 *>(k.box) + m; *bp = make_float4(o.bx, o.by, o.bw, o.bh); }
             if (k.cell) k.cell[m] = ((o.b * k.ny + o.gj) * k.nx + o.gi) * k.na + o.a;
             if (k.cls32) k.cls32[m] = o.cls;
+            if (k.tmask64) k.tmask64[m] = k.tmask_of_target[o.t];
+            if (k.kpts) {
+                const int nk = k.row_stride - 6;
+                const float *src = k.targets + (long long)k.row_stride * o.t + 6;
+                for (int q = 0; q < nk; ++q) k.kpts[m * nk + q] = src[q];
+            }
         }
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *k.count = (int)(s_base + tot);

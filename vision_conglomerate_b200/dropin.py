@@ -36,11 +36,10 @@ def _make_build_target_by_scale(orig):
     def build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold: float = 4.0,
                               edge_threshold: float = 0.5, overlap_masks: Optional[bool] = None,
                               batch_size: Optional[int] = None):
-        # segmentation / keypoint variants stay on the reference's implementation (detection_dataset.py:132-172)
-        if overlap_masks is not None or (isinstance(targets, torch.Tensor) and targets.dim() == 2 and targets.shape[1] > 6):
-            return orig(targets, fmap_shape, anchors, anchor_threshold, edge_threshold, overlap_masks, batch_size)
+        # every variant (detection, segmentation masks, keypoint columns) runs on the CUDA kernel
         _need_cuda(targets, "build_target_by_scale")
-        return ops.build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold, edge_threshold)
+        return ops.build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold, edge_threshold, overlap_masks,
+                                         batch_size)
     return build_target_by_scale
 
 

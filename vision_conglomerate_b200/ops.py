@@ -259,14 +259,18 @@ def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int]
 
 # ---------------------------------------------------------------------------------------------- B1
 def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_threshold: float = 4.0,
-                          edge_threshold: float = 0.5):
-    """``DetectionDataset.build_target_by_scale`` (dataset/detection_dataset.py:90-246), detection branch.
-    Returns ``(indices, classes, anchors, boxes, None, None)`` exactly like the reference."""
+                          edge_threshold: float = 0.5, overlap_masks: Optional[bool] = None,
+                          batch_size: Optional[int] = None):
+    """``DetectionDataset.build_target_by_scale`` (dataset/detection_dataset.py:90-246), including the
+    segmentation (``overlap_masks``) and keypoint-column variants.  Returns
+    ``(indices, classes, anchors, boxes, tmask_idx, keypoints)`` exactly like the reference."""
     t = _req(targets, "targets")
-    if t.dim() != 2 or t.shape[1] != 6:
-        raise RuntimeError("build_target_by_scale: keypoint columns are out of scope for the CUDA path")
+    if t.dim() != 2 or t.shape[1] < 6:
+        raise RuntimeError("build_target_by_scale: targets must be [nt, 6 + keypoint columns]")
+    if overlap_masks and not batch_size:
+        raise ValueError("batch_size is required when overlap_mask is set to True")  # the reference's own error (:149-150)
     dev = t.device
-    nt = t.shape[0]
+    nt, stride = t.shape
     ny, nx = (int(v) for v in (fmap_shape.tolist() if isinstance(fmap_shape, torch.Tensor) else fmap_shape))
     anc = _anchors_host(anchors)
     na = len(anc)
@@ -277,14 +281,35 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_thr
     box = torch.empty(cap, 4, dtype=torch.float32, device=dev)
     count = torch.empty(2, dtype=torch.int32, device=dev)
     L = _lib.lib()
-    ws = _workspace(dev, "assign", max(L.bg_assign_workspace_bytes(nt, na), 256))
-    check(L.bg_assign_targets(t.data_ptr(), nt, ny, nx, _anchor_array(anc), na, float(anchor_threshold),
-                              float(edge_threshold), idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
-                              box.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
-          "bg_assign_targets")
-    M = int(_read_counts(count[:1], "assign")[0])
+    plain = overlap_masks is None and stride == 6
+    if plain:
+        ws = _workspace(dev, "assign", max(L.bg_assign_workspace_bytes(nt, na), 256))
+        check(L.bg_assign_targets(t.data_ptr(), nt, ny, nx, _anchor_array(anc), na, float(anchor_threshold),
+                                  float(edge_threshold), idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
+                                  box.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+              "bg_assign_targets")
+        M = int(_read_counts(count[:1], "assign")[0])
+        tmask = kpts = None
+    else:
+        mode = 0 if overlap_masks is None else (2 if overlap_masks else 1)
+        bs = int(batch_size) if batch_size else 0
+        tmask = torch.empty(cap, dtype=torch.int64, device=dev) if mode else None
+        kpts = torch.empty(cap, stride - 6, dtype=torch.float32, device=dev) if stride > 6 else None
+        ws = _workspace(dev, "assign", max(L.bg_assign_ex_workspace_bytes(nt, na, bs), 256))
+        check(L.bg_assign_targets_ex(t.data_ptr(), nt, stride, ny, nx, _anchor_array(anc), na, float(anchor_threshold),
+                                     float(edge_threshold), mode, bs, idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
+                                     box.data_ptr(), tmask.data_ptr() if mode else None,
+                                     kpts.data_ptr() if kpts is not None else None, cap, count.data_ptr(), ws.data_ptr(),
+                                     ws.numel(), _stream()), "bg_assign_targets_ex")
+        h = _read_counts(count, "assign")
+        if int(h[1]):
+            raise RuntimeError("build_target_by_scale: per-image target counts do not add up to the number of targets "
+                               "(image ids outside 0..batch_size-1)")
+        M = int(h[0])
+        tmask = tmask[:M] if tmask is not None else None
+        kpts = kpts[:M] if kpts is not None else None
     indices = [idx4[k, :M] for k in range(4)]
-    return indices, cls[:M], anc_out[:M], box[:M], None, None
+    return indices, cls[:M], anc_out[:M], box[:M], tmask, kpts
 
 
 # ---------------------------------------------------------------------------------------------- B2

@@ -117,6 +117,15 @@ def adversarial_targets(B: int = 2, C: int = 80) -> torch.Tensor:
     return torch.tensor(rows, dtype=torch.float32)
 
 
+def keypoint_targets(B: int, G: int, num_kp: int = 2, C: int = 80, seed: int = 5) -> torch.Tensor:
+    """``targets`` with ``3 * num_kp`` keypoint columns (x, y, visibility) appended, variable boxes per image."""
+    t = targets(B, G, C, seed, fixed=False)
+    g = torch.Generator().manual_seed(seed + 100)
+    kp = torch.rand(t.shape[0], num_kp, 3, generator=g)
+    kp[..., 2] = torch.randint(0, 3, (t.shape[0], num_kp), generator=g).float()
+    return torch.cat([t, kp.reshape(t.shape[0], -1)], 1).contiguous()
+
+
 def train_preds(B: int, H: int, W: int, C: int = 80, seed: int = 1, na: int = 3) -> List[torch.Tensor]:
     """Training-mode (already decoded) prediction tensors for the loss, ``torch.manual_seed(seed)``."""
     g = torch.Generator().manual_seed(seed)
