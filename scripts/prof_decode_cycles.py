@@ -18,7 +18,7 @@ plan.enqueue(raws); torch.cuda.synchronize()
 L.bg_profile_decode_cycles(None)
 c = buf.cpu().double()
 c = c[c.sum(1) > 0]
-names = ["locate+wait", "phase1", "barrier1", "list+barrier", "phase2a", "barrier+phase2b", "barrier_end", "refill"]
+names = ["locate+wait", "phase1", "barrier1", "list+barrier", "(unused)", "phase2", "barrier_end", "refill"]
 tot = c.sum(1)
 print("CTAs %d, cycles per CTA mean %.0f (%.1f us at 1.965 GHz), tiles/CTA %.1f" % (c.shape[0], tot.mean(), tot.mean() / 1965, 64 * 198 / c.shape[0]))
 for i, n in enumerate(names):

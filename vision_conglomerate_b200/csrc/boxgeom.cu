@@ -165,8 +165,12 @@ static bool det_valid(const bg_detect_params *p)
 {
     if (!p || p->B <= 0 || p->C <= 0 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->H <= 0 || p->W <= 0) return false;
     if (p->n_tracked < 0 || p->n_tracked > BG_MAX_TRACKED) return false;
-    for (int s = 0; s < 3; ++s)
+    for (int s = 0; s < 3; ++s) {
         if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
+        // the decode kernel divides by na and nx with 32-bit magic numbers: exact while n * d < 2^32
+        if ((long long)p->ny[s] * p->nx[s] * p->nx[s] >= (1ll << 32)) return false;
+        if ((long long)p->ny[s] * p->nx[s] * p->na * p->na >= (1ll << 32)) return false;
+    }
     const long long N = det_candidates(p);
     return N > 0 && N < (1ll << 31) && (long long)p->B * N < (1ll << 31);
 }
@@ -326,10 +330,12 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
         d.s0 = (float)pp->H / (float)pp->ny[s];
         d.s1 = (float)pp->W / (float)pp->nx[s];
         d.fnx = (float)pp->nx[s]; d.fny = (float)pp->ny[s];
+        d.magic_nx = (u32)(((1ull << 32) + (u64)pp->nx[s] - 1) / (u64)pp->nx[s]);
         for (int a = 0; a < pp->na; ++a) { d.aw[a] = pp->anchors[s][a][0]; d.ah[a] = pp->anchors[s][a][1]; }
         aligned = aligned && (((uintptr_t)raws[s] & 15) == 0);
     }
     k.B = pp->B; k.C = pp->C; k.D = pp->C + 5; k.na = pp->na; k.N = (int)N;
+    k.magic_na = (u32)(((1ull << 32) + (u64)pp->na - 1) / (u64)pp->na);
     // guard of modules/detection.py:76: rescale only if BOTH dimensions differ
     k.rescale = (pp->og_H > 0 && pp->og_W > 0 && pp->og_H != pp->H && pp->og_W != pp->W) ? 1 : 0;
     k.fW = (float)pp->W; k.fH = (float)pp->H; k.fW0 = (float)pp->og_W; k.fH0 = (float)pp->og_H;

@@ -15,6 +15,7 @@ struct ScaleDesc {
     int cells_na;      // ny*nx*na  (candidates per image on this scale)
     int img_off;       // flat index of this scale's first candidate inside an image
     long long rows;    // B*ny*nx*na
+    u32 magic_nx;      // ceil(2^32 / nx): n / nx == umulhi(n, magic_nx) for the cell counts in range (n * nx < 2^32)
     float s0, s1;      // float(H/ny) (multiplies x), float(W/nx) (multiplies y)  -- detection.py:147-154
     float fnx, fny;
     float aw[BG_MAX_ANCHORS], ah[BG_MAX_ANCHORS];
@@ -23,6 +24,7 @@ struct ScaleDesc {
 struct DetectK {
     ScaleDesc sc[3];
     int B, C, D, na, N;  // N = candidates per image over the three scales
+    u32 magic_na;        // ceil(2^32 / na)
     int rescale;         // apply _bbox_to_size (guard at detection.py:76 evaluated on the host)
     float fW, fH, fW0, fH0;
     int use_allowance;
@@ -97,8 +99,9 @@ __host__ __device__ inline void tile_locate(const DetectK &k, const TilePlan &tp
 // reads outstanding (HBM latency x bandwidth needs ~45 KB per SM).
 //   phase 1  one thread per row: class maximum and score from shared memory (row stride D = 5+C
 //            words, conflict-free when D is odd), strict threshold, survivors listed in smem;
-//   phase 2a one warp per survivor: class id (first index whose sigmoid equals the maximum sigmoid);
-//   phase 2b one thread per survivor: box decode, coalesced writes.
+//   phase 2  each warp finishes its own survivors, four at a time: eight lanes scan the class logits for the
+//            class id (first index whose sigmoid equals the maximum sigmoid), four lanes decode one box
+//            coordinate each and combine them with two shuffles; no barrier inside the phase.
 // Survivors of tile t go to the tile's own slots (b*N + first candidate of the tile + j, candidate order)
 // and their count to tile_count[t]: no global atomics, nothing to zero between calls.
 // ---------------------------------------------------------------------------------------------
@@ -283,54 +286,76 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         __syncthreads();
         DEC_MARK(3);  // survivor list
 
-        // phase 2a: one warp per survivor -- class id = first index whose sigmoid equals the maximum sigmoid.
-        // A logit equal to the maximum always qualifies; a smaller one only inside the tie window (rare), and
-        // only then is its sigmoid evaluated.
-        for (int q = wid; q < n; q += DEC_THREADS / 32) {
-            const float swm = s_surv[q].wm, spm = s_surv[q].pm;
-            const float *sr = tile + s_surv[q].row * D + 1;
-            const float lo = swm - tie_window(spm);
-            int ci = 0x7fffffff;
-            for (int c0 = 0; c0 < C; c0 += 96) {
-                float v[3];
-                u32 hit[3], near[3];
-#pragma unroll
-                for (int u = 0; u < 3; ++u) { const int c = c0 + 32 * u + lane; v[u] = c < C ? sr[c] : -INFINITY; }
-#pragma unroll
-                for (int u = 0; u < 3; ++u) {
-                    hit[u] = __ballot_sync(0xffffffffu, v[u] == swm);
-                    near[u] = __ballot_sync(0xffffffffu, v[u] >= lo && v[u] < swm);
-                }
-                if (near[0] | near[1] | near[2]) {  // warp-uniform
-#pragma unroll
-                    for (int u = 0; u < 3; ++u)
-                        hit[u] |= __ballot_sync(0xffffffffu, v[u] >= lo && v[u] < swm && sigmoid_acc(v[u]) == spm);
-                }
-#pragma unroll
-                for (int u = 2; u >= 0; --u) if (hit[u]) ci = c0 + 32 * u + __ffs(hit[u]) - 1;
-                if (ci != 0x7fffffff) break;
-            }
-            if (lane == 0) s_surv[q].ci = ci == 0x7fffffff ? 0 : ci;
-        }
-        DEC_MARK(4);  // phase 2a (this warp)
-        __syncthreads();
-
-        // phase 2b: one thread per survivor -- box decode and writes
+        // phase 2: every warp finishes its own survivors (q = wid, wid + 4, ...), four at a time -- no barrier
+        // between the class scan and the box decode.
+        //  class id: eight lanes per survivor scan the class logits for the first one equal to the maximum (the
+        //   first index whose sigmoid equals the maximum sigmoid; a smaller logit can only tie inside the tie
+        //   window, which is rare and then re-checked with sigmoids);
+        //  box: four lanes per survivor, one coordinate each (x, y, w, h), combined with two shuffles.
         if (tid == 0) o.tile_count[t] = n;
-        if (tid < n) {
-            const Surv sv = s_surv[tid];
-            const float *sr = tile + sv.row * D;
-            const int rl = lrow0 + sv.row;
-            const int a = rl % k.na, cell = rl / k.na;
-            const int x = cell % s.nx, y = cell / s.nx;
-            const int idx = s.img_off + rl;
-            const float4 bx = decode_xyxy(k, s, sr[C + 1], sr[C + 2], sr[C + 3], sr[C + 4], x, y, a);
-            const long long slot = (long long)b * k.N + s.img_off + lrow0 + tid;
-            k.keys[slot] = make_key(sv.score, (u32)idx);
-            k.box_slots[slot] = bx;
-            k.cls_slots[slot] = sv.ci;
+        {
+            const int grp = lane >> 3, gl = lane & 7;
+            for (int q0 = wid; q0 < n; q0 += 4 * (DEC_THREADS / 32)) {   // warp-uniform trip count
+                const int q = q0 + grp * (DEC_THREADS / 32);
+                const bool act = q < n;
+                const Surv sv = s_surv[act ? q : 0];
+                const float *sr = tile + sv.row * D;
+                const float lo = sv.wm - tie_window(sv.pm);
+                int first = 0x7fffffff, near = 0;
+                if (CT) {   // lane's classes gl, gl+8, ...: all loads in flight, then one select chain (descending)
+                    constexpr int NI = (CT + 7) / 8;
+                    float v[NI ? NI : 1];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) { const int c = gl + 8 * i; v[i] = c < CT ? sr[1 + c] : -INFINITY; }
+#pragma unroll
+                    for (int i = NI - 1; i >= 0; --i) {
+                        first = (v[i] == sv.wm) ? gl + 8 * i : first;
+                        near |= (int)(v[i] >= lo) & (int)(v[i] < sv.wm);
+                    }
+                } else {
+                    for (int c = C - 1 - ((C - 1 - gl) & 7); c >= 0; c -= 8) {
+                        const float v = sr[1 + c];
+                        first = (v == sv.wm) ? c : first;
+                        near |= (int)(v >= lo) & (int)(v < sv.wm);
+                    }
+                }
+#pragma unroll
+                for (int o2 = 1; o2 < 8; o2 <<= 1) {
+                    first = min(first, __shfl_xor_sync(0xffffffffu, first, o2));
+                    near |= __shfl_xor_sync(0xffffffffu, near, o2);
+                }
+                if (near && act) {   // some logit ties the maximum after rounding through the sigmoid?  (rare)
+                    for (int c = 0; c < first && c < C; ++c) {
+                        const float v = sr[1 + c];
+                        if (v >= lo && sigmoid_acc(v) == sv.pm) { first = c; break; }
+                    }
+                }
+                if (first == 0x7fffffff) first = 0;
+                // box: lane gl < 4 owns coordinate gl
+                const int comp = gl & 3;
+                const int rl = lrow0 + sv.row;
+                const int cell = (int)__umulhi((u32)rl, k.magic_na), a = rl - cell * k.na;      // rl / na, rl % na
+                const int gy = (int)__umulhi((u32)cell, s.magic_nx), gx = cell - gy * s.nx;     // cell / nx, cell % nx
+                const bool isx = (comp & 1) == 0;
+                const float sg2 = __fmul_rn(sigmoid_acc(sr[C + 1 + comp]), 2.0f);
+                float val;
+                if (comp < 2) val = __fmul_rn(__fadd_rn(__fsub_rn(sg2, 0.5f), isx ? (float)gx : (float)gy), isx ? s.s0 : s.s1);
+                else val = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(sg2, sg2), isx ? s.aw[a] : s.ah[a]), isx ? s.fnx : s.fny), isx ? s.s0 : s.s1);
+                if (k.rescale) val = __fmul_rn(__fdiv_rn(val, isx ? k.fW : k.fH), isx ? k.fW0 : k.fH0);
+                if (comp >= 2 && k.use_allowance) val = __fadd_rn(val, k.allowance);
+                const float other = __shfl_xor_sync(0xffffffffu, val, 2);                   // x <-> w, y <-> h
+                const float lo_c = __fsub_rn(val, __fmul_rn(other, 0.5f));                  // lanes 0,1: x1 = x - w/2, y1 = y - h/2
+                const float lo_o = __shfl_xor_sync(0xffffffffu, lo_c, 2);                   // lanes 2,3 receive x1, y1
+                const float outv = comp < 2 ? lo_c : __fadd_rn(lo_o, val);                  // x2 = x1 + w, y2 = y1 + h
+                if (act) {
+                    const long long slot = (long long)b * k.N + s.img_off + lrow0 + q;
+                    if (gl < 4) reinterpret_cast<float *>(k.box_slots + slot)[comp] = outv;
+                    if (gl == 4) k.keys[slot] = make_key(sv.score, (u32)(s.img_off + rl));
+                    if (gl == 5) k.cls_slots[slot] = first;
+                }
+            }
         }
-        DEC_MARK(5);  // barrier after 2a + phase 2b (this thread)
+        DEC_MARK(5);  // phase 2 (this warp)
         __syncthreads();  // the tile buffer and the survivor list are free again
         DEC_MARK(6);  // barrier: slowest thread of phase 2b
 
