@@ -477,7 +477,8 @@ static void assign_fill(AssignK &k, const float *targets, long long nt, int ny, 
     k.ncand = 5ll * na * nt;
 }
 
-// `n` scales (all with the same target list, hence the same candidate count) in one pair of launches
+// `n` scales (all with the same target list, hence the same candidate count) in one launch; the caller has
+// zeroed the chain words
 static int assign_launch(Assign3K &kk, int n, cudaStream_t st)
 {
     const AssignK &k = kk.a[0];
@@ -486,19 +487,22 @@ static int assign_launch(Assign3K &kk, int n, cudaStream_t st)
             if (cudaMemsetAsync(kk.a[s].count, 0, sizeof(int), st) != cudaSuccess) return BG_ERR_LAUNCH;
         return BG_OK;
     }
-    const int nblk = (int)((k.ncand + ASSIGN_THREADS - 1) / ASSIGN_THREADS);
-    assign_count_kernel<<<dim3(nblk, n), ASSIGN_THREADS, 0, st>>>(kk);
-    BG_LAUNCH_CHECK();
-    assign_emit_kernel<<<dim3(nblk, n), ASSIGN_THREADS, 0, st>>>(kk);
+    const int nblk = (int)((k.ncand + ASSIGN_BLOCK - 1) / ASSIGN_BLOCK);
+    assign_onepass_kernel<<<dim3(nblk, n), ASSIGN_THREADS, 0, st>>>(kk);
     BG_LAUNCH_CHECK();
     return BG_OK;
+}
+
+static size_t assign_chain_words(long long nt, int na)
+{
+    const long long ncand = 5ll * na * nt;
+    return (size_t)((ncand + ASSIGN_BLOCK - 1) / ASSIGN_BLOCK + 2);
 }
 
 size_t bg_assign_workspace_bytes(int64_t nt, int32_t na)
 {
     if (nt < 0 || na <= 0) return 0;
-    const long long ncand = 5ll * na * nt;
-    return align_up((size_t)((ncand + ASSIGN_THREADS - 1) / ASSIGN_THREADS + 1) * sizeof(int), 256);
+    return align_up(assign_chain_words(nt, na) * sizeof(u64), 256);
 }
 
 size_t bg_assign_ex_workspace_bytes(int64_t nt, int32_t na, int32_t batch_size)
@@ -526,14 +530,15 @@ int bg_assign_targets_ex(const float *targets, int64_t nt, int32_t row_stride, i
     if (cudaMemsetAsync(out_count, 0, 2 * sizeof(int32_t), st) != cudaSuccess) return BG_ERR_LAUNCH;
     if (nt == 0) return BG_OK;
     unsigned char *wsp = (unsigned char *)workspace;
-    int *block_counts = (int *)wsp; wsp += bg_assign_workspace_bytes(nt, na);
+    u64 *chain = (u64 *)wsp; wsp += bg_assign_workspace_bytes(nt, na);
+    if (cudaMemsetAsync(chain, 0, assign_chain_words(nt, na) * sizeof(u64), st) != cudaSuccess) return BG_ERR_LAUNCH;
     int *tmask_of_target = (int *)wsp; wsp += align_up((size_t)(nt + 1) * sizeof(int), 256);
     int *block_start = (int *)wsp;
     Assign3K kk;
     AssignK &k = kk.a[0];
     assign_fill(k, targets, nt, ny, nx, anchors, na, anchor_t, edge_t);
     k.row_stride = row_stride;
-    k.block_counts = block_counts;
+    k.chain = chain;
     k.idx4 = reinterpret_cast<long long *>(out_idx4);
     k.cls64 = reinterpret_cast<long long *>(out_cls);
     k.anchor = out_anchor; k.box = out_box; k.cap = cap; k.count = out_count;
@@ -562,7 +567,8 @@ int bg_assign_targets(const float *targets, int64_t nt, int32_t ny, int32_t nx, 
     Assign3K kk;
     AssignK &k = kk.a[0];
     assign_fill(k, targets, nt, ny, nx, anchors, na, anchor_t, edge_t);
-    k.block_counts = (int *)workspace;
+    k.chain = (u64 *)workspace;
+    if (nt > 0 && cudaMemsetAsync(workspace, 0, assign_chain_words(nt, na) * sizeof(u64), (cudaStream_t)stream) != cudaSuccess) return BG_ERR_LAUNCH;
     k.idx4 = reinterpret_cast<long long *>(out_idx4);
     k.cls64 = reinterpret_cast<long long *>(out_cls);
     k.anchor = out_anchor; k.box = out_box; k.cap = cap; k.count = out_count;
@@ -594,7 +600,8 @@ int bg_ciou_bwd(const float *p, const float *t, const float *go, int64_t M, floa
 // ------------------------------------------------------------------------------------------ B3
 namespace {
 struct LossWs {
-    int *block_counts[3];
+    u64 *chain[3];        // contiguous (one memset)
+    size_t chain_words;
     int *M;               // [3]
     int *cell[3];
     int *cls[3];
@@ -632,7 +639,11 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     if (w.cap < 1) w.cap = 1;
     w.nblk_match = sms * 8;
     w.nblk_dense = sms * 8;
-    const size_t nblk_assign = (size_t)((w.cap + ASSIGN_THREADS - 1) / ASSIGN_THREADS + 1);
+    w.chain_words = assign_chain_words(p->nt, p->na);
+    {
+        u64 *all = b.take<u64>(3 * w.chain_words);
+        for (int s = 0; s < 3; ++s) w.chain[s] = all ? all + s * w.chain_words : nullptr;
+    }
     w.cells_total = 0;
     for (int s = 0; s < 3; ++s) {
         w.cells[s] = (long long)p->B * p->ny[s] * p->nx[s] * p->na;
@@ -643,7 +654,6 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     w.head = b.take<int>(w.cells_total);
     w.gobj = b.take<float>(w.cells_total);
     for (int s = 0; s < 3; ++s) {
-        w.block_counts[s] = b.take<int>(nblk_assign);
         w.cell[s] = b.take<int>(w.cap);
         w.cls[s] = b.take<int>(w.cap);
         w.anchor[s] = b.take<float>(2 * w.cap);
@@ -705,10 +715,11 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
         float anc[2 * BG_MAX_ANCHORS];
         for (int q = 0; q < p->na; ++q) { anc[2 * q] = p->anchors[s][q][0]; anc[2 * q + 1] = p->anchors[s][q][1]; }
         assign_fill(a, targets, p->nt, p->ny[s], p->nx[s], anc, p->na, p->anchor_t, p->edge_t);
-        a.block_counts = w.block_counts[s];
+        a.chain = w.chain[s];
         a.anchor = w.anchor[s]; a.box = w.box[s]; a.cell = w.cell[s]; a.cls32 = w.cls[s];
         a.cap = w.cap; a.count = w.M + s;
     }
+    if (cudaMemsetAsync(w.chain[0], 0, 3 * w.chain_words * sizeof(u64), st) != cudaSuccess) return BG_ERR_LAUNCH;
     int rc = assign_launch(a3, 3, st);
     if (rc != BG_OK) return rc;
     Loss3K k;
@@ -716,7 +727,8 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
     for (int s = 0; s < 3; ++s) k.s[s].hist = reinterpret_cast<long long *>(out_hist) + (size_t)s * 3 * p->C;
     k.scalars = out_scalars;
     k.loss_out = out_loss;
-    loss_match_kernel<<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
+    if (p->C == 80) loss_match_kernel<80><<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
+    else loss_match_kernel<0><<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
     BG_LAUNCH_CHECK();
     loss_dense_kernel<<<dim3(w.nblk_dense, 3), LOSS_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
@@ -744,7 +756,7 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
     k.go_host = grad_out_host;
     const int sms = num_sms();
     {
-        const size_t smem = (size_t)BWD_WARPS * 2 * 32 * k.D * sizeof(float);
+        const size_t smem = (size_t)BWD_WARPS * 32 * k.D * sizeof(float);
         if (smem > 200 * 1024) return BG_ERR_INVALID;  // rows longer than ~780 floats do not fit the chunk images
         static size_t attr_smem = 0;
         if (smem > attr_smem) {
@@ -758,7 +770,8 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
         loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
         BG_LAUNCH_CHECK();
     }
-    loss_bwd_rows_kernel<<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
+    if (k.C == 80) loss_bwd_rows_kernel<80><<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
+    else loss_bwd_rows_kernel<0><<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }

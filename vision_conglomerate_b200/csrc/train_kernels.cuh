@@ -20,7 +20,7 @@ struct AssignK {
     float aw[BG_MAX_ANCHORS], ah[BG_MAX_ANCHORS];  // anchors in grid units: anchor * (nx, ny)   (:183)
     float anchor_t, edge_t;
     long long ncand;       // 5*na*nt
-    int *block_counts;     // [nblocks]
+    u64 *chain;            // [nblocks + 2] ticket counter + look-back words, zeroed by the host
     // outputs (any may be null)
     long long *idx4;       // [4,cap]
     long long *cls64;      // [cap]
@@ -42,9 +42,10 @@ struct Assign3K { AssignK a[3]; };  // one launch covers up to three scales: blo
 
 struct AssignOut { int b, gj, gi, a, cls; long long t; float aw, ah, bx, by, bw, bh; };
 
+// torch.remainder(x, 1): fmod(x, 1) == x - trunc(x) exactly in fp32 (the subtraction cannot round), NaN for +-inf
 __device__ __forceinline__ float torch_remainder1(float x)
 {
-    float r = fmodf(x, 1.0f);
+    float r = __fsub_rn(x, truncf(x));
     if (r != 0.0f && r < 0.0f) r += 1.0f;
     return r;
 }
@@ -52,8 +53,9 @@ __device__ __forceinline__ float torch_remainder1(float x)
 // candidate c = (k*na + a)*nt + t; returns whether it is emitted and, if so, its outputs
 __device__ __forceinline__ bool assign_eval(const AssignK &k, long long c, AssignOut &o)
 {
-    const long long t = c % k.nt;
-    const int ka = (int)(c / k.nt);
+    const u32 ka_u = (u32)c / (u32)k.nt;  // 5*na*nt < 2^31 is checked on the host
+    const long long t = (long long)((u32)c - ka_u * (u32)k.nt);
+    const int ka = (int)ka_u;
     const int a = ka % k.na, kk = ka / k.na;
     const float *tg = k.targets + (long long)k.row_stride * t;
     const float gx = __fmul_rn(tg[2], k.fnx), gy = __fmul_rn(tg[3], k.fny);
@@ -133,69 +135,95 @@ __global__ void __launch_bounds__(1024) assign_tmask_kernel(const float *targets
     }
 }
 
-__global__ void __launch_bounds__(ASSIGN_THREADS) assign_count_kernel(Assign3K kk)
-{
-    const AssignK &k = kk.a[blockIdx.y];
-    __shared__ int s_w[32];
-    const long long c = (long long)blockIdx.x * ASSIGN_THREADS + threadIdx.x;
-    AssignOut o;
-    const bool f = (c < k.ncand) && assign_eval(k, c, o);
-    const int tot = block_count_flags(f, s_w);
-    if (threadIdx.x == 0) k.block_counts[blockIdx.x] = tot;
-}
+// One pass: a block evaluates its 4096 candidates, counts the emitted ones, obtains its output offset by decoupled
+// look-back over the earlier blocks (blocks are numbered by an atomic ticket, so every block a block waits for is
+// already running) and writes its matches -- the reference's (k, a, t) boolean-mask order, deterministically.
+// k.chain: [nblk + 2] u64, zeroed by the host before the launch: word 0 = the ticket counter, word 1 + i = block i
+// (ASSIGN_AGG | own count, later ASSIGN_PREFIX | inclusive count).
+constexpr u64 ASSIGN_PREFIX = 1ull << 63, ASSIGN_AGG = 1ull << 62, ASSIGN_VALUE = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(ASSIGN_THREADS) assign_emit_kernel(Assign3K kk)
+constexpr int ASSIGN_SLICES = 4;  // candidates per thread: a block covers ASSIGN_SLICES * ASSIGN_THREADS consecutive candidates
+constexpr int ASSIGN_BLOCK = ASSIGN_SLICES * ASSIGN_THREADS;
+
+__global__ void __launch_bounds__(ASSIGN_THREADS) assign_onepass_kernel(Assign3K kk)
 {
     const AssignK &k = kk.a[blockIdx.y];
-    __shared__ int s_w[32];
+    __shared__ int s_w[ASSIGN_SLICES][32];
     __shared__ long long s_base;
-    // offset of this block = sum of the counts of all earlier blocks (fixed order -> deterministic)
-    long long part = 0;
-    for (int j = threadIdx.x; j < (int)blockIdx.x; j += ASSIGN_THREADS) part += k.block_counts[j];
-    part = warp_sum(part);
-    __shared__ long long s_p[32];
-    if ((threadIdx.x & 31) == 0) s_p[threadIdx.x >> 5] = part;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        long long v = s_p[threadIdx.x];
-        v = warp_sum(v);
-        if (threadIdx.x == 0) s_base = v;
-    }
-    __syncthreads();
-    const long long c = (long long)blockIdx.x * ASSIGN_THREADS + threadIdx.x;
-    AssignOut o;
-    const bool f = (c < k.ncand) && assign_eval(k, c, o);
-    const u32 bal = __ballot_sync(0xffffffffu, f);
+    __shared__ unsigned s_ticket;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (lane == 0) s_w[wid] = __popc(bal);
+    if (threadIdx.x == 0) s_ticket = (unsigned)atomicAdd((unsigned long long *)k.chain, 1ull);
     __syncthreads();
-    int woff = 0, tot = 0;
-    for (int q = 0; q < ASSIGN_THREADS / 32; ++q) {
-        const int v = s_w[q];
-        if (q < wid) woff += v;
-        tot += v;
+    const int bid = (int)s_ticket;
+    AssignOut o[ASSIGN_SLICES];
+    bool f[ASSIGN_SLICES];
+    u32 bal[ASSIGN_SLICES];
+#pragma unroll
+    for (int i = 0; i < ASSIGN_SLICES; ++i) {  // slice i = candidates [bid*BLOCK + i*1024, +1024): ballot order = candidate order
+        const long long c = (long long)bid * ASSIGN_BLOCK + i * ASSIGN_THREADS + threadIdx.x;
+        f[i] = (c < k.ncand) && assign_eval(k, c, o[i]);
+        bal[i] = __ballot_sync(0xffffffffu, f[i]);
+        if (lane == 0) s_w[i][wid] = __popc(bal[i]);
     }
-    if (f) {
-        const long long m = s_base + woff + __popc(bal & lanemask_lt());
-        if (m < k.cap) {
-            if (k.idx4) {
-                k.idx4[0 * k.cap + m] = o.b; k.idx4[1 * k.cap + m] = o.gj;
-                k.idx4[2 * k.cap + m] = o.gi; k.idx4[3 * k.cap + m] = o.a;
-            }
-            if (k.cls64) k.cls64[m] = o.cls;
-            if (k.anchor) { k.anchor[2 * m] = o.aw; k.anchor[2 * m + 1] = o.ah; }
-            if (k.box) { float4 *bp = reinterpret_cast<float4 *>(k.box) + m; *bp = make_float4(o.bx, o.by, o.bw, o.bh); }
-            if (k.cell) k.cell[m] = ((o.b * k.ny + o.gj) * k.nx + o.gi) * k.na + o.a;
-            if (k.cls32) k.cls32[m] = o.cls;
-            if (k.tmask64) k.tmask64[m] = k.tmask_of_target[o.t];
-            if (k.kpts) {
-                const int nk = k.row_stride - 6;
-                const float *src = k.targets + (long long)k.row_stride * o.t + 6;
-                for (int q = 0; q < nk; ++q) k.kpts[m * nk + q] = src[q];
-            }
+    __syncthreads();
+    int off[ASSIGN_SLICES], tot = 0;
+#pragma unroll
+    for (int i = 0; i < ASSIGN_SLICES; ++i) {
+        int woff = 0, st = 0;
+        for (int q = 0; q < ASSIGN_THREADS / 32; ++q) {
+            const int v = s_w[i][q];
+            if (q < wid) woff += v;
+            st += v;
+        }
+        off[i] = tot + woff;
+        tot += st;
+    }
+    if (wid == 0) {
+        volatile u64 *words = (volatile u64 *)k.chain + 1;
+        if (lane == 0) words[bid] = ASSIGN_AGG | (u64)tot;
+        long long base = 0;
+        int hi = bid - 1;
+        while (hi >= 0) {
+            const int j = hi - lane;  // newest first
+            u64 v = ASSIGN_PREFIX;    // lanes past block 0 read as "prefix 0"
+            if (j >= 0) { do { v = words[j]; } while (!(v & (ASSIGN_AGG | ASSIGN_PREFIX))); }
+            const u32 pm = __ballot_sync(0xffffffffu, (v & ASSIGN_PREFIX) != 0);
+            const int stop = pm ? (__ffs(pm) - 1) : 32;
+            long long part = (lane <= stop) ? (long long)(v & ASSIGN_VALUE) : 0;
+            part = warp_sum(part);
+            base += part;
+            if (pm) break;
+            hi -= 32;
+        }
+        if (lane == 0) {
+            s_base = base;
+            words[bid] = ASSIGN_PREFIX | (u64)(base + tot);
+            if (bid == (int)gridDim.x - 1) *k.count = (int)(base + tot);
         }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *k.count = (int)(s_base + tot);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < ASSIGN_SLICES; ++i) {
+        if (!f[i]) continue;
+        const long long m = s_base + off[i] + __popc(bal[i] & lanemask_lt());
+        if (m >= k.cap) continue;
+        const AssignOut &q = o[i];
+        if (k.idx4) {
+            k.idx4[0 * k.cap + m] = q.b; k.idx4[1 * k.cap + m] = q.gj;
+            k.idx4[2 * k.cap + m] = q.gi; k.idx4[3 * k.cap + m] = q.a;
+        }
+        if (k.cls64) k.cls64[m] = q.cls;
+        if (k.anchor) { k.anchor[2 * m] = q.aw; k.anchor[2 * m + 1] = q.ah; }
+        if (k.box) { float4 *bp = reinterpret_cast<float4 *>(k.box) + m; *bp = make_float4(q.bx, q.by, q.bw, q.bh); }
+        if (k.cell) k.cell[m] = ((q.b * k.ny + q.gj) * k.nx + q.gi) * k.na + q.a;
+        if (k.cls32) k.cls32[m] = q.cls;
+        if (k.tmask64) k.tmask64[m] = k.tmask_of_target[q.t];
+        if (k.kpts) {
+            const int nk = k.row_stride - 6;
+            const float *src = k.targets + (long long)k.row_stride * q.t + 6;
+            for (int r = 0; r < nk; ++r) k.kpts[m * nk + r] = src[r];
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -342,6 +370,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 constexpr int LOSS_THREADS = 256;
 constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
 
+template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled class loop); 0 = runtime
 __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
 {
     extern __shared__ int s_hist[];  // [3,C] block-local confusion counters
@@ -349,7 +378,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
     const LossScale &S = k.s[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int M = *S.M;
-    const int C = k.C, D = k.D;
+    const int C = CT ? CT : k.C, D = C + 5;
+    constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
     for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
     __syncthreads();
 
@@ -388,11 +418,11 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
             for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
                 float x[ROWS_UNROLL];
 #pragma unroll
-                for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = c < C ? __ldg(row + c) : -INFINITY; }
+                for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = (kFull || c < C) ? __ldg(row + c) : -INFINITY; }
 #pragma unroll
                 for (int u = 0; u < ROWS_UNROLL; ++u) {
                     const int c = cb + 8 * u + gl;
-                    if (c < C) {
+                    if (kFull || c < C) {
                         bsum += bce_logits_fast(x[u], c == tc ? k.cp : k.cn);
                         if (x[u] > best) { best = x[u]; bi = c; }
                     }
@@ -521,34 +551,29 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
 // grad_preds is zeros, one objectness value per row, and the class / box columns of the matched rows (6 % of
 // the rows).  Two kernels, no atomics, both with every warp of the machine busy:
 //
-// loss_bwd_stream_kernel: written the way a memset would be.  Every warp owns two shared-memory images of a
-//   32-row chunk (32*D floats, zero-filled once); per chunk it drops the 32 objectness values into column 0 of
-//   the rows (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and hands the
-//   image to the TMA store engine (cp.async.bulk.global.shared::cta: ONE instruction per 32*D*4-byte chunk),
-//   alternating between its two images so the next chunk is prepared while the copy drains.
+// loss_bwd_stream_kernel: written the way a fill would be.  Every warp owns a shared-memory image of a 32-row
+//   chunk (32*D floats, zero-filled once); per chunk it drops the 32 objectness values into column 0 of the rows
+//   (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and copies the image out
+//   with 16-byte loads from shared memory and 512-byte coalesced stores -- no per-element index arithmetic.
+//   (A TMA bulk store of the image, cp.async.bulk.global.shared::cta, measured 5.5 TB/s; this loop is faster.)
 // loss_bwd_rows_kernel: eight lanes per match; the most recently linked match of a cell (head of its list) owns
 //   the row, walks the list (gather backward = index_put(accumulate=True): every match of the cell contributes)
 //   and rewrites the row's class / box columns:
 //   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
 constexpr int BWD_THREADS = 256;
 
-constexpr int BWD_WARPS = 4;  // warps per CTA of the streaming kernel (each owns two chunk images)
-
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"((u32)__cvta_generic_to_shared(src)), "r"(bytes)
-                 : "memory");
-}
+constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
 
 __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
 {
-    extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][2][32*D]
+    extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][32*D]
     const int D = k.D;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int chunk_floats = 32 * D;
-    float *img0 = bwd_smem + (size_t)(2 * wid) * chunk_floats;
-    for (int i = lane; i < 2 * chunk_floats; i += 32) img0[i] = 0.f;  // both images; only column 0 of a row ever changes
+    const int chunk_floats = 32 * D, chunk_f4 = 8 * D;
+    float *im = bwd_smem + (size_t)wid * chunk_floats;
+    for (int i = lane; i < chunk_floats; i += 32) im[i] = 0.f;  // only column 0 of a row ever changes
     __syncwarp();
+    const float4 *im4 = reinterpret_cast<const float4 *>(im);
 
     long long nch[3], tot = 0;
     for (int s = 0; s < 3; ++s) { nch[s] = k.s[s].cells >> 5; tot += nch[s]; }  // full chunks; remainders below
@@ -564,24 +589,14 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
     int si = 0; long long row0 = 0;
     float gobj_n = 0.f;
     if (gw < tot) { locate(gw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }
-    int it = 0;
-    for (long long g = gw; g < tot; g += nw, ++it) {
-        float *dst = k.s[si].grad + row0 * D;
-        const float go = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gobj_n;
+    for (long long g = gw; g < tot; g += nw) {
+        float4 *dst = reinterpret_cast<float4 *>(k.s[si].grad + row0 * D);
+        im[lane * D] = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gobj_n;
         if (g + nw < tot) { locate(g + nw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }  // prefetch
-        float *im = img0 + (size_t)(it & 1) * chunk_floats;
-        // the bulk store issued from this image two chunks ago must have finished reading it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
-        im[lane * D] = go;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // every lane's value -> visible to the bulk copy
+        for (int f = lane; f < chunk_f4; f += 32) dst[f] = im4[f];  // shared-memory image -> 512-byte coalesced stores
         __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(dst, im, (u32)chunk_floats * 4);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
     // rows beyond the last full chunk of a scale (cells not a multiple of 32): plain stores by one CTA
     if (blockIdx.x == 0) {
@@ -594,6 +609,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
     }
 }
 
+template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled row loop); 0 = runtime
 __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
 {
     const LossScale &S = k.s[blockIdx.y];
@@ -601,7 +617,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
     const int M = *S.M;
     if (M <= 0) return;
     const BwdScales sc = bwd_scales(k, S);
-    const int C = k.C, D = k.D;
+    const int C = CT ? CT : k.C, D = C + 5;
     for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
          mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
         const long long m = mb + (lane >> 3);
@@ -618,29 +634,28 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
         }
         const float *xrow = S.preds + (long long)cell * D;
         float *grow = S.grad + (long long)cell * D;
-        // cls*(n*(sg - cn) - (cp - cn)*hits) = ka*sg - kb - kc*hits
+        // class column c: cls*(n*(sg - cn) - (cp - cn)*hits(c)) = ka*sg - kb - kc*hits(c); the (at most two) columns
+        // with hits are fixed up after the row loop by the lane that wrote them
         const float ka = sc.cls * (float)n, kb = ka * k.cn, kc = sc.cls * (k.cp - k.cn);
         for (int cb = 1; cb <= C; cb += 8 * ROWS_UNROLL) {
             float x[ROWS_UNROLL];
 #pragma unroll
             for (int u = 0; u < ROWS_UNROLL; ++u) {  // all loads of the batch in flight before the first store
                 const int col = cb + 8 * u + gl;
-                x[u] = col <= C ? __ldg(xrow + col) : 0.f;
+                x[u] = (CT != 0 && CT % (8 * ROWS_UNROLL) == 0) || col <= C ? __ldg(xrow + col) : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < ROWS_UNROLL; ++u) {
                 const int col = cb + 8 * u + gl;
-                if (col > C) continue;
-                const float sg = sigmoid_fast(x[u]);
-                const int c = col - 1;
-                float v;
-                if (n <= 2) v = (ka * sg - kb) - ((c == c1 ? kc : 0.f) + (c == c2 ? kc : 0.f));
-                else {  // three or more matches on one cell: walk the list
-                    v = 0.f;
-                    for (int j = (int)m; j >= 0; j = S.next[j]) v += sc.cls * (sg - ((c == S.cls[j]) ? k.cp : k.cn));
-                }
-                grow[col] = v;
+                if (!(CT != 0 && CT % (8 * ROWS_UNROLL) == 0) && col > C) continue;
+                grow[col] = ka * sigmoid_fast(x[u]) - kb;
             }
+        }
+        if (n <= 2) {
+            if (c1 >= 0 && gl == (c1 & 7)) grow[1 + c1] -= kc;
+            if (c2 >= 0 && gl == (c2 & 7)) grow[1 + c2] -= kc;
+        } else if (gl == 0) {  // three or more matches on one cell: one subtraction per match
+            for (int j = (int)m; j >= 0; j = S.next[j]) grow[1 + S.cls[j]] -= kc;
         }
         if (gl < 4) grow[C + 1 + gl] = sc.box * (gl == 0 ? gb[0] : gl == 1 ? gb[1] : gl == 2 ? gb[2] : gb[3]);
     }
