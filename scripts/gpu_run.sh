@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/stages.txt
 timeout 1500 python -m pytest tests -m gpu -q --timeout 300 -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/stages.txt
-timeout 600 python bench.py --steps 20 --warmup 3 --extra > gpurun_out/bench_auto.log 2>&1; echo "bench rc=$?" >> gpurun_out/stages.txt
+timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_auto.log 2>&1; echo "bench rc=$?" >> gpurun_out/stages.txt
 timeout 300 python scripts/prof_train.py > gpurun_out/train_plain.log 2>&1; echo "train rc=$?" >> gpurun_out/stages.txt
 if [ "$1" = "ncu" ]; then
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-extra"
 timeout 300 $CMD > gpurun_out/plain.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "ncu list rc=$?" >> gpurun_out/stages.txt

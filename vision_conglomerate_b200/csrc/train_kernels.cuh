@@ -84,19 +84,6 @@ __device__ __forceinline__ bool assign_eval(const AssignK &k, long long c, Assig
     return true;
 }
 
-__device__ __forceinline__ int block_count_flags(bool f, int *s_w /*[32]*/)
-{
-    const u32 b = __ballot_sync(0xffffffffu, f);
-    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(b);
-    __syncthreads();
-    int tot = 0;
-    if (threadIdx.x < 32) {
-        int v = (threadIdx.x < (int)(blockDim.x >> 5)) ? s_w[threadIdx.x] : 0;
-        tot = warp_sum(v);
-    }
-    return tot;  // valid in warp 0
-}
-
 // Mask index of every target (detection_dataset.py:132-170).  overlap = 0: the target's own position.
 // overlap = 1: masks of one image are merged into one plane, the index is 1 + the position inside the image's
 // block, the blocks being laid out by the per-image counts for image ids 0..batch_size-1 in order (which is the
@@ -560,7 +547,6 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
 //   the row, walks the list (gather backward = index_put(accumulate=True): every match of the cell contributes)
 //   and rewrites the row's class / box columns:
 //   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
-constexpr int BWD_THREADS = 256;
 
 constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
 
