@@ -550,6 +550,23 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
 
 constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
 
+// Mixing the 26 MB of residual reads into the 2.1 GB write stream costs ~45 us of DRAM read/write turnarounds
+// (measured: the same kernel without the loads runs 352 instead of 396 us).  So the residuals are pulled into L2
+// first, marked evict-last, and the write stream below uses evict-first stores: the streaming kernel's loads hit L2.
+__global__ void __launch_bounds__(256) l2_pin_kernel(const float4 *p, long long n4)
+{
+    float acc = 0.f;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 v;
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i), "l"(pol));
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 1.2345e-30f) asm volatile("trap;");  // keeps the loads alive
+}
+
 __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
 {
     extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][32*D]
@@ -572,15 +589,28 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
         if (ch >= nch[0]) { ch -= nch[0]; si = 1; if (ch >= nch[1]) { ch -= nch[1]; si = 2; } }
         row0 = ch << 5;
     };
-    int si = 0; long long row0 = 0;
-    float gobj_n = 0.f;
-    if (gw < tot) { locate(gw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }
+    // the residuals of the next BWD_AHEAD chunks are kept in flight: a chunk is only ~22 store instructions long,
+    // far shorter than the latency of the load that feeds the one after it
+    constexpr int BWD_AHEAD = 4;
+    float gq[BWD_AHEAD];
+#pragma unroll
+    for (int a = 0; a < BWD_AHEAD; ++a) {
+        gq[a] = 0.f;
+        const long long ga = gw + a * nw;
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[a] = k.s[s2].gobj[r2 + lane]; }
+    }
     for (long long g = gw; g < tot; g += nw) {
+        int si; long long row0;
+        locate(g, si, row0);
         float4 *dst = reinterpret_cast<float4 *>(k.s[si].grad + row0 * D);
-        im[lane * D] = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gobj_n;
-        if (g + nw < tot) { locate(g + nw, si, row0); gobj_n = k.s[si].gobj[row0 + lane]; }  // prefetch
+        im[lane * D] = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gq[0];
+#pragma unroll
+        for (int a = 0; a + 1 < BWD_AHEAD; ++a) gq[a] = gq[a + 1];
+        gq[BWD_AHEAD - 1] = 0.f;
+        const long long ga = g + BWD_AHEAD * nw;
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[BWD_AHEAD - 1] = k.s[s2].gobj[r2 + lane]; }
         __syncwarp();
-        for (int f = lane; f < chunk_f4; f += 32) dst[f] = im4[f];  // shared-memory image -> 512-byte coalesced stores
+        for (int f = lane; f < chunk_f4; f += 32) __stcs(dst + f, im4[f]);  // shared-memory image -> 512-byte coalesced, evict-first stores
         __syncwarp();
     }
 
