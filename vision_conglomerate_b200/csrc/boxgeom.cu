@@ -611,6 +611,7 @@ struct LossWs {
     float4 *gbox[3];
     int *head;            // all scales, contiguous (one memset)
     int *next[3];
+    unsigned char *succ;  // all scales, contiguous (one memset)
     float *gobj;          // all scales, contiguous
     double *part_match[3];
     double *part_dense[3];
@@ -652,6 +653,7 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     }
     w.M = b.take<int>(4);
     w.head = b.take<int>(w.cells_total);
+    w.succ = b.take<unsigned char>(3 * (size_t)w.cap);
     w.gobj = b.take<float>(w.cells_total);
     for (int s = 0; s < 3; ++s) {
         w.cell[s] = b.take<int>(w.cap);
@@ -681,7 +683,7 @@ void loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const float 
         S.preds = preds[s]; S.grad = grads ? grads[s] : nullptr; S.cells = w.cells[s];
         S.M = w.M + s; S.cell = w.cell[s]; S.cls = w.cls[s]; S.anchor = w.anchor[s]; S.box = w.box[s];
         S.ciou = w.ciou[s]; S.gbox = w.gbox[s];
-        S.head = w.head + w.cell_off[s]; S.next = w.next[s]; S.gobj = w.gobj + w.cell_off[s];
+        S.head = w.head + w.cell_off[s]; S.next = w.next[s]; S.succ = w.succ + (size_t)s * w.cap; S.gobj = w.gobj + w.cell_off[s];
         S.part_match = w.part_match[s]; S.part_dense = w.part_dense[s];
         S.scale_w = p->scale_w[s];
     }
@@ -709,6 +711,7 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
     const float *preds[3] = {preds_sm, preds_md, preds_lg};
     if (cudaMemsetAsync(out_hist, 0, sizeof(int64_t) * 9 * (size_t)p->C, st) != cudaSuccess) return BG_ERR_LAUNCH;
     if (cudaMemsetAsync(w.head, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (cudaMemsetAsync(w.succ, 0, 3 * (size_t)w.cap, st) != cudaSuccess) return BG_ERR_LAUNCH;
     Assign3K a3;
     for (int s = 0; s < 3; ++s) {
         AssignK &a = a3.a[s];

@@ -318,7 +318,8 @@ struct LossScale {
     float *ciou;         // [cap]
     float4 *gbox;        // [cap] d ciou / d (x, y, w_raw, h_raw) of the matched prediction
     int *head;           // [cells] most recently linked match of the cell (-1: none); list through next[]
-    int *next;           // [cap] previous match of the same cell, -1 at the end of the list
+    int *next;           // [cap] previous match of the same cell, -1 at the end of the list (= the cell's first match)
+    unsigned char *succ; // [cap] 1 if a later match was linked in front of this one (zeroed by the host)
     float *gobj;         // [cells] sigmoid(obj) - t_conf
     double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
     double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
@@ -385,7 +386,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
         const float ci = ciou_eval<float>(p, t, 1e-7f, g);
         S.ciou[m] = ci;
         S.gbox[m] = make_float4(g[0], g[1], g[2] * aw, g[3] * ah);
-        S.next[m] = atomicExch(&S.head[cell], (int)m);
+        const int prev = atomicExch(&S.head[cell], (int)m);
+        S.next[m] = prev;
+        if (prev >= 0) S.succ[prev] = 1;
         a0 += (double)__fsub_rn(1.0f, ci);
         a1 += (double)ci;
         a2 += (double)sigmoid_acc(obj);
@@ -543,8 +546,9 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
 //   (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and copies the image out
 //   with 16-byte loads from shared memory and 512-byte coalesced stores -- no per-element index arithmetic.
 //   (A TMA bulk store of the image, cp.async.bulk.global.shared::cta, measured 5.5 TB/s; this loop is faster.)
-// loss_bwd_rows_kernel: eight lanes per match; the most recently linked match of a cell (head of its list) owns
-//   the row, walks the list (gather backward = index_put(accumulate=True): every match of the cell contributes)
+// loss_bwd_rows_kernel: eight lanes per match; the first match linked into a cell owns the row (known from the
+//   forward: next == -1; and succ == 0 says it is the cell's only match, so nothing has to be looked up by cell),
+//   otherwise it walks the cell's list (gather backward = index_put(accumulate=True): every match of the cell contributes)
 //   and rewrites the row's class / box columns:
 //   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
 
@@ -638,15 +642,24 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
          mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
         const long long m = mb + (lane >> 3);
         if (m >= M) continue;
+        if (S.next[m] != -1) continue;  // the cell's first match owns the row
         const int cell = S.cell[m];
-        if (S.head[cell] != (int)m) continue;  // another match of the cell owns the row
         int n = 0, c1 = -1, c2 = -1;
         float gb[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = (int)m; j >= 0; j = S.next[j]) {
-            const float4 gq = S.gbox[j];
-            gb[0] += gq.x; gb[1] += gq.y; gb[2] += gq.z; gb[3] += gq.w;
-            if (n == 0) c1 = S.cls[j]; else if (n == 1) c2 = S.cls[j];
-            ++n;
+        int lhead = (int)m;
+        if (!S.succ[m]) {  // the only match of its cell (the usual case): everything is addressed by m, no list walk
+            const float4 gq = S.gbox[m];
+            gb[0] = gq.x; gb[1] = gq.y; gb[2] = gq.z; gb[3] = gq.w;
+            c1 = S.cls[m];
+            n = 1;
+        } else {
+            lhead = S.head[cell];
+            for (int j = lhead; j >= 0; j = S.next[j]) {
+                const float4 gq = S.gbox[j];
+                gb[0] += gq.x; gb[1] += gq.y; gb[2] += gq.z; gb[3] += gq.w;
+                if (n == 0) c1 = S.cls[j]; else if (n == 1) c2 = S.cls[j];
+                ++n;
+            }
         }
         const float *xrow = S.preds + (long long)cell * D;
         float *grow = S.grad + (long long)cell * D;
@@ -671,7 +684,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
             if (c1 >= 0 && gl == (c1 & 7)) grow[1 + c1] -= kc;
             if (c2 >= 0 && gl == (c2 & 7)) grow[1 + c2] -= kc;
         } else if (gl == 0) {  // three or more matches on one cell: one subtraction per match
-            for (int j = (int)m; j >= 0; j = S.next[j]) grow[1 + S.cls[j]] -= kc;
+            for (int j = lhead; j >= 0; j = S.next[j]) grow[1 + S.cls[j]] -= kc;
         }
         if (gl < 4) grow[C + 1 + gl] = sc.box * (gl == 0 ? gb[0] : gl == 1 ? gb[1] : gl == 2 ? gb[2] : gb[3]);
     }
