@@ -103,6 +103,13 @@ def cpu_oracle_run(sample_images, steps=1, warmup=0):
     from oracle import oracle as O
     from vision_conglomerate_b200 import synth
     w = WORKLOAD
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU baseline is meant to use every host core
+    threads = os.cpu_count() or 1
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(threads))
+    except OSError:
+        threads = int(os.environ.get("OMP_NUM_THREADS", threads))
     raws = synth.raw_head_outputs(sample_images, w["H"], w["W"], w["C"], w["dist"], w["seed"])
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
     times = []
@@ -114,7 +121,7 @@ def cpu_oracle_run(sample_images, steps=1, warmup=0):
         if it >= warmup:
             times.append(dt)
     t = sum(times) / len(times)
-    return sample_images / t, int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1)), t, int(out["keep"].shape[0])
+    return sample_images / t, int(threads), t, int(out["keep"].shape[0])
 
 
 def run_reference(args):

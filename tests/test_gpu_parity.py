@@ -137,6 +137,29 @@ def test_detect_oracle(ops, variant, nms_path, B, H, W, C, dist, og, iou, thr, a
                       nms_path=nms_path)
 
 
+@pytest.mark.parametrize("B,dist,iou", [(1, "T", 0.65), (100, "T", 0.65), (90, "N", 0.4)])
+def test_detect_batch_extremes(ops, B, dist, iou):
+    """B = 1 (video frames) and B > #SM/2 (one CTA per image, several look-back windows over the images)."""
+    H = W = 128
+    raws = synth.raw_head_outputs(B, H, W, 80, dist, seed=3)
+    _detect_vs_oracle(ops, raws, H, W, 80, None, iou, 0.001 if dist == "T" else 0.2, 4, None, 0, "image",
+                      max_mismatch=B // 8)
+
+
+def test_detect_dense_overlaps_spill(ops):
+    """Every box overlaps dozens of neighbours: the overlap edges outgrow the shared-memory list and are replayed
+    from the spill list; the per-image path must still agree bitwise with the general engine."""
+    B, H, W, C = 3, 224, 224, 80
+    raws = [dev(r) for r in synth.raw_head_outputs(B, H, W, C, "R", seed=5)]   # K = 3087 per image, all overlapping
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    a = ops.detect(raws, anc, (H, W), C, iou_threshold=0.5, score_threshold=0.001, box_allowance=4, nms_path="auto")
+    assert int(a.candidates.max()) <= 4096          # stayed on the per-image path
+    a = [t.clone() for t in (a.pred_boxes, a.sample_idxs, a.keep_idxs, a.counts)]
+    g = ops.detect(raws, anc, (H, W), C, iou_threshold=0.5, score_threshold=0.001, box_allowance=4, nms_path="general")
+    for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
+        assert torch.equal(x, y)
+
+
 def test_detect_paths_agree_exactly(ops):
     """The one-CTA-per-image NMS and the general segmented engine produce identical rows (bitwise)."""
     B, H, W, C = 8, 640, 640, 80
