@@ -38,7 +38,8 @@ extern "C" {
 /* bits of the device-side status word (out_counts[1]) */
 #define BG_STATUS_GROUP_RANGE 1 /* batched_nms: max(idxs)-min(idxs) exceeds max_groups */
 #define BG_STATUS_MASK_SPACE 2  /* suppression-mask scratch exhausted: retry with a larger workspace */
-#define BG_STATUS_NEED_GENERAL 4 /* bg_detect, per-image NMS path: an image has too many survivors or overlaps; retry with nms_path = 1 */
+#define BG_STATUS_NEED_GENERAL 4 /* bg_detect, per-image NMS path: an image has too many survivors (out_counts[2+B+b]) or overlaps;
+                                   * retry with nms_path = 4 (up to 8,192 survivors) or 1 */
 
 #define BG_MAX_ANCHORS 8
 #define BG_MAX_TRACKED 64
@@ -86,8 +87,9 @@ typedef struct {
     int32_t tracked[BG_MAX_TRACKED];
     int32_t order;              /* 0: image-major, score-descending inside an image; 1: globally score-descending (reference row order) */
     int32_t variant;            /* decode kernel tile loads: 0 auto, 1 plain loads, 2 TMA bulk pipeline (needs 16-byte aligned inputs) */
-    int32_t nms_path;           /* 0 auto (per-image CTAs when the threshold allows), 1 general segmented engine,
-                                 * 2 per-image only, 3 per-image only with one CTA per image (no helper CTA) */
+    int32_t nms_path;           /* 0 auto (per-image CTAs, up to 4,096 score survivors per image), 1 general segmented engine,
+                                 * 2 = 0 but an error instead of the general engine when the threshold rules it out,
+                                 * 3 = 2 with one CTA per image (no helper CTA), 4 per-image CTAs for up to 8,192 survivors */
 } bg_detect_params;
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);

@@ -164,6 +164,27 @@ def test_detect_dense_overlaps_spill(ops):
         assert torch.equal(x, y)
 
 
+def test_detect_large_per_image_variant(ops):
+    """More than 4,096 survivors per image: the shim steps up to the 8,192-survivor kernel (boxes in L2) and the
+    rows equal the general engine's bitwise."""
+    B, H, W, C = 3, 1280, 1280, 80
+    raws = [dev(r) for r in synth.raw_head_outputs(B, H, W, C, "T", seed=9)]        # ~6,800 survivors per image
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    a = ops.detect(raws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, nms_path="auto")
+    assert 4096 < int(a.candidates.max()) <= 8192
+    a = [t.clone() for t in (a.pred_boxes, a.sample_idxs, a.keep_idxs, a.counts)]
+    for path in ("per_image_large", "general"):
+        g = ops.detect(raws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, nms_path=path)
+        for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
+            assert torch.equal(x, y), path
+    # small inputs through the large kernel as well
+    raws = [dev(r) for r in synth.raw_head_outputs(4, 320, 320, C, "T", seed=2)]
+    s1 = ops.detect(raws, anc, (320, 320), C, iou_threshold=0.5, score_threshold=0.001, box_allowance=4, nms_path="per_image")
+    s1 = [t.clone() for t in (s1.pred_boxes, s1.keep_idxs)]
+    s2 = ops.detect(raws, anc, (320, 320), C, iou_threshold=0.5, score_threshold=0.001, box_allowance=4, nms_path="per_image_large")
+    assert torch.equal(s1[0], s2.pred_boxes) and torch.equal(s1[1], s2.keep_idxs)
+
+
 def test_detect_paths_agree_exactly(ops):
     """The one-CTA-per-image NMS and the general segmented engine produce identical rows (bitwise)."""
     B, H, W, C = 8, 640, 640, 80

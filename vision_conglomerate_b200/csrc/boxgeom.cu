@@ -112,6 +112,7 @@ struct DetWs {
     u32 *gedges;
     u32 *gspill;
     u64 *gsorted;
+    float4 *gboxp;
     u64 *f_emit_key;      // globally ordered output only
     float4 *f_emit_box;
     int *f_emit_cls;
@@ -139,7 +140,8 @@ static size_t det_carve(unsigned char *base, int B, long long N, int tiles_per_i
     if (!general) {
         w.gedges = b.take<u32>((size_t)B * INMS_HCAP);
         w.gspill = b.take<u32>((size_t)B * DET_SPILL_EDGES);
-        w.gsorted = b.take<u64>((size_t)B * INMS_CAP);
+        w.gsorted = b.take<u64>((size_t)B * INMS_CAP_MAX);
+        w.gboxp = b.take<float4>((size_t)B * INMS_CAP_MAX);
     }
     w.stride = (long long)next_pow2((u32)N);
     if (general) {
@@ -200,8 +202,8 @@ static int det_nms_path(const bg_detect_params *p, const TilePlan &tp)
     if (p->nms_path == 1) return 1;
     const IouThr t = make_iou_thr(p->iou_threshold);
     const bool ok = t.fast_ok && !t.zero_suppresses && t.tdn >= 0.05f && t.tdn < 1.0f && tp.tpi_total < INMS_MAXT &&
-                    det_candidates(p) <= INMS_MAX_N && p->C <= 65535;
-    if (p->nms_path == 2 || p->nms_path == 3) return ok ? 0 : -1;
+                    det_candidates(p) <= InmsLarge::MAX_N && p->C <= 65535;
+    if (p->nms_path >= 2 && p->nms_path <= 4) return ok ? 0 : -1;
     return ok ? 0 : 1;
 }
 
@@ -350,7 +352,8 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     if (!attr_set) {
         if (cudaFuncSetAttribute(decode_filter_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(decode_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(image_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem)) != cudaSuccess) {
+            cudaFuncSetAttribute(image_nms_kernel<InmsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsSmall>)) != cudaSuccess ||
+            cudaFuncSetAttribute(image_nms_kernel<InmsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsLarge>)) != cudaSuccess) {
             (void)cudaGetLastError();
             return BG_ERR_LAUNCH;
         }
@@ -398,17 +401,20 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
             q.split = pp->nms_path == 3 ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
         }
         q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted; q.gspill = w.gspill; q.gcap = DET_SPILL_EDGES;
+        q.gboxp = w.gboxp;
+        const bool large = pp->nms_path == 4;  // up to 8,192 survivors per image, boxes in L2 instead of shared memory
         {   // programmatic dependent launch: the CTAs become resident while the decode kernel drains
             static const bool pdl = []() { const char *e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
             cfg.gridDim = dim3(pp->B * (q.split ? 2 : 1)); cfg.blockDim = dim3(INMS_THREADS);
-            cfg.dynamicSmemBytes = sizeof(ImgNmsSmem); cfg.stream = st;
+            cfg.dynamicSmemBytes = large ? sizeof(ImgNmsSmem<InmsLarge>) : sizeof(ImgNmsSmem<InmsSmall>); cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-            if (cudaLaunchKernelEx(&cfg, image_nms_kernel, q) != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
+            const cudaError_t le = large ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLarge>, q) : cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsSmall>, q);
+            if (le != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
             ++g_launches;
         }
         if (pp->order) {

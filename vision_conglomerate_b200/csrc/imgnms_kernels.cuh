@@ -24,15 +24,27 @@
 namespace bg {
 
 constexpr int INMS_THREADS = 1024;
-constexpr int INMS_CAP = 4096;       // survivors per image held in shared memory
-constexpr int INMS_PBITS = 12;       // bits of p inside the sort key
-constexpr int INMS_ECAP = 12288;     // overlap edges per image
 constexpr int INMS_MAXT = 1024;      // tiles per image
 constexpr int INMS_GMAX = 64;        // grid cells per axis
-constexpr int INMS_ITEMS = 8192;     // (box, grid row) work items per pass
-constexpr int INMS_MAX_N = 1 << (32 - INMS_PBITS);  // candidates per image (key = score | idx | p)
-constexpr int INMS_HCAP = INMS_ECAP;  // edges a helper CTA hands over from its shared-memory list
 constexpr int INMS_HELPER_SHARE_32 = 7;  // the helper takes 7/32 of the pair-test items (it also does the sort)
+
+// Two sizes of the kernel.  Small: up to 4 096 survivors per image, boxes in shared memory (the headline case).
+// Large: up to 8 192 survivors; the boxes no longer fit next to the keys, so they live in a compact global
+// array (L2-resident) and only the bf16 extents used by the pre-filter stay in shared memory.
+template <int CAP_, bool BOX_SMEM_>
+struct InmsCfg {
+    static constexpr int CAP = CAP_;                 // survivors per image
+    static constexpr bool BOX_SMEM = BOX_SMEM_;
+    static constexpr int PBITS = CAP_ == 4096 ? 12 : 13;   // bits of p inside the sort key
+    static constexpr int ECAP = BOX_SMEM_ ? 12288 : 8192;  // overlap edges in shared memory (more spill to global)
+    static constexpr int ITEMS = 2 * CAP_;           // (box, grid row) work items per pass
+    static constexpr int PER = CAP_ / INMS_THREADS;  // boxes / sort keys per thread
+    static constexpr int MAX_N = 1 << (32 - PBITS);  // candidates per image (key = score | idx | p)
+};
+typedef InmsCfg<4096, true> InmsSmall;
+typedef InmsCfg<8192, false> InmsLarge;
+constexpr int INMS_CAP_MAX = InmsLarge::CAP;
+constexpr int INMS_HCAP = 12288;     // edges a helper CTA hands over from its shared-memory list (>= any ECAP)
 
 struct ImgNmsK {
     int B, N, TR, tpi_total;
@@ -63,7 +75,8 @@ struct ImgNmsK {
     u32 *gedges;               // [B, INMS_HCAP] the helper's shared-memory edge list
     u32 *gspill;               // [B, gcap] edges that did not fit a CTA's shared-memory list (main and helper)
     int gcap;
-    u64 *gsorted;              // [B, INMS_CAP]
+    u64 *gsorted;              // [B, INMS_CAP_MAX]
+    float4 *gboxp;             // [B, INMS_CAP_MAX] large variant: boxes in survivor (p) order
 };
 constexpr int INMS_STAMPS = 10;
 
@@ -75,34 +88,34 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #define INMS_STAMP(i) do { if (k.stamps && tid == 0 && role == 1) k.stamps[(long long)b * INMS_STAMPS + (i)] = globaltimer_ns(); } while (0)
 
+template <class Cfg>
 struct ImgNmsSmem {
-    u64 keys[INMS_CAP];                          // (~score | idx | p); indexed by p until the sort
-    float4 box[INMS_CAP];                        // by p
-    u32 edges[INMS_ECAP];                        // (from << 16) | to, in p numbers
+    u64 keys[Cfg::CAP];                          // (~score | idx | p); indexed by p until the sort
+    float4 box[Cfg::BOX_SMEM ? Cfg::CAP : 1];    // by p (small variant only)
+    u32 edges[Cfg::ECAP];                        // (from << 16) | to, in p numbers
     int cell_start[INMS_GMAX * INMS_GMAX + 1];
     union {
         int tile_pref[INMS_MAXT + 1];            // stage 1
-        unsigned short cellord[INMS_CAP];        // stage 2..3: box numbers in cell order
+        unsigned short cellord[Cfg::CAP];        // stage 2..3: box numbers in cell order
     };
     union {
-        struct { unsigned short cell_of[INMS_CAP], rank_in_cell[INMS_CAP]; };  // stage 2
-        unsigned short item_owner[INMS_ITEMS];                                 // stage 3
+        struct { unsigned short cell_of[Cfg::CAP], rank_in_cell[Cfg::CAP]; };  // stage 2
+        unsigned short item_owner[Cfg::ITEMS];                                 // stage 3
     };
     union {
-        unsigned char item_row[INMS_ITEMS];                                    // stage 3
-        struct { unsigned char state[INMS_CAP], blocked[INMS_CAP]; };          // stage 4..6: 0 undecided, 1 kept, 2 suppressed
+        unsigned char item_row[Cfg::ITEMS];                                    // stage 3
+        struct { unsigned char state[Cfg::CAP], blocked[Cfg::CAP]; };          // stage 4..6: 0 undecided, 1 kept, 2 suppressed
     };
-    unsigned short cls[INMS_CAP];                // by p
-    u32 whc[INMS_CAP];                           // stage 3: (w, h) of the boxes in cell order, truncated to bf16 pairs
+    unsigned short cls[Cfg::CAP];                // by p
+    u32 whc[Cfg::CAP];                           // stage 3: (w, h) of the boxes in cell order, truncated to bf16 pairs
     int wsum[33];
     float red[4][32];
     int n_edges;
     int img;
     long long base;
 };
-static_assert(INMS_ITEMS * sizeof(unsigned short) == 2 * INMS_CAP * sizeof(unsigned short), "item_owner aliases cell_of + rank_in_cell");
-static_assert(INMS_CAP == 4 * INMS_THREADS, "the register sort holds at most four keys per thread");
-static_assert(sizeof(ImgNmsSmem) <= 227 * 1024, "per-image NMS state must fit one SM's shared memory");
+static_assert(sizeof(ImgNmsSmem<InmsSmall>) <= 227 * 1024 && sizeof(ImgNmsSmem<InmsLarge>) <= 227 * 1024,
+              "per-image NMS state must fit one SM's shared memory");
 
 __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, int &total)
 {
@@ -194,6 +207,20 @@ __device__ __forceinline__ void inms_sort_reg(u64 *s)
     __syncthreads();
 }
 
+// pads keys[K..P) with ~0 and sorts keys[0..P), P = the smallest of 1024, 2048, 4096 (, 8192) >= K
+template <class Cfg>
+__device__ __forceinline__ void inms_sort_keys(u64 *keys, int K)
+{
+    int P = INMS_THREADS;
+    while (P < K) P <<= 1;
+    for (int j = K + threadIdx.x; j < P; j += INMS_THREADS) keys[j] = ~0ull;
+    __syncthreads();
+    if (P == INMS_THREADS) inms_sort_reg<1>(keys);
+    else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(keys);
+    else if (P == 4 * INMS_THREADS || Cfg::CAP <= 4 * INMS_THREADS) inms_sort_reg<4>(keys);
+    else inms_sort_reg<8>(keys);
+}
+
 __device__ __forceinline__ bool inms_tracked(const ImgNmsK &k, int c)
 {
     for (int i = 0; i < k.n_tracked; ++i)
@@ -216,11 +243,13 @@ __device__ __forceinline__ bool inms_box_valid(const float4 bx, float &w, float 
     return (w > 0.0f) && (h > 0.0f) && (w < INFINITY) && (h < INFINITY) && (fabsf(cx) < INFINITY) && (fabsf(cy) < INFINITY);
 }
 
+template <class Cfg>
 __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
 {
     extern __shared__ __align__(16) unsigned char inms_raw[];
-    ImgNmsSmem &S = *reinterpret_cast<ImgNmsSmem *>(inms_raw);
+    ImgNmsSmem<Cfg> &S = *reinterpret_cast<ImgNmsSmem<Cfg> *>(inms_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int CAP = Cfg::CAP, PER = Cfg::PER;
 
     // launched with programmatic stream serialization: the CTA may become resident while the decode kernel
     // drains; everything it reads is produced by that kernel, so wait for it here
@@ -233,6 +262,10 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     const int role = k.split ? (S.img & 1) : 1;
     if (b >= k.B) return;
     const long long ibase = (long long)b * k.N;
+    // boxes by survivor number p: shared memory (small variant) or the image's compact global array (large variant;
+    // both CTAs of an image write identical values there, then read their own writes)
+    float4 *gbx = k.gboxp + (long long)b * INMS_CAP_MAX;
+    auto box_at = [&](int i) -> float4 { return Cfg::BOX_SMEM ? S.box[i] : gbx[i]; };
     INMS_STAMP(0);
 
     // ---- 1. tile counts -> prefix; keys, boxes, classes into shared memory (slot order = candidate order) ----
@@ -244,7 +277,8 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         if (tid == 0) S.n_edges = 0;
     }
     __syncthreads();
-    bool over = K > INMS_CAP;
+    const int K_all = K;
+    bool over = K > CAP;
     if (over) K = 0;  // this image is left to the general path; it still takes part in the look-back chain
     float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
     for (int j = tid; j < K; j += INMS_THREADS) {
@@ -259,12 +293,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         const u64 key = k.keys[slot];
         const float4 bx = k.box_slots[slot];
         const int cl = k.cls_slots[slot];
-        S.keys[j] = (key & 0xffffffff00000000ull) | ((u64)key_id(key) << INMS_PBITS) | (u64)j;
-        S.box[j] = bx;
+        S.keys[j] = (key & 0xffffffff00000000ull) | ((u64)key_id(key) << Cfg::PBITS) | (u64)j;
+        if (Cfg::BOX_SMEM) S.box[j] = bx; else gbx[j] = bx;
         S.cls[j] = (unsigned short)cl;
         float w, h, cx, cy;
         if (inms_box_valid(bx, w, h, cx, cy)) { mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy); }
     }
+    if (!Cfg::BOX_SMEM) __syncthreads();  // the global box array is complete (block-scope visibility)
     INMS_STAMP(1);
 
     // ---- 2. grid over the valid centres, counting sort by cell --------------------------------------------------
@@ -297,7 +332,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     for (int i = tid; i < K; i += INMS_THREADS) {
         float w, h, cx, cy;
         unsigned short cell = 0xffff;
-        if (inms_box_valid(S.box[i], w, h, cx, cy)) {
+        if (inms_box_valid(box_at(i), w, h, cx, cy)) {
             cell = (unsigned short)(gr.cy(cy) * G + gr.cx(cx));
             S.rank_in_cell[i] = (unsigned short)atomicAdd(&S.cell_start[cell], 1);
         }
@@ -320,7 +355,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         const unsigned short cell = S.cell_of[i];
         if (cell != 0xffff) {
             const int pos = S.cell_start[cell] + S.rank_in_cell[i];
-            const float4 bx = S.box[i];
+            const float4 bx = box_at(i);
             S.cellord[pos] = (unsigned short)i;
             // extents rounded toward zero to bf16: stored <= true < stored * (1 + 2^-7)
             S.whc[pos] = (__float_as_uint(__fsub_rn(bx.z, bx.x)) >> 16) | (__float_as_uint(__fsub_rn(bx.w, bx.y)) & 0xffff0000u);
@@ -329,14 +364,14 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     // Work items = (box, grid row) for the rows from the box's own row down to the end of its reach: a pair in
     // different cells is tested by the box whose cell comes first in row-major order, a pair inside one cell
     // by the lower-numbered box (each box of a pair lies in the other's reach, so either side finds it).
-    // Thread t owns boxes 4t..4t+3.
-    int y0[4], nrow[4], items = 0;
+    // Thread t owns boxes PER*t .. PER*t + PER-1.
+    int y0[PER], nrow[PER], items = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = tid * 4 + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         y0[q] = 0; nrow[q] = 0;
         float w, h, cx, cy;
-        if (i < K && inms_box_valid(S.box[i], w, h, cx, cy)) {
+        if (i < K && inms_box_valid(box_at(i), w, h, cx, cy)) {
             const float ry = gr.reach * h + gr.pad;
             y0[q] = gr.cy(cy);
             nrow[q] = gr.cy(cy + ry) - y0[q] + 1;
@@ -351,16 +386,16 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     const IouThr thr = k.thr;
     const int T_helper = k.split ? (int)(((long long)T * INMS_HELPER_SHARE_32) >> 5) : 0;
     const int it_lo = role == 1 ? T_helper : 0, it_hi = role == 1 ? T : T_helper;
-    for (int c0 = it_lo; c0 < it_hi; c0 += INMS_ITEMS) {
-        const int nit = min(INMS_ITEMS, it_hi - c0);
+    for (int c0 = it_lo; c0 < it_hi; c0 += Cfg::ITEMS) {
+        const int nit = min(Cfg::ITEMS, it_hi - c0);
         {   // publish the items of this pass
             int it = item0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < PER; ++q) {
                 for (int r = 0; r < nrow[q]; ++r, ++it) {
                     const int rel = it - c0;
                     if (rel >= 0 && rel < nit) {
-                        S.item_owner[rel] = (unsigned short)(tid * 4 + q);
+                        S.item_owner[rel] = (unsigned short)(tid * PER + q);
                         S.item_row[rel] = (unsigned char)(y0[q] + r);
                     }
                 }
@@ -370,7 +405,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         for (int it = tid; it < nit; it += INMS_THREADS) {
             const int i = S.item_owner[it];
             const int gy = S.item_row[it];
-            const float4 a = S.box[i];
+            const float4 a = box_at(i);
             const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
             const float aa = __fmul_rn(w, h);
             const float cx = 0.5f * a.x + 0.5f * a.z, cy = 0.5f * a.y + 0.5f * a.w;
@@ -394,13 +429,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
                     if (wt * 1.008f < wlo || ht * 1.008f < hlo || tsc * wt > w || tsc * ht > h) continue;
                     const int j = S.cellord[q + u];
                     if (q + u < q_own && j <= i) continue;  // same cell: the lower-numbered box owns the test
-                    const float4 c = S.box[j];
+                    const float4 c = box_at(j);
                     const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
                     if (iou_suppresses(a, aa, c, ac, thr)) {
                         const bool i_first = S.keys[i] < S.keys[j];  // earlier in (score desc, index asc) order
                         const u32 ed = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
                         const int e = atomicAdd(&S.n_edges, 1);
-                        if (e < INMS_ECAP) S.edges[e] = ed;
+                        if (e < Cfg::ECAP) S.edges[e] = ed;
                         else {  // shared-memory list full: spill to the image's global list
                             const u32 o = atomicAdd(&k.gflag[4 * b + 2], 1u);
                             if (o < (u32)k.gcap) k.gspill[(long long)b * k.gcap + o] = ed;
@@ -411,7 +446,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         }
         __syncthreads();
     }
-    int ne = min(S.n_edges, INMS_ECAP);  // edges in this CTA's shared-memory list (the rest were spilled)
+    int ne = min(S.n_edges, Cfg::ECAP);  // edges in this CTA's shared-memory list (the rest were spilled)
     if (role == 0) {
         // ---- helper: hand the edges over, sort the keys, hand them over, done ----
         u32 *ge = k.gedges + (long long)b * INMS_HCAP;
@@ -419,13 +454,8 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         __threadfence();
         __syncthreads();
         if (tid == 0) ((volatile u32 *)k.gflag)[4 * b] = (u32)ne + 1u;
-        const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
-        for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
-        __syncthreads();
-        if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
-        else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
-        else inms_sort_reg<4>(S.keys);
-        u64 *gs = k.gsorted + (long long)b * INMS_CAP;
+        inms_sort_keys<Cfg>(S.keys, K);
+        u64 *gs = k.gsorted + (long long)b * INMS_CAP_MAX;
         for (int j = tid; j < K; j += INMS_THREADS) gs[j] = S.keys[j];
         __threadfence();
         __syncthreads();
@@ -451,7 +481,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     INMS_STAMP(3);
 
     // ---- 4. greedy resolution by rounds -------------------------------------------------------------------------------
-    for (int i = tid; i < INMS_CAP; i += INMS_THREADS) { S.state[i] = 0; S.blocked[i] = 0; }  // (aliases item_row)
+    for (int i = tid; i < CAP; i += INMS_THREADS) { S.state[i] = 0; S.blocked[i] = 0; }  // (aliases item_row)
     __syncthreads();
     auto relax = [&](u32 ed) {
         const int i = (int)(ed >> 16), j = (int)(ed & 0xffffu);
@@ -482,30 +512,25 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         if (tid == 0) { while (((volatile u32 *)k.gflag)[4 * b + 1] == 0u) { } }
         __syncthreads();
         __threadfence();
-        const u64 *gs = k.gsorted + (long long)b * INMS_CAP;
+        const u64 *gs = k.gsorted + (long long)b * INMS_CAP_MAX;
         for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = __ldcg(gs + j);
         __syncthreads();
     } else {
-        const int P = K <= INMS_THREADS ? INMS_THREADS : (K <= 2 * INMS_THREADS ? 2 * INMS_THREADS : 4 * INMS_THREADS);
-        for (int j = K + tid; j < P; j += INMS_THREADS) S.keys[j] = ~0ull;
-        __syncthreads();
-        if (P == INMS_THREADS) inms_sort_reg<1>(S.keys);
-        else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(S.keys);
-        else inms_sort_reg<4>(S.keys);
+        inms_sort_keys<Cfg>(S.keys, K);
     }
     INMS_STAMP(5);
 
     // ---- 6. emission ---------------------------------------------------------------------------------------------------
-    // thread t owns the 4 consecutive score positions 4t..4t+3, so ranks follow the score order
+    // thread t owns the PER consecutive score positions PER*t.., so ranks follow the score order
     int flags = 0, cnt = 0;
-    u64 mykeys[4];
+    u64 mykeys[PER];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = tid * 4 + q;
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid * PER + q;
         mykeys[q] = 0;
         if (i < K) {
             const u64 key = S.keys[i];
-            const int p = (int)(key & (INMS_CAP - 1));
+            const int p = (int)(key & (CAP - 1));
             if (S.state[p] == 1 && (k.n_tracked == 0 || inms_tracked(k, S.cls[p]))) {
                 mykeys[q] = key;
                 flags |= 1 << q;
@@ -522,9 +547,9 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         if (lane == 0) {
             ((volatile u64 *)k.chain)[b + 1] = CHAIN_AGG | (u64)total;
             k.emit_count[b] = total;
-            k.cand_count[b] = over ? (INMS_CAP + 1) : K;
+            k.cand_count[b] = K_all;
             k.out_counts[2 + b] = total;
-            k.out_counts[2 + k.B + b] = over ? (INMS_CAP + 1) : K;
+            k.out_counts[2 + k.B + b] = K_all;  // survivors of the score threshold, also when the image was left out
             if (over) atomicOr(&k.hdr->status, BG_STATUS_NEED_GENERAL);
         }
         long long base = 0;
@@ -553,13 +578,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     INMS_STAMP(6);
     const long long base = S.base;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < PER; ++q) {
         if (!((flags >> q) & 1)) continue;
         const u64 key = mykeys[q];
-        const int p = (int)(key & (INMS_CAP - 1));
-        const u32 id = (u32)((key & 0xffffffffull) >> INMS_PBITS);
+        const int p = (int)(key & (CAP - 1));
+        const u32 id = (u32)((key & 0xffffffffull) >> Cfg::PBITS);
         const float score = from_orderable(~(u32)(key >> 32));
-        const float4 bx = S.box[p];
+        const float4 bx = box_at(p);
         if (k.order == 0) {
             const long long dst = base + rank;
             float2 *o = reinterpret_cast<float2 *>(k.out_boxes + dst * 6);  // rows are 24 bytes: 8-byte aligned

@@ -22,10 +22,12 @@ _ws: Dict[Tuple[int, str], torch.Tensor] = {}
 _pinned: Dict[Tuple[int, str], torch.Tensor] = {}
 _mask_budget: Dict[Tuple[int, str], int] = {}
 DEFAULT_MASK_BYTES = 64 << 20
-# bg_detect NMS path remembered per (device, batch, candidates, thresholds): 0 = one CTA per image (default),
-# 1 = general segmented engine (images with many survivors), 3 = general for good (overlap-edge overflow)
+# bg_detect NMS path remembered per (device, batch, candidates, thresholds): absent = per-image kernel for up to
+# 4,096 survivors (default), 4 = per-image kernel for up to 8,192, 1 = general segmented engine (more survivors),
+# 3 = general for good (overlap-edge overflow)
 _nms_path_hint: Dict[Tuple, int] = {}
-PER_IMAGE_NMS_CAP = 4096  # INMS_CAP of csrc/imgnms_kernels.cuh
+PER_IMAGE_NMS_CAP = 4096        # InmsSmall::CAP of csrc/imgnms_kernels.cuh
+PER_IMAGE_NMS_CAP_LARGE = 8192  # InmsLarge::CAP
 
 
 def _stream() -> int:
@@ -174,8 +176,13 @@ class DetectPlan:
         self.params, self.B, self.dev = p, B, device
         self.N = sum(sh[1] * sh[2] * na for sh in shapes)
         self.hint_key = (device.index, B, self.N, p.iou_threshold, p.score_threshold)
-        p.nms_path = 1 if (nms_path == "general" or _nms_path_hint.get(self.hint_key, 0)) else \
-            {"per_image": 2, "per_image_single": 3}.get(nms_path, 0)
+        hint = _nms_path_hint.get(self.hint_key, 0)
+        if nms_path == "general":
+            p.nms_path = 1
+        elif nms_path in ("per_image", "per_image_single", "per_image_large"):
+            p.nms_path = {"per_image": 2, "per_image_single": 3, "per_image_large": 4}[nms_path]
+        else:
+            p.nms_path = {0: 0, 4: 4}.get(hint, 1)
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
         self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
@@ -207,14 +214,23 @@ class DetectPlan:
             if int(h[1]) & _lib.STATUS_NEED_GENERAL:
                 # an image exceeded what the one-CTA-per-image NMS holds: run again through the general engine
                 # and remember it (survivor overflow is re-evaluated from the counts, edge overflow is kept)
-                many = int(h[2 + B: 2 + 2 * B].max()) > PER_IMAGE_NMS_CAP
-                _nms_path_hint[self.hint_key] = 1 if many else 3
-                self.params.nms_path = 1
+                most = int(h[2 + B: 2 + 2 * B].max())
+                if most > PER_IMAGE_NMS_CAP and most <= PER_IMAGE_NMS_CAP_LARGE and self.params.nms_path != 4:
+                    nxt = 4       # the larger per-image kernel holds it
+                elif most > PER_IMAGE_NMS_CAP_LARGE:
+                    nxt = 1       # general engine while the images are this crowded
+                else:
+                    nxt = 3       # overlap-edge overflow: general engine for good
+                _nms_path_hint[self.hint_key] = nxt
+                self.params.nms_path = 4 if nxt == 4 else 1
                 self.enqueue(self.raws)
                 continue
-            if self.params.nms_path == 1 and _nms_path_hint.get(self.hint_key) == 1 \
-                    and int(h[2 + B: 2 + 2 * B].max()) <= PER_IMAGE_NMS_CAP // 2:
-                _nms_path_hint.pop(self.hint_key, None)  # sparse again: the next plan starts on the per-image path
+            if _nms_path_hint.get(self.hint_key) in (1, 4):   # crowded earlier; step back down when it is sparse again
+                most = int(h[2 + B: 2 + 2 * B].max())
+                if self.params.nms_path == 1 and most <= PER_IMAGE_NMS_CAP_LARGE // 2:
+                    _nms_path_hint[self.hint_key] = 4 if most > PER_IMAGE_NMS_CAP // 2 else 0
+                elif self.params.nms_path == 4 and most <= PER_IMAGE_NMS_CAP // 2:
+                    _nms_path_hint.pop(self.hint_key, None)
             if int(h[1]) & _lib.STATUS_MASK_SPACE:
                 # the per-image survivor counts are known now: size the bit matrix exactly and run again
                 cand = h[2 + B: 2 + 2 * B].to(torch.int64)
