@@ -416,6 +416,83 @@ def test_loss_config3_full_size_properties(ops):
     assert matched >= 0.8 * int(sc_full[:, 6].sum())
 
 
+# ------------------------------------------------------------------------------ drop-in glue on the GPU
+def test_dropin_glue_with_reference_shaped_classes(ops):
+    """The reference cannot travel to the GPU box, so the drop-in layer is exercised here on stand-ins that carry
+    exactly the attributes and call signatures the reference classes have (modules/detection_loss.py:40-122,
+    dataset/detection_dataset.py:90-107, modules/detection.py:98-104): install() must route their call sites to
+    the CUDA operators and uninstall() must restore them."""
+    import torchvision
+    from vision_conglomerate_b200 import dropin
+
+    class DetectionDataset:
+        @staticmethod
+        def build_target_by_scale(targets, fmap_shape, anchors, anchor_threshold=4.0, edge_threshold=0.5,
+                                  overlap_masks=None, batch_size=None):
+            raise AssertionError("reference implementation called")
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.num_classes, self.num_keypoints = 80, None
+            for k in synth.SCALES:
+                setattr(self, k + "_anchors", torch.nn.Parameter(synth.anchors_tensor(k).cuda()))
+
+    class DetectionLoss(torch.nn.Module):
+        def __init__(self, model, **kw):
+            super().__init__()
+            self.model = model
+            for k, v in kw.items():
+                setattr(self, k, v)
+            self.scale_w = kw.get("scale_w") or [4.0, 2.0, 1.0]
+
+        def forward(self, preds, targets):
+            raise AssertionError("reference implementation called")
+
+        def loss_fn(self, preds, targets, anchors):
+            raise AssertionError("reference implementation called")
+
+        @staticmethod
+        def compute_ciou(preds_xywh, targets_xywh, e=1e-7):
+            raise AssertionError("reference implementation called")
+
+    class DetectionNet(torch.nn.Module):
+        num_keypoints = None
+
+        def _get_scale_pred(self, scale_pred, anchors, input_shape, inference=False):
+            raise AssertionError("reference implementation called")
+
+    orig_nms = torchvision.ops.batched_nms
+    dropin.install(DetectionDataset, DetectionLoss, DetectionNet)
+    try:
+        B, H, W, C = 2, 128, 128, 80
+        t = synth.targets(B, 9, C, 0).cuda()
+        preds = [p.cuda().requires_grad_(True) for p in synth.train_preds(B, H, W, C, 1)]
+        anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+        loss_mod = DetectionLoss(Model(), **synth.LOSS_CONFIG)
+        loss, metrics = loss_mod(tuple(preds), t)
+        loss.backward()
+        ref_loss, ref_metrics = ops.detection_loss([p.detach() for p in preds], t, anc, synth.LOSS_CONFIG)
+        assert float(loss) == float(ref_loss) and set(metrics) == set(ref_metrics) and len(metrics) == 10
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in preds)
+        out = DetectionDataset.build_target_by_scale(t, (16, 16), anc[0].cuda())
+        exp = ops.build_target_by_scale(t, (16, 16), anc[0])
+        assert torch.equal(torch.stack(out[0]), torch.stack(exp[0])) and out[4] is None and out[5] is None
+        p4, t4 = torch.rand(64, 4).cuda() + 0.1, torch.rand(64, 4).cuda() + 0.1
+        assert torch.equal(DetectionLoss.compute_ciou(p4, t4), ops.compute_ciou(p4, t4))
+        x = synth.raw_head_outputs(1, 64, 64, C, "N", 3)[0].cuda()
+        dec = DetectionNet()._get_scale_pred(x, anc[0].cuda(), (64, 64), inference=True)
+        assert torch.equal(dec, ops.decode_scale(x, anc[0], (64, 64), True))
+        b, s, i = synth.nms_boxes(5000, 3, seed=5)
+        keep = torchvision.ops.batched_nms(b.cuda(), s.cuda(), i.cuda(), 0.5)
+        assert np.array_equal(keep.cpu().numpy(), canon(orig_nms(b, s, i, 0.5).numpy(), s.numpy()))
+        with pytest.raises(RuntimeError, match="CUDA"):
+            torchvision.ops.batched_nms(b, s, i, 0.5)
+    finally:
+        dropin.uninstall()
+    assert torchvision.ops.batched_nms is orig_nms
+
+
 # ------------------------------------------------------------------------------ anchor metrics (a13)
 def test_ratio_metrics(ops):
     g = golden("ratio")

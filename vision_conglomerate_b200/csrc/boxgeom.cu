@@ -47,15 +47,24 @@ struct Bump {  // workspace carving; with base == nullptr it only measures
     }
 };
 
+static int cur_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = 0; }
+    return (dev >= 0 && dev < 64) ? dev : 0;
+}
+
 static int num_sms()
 {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static int n[64] = {0};
+    const int dev = cur_device();
+    if (!n[dev]) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) {
+            (void)cudaGetLastError();
+            n[dev] = 148;
+        }
     }
-    return n;
+    return n[dev];
 }
 
 static void carve_seg(Bump &b, SegNms &p, long long S_max, long long elems, size_t mask_bytes)
@@ -348,8 +357,9 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     k.box_dense = w.box_dense; k.cls_dense = w.cls_dense;
 
     const int sms = num_sms();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // function attributes are per device
+    const int dev = cur_device();
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(decode_filter_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(decode_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(image_nms_kernel<InmsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsSmall>)) != cudaSuccess ||
@@ -357,7 +367,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
             (void)cudaGetLastError();
             return BG_ERR_LAUNCH;
         }
-        attr_set = true;
+        attr_set[dev] = true;
     }
 
     // ---- decode + score filter: variant 1 forces plain loads, variant 2 insists on the TMA pipeline ----
@@ -767,7 +777,8 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
     {
         const size_t smem = (size_t)BWD_WARPS * 32 * k.D * sizeof(float);
         if (smem > 200 * 1024) return BG_ERR_INVALID;  // rows longer than ~780 floats do not fit the chunk images
-        static size_t attr_smem = 0;
+        static size_t attr_smem_dev[64] = {0};
+        size_t &attr_smem = attr_smem_dev[cur_device()];
         if (smem > attr_smem) {
             if (cudaFuncSetAttribute(loss_bwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
                 (void)cudaGetLastError();

@@ -602,7 +602,10 @@ static inline void segnms_configure(SegNms &p)
 static int segnms_run(const SegNms &p, int S_launch, int32_t *out_counts, int counts_per_seg, int num_sms,
                       cudaStream_t st)
 {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};  // function attributes are per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); dev = 0; }
+    bool &attr_set = attr_set_dev[dev];
     if (!attr_set) {
         cudaFuncSetAttribute(seg_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segnms_sort_smem());
         cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segnms_reduce_smem());
