@@ -104,6 +104,16 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
               float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
               size_t workspace_bytes, size_t mask_bytes, void *stream);
 
+/* The same pipeline from the DECODED tensor the reference hands to its post-processing: inference_det.py
+ * post_process_preds lines 57-97 and :107-109 (score = max_c sigmoid(cls_c) * sigmoid(obj), box allowance, xyxy,
+ * per-image NMS, strict score threshold, row assembly, tracked-class filter) for preds [B, N, 5+C] f32 =
+ * DetectionNet.forward(x, inference=True) (modules/detection.py:69-91), rows [obj, cls*C, x, y, w, h] with the
+ * boxes already in pixels.  `p` as for bg_detect (ny/nx/na give the three scale segments of N; H, W, og_*, anchors
+ * are ignored); workspace size from bg_detect_workspace_bytes; outputs as bg_detect. */
+int bg_post_process(const float *preds, const bg_detect_params *p /*host*/, float *out_boxes, int64_t *out_img,
+                    int64_t *out_keep, int32_t *out_counts, void *workspace, size_t workspace_bytes, size_t mask_bytes,
+                    void *stream);
+
 /* Profiling hook for bench.py: when both are non-NULL, the next bg_detect call records `start`/`stop`
  * (cudaEvent_t) on its stream immediately around the decode+filter kernel, then clears the hook. */
 void bg_profile_events(void *start, void *stop);

@@ -121,6 +121,34 @@ def test_detect_golden(ops, name, variant):
     assert np.array_equal(got[:, 1], ref_rows[:, 1])
 
 
+@pytest.mark.parametrize("name", ["post_sq64", "post_sq64_lowthr", "post_T128_tracked", "post_T128"])
+def test_post_process_golden(ops, name):
+    """ops.post_process on the decoded [B, N, 85] tensor (what inference_det.post_process_preds receives) against
+    the rows the unmodified reference produced, and bitwise against the fused path from the raw head outputs."""
+    g = golden(name)
+    gd = golden(str(g["decode_case"]))
+    B, H, W, C, seed, og0, og1 = (int(v) for v in gd["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(gd["dist"]), seed)
+    og = None if og0 < 0 else (og0, og1)
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = torch.cat([ops.decode_scale(dev(r), a, (H, W), True, og).reshape(B, -1, C + 5) for r, a in zip(raws, anc)], 1).contiguous()
+    det = ops.post_process(preds, (H, W), C, float(g["iou"]), float(g["thr"]), allow, tracked, order="global")
+    counts = g["per_image_counts"]
+    ref_rows = rows_canon(g["per_image"], np.repeat(np.arange(len(counts)), counts))
+    got_img = np.unique(det.sample_idxs.cpu().numpy(), return_inverse=True)[1]
+    got = rows_canon(det.pred_boxes.cpu().numpy(), got_img)
+    assert_close(got, ref_rows, rtol=1e-5, atol=2e-5 * max(H, W), what="rows vs reference")
+    assert np.array_equal(got[:, 1], ref_rows[:, 1])
+    assert bool((det.pred_boxes[1:, 0] <= det.pred_boxes[:-1, 0]).all())      # the reference's global score order
+    fused = ops.detect([dev(r) for r in raws], anc, (H, W), C, og_size=og, iou_threshold=float(g["iou"]),
+                       score_threshold=float(g["thr"]), box_allowance=allow, tracked_classes=tracked, order="global")
+    assert torch.equal(fused.pred_boxes, det.pred_boxes) and torch.equal(fused.keep_idxs, det.keep_idxs)
+    with pytest.raises(RuntimeError):
+        ops.post_process(preds[:, :-1].contiguous(), (H, W), C)             # N does not match the input shape
+
+
 @pytest.mark.parametrize("nms_path", ["auto", "general", "per_image_single"])
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,W,C,dist,og,iou,thr,allow,tracked,order", [

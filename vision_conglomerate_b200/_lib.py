@@ -24,7 +24,7 @@ SYMBOLS = (
     "bg_strerror", "bg_version", "bg_launch_count", "bg_sizeof_detect_params", "bg_sizeof_loss_params", "bg_profile_events",
     "bg_profile_stamps", "bg_profile_stamps_per_image", "bg_profile_decode_cycles",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
-    "bg_detect_workspace_bytes", "bg_detect", "bg_decode_scale",
+    "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale",
     "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd",
@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
     L.bg_detect_workspace_bytes.argtypes = [C.POINTER(DetectParams), sz]
     L.bg_detect_workspace_bytes.restype = sz
     L.bg_detect.argtypes = [vp, vp, vp, C.POINTER(DetectParams), vp, vp, vp, vp, vp, sz, sz, vp]
+    L.bg_post_process.argtypes = [vp, C.POINTER(DetectParams), vp, vp, vp, vp, vp, sz, sz, vp]
     L.bg_decode_scale.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, i32, i32, i32, vp]
     L.bg_assign_workspace_bytes.argtypes = [i64, i32]
     L.bg_assign_workspace_bytes.restype = sz
@@ -121,7 +122,7 @@ def lib() -> C.CDLL:
     L.bg_loss_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(LossParams), vp, vp, vp, vp, sz, vp]
     L.bg_loss_bwd.argtypes = [vp, vp, vp, C.POINTER(LossParams), vp, f32, vp, vp, vp, vp, sz, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
-    for name in ("bg_batched_nms", "bg_detect", "bg_decode_scale", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
+    for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_ratio_metrics"):
         getattr(L, name).restype = C.c_int
     _lib = L

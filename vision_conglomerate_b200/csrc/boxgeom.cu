@@ -310,9 +310,12 @@ size_t bg_detect_workspace_bytes(const bg_detect_params *p, size_t mask_bytes)
     return det_carve(nullptr, p->B, det_candidates(p), tp.tpi_total, path == 1, p->order != 0, mask_bytes, w);
 }
 
-int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *pp,
-              float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
-              size_t workspace_bytes, size_t mask_bytes, void *stream)
+}  // extern "C"
+
+// shared body of bg_detect (three raw head tensors) and bg_post_process (one decoded [B,N,D] tensor)
+static int detect_impl(const float *raw_sm, const float *raw_md, const float *raw_lg, int predecoded, const bg_detect_params *pp,
+                       float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
+                       size_t workspace_bytes, size_t mask_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!det_valid(pp) || !raw_sm || !raw_md || !raw_lg || !out_boxes || !out_img || !out_keep || !out_counts || !workspace)
@@ -335,6 +338,7 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
         d.raw = raws[s];
         d.ny = pp->ny[s]; d.nx = pp->nx[s];
         d.cells_na = pp->ny[s] * pp->nx[s] * pp->na;
+        d.img_stride = predecoded ? N : d.cells_na;
         d.img_off = off;
         off += d.cells_na;
         d.rows = (long long)pp->B * d.cells_na;
@@ -347,8 +351,9 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
     }
     k.B = pp->B; k.C = pp->C; k.D = pp->C + 5; k.na = pp->na; k.N = (int)N;
     k.magic_na = (u32)(((1ull << 32) + (u64)pp->na - 1) / (u64)pp->na);
-    // guard of modules/detection.py:76: rescale only if BOTH dimensions differ
-    k.rescale = (pp->og_H > 0 && pp->og_W > 0 && pp->og_H != pp->H && pp->og_W != pp->W) ? 1 : 0;
+    k.predecoded = predecoded;
+    // guard of modules/detection.py:76: rescale only if BOTH dimensions differ (already applied to decoded rows)
+    k.rescale = (!predecoded && pp->og_H > 0 && pp->og_W > 0 && pp->og_H != pp->H && pp->og_W != pp->W) ? 1 : 0;
     k.fW = (float)pp->W; k.fH = (float)pp->H; k.fW0 = (float)pp->og_W; k.fH0 = (float)pp->og_H;
     k.use_allowance = pp->box_allowance != 0.0f;
     k.allowance = pp->box_allowance;
@@ -457,6 +462,26 @@ int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, con
                                                                    reinterpret_cast<long long *>(out_keep), out_counts);
     BG_LAUNCH_CHECK();
     return BG_OK;
+}
+
+extern "C" {
+
+int bg_detect(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *pp,
+              float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
+              size_t workspace_bytes, size_t mask_bytes, void *stream)
+{
+    return detect_impl(raw_sm, raw_md, raw_lg, 0, pp, out_boxes, out_img, out_keep, out_counts, workspace, workspace_bytes,
+                       mask_bytes, stream);
+}
+
+int bg_post_process(const float *preds, const bg_detect_params *pp, float *out_boxes, int64_t *out_img, int64_t *out_keep,
+                    int32_t *out_counts, void *workspace, size_t workspace_bytes, size_t mask_bytes, void *stream)
+{
+    if (!det_valid(pp) || !preds) return BG_ERR_INVALID;
+    const long long D = pp->C + 5;
+    const long long n0 = (long long)pp->ny[0] * pp->nx[0] * pp->na, n1 = (long long)pp->ny[1] * pp->nx[1] * pp->na;
+    return detect_impl(preds, preds + n0 * D, preds + (n0 + n1) * D, 1, pp, out_boxes, out_img, out_keep, out_counts, workspace,
+                       workspace_bytes, mask_bytes, stream);
 }
 
 int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,

@@ -13,6 +13,7 @@ struct ScaleDesc {
     const float *raw;
     int ny, nx;
     int cells_na;      // ny*nx*na  (candidates per image on this scale)
+    long long img_stride;  // rows between consecutive images: cells_na (own tensor per scale) or N (slices of [B,N,D])
     int img_off;       // flat index of this scale's first candidate inside an image
     long long rows;    // B*ny*nx*na
     u32 magic_nx;      // ceil(2^32 / nx): n / nx == umulhi(n, magic_nx) for the cell counts in range (n * nx < 2^32)
@@ -25,6 +26,7 @@ struct DetectK {
     ScaleDesc sc[3];
     int B, C, D, na, N;  // N = candidates per image over the three scales
     u32 magic_na;        // ceil(2^32 / na)
+    int predecoded;      // rows already hold decoded pixel xywh (DetectionNet.forward output): no sigmoid / grid / anchor step
     int rescale;         // apply _bbox_to_size (guard at detection.py:76 evaluated on the host)
     float fW, fH, fW0, fH0;
     int use_allowance;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
 
     auto tile_src = [&](int b, int r, int &si, int &lrow0, int &rows) -> const float * {
         tile_locate(k, tp, b, r, si, lrow0, rows);
-        return k.sc[si].raw + ((long long)b * k.sc[si].cells_na + lrow0) * D;
+        return k.sc[si].raw + ((long long)b * k.sc[si].img_stride + lrow0) * D;
     };
     // a CTA steps its tile number by gridDim.x: (image, tile in image) advance without divisions
     const int step_b = (int)gridDim.x / tp.tpi_total, step_r = (int)gridDim.x - step_b * tp.tpi_total;
@@ -337,9 +339,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
                 const int cell = (int)__umulhi((u32)rl, k.magic_na), a = rl - cell * k.na;      // rl / na, rl % na
                 const int gy = (int)__umulhi((u32)cell, s.magic_nx), gx = cell - gy * s.nx;     // cell / nx, cell % nx
                 const bool isx = (comp & 1) == 0;
-                const float sg2 = __fmul_rn(sigmoid_acc(sr[C + 1 + comp]), 2.0f);
+                const float tv = sr[C + 1 + comp];
+                const float sg2 = k.predecoded ? 0.f : __fmul_rn(sigmoid_acc(tv), 2.0f);
                 float val;
-                if (comp < 2) val = __fmul_rn(__fadd_rn(__fsub_rn(sg2, 0.5f), isx ? (float)gx : (float)gy), isx ? s.s0 : s.s1);
+                if (k.predecoded) val = tv;
+                else if (comp < 2) val = __fmul_rn(__fadd_rn(__fsub_rn(sg2, 0.5f), isx ? (float)gx : (float)gy), isx ? s.s0 : s.s1);
                 else val = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(sg2, sg2), isx ? s.aw[a] : s.ah[a]), isx ? s.fnx : s.fny), isx ? s.s0 : s.s1);
                 if (k.rescale) val = __fmul_rn(__fdiv_rn(val, isx ? k.fW : k.fH), isx ? k.fW0 : k.fH0);
                 if (comp >= 2 && k.use_allowance) val = __fadd_rn(val, k.allowance);

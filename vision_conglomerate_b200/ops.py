@@ -145,7 +145,8 @@ class DetectPlan:
                  num_classes: int, device: torch.device, og_size: Optional[Tuple[int, int]] = None,
                  iou_threshold: float = 0.5, score_threshold: float = 0.1, box_allowance: Optional[float] = None,
                  tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0,
-                 nms_path: str = "auto"):
+                 nms_path: str = "auto", predecoded: bool = False):
+        self.predecoded = bool(predecoded)
         if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
             raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
         B, _, _, na, D = shapes[0]
@@ -192,17 +193,29 @@ class DetectPlan:
         self.key = (device.index, "detect")
         self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
 
-    def enqueue(self, raws: Sequence[torch.Tensor]) -> None:
+    def enqueue(self, raws) -> None:
+        """``raws``: the three head tensors, or (``predecoded`` plans) the one decoded ``[B, N, 5+C]`` tensor."""
         L = _lib.lib()
         p = self.params
-        self.raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
-        if [tuple(r.shape) for r in self.raws] != self.shapes:
-            raise RuntimeError("detect: head output shapes differ from the plan")
+        if self.predecoded:
+            preds = _req(raws[0] if isinstance(raws, (list, tuple)) else raws, "preds")
+            if tuple(preds.shape) != (self.B, self.N, p.C + 5):
+                raise RuntimeError("post_process: preds shape differs from the plan")
+            self.raws = [preds]
+        else:
+            self.raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
+            if [tuple(r.shape) for r in self.raws] != self.shapes:
+                raise RuntimeError("detect: head output shapes differ from the plan")
         self.mask_bytes = _mask_budget.get(self.key, DEFAULT_MASK_BYTES)
         need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
         if need == 0:
             raise RuntimeError("detect: invalid parameters")
         ws = _workspace(self.dev, "detect", need)
+        if self.predecoded:
+            check(L.bg_post_process(self.raws[0].data_ptr(), C.byref(p), self.out_boxes.data_ptr(), self.out_img.data_ptr(),
+                                    self.out_keep.data_ptr(), self.counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                                    self.mask_bytes, _stream()), "bg_post_process")
+            return
         check(L.bg_detect(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(), C.byref(p),
                           self.out_boxes.data_ptr(), self.out_img.data_ptr(), self.out_keep.data_ptr(),
                           self.counts.data_ptr(), ws.data_ptr(), ws.numel(), self.mask_bytes, _stream()), "bg_detect")
@@ -256,6 +269,30 @@ def detect(raws: Sequence[torch.Tensor], anchors3: Sequence, input_shape: Tuple[
     plan = DetectPlan([tuple(r.shape) for r in raws], anchors3, input_shape, num_classes, raws[0].device, og_size,
                       iou_threshold, score_threshold, box_allowance, tracked_classes, order, variant, nms_path)
     plan.enqueue(raws)
+    return plan.result()
+
+
+def post_process(preds: torch.Tensor, input_shape: Tuple[int, int], num_classes: int, iou_threshold: float = 0.5,
+                 score_threshold: float = 0.1, box_allowance: Optional[float] = None,
+                 tracked_classes: Optional[Sequence[int]] = None, order: str = "global", na: int = 3,
+                 strides: Sequence[int] = (8, 16, 32), nms_path: str = "auto") -> Detections:
+    """The compute of ``inference_det.post_process_preds`` (lines 57-97 and 107-109) on the tensor the reference
+    hands it: ``preds [B, N, 5+C] = DetectionNet.forward(x, inference=True)`` with rows ``[obj, cls*C, x, y, w, h]``
+    (logits + decoded pixel boxes).  Scores, box allowance, xyxy, per-image NMS, strict score threshold, rows
+    ``(score, class, x1, y1, x2, y2)`` and the tracked-class filter in one pass; ``order='global'`` is the
+    reference's row order (score-descending over the batch)."""
+    preds = _req(preds, "preds")
+    if preds.dim() != 3 or preds.shape[2] != num_classes + 5:
+        raise RuntimeError("post_process: expected preds [B, N, 5 + num_classes] (keypoint / mask columns are out of scope)")
+    B, N, D = preds.shape
+    H, W = int(input_shape[0]), int(input_shape[1])
+    shapes = [(B, H // s, W // s, na, D) for s in strides]
+    if sum(sh[1] * sh[2] * na for sh in shapes) != N:
+        raise RuntimeError("post_process: N does not match input_shape / strides / na")
+    anchors3 = [[[1.0, 1.0]] * na] * 3  # unused: the boxes are already decoded
+    plan = DetectPlan(shapes, anchors3, (H, W), num_classes, preds.device, None, iou_threshold, score_threshold,
+                      box_allowance, tracked_classes, order, 0, nms_path, predecoded=True)
+    plan.enqueue(preds)
     return plan.result()
 
 
