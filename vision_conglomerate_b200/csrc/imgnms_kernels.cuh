@@ -1,14 +1,17 @@
-// Per-image greedy NMS in one CTA (the NMS stage of the fused detect path).
+// Per-image greedy NMS (the NMS stage of the fused detect path).
 //
-// One CTA of 1024 threads owns one image and keeps everything in shared memory.  Survivors are numbered
-// p = 0..K-1 in candidate order (the order of the decode kernel's tile slots):
+// A CTA of 1024 threads owns one image and keeps its working set in shared memory; while the GPU has room every
+// image gets a second, helper CTA that takes a share of the pair tests (step 3) and the sort (step 5) and hands
+// its results over through global memory.  Survivors are numbered p = 0..K-1 in candidate order (the order of
+// the decode kernel's tile slots):
 //   1. load keys, boxes and classes from the tile slots (coalesced; prefix over the tile counts);
 //   2. bucket the box centres on a uniform grid (counting sort), bounds from a block reduction;
 //   3. pair tests.  IoU > t needs |dcx| < (1-t)/t * w and |dcy| < (1-t)/t * h for EITHER box of the pair
 //      (DESIGN.md has the derivation), so a box only meets the boxes of the grid cells inside that reach.
 //      The work is cut into (box, grid row) items spread evenly over the threads -- a tall box has hundreds
-//      of cells in reach, a small one a handful.  The lower-numbered box of a pair owns the test; the exact
-//      fp32 IoU decision is iou_suppresses() of the segmented engine.  A hit becomes an edge from the box
+//      of cells in reach, a small one a handful.  A pair is tested once (by the box whose cell comes first; inside
+//      a cell by the lower-numbered box), after a cheap reject on bf16 extents; the exact fp32 IoU decision is
+//      iou_suppresses() of the segmented engine.  A hit becomes an edge from the box
 //      that comes first in score order to the other one;
 //   4. greedy resolution by rounds over the edge list: a box is suppressed once a kept earlier neighbour is
 //      known, kept once all its earlier neighbours are known to be suppressed -- the fixed point is exactly
@@ -16,8 +19,8 @@
 //   5. bitonic sort of the keys (score desc, candidate index asc -- torchvision's stable order);
 //   6. class filter, ranks, output offset by decoupled look-back over the images, rows.
 // Overlap edges beyond the shared-memory list spill to a per-image list in global memory (L2 resident).  Images
-// with more than INMS_CAP survivors, or more edges than the spill list holds, are left to the general segmented
-// engine: the kernel raises BG_STATUS_NEED_GENERAL and the caller re-enqueues in general mode.
+// with more survivors than the kernel variant holds (4,096 / 8,192), or more edges than the spill list, are left to
+// the general segmented engine: the kernel raises BG_STATUS_NEED_GENERAL and the caller re-enqueues accordingly.
 #pragma once
 #include "detect_kernels.cuh"
 

@@ -299,7 +299,7 @@ __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go,
 //   forward : loss_match_kernel  pass A, one thread per match   : gather, CIoU and its gradient, link the match
 //                                                                  into its cell's list (atomicExch on the head)
 //                                pass B, eight lanes per match  : class BCE, argmax, confusion counters
-//             loss_dense_kernel  one thread per cell            : objectness BCE against the winner's CIoU;
+//             loss_dense_kernel  one thread per cell            : objectness BCE against the CIoU of the cell's last match;
 //                                                                  keeps sigmoid(x) - t for the backward
 //             loss_finalize_kernel                              : fixed-order reduction, scalars, total loss
 //   backward: loss_bwd_stream_kernel  zeros + the objectness column, one 16-byte store per four elements
