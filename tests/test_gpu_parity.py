@@ -45,6 +45,23 @@ def test_nms_oracle(ops, n, groups, thr, ties):
     assert np.array_equal(keep, ref)
 
 
+@pytest.mark.parametrize("n,groups,thr", [(7000, 1, 0.5), (9000, 3, 0.3), (5000, 2, 0.04), (5000, 2, 0.0)])
+def test_nms_crowded_and_tiny_thresholds(ops, n, groups, thr):
+    """Heavily overlapping clusters overflow the overlap-edge list (the dense bit-matrix fallback takes over inside
+    the same call); thresholds below 0.05 / at 0 use the dense path from the start.  Degenerate boxes included."""
+    g = np.random.default_rng(n)
+    c = g.uniform(100, 140, size=(n, 2)).astype(np.float32)           # all centres inside a 40 px window
+    wh = g.uniform(30, 60, size=(n, 2)).astype(np.float32)
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    b[::97, 2] = b[::97, 0]                                            # zero width
+    b[5::211, 3] = b[5::211, 1] - 1.0                                  # negative height
+    s = g.uniform(0, 1, size=n).astype(np.float32)
+    i = g.integers(0, groups, size=n).astype(np.int64)
+    ref = O.batched_nms(b, s, i, thr)
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), thr).cpu().numpy()
+    assert np.array_equal(keep, ref)
+
+
 def test_nms_empty_and_props(ops):
     e = ops.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), 0.5)
     assert e.numel() == 0 and e.dtype == torch.int64

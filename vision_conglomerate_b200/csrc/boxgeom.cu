@@ -83,6 +83,13 @@ static void carve_seg(Bump &b, SegNms &p, long long S_max, long long elems, size
     p.bkeys = b.take<u64>(elems);
     p.bbox = b.take<float4>(elems);
     p.barea = b.take<float>(elems);
+    p.bwh = b.take<u32>(elems);
+    p.edge_off = b.take<long long>(S_max + 1);
+    p.cell_off = b.take<long long>(S_max + 1);
+    p.cell_start = b.take<int>(elems / 2 + 2 * S_max + 2);  // sum of G*G + 1 with G*G <= max(1, count / 2)
+    p.grid = b.take<SegGrid>(S_max);
+    p.edge_count = b.take<unsigned long long>(S_max);
+    p.gstate = b.take<unsigned char>(2 * elems);
     p.keepbits = b.take<u64>(elems / 64 + S_max + 1);
     p.ew32 = b.take<u32>(2 * (elems / 64 + S_max + 1));
     p.rank32 = b.take<u32>(2 * (elems / 64 + S_max + 1));
@@ -293,8 +300,17 @@ int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs,
     const int S_launch = (int)(max_groups < n ? max_groups : n);
     int rc = segnms_run(p, S_launch, out_counts, 0, sms, st);
     if (rc != BG_OK) return rc;
+    // global order: gather the per-segment lists, merge them pairwise level by level (ping-pong between two key
+    // arrays the engine no longer needs), write the candidate indices
     const int go = S_launch < 1 ? 1 : (S_launch > 4096 ? 4096 : S_launch);
-    gnms_output_kernel<<<dim3(S_launch > 256 ? 1 : 8, go), 256, 0, st>>>(p, reinterpret_cast<long long *>(out_keep));
+    u64 *ping = p.bkeys, *pong = p.keys;
+    gnms_gather_kernel<<<dim3(S_launch > 256 ? 1 : 8, go), 256, 0, st>>>(p, ping);
+    BG_LAUNCH_CHECK();
+    for (int L = 0; (1ll << L) < S_launch; ++L) {
+        gnms_merge_level_kernel<<<gs, 256, 0, st>>>(p, (L & 1) ? pong : ping, (L & 1) ? ping : pong, L);
+        BG_LAUNCH_CHECK();
+    }
+    gnms_output_kernel<<<gs, 256, 0, st>>>(p, ping, pong, reinterpret_cast<long long *>(out_keep));
     BG_LAUNCH_CHECK();
     return BG_OK;
 }

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(1024) detect_compact_kernel(SegNms p, DetectK 
     if (blockIdx.x == 0 && tid == 0) {
         SegHdr h;
         h.S = k.B; h.status = 0; h.item_ctr = 0; h.reduce_done = 0; h.gmin = 0; h.gmax = 0; h.total_out = 0;
-        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        h.item_ctr2 = 0; h.overflow = 0; h.dense_fits = 0; h.pad0 = 0; h.pad[0] = 0;
         *p.hdr = h;
         out_counts[0] = 0;
         out_counts[1] = 0;

@@ -1,16 +1,19 @@
-// Segmented greedy NMS: per-segment bitonic sort -> suppression bit matrix -> ordered reduce.
+// Segmented greedy NMS.  Two modes share the per-segment score sort and the emission:
+//
+//  * grid mode (0.05 <= thr < 1): IoU > t bounds the centre distance of a pair by (1-t)/t times the smaller
+//    extent per axis (DESIGN.md has the derivation), so every segment gets a uniform grid over its box centres,
+//    boxes are put in cell order by a counting sort and nms_grid_pairs_kernel tests a box only against the cells
+//    in its reach (forward half of the neighbourhood, bf16 extent prefilter).  Overlapping pairs go to an edge
+//    list (earlier score position -> later one) and nms_resolve_kernel settles the greedy outcome by rounds:
+//    a box whose earlier overlapping neighbours are all decided is kept iff none of them is kept -- the same
+//    fixed point as the sequential scan.  Work and memory are O(edges), so segments of any size stay cheap.
+//  * dense mode (any other threshold): nms_mask_kernel fills a K x K suppression bit matrix in 64x64 tiles and
+//    nms_reduce_kernel scans it in score order.
 //
 // Semantics follow torchvision's CPU nms kernel (the arithmetic behind the reference's
 // torchvision.ops.batched_nms call, inference_det.py:77-82): candidates in stable descending score
 // order, box j is suppressed by a kept box i iff  (double)(inter / (area_i + area_j - inter)) > thr
 // with every operation rounded to fp32 individually (no FMA contraction).
-//
-// The bit matrix is filled by one of two kernels:
-//  * nms_pairs_kernel (thr > 0): IoU > t requires width AND height ratios above t, so boxes are
-//    bucketed by (log2 w, log2 h) in bins one threshold-ratio wide and every box is only tested
-//    against the 3x3 neighbouring bins (three contiguous ranges of the bin-sorted order).  Bits are
-//    OR-ed into a zeroed matrix.  For trained-like detections this visits ~15 % of the pairs.
-//  * nms_mask_kernel (any threshold): dense 64x64 tiles, every word written exactly once.
 #pragma once
 #include "nms.cuh"
 
@@ -40,16 +43,22 @@ __device__ __forceinline__ bool iou_suppresses(const float4 a, const float aa, c
     return __fdiv_rn(inter, uni) > t.tdn;
 }
 
-// size bin of a box: (log2 h bin) * nb + (log2 w bin); degenerate boxes (w <= 0, h <= 0, NaN) can neither
-// suppress nor be suppressed under a non-negative threshold and get the sentinel bin.
-__device__ __forceinline__ u32 size_bin(const SegNms &p, const float4 b)
+// boxes without a positive finite extent have IoU 0 or NaN with everything: they never suppress nor get suppressed
+__device__ __forceinline__ bool seg_box_valid(const float4 bx, float &w, float &h, float &cx, float &cy)
 {
-    const float w = __fsub_rn(b.z, b.x), h = __fsub_rn(b.w, b.y);
-    if (!(w > 0.0f && h > 0.0f)) return 0xffffffffu;
-    const float top = (float)(p.nb - 1);
-    const int bw = (int)fminf(fmaxf(floorf((log2f(w) + 16.0f) * p.inv_delta), 0.0f), top);
-    const int bh = (int)fminf(fmaxf(floorf((log2f(h) + 16.0f) * p.inv_delta), 0.0f), top);
-    return (u32)(bh * p.nb + bw);
+    w = __fsub_rn(bx.z, bx.x); h = __fsub_rn(bx.w, bx.y);
+    cx = 0.5f * bx.x + 0.5f * bx.z; cy = 0.5f * bx.y + 0.5f * bx.w;
+    return (w > 0.0f) && (h > 0.0f) && (w < INFINITY) && (h < INFINITY) && (fabsf(cx) < INFINITY) && (fabsf(cy) < INFINITY);
+}
+// cell of a centre coordinate: monotone in the coordinate, so a conservative interval maps to a conservative cell range
+__device__ __forceinline__ int seg_cell_x(const SegGrid &g, float x) { return (int)fminf(fmaxf(floorf(__fmul_rn(__fsub_rn(x, g.mnx), g.invx)), 0.0f), (float)(g.G - 1)); }
+__device__ __forceinline__ int seg_cell_y(const SegGrid &g, float y) { return (int)fminf(fmaxf(floorf(__fmul_rn(__fsub_rn(y, g.mny), g.invy)), 0.0f), (float)(g.G - 1)); }
+constexpr int SEG_GMAX = 2048;
+__host__ __device__ __forceinline__ int seg_grid_dim(long long K)  // about two boxes per cell
+{
+    int G = 1;
+    while (G < SEG_GMAX && 2ll * (G + 1) * (G + 1) <= K) ++G;
+    return G;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -94,30 +103,54 @@ constexpr int PAIR_THREADS = 128;
 __global__ void __launch_bounds__(1024) seg_tables_kernel(SegNms p)
 {
     __shared__ ScanPair s_scan[33];
+    __shared__ long long s_total;
     const int S = p.hdr->S;
     ScanPair carry{0, 0};
-    long long icarry = 0;
+    ScanPair icarry{0, 0};
+    long long kcarry = 0;
     for (int base = 0; base < S; base += 1024) {
         const int sg = base + threadIdx.x;
         const long long K = (sg < S) ? p.seg_count[sg] : 0;
         const long long T = (K + 63) >> 6;
+        long long cells = 0;
+        if (sg < S) { const long long G = seg_grid_dim(K); cells = G * G + 1; }
         ScanPair tot, tot2;
         const ScanPair ex = block_excl_scan_1024(ScanPair{T, K * T}, s_scan, tot);
-        const ScanPair ex2 = block_excl_scan_1024(ScanPair{(K + PAIR_THREADS - 1) / PAIR_THREADS, 0}, s_scan, tot2);
+        const ScanPair ex2 = block_excl_scan_1024(ScanPair{(K + PAIR_THREADS - 1) / PAIR_THREADS, cells}, s_scan, tot2);
+        ScanPair tot3;
+        const ScanPair ex3 = block_excl_scan_1024(ScanPair{K, 0}, s_scan, tot3);
         if (sg < S) {
             p.tile_prefix[sg] = (int)(carry.a + ex.a);
             p.mask_off[sg] = carry.b + ex.b;
-            p.item_prefix[sg] = (int)(icarry + ex2.a);
+            p.item_prefix[sg] = (int)(icarry.a + ex2.a);
+            p.cell_off[sg] = icarry.b + ex2.b;
+            p.edge_off[sg] = kcarry + ex3.a;  // candidate prefix, scaled to edge regions below
+            p.edge_count[sg] = 0ull;
         }
         carry.a += tot.a;
         carry.b += tot.b;
-        icarry += tot2.a;
+        icarry.a += tot2.a;
+        icarry.b += tot2.b;
+        kcarry += tot3.a;
     }
     if (threadIdx.x == 0) {
         p.tile_prefix[S] = (int)carry.a;
         p.mask_off[S] = carry.b;
-        p.item_prefix[S] = (int)icarry;
-        if (carry.b > p.mask_words) atomicOr(&p.hdr->status, BG_STATUS_MASK_SPACE);
+        p.item_prefix[S] = (int)icarry.a;
+        p.cell_off[S] = icarry.b;
+        p.edge_off[S] = kcarry;
+        s_total = kcarry;
+        p.hdr->dense_fits = carry.b <= p.mask_words;
+        if (!p.sparse && carry.b > p.mask_words) atomicOr(&p.hdr->status, BG_STATUS_MASK_SPACE);
+    }
+    if (!p.sparse) return;
+    __syncthreads();
+    // grid mode: every segment gets a share of the edge list proportional to its candidate count (the double
+    // product is monotone in the prefix, so the regions are disjoint)
+    const double scale = s_total > 0 ? (double)p.mask_words / (double)s_total : 0.0;
+    for (int sg = threadIdx.x; sg <= S; sg += 1024) {
+        long long o = (long long)((double)p.edge_off[sg] * scale);
+        p.edge_off[sg] = o > p.mask_words ? p.mask_words : o;
     }
 }
 
@@ -195,8 +228,11 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) seg_sort_kernel(SegNms p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s = reinterpret_cast<u64 *>(smem_raw);
+    __shared__ float s_red[4][32];
+    __shared__ int s_wsum[33];
     const int S = p.hdr->S;
     const bool bad = (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) != 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     for (int seg = blockIdx.x; seg < S; seg += gridDim.x) {
         const int K = p.seg_count[seg];
@@ -206,60 +242,116 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) seg_sort_kernel(SegNms p)
         block_sort_u64(keys, K, s);
         // gather boxes into score order; area rounded exactly like the CPU kernel: (x2-x1)*(y2-y1)
         const long long bbase = (long long)seg * p.box_seg_stride;
+        float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
         for (int i = threadIdx.x; i < K; i += SORT_THREADS) {
             const float4 b = p.boxes[bbase + key_id(keys[i])];
             p.sorted_box[off + i] = b;
             p.sorted_area[off + i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-            if (p.sparse) p.bkeys[off + i] = ((u64)size_bin(p, b) << 32) | (u32)i;
+            float w, h, cx, cy;
+            if (p.sparse && seg_box_valid(b, w, h, cx, cy)) { mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy); }
+        }
+        if (!p.sparse) { __syncthreads(); continue; }
+
+        // ---- grid mode: uniform grid over the valid centres, counting sort into cell order ----
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (lane == 0) { s_red[0][wid] = mnx; s_red[1][wid] = mxx; s_red[2][wid] = mny; s_red[3][wid] = mxy; }
+        __syncthreads();
+        mnx = s_red[0][lane]; mxx = s_red[1][lane]; mny = s_red[2][lane]; mxy = s_red[3][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        SegGrid gr;
+        gr.G = seg_grid_dim(K);
+        gr.mnx = mnx; gr.mny = mny;
+        gr.invx = (mxx > mnx) ? (float)gr.G / (mxx - mnx) : 0.0f;
+        gr.invy = (mxy > mny) ? (float)gr.G / (mxy - mny) : 0.0f;
+        gr.pad = 1e-6f * fmaxf(fmaxf(fabsf(mnx), fabsf(mxx)), fmaxf(fabsf(mny), fabsf(mxy)));  // fp32 rounding of the centres
+        gr.nvalid = 0; gr.pad2 = 0;
+        const int G = gr.G, ncell = G * G;
+        int *cs = p.cell_start + p.cell_off[seg];
+        u64 *tmp = p.emit_key + off;  // (cell << 32 | rank inside the cell); free until the emission
+        for (int c = threadIdx.x; c <= ncell; c += SORT_THREADS) cs[c] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += SORT_THREADS) {
+            float w, h, cx, cy;
+            u64 t = ~0ull;
+            if (seg_box_valid(p.sorted_box[off + i], w, h, cx, cy)) {
+                const u32 cell = (u32)(seg_cell_y(gr, cy) * G + seg_cell_x(gr, cx));
+                t = ((u64)cell << 32) | (u32)atomicAdd(&cs[cell], 1);
+            }
+            tmp[i] = t;
         }
         __syncthreads();
-        if (p.sparse) {
-            u64 *bk = p.bkeys + off;
-            block_sort_u64(bk, K, s);
-            for (int q = threadIdx.x; q < K; q += SORT_THREADS) {
-                const u32 pos = (u32)bk[q];
-                p.bbox[off + q] = p.sorted_box[off + pos];
-                p.barea[off + q] = p.sorted_area[off + pos];
+        int carry = 0;  // exclusive scan of the cell counts, 4 consecutive cells per thread and pass
+        for (int base = 0; base < ncell; base += 4 * SORT_THREADS) {
+            const int c0 = base + threadIdx.x * 4;
+            int v[4], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { v[q] = (c0 + q < ncell) ? cs[c0 + q] : 0; sum += v[q]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            if (wid == 0) {
+                const int x = s_wsum[lane];
+                int xi = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += u; }
+                s_wsum[lane] = xi - x;
+                if (lane == 31) s_wsum[32] = xi;
             }
-            // the pair kernel ORs bits into the matrix: clear this segment's words
-            const long long words = (long long)K * ((K + 63) >> 6);
-            ulonglong2 *m2 = reinterpret_cast<ulonglong2 *>(p.mask + p.mask_off[seg]);
-            if ((p.mask_off[seg] & 1) == 0) {
-                for (long long w = threadIdx.x; w < (words >> 1); w += SORT_THREADS) m2[w] = make_ulonglong2(0ull, 0ull);
-                if ((words & 1) && threadIdx.x == 0) p.mask[p.mask_off[seg] + words - 1] = 0ull;
-            } else {
-                u64 *m = p.mask + p.mask_off[seg];
-                for (long long w = threadIdx.x; w < words; w += SORT_THREADS) m[w] = 0ull;
-            }
+            __syncthreads();
+            int ex = carry + s_wsum[wid] + inc - sum;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { if (c0 + q < ncell) cs[c0 + q] = ex; ex += v[q]; }
+            carry += s_wsum[32];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            cs[ncell] = carry;
+            gr.nvalid = carry;
+            p.grid[seg] = gr;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += SORT_THREADS) {
+            const u64 t = tmp[i];
+            if (t == ~0ull) continue;
+            const u32 cell = (u32)(t >> 32);
+            const long long q = off + cs[cell] + (int)(u32)t;
+            const float4 bx = p.sorted_box[off + i];
+            p.bkeys[q] = ((u64)cell << 32) | (u32)i;
+            p.bbox[q] = bx;
+            p.barea[q] = p.sorted_area[off + i];
+            // extents rounded toward zero to bf16: stored <= true < stored * (1 + 2^-7)
+            p.bwh[q] = (__float_as_uint(__fsub_rn(bx.z, bx.x)) >> 16) | (__float_as_uint(__fsub_rn(bx.w, bx.y)) & 0xffff0000u);
         }
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel P: bin-pruned pair tests.  Work item = 128 consecutive boxes of one segment in bin order.
+// kernel P (grid mode): spatially pruned pair tests.  Work item = 128 consecutive boxes of one segment in cell
+// order.  A pair in different cells is tested by the box whose cell comes first in row-major order, a pair inside
+// one cell by the box that is earlier in cell order (each box of an overlapping pair lies in the other's reach).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int bin_lower_bound(const u64 *bk, int K, u32 bin)  // first q with bin(q) >= bin
-{
-    int lo = 0, hi = K;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if ((u32)(bk[mid] >> 32) < bin) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-__global__ void __launch_bounds__(PAIR_THREADS) nms_pairs_kernel(SegNms p)
+__global__ void __launch_bounds__(PAIR_THREADS) nms_grid_pairs_kernel(SegNms p)
 {
     __shared__ int s_item;
     if (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) return;
     const int S = p.hdr->S;
     const int total = p.item_prefix[S];
     const IouThr thr = p.thr;
-    const int nb = p.nb;
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(&p.hdr->item_ctr, 1u);
+        // (once some edge list is full the dense fallback redoes everything: stop early)
+        if (threadIdx.x == 0) s_item = ((volatile SegHdr *)p.hdr)->overflow ? total : (int)atomicAdd(&p.hdr->item_ctr, 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
@@ -269,28 +361,44 @@ __global__ void __launch_bounds__(PAIR_THREADS) nms_pairs_kernel(SegNms p)
             if (p.item_prefix[mid] <= item) lo = mid; else hi = mid;
         }
         const int seg = lo;
-        const int K = p.seg_count[seg];
+        const SegGrid gr = p.grid[seg];
+        const int q = (item - p.item_prefix[seg]) * PAIR_THREADS + threadIdx.x;
+        if (q >= gr.nvalid) continue;
         const long long off = p.seg_off[seg];
         const u64 *bk = p.bkeys + off;
-        const int q = (item - p.item_prefix[seg]) * PAIR_THREADS + threadIdx.x;
-        if (q >= K) continue;
+        const u32 *wh = p.bwh + off;
+        const int *cs = p.cell_start + p.cell_off[seg];
+        const int G = gr.G;
         const u64 key = bk[q];
-        const u32 bin = (u32)(key >> 32), pos = (u32)key;
-        if (bin == 0xffffffffu) continue;
-        const float4 rb = p.bbox[off + q];
-        const float ra = p.barea[off + q];
-        u64 *mrow = p.mask + p.mask_off[seg] + pos;
-        const int bh = (int)bin / nb, bw = (int)bin % nb;
-        for (int dh = -1; dh <= 1; ++dh) {
-            const int bh2 = bh + dh;
-            if (bh2 < 0 || bh2 >= nb) continue;
-            const u32 klo = (u32)(bh2 * nb + max(bw - 1, 0)), khi = (u32)(bh2 * nb + min(bw + 1, nb - 1));
-            const int a = bin_lower_bound(bk, K, klo), b = bin_lower_bound(bk, K, khi + 1);
-            for (int q2 = a; q2 < b; ++q2) {
+        const u32 cell = (u32)(key >> 32), pos = (u32)key;
+        const float4 a = p.bbox[off + q];
+        const float aa = p.barea[off + q];
+        const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
+        const float cx = 0.5f * a.x + 0.5f * a.z, cy = 0.5f * a.y + 0.5f * a.w;
+        const float rx = p.reach * w + gr.pad, ry = p.reach * h + gr.pad;
+        const int ay = (int)cell / G, ax = (int)cell - ay * G;
+        const int y1 = seg_cell_y(gr, cy + ry), xl = seg_cell_x(gr, cx - rx), x1 = seg_cell_x(gr, cx + rx);
+        // IoU > t needs both extent ratios above t: conservative reject on the bf16 extents (1 % slack for the fp32
+        // rounding of the exact test, 2^-7 for the truncation) before the partner's box is touched
+        const float wlo = 0.99f * thr.tdn * w, hlo = 0.99f * thr.tdn * h, tsc = 0.99f * thr.tdn;
+        u64 *edges = p.mask + p.edge_off[seg];
+        const unsigned long long ecap = (unsigned long long)(p.edge_off[seg + 1] - p.edge_off[seg]);
+        for (int gy = ay; gy <= y1; ++gy) {
+            const bool own_row = gy == ay;
+            const int x0 = own_row ? ax : xl;
+            int qa = cs[gy * G + x0];
+            const int qb = cs[gy * G + x1 + 1];
+            if (own_row) qa = max(qa, q + 1);  // own cell: only the boxes after this one in cell order
+            for (int q2 = qa; q2 < qb; ++q2) {
+                const u32 v = wh[q2];
+                const float wt = __uint_as_float(v << 16), ht = __uint_as_float(v & 0xffff0000u);
+                if (wt * 1.008f < wlo || ht * 1.008f < hlo || tsc * wt > w || tsc * ht > h) continue;
+                if (!iou_suppresses(a, aa, p.bbox[off + q2], p.barea[off + q2], thr)) continue;
                 const u32 pos2 = (u32)bk[q2];
-                if (pos2 <= pos) continue;  // the earlier box of a pair owns the test
-                if (iou_suppresses(rb, ra, p.bbox[off + q2], p.barea[off + q2], thr))
-                    atomicOr(mrow + (long long)(pos2 >> 6) * K, 1ull << (pos2 & 63));
+                const u64 ed = pos < pos2 ? (((u64)pos << 32) | pos2) : (((u64)pos2 << 32) | pos);
+                const unsigned long long e = atomicAdd(&p.edge_count[seg], 1ull);
+                if (e < ecap) edges[e] = ed;
+                else if (e == ecap) atomicOr(&p.hdr->overflow, 1);
             }
         }
     }
@@ -308,13 +416,18 @@ __global__ void __launch_bounds__(MASK_THREADS) nms_mask_kernel(SegNms p)
     __shared__ float carea[4][64];
     __shared__ int s_item;
     if (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) return;
+    if (p.sparse) {  // launched behind the grid pair kernel: only needed when an edge list overflowed
+        if (!p.hdr->overflow) return;
+        if (!p.hdr->dense_fits) return;  // (nms_reduce_kernel reports BG_STATUS_MASK_SPACE)
+    }
+    unsigned *ctr = p.sparse ? &p.hdr->item_ctr2 : &p.hdr->item_ctr;
     const int S = p.hdr->S;
     const int total = p.tile_prefix[S];
     const int sub = threadIdx.x >> 6, rl = threadIdx.x & 63;
     const IouThr thr = p.thr;
     while (true) {
         __syncthreads();
-        if (threadIdx.x == 0) s_item = (int)atomicAdd(&p.hdr->item_ctr, 1u);
+        if (threadIdx.x == 0) s_item = (int)atomicAdd(ctr, 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
@@ -369,6 +482,106 @@ __device__ __forceinline__ bool class_tracked(const SegNms &p, int c)
     return false;
 }
 
+// emission of one segment from its kept bitmap `kb` (score order): class filter, ranks, compact lists
+template <int NT>
+__device__ __forceinline__ void segnms_emit_segment(const SegNms &p, int seg, int K, long long off, const u64 *kb,
+                                                    long long *s_scan /*[NT/32]*/, int32_t *out_counts, int counts_per_seg)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int G = (K + 31) >> 5;  // 32-bit words
+    u32 *ew = p.ew32 + 2 * (long long)p.tile_prefix[seg];
+    u32 *rk = p.rank32 + 2 * (long long)p.tile_prefix[seg];
+    const long long cbase = (long long)seg * p.box_seg_stride;
+    long long carry = 0;
+    for (int base = 0; base < G; base += NT) {
+        const int g = base + threadIdx.x;
+        u32 bits = 0;
+        if (g < G) {
+            bits = (u32)(kb[g >> 1] >> ((g & 1) * 32));
+            if (p.n_tracked > 0) {
+                u32 rest = bits;
+                while (rest) {
+                    const int bit = __ffs(rest) - 1;
+                    rest &= rest - 1;
+                    if (!class_tracked(p, p.cls[cbase + key_id(p.keys[off + g * 32 + bit])])) bits &= ~(1u << bit);
+                }
+            }
+            ew[g] = bits;
+        }
+        long long inc = __popc(bits);
+        const long long v = inc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        long long woff = 0, tot = 0;
+        for (int q = 0; q < NT / 32; ++q) {
+            const long long x = s_scan[q];
+            if (q < wid) woff += x;
+            tot += x;
+        }
+        if (g < G) rk[g] = (u32)(carry + woff + inc - v);
+        carry += tot;
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < K; i += NT) {
+        const u32 bits = ew[i >> 5];
+        if ((bits >> (i & 31)) & 1u) {
+            const u32 r = rk[i >> 5] + __popc(bits & ((1u << (i & 31)) - 1u));
+            p.emit_pos[off + r] = (u32)i;
+            p.emit_key[off + r] = p.keys[off + i];
+        }
+    }
+    if (threadIdx.x == 0) {
+        p.emit_count[seg] = (int)carry;
+        if (counts_per_seg) out_counts[2 + seg] = (int)carry;
+    }
+    __syncthreads();
+}
+
+// last CTA of the kernel: exclusive prefix of the emitted rows -> output offsets, total, status
+template <int NT>
+__device__ __forceinline__ void segnms_finish(const SegNms &p, int S, long long *s_scan, unsigned *s_ticket, int32_t *out_counts)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __threadfence();
+    if (threadIdx.x == 0) *s_ticket = atomicAdd(&p.hdr->reduce_done, 1u);
+    __syncthreads();
+    if (*s_ticket != gridDim.x - 1) return;
+    __threadfence();
+    long long carry = 0;
+    for (int base = 0; base < S; base += NT) {
+        const int sg = base + threadIdx.x;
+        const long long v = (sg < S) ? (long long)((volatile int *)p.emit_count)[sg] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) s_scan[wid] = inc;
+        __syncthreads();
+        long long woff = 0, tot = 0;
+        for (int q = 0; q < NT / 32; ++q) {
+            const long long x = s_scan[q];
+            if (q < wid) woff += x;
+            tot += x;
+        }
+        if (sg < S) p.out_prefix[sg] = carry + woff + inc - v;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        p.out_prefix[S] = carry;
+        p.hdr->total_out = carry;
+        out_counts[0] = (int)carry;
+        out_counts[1] = p.hdr->status;
+    }
+}
+
 __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(SegNms p, int32_t *out_counts, int counts_per_seg)
 {
     extern __shared__ __align__(16) unsigned char red_smem[];
@@ -379,7 +592,9 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(SegNms p, in
     __shared__ long long s_scan[REDUCE_THREADS / 32];
     __shared__ unsigned s_ticket;
     const int S = p.hdr->S;
-    const bool bad = (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) != 0;
+    if (p.sparse && !p.hdr->overflow) return;  // grid mode went through: nms_resolve_kernel has done everything
+    if (p.sparse && !p.hdr->dense_fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&p.hdr->status, BG_STATUS_MASK_SPACE);
+    const bool bad = (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) != 0 || (p.sparse && !p.hdr->dense_fits);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
     for (int seg = blockIdx.x; seg < S; seg += gridDim.x) {
@@ -461,95 +676,73 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(SegNms p, in
             __syncthreads();
         }
 
-        // ---- emission: rows that are kept and (optionally) of a tracked class, compacted in score order ----
-        const int G = (K + 31) >> 5;  // 32-bit words
-        u32 *ew = p.ew32 + 2 * (long long)p.tile_prefix[seg];
-        u32 *rk = p.rank32 + 2 * (long long)p.tile_prefix[seg];
-        const long long cbase = (long long)seg * p.box_seg_stride;
-        long long carry = 0;
-        for (int base = 0; base < G; base += REDUCE_THREADS) {
-            const int g = base + threadIdx.x;
-            u32 bits = 0;
-            if (g < G) {
-                bits = (u32)(kb[g >> 1] >> ((g & 1) * 32));
-                if (p.n_tracked > 0) {
-                    u32 rest = bits;
-                    while (rest) {
-                        const int bit = __ffs(rest) - 1;
-                        rest &= rest - 1;
-                        if (!class_tracked(p, p.cls[cbase + key_id(p.keys[off + g * 32 + bit])])) bits &= ~(1u << bit);
-                    }
-                }
-                ew[g] = bits;
-            }
-            long long inc = __popc(bits);
-            const long long v = inc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += u;
-            }
-            if (lane == 31) s_scan[wid] = inc;
-            __syncthreads();
-            long long woff = 0, tot = 0;
-            for (int q = 0; q < REDUCE_THREADS / 32; ++q) {
-                const long long x = s_scan[q];
-                if (q < wid) woff += x;
-                tot += x;
-            }
-            if (g < G) rk[g] = (u32)(carry + woff + inc - v);
-            carry += tot;
-            __syncthreads();
-        }
-        for (int i = threadIdx.x; i < K; i += REDUCE_THREADS) {
-            const u32 bits = ew[i >> 5];
-            if ((bits >> (i & 31)) & 1u) {
-                const u32 r = rk[i >> 5] + __popc(bits & ((1u << (i & 31)) - 1u));
-                p.emit_pos[off + r] = (u32)i;
-                p.emit_key[off + r] = p.keys[off + i];
-            }
-        }
-        if (threadIdx.x == 0) {
-            p.emit_count[seg] = (int)carry;
-            if (counts_per_seg) out_counts[2 + seg] = (int)carry;
-        }
-        __syncthreads();
+        segnms_emit_segment<REDUCE_THREADS>(p, seg, K, off, kb, s_scan, out_counts, counts_per_seg);
     }
+    segnms_finish<REDUCE_THREADS>(p, S, s_scan, &s_ticket, out_counts);
+}
 
-    // last CTA: exclusive prefix of the emitted rows -> output offsets, total, status
-    __threadfence();
-    if (threadIdx.x == 0) s_ticket = atomicAdd(&p.hdr->reduce_done, 1u);
-    __syncthreads();
-    if (s_ticket != gridDim.x - 1) return;
-    __threadfence();
-    long long carry = 0;
-    for (int base = 0; base < S; base += REDUCE_THREADS) {
-        const int sg = base + threadIdx.x;
-        const long long v = (sg < S) ? (long long)((volatile int *)p.emit_count)[sg] : 0;
-        long long inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const long long u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        if (lane == 31) s_scan[wid] = inc;
+// ------------------------------------------------------------------------------------------------
+// kernel G (grid mode): greedy outcome from the edge list, one CTA per segment.  state: 0 undecided, 1 kept,
+// 2 suppressed.  Per round every edge (i -> j, i earlier) of an undecided j either suppresses j (i kept) or blocks
+// it (i undecided); undecided boxes that were not blocked are kept.  The earliest undecided box is never blocked,
+// so every round decides at least one box, and a box is decided only from decided predecessors: the result is
+// the sequential greedy scan's.  Then the same emission as the dense path.
+// ------------------------------------------------------------------------------------------------
+constexpr int RESOLVE_THREADS = 512;
+constexpr int RESOLVE_SMEM_BOXES = 32768;  // segments up to this size keep their state in shared memory (2 x 32 KB)
+
+__global__ void __launch_bounds__(RESOLVE_THREADS) nms_resolve_kernel(SegNms p, int32_t *out_counts, int counts_per_seg)
+{
+    extern __shared__ __align__(16) unsigned char res_smem[];
+    __shared__ long long s_scan[RESOLVE_THREADS / 32];
+    __shared__ unsigned s_ticket;
+    if (p.hdr->overflow) return;  // the dense fallback (nms_mask_kernel + nms_reduce_kernel) takes over
+    const int S = p.hdr->S;
+    const bool bad = (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) != 0;
+    const int lane = threadIdx.x & 31;
+
+    for (int seg = blockIdx.x; seg < S; seg += gridDim.x) {
+        const int K = bad ? 0 : p.seg_count[seg];
+        const long long off = p.seg_off[seg];
+        u64 *kb = p.keepbits + p.tile_prefix[seg];
+        unsigned char *state = (K <= RESOLVE_SMEM_BOXES) ? res_smem : p.gstate + 2 * off;
+        unsigned char *blocked = state + ((K <= RESOLVE_SMEM_BOXES) ? RESOLVE_SMEM_BOXES : K);
+        const u64 *edges = p.mask + p.edge_off[seg];
+        const long long ne = bad ? 0 : (long long)p.edge_count[seg];
+        for (int i = threadIdx.x; i < K; i += RESOLVE_THREADS) { state[i] = 0; blocked[i] = 0; }
         __syncthreads();
-        long long woff = 0, tot = 0;
-        for (int q = 0; q < REDUCE_THREADS / 32; ++q) {
-            const long long x = s_scan[q];
-            if (q < wid) woff += x;
-            tot += x;
+        while (ne > 0) {
+            for (long long e = threadIdx.x; e < ne; e += RESOLVE_THREADS) {
+                const u64 ed = __ldcg(edges + e);
+                const u32 i = (u32)(ed >> 32), j = (u32)ed;
+                if (state[j] == 0) {
+                    const unsigned char si = state[i];
+                    if (si == 1) state[j] = 2;
+                    else if (si == 0) blocked[j] = 1;
+                }
+            }
+            __syncthreads();
+            int pending = 0;
+            for (int j = threadIdx.x; j < K; j += RESOLVE_THREADS) {
+                if (state[j] == 0) {
+                    if (blocked[j]) { blocked[j] = 0; pending = 1; }
+                    else state[j] = 1;
+                }
+            }
+            if (!__syncthreads_or(pending)) break;
         }
-        if (sg < S) p.out_prefix[sg] = carry + woff + inc - v;
-        carry += tot;
+        // kept bitmap in score order (boxes without edges are still in state 0: kept)
+        const int T = (K + 63) >> 6;
+        for (int c = threadIdx.x >> 5; c < T; c += RESOLVE_THREADS / 32) {  // one 64-box word per warp and pass
+            const int i0 = 64 * c + lane, i1 = i0 + 32;
+            const u32 lo = __ballot_sync(0xffffffffu, i0 < K && state[i0] != 2);
+            const u32 hi = __ballot_sync(0xffffffffu, i1 < K && state[i1] != 2);
+            if (lane == 0) kb[c] = ((u64)hi << 32) | lo;
+        }
         __syncthreads();
+        segnms_emit_segment<RESOLVE_THREADS>(p, seg, K, off, kb, s_scan, out_counts, counts_per_seg);
     }
-    if (threadIdx.x == 0) {
-        p.out_prefix[S] = carry;
-        p.hdr->total_out = carry;
-        out_counts[0] = (int)carry;
-        out_counts[1] = p.hdr->status;
-    }
+    segnms_finish<RESOLVE_THREADS>(p, S, s_scan, &s_ticket, out_counts);
 }
 
 // rank of an emitted row in the global (score desc, flat index asc) order across all segments:
@@ -580,25 +773,17 @@ __device__ __forceinline__ long long segnms_global_rank(const SegNms &p, int S, 
 
 static inline size_t segnms_sort_smem() { return (size_t)SORT_CHUNK * sizeof(u64); }
 static inline size_t segnms_reduce_smem() { return (size_t)2 * REDUCE_SMEM_ROWS * sizeof(u64); }
+static inline size_t segnms_resolve_smem() { return (size_t)2 * RESOLVE_SMEM_BOXES; }
 
-// bin geometry for the pair kernel: bins one threshold-ratio wide (plus a safety margin for the fp32
-// log2 and the few-ulp slack of the rounded IoU), at most 64 per axis over log2 size in [-16, 16)
+// grid mode needs a positive threshold: the reach bound is (1-t)/t extents, useless for tiny t
 static inline void segnms_configure(SegNms &p)
 {
-    p.sparse = (p.thr.fast_ok && !p.thr.zero_suppresses && p.thr.tdn < 1.0f) ? 1 : 0;
-    p.nb = 1;
-    p.inv_delta = 0.0f;
-    if (p.sparse) {
-        double delta = log2(1.0 / (double)p.thr.tdn) * 1.0005 + 2e-4;
-        if (delta < 32.0 / 63.0) delta = 32.0 / 63.0;
-        int nb = (int)ceil(32.0 / delta) + 1;
-        if (nb > 64) nb = 64;
-        p.nb = nb;
-        p.inv_delta = (float)(1.0 / delta);
-    }
+    p.sparse = (p.thr.fast_ok && !p.thr.zero_suppresses && p.thr.tdn >= 0.05f && p.thr.tdn < 1.0f) ? 1 : 0;
+    p.reach = p.sparse ? (1.0f - p.thr.tdn) / p.thr.tdn * 1.01f + 0.01f : 0.0f;
 }
 
-// Enqueue tables -> sort -> pairs|mask -> reduce.  `S_launch` is a host-side upper bound of the segment count.
+// Enqueue tables -> sort -> [grid pairs] -> mask -> [resolve] -> reduce.  In grid mode the mask and reduce kernels
+// return at once unless an edge list overflowed.  `S_launch` is a host-side upper bound of the segment count.
 static int segnms_run(const SegNms &p, int S_launch, int32_t *out_counts, int counts_per_seg, int num_sms,
                       cudaStream_t st)
 {
@@ -609,6 +794,7 @@ static int segnms_run(const SegNms &p, int S_launch, int32_t *out_counts, int co
     if (!attr_set) {
         cudaFuncSetAttribute(seg_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segnms_sort_smem());
         cudaFuncSetAttribute(nms_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segnms_reduce_smem());
+        cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)segnms_resolve_smem());
         attr_set = true;
     }
     seg_tables_kernel<<<1, 1024, 0, st>>>(p);
@@ -617,11 +803,18 @@ static int segnms_run(const SegNms &p, int S_launch, int32_t *out_counts, int co
     if (g > num_sms * 2) g = num_sms * 2;
     seg_sort_kernel<<<g, SORT_THREADS, segnms_sort_smem(), st>>>(p);
     BG_LAUNCH_CHECK();
-    if (p.sparse) nms_pairs_kernel<<<num_sms * 8, PAIR_THREADS, 0, st>>>(p);
-    else nms_mask_kernel<<<num_sms * 8, MASK_THREADS, 0, st>>>(p);
+    if (p.sparse) {
+        nms_grid_pairs_kernel<<<num_sms * 8, PAIR_THREADS, 0, st>>>(p);
+        BG_LAUNCH_CHECK();
+    }
+    nms_mask_kernel<<<num_sms * 8, MASK_THREADS, 0, st>>>(p);
     BG_LAUNCH_CHECK();
     int gr = S_launch < 1 ? 1 : S_launch;
     if (gr > num_sms * 3) gr = num_sms * 3;
+    if (p.sparse) {
+        nms_resolve_kernel<<<gr, RESOLVE_THREADS, segnms_resolve_smem(), st>>>(p, out_counts, counts_per_seg);
+        BG_LAUNCH_CHECK();
+    }
     nms_reduce_kernel<<<gr, REDUCE_THREADS, segnms_reduce_smem(), st>>>(p, out_counts, counts_per_seg);
     BG_LAUNCH_CHECK();
     return BG_OK;
@@ -637,7 +830,7 @@ __global__ void gnms_init_kernel(SegNms p, long long max_groups)
         SegHdr h;
         h.S = 0; h.status = 0; h.item_ctr = 0; h.reduce_done = 0;
         h.gmin = 0x7fffffffffffffffLL; h.gmax = -0x7fffffffffffffffLL - 1; h.total_out = 0;
-        h.pad[0] = h.pad[1] = h.pad[2] = 0;
+        h.item_ctr2 = 0; h.overflow = 0; h.dense_fits = 0; h.pad0 = 0; h.pad[0] = 0;
         *p.hdr = h;
     }
     for (long long k = i; k < max_groups; k += (long long)gridDim.x * blockDim.x) p.seg_count[k] = 0;
@@ -672,8 +865,18 @@ __global__ void gnms_count_kernel(SegNms p, const long long *idxs, long long n, 
         else p.hdr->S = (int)(gmax - gmin + 1);
     }
     if (bad) return;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        slot[i] = (u32)atomicAdd(&p.seg_count[idxs[i] - gmin], 1);
+    // one atomic per distinct group and warp (group ids usually come in long runs)
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += (long long)gridDim.x * blockDim.x) {
+        const bool active = i < n;
+        const long long g = active ? idxs[i] - gmin : -1 - lane;
+        const u32 peers = __match_any_sync(0xffffffffu, g);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (active && lane == leader) base = atomicAdd(&p.seg_count[g], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (active) slot[i] = (u32)(base + __popc(peers & ((1u << lane) - 1u)));
+    }
 }
 
 __global__ void __launch_bounds__(1024) gnms_offsets_kernel(SegNms p)
@@ -701,17 +904,76 @@ __global__ void gnms_scatter_kernel(SegNms p, const long long *idxs, const float
         p.keys[p.seg_off[idxs[i] - gmin] + slot[i]] = make_key(scores[i], (u32)i);
 }
 
-__global__ void gnms_output_kernel(SegNms p, long long *out_keep)
+// Global (score desc, index asc) order of the kept candidates: the per-segment lists are sorted already, so a merge
+// tree over adjacent runs finishes in ceil(log2 S) passes.  Level L merges the runs of 2^L segments pairwise; an
+// element's place is its index in its own run plus the number of smaller keys in the sibling run (keys are unique:
+// they carry the candidate index).  Lanes of a warp that sit in the same run share the search: the first and last
+// of them search the whole sibling run, the others only between those two results.
+__global__ void gnms_gather_kernel(SegNms p, u64 *dst)
 {
     const int S = p.hdr->S;
     for (int seg = blockIdx.y; seg < S; seg += gridDim.y) {
         const int cnt = p.emit_count[seg];
-        const long long off = p.seg_off[seg];
-        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt; r += gridDim.x * blockDim.x) {
-            const u64 key = p.emit_key[off + r];
-            out_keep[segnms_global_rank(p, S, seg, r, key)] = (long long)key_id(key);
+        const u64 *src = p.emit_key + p.seg_off[seg];
+        u64 *d = dst + p.out_prefix[seg];
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < cnt; r += gridDim.x * blockDim.x) d[r] = src[r];
+    }
+}
+
+__device__ __forceinline__ long long key_lower_bound(const u64 *a, long long lo, long long hi, u64 key)
+{
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) gnms_merge_level_kernel(SegNms p, const u64 *src, u64 *dst, int L)
+{
+    const int S = p.hdr->S;
+    if ((1ll << L) >= S) return;  // a single run already
+    const long long total = p.out_prefix[S];
+    const int lane = threadIdx.x & 31;
+    auto bnd = [&](long long run) -> long long { const long long sg = run << L; return p.out_prefix[sg < S ? sg : S]; };
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g - lane < total; g += (long long)gridDim.x * blockDim.x) {
+        const bool active = g < total;
+        long long run = -1 - lane;
+        u64 key = 0;
+        if (active) {
+            int lo = 0, hi = S;  // largest segment with out_prefix[seg] <= g (the non-empty one that holds g)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (p.out_prefix[mid] <= g) lo = mid; else hi = mid;
+            }
+            run = lo >> L;
+            key = src[g];
+        }
+        const u32 peers = __match_any_sync(0xffffffffu, run);
+        const int first = __ffs(peers) - 1, last = 31 - __clz(peers);
+        long long a0 = 0, b0 = 0, b1 = 0, m0 = 0, lb = 0;
+        const bool edge = lane == first || lane == last;
+        if (active) {
+            a0 = bnd(run); b0 = bnd(run ^ 1); b1 = bnd((run ^ 1) + 1); m0 = bnd(run & ~1ll);
+            if (edge) lb = key_lower_bound(src, b0, b1, key);
+        }
+        const long long lbf = __shfl_sync(0xffffffffu, lb, first), lbl = __shfl_sync(0xffffffffu, lb, last);
+        if (active) {
+            if (!edge) lb = key_lower_bound(src, lbf, lbl, key);
+            dst[m0 + (g - a0) + (lb - b0)] = key;
         }
     }
+}
+
+__global__ void gnms_output_kernel(SegNms p, const u64 *ping, const u64 *pong, long long *out_keep)
+{
+    const int S = p.hdr->S;
+    int levels = 0;
+    while ((1ll << levels) < S) ++levels;
+    const u64 *src = (levels & 1) ? pong : ping;
+    const long long total = p.out_prefix[S];
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (long long)gridDim.x * blockDim.x)
+        out_keep[r] = (long long)key_id(src[r]);
 }
 
 }  // namespace bg

@@ -245,12 +245,13 @@ class DetectPlan:
                 elif self.params.nms_path == 4 and most <= PER_IMAGE_NMS_CAP // 2:
                     _nms_path_hint.pop(self.hint_key, None)
             if int(h[1]) & _lib.STATUS_MASK_SPACE:
-                # the per-image survivor counts are known now: size the bit matrix exactly and run again
+                # neither the overlap-edge list nor the dense bit matrix fitted.  The per-image survivor counts are
+                # known now: grow the scratch fourfold (room for more edges) up to the exact matrix size, run again
                 cand = h[2 + B: 2 + 2 * B].to(torch.int64)
                 exact = int((cand * ((cand + 63) // 64)).sum()) * 8
                 if exact <= self.mask_bytes:
                     raise RuntimeError("detect: suppression-mask workspace exhausted")
-                _mask_budget[self.key] = exact + (exact >> 3)
+                _mask_budget[self.key] = min(exact + (exact >> 3), self.mask_bytes * 4)
                 self.enqueue(self.raws)
                 continue
             k = int(h[0])
