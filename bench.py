@@ -151,7 +151,9 @@ def _config():
                         "conf %.3f, IoU %.2f, box_allowance %d, trained-like logits (dist T, ~1,700 survivors/img)"
                         % (w["B"], w["H"], w["W"], w["C"], w["score"], w["iou"], w["allow"]),
             "per_gpu_batch": w["B"], "parallelism": "image-sharded replicas, no data-path collective",
-            "l2": "inputs (548 MB per step) exceed the 126 MB L2; no explicit flush"}
+            "l2": "inputs (548 MB per step) exceed the 126 MB L2; no explicit flush",
+            "pipelining": "consecutive batches in flight on separate CUDA streams (ops.DetectPipeline, --depth); "
+                          "every step is a full decode+NMS of its batch into its own output buffers"}
 
 
 def run_ours(args):
@@ -181,12 +183,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up (also settles the workspace / mask budget)
+    # the headline runs consecutive batches through ops.DetectPipeline: `depth` batches in flight on as many CUDA
+    # streams (own scratch and outputs each), so one batch's NMS tail overlaps the next batch's HBM-bound decode
+    depth = max(1, args.depth)
+    pipe = ops.DetectPipeline([tuple(r.shape) for r in raws_d], anc, (H, W), C, devc, None, w["iou"], w["score"],
+                              w["allow"], None, "image", args.variant, depth=depth)
+
+    # warm-up (also settles the workspace / mask budget), every slot of the pipeline and the single-stream plan
     for _ in range(max(args.warmup, 3)):
         plan.enqueue(raws_d)
         det = plan.result()
+        for _d in range(depth):
+            pipe.submit(raws_d)
+        for d in range(depth):
+            det_p = pipe.result(d)
+    pipe.join()
     kept_rows = int(det.pred_boxes.shape[0])
     survivors = float(det.candidates.float().mean())
+    if int(det_p.pred_boxes.shape[0]) != kept_rows or not torch.equal(det_p.pred_boxes, det.pred_boxes):
+        raise RuntimeError("pipelined and single-stream results differ")
 
     # ---- value: device-resident inputs, K steps back to back, CUDA events -----------------------
     K = args.steps
@@ -200,10 +215,19 @@ def run_ours(args):
     with ClockSampler(local) as clk:
         e0.record()
         for i in range(K):
-            plan.enqueue(raws_d)
+            pipe.submit(raws_d)
+        pipe.join()
         e1.record()
         launches = _lib.launch_count() - launches0  # kernels of ours enqueued inside the timed region
         barrier()
+        # the same K steps on one stream, one batch at a time: the latency view of a step
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for i in range(K):
+            plan.enqueue(raws_d)
+        l1.record()
+        barrier()
+        single_ms = l0.elapsed_time(l1) / K
         # second pass, untimed as a whole: the same K steps with CUDA events recorded immediately around the
         # decode+filter kernel on its stream (the roofline numerator's duration)
         for i in range(K):
@@ -247,26 +271,41 @@ def run_ours(args):
     L.bg_profile_events(None, None)
 
     # ---- e2e: pinned host inputs -> H2D -> kernels -> D2H of the result rows, every step ---------
-    stage = [torch.empty_like(r) for r in raws_d]
-    for _ in range(2):
-        for s, h in zip(stage, raws_h):
-            s.copy_(h, non_blocking=True)
-        plan.enqueue(stage)
-        plan.result().pred_boxes.cpu()
+    # through the same pipeline: the copy of a batch runs on its slot's stream, so it overlaps the kernels and the
+    # result read of the batches before it (the PCIe link is the bound: 548 MB per step)
+    stages = [[torch.empty_like(r) for r in raws_d] for _ in range(depth)]
+    d2h_box = [0]
+
+    def e2e_fetch(slot):
+        r = pipe.result(slot)
+        with torch.cuda.stream(pipe.streams[slot]):
+            rows = r.pred_boxes.cpu()
+        d2h_box[0] = rows.numel() * 4 + pipe.plans[slot].counts.numel() * 4
+
+    def e2e_steps(n):
+        for k in range(n):
+            slot = pipe.submitted % pipe.depth
+            if k >= depth:
+                e2e_fetch(slot)          # the batch that used this slot `depth` steps ago
+            st = pipe.streams[slot]
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                for sbuf, h in zip(stages[slot], raws_h):
+                    sbuf.copy_(h, non_blocking=True)
+            pipe.submit(stages[slot])
+        for k in range(max(0, n - depth), n):
+            e2e_fetch((pipe.submitted - n + k) % pipe.depth)
+        pipe.join()
+
+    e2e_steps(max(2, depth))
     barrier()
-    d2h = 0
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(K):
-        for s, h in zip(stage, raws_h):
-            s.copy_(h, non_blocking=True)
-        plan.enqueue(stage)
-        r = plan.result()
-        rows = r.pred_boxes.cpu()
-        d2h = rows.numel() * 4 + plan.counts.numel() * 4
+    e2e_steps(K)
     t1.record()
     barrier()
+    d2h = d2h_box[0]
     te = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=devc)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -293,7 +332,8 @@ def run_ours(args):
                      "traffic": _ncu_traffic(), "peak_source": peak_src, "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "whole_step_frac": (alg_bytes / (ms_max / K * 1e-3) / 1e9) / peak},
-        "detail": {"kept_rows_per_step": kept_rows, "survivors_per_image": survivors,
+        "detail": {"batches_in_flight": depth, "single_batch_latency_us": single_ms * 1e3,
+                   "kept_rows_per_step": kept_rows, "survivors_per_image": survivors,
                    "launches_per_step": launches_per_step, "image_nms_kernel_stages_us": nms_stages},
     }
     if world == 1 and not args.no_cpu:
@@ -372,6 +412,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="decode kernel: 0 auto, 1 plain loads, 2 TMA bulk")
+    ap.add_argument("--depth", type=int, default=4, help="batches in flight (CUDA streams) in the headline loop; 1 = one stream")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extra", action="store_true", help="(default at N=1) also measure the training side and the stress case")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")

@@ -90,6 +90,9 @@ typedef struct {
     int32_t nms_path;           /* 0 auto (per-image CTAs, up to 4,096 score survivors per image), 1 general segmented engine,
                                  * 2 = 0 but an error instead of the general engine when the threshold rules it out,
                                  * 3 = 2 with one CTA per image (no helper CTA), 4 per-image CTAs for up to 8,192 survivors */
+    int32_t throughput;         /* 0: tuned for the latency of one batch (helper CTA per image while the GPU has room, the NMS
+                                 * kernel launched programmatically behind the decode kernel); 1: tuned for several batches in
+                                 * flight on different streams (one NMS CTA per image, plain stream-ordered launches) */
 } bg_detect_params;
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);

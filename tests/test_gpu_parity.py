@@ -244,6 +244,36 @@ def test_detect_paths_agree_exactly(ops):
                 assert torch.equal(x, y), (iou, path)
 
 
+@pytest.mark.parametrize("depth", [1, 3])
+def test_detect_pipeline_matches_single_stream(ops, depth):
+    """ops.DetectPipeline (batches in flight on several streams, own scratch each) returns, batch by batch,
+    exactly the rows of a single-stream plan -- also when a slot is reused and when inputs differ per batch."""
+    B, H, W, C = 8, 640, 640, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    batches = [[dev(r) for r in synth.raw_head_outputs(B, H, W, C, "T", seed=20 + i)] for i in range(5)]
+    shapes = [tuple(r.shape) for r in batches[0]]
+    ref = []
+    for raws in batches:
+        d = ops.detect(raws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, tracked_classes=[0, 3, 17])
+        ref.append([t.clone() for t in (d.pred_boxes, d.sample_idxs, d.keep_idxs, d.counts)])
+    pipe = ops.DetectPipeline(shapes, anc, (H, W), C, torch.device("cuda", 0), None, 0.65, 0.001, 4, [0, 3, 17], depth=depth)
+    slots = {}
+    for i, raws in enumerate(batches):
+        slot = pipe.submitted % pipe.depth
+        if slot in slots:                       # take the earlier batch's rows before its slot is reused
+            j = slots.pop(slot)
+            got = pipe.result(slot)
+            for x, y in zip(ref[j], (got.pred_boxes, got.sample_idxs, got.keep_idxs, got.counts)):
+                assert torch.equal(x, y), (depth, j)
+        assert pipe.submit(raws) == slot
+        slots[slot] = i
+    for slot, j in slots.items():
+        got = pipe.result(slot)
+        for x, y in zip(ref[j], (got.pred_boxes, got.sample_idxs, got.keep_idxs, got.counts)):
+            assert torch.equal(x, y), (depth, j)
+    pipe.join()
+
+
 def test_detect_config2_full_size(ops):
     """BASELINE config 2 (B=64, 640^2, conf 0.001, IoU 0.65, dist T): oracle parity on 4 images, and
     size-independent properties on the whole batch."""

@@ -429,7 +429,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         q.stamps = g_prof_stamps;
         {   // two CTAs per image (helper + main) while every CTA of the grid can be resident at once
             static const int split_env = []() { const char *e = getenv("BG_NMS_SPLIT"); return e ? atoi(e) : -1; }();
-            q.split = pp->nms_path == 3 ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
+            q.split = (pp->nms_path == 3 || pp->throughput) ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
         }
         q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted; q.gspill = w.gspill; q.gcap = DET_SPILL_EDGES;
         q.gboxp = w.gboxp;
@@ -443,7 +443,8 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
-            cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+            // (throughput mode: CTAs resident early would hold SMs the other streams' decode kernels can use)
+            cfg.attrs = at; cfg.numAttrs = (pdl && !pp->throughput) ? 1 : 0;
             const cudaError_t le = large ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLarge>, q) : cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsSmall>, q);
             if (le != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
             ++g_launches;

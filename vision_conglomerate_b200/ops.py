@@ -139,13 +139,15 @@ class Detections:
 class DetectPlan:
     """Parameters, output buffers and workspace of one fused decode+NMS configuration, reusable across
     batches of the same shape.  ``enqueue`` launches the kernels on the current stream without any host
-    synchronisation; ``result`` performs the single device->host read the reference signature forces."""
+    synchronisation; ``result`` performs the single device->host read the reference signature forces.
+    ``throughput=True`` tunes the launches for several batches in flight (see :class:`DetectPipeline`): one NMS CTA
+    per image instead of main + helper, no programmatic dependent launch."""
 
     def __init__(self, shapes: Sequence[Tuple[int, ...]], anchors3: Sequence, input_shape: Tuple[int, int],
                  num_classes: int, device: torch.device, og_size: Optional[Tuple[int, int]] = None,
                  iou_threshold: float = 0.5, score_threshold: float = 0.1, box_allowance: Optional[float] = None,
                  tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0,
-                 nms_path: str = "auto", predecoded: bool = False):
+                 nms_path: str = "auto", predecoded: bool = False, throughput: bool = False):
         self.predecoded = bool(predecoded)
         if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
             raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
@@ -184,6 +186,7 @@ class DetectPlan:
             p.nms_path = {"per_image": 2, "per_image_single": 3, "per_image_large": 4}[nms_path]
         else:
             p.nms_path = {0: 0, 4: 4}.get(hint, 1)
+        p.throughput = 1 if throughput else 0
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
         self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
@@ -191,6 +194,7 @@ class DetectPlan:
         self.out_keep = torch.empty(n, dtype=torch.int64, device=device)
         self.counts = torch.empty(2 + 2 * B, dtype=torch.int32, device=device)
         self.key = (device.index, "detect")
+        self.ws_tag = "detect"   # plans that run concurrently on different streams need distinct scratch: set a distinct tag
         self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
 
     def enqueue(self, raws) -> None:
@@ -210,7 +214,7 @@ class DetectPlan:
         need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
         if need == 0:
             raise RuntimeError("detect: invalid parameters")
-        ws = _workspace(self.dev, "detect", need)
+        ws = _workspace(self.dev, self.ws_tag, need)
         if self.predecoded:
             check(L.bg_post_process(self.raws[0].data_ptr(), C.byref(p), self.out_boxes.data_ptr(), self.out_img.data_ptr(),
                                     self.out_keep.data_ptr(), self.counts.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -257,6 +261,50 @@ class DetectPlan:
             k = int(h[0])
             return Detections(self.out_boxes[:k], self.out_img[:k], self.out_keep[:k], h[2: 2 + B].clone(),
                               h[2 + B: 2 + 2 * B].clone())
+
+
+class DetectPipeline:
+    """Consecutive batches of one fused decode+NMS configuration in flight on ``depth`` CUDA streams, each with its
+    own plan, scratch and output buffers.  The decode kernel is HBM-bound and the per-image NMS is a latency-bound
+    tail on a subset of the SMs, so the next batch's decode fills the machine while the previous batch resolves.
+
+    ``submit(raws)`` enqueues a batch (after whatever the caller's current stream has queued) and returns its slot;
+    ``result(slot)`` is that batch's :class:`Detections` (one host read).  A slot's buffers are reused ``depth``
+    submissions later: take the result before that."""
+
+    def __init__(self, shapes, anchors3, input_shape, num_classes, device, og_size=None, iou_threshold=0.5,
+                 score_threshold=0.1, box_allowance=None, tracked_classes=None, order="image", variant=0,
+                 depth: int = 4):
+        if depth < 1:
+            raise RuntimeError("DetectPipeline: depth must be at least 1")
+        self.depth = int(depth)
+        self.plans = []
+        for i in range(self.depth):
+            pl = DetectPlan(shapes, anchors3, input_shape, num_classes, device, og_size, iou_threshold, score_threshold,
+                            box_allowance, tracked_classes, order, variant, "auto", False, throughput=self.depth > 1)
+            pl.ws_tag = "detect/pipe%d" % i
+            self.plans.append(pl)
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.depth)]
+        self.submitted = 0
+
+    def submit(self, raws) -> int:
+        slot = self.submitted % self.depth
+        st = self.streams[slot]
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            self.plans[slot].enqueue(raws)
+        self.submitted += 1
+        return slot
+
+    def result(self, slot: int) -> Detections:
+        with torch.cuda.stream(self.streams[slot]):
+            return self.plans[slot].result()
+
+    def join(self) -> None:
+        """Make the caller's current stream wait for every batch submitted so far."""
+        cur = torch.cuda.current_stream()
+        for st in self.streams:
+            cur.wait_stream(st)
 
 
 def detect(raws: Sequence[torch.Tensor], anchors3: Sequence, input_shape: Tuple[int, int], num_classes: int,
