@@ -62,6 +62,43 @@ def test_nms_crowded_and_tiny_thresholds(ops, n, groups, thr):
     assert np.array_equal(keep, ref)
 
 
+@pytest.mark.parametrize("kind,n,groups,thr", [("mixed_sizes", 20000, 3, 0.5), ("far_coords", 12000, 2, 0.7),
+                                               ("line", 15000, 1, 0.3), ("one_big_segment", 40000, 1, 0.5),
+                                               ("nonfinite", 6000, 2, 0.45), ("thr_high", 10000, 4, 0.95),
+                                               ("thr_edge", 10000, 4, 0.05)])
+def test_nms_adversarial_geometry(ops, kind, n, groups, thr):
+    """Shapes that stress the grid pruning of the general engine: extents over four orders of magnitude, large
+    coordinates (grid padding / fp32 rounding of the centres), all centres on one line (degenerate grid axis), one
+    segment too large for the shared-memory resolve state, inf / NaN boxes, thresholds at both ends of the range."""
+    g = np.random.default_rng(len(kind) * 1000 + n)
+    c = g.uniform(0, 640, size=(n, 2))
+    wh = g.uniform(8, 160, size=(n, 2))
+    if kind == "mixed_sizes":
+        wh = 10.0 ** g.uniform(-1, 3, size=(n, 2))
+        c[: n // 4] = c[n // 4: n // 2]                     # coincident centres with unrelated extents
+    elif kind == "far_coords":
+        c = c + np.array([3.0e6, -7.0e5])
+    elif kind == "line":
+        c[:, 1] = 123.0
+        wh[:, 1] = 40.0
+    elif kind == "thr_high":
+        c = g.uniform(0, 64, size=(n, 2))
+        wh = g.uniform(30, 34, size=(n, 2))                 # near-identical boxes: IoU above 0.95 does occur
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    if kind == "nonfinite":
+        b[::50, 2] = np.inf
+        b[7::90, 0] = -np.inf
+        b[11::130, 1] = np.nan
+        b[13::170] = np.nan
+    s = g.uniform(0, 1, size=n).astype(np.float32)
+    m = n // 3
+    s[0:3 * m:3] = s[1:3 * m:3]                             # score ties
+    i = g.integers(0, groups, size=n).astype(np.int64)
+    ref = O.batched_nms(b, s, i, thr)
+    keep = ops.batched_nms(dev(b), dev(s), dev(i), thr).cpu().numpy()
+    assert np.array_equal(keep, ref)
+
+
 def test_nms_empty_and_props(ops):
     e = ops.batched_nms(torch.zeros(0, 4).cuda(), torch.zeros(0).cuda(), torch.zeros(0, dtype=torch.int64).cuda(), 0.5)
     assert e.numel() == 0 and e.dtype == torch.int64
