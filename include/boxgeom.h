@@ -90,6 +90,9 @@ typedef struct {
     int32_t nms_path;           /* 0 auto (per-image CTAs, up to 4,096 score survivors per image), 1 general segmented engine,
                                  * 2 = 0 but an error instead of the general engine when the threshold rules it out,
                                  * 3 = 2 with one CTA per image (no helper CTA), 4 per-image CTAs for up to 8,192 survivors */
+    int32_t extra_cols;         /* columns per row after the four box columns that the kernels skip (mask coefficients and
+                                 * keypoints of the segmentation / keypoint heads, inference_seg.py:66-68): rows are
+                                 * 5 + C + extra_cols floats; the caller gathers them by out_keep */
     int32_t throughput;         /* 0: tuned for the latency of one batch (helper CTA per image while the GPU has room, the NMS
                                  * kernel launched programmatically behind the decode kernel); 1: tuned for several batches in
                                  * flight on different streams (one NMS CTA per image, plain stream-ordered launches) */

@@ -92,6 +92,45 @@ def gen_decode_post(ns):
              per_image_counts=np.array([p.shape[0] for p in per], dtype=np.int64))
 
 
+SEG_POST_CASES = {
+    # name: (decode case, iou, score_thr, box_allowance, tracked, keypoint columns)
+    "segpost_T128": ("dec_T128", 0.65, 0.001, 4, None, 0),
+    "segpost_T128_tracked": ("dec_T128", 0.35, 0.3, 4, (1, 4, 7, 16, 17), 0),   # (keypoint columns next to masks trip the reference's own assert, inference_seg.py:70)
+}
+SEG_MASKS = 4
+
+
+def seg_extra_columns(B, N, n_kp, seed):
+    """Mask coefficients (tanh range) and keypoint columns appended to the decoded rows, seeded."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.tanh(torch.randn(B, N, SEG_MASKS + n_kp, generator=g))
+
+
+def gen_seg_post(ns):
+    """inference_seg.post_process_preds (f2): same box geometry on rows that carry mask coefficients (and keypoints).
+    The protos are the 4 unit masks over a 2x2 map and the image is 2x2, so the masks the reference draws are
+    `coef > 0` of the kept rows: they pin the row gather of the extra columns."""
+    for name, (dname, iou, thr, allow, tracked, n_kp) in SEG_POST_CASES.items():
+        B, H, W, C, dist, seed, og = DECODE_CASES[dname]
+        raws = synth.raw_head_outputs(B, H, W, C, dist, seed)
+        anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+        base = ref_harness.ref_decode_inference(raws, anc, H, W, og, C)
+        extra = seg_extra_columns(B, base.shape[1], n_kp, 500 + seed)
+        preds = torch.cat([base, extra], dim=-1).contiguous()
+        protos = torch.eye(SEG_MASKS).reshape(1, SEG_MASKS, 2, 2).repeat(B, 1, 1, 1).contiguous()
+        cap = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, allow, tracked)
+        per, masks, kps = cap["per_image"], cap["masks"], cap["keypoints"]
+        save(name, decode_case=np.array(dname), iou=np.array(iou), thr=np.array(thr),
+             allow=np.array(-1 if allow is None else allow), n_kp=np.array(n_kp), extra_seed=np.array(500 + seed),
+             tracked=np.array(tracked if tracked else [], dtype=np.int64),
+             nms_keep=cap["keep"].numpy(),
+             per_image=np.concatenate(per, 0) if per else np.zeros((0, 6), np.float32),
+             per_image_counts=np.array([p.shape[0] for p in per], dtype=np.int64),
+             masks=np.concatenate([m.reshape(m.shape[0], -1) for m in masks], 0) if masks else np.zeros((0, SEG_MASKS), bool),
+             keypoints=np.concatenate([k.reshape(-1, 3) for k in kps], 0) if kps else np.zeros((0, 3), np.float32),
+             keypoint_rows=np.array([k.reshape(-1, 3).shape[0] for k in kps], dtype=np.int64))
+
+
 def gen_nms():
     cases = {}
     b, s, g = synth.nms_boxes(3000, 4, seed=3)
@@ -239,6 +278,7 @@ def gen_ratio(ns):
 if __name__ == "__main__":
     ns = ref_harness.load()
     gen_decode_post(ns)
+    gen_seg_post(ns)
     gen_nms()
     gen_assign(ns)
     gen_assign_variants(ns)

@@ -145,3 +145,63 @@ def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_all
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
     return cap
+
+
+def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_threshold, box_allowance=None,
+                         tracked_classes=None):
+    """Calls the reference's inference_seg.post_process_preds unmodified (inference_seg.py:40-175) and captures the
+    arguments / result of its torchvision.ops.batched_nms call and, per surviving image, the box array, the boolean
+    masks and the keypoint array it hands to the drawing code."""
+    import numpy as np
+    import torch
+    import torchvision
+    load()
+    import inference_seg as inf
+    inf.device = "cpu"  # module-global only defined under __main__, read by the tracked-class filter
+    cap = {"per_image": [], "masks": [], "keypoints": []}
+    real_nms = torchvision.ops.batched_nms
+
+    def spy_nms(boxes, scores, idxs, iou_threshold):
+        keep = real_nms(boxes, scores, idxs, iou_threshold)
+        cap.update(boxes=boxes.clone(), scores=scores.clone(), idxs=idxs.clone(), keep=keep.clone())
+        return keep
+
+    def spy_boxes(img, boxes, **kw):
+        cap["per_image"].append(np.array(boxes, copy=True))
+        return img
+
+    def spy_segments(img, masks, **kw):
+        cap["masks"].append(np.array(masks, copy=True))
+        return img
+
+    def spy_keypoints(img, kp, **kw):
+        cap["keypoints"].append(np.array(kp, copy=True))
+        return img
+
+    class _NullImg:
+        @staticmethod
+        def fromarray(a):
+            class _I:
+                def save(self, f):
+                    pass
+            return _I()
+
+    old = (torchvision.ops.batched_nms, inf.apply_bboxes, inf.apply_segments, inf.apply_keypoints, inf.Image, inf.STORAGE_PATH)
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    try:
+        torchvision.ops.batched_nms = spy_nms
+        inf.apply_bboxes, inf.apply_segments, inf.apply_keypoints = spy_boxes, spy_segments, spy_keypoints
+        inf.Image = _NullImg
+        inf.STORAGE_PATH = tmp
+        B = preds.shape[0]
+        imgs = torch.zeros(B, 3, protos.shape[2], protos.shape[3], dtype=torch.uint8)  # same size as the protos: the resize is the identity
+        with torch.no_grad():
+            inf.post_process_preds(imgs, preds.clone(), protos.clone(), num_classes, iou_threshold=iou_threshold,
+                                   score_threshold=score_threshold, box_allowance=box_allowance,
+                                   tracked_classes=list(tracked_classes) if tracked_classes else None)
+    finally:
+        (torchvision.ops.batched_nms, inf.apply_bboxes, inf.apply_segments, inf.apply_keypoints, inf.Image, inf.STORAGE_PATH) = old
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return cap

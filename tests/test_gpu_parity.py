@@ -8,7 +8,8 @@ import torch
 
 from oracle import oracle as O
 from vision_conglomerate_b200 import synth
-from tests.util import ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon
+from tests.util import (ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon, rows_order,
+                        seg_extra_columns)
 
 pytestmark = pytest.mark.gpu
 
@@ -201,6 +202,36 @@ def test_post_process_golden(ops, name):
     assert torch.equal(fused.pred_boxes, det.pred_boxes) and torch.equal(fused.keep_idxs, det.keep_idxs)
     with pytest.raises(RuntimeError):
         ops.post_process(preds[:, :-1].contiguous(), (H, W), C)             # N does not match the input shape
+
+
+@pytest.mark.parametrize("name", ["segpost_T128", "segpost_T128_tracked"])
+@pytest.mark.parametrize("nms_path", ["auto", "general"])
+def test_seg_post_process_golden(ops, name, nms_path):
+    """SURVEY 8 f2, inference side: ops.post_process on rows [obj, cls*C, x,y,w,h, 4 mask coefficients] (what
+    inference_seg.post_process_preds receives) against the rows and the drawn masks of the unmodified reference
+    (unit protos: mask = coef > 0, which pins the gather of the extra columns), and bitwise against the 85-column call."""
+    g = golden(name)
+    gd = golden(str(g["decode_case"]))
+    B, H, W, C, seed, og0, og1 = (int(v) for v in gd["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(gd["dist"]), seed)
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    base = torch.cat([ops.decode_scale(dev(r), a, (H, W), True, None).reshape(B, -1, C + 5) for r, a in zip(raws, anc)], 1)
+    extra = seg_extra_columns(B, base.shape[1], 4, int(g["extra_seed"]))
+    preds = torch.cat([base, dev(extra)], dim=-1).contiguous()
+    det = ops.post_process(preds, (H, W), C, float(g["iou"]), float(g["thr"]), allow, tracked, order="global", nms_path=nms_path)
+    rows, keep = det.pred_boxes.clone(), det.keep_idxs.clone()
+    coefs = ops.extra_columns(preds, det, C)
+    assert coefs.shape == (rows.shape[0], 4)
+    counts = g["per_image_counts"]
+    ref_img = np.repeat(np.arange(len(counts)), counts)
+    got_img = np.unique(det.sample_idxs.cpu().numpy(), return_inverse=True)[1]
+    po, pr = rows_order(rows.cpu().numpy(), got_img), rows_order(g["per_image"], ref_img)
+    assert_close(rows.cpu().numpy()[po], g["per_image"][pr], rtol=1e-5, atol=2e-5 * max(H, W), what="rows vs reference")
+    assert np.array_equal(coefs.cpu().numpy()[po] > 0, g["masks"][pr].astype(bool))
+    plain = ops.post_process(base.contiguous(), (H, W), C, float(g["iou"]), float(g["thr"]), allow, tracked, order="global")
+    assert torch.equal(plain.pred_boxes, rows) and torch.equal(plain.keep_idxs, keep)
 
 
 @pytest.mark.parametrize("nms_path", ["auto", "general", "per_image_single"])

@@ -6,7 +6,8 @@ import torch
 
 from oracle import oracle as O
 from vision_conglomerate_b200 import synth
-from tests.util import ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon
+from tests.util import (ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon, rows_order,
+                        seg_extra_columns)
 
 DEC = ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"]
 
@@ -60,6 +61,30 @@ def test_post_process(name):
     got, ref_rows = rows_canon(got, got_img), rows_canon(ref_rows, ref_img)
     assert_close(got, ref_rows, rtol=1e-5, atol=1e-4, what="pred_boxes")
     assert np.array_equal(got[:, 1], ref_rows[:, 1])  # class ids exact
+
+
+@pytest.mark.parametrize("name", ["segpost_T128", "segpost_T128_tracked"])
+def test_seg_post_process(name):
+    """inference_seg.post_process_preds: the box geometry is the detection one on rows that also carry
+    mask coefficients; the reference's drawn masks (unit protos: mask = coef > 0) pin the gather of those columns."""
+    g = golden(name)
+    gd = golden(str(g["decode_case"]))
+    raws, B, H, W, C, og = _decode_inputs(gd)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = O.decode_inference(raws, anc, H, W, og)
+    extra = seg_extra_columns(B, preds.shape[1], 4, int(g["extra_seed"])).numpy()
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    out = O.post_process(preds, float(g["iou"]), float(g["thr"]), allow, tracked)
+    counts = g["per_image_counts"]
+    got, ref_rows = out["pred_boxes"], g["per_image"]
+    assert got.shape[0] == counts.sum()
+    ref_img = np.repeat(np.arange(len(counts)), counts)
+    got_img = np.unique(out["sample_idxs"], return_inverse=True)[1] if len(got) else out["sample_idxs"]
+    po, pr = rows_order(got, got_img), rows_order(ref_rows, ref_img)
+    assert_close(got[po], ref_rows[pr], rtol=1e-5, atol=1e-4, what="pred_boxes")
+    coefs = extra.reshape(-1, 4)[out["keep"]]
+    assert np.array_equal(coefs[po] > 0, g["masks"][pr].astype(bool))
 
 
 @pytest.mark.parametrize("case", ["rand", "ties", "dense1", "hand_thr05", "hand_thr05m", "hand_thr0"])

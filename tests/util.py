@@ -60,3 +60,18 @@ def assign_variant_case(name):
 
 
 ASSIGN_VARIANTS = ("seg_overlap", "seg_plain", "kpt", "kpt_seg_overlap")
+
+
+def seg_extra_columns(B, N, n_extra, seed):
+    """The seeded mask-coefficient columns oracle/make_golden.py appended to the decoded rows (gen_seg_post)."""
+    import torch
+    g = torch.Generator().manual_seed(int(seed))
+    return torch.tanh(torch.randn(B, N, n_extra, generator=g))
+
+
+def rows_order(rows, img):
+    """The permutation rows_canon applies."""
+    r = np.asarray(rows).astype(np.float64)
+    if r.shape[0] == 0:
+        return np.zeros(0, dtype=np.int64)
+    return np.lexsort((r[:, 5], r[:, 4], r[:, 3], r[:, 2], r[:, 1], -r[:, 0], np.asarray(img)))

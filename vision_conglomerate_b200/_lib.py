@@ -47,6 +47,7 @@ class DetectParams(C.Structure):
         ("order", C.c_int32),
         ("variant", C.c_int32),
         ("nms_path", C.c_int32),
+        ("extra_cols", C.c_int32),
         ("throughput", C.c_int32),
     ]
 

@@ -183,6 +183,7 @@ static bool det_valid(const bg_detect_params *p)
 {
     if (!p || p->B <= 0 || p->C <= 0 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->H <= 0 || p->W <= 0) return false;
     if (p->n_tracked < 0 || p->n_tracked > BG_MAX_TRACKED) return false;
+    if (p->extra_cols < 0 || p->extra_cols > 4096) return false;
     for (int s = 0; s < 3; ++s) {
         if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
         // the decode kernel divides by na and nx with 32-bit magic numbers: exact while n * d < 2^32
@@ -196,7 +197,7 @@ static bool det_valid(const bg_detect_params *p)
 static TilePlan det_tile_plan(const bg_detect_params *p)
 {
     TilePlan tp;
-    const int D = p->C + 5;
+    const int D = p->C + 5 + p->extra_cols;
     int TR = (int)(DEC_TILE_BYTES / ((size_t)D * 4));
     TR = TR > DEC_THREADS ? DEC_THREADS : (TR / 4) * 4;  // multiple of 4 rows keeps every full tile 16-byte sized
     if (TR < 4) TR = 4;
@@ -225,7 +226,7 @@ static int det_nms_path(const bg_detect_params *p, const TilePlan &tp)
 
 static bool det_plan_valid(const bg_detect_params *p, const TilePlan &tp)
 {
-    return (size_t)tp.TR * (p->C + 5) * 4 <= (size_t)DEC_TILE_BYTES && (long long)p->B * tp.tpi_total < (1ll << 31);
+    return (size_t)tp.TR * (p->C + 5 + p->extra_cols) * 4 <= (size_t)DEC_TILE_BYTES && (long long)p->B * tp.tpi_total < (1ll << 31);
 }
 
 }  // namespace bg
@@ -365,7 +366,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         for (int a = 0; a < pp->na; ++a) { d.aw[a] = pp->anchors[s][a][0]; d.ah[a] = pp->anchors[s][a][1]; }
         aligned = aligned && (((uintptr_t)raws[s] & 15) == 0);
     }
-    k.B = pp->B; k.C = pp->C; k.D = pp->C + 5; k.na = pp->na; k.N = (int)N;
+    k.B = pp->B; k.C = pp->C; k.D = pp->C + 5 + pp->extra_cols; k.na = pp->na; k.N = (int)N;
     k.magic_na = (u32)(((1ull << 32) + (u64)pp->na - 1) / (u64)pp->na);
     k.predecoded = predecoded;
     // guard of modules/detection.py:76: rescale only if BOTH dimensions differ (already applied to decoded rows)
@@ -404,7 +405,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         const int cap = sms * DEC_CTAS_PER_SM;
         const int grid = tp.total < cap ? tp.total : cap;
         const size_t smem = (size_t)DEC_STAGES * tp.TR * k.D * 4;
-        if (k.C == 80) decode_filter_kernel<80><<<grid, DEC_THREADS, smem, st>>>(k, tp, o);
+        if (k.C == 80 && k.D == 85) decode_filter_kernel<80><<<grid, DEC_THREADS, smem, st>>>(k, tp, o);
         else decode_filter_kernel<0><<<grid, DEC_THREADS, smem, st>>>(k, tp, o);
         BG_LAUNCH_CHECK();
     }
@@ -495,7 +496,7 @@ int bg_post_process(const float *preds, const bg_detect_params *pp, float *out_b
                     int32_t *out_counts, void *workspace, size_t workspace_bytes, size_t mask_bytes, void *stream)
 {
     if (!det_valid(pp) || !preds) return BG_ERR_INVALID;
-    const long long D = pp->C + 5;
+    const long long D = pp->C + 5 + pp->extra_cols;
     const long long n0 = (long long)pp->ny[0] * pp->nx[0] * pp->na, n1 = (long long)pp->ny[1] * pp->nx[1] * pp->na;
     return detect_impl(preds, preds + n0 * D, preds + (n0 + n1) * D, 1, pp, out_boxes, out_img, out_keep, out_counts, workspace,
                        workspace_bytes, mask_bytes, stream);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
     __shared__ Surv s_surv[DEC_THREADS];
     __shared__ int s_wcnt[DEC_THREADS / 32];
     const int C = CT ? CT : k.C;
-    const int D = C + 5;
+    const int D = CT ? CT + 5 : k.D;  // row stride; the runtime variant also serves rows with trailing extra columns
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int stage_floats = tp.TR * D;
     float *ring = reinterpret_cast<float *>(dec_smem);

@@ -152,10 +152,13 @@ class DetectPlan:
         if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
             raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
         B, _, _, na, D = shapes[0]
-        if D != num_classes + 5:
-            raise RuntimeError("detect: the keypoint / mask-coefficient variants are out of scope for the fused path")
+        if D < num_classes + 5:
+            raise RuntimeError("detect: rows must hold at least 5 + num_classes columns")
         p = DetectParams()
         p.B, p.C, p.na = B, num_classes, na
+        # trailing columns (mask coefficients / keypoints of the segmentation and keypoint heads, inference_seg.py:66-68)
+        # take no part in the box geometry: the kernels skip them, `extra_columns` gathers them for the kept rows
+        p.extra_cols = D - (num_classes + 5)
         p.H, p.W = int(input_shape[0]), int(input_shape[1])
         p.og_H, p.og_W = (int(og_size[0]), int(og_size[1])) if og_size is not None else (-1, -1)
         for s, sh in enumerate(shapes):
@@ -203,7 +206,7 @@ class DetectPlan:
         p = self.params
         if self.predecoded:
             preds = _req(raws[0] if isinstance(raws, (list, tuple)) else raws, "preds")
-            if tuple(preds.shape) != (self.B, self.N, p.C + 5):
+            if tuple(preds.shape) != (self.B, self.N, p.C + 5 + p.extra_cols):
                 raise RuntimeError("post_process: preds shape differs from the plan")
             self.raws = [preds]
         else:
@@ -321,18 +324,28 @@ def detect(raws: Sequence[torch.Tensor], anchors3: Sequence, input_shape: Tuple[
     return plan.result()
 
 
+def extra_columns(preds: torch.Tensor, det: Detections, num_classes: int) -> torch.Tensor:
+    """Trailing columns of the kept rows, ``preds[..., 5+num_classes:]`` gathered by ``det.keep_idxs`` -- the
+    ``mask_coefs`` / ``keypoints`` of ``inference_seg.post_process_preds`` (lines 66-68, 94-95) in the row order of
+    ``det.pred_boxes``."""
+    flat = preds.reshape(-1, preds.shape[-1])
+    return flat[det.keep_idxs, 5 + num_classes:]
+
+
 def post_process(preds: torch.Tensor, input_shape: Tuple[int, int], num_classes: int, iou_threshold: float = 0.5,
                  score_threshold: float = 0.1, box_allowance: Optional[float] = None,
                  tracked_classes: Optional[Sequence[int]] = None, order: str = "global", na: int = 3,
                  strides: Sequence[int] = (8, 16, 32), nms_path: str = "auto") -> Detections:
     """The compute of ``inference_det.post_process_preds`` (lines 57-97 and 107-109) on the tensor the reference
     hands it: ``preds [B, N, 5+C] = DetectionNet.forward(x, inference=True)`` with rows ``[obj, cls*C, x, y, w, h]``
-    (logits + decoded pixel boxes).  Scores, box allowance, xyxy, per-image NMS, strict score threshold, rows
+    (logits + decoded pixel boxes; the segmentation / keypoint heads append mask coefficients and keypoints,
+    ``inference_seg.py:58,62-97`` -- the same arithmetic; fetch those columns with :func:`extra_columns`).
+    Scores, box allowance, xyxy, per-image NMS, strict score threshold, rows
     ``(score, class, x1, y1, x2, y2)`` and the tracked-class filter in one pass; ``order='global'`` is the
     reference's row order (score-descending over the batch)."""
     preds = _req(preds, "preds")
-    if preds.dim() != 3 or preds.shape[2] != num_classes + 5:
-        raise RuntimeError("post_process: expected preds [B, N, 5 + num_classes] (keypoint / mask columns are out of scope)")
+    if preds.dim() != 3 or preds.shape[2] < num_classes + 5:
+        raise RuntimeError("post_process: expected preds [B, N, 5 + num_classes (+ mask coefficients / keypoints)]")
     B, N, D = preds.shape
     H, W = int(input_shape[0]), int(input_shape[1])
     shapes = [(B, H // s, W // s, na, D) for s in strides]
