@@ -75,4 +75,66 @@ struct IouThr {
 };
 IouThr make_iou_thr(double thr);
 
+// Ascending bitonic sort of s[0..P), P = E * 1024 keys (callers pad with ~0), by 1024 threads.  Thread t holds
+// the E consecutive keys t*E..t*E+E-1 in registers: strides below E are register compare-exchanges, strides
+// below 32*E are warp shuffles with lane ^ (j/E), and only the larger strides go through shared memory
+// (staged key-index-major, s[e*1024 + t], so the exchange reads are conflict-free).
+template <int E>
+__device__ __forceinline__ void sort_reg_1024(u64 *s, int k_start = 2)  // k_start = P: only the last merge (input bitonic)
+{
+    const int t = threadIdx.x;
+    constexpr int P = E * 1024;
+    u64 v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = s[t * E + e];
+    __syncthreads();
+    for (int k = k_start; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32 * E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) s[e * 1024 + t] = v[e];
+                __syncthreads();
+                const int pt = t ^ (j / E);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const u64 o = s[e * 1024 + pt];
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
+                }
+                __syncthreads();
+            } else if (j >= E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = t * E + e;
+                    const u64 o = __shfl_xor_sync(0xffffffffu, v[e], j / E);
+                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
+                }
+            } else {
+                // register compare-exchange; j is 1 (E >= 2) or 2 (E == 4): static indices keep v[] in registers
+#pragma unroll
+                for (int jj = 1; jj < E; jj <<= 1) {
+                    if (jj != j) continue;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        if ((e & jj) == 0) {
+                            const int i = t * E + e;
+                            const bool up = (i & k) == 0;
+                            const u64 a = v[e], c = v[e | jj];
+                            const bool sw = (a > c) == up;
+                            v[e] = sw ? c : a;
+                            v[e | jj] = sw ? a : c;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) s[t * E + e] = v[e];
+    __syncthreads();
+}
+
+
 }  // namespace bg

@@ -149,67 +149,6 @@ __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, i
     return r;
 }
 
-// Ascending bitonic sort of s[0..P), P = E * 1024 keys (callers pad with ~0), by 1024 threads.  Thread t holds
-// the E consecutive keys t*E..t*E+E-1 in registers: strides below E are register compare-exchanges, strides
-// below 32*E are warp shuffles with lane ^ (j/E), and only the larger strides go through shared memory
-// (staged key-index-major, s[e*1024 + t], so the exchange reads are conflict-free).
-template <int E>
-__device__ __forceinline__ void inms_sort_reg(u64 *s)
-{
-    const int t = threadIdx.x;
-    constexpr int P = E * INMS_THREADS;
-    u64 v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) v[e] = s[t * E + e];
-    __syncthreads();
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            if (j >= 32 * E) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) s[e * INMS_THREADS + t] = v[e];
-                __syncthreads();
-                const int pt = t ^ (j / E);
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int i = t * E + e;
-                    const u64 o = s[e * INMS_THREADS + pt];
-                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
-                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
-                }
-                __syncthreads();
-            } else if (j >= E) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int i = t * E + e;
-                    const u64 o = __shfl_xor_sync(0xffffffffu, v[e], j / E);
-                    const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
-                    v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
-                }
-            } else {
-                // register compare-exchange; j is 1 (E >= 2) or 2 (E == 4): static indices keep v[] in registers
-#pragma unroll
-                for (int jj = 1; jj < E; jj <<= 1) {
-                    if (jj != j) continue;
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        if ((e & jj) == 0) {
-                            const int i = t * E + e;
-                            const bool up = (i & k) == 0;
-                            const u64 a = v[e], c = v[e | jj];
-                            const bool sw = (a > c) == up;
-                            v[e] = sw ? c : a;
-                            v[e | jj] = sw ? a : c;
-                        }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) s[t * E + e] = v[e];
-    __syncthreads();
-}
-
 // pads keys[K..P) with ~0 and sorts keys[0..P), P = the smallest of 1024, 2048, 4096 (, 8192) >= K
 template <class Cfg>
 __device__ __forceinline__ void inms_sort_keys(u64 *keys, int K)
@@ -218,10 +157,10 @@ __device__ __forceinline__ void inms_sort_keys(u64 *keys, int K)
     while (P < K) P <<= 1;
     for (int j = K + threadIdx.x; j < P; j += INMS_THREADS) keys[j] = ~0ull;
     __syncthreads();
-    if (P == INMS_THREADS) inms_sort_reg<1>(keys);
-    else if (P == 2 * INMS_THREADS) inms_sort_reg<2>(keys);
-    else if (P == 4 * INMS_THREADS || Cfg::CAP <= 4 * INMS_THREADS) inms_sort_reg<4>(keys);
-    else inms_sort_reg<8>(keys);
+    if (P == INMS_THREADS) sort_reg_1024<1>(keys);
+    else if (P == 2 * INMS_THREADS) sort_reg_1024<2>(keys);
+    else if (P == 4 * INMS_THREADS || Cfg::CAP <= 4 * INMS_THREADS) sort_reg_1024<4>(keys);
+    else sort_reg_1024<8>(keys);
 }
 
 __device__ __forceinline__ bool inms_tracked(const ImgNmsK &k, int c)

@@ -171,6 +171,22 @@ __device__ __forceinline__ void bitonic_step_smem(u64 *s, int cnt, int gbase, in
     }
 }
 
+// sort of the P = E*1024 keys in shared memory by the register-blocked network of common.cuh; descending order is
+// the ascending order of the complements
+template <int E>
+__device__ __forceinline__ void sort_chunk_smem(u64 *s, bool desc, bool merge_only = false)
+{
+    if (desc) {
+        for (int i = threadIdx.x; i < E * 1024; i += SORT_THREADS) s[i] = ~s[i];
+        __syncthreads();
+    }
+    sort_reg_1024<E>(s, merge_only ? E * 1024 : 2);
+    if (desc) {
+        for (int i = threadIdx.x; i < E * 1024; i += SORT_THREADS) s[i] = ~s[i];
+        __syncthreads();
+    }
+}
+
 // ascending sort of keys[0..K) (global, with room for next_pow2(K) entries) by the whole CTA
 __device__ void block_sort_u64(u64 *keys, int K, u64 *s)
 {
@@ -178,23 +194,25 @@ __device__ void block_sort_u64(u64 *keys, int K, u64 *s)
     if (P <= SORT_CHUNK) {
         for (int i = threadIdx.x; i < P; i += SORT_THREADS) s[i] = (i < K) ? keys[i] : ~0ull;
         __syncthreads();
-        for (int k = 2; k <= P; k <<= 1)
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                bitonic_step_smem(s, P, 0, k, j);
-                __syncthreads();
-            }
+        if (P == 8192) sort_chunk_smem<8>(s, false);
+        else if (P == 4096) sort_chunk_smem<4>(s, false);
+        else if (P == 2048) sort_chunk_smem<2>(s, false);
+        else if (P == 1024) sort_chunk_smem<1>(s, false);
+        else {
+            for (int k = 2; k <= P; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    bitonic_step_smem(s, P, 0, k, j);
+                    __syncthreads();
+                }
+        }
         for (int i = threadIdx.x; i < K; i += SORT_THREADS) keys[i] = s[i];
     } else {
         for (int i = K + threadIdx.x; i < P; i += SORT_THREADS) keys[i] = ~0ull;
         __syncthreads();
-        for (int c = 0; c < P; c += SORT_CHUNK) {  // phase 1: every stage k <= SORT_CHUNK, chunk by chunk
+        for (int c = 0; c < P; c += SORT_CHUNK) {  // phase 1: chunks sorted in alternating directions (every stage k <= SORT_CHUNK)
             for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) s[i] = keys[c + i];
             __syncthreads();
-            for (int k = 2; k <= SORT_CHUNK; k <<= 1)
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    bitonic_step_smem(s, SORT_CHUNK, c, k, j);
-                    __syncthreads();
-                }
+            sort_chunk_smem<SORT_CHUNK / 1024>(s, (c & SORT_CHUNK) != 0);
             for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) keys[c + i] = s[i];
             __syncthreads();
         }
@@ -212,10 +230,7 @@ __device__ void block_sort_u64(u64 *keys, int K, u64 *s)
             for (int c = 0; c < P; c += SORT_CHUNK) {
                 for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) s[i] = keys[c + i];
                 __syncthreads();
-                for (int j = SORT_CHUNK >> 1; j > 0; j >>= 1) {
-                    bitonic_step_smem(s, SORT_CHUNK, c, k, j);
-                    __syncthreads();
-                }
+                sort_chunk_smem<SORT_CHUNK / 1024>(s, (c & k) != 0, true);  // the chunk is bitonic: one merge, direction of stage k
                 for (int i = threadIdx.x; i < SORT_CHUNK; i += SORT_THREADS) keys[c + i] = s[i];
                 __syncthreads();
             }
