@@ -37,7 +37,8 @@ extern "C" {
 
 /* bits of the device-side status word (out_counts[1]) */
 #define BG_STATUS_GROUP_RANGE 1 /* batched_nms: max(idxs)-min(idxs) exceeds max_groups */
-#define BG_STATUS_MASK_SPACE 2  /* suppression-mask scratch exhausted: retry with a larger workspace */
+#define BG_STATUS_MASK_SPACE 2  /* suppression scratch (mask_bytes) exhausted: neither the overlap-edge list nor the dense
+                                 * bit matrix fits; retry with a larger mask_bytes */
 #define BG_STATUS_NEED_GENERAL 4 /* bg_detect, per-image NMS path: an image has too many survivors (out_counts[2+B+b]) or overlaps;
                                    * retry with nms_path = 4 (up to 8,192 survivors) or 1 */
 
@@ -62,6 +63,11 @@ size_t bg_sizeof_loss_params(void);
  *                     equal scores (torchvision's order inside ties is arbitrary);
  *   out_counts [2] i32: [0] = number kept, [1] = status bits.
  *   max_groups bounds max(idxs)-min(idxs)+1 (sizes the per-group tables).
+ *   mask_bytes: size of the suppression scratch inside the workspace.  For 0.05 <= iou_threshold < 1 it
+ *               holds overlap edges (8 bytes per overlapping pair, shared out to the groups in proportion to
+ *               their size); when a group's share overflows, the same call falls back to the dense bit
+ *               matrix (sum over groups of count * ceil(count/64) * 8 bytes) if that fits; other thresholds
+ *               use the matrix directly.  BG_STATUS_MASK_SPACE if neither fits.
  */
 size_t bg_batched_nms_workspace_bytes(int64_t n, int64_t max_groups, size_t mask_bytes);
 int bg_batched_nms(const float *boxes, const float *scores, const int64_t *idxs, int64_t n,
