@@ -35,7 +35,23 @@ def detect_case(name, B, S, dist, iou, thr, iters=10, tracked=None):
     plan.enqueue(raws)
     r = plan.result()
     ms = timed(lambda: plan.enqueue(raws), iters)
-    out[name] = {"ms_per_batch": ms, "img_per_s": B / ms * 1e3, "batch": B, "kept_rows": int(r.pred_boxes.shape[0]),
+    # the same configuration with four batches in flight (ops.DetectPipeline)
+    pipe = ops.DetectPipeline([tuple(r.shape) for r in raws], anc, (S, S), 80, dev, None, iou, thr, 4, tracked, depth=4)
+    for _ in range(2):
+        for _d in range(4):
+            pipe.submit(raws)
+        for d in range(4):
+            pipe.result(d)
+    pipe.join()
+
+    def piped():
+        for _d in range(8):
+            pipe.submit(raws)
+        pipe.join()
+    ms_p = timed(piped, max(2, iters // 2)) / 8
+    out[name] = {"ms_per_batch": ms, "img_per_s": B / ms * 1e3, "ms_per_batch_pipelined": ms_p, "img_per_s_pipelined": B / ms_p * 1e3,
+                 "hbm_frac_pipelined": plan.input_bytes / (ms_p * 1e-3) / 1e9 / 6552.6,
+                 "batch": B, "kept_rows": int(r.pred_boxes.shape[0]),
                  "survivors_per_image": float(r.candidates.float().mean()), "nms_path": "general" if plan.params.nms_path == 1 else "per-image",
                  "hbm_frac_of_measured": plan.input_bytes / (ms * 1e-3) / 1e9 / 6552.6}
     return raws, plan
