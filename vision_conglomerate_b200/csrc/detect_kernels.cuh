@@ -233,6 +233,15 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         int si, lrow0, rows;
         const float *src = tile_src(b, tr, si, lrow0, rows);
         const ScaleDesc &s = k.sc[si];
+        // thread 0 works out the refill of this stage (the tile DEC_STAGES iterations ahead) now, while the CTA is
+        // about to wait for data anyway; at the end of the iteration it only has to issue the copy
+        const float *rsrc = nullptr;
+        u32 rbytes = 0;
+        if (tid == 0 && nb < k.B) {
+            int si2, l2, r2;
+            const float *src2 = tile_src(nb, nr, si2, l2, r2);
+            if (tma_ok(src2, r2)) { rsrc = src2; rbytes = (u32)(r2 * D) * 4; }
+        }
         if (tma_ok(src, rows)) {
             mbar_wait(&full_bar[stage], (phases >> stage) & 1u);
             phases ^= 1u << stage;
@@ -363,17 +372,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_filter_ke
         __syncthreads();  // the tile buffer and the survivor list are free again
         DEC_MARK(6);  // barrier: slowest thread of phase 2b
 
-        if (tid == 0) {   // refill this stage with the tile DEC_STAGES iterations ahead
-            if (nb < k.B) {
-                int si2, l2, r2;
-                const float *src2 = tile_src(nb, nr, si2, l2, r2);
-                if (tma_ok(src2, r2)) {
-                    // the generic-proxy reads of this buffer are ordered before the copy by the barrier above (write
-                    // after read needs no proxy fence; only generic writes must be fenced before an async-proxy access)
-                    mbar_expect_tx(&full_bar[stage], (u32)(r2 * D) * 4);
-                    bulk_g2s(tile, src2, (u32)(r2 * D) * 4, &full_bar[stage]);
-                }
-            }
+        if (tid == 0 && rsrc) {   // refill this stage with the tile DEC_STAGES iterations ahead
+            // the generic-proxy reads of this buffer are ordered before the copy by the barrier above (write after
+            // read needs no proxy fence; only generic writes must be fenced before an async-proxy access)
+            mbar_expect_tx(&full_bar[stage], rbytes);
+            bulk_g2s(tile, rsrc, rbytes, &full_bar[stage]);
         }
         DEC_MARK(7);  // refill
     }
