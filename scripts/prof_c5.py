@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Where the batch-1 latency (config 5) goes: host enqueue, GPU time of the two kernels, result read."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vision_conglomerate_b200 import ops, synth
+
+dev = torch.device("cuda", 0)
+anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+frames = [[r.to(dev) for r in synth.raw_head_outputs(1, 640, 640, 80, "TP", 7 + f)] for f in range(32)]
+plan = ops.DetectPlan([tuple(r.shape) for r in frames[0]], anc, (640, 640), 80, dev, (720, 1280), 0.35, 0.3, 4, synth.tracked_classes_default())
+for f in range(64):
+    plan.enqueue(frames[f % 32]); plan.result()
+enq, res, tot, gpu = [], [], [], []
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for f in range(500):
+    t0 = time.perf_counter()
+    e0.record()
+    plan.enqueue(frames[f % 32])
+    e1.record()
+    t1 = time.perf_counter()
+    r = plan.result()
+    t2 = time.perf_counter()
+    enq.append((t1 - t0) * 1e6); res.append((t2 - t1) * 1e6); tot.append((t2 - t0) * 1e6)
+    gpu.append(e0.elapsed_time(e1) * 1e3)
+med = lambda v: sorted(v)[len(v) // 2]
+print("p50 us: host enqueue (incl. 2 event records) %.1f, result() %.1f, total %.1f; GPU span of the two kernels %.1f; rows %d"
+      % (med(enq), med(res), med(tot), med(gpu), int(r.pred_boxes.shape[0])))
+# CUDA graph replay of the same two launches from a static input
+static = [t.clone() for t in frames[0]]
+plan.enqueue(static); plan.result()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    plan.enqueue(static)
+torch.cuda.synchronize()
+tot2 = []
+for f in range(500):
+    t0 = time.perf_counter()
+    for s, src in zip(static, frames[f % 32]):
+        s.copy_(src, non_blocking=True)
+    g.replay()
+    r = plan.result()
+    tot2.append((time.perf_counter() - t0) * 1e6)
+print("graph replay (3 d2d input copies + replay + result): p50 %.1f us, p99 %.1f us, rows %d" % (med(tot2), sorted(tot2)[int(len(tot2) * 0.99)], int(r.pred_boxes.shape[0])))
