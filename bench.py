@@ -409,7 +409,7 @@ def extras(torch, ops, synth, devc, peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="decode kernel: 0 auto, 1 plain loads, 2 TMA bulk")
