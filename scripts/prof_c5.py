@@ -42,3 +42,14 @@ for f in range(500):
     r = plan.result()
     tot2.append((time.perf_counter() - t0) * 1e6)
 print("graph replay (3 d2d input copies + replay + result): p50 %.1f us, p99 %.1f us, rows %d" % (med(tot2), sorted(tot2)[int(len(tot2) * 0.99)], int(r.pred_boxes.shape[0])))
+# stage stamps of the per-image NMS kernel for one frame (%globaltimer hook)
+from vision_conglomerate_b200 import _lib
+L = _lib.lib()
+ns = int(L.bg_profile_stamps_per_image())
+st = torch.zeros(1, ns, dtype=torch.int64, device=dev)
+L.bg_profile_stamps(st.data_ptr())
+plan.enqueue(frames[0]); torch.cuda.synchronize()
+L.bg_profile_stamps(None)
+s = st.cpu()[0].tolist()
+names = ["load_slots", "grid_bucket", "pair_tests", "resolve", "sort", "rank+lookback", "write_rows"]
+print("NMS stages (us):", {n: round((s[i + 1] - s[i]) / 1e3, 2) for i, n in enumerate(names)}, "candidates", int(plan.result().candidates[0]))
