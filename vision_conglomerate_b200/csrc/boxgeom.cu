@@ -829,8 +829,11 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
             }
             attr_smem = smem;
         }
-        l2_pin_kernel<<<sms * 4, 256, 0, st>>>(reinterpret_cast<const float4 *>(w.gobj), w.cells_total / 4);
-        BG_LAUNCH_CHECK();
+        static const bool pin = []() { const char *e = getenv("BG_L2_PIN"); return e && e[0] == '1'; }();
+        if (pin) {
+            l2_pin_kernel<<<sms * 4, 256, 0, st>>>(reinterpret_cast<const float4 *>(w.gobj), w.cells_total / 4);
+            BG_LAUNCH_CHECK();
+        }
         const int per_sm = smem <= 110 * 1024 ? 2 : 1;
         loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
         BG_LAUNCH_CHECK();

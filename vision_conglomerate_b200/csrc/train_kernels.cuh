@@ -470,6 +470,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
     const LossScale &S = k.s[blockIdx.y];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < S.cells;
          c += (long long)gridDim.x * LOSS_THREADS) {
         const float x = ld_stride_f32(S.preds + c * k.D);
@@ -479,7 +481,9 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
         const float sg = sigmoid_acc(x);
         a0 += (double)bce_logits(x, t);
         if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
-        S.gobj[c] = __fsub_rn(sg, t);
+        // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
+        // (evict-last), so those reads do not turn into DRAM read/write turnarounds
+        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
