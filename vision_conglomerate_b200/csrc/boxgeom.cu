@@ -674,6 +674,7 @@ struct LossWs {
     float *gobj;          // all scales, contiguous
     double *part_match[3];
     double *part_dense[3];
+    size_t zero_begin, zero_bytes;  // workspace range cleared before the assignment (chain words + succ flags)
     long long cap;
     long long cells[3], cell_off[3], cells_total;
     int nblk_match, nblk_dense;
@@ -700,9 +701,12 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     w.nblk_match = sms * 8;
     w.nblk_dense = sms * 8;
     w.chain_words = assign_chain_words(p->nt, p->na);
-    {
+    {   // look-back words of the assignment and the succ flags are zeroed by ONE memset: keep them adjacent
         u64 *all = b.take<u64>(3 * w.chain_words);
         for (int s = 0; s < 3; ++s) w.chain[s] = all ? all + s * w.chain_words : nullptr;
+        w.zero_begin = b.off - 3 * w.chain_words * sizeof(u64);
+        w.succ = b.take<unsigned char>(3 * (size_t)w.cap);
+        w.zero_bytes = b.off - w.zero_begin;
     }
     w.cells_total = 0;
     for (int s = 0; s < 3; ++s) {
@@ -712,7 +716,6 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     }
     w.M = b.take<int>(4);
     w.head = b.take<int>(w.cells_total);
-    w.succ = b.take<unsigned char>(3 * (size_t)w.cap);
     w.gobj = b.take<float>(w.cells_total);
     for (int s = 0; s < 3; ++s) {
         w.cell[s] = b.take<int>(w.cap);
@@ -770,7 +773,6 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
     const float *preds[3] = {preds_sm, preds_md, preds_lg};
     if (cudaMemsetAsync(out_hist, 0, sizeof(int64_t) * 9 * (size_t)p->C, st) != cudaSuccess) return BG_ERR_LAUNCH;
     if (cudaMemsetAsync(w.head, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
-    if (cudaMemsetAsync(w.succ, 0, 3 * (size_t)w.cap, st) != cudaSuccess) return BG_ERR_LAUNCH;
     Assign3K a3;
     for (int s = 0; s < 3; ++s) {
         AssignK &a = a3.a[s];
@@ -781,7 +783,7 @@ int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds
         a.anchor = w.anchor[s]; a.box = w.box[s]; a.cell = w.cell[s]; a.cls32 = w.cls[s];
         a.cap = w.cap; a.count = w.M + s;
     }
-    if (cudaMemsetAsync(w.chain[0], 0, 3 * w.chain_words * sizeof(u64), st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
     int rc = assign_launch(a3, 3, st);
     if (rc != BG_OK) return rc;
     Loss3K k;

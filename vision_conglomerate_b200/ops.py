@@ -10,6 +10,7 @@ reference root).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -30,7 +31,14 @@ PER_IMAGE_NMS_CAP = 4096        # InmsSmall::CAP of csrc/imgnms_kernels.cuh
 PER_IMAGE_NMS_CAP_LARGE = 8192  # InmsLarge::CAP
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw accessors skip ~10 us of Python)."""
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -60,9 +68,21 @@ def _req(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+_anchor_cache: Dict[int, tuple] = {}
+
+
 def _anchors_host(anchors) -> List[List[float]]:
+    """Anchor (w, h) pairs as python floats.  The model keeps them as device parameters (read at call time, like the
+    reference does): the copy to the host -- a stream sync -- is remembered per tensor object and version."""
     if isinstance(anchors, torch.Tensor):
-        return anchors.detach().to("cpu", torch.float32).reshape(-1, 2).tolist()
+        ent = _anchor_cache.get(id(anchors))
+        if ent is not None and ent[0]() is anchors and ent[1] == anchors._version:
+            return ent[2]
+        if len(_anchor_cache) > 256:
+            _anchor_cache.clear()
+        val = anchors.detach().to("cpu", torch.float32).reshape(-1, 2).tolist()
+        _anchor_cache[id(anchors)] = (weakref.ref(anchors), anchors._version, val)
+        return val
     return torch.tensor(anchors, dtype=torch.float32).reshape(-1, 2).tolist()
 
 
@@ -464,8 +484,21 @@ METRIC_KEYS = ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_
                "recall")
 
 
+_loss_param_cache: Dict[tuple, LossParams] = {}
+
+
 def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
-    p = LossParams()
+    """The parameter block of bg_loss_fwd / bg_loss_bwd; built once per (shapes, target count, anchors, weights)."""
+    akey = tuple(tuple(map(tuple, _anchors_host(a))) for a in anchors3)   # by value
+    sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
+    key = (tuple(x.shape for x in preds3), targets.shape[0], akey, cfg.get("anchor_t", 4.0), cfg.get("edge_t", 0.5),
+           cfg.get("label_smoothing", 0.0), cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), tuple(sw))
+    hit = _loss_param_cache.get(key)
+    if hit is not None:
+        return hit
+    if len(_loss_param_cache) > 256:
+        _loss_param_cache.clear()
+    p = _loss_param_cache[key] = LossParams()
     B, _, _, na, D = preds3[0].shape
     p.B, p.C, p.na = B, D - 5, na
     for s, x in enumerate(preds3):
@@ -476,7 +509,6 @@ def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
     p.anchor_t, p.edge_t = float(cfg.get("anchor_t", 4.0)), float(cfg.get("edge_t", 0.5))
     p.label_smoothing = float(cfg.get("label_smoothing", 0.0))
     p.box_w, p.conf_w, p.class_w = float(cfg.get("box_w", 1.0)), float(cfg.get("conf_w", 1.0)), float(cfg.get("class_w", 1.0))
-    sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
     for s in range(3):
         p.scale_w[s] = float(sw[s])
     p.nt = targets.shape[0]
@@ -506,7 +538,8 @@ class _DetLoss(torch.autograd.Function):
         sm, md, lg = ctx.saved_tensors
         L = _lib.lib()
         grads = [torch.empty_like(x) for x in (sm, md, lg)]
-        go = go.detach().to(torch.float32).contiguous()
+        if go.dtype != torch.float32 or not go.is_contiguous():
+            go = go.to(torch.float32).contiguous()
         check(L.bg_loss_bwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), C.byref(ctx.params), go.data_ptr(), 1.0,
                             grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ctx.ws.data_ptr(),
                             ctx.ws.numel(), _stream()), "bg_loss_bwd")
