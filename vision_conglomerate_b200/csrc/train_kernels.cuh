@@ -156,12 +156,17 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) assign_onepass_kernel(Assign3K
     int off[ASSIGN_SLICES], tot = 0;
 #pragma unroll
     for (int i = 0; i < ASSIGN_SLICES; ++i) {
-        int woff = 0, st = 0;
-        for (int q = 0; q < ASSIGN_THREADS / 32; ++q) {
-            const int v = s_w[i][q];
-            if (q < wid) woff += v;
-            st += v;
+        // exclusive prefix of the 32 warp counts of slice i at this warp's index, and their total: one shuffle scan
+        static_assert(ASSIGN_THREADS == 1024, "one warp count per lane");
+        const int v = s_w[i][lane];
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
         }
+        const int woff = __shfl_sync(0xffffffffu, inc - v, wid);
+        const int st = __shfl_sync(0xffffffffu, inc, 31);
         off[i] = tot + woff;
         tot += st;
     }
