@@ -357,7 +357,7 @@ constexpr int LOSS_THREADS = 256;
 constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
 
 template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled class loop); 0 = runtime
-__global__ void __launch_bounds__(LOSS_THREADS) loss_match_kernel(Loss3K k)
+__global__ void __launch_bounds__(LOSS_THREADS, 6) loss_match_kernel(Loss3K k)
 {
     extern __shared__ int s_hist[];  // [3,C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
