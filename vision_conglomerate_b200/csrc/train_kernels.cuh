@@ -477,18 +477,33 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
     double a0 = 0, a1 = 0, a2 = 0;
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    for (long long c = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c < S.cells;
-         c += (long long)gridDim.x * LOSS_THREADS) {
-        const float x = ld_stride_f32(S.preds + c * k.D);
-        int w = S.head[c];  // "last match wins": the highest match index of the cell's list
-        for (int j = w; j >= 0; j = S.next[j]) w = j > w ? j : w;
-        const float t = w >= 0 ? S.ciou[w] : 0.0f;
-        const float sg = sigmoid_acc(x);
-        a0 += (double)bce_logits(x, t);
-        if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
-        // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
-        // (evict-last), so those reads do not turn into DRAM read/write turnarounds
-        asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
+    // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
+    constexpr int DENSE_PER = 4;
+    const long long stride = (long long)gridDim.x * LOSS_THREADS;
+    for (long long c0 = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c0 < S.cells; c0 += DENSE_PER * stride) {
+        float xs[DENSE_PER];
+        int ws[DENSE_PER];
+#pragma unroll
+        for (int u = 0; u < DENSE_PER; ++u) {
+            const long long c = c0 + u * stride;
+            xs[u] = 0.f; ws[u] = -1;
+            if (c < S.cells) { xs[u] = ld_stride_f32(S.preds + c * k.D); ws[u] = S.head[c]; }
+        }
+#pragma unroll
+        for (int u = 0; u < DENSE_PER; ++u) {
+            const long long c = c0 + u * stride;
+            if (c >= S.cells) break;
+            const float x = xs[u];
+            int w = ws[u];  // "last match wins": the highest match index of the cell's list
+            for (int j = w; j >= 0; j = S.next[j]) w = j > w ? j : w;
+            const float t = w >= 0 ? S.ciou[w] : 0.0f;
+            const float sg = sigmoid_acc(x);
+            a0 += (double)bce_logits(x, t);
+            if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
+            // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
+            // (evict-last), so those reads do not turn into DRAM read/write turnarounds
+            asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
+        }
     }
     a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
     if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
