@@ -246,7 +246,7 @@ const char *bg_strerror(int code)
     }
 }
 
-int bg_version(void) { return 100; }
+int bg_version(void) { return 101; }  // 101: bg_detect_params gained extra_cols and throughput
 
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
