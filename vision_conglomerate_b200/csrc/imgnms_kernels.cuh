@@ -114,6 +114,7 @@ struct ImgNmsSmem {
     int wsum[33];
     float red[4][32];
     int n_edges;
+    int next_item;                               // stage 3: warps pull 32 work items at a time
     int img;
     long long base;
 };
@@ -343,8 +344,17 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
                 }
             }
         }
+        if (tid == 0) S.next_item = 0;
         __syncthreads();
-        for (int it = tid; it < nit; it += INMS_THREADS) {
+        // a warp pulls 32 consecutive items at a time: the items differ a lot in length, and a fixed share per warp
+        // left the CTA waiting for its unluckiest warp
+        for (;;) {
+            int ibase = 0;
+            if (lane == 0) ibase = atomicAdd(&S.next_item, 32);
+            ibase = __shfl_sync(0xffffffffu, ibase, 0);
+            if (ibase >= nit) break;
+            const int it = ibase + lane;
+            if (it >= nit) continue;
             const int i = S.item_owner[it];
             const int gy = S.item_row[it];
             const float4 a = box_at(i);
