@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(1024) seg_tables_kernel(SegNms p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// kernel S: per-segment sorts (score order, then bin order) and matrix zeroing
+// kernel S: per-segment score sort, gather, and (grid mode) the grid over the box centres with its cell order
 // ------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 1024;
 constexpr int SORT_CHUNK = 8192;  // keys held in shared memory (64 KB)
