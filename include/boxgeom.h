@@ -184,8 +184,18 @@ int bg_ciou_bwd(const float *preds_xywh, const float *targets_xywh, const float 
  * DetectionLoss.forward (modules/detection_loss.py:84-226) for the default configuration
  * (BCEWithLogits, no focal loss, no keypoints): target assignment, matched-row gather, CIoU,
  * "last match wins" objectness targets, dense objectness BCE, class BCE and the per-class
- * confusion counters behind the sklearn metrics, for all three scales in one call.
+ * confusion counters behind the sklearn metrics, for all three scales in one call -- from the decoded
+ * tensors the reference's loss receives, or directly from the head's logits (the training-mode decode of
+ * DetectionNet._get_scale_pred, modules/detection.py:98-173, fused in), interleaved or as the head's three
+ * conv outputs.
  */
+#define BG_LOSS_DECODED 0   /* rows [obj, cls*C, x, y, w, h (+extra)] as DetectionNet._get_scale_pred(inference=False) returns them */
+#define BG_LOSS_RAW 1       /* the head's own rows (logits): the training-mode decode xy = 2s-0.5, wh = (2s)^2
+                             * (modules/detection.py:122,125) is applied in registers, its derivative in the backward */
+#define BG_LOSS_RAW_SPLIT 2 /* the head's three conv outputs before EffiDecHead.forward concatenates them
+                             * (modules/common.py:908-919), each permuted to channels-last:
+                             * conf [B,ny,nx,na], cls [B,ny,nx,na,C], bbox [B,ny,nx,na,4] */
+
 typedef struct {
     int32_t B, C, na;
     int32_t ny[3], nx[3];
@@ -194,24 +204,36 @@ typedef struct {
     float box_w, conf_w, class_w;
     float scale_w[3];
     int64_t nt;
+    int32_t input_form;  /* BG_LOSS_DECODED / BG_LOSS_RAW / BG_LOSS_RAW_SPLIT */
+    int32_t extra_cols;  /* interleaved forms: columns after the box columns (mask coefficients, keypoints) that the loss
+                          * skips; rows are 5 + C + extra_cols floats and their gradient is written as zeros */
 } bg_loss_params;
 
+/* One scale of the prediction tensors.  Interleaved forms: `obj` is the base of the [B,ny,nx,na,5+C+extra] tensor,
+ * `cls` / `box` are ignored.  BG_LOSS_RAW_SPLIT: the three tensors.  All 16-byte aligned, contiguous. */
+typedef struct { const float *obj, *cls, *box; } bg_head_ptrs;
+typedef struct { float *obj, *cls, *box; } bg_head_grads;
+
 size_t bg_loss_workspace_bytes(const bg_loss_params *p /*host*/);
-/*   preds_* [B,ny,nx,na,5+C] f32 (training-mode decoded, 16-byte aligned); targets [nt,6] f32.
+/*   in[3] (host array of device pointers): scales sm, md, lg;  targets [nt,6] f32.
  *   out_scalars [3,8] f64 per scale: lbox, lconf, lcls (NaN->0 applied), mean_ciou, avg_pos_conf,
  *                 avg_neg_conf, M, n_neg;   out_hist [3,3,C] i64: tp, n_true, n_pred per class;
- *   out_loss [1] f32: box_w*sum_s(scale_w*lbox) + conf_w*... + class_w*...  (:107-110).
- *   The workspace keeps what bg_loss_bwd needs (matches, CIoU gradients, objectness residuals).
+ *   out_loss [1] f32: box_w*sum_s(scale_w*lbox) + conf_w*... + class_w*...  (:107-110);
+ *   out_status [1] i32 (may be NULL): bit 0 = a target row names an image outside 0..B-1 or a class outside 0..C-1
+ *                 (the reference raises IndexError there; here the row is dropped and the bit is set).
+ *   The workspace keeps what bg_loss_bwd needs (matches, CIoU gradients, objectness residuals): it must stay
+ *   untouched until the matching bg_loss_bwd has run -- use one workspace per forward that is still awaiting
+ *   its backward.  Launches: one memset + three kernels (the 2nd and 3rd with programmatic dependent launch).
  */
-int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const float *targets,
-                const bg_loss_params *p /*host*/, double *out_scalars, int64_t *out_hist, float *out_loss,
-                void *workspace, size_t workspace_bytes, void *stream);
-/*   grad_* [same shape as preds_*]: d(grad_out * loss)/d preds, every element written.  The upstream
- *   gradient is read from device memory (grad_out_dev [1] f32) when non-NULL -- no host sync in
- *   loss.backward() -- else grad_out_host is used. */
-int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const bg_loss_params *p /*host*/,
-                const float *grad_out_dev, float grad_out_host, float *grad_sm, float *grad_md, float *grad_lg,
-                void *workspace, size_t workspace_bytes, void *stream);
+int bg_loss_fwd(const bg_head_ptrs in[3] /*host*/, const float *targets, const bg_loss_params *p /*host*/,
+                double *out_scalars, int64_t *out_hist, float *out_loss, int32_t *out_status, void *workspace,
+                size_t workspace_bytes, void *stream);
+/*   grads[3]: d(grad_out * loss)/d in, same form and shapes as `in`, every element written (BG_LOSS_RAW*: the
+ *   gradient with respect to the logits).  The upstream gradient is read from device memory (grad_out_dev [1] f32)
+ *   when non-NULL -- no host sync in loss.backward() -- else grad_out_host is used. */
+int bg_loss_bwd(const bg_head_ptrs in[3] /*host*/, const bg_loss_params *p /*host*/, const float *grad_out_dev,
+                float grad_out_host, const bg_head_grads grads[3] /*host*/, void *workspace, size_t workspace_bytes,
+                void *stream);
 
 /* ------------------------------------------------------------------ a13
  * utils/make_anchors.py:14-39 ratio_metrics / ratio_metrics_w_extras.

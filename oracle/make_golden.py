@@ -238,13 +238,24 @@ LOSS_CASES = {
 }
 
 
-def gen_loss(ns):
+def gen_loss(ns, raw=False):
+    """raw=False: the loss on given (already decoded) tensors.  raw=True: the same seeded tensors taken as the
+    HEAD's outputs -- the unmodified ``DetectionNet._get_scale_pred(inference=False)`` (modules/detection.py:98-173)
+    decodes them first, exactly as ``DetectionNet.forward`` does, and the gradient is taken back to the logits."""
     torch.set_num_threads(1)  # the reference's duplicate-index scatter is racy with more (SURVEY A.3)
     for name, (B, H, W, C, G, fixed, ts, ps) in LOSS_CASES.items():
+        if raw and name not in RAW_LOSS_CASES:
+            continue
         t = synth.targets(B, G, C, ts, fixed) if G > 0 else torch.zeros(0, 6)
         preds = [p.requires_grad_(True) for p in synth.train_preds(B, H, W, C, ps)]
         loss_mod = ns.DetectionLoss(ns.FakeModel(C, synth.ANCHORS), **synth.LOSS_CONFIG)
-        loss, metrics = loss_mod(tuple(preds), t.clone())
+        if raw:
+            net = ns.DecodeOnly(C)
+            dec = tuple(net._get_scale_pred(p, synth.anchors_tensor(sc), input_shape=(H, W), inference=False)
+                        for p, sc in zip(preds, synth.SCALES))
+            loss, metrics = loss_mod(dec, t.clone())
+        else:
+            loss, metrics = loss_mod(tuple(preds), t.clone())
         loss.backward()
         kw = dict(params=np.array([B, H, W, C, G, int(fixed), ts, ps]), in_digest=np.array(digest(t, *preds)),
                   loss=np.array(loss.item(), np.float64),
@@ -262,7 +273,10 @@ def gen_loss(ns):
                 kw["grad_" + sc + "_rows"] = g[sel[:, 0], sel[:, 1], sel[:, 2], sel[:, 3]].numpy()
             else:
                 kw["grad_" + sc] = g.numpy()
-        save(name, **kw)
+        save(("lossraw_" + name[5:]) if raw else name, **kw)
+
+
+RAW_LOSS_CASES = ("loss_sq64", "loss_collide", "loss_empty", "loss_c1_640")
 
 
 def gen_ratio(ns):
@@ -284,5 +298,6 @@ if __name__ == "__main__":
     gen_assign_variants(ns)
     gen_ciou(ns)
     gen_loss(ns)
+    gen_loss(ns, raw=True)
     gen_ratio(ns)
     print("torch", torch.__version__, "torchvision", torchvision.__version__)

@@ -261,9 +261,42 @@ def loss_scale(preds, targets, anchors, cfg: dict, w_scale: float, with_grad: bo
     return scal, m, grad, M
 
 
-def detection_loss(preds3: Sequence, targets, anchors3: Sequence, cfg: dict, with_grad: bool = False):
+def train_decode(raw) -> np.ndarray:
+    """Training-mode ``DetectionNet._get_scale_pred`` (modules/detection.py:122,125,164): xy = 2s - 0.5,
+    wh = (2s)^2 on the four box columns, objectness / class logits copied."""
+    raw = _np(raw, np.float32)
+    return decode_scale(raw, np.ones((raw.shape[3], 2), np.float32), 1, 1, inference=False)
+
+
+def train_decode_backward(raw, grad_decoded) -> np.ndarray:
+    """Chain rule of :func:`train_decode` (what autograd does through sigmoid / mul / sub / pow), in float64."""
+    raw = _np(raw, np.float32)
+    g = np.array(grad_decoded, dtype=np.float64, copy=True)
+    Cc = raw.shape[-1] - 5
+    s = 1.0 / (1.0 + np.exp(-raw[..., Cc + 1:Cc + 5].astype(np.float64)))
+    g[..., Cc + 1:Cc + 3] *= 2.0 * s[..., :2] * (1.0 - s[..., :2])
+    g[..., Cc + 3:Cc + 5] *= 8.0 * s[..., 2:] ** 2 * (1.0 - s[..., 2:])
+    return g.astype(np.float32)
+
+
+def detection_loss(preds3: Sequence, targets, anchors3: Sequence, cfg: dict, with_grad: bool = False,
+                   input_form: str = "decoded"):
     """modules/detection_loss.py:84-122 (DetectionLoss.forward) on the default BCE configuration.
-    Returns (loss, metrics_dict, [grad_sm, grad_md, grad_lg] or None, [M_sm, M_md, M_lg])."""
+    Returns (loss, metrics_dict, [grad_sm, grad_md, grad_lg] or None, [M_sm, M_md, M_lg]).
+
+    ``input_form="raw"``: ``preds3`` are the head's own outputs; the training-mode decode of
+    modules/detection.py:98-173 runs first (what ``DetectionNet.forward`` does before the loss sees the tensors)
+    and the gradients are taken back through it.  ``"split"``: per scale ``(conf [B,ny,nx,na], cls [...,C],
+    bbox [...,4])``, the conv outputs ``EffiDecHead.forward`` concatenates (modules/common.py:908-919); gradients
+    come back as the same triples."""
+    raws = None
+    if input_form == "split":
+        raws = [np.concatenate([_np(c, np.float32).reshape(*_np(k, np.float32).shape[:4], 1), _np(k, np.float32),
+                                _np(b, np.float32)], axis=-1) for c, k, b in preds3]
+    elif input_form == "raw":
+        raws = [_np(p, np.float32) for p in preds3]
+    if raws is not None:
+        preds3 = [train_decode(r) for r in raws]
     sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
     lbox = lconf = lcls = 0.0
     rows, grads, Ms = [], [], []
@@ -280,6 +313,10 @@ def detection_loss(preds3: Sequence, targets, anchors3: Sequence, cfg: dict, wit
     for k in rows[0]:
         vals = np.array([r[k] for r in rows], np.float64)
         metrics[k] = float(np.nanmean(vals)) if not np.all(np.isnan(vals)) else float("nan")
+    if with_grad and raws is not None:
+        grads = [train_decode_backward(r, g) for r, g in zip(raws, grads)]
+        if input_form == "split":
+            grads = [(g[..., 0].copy(), g[..., 1:-4].copy(), g[..., -4:].copy()) for g in grads]
     return float(loss), metrics, (grads if with_grad else None), Ms
 
 

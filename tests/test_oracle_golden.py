@@ -150,15 +150,25 @@ def test_ciou():
     assert_close(grad * g["w"][:, None], g["grad"], rtol=1e-4, atol=1e-5, what="ciou grad")
 
 
-@pytest.mark.parametrize("name", ["loss_sq64", "loss_collide", "loss_c3_rect", "loss_empty", "loss_c1_640"])
+@pytest.mark.parametrize("name", ["loss_sq64", "loss_collide", "loss_c3_rect", "loss_empty", "loss_c1_640",
+                                  "lossraw_sq64", "lossraw_collide", "lossraw_empty", "lossraw_c1_640"])
 def test_loss(name):
+    """loss_*: the loss on decoded tensors.  lossraw_*: the same tensors as the head's logits, decoded by the
+    unmodified _get_scale_pred(inference=False) first, gradients back to the logits (the fused raw form)."""
     g = golden(name)
     B, H, W, C, G, fixed, ts, ps = (int(v) for v in g["params"])
     t = synth.targets(B, G, C, ts, bool(fixed)) if G > 0 else torch.zeros(0, 6)
     preds = synth.train_preds(B, H, W, C, ps)
     assert digest(t, *preds) == str(g["in_digest"])
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
-    loss, metrics, grads, Ms = O.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_grad=True)
+    form = "raw" if name.startswith("lossraw_") else "decoded"
+    loss, metrics, grads, Ms = O.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_grad=True, input_form=form)
+    if form == "raw":  # the split form is the same computation on the three column groups
+        tri = [(p[..., 0].contiguous(), p[..., 1:1 + C].contiguous(), p[..., 1 + C:].contiguous()) for p in preds]
+        loss_s, _, grads_s, _ = O.detection_loss(tri, t, anc, synth.LOSS_CONFIG, with_grad=True, input_form="split")
+        assert loss_s == loss
+        for gr, (gc, gk, gb) in zip(grads, grads_s):
+            assert np.array_equal(gr[..., 0], gc) and np.array_equal(gr[..., 1:1 + C], gk) and np.array_equal(gr[..., 1 + C:], gb)
     assert_close(loss, float(g["loss"]), rtol=1e-5, atol=0, what="loss")
     ref_m = dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"]))
     for k, v in ref_m.items():

@@ -61,7 +61,20 @@ class LossParams(C.Structure):
         ("box_w", C.c_float), ("conf_w", C.c_float), ("class_w", C.c_float),
         ("scale_w", C.c_float * 3),
         ("nt", C.c_int64),
+        ("input_form", C.c_int32),
+        ("extra_cols", C.c_int32),
     ]
+
+
+LOSS_DECODED, LOSS_RAW, LOSS_RAW_SPLIT = 0, 1, 2
+
+
+class HeadPtrs(C.Structure):
+    """One scale of the loss inputs / gradients (bg_head_ptrs, bg_head_grads): interleaved forms use `obj` only."""
+    _fields_ = [("obj", C.c_void_p), ("cls", C.c_void_p), ("box", C.c_void_p)]
+
+
+HeadPtrs3 = HeadPtrs * 3
 
 
 def build(force: bool = False) -> str:
@@ -121,8 +134,8 @@ def lib() -> C.CDLL:
     L.bg_ciou_bwd.argtypes = [vp, vp, vp, i64, f32, vp, vp]
     L.bg_loss_workspace_bytes.argtypes = [C.POINTER(LossParams)]
     L.bg_loss_workspace_bytes.restype = sz
-    L.bg_loss_fwd.argtypes = [vp, vp, vp, vp, C.POINTER(LossParams), vp, vp, vp, vp, sz, vp]
-    L.bg_loss_bwd.argtypes = [vp, vp, vp, C.POINTER(LossParams), vp, f32, vp, vp, vp, vp, sz, vp]
+    L.bg_loss_fwd.argtypes = [C.POINTER(HeadPtrs), vp, C.POINTER(LossParams), vp, vp, vp, vp, vp, sz, vp]
+    L.bg_loss_bwd.argtypes = [C.POINTER(HeadPtrs), C.POINTER(LossParams), vp, f32, C.POINTER(HeadPtrs), vp, sz, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_ratio_metrics"):

@@ -3,6 +3,7 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <math.h>
 #include <stdlib.h>
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -10,12 +11,15 @@
 #include "detect_kernels.cuh"
 #include "imgnms_kernels.cuh"
 #include "train_kernels.cuh"
+#include "loss_kernels.cuh"
 
 namespace bg {
 
-unsigned long long g_launches = 0;
-static cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
-static unsigned long long *g_prof_stamps = nullptr, *g_prof_cycles = nullptr;
+std::atomic<unsigned long long> g_launches{0};
+// profiling hooks are armed per host thread (the thread that arms one is the thread whose next call sees it), so
+// concurrent callers on other threads are unaffected and the entry points stay re-entrant
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static thread_local unsigned long long *g_prof_stamps = nullptr, *g_prof_cycles = nullptr;
 
 IouThr make_iou_thr(double thr)
 {
@@ -46,6 +50,25 @@ struct Bump {  // workspace carving; with base == nullptr it only measures
         return p;
     }
 };
+
+// launch behind the previous kernel of the stream with programmatic stream serialization: the grid may become
+// resident while its predecessor drains; the kernel itself calls griddepcontrol.wait before touching upstream data
+template <typename K>
+int launch_after(void (*kern)(K), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const K &arg, bool after_kernel = true)
+{
+    static const bool pdl_env = []() { const char *e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
+    const bool pdl = pdl_env && after_kernel;  // only behind a kernel of ours (not behind a memset)
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    if (cudaLaunchKernelEx(&cfg, kern, arg) != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
+    ++g_launches;
+    return BG_OK;
+}
 
 static int cur_device()
 {
@@ -246,7 +269,7 @@ const char *bg_strerror(int code)
     }
 }
 
-int bg_version(void) { return 101; }  // 101: bg_detect_params gained extra_cols and throughput
+int bg_version(void) { return 200; }  // 200: bg_loss_* take the input form (decoded / raw / raw split) and per-scale pointer triples
 
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
@@ -659,22 +682,17 @@ int bg_ciou_bwd(const float *p, const float *t, const float *go, int64_t M, floa
 // ------------------------------------------------------------------------------------------ B3
 namespace {
 struct LossWs {
-    u64 *chain[3];        // contiguous (one memset)
-    size_t chain_words;
-    int *M;               // [3]
-    int *cell[3];
-    int *cls[3];
-    float *anchor[3];
-    float *box[3];
+    int *M;               // [3] + status [1]   } one zero-filled block: counters, status, confusion counters,
+    long long *hist;      // [3,3,C]            } succ flags and the cells' list heads
+    unsigned char *succ;  // all scales
+    int *head;            // all scales
+    size_t zero_begin, zero_bytes;
+    float *gobj;          // all scales, contiguous
+    int *cell[3], *cls[3], *key[3], *next[3];
     float *ciou[3];
     float4 *gbox[3];
-    int *head;            // all scales, contiguous (one memset)
-    int *next[3];
-    unsigned char *succ;  // all scales, contiguous (one memset)
-    float *gobj;          // all scales, contiguous
     double *part_match[3];
     double *part_dense[3];
-    size_t zero_begin, zero_bytes;  // workspace range cleared before the assignment (chain words + succ flags)
     long long cap;
     long long cells[3], cell_off[3], cells_total;
     int nblk_match, nblk_dense;
@@ -683,10 +701,12 @@ struct LossWs {
 bool loss_valid(const bg_loss_params *p)
 {
     if (!p || p->B <= 0 || p->C <= 0 || p->C > 4096 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->nt < 0) return false;
+    if (p->input_form < BG_LOSS_DECODED || p->input_form > BG_LOSS_RAW_SPLIT || p->extra_cols < 0 || p->extra_cols > 4096) return false;
+    if (p->input_form == BG_LOSS_RAW_SPLIT && p->extra_cols != 0) return false;
     if (5ll * p->na * p->nt >= (1ll << 31)) return false;
     for (int s = 0; s < 3; ++s) {
         if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
-        if ((long long)p->B * p->ny[s] * p->nx[s] * p->na * (p->C + 5) >= (1ll << 40)) return false;
+        if ((long long)p->B * p->ny[s] * p->nx[s] * p->na * (p->C + 5 + p->extra_cols) >= (1ll << 40)) return false;
         if ((long long)p->B * p->ny[s] * p->nx[s] * p->na >= (1ll << 31)) return false;
     }
     return true;
@@ -697,17 +717,9 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     Bump b{base, 0};
     const int sms = num_sms();
     w.cap = 5ll * p->na * p->nt;
+    w.nblk_match = (int)((w.cap + MATCH_CHUNK - 1) / MATCH_CHUNK);
     if (w.cap < 1) w.cap = 1;
-    w.nblk_match = sms * 8;
     w.nblk_dense = sms * 8;
-    w.chain_words = assign_chain_words(p->nt, p->na);
-    {   // look-back words of the assignment and the succ flags are zeroed by ONE memset: keep them adjacent
-        u64 *all = b.take<u64>(3 * w.chain_words);
-        for (int s = 0; s < 3; ++s) w.chain[s] = all ? all + s * w.chain_words : nullptr;
-        w.zero_begin = b.off - 3 * w.chain_words * sizeof(u64);
-        w.succ = b.take<unsigned char>(3 * (size_t)w.cap);
-        w.zero_bytes = b.off - w.zero_begin;
-    }
     w.cells_total = 0;
     for (int s = 0; s < 3; ++s) {
         w.cells[s] = (long long)p->B * p->ny[s] * p->nx[s] * p->na;
@@ -715,41 +727,76 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
         w.cells_total += w.cells[s];
     }
     w.M = b.take<int>(4);
+    w.zero_begin = b.off - 4 * sizeof(int);
+    w.hist = b.take<long long>(9 * (size_t)p->C);
+    w.succ = b.take<unsigned char>(3 * (size_t)w.cap);
     w.head = b.take<int>(w.cells_total);
+    w.zero_bytes = b.off - w.zero_begin;
     w.gobj = b.take<float>(w.cells_total);
     for (int s = 0; s < 3; ++s) {
         w.cell[s] = b.take<int>(w.cap);
         w.cls[s] = b.take<int>(w.cap);
-        w.anchor[s] = b.take<float>(2 * w.cap);
-        w.box[s] = b.take<float>(4 * w.cap);
+        w.key[s] = b.take<int>(w.cap);
         w.ciou[s] = b.take<float>(w.cap);
         w.gbox[s] = b.take<float4>(w.cap);
         w.next[s] = b.take<int>(w.cap);
-        w.part_match[s] = b.take<double>((size_t)w.nblk_match * 4);
+        w.part_match[s] = b.take<double>((size_t)(w.nblk_match > 0 ? w.nblk_match : 1) * 4);
         w.part_dense[s] = b.take<double>((size_t)w.nblk_dense * 3);
     }
     return align_up(b.off, 256);
 }
 
-void loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const float *const preds[3], float *const grads[3])
+// in/grads: per scale {obj, cls, box}.  Interleaved forms pass the row base as `obj` (cls/box are derived).
+bool loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const bg_head_ptrs in[3], const bg_head_grads *grads,
+               const float *targets)
 {
     memset(&k, 0, sizeof(k));
-    k.C = p->C; k.D = p->C + 5;
+    k.B = p->B; k.C = p->C;
+    k.raw = p->input_form != BG_LOSS_DECODED;
     // python: cn = 0.5 * label_smoothing, cp = 1 - cn in double, written into fp32 tensors (detection_loss.py:191-195)
     k.cn = (float)(0.5 * (double)p->label_smoothing);
     k.cp = (float)(1.0 - 0.5 * (double)p->label_smoothing);
     k.nblk_match = w.nblk_match; k.nblk_dense = w.nblk_dense;
     k.box_w = p->box_w; k.conf_w = p->conf_w; k.class_w = p->class_w;
+    k.status = w.M + 3;
+    const int D = p->C + 5 + p->extra_cols;
+    const bool split = p->input_form == BG_LOSS_RAW_SPLIT;
     for (int s = 0; s < 3; ++s) {
         LossScale &S = k.s[s];
-        S.preds = preds[s]; S.grad = grads ? grads[s] : nullptr; S.cells = w.cells[s];
-        S.M = w.M + s; S.cell = w.cell[s]; S.cls = w.cls[s]; S.anchor = w.anchor[s]; S.box = w.box[s];
+        HeadView &v = S.v;
+        if (split) {
+            if (!in[s].obj || !in[s].cls || !in[s].box) return false;
+            if (((uintptr_t)in[s].obj | (uintptr_t)in[s].cls | (uintptr_t)in[s].box) & 15) return false;
+            v.obj = in[s].obj; v.cls = in[s].cls; v.box = in[s].box;
+            v.so = 1; v.sc = p->C; v.sb = 4;
+            if (grads) {
+                if (!grads[s].obj || !grads[s].cls || !grads[s].box) return false;
+                if (((uintptr_t)grads[s].obj | (uintptr_t)grads[s].cls | (uintptr_t)grads[s].box) & 15) return false;
+                v.g_obj = grads[s].obj; v.g_cls = grads[s].cls; v.g_box = grads[s].box;
+            }
+        } else {
+            if (!in[s].obj || ((uintptr_t)in[s].obj & 15)) return false;
+            v.obj = in[s].obj; v.cls = in[s].obj + 1; v.box = in[s].obj + 1 + p->C;
+            v.so = v.sc = v.sb = D;
+            if (grads) {
+                if (!grads[s].obj || ((uintptr_t)grads[s].obj & 15)) return false;
+                v.g_obj = grads[s].obj; v.g_cls = grads[s].obj + 1; v.g_box = grads[s].obj + 1 + p->C;
+            }
+        }
+        S.cells = w.cells[s];
+        float anc[2 * BG_MAX_ANCHORS];
+        for (int q = 0; q < p->na; ++q) { anc[2 * q] = p->anchors[s][q][0]; anc[2 * q + 1] = p->anchors[s][q][1]; }
+        assign_fill(S.a, targets, p->nt, p->ny[s], p->nx[s], anc, p->na, p->anchor_t, p->edge_t);
+        S.M = w.M + s; S.cell = w.cell[s]; S.cls = w.cls[s]; S.key = w.key[s];
         S.ciou = w.ciou[s]; S.gbox = w.gbox[s];
         S.head = w.head + w.cell_off[s]; S.next = w.next[s]; S.succ = w.succ + (size_t)s * w.cap; S.gobj = w.gobj + w.cell_off[s];
         S.part_match = w.part_match[s]; S.part_dense = w.part_dense[s];
+        S.hist = w.hist + (size_t)s * 3 * p->C;
         S.scale_w = p->scale_w[s];
     }
+    return true;
 }
+
 }  // namespace
 
 size_t bg_loss_workspace_bytes(const bg_loss_params *p)
@@ -759,68 +806,77 @@ size_t bg_loss_workspace_bytes(const bg_loss_params *p)
     return loss_carve(nullptr, p, w);
 }
 
-int bg_loss_fwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const float *targets,
-                const bg_loss_params *p, double *out_scalars, int64_t *out_hist, float *out_loss, void *workspace,
-                size_t workspace_bytes, void *stream)
+int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_params *p, double *out_scalars,
+                int64_t *out_hist, float *out_loss, int32_t *out_status, void *workspace, size_t workspace_bytes,
+                void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!loss_valid(p) || !preds_sm || !preds_md || !preds_lg || !out_scalars || !out_hist || !out_loss || !workspace)
-        return BG_ERR_INVALID;
+    if (!loss_valid(p) || !in || !out_scalars || !out_hist || !out_loss || !workspace) return BG_ERR_INVALID;
     if (p->nt > 0 && !targets) return BG_ERR_INVALID;
-    if (((uintptr_t)preds_sm | (uintptr_t)preds_md | (uintptr_t)preds_lg) & 15) return BG_ERR_INVALID;
     LossWs w;
     if (loss_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
-    const float *preds[3] = {preds_sm, preds_md, preds_lg};
-    if (cudaMemsetAsync(out_hist, 0, sizeof(int64_t) * 9 * (size_t)p->C, st) != cudaSuccess) return BG_ERR_LAUNCH;
-    if (cudaMemsetAsync(w.head, 0xff, sizeof(int) * (size_t)w.cells_total, st) != cudaSuccess) return BG_ERR_LAUNCH;
-    Assign3K a3;
-    for (int s = 0; s < 3; ++s) {
-        AssignK &a = a3.a[s];
-        float anc[2 * BG_MAX_ANCHORS];
-        for (int q = 0; q < p->na; ++q) { anc[2 * q] = p->anchors[s][q][0]; anc[2 * q + 1] = p->anchors[s][q][1]; }
-        assign_fill(a, targets, p->nt, p->ny[s], p->nx[s], anc, p->na, p->anchor_t, p->edge_t);
-        a.chain = w.chain[s];
-        a.anchor = w.anchor[s]; a.box = w.box[s]; a.cell = w.cell[s]; a.cls32 = w.cls[s];
-        a.cap = w.cap; a.count = w.M + s;
-    }
-    if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
-    int rc = assign_launch(a3, 3, st);
-    if (rc != BG_OK) return rc;
     Loss3K k;
-    loss_fill(k, p, w, preds, nullptr);
-    for (int s = 0; s < 3; ++s) k.s[s].hist = reinterpret_cast<long long *>(out_hist) + (size_t)s * 3 * p->C;
+    if (!loss_fill(k, p, w, in, nullptr, targets)) return BG_ERR_INVALID;
+    for (int s = 0; s < 3; ++s) k.s[s].hist_out = reinterpret_cast<long long *>(out_hist) + (size_t)s * 3 * p->C;
     k.scalars = out_scalars;
     k.loss_out = out_loss;
-    if (p->C == 80) loss_match_kernel<80><<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
-    else loss_match_kernel<0><<<dim3(w.nblk_match, 3), LOSS_THREADS, 3 * p->C * sizeof(int), st>>>(k);
-    BG_LAUNCH_CHECK();
-    loss_dense_kernel<<<dim3(w.nblk_dense, 3), LOSS_THREADS, 0, st>>>(k);
-    BG_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 768, 0, st>>>(k);
-    BG_LAUNCH_CHECK();
+    // one clear: match counters, status word, confusion counters, succ flags, list heads
+    if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (p->nt > 0) {
+        const dim3 grid(w.nblk_match, 3);
+        const size_t smem = 3 * (size_t)p->C * sizeof(int);
+        if (p->C == 80) {
+            if (k.raw) loss_match_kernel<80, 1><<<grid, LOSS_THREADS, smem, st>>>(k);
+            else loss_match_kernel<80, 0><<<grid, LOSS_THREADS, smem, st>>>(k);
+        } else {
+            if (k.raw) loss_match_kernel<0, 1><<<grid, LOSS_THREADS, smem, st>>>(k);
+            else loss_match_kernel<0, 0><<<grid, LOSS_THREADS, smem, st>>>(k);
+        }
+        BG_LAUNCH_CHECK();
+    }
+    int rc = launch_after(loss_dense_kernel, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0);
+    if (rc != BG_OK) return rc;
+    rc = launch_after(loss_finalize_kernel, dim3(1), dim3(768), 0, st, k);
+    if (rc != BG_OK) return rc;
+    if (out_status && cudaMemcpyAsync(out_status, k.status, sizeof(int), cudaMemcpyDeviceToDevice, st) != cudaSuccess) return BG_ERR_LAUNCH;
     return BG_OK;
 }
 
-int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds_lg, const bg_loss_params *p,
-                const float *grad_out_dev, float grad_out_host, float *grad_sm, float *grad_md, float *grad_lg,
-                void *workspace, size_t workspace_bytes, void *stream)
+int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *grad_out_dev, float grad_out_host,
+                const bg_head_grads grads[3], void *workspace, size_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!loss_valid(p) || !preds_sm || !preds_md || !preds_lg || !grad_sm || !grad_md || !grad_lg || !workspace)
-        return BG_ERR_INVALID;
-    if (((uintptr_t)preds_sm | (uintptr_t)preds_md | (uintptr_t)preds_lg | (uintptr_t)grad_sm | (uintptr_t)grad_md | (uintptr_t)grad_lg) & 15)
-        return BG_ERR_INVALID;
+    if (!loss_valid(p) || !in || !grads || !workspace) return BG_ERR_INVALID;
     LossWs w;
     if (loss_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
-    const float *preds[3] = {preds_sm, preds_md, preds_lg};
-    float *grads[3] = {grad_sm, grad_md, grad_lg};
     Loss3K k;
-    loss_fill(k, p, w, preds, grads);
+    if (!loss_fill(k, p, w, in, grads, nullptr)) return BG_ERR_INVALID;
     k.go_dev = grad_out_dev;
     k.go_host = grad_out_host;
     const int sms = num_sms();
-    {
-        const size_t smem = (size_t)BWD_WARPS * 32 * k.D * sizeof(float);
+    if (p->input_form == BG_LOSS_RAW_SPLIT) {
+        // class / box planes: cleared by memset (adjacent planes are cleared by one call), objectness plane by a kernel
+        struct Run { unsigned char *p; size_t n; } runs[6];
+        int nr = 0;
+        for (int s = 0; s < 3; ++s) {
+            runs[nr++] = Run{(unsigned char *)grads[s].cls, (size_t)w.cells[s] * p->C * sizeof(float)};
+            runs[nr++] = Run{(unsigned char *)grads[s].box, (size_t)w.cells[s] * 4 * sizeof(float)};
+        }
+        for (int i = 1; i < nr; ++i)  // insertion sort by address
+            for (int j = i; j > 0 && runs[j].p < runs[j - 1].p; --j) { const Run t = runs[j]; runs[j] = runs[j - 1]; runs[j - 1] = t; }
+        for (int i = 0; i < nr;) {
+            unsigned char *b0 = runs[i].p;
+            size_t n = runs[i].n;
+            int j = i + 1;
+            while (j < nr && runs[j].p == b0 + n) { n += runs[j].n; ++j; }
+            if (cudaMemsetAsync(b0, 0, n, st) != cudaSuccess) return BG_ERR_LAUNCH;
+            i = j;
+        }
+        loss_bwd_conf_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(k);
+        BG_LAUNCH_CHECK();
+    } else {
+        const int D = p->C + 5 + p->extra_cols;
+        const size_t smem = (size_t)BWD_WARPS * 32 * D * sizeof(float);
         if (smem > 200 * 1024) return BG_ERR_INVALID;  // rows longer than ~780 floats do not fit the chunk images
         static size_t attr_smem_dev[64] = {0};
         size_t &attr_smem = attr_smem_dev[cur_device()];
@@ -840,10 +896,9 @@ int bg_loss_bwd(const float *preds_sm, const float *preds_md, const float *preds
         loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
         BG_LAUNCH_CHECK();
     }
-    if (k.C == 80) loss_bwd_rows_kernel<80><<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
-    else loss_bwd_rows_kernel<0><<<dim3(sms * 8, 3), LOSS_THREADS, 0, st>>>(k);
-    BG_LAUNCH_CHECK();
-    return BG_OK;
+    if (p->nt == 0) return BG_OK;
+    if (k.C == 80) return launch_after(loss_bwd_rows_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
+    return launch_after(loss_bwd_rows_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
 }
 
 // ------------------------------------------------------------------------------------------ a13

@@ -2,12 +2,13 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 #include "../../include/boxgeom.h"
 
 namespace bg {
 
-extern unsigned long long g_launches;  // host-side count of kernels enqueued by this library
+extern std::atomic<unsigned long long> g_launches;  // host-side count of kernels enqueued by this library
 
 #define BG_LAUNCH_CHECK()                                   \
     do {                                                    \

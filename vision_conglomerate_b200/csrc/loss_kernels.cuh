@@ -1,0 +1,543 @@
+// The fused detection loss (modules/detection_loss.py:84-226) for the default BCE configuration: target
+// assignment, matched-row gather, CIoU, "last match wins" objectness targets, dense objectness BCE, class BCE,
+// confusion counters, and the backward that writes the dense gradient.  Every kernel covers the three scales.
+//
+// Input forms (HeadView / Loss3K::raw):
+//   decoded rows   [B,ny,nx,na,5+C]: what DetectionNet._get_scale_pred(inference=False) returns (detection.py:98-173);
+//   raw rows       the head's own output (logits): the training-mode decode xy = 2s-0.5, wh = (2s)^2 (:122,125) is
+//                  applied in registers in the forward and its derivative in the backward;
+//   raw, split     the head's three conv outputs before EffiDecHead.forward concatenates them (common.py:908-919):
+//                  conf [B,ny,nx,na], cls [B,ny,nx,na,C], bbox [B,ny,nx,na,4]: the objectness plane is
+//                  contiguous and the gradient comes back in the same three pieces.
+//
+//   forward : loss_match_kernel   one block per 512 assignment candidates (k, a, t): evaluates the YOLOv5 rule
+//                                 (dataset/detection_dataset.py:90-246), allots the block's matches a range of the
+//                                 match arrays with one atomic, then per match: gather, CIoU and its gradient, link
+//                                 into the cell's list; eight lanes per match: class BCE, argmax, confusion counters.
+//                                 The reference's (k, a, t) order survives as the candidate number ("key") of a match.
+//             loss_dense_kernel   one thread per cell: objectness BCE against the CIoU of the cell's LAST match in
+//                                 the reference's order (= highest key in the cell's list); keeps sigmoid(x) - t
+//             loss_finalize_kernel  fixed-order reduction of the per-block partial sums, scalars, total loss
+//   backward: loss_bwd_stream_kernel  (interleaved rows) zeros + the objectness column, written like a fill
+//             loss_bwd_conf_kernel    (split) the objectness plane; the class / box planes are cleared by memset
+//             loss_bwd_rows_kernel    class / box columns of the matched rows, summed over the cell's match list
+//                                     (gather backward = index_put(accumulate=True)); no atomics
+// Results do not depend on the order in which blocks run: sums are per block in a fixed order, the match arrays'
+// slot order (the only thing the atomics decide) never reaches a result, integer counters are exact.
+#pragma once
+#include "train_kernels.cuh"
+
+namespace bg {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+struct HeadView {
+    const float *obj, *cls, *box;  // element j of a cell: obj[cell*so], cls[cell*sc + j], box[cell*sb + j]
+    float *g_obj, *g_cls, *g_box;  // backward outputs, same strides
+    int so, sc, sb;
+};
+
+struct LossScale {
+    HeadView v;
+    long long cells;     // B*ny*nx*na
+    AssignK a;           // assignment parameters of this scale (targets, anchors in grid units, thresholds)
+    int *M;              // [1] number of matches (the blocks' allocation counter, zeroed by the host)
+    int *cell;           // [cap] ((b*ny+gj)*nx+gi)*na+a
+    int *cls;            // [cap]
+    int *key;            // [cap] candidate number (k*na + a)*nt + t: the reference's match order
+    float *ciou;         // [cap]
+    float4 *gbox;        // [cap] d ciou / d (the four box values as stored in the input tensor)
+    int *head;           // [cells] 1 + the most recently linked match of the cell (0: none; zeroed by the host); list through next[]
+    int *next;           // [cap] previously linked match of the same cell, -1 for the first linked
+    unsigned char *succ; // [cap] 1 if another match was linked in front of this one (zeroed by the host)
+    float *gobj;         // [cells] sigmoid(obj) - t_conf
+    double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
+    double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
+    long long *hist;     // [3,C] in the workspace (zeroed by the host)
+    long long *hist_out; // [3,C] caller's copy, written by the finalize kernel
+    double scale_w;
+};
+
+struct Loss3K {
+    LossScale s[3];
+    int B, C;
+    int raw;             // 1: the box values are logits, decode in registers
+    float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
+    int nblk_match, nblk_dense;
+    double box_w, conf_w, class_w;
+    double *scalars;     // [3,8]
+    float *loss_out;     // [1] total loss (modules/detection_loss.py:107-110)
+    int *status;         // [1] bit 0: a target's image id or class id is outside the batch / class range (dropped)
+    const float *go_dev; // backward: upstream gradient on the device (or null -> go_host)
+    float go_host;
+};
+
+__device__ __forceinline__ float bce_logits(float x, float t)
+{
+    // ATen binary_cross_entropy_with_logits: (1 - t) * x - log_sigmoid(x)
+    const float ls = __fsub_rn(fminf(x, 0.0f), log1pf(expf(-fabsf(x))));
+    return __fsub_rn(__fmul_rn(__fsub_rn(1.0f, t), x), ls);
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+constexpr int LOSS_THREADS = 256;
+constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
+constexpr int MATCH_PER = 2;     // assignment candidates per thread
+constexpr int MATCH_CHUNK = LOSS_THREADS * MATCH_PER;
+
+template <int CT, int RAW>  // CT: compile-time class count (80: no bounds predicates in the class loop); 0 = runtime
+__global__ void __launch_bounds__(LOSS_THREADS, 4) loss_match_kernel(Loss3K k)
+{
+    extern __shared__ int s_dyn[];           // [3*C] block-local confusion counters
+    __shared__ int s_cell[MATCH_CHUNK], s_cls[MATCH_CHUNK];
+    __shared__ double s_red[LOSS_THREADS / 32][4];
+    __shared__ int s_wcnt[MATCH_PER][LOSS_THREADS / 32];
+    __shared__ int s_base, s_total;
+    int *s_hist = s_dyn;
+    const LossScale &S = k.s[blockIdx.y];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int C = CT ? CT : k.C;
+    constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
+    for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
+
+    // ---- the block's candidates: slice i = candidates [chunk*CHUNK + i*256, +256), so ballot order = candidate order
+    AssignOut o[MATCH_PER];
+    bool f[MATCH_PER];
+    u32 bal[MATCH_PER];
+    const long long c0 = (long long)blockIdx.x * MATCH_CHUNK;
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < MATCH_PER; ++i) {
+        const long long c = c0 + i * LOSS_THREADS + tid;
+        f[i] = (c < S.a.ncand) && assign_eval(S.a, c, o[i]);
+        if (f[i] && ((unsigned)o[i].b >= (unsigned)k.B || (unsigned)o[i].cls >= (unsigned)C)) {
+            f[i] = false;  // the reference raises IndexError on these (preds[batch_idx...], t_cls[range, cls]); here: dropped + flagged
+            bad = true;
+        }
+        bal[i] = __ballot_sync(0xffffffffu, f[i]);
+        if (lane == 0) s_wcnt[i][wid] = __popc(bal[i]);
+    }
+    __syncthreads();
+    pdl_wait();  // everything above reads only the targets; the counters / match arrays / head words are cleared upstream
+    if (bad) atomicOr(k.status, 1);
+    if (tid == 0) {
+        int tot = 0;
+#pragma unroll
+        for (int i = 0; i < MATCH_PER; ++i)
+            for (int w = 0; w < LOSS_THREADS / 32; ++w) { const int v = s_wcnt[i][w]; s_wcnt[i][w] = tot; tot += v; }
+        s_total = tot;
+        s_base = tot ? atomicAdd(S.M, tot) : 0;
+    }
+    __syncthreads();
+    const int nloc = s_total, base = s_base;
+
+    // ---- per match (the thread that evaluated the candidate): gather, CIoU and its gradient, link into the cell's list
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int i = 0; i < MATCH_PER; ++i) {
+        if (!f[i]) continue;
+        const AssignOut &q = o[i];
+        const int j = s_wcnt[i][wid] + __popc(bal[i] & lanemask_lt());
+        const int m = base + j;
+        const int cell = ((q.b * S.a.ny + q.gj) * S.a.nx + q.gi) * S.a.na + q.a;
+        s_cell[j] = cell; s_cls[j] = q.cls;
+        const float *bp = S.v.box + (long long)cell * S.v.sb;
+        float b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+        const float obj = __ldg(S.v.obj + (long long)cell * S.v.so);
+        float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;  // d(decoded)/d(stored)
+        if (RAW) {  // detection.py:122,125: xy = sigmoid*2 - 0.5, wh = (sigmoid*2)^2
+            const float s0 = sigmoid_acc(b0), s1 = sigmoid_acc(b1), s2 = sigmoid_acc(b2), s3 = sigmoid_acc(b3);
+            b0 = __fsub_rn(__fmul_rn(s0, 2.0f), 0.5f); b1 = __fsub_rn(__fmul_rn(s1, 2.0f), 0.5f);
+            const float w2 = __fmul_rn(s2, 2.0f), h2 = __fmul_rn(s3, 2.0f);
+            b2 = __fmul_rn(w2, w2); b3 = __fmul_rn(h2, h2);
+            d0 = 2.0f * s0 * (1.0f - s0); d1 = 2.0f * s1 * (1.0f - s1);
+            d2 = 8.0f * s2 * s2 * (1.0f - s2); d3 = 8.0f * s3 * s3 * (1.0f - s3);
+        }
+        const float p[4] = {b0, b1, __fmul_rn(b2, q.aw), __fmul_rn(b3, q.ah)};
+        const float t[4] = {q.bx, q.by, q.bw, q.bh};
+        float g[4];
+        const float ci = ciou_eval<float>(p, t, 1e-7f, g);
+        S.cell[m] = cell; S.cls[m] = q.cls;
+        S.key[m] = (int)(c0 + i * LOSS_THREADS + tid);
+        S.ciou[m] = ci;
+        S.gbox[m] = make_float4(g[0] * d0, g[1] * d1, g[2] * q.aw * d2, g[3] * q.ah * d3);
+        const int prev = atomicExch(&S.head[cell], m + 1) - 1;
+        S.next[m] = prev;
+        if (prev >= 0) S.succ[prev] = 1;
+        a0 += (double)__fsub_rn(1.0f, ci);
+        a1 += (double)ci;
+        a2 += (double)sigmoid_acc(obj);
+    }
+    __syncthreads();
+
+    // ---- eight lanes per match (four matches per warp in flight): class BCE, argmax, confusion counters
+    const int gl = lane & 7;
+    for (int jb = wid * 4; jb < nloc; jb += (LOSS_THREADS / 32) * 4) {
+        const int j = jb + (lane >> 3);
+        const bool valid = j < nloc;
+        // sum_c bce(x_c, t_c) = sum_c softplus(x_c) - cn * sum_c x_c - (cp - cn) * x_target, with
+        // softplus(x) = max(x, 0) + log(1 + exp(-|x|)); the logs of a lane's classes are taken as ONE log of the
+        // product (each factor lies in (1, 2], ten of them stay far from overflow) -- fast exp/log units, |error| of
+        // the row sum < 1e-6 relative, far inside the rtol 1e-5 bar of the mean over M*C terms
+        float bsum = 0.f, best = -INFINITY;
+        int bi = 0x7fffffff, tc = -1;
+        if (valid) {
+            tc = s_cls[j];
+            const float *row = S.v.cls + (long long)s_cell[j] * S.v.sc;
+            float spos = 0.f, sx = 0.f, lsum = 0.f;
+            for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
+                float x[ROWS_UNROLL];
+#pragma unroll
+                for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = (kFull || c < C) ? __ldg(row + c) : -INFINITY; }
+                float prod = 1.f;
+#pragma unroll
+                for (int u = 0; u < ROWS_UNROLL; ++u) {
+                    const int c = cb + 8 * u + gl;
+                    if (kFull || c < C) {
+                        prod *= 1.0f + __expf(-fabsf(x[u]));
+                        spos += fmaxf(x[u], 0.0f);
+                        sx += x[u];
+                        if (x[u] > best) { best = x[u]; bi = c; }
+                    }
+                }
+                lsum += __logf(prod);
+            }
+            bsum = spos + lsum - k.cn * sx;
+            if (gl == 0) bsum -= (k.cp - k.cn) * __ldg(row + tc);
+        }
+#pragma unroll
+        for (int o2 = 4; o2 > 0; o2 >>= 1) {
+            bsum += __shfl_xor_sync(0xffffffffu, bsum, o2);
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o2);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o2);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (valid && gl == 0) {
+            a3 += (double)bsum;
+            if (bi == tc) atomicAdd(&s_hist[tc], 1);
+            atomicAdd(&s_hist[C + tc], 1);
+            if (bi >= 0 && bi < C) atomicAdd(&s_hist[2 * C + bi], 1);
+        }
+    }
+    pdl_launch_dependents();
+
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; s_red[wid][3] = a3; }
+    __syncthreads();
+    if (tid < 4) {
+        double s = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][tid];
+        S.part_match[(long long)blockIdx.x * 4 + tid] = s;
+    }
+    for (int i = tid; i < 3 * C; i += LOSS_THREADS) {
+        const int v = s_hist[i];
+        if (v) atomicAdd((unsigned long long *)&S.hist[i], (unsigned long long)v);
+    }
+}
+
+// One float every D*4 bytes: ask L2 for 64-byte fills instead of the default (measured on B200 for a 340-byte
+// stride: 89 instead of 122 bytes of DRAM time per element, scripts/micro/write_stride.cu)
+__device__ __forceinline__ float ld_stride_f32(const float *p)
+{
+    float v;
+    asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// dense objectness BCE over every cell
+__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
+{
+    __shared__ double s_red[LOSS_THREADS / 32][3];
+    const LossScale &S = k.s[blockIdx.y];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double a0 = 0, a1 = 0, a2 = 0;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
+    constexpr int DENSE_PER = 4;
+    const long long stride = (long long)gridDim.x * LOSS_THREADS;
+    const int so = S.v.so;
+    const long long first = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x;
+    // the logits do not depend on the upstream kernels: the first batch of loads is issued before the wait
+    float xs[DENSE_PER];
+#pragma unroll
+    for (int u = 0; u < DENSE_PER; ++u) {
+        const long long c = first + u * stride;
+        xs[u] = 0.f;
+        if (c < S.cells) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
+    }
+    pdl_wait();
+    for (long long c0 = first; c0 < S.cells; c0 += DENSE_PER * stride) {
+        int ws[DENSE_PER];
+#pragma unroll
+        for (int u = 0; u < DENSE_PER; ++u) {
+            const long long c = c0 + u * stride;
+            ws[u] = -1;
+            if (c < S.cells) {
+                if (c0 != first) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
+                ws[u] = S.head[c] - 1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < DENSE_PER; ++u) {
+            const long long c = c0 + u * stride;
+            if (c >= S.cells) break;
+            const float x = xs[u];
+            int w = -1, wk = -1;  // "last match wins": the highest candidate number in the cell's list
+            for (int j = ws[u]; j >= 0; j = S.next[j]) { const int kj = S.key[j]; if (kj > wk) { wk = kj; w = j; } }
+            const float t = w >= 0 ? S.ciou[w] : 0.0f;
+            const float sg = sigmoid_acc(x);
+            a0 += (double)bce_logits(x, t);
+            if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
+            // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
+            // (evict-last), so those reads do not turn into DRAM read/write turnarounds
+            asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
+        }
+    }
+    pdl_launch_dependents();
+    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
+        S.part_dense[(long long)blockIdx.x * 3 + threadIdx.x] = s;
+    }
+}
+
+// fixed-order final reduction -> scalars[3,8] and the combined loss; 768 threads, 256 per scale
+__global__ void __launch_bounds__(768) loss_finalize_kernel(Loss3K k)
+{
+    __shared__ double s_red[3][8][7];
+    __shared__ double s_terms[3][3];
+    const int sc = threadIdx.x >> 8, t = threadIdx.x & 255;
+    const int lane = t & 31, wid = t >> 5;
+    const LossScale &S = k.s[sc];
+    pdl_wait();
+    for (int i = t; i < 3 * k.C; i += 256) S.hist_out[i] = S.hist[i];
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int b = t; b < k.nblk_match; b += 256)
+        for (int q = 0; q < 4; ++q) v[q] += S.part_match[(long long)b * 4 + q];
+    for (int b = t; b < k.nblk_dense; b += 256)
+        for (int q = 0; q < 3; ++q) v[4 + q] += S.part_dense[(long long)b * 3 + q];
+    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0) for (int q = 0; q < 7; ++q) s_red[sc][wid][q] = v[q];
+    __syncthreads();
+    if (t == 0) {
+        double s[7];
+        for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[sc][w][q]; }
+        const double M = (double)*S.M;
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        double *o = k.scalars + 8 * sc;
+        o[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
+        o[1] = s[4] / (double)S.cells;
+        o[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
+        o[3] = M > 0 ? s[1] / M : nan;
+        o[4] = M > 0 ? s[2] / M : nan;
+        o[5] = s[6] > 0 ? s[5] / s[6] : nan;
+        o[6] = M;
+        o[7] = s[6];
+        s_terms[sc][0] = S.scale_w * o[0]; s_terms[sc][1] = S.scale_w * o[1]; s_terms[sc][2] = S.scale_w * o[2];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double lbox = s_terms[0][0] + s_terms[1][0] + s_terms[2][0];
+        const double lconf = s_terms[0][1] + s_terms[1][1] + s_terms[2][1];
+        const double lcls = s_terms[0][2] + s_terms[1][2] + s_terms[2][2];
+        *k.loss_out = (float)(k.box_w * lbox + k.conf_w * lconf + k.class_w * lcls);
+    }
+}
+
+struct BwdScales { float conf, cls, box; };
+__device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale &S)
+{
+    const double go = (double)(k.go_dev ? *k.go_dev : k.go_host) * S.scale_w;
+    const int M = *S.M;
+    BwdScales r;
+    r.conf = (float)(k.conf_w * go / (double)S.cells);
+    r.cls = M > 0 ? (float)(k.class_w * go / ((double)M * (double)k.C)) : 0.0f;
+    r.box = M > 0 ? (float)(-k.box_w * go / (double)M) : 0.0f;
+    return r;
+}
+
+// grad_preds is zeros, one objectness value per row, and the class / box columns of the matched rows (6 % of
+// the rows).  Two kernels, no atomics, both with every warp of the machine busy:
+//
+// loss_bwd_stream_kernel: written the way a fill would be.  Every warp owns a shared-memory image of a 32-row
+//   chunk (32*D floats, zero-filled once); per chunk it drops the 32 objectness values into column 0 of the rows
+//   (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and copies the image out
+//   with 16-byte loads from shared memory and 512-byte coalesced stores -- no per-element index arithmetic.
+//   (A TMA bulk store of the image, cp.async.bulk.global.shared::cta, measured 5.5 TB/s; this loop is faster.)
+// loss_bwd_rows_kernel: eight lanes per match; the first match linked into a cell owns the row (known from the
+//   forward: next == -1; and succ == 0 says it is the cell's only match, so nothing has to be looked up by cell),
+//   otherwise it walks the cell's list (gather backward = index_put(accumulate=True): every match of the cell contributes)
+//   and rewrites the row's class / box columns:
+//   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
+
+constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
+
+// Mixing the 26 MB of residual reads into the 2.1 GB write stream costs ~45 us of DRAM read/write turnarounds
+// (measured: the same kernel without the loads runs 352 instead of 396 us).  So the residuals are pulled into L2
+// first, marked evict-last, and the write stream below uses evict-first stores: the streaming kernel's loads hit L2.
+__global__ void __launch_bounds__(256) l2_pin_kernel(const float4 *p, long long n4)
+{
+    float acc = 0.f;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 v;
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i), "l"(pol));
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 1.2345e-30f) asm volatile("trap;");  // keeps the loads alive
+}
+
+// interleaved rows only (v.g_obj is the gradient tensor, v.so its row length D)
+__global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
+{
+    extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][32*D]
+    const int D = k.s[0].v.so;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int chunk_floats = 32 * D, chunk_f4 = 8 * D;
+    float *im = bwd_smem + (size_t)wid * chunk_floats;
+    for (int i = lane; i < chunk_floats; i += 32) im[i] = 0.f;  // only column 0 of a row ever changes
+    __syncwarp();
+    const float4 *im4 = reinterpret_cast<const float4 *>(im);
+
+    long long nch[3], tot = 0;
+    for (int s = 0; s < 3; ++s) { nch[s] = k.s[s].cells >> 5; tot += nch[s]; }  // full chunks; remainders below
+    const float cf0 = bwd_scales(k, k.s[0]).conf, cf1 = bwd_scales(k, k.s[1]).conf, cf2 = bwd_scales(k, k.s[2]).conf;
+    const long long gw = (long long)blockIdx.x * BWD_WARPS + wid, nw = (long long)gridDim.x * BWD_WARPS;
+
+    auto locate = [&](long long g, int &si, long long &row0) {
+        si = 0;
+        long long ch = g;
+        if (ch >= nch[0]) { ch -= nch[0]; si = 1; if (ch >= nch[1]) { ch -= nch[1]; si = 2; } }
+        row0 = ch << 5;
+    };
+    // the residuals of the next BWD_AHEAD chunks are kept in flight: a chunk is only ~22 store instructions long,
+    // far shorter than the latency of the load that feeds the one after it
+    constexpr int BWD_AHEAD = 4;
+    float gq[BWD_AHEAD];
+#pragma unroll
+    for (int a = 0; a < BWD_AHEAD; ++a) {
+        gq[a] = 0.f;
+        const long long ga = gw + a * nw;
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[a] = k.s[s2].gobj[r2 + lane]; }
+    }
+    for (long long g = gw; g < tot; g += nw) {
+        int si; long long row0;
+        locate(g, si, row0);
+        float4 *dst = reinterpret_cast<float4 *>(k.s[si].v.g_obj + row0 * D);
+        im[lane * D] = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gq[0];
+#pragma unroll
+        for (int a = 0; a + 1 < BWD_AHEAD; ++a) gq[a] = gq[a + 1];
+        gq[BWD_AHEAD - 1] = 0.f;
+        const long long ga = g + BWD_AHEAD * nw;
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[BWD_AHEAD - 1] = k.s[s2].gobj[r2 + lane]; }
+        __syncwarp();
+        for (int f = lane; f < chunk_f4; f += 32) __stcs(dst + f, im4[f]);  // shared-memory image -> 512-byte coalesced, evict-first stores
+        __syncwarp();
+    }
+    pdl_launch_dependents();
+
+    // rows beyond the last full chunk of a scale (cells not a multiple of 32): plain stores by one CTA
+    if (blockIdx.x == 0) {
+        for (int s = 0; s < 3; ++s) {
+            const LossScale &S = k.s[s];
+            const float cf = s == 0 ? cf0 : (s == 1 ? cf1 : cf2);
+            for (long long row = (S.cells & ~31LL) + wid; row < S.cells; row += BWD_WARPS)
+                for (int col = lane; col < D; col += 32) S.v.g_obj[row * D + col] = col == 0 ? cf * S.gobj[row] : 0.f;
+        }
+    }
+}
+
+// split layout: the objectness plane of the gradient (the class / box planes are cleared by cudaMemsetAsync)
+__global__ void __launch_bounds__(256) loss_bwd_conf_kernel(Loss3K k)
+{
+    const LossScale &S = k.s[blockIdx.y];
+    const float cf = bwd_scales(k, S).conf;
+    const long long n4 = S.cells >> 2;
+    const float4 *src = reinterpret_cast<const float4 *>(S.gobj);
+    float4 *dst = reinterpret_cast<float4 *>(S.v.g_obj);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+        float4 v = src[i];
+        v.x *= cf; v.y *= cf; v.z *= cf; v.w *= cf;
+        dst[i] = v;
+    }
+    if (blockIdx.x == 0)
+        for (long long c = (n4 << 2) + threadIdx.x; c < S.cells; c += 256) S.v.g_obj[c] = cf * S.gobj[c];
+}
+
+template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled row loop); 0 = runtime
+__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
+{
+    const LossScale &S = k.s[blockIdx.y];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gl = lane & 7;
+    const int M = *S.M;
+    if (M <= 0) return;
+    const BwdScales sc = bwd_scales(k, S);
+    const int C = CT ? CT : k.C;
+    constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;
+    pdl_wait();  // the rows below were cleared by the kernel / memsets launched before this one
+    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
+         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
+        const long long m = mb + (lane >> 3);
+        if (m >= M) continue;
+        if (S.next[m] != -1) continue;  // the first match linked into the cell owns the row
+        const int cell = S.cell[m];
+        int n = 0, c1 = -1, c2 = -1;
+        float gb[4] = {0.f, 0.f, 0.f, 0.f};
+        int lhead = (int)m;
+        if (!S.succ[m]) {  // the only match of its cell (the usual case): everything is addressed by m, no list walk
+            const float4 gq = S.gbox[m];
+            gb[0] = gq.x; gb[1] = gq.y; gb[2] = gq.z; gb[3] = gq.w;
+            c1 = S.cls[m];
+            n = 1;
+        } else {           // sums in double: the list order depends on the block schedule, the rounded sum must not
+            lhead = S.head[cell] - 1;
+            double gd[4] = {0, 0, 0, 0};
+            for (int j = lhead; j >= 0; j = S.next[j]) {
+                const float4 gq = S.gbox[j];
+                gd[0] += gq.x; gd[1] += gq.y; gd[2] += gq.z; gd[3] += gq.w;
+                if (n == 0) c1 = S.cls[j]; else if (n == 1) c2 = S.cls[j];
+                ++n;
+            }
+            gb[0] = (float)gd[0]; gb[1] = (float)gd[1]; gb[2] = (float)gd[2]; gb[3] = (float)gd[3];
+        }
+        const float *xrow = S.v.cls + (long long)cell * S.v.sc;
+        float *grow = S.v.g_cls + (long long)cell * S.v.sc;
+        // class column c: cls*(n*(sg - cn) - (cp - cn)*hits(c)) = ka*sg - kb - kc*hits(c); the (at most two) columns
+        // with hits are fixed up after the row loop by the lane that wrote them
+        const float ka = sc.cls * (float)n, kb = ka * k.cn, kc = sc.cls * (k.cp - k.cn);
+        for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
+            float x[ROWS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < ROWS_UNROLL; ++u) {  // all loads of the batch in flight before the first store
+                const int col = cb + 8 * u + gl;
+                x[u] = (kFull || col < C) ? __ldg(xrow + col) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < ROWS_UNROLL; ++u) {
+                const int col = cb + 8 * u + gl;
+                if (!kFull && col >= C) continue;
+                grow[col] = ka * sigmoid_fast(x[u]) - kb;
+            }
+        }
+        if (n <= 2) {  // the lane that stored a column fixes it up: no cross-lane ordering needed
+            if (c1 >= 0 && gl == (c1 & 7)) grow[c1] -= kc;
+            if (c2 >= 0 && gl == (c2 & 7)) grow[c2] -= kc;
+        } else {  // three or more matches on one cell: one subtraction per match, by one lane, after the group's
+                  // stores are visible to it (n is uniform over the eight lanes of the group)
+            __syncwarp(0xffu << (lane & 24));
+            if (gl == 0)
+                for (int j = lhead; j >= 0; j = S.next[j]) grow[S.cls[j]] -= kc;
+        }
+        if (gl < 4) S.v.g_box[(long long)cell * S.v.sb + gl] = sc.box * (gl == 0 ? gb[0] : gl == 1 ? gb[1] : gl == 2 ? gb[2] : gb[3]);
+    }
+}
+
+}  // namespace bg

@@ -1,5 +1,5 @@
 // Training side: YOLOv5-style target assignment (ordered compaction), element-wise CIoU with its
-// analytic gradient, the fused detection loss (forward + backward) and the anchor-fit metrics.
+// analytic gradient and the anchor-fit metrics.  The fused detection loss is in loss_kernels.cuh.
 //
 // Reference semantics: dataset/detection_dataset.py:90-246,
 // modules/detection_loss.py:125-264, utils/make_anchors.py:14-39.
@@ -300,434 +300,19 @@ __global__ void ciou_bwd_kernel(const float *p, const float *t, const float *go,
 }
 
 // ------------------------------------------------------------------------------------------------
-// fused detection loss: every kernel covers the three scales (blockIdx.y)
-//   forward : loss_match_kernel  pass A, one thread per match   : gather, CIoU and its gradient, link the match
-//                                                                  into its cell's list (atomicExch on the head)
-//                                pass B, eight lanes per match  : class BCE, argmax, confusion counters
-//             loss_dense_kernel  one thread per cell            : objectness BCE against the CIoU of the cell's last match;
-//                                                                  keeps sigmoid(x) - t for the backward
-//             loss_finalize_kernel                              : fixed-order reduction, scalars, total loss
-//   backward: loss_bwd_stream_kernel  zeros + the objectness column, one 16-byte store per four elements
-//             loss_bwd_rows_kernel    class / box columns of the matched rows, summed over the cell's match list
-//                                     (gather backward = index_put(accumulate=True)); no atomics
-// ------------------------------------------------------------------------------------------------
-struct LossScale {
-    const float *preds;  // [B,ny,nx,na,D]
-    float *grad;         // same shape (backward only)
-    long long cells;     // B*ny*nx*na
-    const int *M;        // device count from the assignment
-    const int *cell;     // [cap]
-    const int *cls;      // [cap]
-    const float *anchor; // [cap,2]
-    const float *box;    // [cap,4]
-    float *ciou;         // [cap]
-    float4 *gbox;        // [cap] d ciou / d (x, y, w_raw, h_raw) of the matched prediction
-    int *head;           // [cells] most recently linked match of the cell (-1: none); list through next[]
-    int *next;           // [cap] previous match of the same cell, -1 at the end of the list (= the cell's first match)
-    unsigned char *succ; // [cap] 1 if a later match was linked in front of this one (zeroed by the host)
-    float *gobj;         // [cells] sigmoid(obj) - t_conf
-    double *part_match;  // [nblk_match,4]: sum(1-ciou), sum(ciou), sum(sig(obj)), sum(bce_cls)
-    double *part_dense;  // [nblk_dense,3]: sum(bce_obj), sum(sig(obj) | t==0), n_neg
-    long long *hist;     // [3,C]
-    double scale_w;
-};
-
-struct Loss3K {
-    LossScale s[3];
-    int C, D;
-    float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
-    int nblk_match, nblk_dense;
-    double box_w, conf_w, class_w;
-    double *scalars;     // [3,8]
-    float *loss_out;     // [1] total loss (modules/detection_loss.py:107-110)
-    const float *go_dev; // backward: upstream gradient on the device (or null -> go_host)
-    float go_host;
-};
-
-__device__ __forceinline__ float bce_logits(float x, float t)
-{
-    // ATen binary_cross_entropy_with_logits: (1 - t) * x - log_sigmoid(x)
-    const float ls = __fsub_rn(fminf(x, 0.0f), log1pf(expf(-fabsf(x))));
-    return __fsub_rn(__fmul_rn(__fsub_rn(1.0f, t), x), ls);
-}
-
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-
-constexpr int LOSS_THREADS = 256;
-constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
-
-template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled class loop); 0 = runtime
-__global__ void __launch_bounds__(LOSS_THREADS, 6) loss_match_kernel(Loss3K k)
-{
-    extern __shared__ int s_hist[];  // [3,C] block-local confusion counters
-    __shared__ double s_red[LOSS_THREADS / 32][4];
-    const LossScale &S = k.s[blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int M = *S.M;
-    const int C = CT ? CT : k.C, D = C + 5;
-    constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
-    for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
-    __syncthreads();
-
-    // pass A: one thread per match -- gather, CIoU and its gradient, link the match into its cell's list
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (long long m = (long long)blockIdx.x * LOSS_THREADS + tid; m < M; m += (long long)gridDim.x * LOSS_THREADS) {
-        const int cell = S.cell[m];
-        const float *row = S.preds + (long long)cell * D;
-        const float aw = S.anchor[2 * m], ah = S.anchor[2 * m + 1];
-        const float p[4] = {__ldg(row + C + 1), __ldg(row + C + 2), __fmul_rn(__ldg(row + C + 3), aw),
-                            __fmul_rn(__ldg(row + C + 4), ah)};
-        const float obj = __ldg(row);
-        const float4 tb = reinterpret_cast<const float4 *>(S.box)[m];
-        const float t[4] = {tb.x, tb.y, tb.z, tb.w};
-        float g[4];
-        const float ci = ciou_eval<float>(p, t, 1e-7f, g);
-        S.ciou[m] = ci;
-        S.gbox[m] = make_float4(g[0], g[1], g[2] * aw, g[3] * ah);
-        const int prev = atomicExch(&S.head[cell], (int)m);
-        S.next[m] = prev;
-        if (prev >= 0) S.succ[prev] = 1;
-        a0 += (double)__fsub_rn(1.0f, ci);
-        a1 += (double)ci;
-        a2 += (double)sigmoid_acc(obj);
-    }
-
-    // pass B: eight lanes per match (four matches per warp in flight)
-    const int gl = lane & 7;
-    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
-         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
-        const long long m = mb + (lane >> 3);
-        const bool valid = m < M;
-        // sum_c bce(x_c, t_c) = sum_c softplus(x_c) - cn * sum_c x_c - (cp - cn) * x_target, with
-        // softplus(x) = max(x, 0) + log(1 + exp(-|x|)); the logs of a lane's classes are taken as ONE log of the
-        // product (each factor lies in (1, 2], ten of them stay far from overflow) -- fast exp/log units, |error| of
-        // the row sum < 1e-6 relative, far inside the rtol 1e-5 bar of the mean over M*C terms
-        float bsum = 0.f, best = -INFINITY;
-        int bi = 0x7fffffff, tc = -1;
-        if (valid) {
-            tc = S.cls[m];
-            const float *row = S.preds + (long long)S.cell[m] * D + 1;
-            float spos = 0.f, sx = 0.f, lsum = 0.f;
-            for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
-                float x[ROWS_UNROLL];
-#pragma unroll
-                for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = (kFull || c < C) ? __ldg(row + c) : -INFINITY; }
-                float prod = 1.f;
-#pragma unroll
-                for (int u = 0; u < ROWS_UNROLL; ++u) {
-                    const int c = cb + 8 * u + gl;
-                    if (kFull || c < C) {
-                        prod *= 1.0f + __expf(-fabsf(x[u]));
-                        spos += fmaxf(x[u], 0.0f);
-                        sx += x[u];
-                        if (x[u] > best) { best = x[u]; bi = c; }
-                    }
-                }
-                lsum += __logf(prod);
-            }
-            bsum = spos + lsum - k.cn * sx;
-            if (gl == 0 && tc >= 0 && tc < C) bsum -= (k.cp - k.cn) * __ldg(row + tc);  // (labels outside 0..C-1 have no target column)
-        }
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (valid && gl == 0) {
-            a3 += (double)bsum;
-            if (tc >= 0 && tc < C) {
-                if (bi == tc) atomicAdd(&s_hist[tc], 1);
-                atomicAdd(&s_hist[C + tc], 1);
-            }
-            if (bi >= 0 && bi < C) atomicAdd(&s_hist[2 * C + bi], 1);
-        }
-    }
-
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
-    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; s_red[wid][3] = a3; }
-    __syncthreads();
-    if (tid < 4) {
-        double s = 0;
-        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][tid];
-        S.part_match[(long long)blockIdx.x * 4 + tid] = s;
-    }
-    for (int i = tid; i < 3 * C; i += LOSS_THREADS) {
-        const int v = s_hist[i];
-        if (v) atomicAdd((unsigned long long *)&S.hist[i], (unsigned long long)v);
-    }
-}
-
-// One float every D*4 bytes: ask L2 for 64-byte fills instead of the default (measured on B200 for a 340-byte
-// stride: 89 instead of 122 bytes of DRAM time per element, scripts/micro/write_stride.cu)
-__device__ __forceinline__ float ld_stride_f32(const float *p)
-{
-    float v;
-    asm volatile("ld.global.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
-// dense objectness BCE over every cell
-__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
-{
-    __shared__ double s_red[LOSS_THREADS / 32][3];
-    const LossScale &S = k.s[blockIdx.y];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    double a0 = 0, a1 = 0, a2 = 0;
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
-    constexpr int DENSE_PER = 4;
-    const long long stride = (long long)gridDim.x * LOSS_THREADS;
-    for (long long c0 = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x; c0 < S.cells; c0 += DENSE_PER * stride) {
-        float xs[DENSE_PER];
-        int ws[DENSE_PER];
-#pragma unroll
-        for (int u = 0; u < DENSE_PER; ++u) {
-            const long long c = c0 + u * stride;
-            xs[u] = 0.f; ws[u] = -1;
-            if (c < S.cells) { xs[u] = ld_stride_f32(S.preds + c * k.D); ws[u] = S.head[c]; }
-        }
-#pragma unroll
-        for (int u = 0; u < DENSE_PER; ++u) {
-            const long long c = c0 + u * stride;
-            if (c >= S.cells) break;
-            const float x = xs[u];
-            int w = ws[u];  // "last match wins": the highest match index of the cell's list
-            for (int j = w; j >= 0; j = S.next[j]) w = j > w ? j : w;
-            const float t = w >= 0 ? S.ciou[w] : 0.0f;
-            const float sg = sigmoid_acc(x);
-            a0 += (double)bce_logits(x, t);
-            if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
-            // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
-            // (evict-last), so those reads do not turn into DRAM read/write turnarounds
-            asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
-        }
-    }
-    a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
-    if (lane == 0) { s_red[wid][0] = a0; s_red[wid][1] = a1; s_red[wid][2] = a2; }
-    __syncthreads();
-    if (threadIdx.x < 3) {
-        double s = 0;
-        for (int w = 0; w < LOSS_THREADS / 32; ++w) s += s_red[w][threadIdx.x];
-        S.part_dense[(long long)blockIdx.x * 3 + threadIdx.x] = s;
-    }
-}
-
-// fixed-order final reduction -> scalars[3,8] and the combined loss; 768 threads, 256 per scale
-__global__ void __launch_bounds__(768) loss_finalize_kernel(Loss3K k)
-{
-    __shared__ double s_red[3][8][7];
-    __shared__ double s_terms[3][3];
-    const int sc = threadIdx.x >> 8, t = threadIdx.x & 255;
-    const int lane = t & 31, wid = t >> 5;
-    const LossScale &S = k.s[sc];
-    double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int b = t; b < k.nblk_match; b += 256)
-        for (int q = 0; q < 4; ++q) v[q] += S.part_match[(long long)b * 4 + q];
-    for (int b = t; b < k.nblk_dense; b += 256)
-        for (int q = 0; q < 3; ++q) v[4 + q] += S.part_dense[(long long)b * 3 + q];
-    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
-    if (lane == 0) for (int q = 0; q < 7; ++q) s_red[sc][wid][q] = v[q];
-    __syncthreads();
-    if (t == 0) {
-        double s[7];
-        for (int q = 0; q < 7; ++q) { s[q] = 0; for (int w = 0; w < 8; ++w) s[q] += s_red[sc][w][q]; }
-        const double M = (double)*S.M;
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-        double *o = k.scalars + 8 * sc;
-        o[0] = M > 0 ? s[0] / M : 0.0;                      // NaN -> 0 (:209-210)
-        o[1] = s[4] / (double)S.cells;
-        o[2] = M > 0 ? s[3] / (M * (double)k.C) : 0.0;
-        o[3] = M > 0 ? s[1] / M : nan;
-        o[4] = M > 0 ? s[2] / M : nan;
-        o[5] = s[6] > 0 ? s[5] / s[6] : nan;
-        o[6] = M;
-        o[7] = s[6];
-        s_terms[sc][0] = S.scale_w * o[0]; s_terms[sc][1] = S.scale_w * o[1]; s_terms[sc][2] = S.scale_w * o[2];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double lbox = s_terms[0][0] + s_terms[1][0] + s_terms[2][0];
-        const double lconf = s_terms[0][1] + s_terms[1][1] + s_terms[2][1];
-        const double lcls = s_terms[0][2] + s_terms[1][2] + s_terms[2][2];
-        *k.loss_out = (float)(k.box_w * lbox + k.conf_w * lconf + k.class_w * lcls);
-    }
-}
-
-struct BwdScales { float conf, cls, box; };
-__device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale &S)
-{
-    const double go = (double)(k.go_dev ? *k.go_dev : k.go_host) * S.scale_w;
-    const int M = *S.M;
-    BwdScales r;
-    r.conf = (float)(k.conf_w * go / (double)S.cells);
-    r.cls = M > 0 ? (float)(k.class_w * go / ((double)M * (double)k.C)) : 0.0f;
-    r.box = M > 0 ? (float)(-k.box_w * go / (double)M) : 0.0f;
-    return r;
-}
-
-// grad_preds is zeros, one objectness value per row, and the class / box columns of the matched rows (6 % of
-// the rows).  Two kernels, no atomics, both with every warp of the machine busy:
-//
-// loss_bwd_stream_kernel: written the way a fill would be.  Every warp owns a shared-memory image of a 32-row
-//   chunk (32*D floats, zero-filled once); per chunk it drops the 32 objectness values into column 0 of the rows
-//   (lane = row, residual fetched with one coalesced load, the next chunk's prefetched) and copies the image out
-//   with 16-byte loads from shared memory and 512-byte coalesced stores -- no per-element index arithmetic.
-//   (A TMA bulk store of the image, cp.async.bulk.global.shared::cta, measured 5.5 TB/s; this loop is faster.)
-// loss_bwd_rows_kernel: eight lanes per match; the first match linked into a cell owns the row (known from the
-//   forward: next == -1; and succ == 0 says it is the cell's only match, so nothing has to be looked up by cell),
-//   otherwise it walks the cell's list (gather backward = index_put(accumulate=True): every match of the cell contributes)
-//   and rewrites the row's class / box columns:
-//   class c: cls*(n*(sigmoid(x)-cn) - (cp-cn)*#{matches of class c}),  box j: box * sum of the CIoU gradients.
-
-constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
-
-// Mixing the 26 MB of residual reads into the 2.1 GB write stream costs ~45 us of DRAM read/write turnarounds
-// (measured: the same kernel without the loads runs 352 instead of 396 us).  So the residuals are pulled into L2
-// first, marked evict-last, and the write stream below uses evict-first stores: the streaming kernel's loads hit L2.
-__global__ void __launch_bounds__(256) l2_pin_kernel(const float4 *p, long long n4)
-{
-    float acc = 0.f;
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-        float4 v;
-        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i), "l"(pol));
-        acc += v.x + v.y + v.z + v.w;
-    }
-    if (acc == 1.2345e-30f) asm volatile("trap;");  // keeps the loads alive
-}
-
-__global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
-{
-    extern __shared__ __align__(128) float bwd_smem[];  // [BWD_WARPS][32*D]
-    const int D = k.D;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int chunk_floats = 32 * D, chunk_f4 = 8 * D;
-    float *im = bwd_smem + (size_t)wid * chunk_floats;
-    for (int i = lane; i < chunk_floats; i += 32) im[i] = 0.f;  // only column 0 of a row ever changes
-    __syncwarp();
-    const float4 *im4 = reinterpret_cast<const float4 *>(im);
-
-    long long nch[3], tot = 0;
-    for (int s = 0; s < 3; ++s) { nch[s] = k.s[s].cells >> 5; tot += nch[s]; }  // full chunks; remainders below
-    const float cf0 = bwd_scales(k, k.s[0]).conf, cf1 = bwd_scales(k, k.s[1]).conf, cf2 = bwd_scales(k, k.s[2]).conf;
-    const long long gw = (long long)blockIdx.x * BWD_WARPS + wid, nw = (long long)gridDim.x * BWD_WARPS;
-
-    auto locate = [&](long long g, int &si, long long &row0) {
-        si = 0;
-        long long ch = g;
-        if (ch >= nch[0]) { ch -= nch[0]; si = 1; if (ch >= nch[1]) { ch -= nch[1]; si = 2; } }
-        row0 = ch << 5;
-    };
-    // the residuals of the next BWD_AHEAD chunks are kept in flight: a chunk is only ~22 store instructions long,
-    // far shorter than the latency of the load that feeds the one after it
-    constexpr int BWD_AHEAD = 4;
-    float gq[BWD_AHEAD];
-#pragma unroll
-    for (int a = 0; a < BWD_AHEAD; ++a) {
-        gq[a] = 0.f;
-        const long long ga = gw + a * nw;
-        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[a] = k.s[s2].gobj[r2 + lane]; }
-    }
-    for (long long g = gw; g < tot; g += nw) {
-        int si; long long row0;
-        locate(g, si, row0);
-        float4 *dst = reinterpret_cast<float4 *>(k.s[si].grad + row0 * D);
-        im[lane * D] = (si == 0 ? cf0 : (si == 1 ? cf1 : cf2)) * gq[0];
-#pragma unroll
-        for (int a = 0; a + 1 < BWD_AHEAD; ++a) gq[a] = gq[a + 1];
-        gq[BWD_AHEAD - 1] = 0.f;
-        const long long ga = g + BWD_AHEAD * nw;
-        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[BWD_AHEAD - 1] = k.s[s2].gobj[r2 + lane]; }
-        __syncwarp();
-        for (int f = lane; f < chunk_f4; f += 32) __stcs(dst + f, im4[f]);  // shared-memory image -> 512-byte coalesced, evict-first stores
-        __syncwarp();
-    }
-
-    // rows beyond the last full chunk of a scale (cells not a multiple of 32): plain stores by one CTA
-    if (blockIdx.x == 0) {
-        for (int s = 0; s < 3; ++s) {
-            const LossScale &S = k.s[s];
-            const float cf = s == 0 ? cf0 : (s == 1 ? cf1 : cf2);
-            for (long long row = (S.cells & ~31LL) + wid; row < S.cells; row += BWD_WARPS)
-                for (int col = lane; col < D; col += 32) S.grad[row * D + col] = col == 0 ? cf * S.gobj[row] : 0.f;
-        }
-    }
-}
-
-template <int CT>  // compile-time class count (80: no bounds predicates in the unrolled row loop); 0 = runtime
-__global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
-{
-    const LossScale &S = k.s[blockIdx.y];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, gl = lane & 7;
-    const int M = *S.M;
-    if (M <= 0) return;
-    const BwdScales sc = bwd_scales(k, S);
-    const int C = CT ? CT : k.C, D = C + 5;
-    for (long long mb = ((long long)blockIdx.x * (LOSS_THREADS / 32) + wid) * 4; mb < M;
-         mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
-        const long long m = mb + (lane >> 3);
-        if (m >= M) continue;
-        if (S.next[m] != -1) continue;  // the cell's first match owns the row
-        const int cell = S.cell[m];
-        int n = 0, c1 = -1, c2 = -1;
-        float gb[4] = {0.f, 0.f, 0.f, 0.f};
-        int lhead = (int)m;
-        if (!S.succ[m]) {  // the only match of its cell (the usual case): everything is addressed by m, no list walk
-            const float4 gq = S.gbox[m];
-            gb[0] = gq.x; gb[1] = gq.y; gb[2] = gq.z; gb[3] = gq.w;
-            c1 = S.cls[m];
-            n = 1;
-        } else {
-            lhead = S.head[cell];
-            for (int j = lhead; j >= 0; j = S.next[j]) {
-                const float4 gq = S.gbox[j];
-                gb[0] += gq.x; gb[1] += gq.y; gb[2] += gq.z; gb[3] += gq.w;
-                if (n == 0) c1 = S.cls[j]; else if (n == 1) c2 = S.cls[j];
-                ++n;
-            }
-        }
-        const float *xrow = S.preds + (long long)cell * D;
-        float *grow = S.grad + (long long)cell * D;
-        // class column c: cls*(n*(sg - cn) - (cp - cn)*hits(c)) = ka*sg - kb - kc*hits(c); the (at most two) columns
-        // with hits are fixed up after the row loop by the lane that wrote them
-        const float ka = sc.cls * (float)n, kb = ka * k.cn, kc = sc.cls * (k.cp - k.cn);
-        for (int cb = 1; cb <= C; cb += 8 * ROWS_UNROLL) {
-            float x[ROWS_UNROLL];
-#pragma unroll
-            for (int u = 0; u < ROWS_UNROLL; ++u) {  // all loads of the batch in flight before the first store
-                const int col = cb + 8 * u + gl;
-                x[u] = (CT != 0 && CT % (8 * ROWS_UNROLL) == 0) || col <= C ? __ldg(xrow + col) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < ROWS_UNROLL; ++u) {
-                const int col = cb + 8 * u + gl;
-                if (!(CT != 0 && CT % (8 * ROWS_UNROLL) == 0) && col > C) continue;
-                grow[col] = ka * sigmoid_fast(x[u]) - kb;
-            }
-        }
-        if (n <= 2) {
-            if (c1 >= 0 && gl == (c1 & 7)) grow[1 + c1] -= kc;
-            if (c2 >= 0 && gl == (c2 & 7)) grow[1 + c2] -= kc;
-        } else if (gl == 0) {  // three or more matches on one cell: one subtraction per match
-            for (int j = lhead; j >= 0; j = S.next[j]) grow[1 + S.cls[j]] -= kc;
-        }
-        if (gl < 4) grow[C + 1 + gl] = sc.box * (gl == 0 ? gb[0] : gl == 1 ? gb[1] : gl == 2 ? gb[2] : gb[3]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // anchor-fit metrics (utils/make_anchors.py:14-39)
 // ------------------------------------------------------------------------------------------------
 struct RatioK { const float *wh; long long n; int k; float aw[32], ah[32]; float inv_thr; double *out; };
 
+// The two sums are accumulated as 64-bit integers (the values lie in (0, 1]: fixed point with 40 fractional bits is
+// exact for every value >= 2^-17 and holds 2^23 boxes), so the result does not depend on the order in which the
+// blocks finish.  The accumulators live in the output words themselves (out[0..2] viewed as u64: sum, count, blocks
+// done; zeroed by the host) and the last block to finish converts them to doubles in place.
+constexpr double RATIO_FIX = 1099511627776.0;  // 2^40
+
 __global__ void __launch_bounds__(256) ratio_metrics_kernel(RatioK k)
 {
-    double s0 = 0, s1 = 0;
+    unsigned long long s0 = 0, s1 = 0;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < k.n; i += (long long)gridDim.x * 256) {
         const float w = k.wh[2 * i], h = k.wh[2 * i + 1];
         float best = -INFINITY;
@@ -736,11 +321,22 @@ __global__ void __launch_bounds__(256) ratio_metrics_kernel(RatioK k)
             const float v = fminf(fminf(r0, __fdiv_rn(1.0f, r0)), fminf(r1, __fdiv_rn(1.0f, r1)));
             best = fmaxf(best, v);
         }
-        if (best > k.inv_thr) { s0 += (double)best; s1 += 1.0; }
+        if (best > k.inv_thr) { s0 += (unsigned long long)((double)best * RATIO_FIX); s1 += 1; }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(k.out, s0); atomicAdd(k.out + 1, s1); }
-    if (blockIdx.x == 0 && threadIdx.x == 0) k.out[2] = (double)k.n;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(k.out);
+    if ((threadIdx.x & 31) == 0 && s1) { atomicAdd(acc, s0); atomicAdd(acc + 1, s1); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(acc + 2, 1ull) == (unsigned long long)gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long a0 = atomicAdd(acc, 0ull), a1 = atomicAdd(acc + 1, 0ull);
+            k.out[0] = (double)a0 / RATIO_FIX;
+            k.out[1] = (double)a1;
+            k.out[2] = (double)k.n;
+        }
+    }
 }
 
 }  // namespace bg

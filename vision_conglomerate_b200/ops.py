@@ -35,11 +35,27 @@ _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 _raw_device = getattr(torch._C, "_cuda_getDevice", None)
 
 
-def _stream() -> int:
-    """cudaStream_t of torch's current stream on the current device (the raw accessors skip ~10 us of Python)."""
+def _stream(dev: Optional[torch.device] = None) -> int:
+    """cudaStream_t of torch's current stream on `dev` (default: the current device); the raw accessors skip
+    ~10 us of Python."""
     if _raw_stream is not None and _raw_device is not None:
-        return _raw_stream(_raw_device())
-    return torch.cuda.current_stream().cuda_stream
+        return _raw_stream(_raw_device() if dev is None or dev.index is None else dev.index)
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _on(dev: torch.device):
+    """Context that makes `dev` the current CUDA device.  libboxgeom launches on the current device (its
+    per-device tables, the stream handle and the pointers must all belong to it), while callers such as the
+    reference's DDP path address ranks as ``cuda:k`` without ever calling ``torch.cuda.set_device``."""
+    return torch.cuda.device(dev)
+
+
+def _same_device(*tensors) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors[1:]:
+        if t is not None and t.device != dev:
+            raise RuntimeError(f"all tensors of one call must live on one device (got {dev} and {t.device})")
+    return dev
 
 
 def _workspace(dev: torch.device, kind: str, nbytes: int) -> torch.Tensor:
@@ -99,7 +115,7 @@ def _read_counts(dev_counts: torch.Tensor, kind: str) -> torch.Tensor:
     """One device->host copy + one stream sync: the only host-visible sync of an operator."""
     host = _pinned_i32(dev_counts.device, kind, dev_counts.numel())[: dev_counts.numel()]
     host.copy_(dev_counts, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    torch.cuda.current_stream(dev_counts.device).synchronize()
     return host
 
 
@@ -112,9 +128,14 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
     scores = _req(scores, "scores").reshape(-1)
     idxs = _req(idxs, "idxs", torch.int64).reshape(-1)
     n = scores.numel()
-    dev = boxes.device
+    dev = _same_device(boxes, scores, idxs)
     if n == 0:
         return torch.empty(0, dtype=torch.int64, device=dev)
+    with _on(dev):
+        return _batched_nms_on(dev, boxes, scores, idxs, n, iou_threshold, max_groups)
+
+
+def _batched_nms_on(dev, boxes, scores, idxs, n, iou_threshold, max_groups):
     L = _lib.lib()
     keep = torch.empty(n, dtype=torch.int64, device=dev)
     counts = torch.empty(2, dtype=torch.int32, device=dev)
@@ -124,7 +145,7 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, idxs: torch.Tensor, i
         ws = _workspace(dev, "gnms", L.bg_batched_nms_workspace_bytes(n, max_groups, mask_bytes))
         check(L.bg_batched_nms(boxes.data_ptr(), scores.data_ptr(), idxs.data_ptr(), n, float(iou_threshold),
                                max_groups, keep.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(), mask_bytes,
-                               _stream()), "bg_batched_nms")
+                               _stream(dev)), "bg_batched_nms")
         h = _read_counts(counts, "gnms")
         status = int(h[1])
         if status & _lib.STATUS_GROUP_RANGE:
@@ -199,6 +220,8 @@ class DetectPlan:
             p.tracked[i] = int(c)
         p.order = 1 if order == "global" else 0
         p.variant = int(variant)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.params, self.B, self.dev = p, B, device
         self.N = sum(sh[1] * sh[2] * na for sh in shapes)
         self.hint_key = (device.index, B, self.N, p.iou_threshold, p.score_threshold)
@@ -222,6 +245,10 @@ class DetectPlan:
 
     def enqueue(self, raws) -> None:
         """``raws``: the three head tensors, or (``predecoded`` plans) the one decoded ``[B, N, 5+C]`` tensor."""
+        with _on(self.dev):
+            self._enqueue(raws)
+
+    def _enqueue(self, raws) -> None:
         L = _lib.lib()
         p = self.params
         if self.predecoded:
@@ -233,6 +260,8 @@ class DetectPlan:
             self.raws = [_req(r, f"raw[{i}]") for i, r in enumerate(raws)]
             if [tuple(r.shape) for r in self.raws] != self.shapes:
                 raise RuntimeError("detect: head output shapes differ from the plan")
+        if any(r.device != self.dev for r in self.raws):
+            raise RuntimeError(f"detect: the plan lives on {self.dev}, the inputs on {self.raws[0].device}")
         self.mask_bytes = _mask_budget.get(self.key, DEFAULT_MASK_BYTES)
         need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
         if need == 0:
@@ -241,13 +270,17 @@ class DetectPlan:
         if self.predecoded:
             check(L.bg_post_process(self.raws[0].data_ptr(), C.byref(p), self.out_boxes.data_ptr(), self.out_img.data_ptr(),
                                     self.out_keep.data_ptr(), self.counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                                    self.mask_bytes, _stream()), "bg_post_process")
+                                    self.mask_bytes, _stream(self.dev)), "bg_post_process")
             return
         check(L.bg_detect(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(), C.byref(p),
                           self.out_boxes.data_ptr(), self.out_img.data_ptr(), self.out_keep.data_ptr(),
-                          self.counts.data_ptr(), ws.data_ptr(), ws.numel(), self.mask_bytes, _stream()), "bg_detect")
+                          self.counts.data_ptr(), ws.data_ptr(), ws.numel(), self.mask_bytes, _stream(self.dev)), "bg_detect")
 
     def result(self) -> Detections:
+        with _on(self.dev):
+            return self._result()
+
+    def _result(self) -> Detections:
         B = self.B
         while True:
             h = _read_counts(self.counts, "detect")
@@ -263,7 +296,7 @@ class DetectPlan:
                     nxt = 3       # overlap-edge overflow: general engine for good
                 _nms_path_hint[self.hint_key] = nxt
                 self.params.nms_path = 4 if nxt == 4 else 1
-                self.enqueue(self.raws)
+                self._enqueue(self.raws)
                 continue
             if _nms_path_hint.get(self.hint_key) in (1, 4):   # crowded earlier; step back down when it is sparse again
                 most = int(h[2 + B: 2 + 2 * B].max())
@@ -279,7 +312,7 @@ class DetectPlan:
                 if exact <= self.mask_bytes:
                     raise RuntimeError("detect: suppression-mask workspace exhausted")
                 _mask_budget[self.key] = min(exact + (exact >> 3), self.mask_bytes * 4)
-                self.enqueue(self.raws)
+                self._enqueue(self.raws)
                 continue
             k = int(h[0])
             return Detections(self.out_boxes[:k], self.out_img[:k], self.out_keep[:k], h[2: 2 + B].clone(),
@@ -313,7 +346,7 @@ class DetectPipeline:
     def submit(self, raws) -> int:
         slot = self.submitted % self.depth
         st = self.streams[slot]
-        st.wait_stream(torch.cuda.current_stream())
+        st.wait_stream(torch.cuda.current_stream(st.device))
         with torch.cuda.stream(st):
             self.plans[slot].enqueue(raws)
         self.submitted += 1
@@ -325,7 +358,7 @@ class DetectPipeline:
 
     def join(self) -> None:
         """Make the caller's current stream wait for every batch submitted so far."""
-        cur = torch.cuda.current_stream()
+        cur = torch.cuda.current_stream(self.streams[0].device)
         for st in self.streams:
             cur.wait_stream(st)
 
@@ -386,9 +419,10 @@ def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int]
     B, ny, nx, na, D = x.shape
     out = torch.empty_like(x)
     og = (int(og_size[0]), int(og_size[1])) if og_size is not None else (-1, -1)
-    check(_lib.lib().bg_decode_scale(x.data_ptr(), out.data_ptr(), B, ny, nx, na, D - 5, _anchor_array(anchors),
-                                     int(input_shape[0]), int(input_shape[1]), int(bool(inference)), og[0], og[1],
-                                     _stream()), "bg_decode_scale")
+    with _on(x.device):
+        check(_lib.lib().bg_decode_scale(x.data_ptr(), out.data_ptr(), B, ny, nx, na, D - 5, _anchor_array(anchors),
+                                         int(input_shape[0]), int(input_shape[1]), int(bool(inference)), og[0], og[1],
+                                         _stream(x.device)), "bg_decode_scale")
     return out
 
 
@@ -404,6 +438,11 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_thr
         raise RuntimeError("build_target_by_scale: targets must be [nt, 6 + keypoint columns]")
     if overlap_masks and not batch_size:
         raise ValueError("batch_size is required when overlap_mask is set to True")  # the reference's own error (:149-150)
+    with _on(t.device):
+        return _build_target_on(t, fmap_shape, anchors, anchor_threshold, edge_threshold, overlap_masks, batch_size)
+
+
+def _build_target_on(t, fmap_shape, anchors, anchor_threshold, edge_threshold, overlap_masks, batch_size):
     dev = t.device
     nt, stride = t.shape
     ny, nx = (int(v) for v in (fmap_shape.tolist() if isinstance(fmap_shape, torch.Tensor) else fmap_shape))
@@ -421,7 +460,7 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_thr
         ws = _workspace(dev, "assign", max(L.bg_assign_workspace_bytes(nt, na), 256))
         check(L.bg_assign_targets(t.data_ptr(), nt, ny, nx, _anchor_array(anc), na, float(anchor_threshold),
                                   float(edge_threshold), idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
-                                  box.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                                  box.data_ptr(), cap, count.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)),
               "bg_assign_targets")
         M = int(_read_counts(count[:1], "assign")[0])
         tmask = kpts = None
@@ -435,7 +474,7 @@ def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_thr
                                      float(edge_threshold), mode, bs, idx4.data_ptr(), cls.data_ptr(), anc_out.data_ptr(),
                                      box.data_ptr(), tmask.data_ptr() if mode else None,
                                      kpts.data_ptr() if kpts is not None else None, cap, count.data_ptr(), ws.data_ptr(),
-                                     ws.numel(), _stream()), "bg_assign_targets_ex")
+                                     ws.numel(), _stream(dev)), "bg_assign_targets_ex")
         h = _read_counts(count, "assign")
         if int(h[1]):
             raise RuntimeError("build_target_by_scale: per-image target counts do not add up to the number of targets "
@@ -452,9 +491,11 @@ class _CIoU(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, t, e):
         p32, t32 = _req(p, "preds_xywh").reshape(-1, 4), _req(t, "targets_xywh").reshape(-1, 4)
-        out = torch.empty(p32.shape[0], dtype=torch.float32, device=p32.device)
-        check(_lib.lib().bg_ciou_fwd(p32.data_ptr(), t32.data_ptr(), p32.shape[0], float(e), out.data_ptr(), _stream()),
-              "bg_ciou_fwd")
+        dev = _same_device(p32, t32)
+        out = torch.empty(p32.shape[0], dtype=torch.float32, device=dev)
+        with _on(dev):
+            check(_lib.lib().bg_ciou_fwd(p32.data_ptr(), t32.data_ptr(), p32.shape[0], float(e), out.data_ptr(),
+                                         _stream(dev)), "bg_ciou_fwd")
         ctx.save_for_backward(p32, t32)
         ctx.e = float(e)
         ctx.shape = p.shape
@@ -465,8 +506,9 @@ class _CIoU(torch.autograd.Function):
         p32, t32 = ctx.saved_tensors
         go = go.contiguous().reshape(-1).float()
         gp = torch.empty_like(p32)
-        check(_lib.lib().bg_ciou_bwd(p32.data_ptr(), t32.data_ptr(), go.data_ptr(), p32.shape[0], ctx.e, gp.data_ptr(),
-                                     _stream()), "bg_ciou_bwd")
+        with _on(p32.device):
+            check(_lib.lib().bg_ciou_bwd(p32.data_ptr(), t32.data_ptr(), go.data_ptr(), p32.shape[0], ctx.e,
+                                         gp.data_ptr(), _stream(p32.device)), "bg_ciou_bwd")
         return gp.reshape(ctx.shape), None, None
 
 
@@ -485,25 +527,31 @@ METRIC_KEYS = ("mean_ciou", "conf_loss", "avg_pos_conf", "avg_neg_conf", "class_
 
 
 _loss_param_cache: Dict[tuple, LossParams] = {}
+_FORMS = {"decoded": _lib.LOSS_DECODED, "raw": _lib.LOSS_RAW, "split": _lib.LOSS_RAW_SPLIT}
 
 
-def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
+def _loss_params(shapes, C_cls, extra, nt, anchors3, cfg, form) -> LossParams:
     """The parameter block of bg_loss_fwd / bg_loss_bwd; built once per (shapes, target count, anchors, weights)."""
     akey = tuple(tuple(map(tuple, _anchors_host(a))) for a in anchors3)   # by value
     sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
-    key = (tuple(x.shape for x in preds3), targets.shape[0], akey, cfg.get("anchor_t", 4.0), cfg.get("edge_t", 0.5),
-           cfg.get("label_smoothing", 0.0), cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), tuple(sw))
+    key = (shapes, C_cls, extra, nt, akey, cfg.get("anchor_t", 4.0), cfg.get("edge_t", 0.5), cfg.get("label_smoothing", 0.0),
+           cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), tuple(sw), form)
     hit = _loss_param_cache.get(key)
     if hit is not None:
         return hit
     if len(_loss_param_cache) > 256:
         _loss_param_cache.clear()
     p = _loss_param_cache[key] = LossParams()
-    B, _, _, na, D = preds3[0].shape
-    p.B, p.C, p.na = B, D - 5, na
-    for s, x in enumerate(preds3):
-        p.ny[s], p.nx[s] = x.shape[1], x.shape[2]
-        for a, (w, h) in enumerate(_anchors_host(anchors3[s])):
+    B, _, _, na = shapes[0]
+    p.B, p.C, p.na = B, C_cls, na
+    for s, sh in enumerate(shapes):
+        if sh[0] != B or sh[3] != na:
+            raise RuntimeError("detection_loss: inconsistent prediction shapes")
+        p.ny[s], p.nx[s] = sh[1], sh[2]
+        anc = _anchors_host(anchors3[s])
+        if len(anc) != na:
+            raise RuntimeError("detection_loss: anchors do not match the prediction tensors")
+        for a, (w, h) in enumerate(anc):
             p.anchors[s][a][0] = w
             p.anchors[s][a][1] = h
     p.anchor_t, p.edge_t = float(cfg.get("anchor_t", 4.0)), float(cfg.get("edge_t", 0.5))
@@ -511,39 +559,72 @@ def _loss_params(preds3, targets, anchors3, cfg) -> LossParams:
     p.box_w, p.conf_w, p.class_w = float(cfg.get("box_w", 1.0)), float(cfg.get("conf_w", 1.0)), float(cfg.get("class_w", 1.0))
     for s in range(3):
         p.scale_w[s] = float(sw[s])
-    p.nt = targets.shape[0]
+    p.nt = nt
+    p.input_form = form
+    p.extra_cols = extra
     return p
+
+
+def _head_ptrs(tensors, split: bool):
+    arr = _lib.HeadPtrs3()
+    if split:
+        for s in range(3):
+            arr[s].obj, arr[s].cls, arr[s].box = (tensors[3 * s].data_ptr(), tensors[3 * s + 1].data_ptr(),
+                                                  tensors[3 * s + 2].data_ptr())
+    else:
+        for s in range(3):
+            arr[s].obj = tensors[s].data_ptr()
+    return arr
 
 
 class _DetLoss(torch.autograd.Function):
     """Forward: assignment + gather + CIoU + objectness/class BCE for the three scales and the combined loss,
-    all on the device, no host sync.  Backward: dense ``grad_preds`` written once per scale; the upstream
-    gradient stays on the device."""
+    all on the device, no host sync.  Backward: dense gradients written once per scale; the upstream
+    gradient stays on the device.  Everything the backward needs lives in a workspace allocated per forward and
+    owned by ``ctx`` -- any number of forwards may precede their backwards (gradient accumulation, several
+    loss modules, a validation loss in between)."""
 
     @staticmethod
-    def forward(ctx, sm, md, lg, targets, params: LossParams, scalars, hist):
+    def forward(ctx, targets, params: LossParams, scalars, hist, status, *tensors):
         L = _lib.lib()
-        dev = sm.device
-        ws = _workspace(dev, "loss", L.bg_loss_workspace_bytes(C.byref(params)))
-        loss = torch.empty(1, dtype=torch.float32, device=dev)
-        check(L.bg_loss_fwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), targets.data_ptr() if targets.numel() else None,
-                            C.byref(params), scalars.data_ptr(), hist.data_ptr(), loss.data_ptr(), ws.data_ptr(),
-                            ws.numel(), _stream()), "bg_loss_fwd")
-        ctx.save_for_backward(sm, md, lg)
+        dev = tensors[0].device
+        split = params.input_form == _lib.LOSS_RAW_SPLIT
+        with _on(dev):
+            ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            check(L.bg_loss_fwd(_head_ptrs(tensors, split), targets.data_ptr() if targets.numel() else None,
+                                C.byref(params), scalars.data_ptr(), hist.data_ptr(), loss.data_ptr(), status.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream(dev)), "bg_loss_fwd")
+        ctx.save_for_backward(*tensors)
         ctx.params, ctx.ws = params, ws
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, go):
-        sm, md, lg = ctx.saved_tensors
+        tensors = ctx.saved_tensors
         L = _lib.lib()
-        grads = [torch.empty_like(x) for x in (sm, md, lg)]
-        if go.dtype != torch.float32 or not go.is_contiguous():
-            go = go.to(torch.float32).contiguous()
-        check(L.bg_loss_bwd(sm.data_ptr(), md.data_ptr(), lg.data_ptr(), C.byref(ctx.params), go.data_ptr(), 1.0,
-                            grads[0].data_ptr(), grads[1].data_ptr(), grads[2].data_ptr(), ctx.ws.data_ptr(),
-                            ctx.ws.numel(), _stream()), "bg_loss_bwd")
-        return grads[0], grads[1], grads[2], None, None, None, None
+        params = ctx.params
+        dev = tensors[0].device
+        split = params.input_form == _lib.LOSS_RAW_SPLIT
+        with _on(dev):
+            if split:
+                # class / box gradients of the three scales share one buffer: one memset clears them all
+                big = [t for i, t in enumerate(tensors) if i % 3]
+                flat = torch.empty(sum(t.numel() for t in big), dtype=torch.float32, device=dev)
+                grads, off = [], 0
+                for i, t in enumerate(tensors):
+                    if i % 3 == 0:
+                        grads.append(torch.empty_like(t))
+                    else:
+                        grads.append(flat[off: off + t.numel()].view(t.shape))
+                        off += t.numel()
+            else:
+                grads = [torch.empty_like(x) for x in tensors]
+            if go.dtype != torch.float32 or not go.is_contiguous():
+                go = go.to(torch.float32).contiguous()
+            check(L.bg_loss_bwd(_head_ptrs(tensors, split), C.byref(params), go.data_ptr(), 1.0, _head_ptrs(grads, split),
+                                ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "bg_loss_bwd")
+        return (None, None, None, None, None, *grads)
 
 
 def _macro_metrics(hist: torch.Tensor, M: int) -> Dict[str, float]:
@@ -560,28 +641,69 @@ def _macro_metrics(hist: torch.Tensor, M: int) -> Dict[str, float]:
     return dict(accuracy=float(tp.sum() / M), f1=float(f1.mean()), precision=float(prec.mean()), recall=float(rec.mean()))
 
 
-def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchors3: Sequence, cfg: dict,
-                   with_metrics: bool = True, return_scalars: bool = False):
+def detection_loss(preds3: Sequence, targets: torch.Tensor, anchors3: Sequence, cfg: dict,
+                   with_metrics: bool = True, return_scalars: bool = False, input_form: str = "decoded",
+                   num_classes: Optional[int] = None):
     """``DetectionLoss.forward`` (modules/detection_loss.py:84-122) for the default configuration.
     Returns ``(loss, metrics_dict)``; ``loss`` is a 0-d tensor attached to autograd through ``preds3``.
-    ``return_scalars=True`` appends the device tensor ``[3, 8]`` float64 of per-scale terms (lbox, lconf, lcls,
-    mean_ciou, avg_pos_conf, avg_neg_conf, M, n_neg) -- what ``shard.allreduce_loss_terms`` combines across ranks."""
-    preds3 = [_req(x, f"preds[{i}]") for i, x in enumerate(preds3)]
+
+    ``input_form``:
+      ``"decoded"``  ``preds3`` = what ``DetectionNet.forward(x)`` returns in training mode (the reference's contract);
+      ``"raw"``      ``preds3`` = the three head outputs ``[B,ny,nx,na,5+C]`` themselves: the training-mode decode of
+                     ``_get_scale_pred`` (modules/detection.py:122,125) is fused into the loss, the gradient comes back
+                     with respect to the logits;
+      ``"split"``    ``preds3`` = three ``(conf [B,ny,nx,na], cls [B,ny,nx,na,C], bbox [B,ny,nx,na,4])`` triples, the
+                     head's conv outputs before ``EffiDecHead.forward`` concatenates them (modules/common.py:908-919).
+    ``num_classes`` is only needed when interleaved rows carry trailing columns (mask coefficients / keypoints),
+    which the loss skips.  ``return_scalars=True`` appends the device tensor ``[3, 8]`` float64 of per-scale terms
+    (lbox, lconf, lcls, mean_ciou, avg_pos_conf, avg_neg_conf, M, n_neg) -- what ``shard.allreduce_loss_terms``
+    combines across ranks.  A target row that names an image outside the batch or a class outside ``0..C-1`` makes
+    the reference raise IndexError; here it is dropped on the device and the IndexError is raised when the metrics
+    are read (``with_metrics=True``)."""
+    form = _FORMS[input_form]
+    if form == _lib.LOSS_RAW_SPLIT:
+        tensors = []
+        for i, tri in enumerate(preds3):
+            if len(tri) != 3:
+                raise RuntimeError("detection_loss: the split form takes (conf, cls, bbox) per scale")
+            conf, cls, box = (_req(x, f"preds[{i}]") for x in tri)
+            if conf.dim() == 5 and conf.shape[-1] == 1:
+                conf = conf.reshape(conf.shape[:-1])
+            if conf.dim() != 4 or cls.dim() != 5 or box.dim() != 5 or cls.shape[:4] != conf.shape or box.shape[:4] != conf.shape \
+                    or box.shape[4] != 4:
+                raise RuntimeError("detection_loss: expected conf [B,ny,nx,na], cls [B,ny,nx,na,C], bbox [B,ny,nx,na,4]")
+            tensors += [conf, cls, box]
+        shapes = tuple(tuple(tensors[3 * s].shape) for s in range(3))
+        Cc, extra = int(tensors[1].shape[4]), 0
+    else:
+        tensors = [_req(x, f"preds[{i}]") for i, x in enumerate(preds3)]
+        if len(tensors) != 3 or any(x.dim() != 5 for x in tensors):
+            raise RuntimeError("detection_loss: expected three [B, ny, nx, na, 5+C] tensors")
+        D = int(tensors[0].shape[4])
+        Cc = int(num_classes) if num_classes is not None else D - 5
+        extra = D - 5 - Cc
+        if extra < 0 or any(int(x.shape[4]) != D for x in tensors):
+            raise RuntimeError("detection_loss: rows must hold 5 + num_classes (+ extra) columns")
+        shapes = tuple(tuple(x.shape[:4]) for x in tensors)
     targets = _req(targets, "targets")
     if targets.dim() != 2 or targets.shape[1] != 6:
         raise RuntimeError("detection_loss: keypoint targets are out of scope for the CUDA path")
-    dev = preds3[0].device
-    params = _loss_params(preds3, targets, anchors3, cfg)
-    Cc = params.C
+    dev = _same_device(*tensors, targets)
+    params = _loss_params(shapes, Cc, extra, int(targets.shape[0]), anchors3, cfg, form)
     scalars = torch.empty(3, 8, dtype=torch.float64, device=dev)
     hist = torch.empty(3, 3, Cc, dtype=torch.int64, device=dev)
-    loss = _DetLoss.apply(preds3[0], preds3[1], preds3[2], targets, params, scalars, hist)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    loss = _DetLoss.apply(targets, params, scalars, hist, status, *tensors)
     if cfg.get("batch_scale_loss"):
-        loss = loss * preds3[-1].shape[0]
+        loss = loss * shapes[-1][0]
     if not with_metrics:
         return (loss, {}, scalars) if return_scalars else (loss, {})
     # one D2H copy for everything the reference fetches with ~28 .item() calls
-    host = torch.cat([scalars.reshape(-1), hist.reshape(-1).double(), loss.detach().double().reshape(1)]).cpu()
+    host = torch.cat([scalars.reshape(-1), hist.reshape(-1).double(), loss.detach().double().reshape(1),
+                      status.double()]).cpu()
+    if int(host[-1]):
+        raise IndexError("detection_loss: a target row names an image outside the batch or a class outside "
+                         "0..num_classes-1 (index out of range)")
     sc = host[:24].reshape(3, 8)
     hh = host[24:24 + 9 * Cc].reshape(3, 3, Cc).long()
     rows = []
@@ -591,7 +713,7 @@ def detection_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, anchor
                  avg_neg_conf=float(sc[s, 5]), class_loss=float(sc[s, 2]) if M else float("nan"))
         m.update(_macro_metrics(hh[s], M))
         rows.append(m)
-    metrics = {"aggregate_loss": float(host[-1])}
+    metrics = {"aggregate_loss": float(host[-2])}
     for k in METRIC_KEYS:
         vals = [r[k] for r in rows if r[k] == r[k]]  # pandas column mean skips NaN (:117-121)
         metrics[k] = sum(vals) / len(vals) if vals else float("nan")
@@ -604,8 +726,9 @@ def ratio_metrics_w_extras(anchors, wh_data: torch.Tensor, threshold: float = 4.
     wh = _req(wh_data, "wh_data").reshape(-1, 2)
     anc = _anchors_host(anchors)
     out = torch.empty(3, dtype=torch.float64, device=wh.device)
-    check(_lib.lib().bg_ratio_metrics(wh.data_ptr(), wh.shape[0], _anchor_array(anc), len(anc), float(threshold),
-                                      out.data_ptr(), _stream()), "bg_ratio_metrics")
+    with _on(wh.device):
+        check(_lib.lib().bg_ratio_metrics(wh.data_ptr(), wh.shape[0], _anchor_array(anc), len(anc), float(threshold),
+                                          out.data_ptr(), _stream(wh.device)), "bg_ratio_metrics")
     s, m, n = out.cpu().tolist()
     nan = float("nan")
     return (s / n if n else nan, m / n if n else nan, m)
