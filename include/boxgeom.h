@@ -129,6 +129,10 @@ int bg_post_process(const float *preds, const bg_detect_params *p /*host*/, floa
 /* Profiling hook for bench.py: when both are non-NULL, the next bg_detect call records `start`/`stop`
  * (cudaEvent_t) on its stream immediately around the decode+filter kernel, then clears the hook. */
 void bg_profile_events(void *start, void *stop);
+/* The same for bg_loss_bwd: events around its dense-gradient fill (loss_bwd_stream_kernel for interleaved rows; the
+ * memsets + objectness-plane kernel for the split form), i.e. before the matched-row kernel.  Hooks are per host
+ * thread: the thread that arms one is the thread whose next call consumes it. */
+void bg_profile_events_loss(void *start, void *stop);
 /* Profiling hook: while `dev_buf` ([B, bg_profile_stamps_per_image()] u64, device) is non-NULL, the per-image NMS
  * kernel of bg_detect writes the %globaltimer value (ns) at each of its stage boundaries for every image. */
 void bg_profile_stamps(void *dev_buf);
@@ -144,6 +148,17 @@ void bg_profile_decode_cycles(void *dev_buf);
 int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
                     const float *anchors /*host [na,2]*/, int32_t H, int32_t W, int32_t inference, int32_t og_H,
                     int32_t og_W, void *stream);
+
+/* DetectionNet._bbox_to_size (modules/detection.py:175-190) as called at :79-81, in place on decoded rows of D floats
+ * (box columns at C+1..C+4): box = (box / from) * to; from4 / to4 are the DEVICE int64[4] tensors [W,H,W,H] /
+ * [W0,H0,W0,H0] the reference builds at :77-78 (read on the device: no host sync). */
+int bg_bbox_to_size(float *pred, int64_t rows, int32_t C, int32_t D, const int64_t *from4, const int64_t *to4, void *stream);
+
+/* Backward of the training-mode decode (inference = 0 above; modules/detection.py:122,125,164), rows of 5+C floats:
+ * grad_raw = grad_out on the objectness / class columns, grad_out * 2s(1-s) on x, y, grad_out * 8s^2(1-s) on w, h,
+ * s = sigmoid(raw).  Makes DetectionNet._get_scale_pred differentiable on the CUDA path when its result is consumed
+ * by something other than the fused loss (which takes the logits directly, BG_LOSS_RAW). */
+int bg_decode_train_bwd(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, void *stream);
 
 /* ------------------------------------------------------------------ B1
  * DetectionDataset.build_target_by_scale (dataset/detection_dataset.py:90-246), detection branch.

@@ -155,7 +155,7 @@ def post_process(preds, iou_threshold: float, score_threshold: float, box_allowa
     if tracked_classes:
         keep = keep[np.isin(cls[keep], np.asarray(tracked_classes))]
     pb = np.concatenate([score[keep, None], cls[keep, None].astype(np.float32), xyxy[keep]], axis=1)
-    return {"pred_boxes": pb, "sample_idxs": sample[keep], "keep": keep}
+    return {"pred_boxes": pb, "sample_idxs": sample[keep], "keep": keep, "score": score, "cls": cls, "xyxy": xyxy}
 
 
 # ------------------------------------------------------------------- training side

@@ -1,9 +1,11 @@
-"""Import the *unmodified* reference from /root/reference (build container only).
+"""Import the *unmodified* reference: from /root/reference in the build container, or from the untouched copy
+``baseline/_ref/`` that ``__graft_entry__.build()`` makes there (git-ignored, but it travels to the GPU box with
+the snapshot; the reference is a script tree without setup.py / pyproject.toml, so "installing" it is a copy).
 
-TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` to generate the committed
-fixtures under ``tests/golden/`` and by the ``-m "not gpu"`` tests that diff the
-oracle against the live reference when it is present.  The GPU box has no
-/root/reference: nothing that runs there imports this module.
+TEST INFRASTRUCTURE.  Used by ``oracle/make_golden.py`` to generate the committed fixtures under ``tests/golden/``,
+by the tests that run the drop-in layer on the REAL reference classes and compare patched against unpatched
+results, and by ``bench.py``'s reference arm / ``gpu_library_baseline`` leg (the reference's own code on the
+host cores and on torch-CUDA / torchvision-CUDA).  Never imported by the product.
 
 Recipe from SURVEY.md Appendix B: the reference imports ``supervision`` at module
 top (utils/utils.py:11, inference_det.py:12), which is not installed, so a stub
@@ -16,11 +18,34 @@ import os
 import sys
 import types
 
-REF = os.environ.get("BOXGEOM_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find():
+    for cand in (os.environ.get("BOXGEOM_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "modules", "detection_loss.py")):
+            return cand
+    return os.environ.get("BOXGEOM_REFERENCE", "/root/reference")
+
+
+REF = _find()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REF, "modules", "detection_loss.py"))
+
+
+def install_copy(dst=None) -> str:
+    """Copy the reference's source tree (code and configs; not its 4 MB of PNG/PDF resources) to baseline/_ref."""
+    import shutil
+    dst = dst or os.path.join(_ROOT, "baseline", "_ref")
+    src = "/root/reference"
+    if not os.path.isfile(os.path.join(src, "modules", "detection_loss.py")):
+        raise RuntimeError("no reference at %s" % src)
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns("resources", ".git", "__pycache__", "*.pyc"))
+    return dst
 
 
 _mods = None
@@ -79,6 +104,13 @@ def load():
     return ns
 
 
+def model_config() -> dict:
+    """``model_config`` of the reference's config/detection/config.yaml (CSPBackBone + RepBiPAN + EffiDecHead)."""
+    import yaml
+    with open(os.path.join(REF, "config", "detection", "config.yaml")) as f:
+        return yaml.safe_load(f)["model_config"]
+
+
 def ref_decode_inference(raws, anchors3, H, W, og_size=None, num_classes=80):
     """Runs the reference's own _get_scale_pred x3, the rescale guard and the reshape/cat of
     DetectionNet.forward (modules/detection.py:69-91) starting from the three head outputs."""
@@ -135,7 +167,7 @@ def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_all
         inf.Image = _NullImg
         inf.STORAGE_PATH = tmp
         B = preds.shape[0]
-        imgs = torch.zeros(B, 3, 8, 8, dtype=torch.uint8)
+        imgs = torch.zeros(B, 3, 8, 8, dtype=torch.uint8, device=preds.device)
         with torch.no_grad():
             inf.post_process_preds(imgs, preds.clone(), num_classes, iou_threshold=iou_threshold,
                                    score_threshold=score_threshold, box_allowance=box_allowance,

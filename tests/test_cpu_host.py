@@ -78,9 +78,13 @@ def test_dropin_keeps_reference_signatures():
         "ciou": inspect.signature(ns.DetectionLoss.compute_ciou),
         "fwd": inspect.signature(ns.DetectionLoss.forward),
         "gsp": inspect.signature(ns.DetectionNet._get_scale_pred),
+        "b2s": inspect.signature(ns.DetectionNet._bbox_to_size),
+        "grid": inspect.signature(ns.DetectionNet._make_2dgrid),
+        "rm": inspect.signature(ns.make_anchors.ratio_metrics),
+        "rmx": inspect.signature(ns.make_anchors.ratio_metrics_w_extras),
         "nms": inspect.signature(torchvision.ops.batched_nms),
     }
-    dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet)
+    dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, make_anchors=ns.make_anchors)
     try:
         assert all(dropin.installed().values())
         after = {
@@ -88,6 +92,10 @@ def test_dropin_keeps_reference_signatures():
             "ciou": inspect.signature(ns.DetectionLoss.compute_ciou),
             "fwd": inspect.signature(ns.DetectionLoss.forward),
             "gsp": inspect.signature(ns.DetectionNet._get_scale_pred),
+            "b2s": inspect.signature(ns.DetectionNet._bbox_to_size),
+            "grid": inspect.signature(ns.DetectionNet._make_2dgrid),
+            "rm": inspect.signature(ns.make_anchors.ratio_metrics),
+            "rmx": inspect.signature(ns.make_anchors.ratio_metrics_w_extras),
             "nms": inspect.signature(torchvision.ops.batched_nms),
         }
         for k in before:
@@ -102,6 +110,13 @@ def test_dropin_keeps_reference_signatures():
         # the segmentation / keypoint variants of build_target_by_scale run on the CUDA kernel too: CPU refused
         with pytest.raises(RuntimeError, match="CUDA"):
             ns.DetectionDataset.build_target_by_scale(synth.targets(2, 3), (20, 20), synth.anchors_tensor("lg"), overlap_masks=False)
+        # host tensors keep the reference's own anchor-fit metrics (train_det.py builds them from the label files)
+        wh = 0.02 + 0.3 * torch.rand(50, 2)
+        anc9 = torch.tensor(sum((synth.ANCHORS[k] for k in synth.SCALES), []))
+        assert ns.make_anchors.ratio_metrics(anc9, wh) == _saved_ratio(dropin)(anc9, wh)
+        # the cell grid stays the reference's own (cached per shape)
+        net = ns.DecodeOnly(80)
+        assert torch.equal(ns.DetectionNet._make_2dgrid(net, 5, 4), _saved_grid(dropin)(net, 5, 4))
         # out-of-scope variants are delegated to the reference's original callable (broadcasting CIoU form)
         p4 = torch.rand(2, 5, 4) + 0.1
         assert ns.DetectionLoss.compute_ciou(p4, p4[:, 0]).shape[:2] == (2, 5)
@@ -110,6 +125,49 @@ def test_dropin_keeps_reference_signatures():
     assert not any(dropin.installed().values())
     ref = ns.DetectionDataset.build_target_by_scale(synth.targets(1, 3), (20, 20), synth.anchors_tensor("lg"))
     assert len(ref) == 6
+
+
+def _saved_ratio(dropin):
+    return dropin._saved["ratio_metrics"][1]
+
+
+def _saved_grid(dropin):
+    return dropin._saved["_make_2dgrid"][1]
+
+
+def test_lazy_decoded_stand_in_mechanics():
+    """lazy.LazyDecoded (what the patched _get_scale_pred returns in training mode): metadata comes from the logits
+    without materialising; any torch function on it sees the decoded tensor; autograd reaches the logits.  The
+    materialiser is stubbed here (the real one is the CUDA decode) with the reference's own arithmetic."""
+    from vision_conglomerate_b200 import lazy, ops
+    C = 3
+    raw = torch.randn(2, 4, 4, 3, 5 + C, requires_grad=True)
+
+    def ref_decode(x):  # modules/detection.py:122,125,164
+        xy = x[..., C + 1:C + 3].sigmoid() * 2 - 0.5
+        wh = (x[..., C + 3:C + 5].sigmoid() * 2).pow(2)
+        return torch.cat((x[..., :C + 1], xy, wh), dim=-1)
+
+    real = ops.decode_train
+    ops.decode_train = ref_decode
+    try:
+        z = lazy.LazyDecoded(raw)
+        assert isinstance(z, torch.Tensor) and z.pending
+        assert z.shape == raw.shape and z.shape[0] == 2 and z.dim() == 5 and z.dtype == raw.dtype and z.device == raw.device
+        assert z.requires_grad and len(z) == 2 and z.numel() == raw.numel() and z.is_contiguous()
+        assert z.pending and lazy.logits_if_pending((z, z, z))[0] is raw       # none of that materialised it
+        sm, md, lg = (z, z, z)                                                 # tuple packing / unpacking neither
+        assert sm.pending
+        got = z[..., C + 1:]                                                   # a real consumer: decoded values
+        assert not z.pending and lazy.logits_if_pending((z,)) is None
+        assert torch.equal(got, ref_decode(raw)[..., C + 1:]) and type(got) is torch.Tensor
+        (z * 1.0).sum().backward()
+        exp = torch.autograd.grad(ref_decode(raw).sum(), raw)[0]
+        assert torch.allclose(raw.grad, exp)
+        z2 = lazy.LazyDecoded(raw.detach())
+        assert torch.equal(torch.cat([z2, z2], 0)[:2], ref_decode(raw.detach()))   # functions taking lists see it too
+    finally:
+        ops.decode_train = real
 
 
 def test_shard_range_partitions():

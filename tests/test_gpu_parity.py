@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import oracle as O
+from oracle.parity import explain_keep_mismatches, summarize
 from vision_conglomerate_b200 import synth
 from tests.util import (ASSIGN_VARIANTS, assign_variant_case, assert_close, canon, digest, golden, rows_canon, rows_order,
                         seg_extra_columns)
@@ -123,8 +124,10 @@ def test_nms_live_torchvision_cpu(ops):
 
 
 # ------------------------------------------------------------------------- decode + NMS (B5, a1-a8)
-def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order="image", max_mismatch=0,
-                      nms_path="auto"):
+def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order="image", nms_path="auto"):
+    """Keep-lists must be identical to the oracle's, except for candidates that are PROVEN marginal (a score or a
+    deciding IoU on the threshold to within the last-bit differences of expf; oracle/parity.py): the measured
+    counts are printed (pytest -s / the captured log) and anything unexplained fails."""
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
     preds = O.decode_inference(raws, anc, H, W, og)
     ref = O.post_process(preds, iou, thr, allow, tracked)
@@ -137,7 +140,9 @@ def _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant,
     assert np.array_equal(img, keep // N)
     assert int(det.counts.sum()) == keep.shape[0]
     miss = np.setxor1d(keep, ref["keep"])
-    assert miss.size <= max_mismatch, f"{miss.size} keep mismatches (allowed {max_mismatch})"
+    par = explain_keep_mismatches(ref["score"], ref["xyxy"], N, ref["keep"], keep, iou, thr)
+    print("keep-list parity B=%d %dx%d %s: %s" % (raws[0].shape[0], H, W, nms_path, summarize(par)))
+    assert not par["unexplained"], summarize(par)
     if order == "global":
         assert np.all(np.diff(rows[:, 0]) <= 0)
     else:
@@ -249,9 +254,7 @@ def test_seg_post_process_golden(ops, name, nms_path):
 ])
 def test_detect_oracle(ops, variant, nms_path, B, H, W, C, dist, og, iou, thr, allow, tracked, order):
     raws = synth.raw_head_outputs(B, H, W, C, dist, seed=7)
-    K = synth.candidates_per_image(H, W) * B
-    _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order, max_mismatch=max(0, K // 5000),
-                      nms_path=nms_path)
+    _detect_vs_oracle(ops, raws, H, W, C, og, iou, thr, allow, tracked, variant, order, nms_path=nms_path)
 
 
 @pytest.mark.parametrize("B,dist,iou", [(1, "T", 0.65), (100, "T", 0.65), (90, "N", 0.4)])
@@ -259,8 +262,7 @@ def test_detect_batch_extremes(ops, B, dist, iou):
     """B = 1 (video frames) and B > #SM/2 (one CTA per image, several look-back windows over the images)."""
     H = W = 128
     raws = synth.raw_head_outputs(B, H, W, 80, dist, seed=3)
-    _detect_vs_oracle(ops, raws, H, W, 80, None, iou, 0.001 if dist == "T" else 0.2, 4, None, 0, "image",
-                      max_mismatch=B // 8)
+    _detect_vs_oracle(ops, raws, H, W, 80, None, iou, 0.001 if dist == "T" else 0.2, 4, None, 0, "image")
 
 
 def test_detect_dense_overlaps_spill(ops):
@@ -343,31 +345,60 @@ def test_detect_pipeline_matches_single_stream(ops, depth):
 
 
 def test_detect_config2_full_size(ops):
-    """BASELINE config 2 (B=64, 640^2, conf 0.001, IoU 0.65, dist T): oracle parity on 4 images, and
-    size-independent properties on the whole batch."""
+    """BASELINE config 2 (B=64, 640^2, conf 0.001, IoU 0.65, dist T): ALL 64 images against the oracle (the
+    oracle needs ~2 s per image and runs one thread per image), plus size-independent properties."""
     B, H, W, C = 64, 640, 640, 80
     raws = synth.raw_head_outputs(B, H, W, C, "T", seed=7)
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
-    graws = [dev(r) for r in raws]
-    det = ops.detect(graws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4)
-    N = synth.candidates_per_image(H, W)
+    det, ref = _detect_vs_oracle(ops, raws, H, W, C, None, 0.65, 0.001, 4, None, 0)
     keep = det.keep_idxs.cpu().numpy()
-    sub = [0, 1, 31, 63]
-    preds = O.decode_inference([r[sub] for r in raws], anc, H, W, None)
-    ref = O.post_process(preds, 0.65, 0.001, 4, None)
-    for j, b in enumerate(sub):
-        got = np.sort(keep[(keep // N) == b] - b * N)
-        exp = np.sort(ref["keep"][(ref["keep"] // N) == j] - j * N)
-        assert np.setxor1d(got, exp).size <= 1, f"image {b}"
+    graws = [dev(r) for r in raws]
     # both decode variants and both row orders agree exactly
     det1 = ops.detect(graws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, variant=1,
                       order="global")
     assert np.array_equal(np.sort(det1.keep_idxs.cpu().numpy()), np.sort(keep))
     assert bool((det1.pred_boxes[1:, 0] <= det1.pred_boxes[:-1, 0]).all())
     # idempotence: batched NMS over the kept boxes, grouped by image, keeps all of them
+    det = ops.detect(graws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4)
     again = ops.batched_nms(det.pred_boxes[:, 2:6].contiguous(), det.pred_boxes[:, 0].contiguous(), det.sample_idxs, 0.65)
     assert again.numel() == keep.shape[0]
     assert int(det.counts.sum()) == keep.shape[0] and int(det.candidates.min()) > 0
+
+
+def test_detect_config4_vs_oracle(ops):
+    """BASELINE config 4 inference side (1280^2, 100,800 candidates per image, dist T: ~6,800 survivors per image,
+    i.e. the 8,192-survivor per-image kernel with the boxes in L2) against the oracle, which runs the reference's
+    NMS over all 100,800 candidates of an image (~30 s per image, one thread per image)."""
+    B, H, W, C = 2, 1280, 1280, 80
+    raws = synth.raw_head_outputs(B, H, W, C, "T", seed=9)
+    det, _ = _detect_vs_oracle(ops, raws, H, W, C, None, 0.65, 0.001, 4, None, 0)
+    assert 4096 < int(det.candidates.max()) <= 8192
+
+
+def test_detect_config5_video_frames(ops):
+    """BASELINE config 5: batch-1 frames at 640^2, dist T+P re-seeded per frame, og_size (720, 1280), IoU 0.35,
+    score 0.3, tracked classes: 50 frames through the B=1 plan, each against the oracle (the oracle processes the
+    50 frames as one batch, one thread per frame)."""
+    F, H, W, C = 50, 640, 640, 80
+    tracked = list(synth.tracked_classes_default())
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    frames = [synth.raw_head_outputs(1, H, W, C, "TP", seed=7 + f) for f in range(F)]
+    stacked = [torch.cat([fr[s] for fr in frames], 0) for s in range(3)]
+    ref = O.post_process(O.decode_inference(stacked, anc, H, W, (720, 1280)), 0.35, 0.3, 4, tracked)
+    N = synth.candidates_per_image(H, W)
+    plan = ops.DetectPlan([tuple(r.shape) for r in frames[0]], anc, (H, W), C, torch.device("cuda", 0), (720, 1280), 0.35, 0.3,
+                          4, tracked)
+    got = []
+    for f, fr in enumerate(frames):
+        plan.enqueue([dev(r) for r in fr])
+        d = plan.result()
+        assert int(d.counts[0]) == d.keep_idxs.numel()
+        got.append(d.keep_idxs.cpu().numpy() + f * N)
+    got = np.concatenate(got)
+    par = explain_keep_mismatches(ref["score"], ref["xyxy"], N, ref["keep"], got, 0.35, 0.3)
+    print("keep-list parity config 5 (50 frames, B=1): " + summarize(par))
+    assert not par["unexplained"], summarize(par)
+    assert got.size > 0
 
 
 @pytest.mark.parametrize("name", ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"])
@@ -504,6 +535,191 @@ def test_loss_config3_shard(ops):
         assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
     for a, b in zip(grads, ref_g):
         assert_close(a, b, rtol=1e-4, atol=1e-9, what="grad")
+
+
+def _split(p, C):
+    return (p[..., 0].contiguous(), p[..., 1:1 + C].contiguous(), p[..., 1 + C:].contiguous())
+
+
+@pytest.mark.parametrize("name", ["lossraw_sq64", "lossraw_collide", "lossraw_empty", "lossraw_c1_640"])
+def test_loss_raw_and_split_golden(ops, name):
+    """the loss from the head's own logits -- interleaved rows (`raw`) and the head's three conv
+    outputs (`split`) -- against the UNMODIFIED reference running _get_scale_pred(inference=False) + DetectionLoss on
+    the same logits, gradients with respect to the logits (tests/golden/lossraw_*.npz)."""
+    g = golden(name)
+    B, H, W, C, G, fixed, ts, ps = (int(v) for v in g["params"])
+    t = synth.targets(B, G, C, ts, bool(fixed)) if G > 0 else torch.zeros(0, 6)
+    raws = synth.train_preds(B, H, W, C, ps)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    td = dev(t) if t.numel() else torch.zeros(0, 6).cuda()
+    gp = [dev(p).requires_grad_(True) for p in raws]
+    loss, metrics = ops.detection_loss(gp, td, anc, synth.LOSS_CONFIG, input_form="raw")
+    loss.backward()
+    assert_close(float(loss), float(g["loss"]), rtol=1e-5, atol=0, what="loss vs reference")
+    for k, v in dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"])).items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    grads = [p.grad.cpu().numpy() for p in gp]
+    for sc, gr in zip(synth.SCALES, grads):
+        if "grad_" + sc in g.files:
+            assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
+        else:
+            assert_close(gr[..., 0].astype(np.float64).sum(), float(g["grad_" + sc + "_obj_sum"]), rtol=1e-4, atol=1e-7)
+            assert_close(np.abs(gr.astype(np.float64)).sum(), float(g["grad_" + sc + "_abs_sum"]), rtol=1e-4)
+            ix = g["grad_" + sc + "_rows_idx"]
+            assert_close(gr[ix[:, 0], ix[:, 1], ix[:, 2], ix[:, 3]], g["grad_" + sc + "_rows"], rtol=1e-4, atol=1e-7)
+    # the split form: same arithmetic on the three column groups -> identical loss and gradients, piece by piece
+    tri = [tuple(x.requires_grad_(True) for x in _split(dev(p), C)) for p in raws]
+    loss_s, metrics_s = ops.detection_loss(tri, td, anc, synth.LOSS_CONFIG, input_form="split")
+    loss_s.backward()
+    assert float(loss_s) == float(loss)
+    assert all(metrics_s[k] == metrics[k] or (metrics_s[k] != metrics_s[k] and metrics[k] != metrics[k]) for k in metrics)
+    for gr, (c, k, b) in zip(grads, tri):
+        assert np.array_equal(gr[..., 0], c.grad.cpu().numpy())
+        assert np.array_equal(gr[..., 1:1 + C], k.grad.cpu().numpy())
+        assert np.array_equal(gr[..., 1 + C:], b.grad.cpu().numpy())
+    # and the decoded form fed with the reference's own decode of the logits gives the same loss
+    dec = [ops.decode_scale(dev(p), a, (H, W), False) for p, a in zip(raws, anc)]
+    loss_d, _ = ops.detection_loss(dec, td, anc, synth.LOSS_CONFIG, with_metrics=False)
+    assert_close(float(loss_d), float(loss), rtol=1e-6, atol=0, what="decoded form vs raw form")
+
+
+def test_loss_forms_vs_oracle_config3_shard(ops):
+    """The raw and split forms at the per-GPU shard of config 3 (B=32, 100 gt/img) against the oracle
+    (decode + loss + chain rule), incl. the dense gradient."""
+    B, H, W, C = 32, 640, 640, 80
+    t = synth.targets(B, 100, C, 0)
+    raws = synth.train_preds(B, H, W, C, 1)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    ref_loss, ref_m, ref_g, _ = O.detection_loss(raws, t, anc, synth.LOSS_CONFIG, with_grad=True, input_form="raw")
+    gp = [dev(p).requires_grad_(True) for p in raws]
+    loss, metrics = ops.detection_loss(gp, dev(t), anc, synth.LOSS_CONFIG, input_form="raw")
+    loss.backward()
+    assert_close(float(loss), ref_loss, rtol=1e-5, what="loss (raw)")
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for a, b in zip(gp, ref_g):
+        assert_close(a.grad.cpu().numpy(), b, rtol=1e-4, atol=1e-9, what="grad (raw)")
+    tri = [tuple(x.requires_grad_(True) for x in _split(dev(p), C)) for p in raws]
+    loss_s, _ = ops.detection_loss(tri, dev(t), anc, synth.LOSS_CONFIG, input_form="split", with_metrics=False)
+    loss_s.backward()
+    assert float(loss_s) == float(loss)
+    for a, (c, k, b) in zip(gp, tri):
+        assert torch.equal(a.grad[..., 0], c.grad) and torch.equal(a.grad[..., 1:1 + C], k.grad) and torch.equal(a.grad[..., 1 + C:], b.grad)
+
+
+def test_loss_config4_vs_oracle(ops):
+    """BASELINE config 4 training side at full size: B=32 at 1280^2 (100,800 cells/img), 300 gt/img, against the
+    oracle incl. the dense gradient (1.1 GB per tensor set)."""
+    B, H, W, C = 32, 1280, 1280, 80
+    t = synth.targets(B, 300, C, 0)
+    preds = synth.train_preds(B, H, W, C, 1)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    ref_loss, ref_m, ref_g, Ms = O.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_grad=True)
+    loss, metrics, grads = _loss_case(ops, B, H, W, C, t, preds)
+    assert_close(float(loss), ref_loss, rtol=1e-5, what="loss")
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for a, b in zip(grads, ref_g):
+        assert_close(a, b, rtol=1e-4, atol=1e-9, what="grad")
+    assert sum(Ms) > 300000
+
+
+def test_loss_forwards_may_precede_their_backwards(ops):
+    """Two forwards, then their two backwards (gradient accumulation, several loss modules, a validation loss in
+    between): every forward owns the state its backward reads.  Each gradient must equal the one obtained alone."""
+    B, H, W, C = 4, 128, 128, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    ta, tb = dev(synth.targets(B, 12, C, 0)), dev(synth.targets(B, 7, C, 5, fixed=False))
+    pa = [dev(p).requires_grad_(True) for p in synth.train_preds(B, H, W, C, 1)]
+    pb = [dev(p).requires_grad_(True) for p in synth.train_preds(B, H, W, C, 2)]
+
+    def alone(p, t):
+        q = [x.detach().clone().requires_grad_(True) for x in p]
+        l, _ = ops.detection_loss(q, t, anc, synth.LOSS_CONFIG, with_metrics=False)
+        l.backward()
+        return float(l), [x.grad.clone() for x in q]
+
+    la_ref, ga_ref = alone(pa, ta)
+    lb_ref, gb_ref = alone(pb, tb)
+    la, _ = ops.detection_loss(pa, ta, anc, synth.LOSS_CONFIG, with_metrics=False)
+    lb, _ = ops.detection_loss(pb, tb, anc, synth.LOSS_CONFIG, with_metrics=False)      # second forward before the first backward
+    with torch.no_grad():
+        ops.detection_loss([x.detach() for x in pb], ta, anc, synth.LOSS_CONFIG)        # an evaluation loss in between
+    (la + 2.0 * lb).backward()
+    assert float(la) == la_ref and float(lb) == lb_ref
+    for x, r in zip(pa, ga_ref):
+        assert torch.equal(x.grad, r)
+    for x, r in zip(pb, gb_ref):
+        assert_close(x.grad.cpu().numpy(), (2.0 * r).cpu().numpy(), rtol=1e-6, atol=0, what="scaled upstream gradient")
+    oracle_loss, _, og, _ = O.detection_loss([p.detach().cpu() for p in pa], ta.cpu(), anc, synth.LOSS_CONFIG, with_grad=True)
+    assert_close(la_ref, oracle_loss, rtol=1e-5, what="loss vs oracle")
+    for x, r in zip(pa, og):
+        assert_close(x.grad.cpu().numpy(), r, rtol=1e-4, atol=1e-9, what="grad vs oracle")
+
+
+def test_loss_rejects_out_of_range_ids(ops):
+    """Image ids outside 0..B-1 and class ids outside 0..C-1: the reference raises IndexError (preds[batch_idx, ...],
+    t_cls[range, classes]); the CUDA path drops those rows on the device -- no out-of-bounds access -- and raises
+    the IndexError with the metrics read."""
+    B, H, W, C = 2, 128, 128, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = [dev(p).requires_grad_(True) for p in synth.train_preds(B, H, W, C, 1)]
+    good = synth.targets(B, 9, C, 0)
+    for col, val in ((0, float(B)), (0, 57.0), (1, float(C)), (1, 1.0e6)):
+        bad = good.clone()
+        bad[3, col] = val
+        with pytest.raises(IndexError):
+            ops.detection_loss(preds, dev(bad), anc, synth.LOSS_CONFIG)
+        loss, _ = ops.detection_loss(preds, dev(bad), anc, synth.LOSS_CONFIG, with_metrics=False)
+        loss.backward()                                          # nothing is corrupted: the bad row is simply absent
+        keep = torch.ones(bad.shape[0], dtype=torch.bool)
+        keep[3] = False
+        ref, _ = ops.detection_loss([p.detach() for p in preds], dev(good[keep]), anc, synth.LOSS_CONFIG, with_metrics=False)
+        assert_close(float(loss), float(ref), rtol=1e-6, atol=0, what="loss without the bad row")
+    assert all(bool(torch.isfinite(p.grad).all()) for p in preds)
+
+
+def test_ratio_metrics_is_deterministic(ops):
+    g = np.random.default_rng(3)
+    wh = torch.from_numpy(g.uniform(0.01, 0.6, size=(300000, 2)).astype(np.float32)).cuda()
+    anc = torch.tensor(sum((synth.ANCHORS[s] for s in synth.SCALES), []), dtype=torch.float32)
+    first = ops.ratio_metrics_w_extras(anc, wh, 4.0)
+    assert all(ops.ratio_metrics_w_extras(anc, wh, 4.0) == first for _ in range(5))
+    ref = O.ratio_metrics(anc, wh.cpu(), 4.0)
+    assert_close(np.array(first), np.array([ref[0] / ref[2], ref[1] / ref[2], ref[1]]), rtol=1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_follow_the_tensors_device(ops):
+    """The reference's DDP path addresses ranks as cuda:k without calling torch.cuda.set_device: every operator must
+    run on the device (and stream) of its tensors, whatever the current device is."""
+    assert torch.cuda.current_device() == 0
+    d1 = torch.device("cuda", 1)
+    B, H, W, C = 2, 128, 128, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    t = synth.targets(B, 9, C, 0)
+    preds = synth.train_preds(B, H, W, C, 1)
+    p0 = [p.cuda(0).requires_grad_(True) for p in preds]
+    p1 = [p.to(d1).requires_grad_(True) for p in preds]
+    l0, m0 = ops.detection_loss(p0, t.cuda(0), anc, synth.LOSS_CONFIG)
+    l1, m1 = ops.detection_loss(p1, t.to(d1), anc, synth.LOSS_CONFIG)
+    l0.backward()
+    l1.backward()
+    assert l1.device == d1 and float(l0) == float(l1) and m0 == m1
+    for a, b in zip(p0, p1):
+        assert b.grad.device == d1 and torch.equal(a.grad.cpu(), b.grad.cpu())
+    raws = synth.raw_head_outputs(B, H, W, C, "TP", seed=7)
+    a = ops.detect([r.cuda(0) for r in raws], anc, (H, W), C, iou_threshold=0.5, score_threshold=0.01, box_allowance=4)
+    b = ops.detect([r.to(d1) for r in raws], anc, (H, W), C, iou_threshold=0.5, score_threshold=0.01, box_allowance=4)
+    assert b.pred_boxes.device == d1 and torch.equal(a.pred_boxes.cpu(), b.pred_boxes.cpu()) and torch.equal(a.keep_idxs.cpu(), b.keep_idxs.cpu())
+    bx, sx, ix = synth.nms_boxes(3000, 3, seed=5)
+    assert torch.equal(ops.batched_nms(bx.cuda(0), sx.cuda(0), ix.cuda(0), 0.5).cpu(), ops.batched_nms(bx.to(d1), sx.to(d1), ix.to(d1), 0.5).cpu())
+    idx0 = ops.build_target_by_scale(t.cuda(0), (16, 16), anc[0])
+    idx1 = ops.build_target_by_scale(t.to(d1), (16, 16), anc[0])
+    assert idx1[1].device == d1 and torch.equal(torch.stack(idx0[0]).cpu(), torch.stack(idx1[0]).cpu())
+    assert torch.cuda.current_device() == 0
+    with pytest.raises(RuntimeError, match="one device"):
+        ops.detection_loss(p0, t.to(d1), anc, synth.LOSS_CONFIG)
 
 
 def test_loss_config3_full_size_properties(ops):

@@ -19,6 +19,7 @@ std::atomic<unsigned long long> g_launches{0};
 // profiling hooks are armed per host thread (the thread that arms one is the thread whose next call sees it), so
 // concurrent callers on other threads are unaffected and the entry points stay re-entrant
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static thread_local cudaEvent_t g_prof_loss_start = nullptr, g_prof_loss_stop = nullptr;
 static thread_local unsigned long long *g_prof_stamps = nullptr, *g_prof_cycles = nullptr;
 
 IouThr make_iou_thr(double thr)
@@ -273,6 +274,7 @@ int bg_version(void) { return 200; }  // 200: bg_loss_* take the input form (dec
 
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
+void bg_profile_events_loss(void *start, void *stop) { g_prof_loss_start = (cudaEvent_t)start; g_prof_loss_stop = (cudaEvent_t)stop; }
 void bg_profile_stamps(void *dev_buf) { g_prof_stamps = (unsigned long long *)dev_buf; }
 void bg_profile_decode_cycles(void *dev_buf) { g_prof_cycles = (unsigned long long *)dev_buf; }
 int bg_profile_stamps_per_image(void) { return INMS_STAMPS; }
@@ -543,6 +545,29 @@ int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t
     k.fW = (float)W; k.fH = (float)H; k.fW0 = (float)og_W; k.fH0 = (float)og_H;
     if (anchors) for (int a = 0; a < na; ++a) { k.aw[a] = anchors[2 * a]; k.ah[a] = anchors[2 * a + 1]; }
     decode_scale_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+int bg_bbox_to_size(float *pred, int64_t rows, int32_t C, int32_t D, const int64_t *from4, const int64_t *to4, void *stream)
+{
+    if (rows < 0 || C <= 0 || D < C + 5) return BG_ERR_INVALID;
+    if (rows == 0) return BG_OK;
+    if (!pred || !from4 || !to4) return BG_ERR_INVALID;
+    long long blocks = (rows * 4 + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    bbox_to_size_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, rows, C, D, reinterpret_cast<const long long *>(from4),
+                                                                      reinterpret_cast<const long long *>(to4));
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+int bg_decode_train_bwd(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, void *stream)
+{
+    if (rows < 0 || C <= 0) return BG_ERR_INVALID;
+    if (rows == 0) return BG_OK;
+    if (!raw || !grad_out || !grad_raw) return BG_ERR_INVALID;
+    decode_train_bwd_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(raw, grad_out, grad_raw, rows, C);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -854,6 +879,8 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
     k.go_dev = grad_out_dev;
     k.go_host = grad_out_host;
     const int sms = num_sms();
+    const bool prof = g_prof_loss_start && g_prof_loss_stop;
+    if (prof) cudaEventRecord(g_prof_loss_start, st);
     if (p->input_form == BG_LOSS_RAW_SPLIT) {
         // class / box planes: cleared by memset (adjacent planes are cleared by one call), objectness plane by a kernel
         struct Run { unsigned char *p; size_t n; } runs[6];
@@ -896,6 +923,7 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
         loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
         BG_LAUNCH_CHECK();
     }
+    if (prof) { cudaEventRecord(g_prof_loss_stop, st); g_prof_loss_start = g_prof_loss_stop = nullptr; }
     if (p->nt == 0) return BG_OK;
     if (k.C == 80) return launch_after(loss_bwd_rows_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
     return launch_after(loss_bwd_rows_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);

@@ -536,4 +536,37 @@ __global__ void __launch_bounds__(256) decode_scale_kernel(DecodeK k)
     }
 }
 
+// Backward of the training-mode decode (modules/detection.py:122,125): grad_raw = grad_out on the objectness / class
+// columns, grad_out * 2s(1-s) on x, y and grad_out * 8s^2(1-s) on w, h, with s = sigmoid(raw).
+__global__ void __launch_bounds__(256) decode_train_bwd_kernel(const float *raw, const float *go, float *gr, long long rows, int C)
+{
+    const int D = C + 5;
+    const long long total = rows * D;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % D);
+        float g = __ldg(go + e);
+        if (c > C) {
+            const float s = sigmoid_acc(__ldg(raw + e));
+            const float t = __fmul_rn(s, __fsub_rn(1.0f, s));                    // sigmoid'
+            g = (c - C - 1 < 2) ? __fmul_rn(__fmul_rn(g, 2.0f), t)              // d(2s - 0.5)
+                                : __fmul_rn(__fmul_rn(g, __fmul_rn(4.0f, s)), __fmul_rn(2.0f, t));  // d((2s)^2) = 2*(2s) * 2s'
+        }
+        gr[e] = g;
+    }
+}
+
+// DetectionNet._bbox_to_size (modules/detection.py:175-190) on decoded rows, in place: box = (box / from) * to with
+// from = [W,H,W,H], to = [W0,H0,W0,H0] read from the int64 device tensors the reference builds (:77-78).
+__global__ void __launch_bounds__(256) bbox_to_size_kernel(float *pred, long long rows, int C, int D, const long long *from4,
+                                                           const long long *to4)
+{
+    const long long total = rows * 4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(e & 3);
+        float *p = pred + (e >> 2) * D + C + 1 + q;
+        *p = __fmul_rn(__fdiv_rn(*p, (float)from4[q]), (float)to4[q]);
+    }
+}
+
 }  // namespace bg

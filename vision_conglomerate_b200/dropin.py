@@ -6,9 +6,15 @@ attribute look-ups resolved at call time (``DetectionDataset.build_target_by_sca
 ``DetectionNet._get_scale_pred``).  :func:`install` re-points those attributes at the CUDA operators,
 keeping every signature and return contract, so the host scripts run unmodified.
 
-Variants that are out of scope for the CUDA path (segmentation ``overlap_masks``, keypoint columns,
-focal loss) are delegated to the reference's *own original callable*, which is saved at install time --
-never to a re-implementation of ours.  CPU tensors are refused: there is no CPU fallback.
+Variants that are out of scope for the CUDA path (keypoint columns, focal loss, the segmentation model's loss)
+are delegated to the reference's *own original callable*, which is saved at install time -- never to a
+re-implementation of ours.  CPU tensors are refused: there is no CPU fallback.
+
+Training (``train_det.py``): ``_get_scale_pred(inference=False)`` returns a :class:`lazy.LazyDecoded` stand-in and
+``DetectionLoss.forward`` feeds the head's logits to the fused loss (decode applied in registers, gradient back to
+the logits); nothing else in the reference's step touches the predictions (pipeline/detection_trainer.py:178-184).
+Inference (``inference_det.py``): decode and ``_bbox_to_size`` per scale on the device, ``batched_nms`` on the
+segmented engine.  The fully fused decode+NMS (``ops.detect``) needs the 3-line edit of INTEGRATION.md section 2.
 """
 from __future__ import annotations
 
@@ -17,6 +23,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import ops
+from .lazy import LazyDecoded, logits_if_pending
 
 _saved: Dict[str, Any] = {}
 
@@ -66,7 +73,7 @@ def _make_loss_forward(orig):
             or type(self).loss_fn is not _saved.get("DetectionLoss.loss_fn", type(self).loss_fn)
         )
         if out_of_scope:
-            return orig(self, preds, targets)
+            return orig(self, preds, targets)   # (LazyDecoded predictions materialise themselves there)
         for p in preds:
             _need_cuda(p, "DetectionLoss.forward")
         cfg = dict(anchor_t=self.anchor_t, edge_t=self.edge_t, box_w=self.box_w, conf_w=self.conf_w,
@@ -74,7 +81,11 @@ def _make_loss_forward(orig):
                    batch_scale_loss=self.batch_scale_loss)
         # anchors are read from the module at call time: they live in the state dict (detection.py:36-38)
         anchors3 = [model.sm_anchors.data, model.md_anchors.data, model.lg_anchors.data]
-        return ops.detection_loss(preds, targets.to(preds[0].device, torch.float32), anchors3, cfg)
+        targets = targets.to(preds[0].device, torch.float32)
+        logits = logits_if_pending(preds)
+        if logits is not None:   # straight from the head: the training-mode decode is fused into the loss
+            return ops.detection_loss(logits, targets, anchors3, cfg, input_form="raw")
+        return ops.detection_loss(preds, targets, anchors3, cfg)
     return forward
 
 
@@ -91,18 +102,66 @@ def _make_get_scale_pred(orig):
     def _get_scale_pred(self, scale_pred, anchors, input_shape, inference: bool = False):
         if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
             return orig(self, scale_pred, anchors, input_shape, inference)
-        if scale_pred.requires_grad and torch.is_grad_enabled():
-            # training: the decode must stay differentiable; the fused CUDA decode is inference-only
-            return orig(self, scale_pred, anchors, input_shape, inference)
         _need_cuda(scale_pred, "_get_scale_pred")
+        if not inference:
+            if scale_pred.shape[-1] != self.num_classes + 5:
+                return orig(self, scale_pred, anchors, input_shape, inference)
+            if _options["fuse_train_decode"]:
+                # stands for the decoded tensor; DetectionLoss.forward takes the logits from it, any other consumer
+                # gets the decoded values (differentiable CUDA decode) on first use
+                return LazyDecoded(scale_pred if scale_pred.is_contiguous() else scale_pred.contiguous())
+            return ops.decode_train(scale_pred)
         return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), inference)
     return _get_scale_pred
 
 
-def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True) -> None:
+def _make_bbox_to_size(orig):
+    def _bbox_to_size(self, pred, _from, _to):
+        if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
+            return orig(self, pred, _from, _to)
+        _need_cuda(pred, "_bbox_to_size")
+        return ops.bbox_to_size(pred, _from, _to, self.num_classes)
+    return _bbox_to_size
+
+
+def _make_2dgrid(orig):
+    cache: Dict[Any, torch.Tensor] = {}
+
+    def _make_2dgrid(self, nx, ny, device="cpu"):
+        # never reached under the patched _get_scale_pred (the kernels derive the cell from the row number); kept
+        # callable for other users of the model, built once per (nx, ny, device) by the reference's own code
+        key = (int(nx), int(ny), str(device))
+        if key not in cache:
+            cache[key] = orig(self, nx, ny, device)
+        return cache[key].clone()
+    return _make_2dgrid
+
+
+# ------------------------------------------------------------------------------------------------ a13
+def _make_ratio_metrics(orig, extras: bool):
+    def ratio_metrics(anchors, wh_data, threshold: float = 4.0):
+        if not (isinstance(wh_data, torch.Tensor) and wh_data.is_cuda):
+            return orig(anchors, wh_data, threshold)   # host tensors (what train_det.py builds from the label files)
+        wh = wh_data.to(torch.float32)
+        if extras:
+            return ops.ratio_metrics_w_extras(anchors, wh, threshold)
+        return ops.ratio_metrics(anchors, wh, threshold)
+    ratio_metrics.__name__ = orig.__name__
+    return ratio_metrics
+
+
+_options = {"fuse_train_decode": True}
+
+
+def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True, make_anchors=None,
+            fuse_train_decode: bool = True) -> None:
     """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
     imported in your process (any subset); ``torchvision_ops=True`` also replaces
-    ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time)."""
+    ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time); ``make_anchors`` is the
+    reference's ``utils.make_anchors`` module (``ratio_metrics*``).  ``fuse_train_decode=False`` makes the
+    training-mode ``_get_scale_pred`` return a real decoded tensor (one CUDA kernel each way) instead of the
+    deferred stand-in."""
+    _options["fuse_train_decode"] = bool(fuse_train_decode)
     from . import _lib
     _lib.lib()  # fail loudly now if the extension is not built
     if DetectionDataset is not None and "build_target_by_scale" not in _saved:
@@ -118,14 +177,29 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
     if DetectionNet is not None and "_get_scale_pred" not in _saved:
         _saved["_get_scale_pred"] = (DetectionNet, DetectionNet.__dict__["_get_scale_pred"])
         DetectionNet._get_scale_pred = _make_get_scale_pred(DetectionNet.__dict__["_get_scale_pred"])
+        if "_bbox_to_size" in DetectionNet.__dict__:
+            _saved["_bbox_to_size"] = (DetectionNet, DetectionNet.__dict__["_bbox_to_size"])
+            DetectionNet._bbox_to_size = _make_bbox_to_size(DetectionNet.__dict__["_bbox_to_size"])
+        if "_make_2dgrid" in DetectionNet.__dict__:
+            _saved["_make_2dgrid"] = (DetectionNet, DetectionNet.__dict__["_make_2dgrid"])
+            DetectionNet._make_2dgrid = _make_2dgrid(DetectionNet.__dict__["_make_2dgrid"])
+    if make_anchors is not None and "ratio_metrics" not in _saved:
+        _saved["ratio_metrics"] = (make_anchors, make_anchors.ratio_metrics)
+        _saved["ratio_metrics_w_extras"] = (make_anchors, make_anchors.ratio_metrics_w_extras)
+        make_anchors.ratio_metrics = _make_ratio_metrics(make_anchors.ratio_metrics, False)
+        make_anchors.ratio_metrics_w_extras = _make_ratio_metrics(make_anchors.ratio_metrics_w_extras, True)
     if torchvision_ops and "batched_nms" not in _saved:
         import torchvision
         _saved["batched_nms"] = (torchvision.ops, torchvision.ops.batched_nms)
         torchvision.ops.batched_nms = _make_batched_nms(torchvision.ops.batched_nms)
 
 
+_NAMES = ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "_bbox_to_size", "_make_2dgrid",
+          "batched_nms", "ratio_metrics", "ratio_metrics_w_extras")
+
+
 def uninstall() -> None:
-    for name in ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "batched_nms"):
+    for name in _NAMES:
         if name in _saved:
             owner, orig = _saved.pop(name)
             setattr(owner, name, orig)
@@ -133,4 +207,4 @@ def uninstall() -> None:
 
 
 def installed() -> Dict[str, bool]:
-    return {k: (k in _saved) for k in ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "batched_nms")}
+    return {k: (k in _saved) for k in _NAMES}

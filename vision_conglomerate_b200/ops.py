@@ -426,6 +426,50 @@ def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int]
     return out
 
 
+class _TrainDecode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return decode_scale(x, [[1.0, 1.0]] * x.shape[3], (1, 1), False)
+
+    @staticmethod
+    def backward(ctx, go):
+        (x,) = ctx.saved_tensors
+        go = go.contiguous() if go.dtype == torch.float32 else go.float().contiguous()
+        gr = torch.empty_like(x)
+        with _on(x.device):
+            check(_lib.lib().bg_decode_train_bwd(x.data_ptr(), go.data_ptr(), gr.data_ptr(), x.numel() // x.shape[-1],
+                                                 x.shape[-1] - 5, _stream(x.device)), "bg_decode_train_bwd")
+        return gr
+
+
+def decode_train(scale_pred: torch.Tensor) -> torch.Tensor:
+    """``DetectionNet._get_scale_pred(..., inference=False)`` (modules/detection.py:98-173), differentiable: one CUDA
+    kernel each way instead of ~15 ATen kernels and their autograd graph.  (The fused loss does not need it -- it
+    takes the logits, ``detection_loss(..., input_form="raw")``; this is for every other consumer.)"""
+    return _TrainDecode.apply(_req(scale_pred, "scale_pred"))
+
+
+def bbox_to_size(pred: torch.Tensor, _from: torch.Tensor, _to: torch.Tensor, num_classes: int) -> torch.Tensor:
+    """``DetectionNet._bbox_to_size`` (modules/detection.py:175-190): rescales the box columns of decoded rows in
+    place and returns ``pred.contiguous()`` like the reference.  ``_from`` / ``_to`` are the int64 device tensors the
+    reference builds at :77-78 and are read on the device."""
+    if not pred.is_cuda or pred.dtype != torch.float32:
+        raise RuntimeError("bbox_to_size: the box-geometry kernels need a CUDA fp32 tensor (no CPU fallback exists)")
+    out = pred if pred.is_contiguous() else pred.contiguous()
+    D = out.shape[-1]
+    f = _from.to(device=out.device, dtype=torch.int64).contiguous()
+    t = _to.to(device=out.device, dtype=torch.int64).contiguous()
+    if f.numel() != 4 or t.numel() != 4:
+        raise RuntimeError("bbox_to_size: _from / _to must hold four values")
+    with _on(out.device):
+        check(_lib.lib().bg_bbox_to_size(out.data_ptr(), out.numel() // D, int(num_classes), D, f.data_ptr(), t.data_ptr(),
+                                         _stream(out.device)), "bg_bbox_to_size")
+    if out is not pred:
+        pred.copy_(out)  # the reference writes through `pred` (a view) before returning the contiguous copy
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- B1
 def build_target_by_scale(targets: torch.Tensor, fmap_shape, anchors, anchor_threshold: float = 4.0,
                           edge_threshold: float = 0.5, overlap_masks: Optional[bool] = None,
