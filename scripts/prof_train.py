@@ -17,6 +17,7 @@ ap.add_argument("--gt", type=int, default=100)
 ap.add_argument("--size", type=int, default=640)
 ap.add_argument("--iters", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--form", default="decoded", choices=["decoded", "raw", "split"], help="input form of ops.detection_loss")
 ap.add_argument("--l2-fetch", type=int, default=0, help="experiment: cudaLimitMaxL2FetchGranularity in bytes (32/64/128)")
 a = ap.parse_args()
 if a.l2_fetch:
@@ -35,12 +36,16 @@ t = synth.targets(B, a.gt, C, 0).to(dev)
 g = torch.Generator(device=dev).manual_seed(1)
 preds = [torch.randn(B, ny, nx, 3, 5 + C, generator=g, device=dev).requires_grad_(True) for ny, nx in synth.fmap_shapes(S, S)]
 anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+if a.form == "split":
+    preds = [tuple(y.contiguous().requires_grad_(True) for y in (x.detach()[..., 0], x.detach()[..., 1:1 + C], x.detach()[..., 1 + C:]))
+             for x in preds]
+leaves = [q for p in preds for q in (p if isinstance(p, tuple) else (p,))]
 
 
 def step():
-    for p in preds:
+    for p in leaves:
         p.grad = None
-    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False)
+    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False, input_form=a.form)
     loss.backward()
     return loss
 
@@ -51,9 +56,9 @@ torch.cuda.synchronize()
 e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
 e[0].record()
 for _ in range(a.iters):
-    for p in preds:
+    for p in leaves:
         p.grad = None
-    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False)
+    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False, input_form=a.form)
 e[1].record()
 for _ in range(a.iters):
     step()
@@ -61,4 +66,4 @@ e[2].record()
 torch.cuda.synchronize()
 fwd = e[0].elapsed_time(e[1]) / a.iters
 both = e[1].elapsed_time(e[2]) / a.iters
-print("train B=%d gt=%d S=%d: fwd %.3f ms, fwd+bwd %.3f ms (%.0f img/s), loss %.6f" % (B, a.gt, S, fwd, both, B / both * 1e3, float(loss)))
+print("train form=%s B=%d gt=%d S=%d: fwd %.3f ms, fwd+bwd %.3f ms (%.0f img/s), loss %.6f" % (a.form, B, a.gt, S, fwd, both, B / both * 1e3, float(loss)))
