@@ -124,14 +124,16 @@ def _all_host_threads():
 
 
 # ------------------------------------------------------------------------------------------ CPU arms
-def cpu_oracle_detect(sample_images, steps=1, warmup=0):
-    """The C oracle port of decode + post_process on `sample_images` images of the headline workload.
-    Returns (img/s, threads, seconds per step, oracle result of the last step, raws)."""
+def cpu_oracle_detect(sample_images, steps=1, warmup=0, raws=None):
+    """The C oracle port of decode + post_process on `sample_images` images of the headline workload (`raws`: the
+    images themselves, e.g. the first ones of the batch the GPU arm processed).
+    Returns (img/s, threads, seconds per step, oracle result of the last step)."""
     from oracle import oracle as O
     from vision_conglomerate_b200 import synth
     w = WORKLOAD
     threads = _all_host_threads()
-    raws = synth.raw_head_outputs(sample_images, w["H"], w["W"], w["C"], w["dist"], w["seed"])
+    if raws is None:
+        raws = synth.raw_head_outputs(sample_images, w["H"], w["W"], w["C"], w["dist"], w["seed"])
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
     times, out = [], None
     for it in range(warmup + steps):
@@ -448,7 +450,7 @@ def run_ours(args):
         if k in train:
             line[k] = train[k]
     if world == 1 and not args.no_cpu:
-        line.update(cpu_legs(torch, keep_set0, B))
+        line.update(cpu_legs(torch, keep_set0, B, raws_h))
     if world == 1 and not args.no_extra:
         line["gpu_library_baseline"] = gpu_library_baseline(torch, ops, synth, devc)
         line["extra"] = extras(torch, ops, synth, devc)
@@ -667,7 +669,7 @@ def graphed_step_ms(torch, ops, logits, t_loc, anc, cfg, K, barrier):
     return a.elapsed_time(b) / K
 
 
-def cpu_legs(torch, keep_gpu, B):
+def cpu_legs(torch, keep_gpu, B, raws_h):
     """cpu_baseline (+ parity_check against the oracle on the same images) and cpu_baseline_train."""
     from oracle import ref_harness
     from oracle.parity import explain_keep_mismatches
@@ -675,7 +677,7 @@ def cpu_legs(torch, keep_gpu, B):
     out = {}
     cores = os.cpu_count() or 1
     sample = min(B, max(8, cores))
-    ips, threads, tcpu, ref = cpu_oracle_detect(sample)
+    ips, threads, tcpu, ref = cpu_oracle_detect(sample, raws=[r[:sample].contiguous() for r in raws_h])
     N = synth.candidates_per_image(WORKLOAD["H"], WORKLOAD["W"])
     kg = keep_gpu.cpu().numpy()
     kg = kg[kg < sample * N]

@@ -250,6 +250,14 @@ int bg_loss_bwd(const bg_head_ptrs in[3] /*host*/, const bg_loss_params *p /*hos
                 float grad_out_host, const bg_head_grads grads[3] /*host*/, void *workspace, size_t workspace_bytes,
                 void *stream);
 
+/* Image-sharded training: per-shard sums that add up over the shards, and the big-batch loss from the
+ * summed terms.  pack15 [3,5] f64 per scale = {lbox*M, lconf*cells, lcls*M*C, M, cells}; the caller all-reduces (SUM)
+ * the 15 doubles between the two calls (NCCL).  cells3: host int64[3], this shard's B*ny*nx*na per scale.
+ * bg_loss_combine: out_loss [1] f64 = box_w*sum_s(w_s*lbox_s) + conf_w*... + class_w*... with global means
+ * (modules/detection_loss.py:107-110 on the concatenated batch); only p->C, the weights and scale_w are read. */
+int bg_loss_pack(const double *scalars, const int64_t *cells3 /*host*/, int32_t C, double *pack15, void *stream);
+int bg_loss_combine(const double *pack15, const bg_loss_params *p /*host*/, double *out_loss, void *stream);
+
 /* ------------------------------------------------------------------ a13
  * utils/make_anchors.py:14-39 ratio_metrics / ratio_metrics_w_extras.
  *   wh [n,2] f32, anchors host [k,2]; out3 [3] f64 = sum(v*m), sum(m), n  (score = out[0]/n, bpr = out[1]/n, aat = out[1]).

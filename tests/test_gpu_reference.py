@@ -93,13 +93,19 @@ def test_train_step_patched_equals_unpatched(ns):
         for k in met_u:
             assert_close(mp[k], met_u[k], rtol=2e-5, atol=1e-7, what=k)
         assert set(gp) == set(grads_u)
-        worst = 0.0
+        # per-parameter L2 error against that parameter's gradient norm, with an absolute floor tied to the largest
+        # gradient in the model: conv biases in front of a BatchNorm have a mathematically zero gradient, what
+        # either run holds there is rounding noise
+        gmax = max(float(g.double().norm()) for g in grads_u.values())
+        worst, worst_name = 0.0, ""
         for n in grads_u:
             den = float(grads_u[n].double().norm())
             err = float((gp[n].double() - grads_u[n].double()).norm())
-            worst = max(worst, err / max(den, 1e-12))
-        print("  worst relative L2 error over %d parameter gradients: %.2e" % (len(gp), worst))
-        assert worst < 2e-4
+            rel = err / (den + 1e-5 * gmax)
+            if rel > worst:
+                worst, worst_name = rel, n
+        print("  worst relative L2 error over %d parameter gradients: %.2e (%s)" % (len(gp), worst, worst_name))
+        assert worst < 2e-4, worst_name
 
 
 def test_inference_patched_equals_unpatched_and_fused(ns):

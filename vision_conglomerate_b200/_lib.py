@@ -27,7 +27,7 @@ SYMBOLS = (
     "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_bbox_to_size", "bg_decode_train_bwd",
     "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
-    "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd",
+    "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_pack", "bg_loss_combine",
     "bg_ratio_metrics",
 )
 
@@ -140,9 +140,11 @@ def lib() -> C.CDLL:
     L.bg_loss_workspace_bytes.restype = sz
     L.bg_loss_fwd.argtypes = [C.POINTER(HeadPtrs), vp, C.POINTER(LossParams), vp, vp, vp, vp, vp, sz, vp]
     L.bg_loss_bwd.argtypes = [C.POINTER(HeadPtrs), C.POINTER(LossParams), vp, f32, C.POINTER(HeadPtrs), vp, sz, vp]
+    L.bg_loss_pack.argtypes = [vp, C.POINTER(i64), i32, vp, vp]
+    L.bg_loss_combine.argtypes = [vp, C.POINTER(LossParams), vp, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
-                 "bg_loss_fwd", "bg_loss_bwd", "bg_ratio_metrics"):
+                 "bg_loss_fwd", "bg_loss_bwd", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

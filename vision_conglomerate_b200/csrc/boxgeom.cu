@@ -19,7 +19,8 @@ std::atomic<unsigned long long> g_launches{0};
 // profiling hooks are armed per host thread (the thread that arms one is the thread whose next call sees it), so
 // concurrent callers on other threads are unaffected and the entry points stay re-entrant
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
-static thread_local cudaEvent_t g_prof_loss_start = nullptr, g_prof_loss_stop = nullptr;
+// (armed from the caller's thread, consumed by bg_loss_bwd on whichever thread runs it -- autograd's worker thread under torch)
+static std::atomic<cudaEvent_t> g_prof_loss_start{nullptr}, g_prof_loss_stop{nullptr};
 static thread_local unsigned long long *g_prof_stamps = nullptr, *g_prof_cycles = nullptr;
 
 IouThr make_iou_thr(double thr)
@@ -849,14 +850,20 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
     if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
     if (p->nt > 0) {
         const dim3 grid(w.nblk_match, 3);
-        const size_t smem = 3 * (size_t)p->C * sizeof(int);
+        const size_t smem = sizeof(MatchRec) * MATCH_CHUNK + 3 * (size_t)p->C * sizeof(int);
+        // CTAs per SM of the match kernel: 6 (40 registers, some spills) hides the scattered-row latency better than 4
+        static const int occ = []() { const char *e = getenv("BG_MATCH_OCC"); return (e && e[0] == '4') ? 4 : 6; }();
+#define BG_MATCH_LAUNCH(CT, RAW)                                                                   \
+        do {                                                                                       \
+            if (occ == 4) loss_match_kernel<CT, RAW, 4><<<grid, LOSS_THREADS, smem, st>>>(k);      \
+            else loss_match_kernel<CT, RAW, 6><<<grid, LOSS_THREADS, smem, st>>>(k);               \
+        } while (0)
         if (p->C == 80) {
-            if (k.raw) loss_match_kernel<80, 1><<<grid, LOSS_THREADS, smem, st>>>(k);
-            else loss_match_kernel<80, 0><<<grid, LOSS_THREADS, smem, st>>>(k);
+            if (k.raw) BG_MATCH_LAUNCH(80, 1); else BG_MATCH_LAUNCH(80, 0);
         } else {
-            if (k.raw) loss_match_kernel<0, 1><<<grid, LOSS_THREADS, smem, st>>>(k);
-            else loss_match_kernel<0, 0><<<grid, LOSS_THREADS, smem, st>>>(k);
+            if (k.raw) BG_MATCH_LAUNCH(0, 1); else BG_MATCH_LAUNCH(0, 0);
         }
+#undef BG_MATCH_LAUNCH
         BG_LAUNCH_CHECK();
     }
     int rc = launch_after(loss_dense_kernel, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0);
@@ -879,8 +886,9 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
     k.go_dev = grad_out_dev;
     k.go_host = grad_out_host;
     const int sms = num_sms();
-    const bool prof = g_prof_loss_start && g_prof_loss_stop;
-    if (prof) cudaEventRecord(g_prof_loss_start, st);
+    const cudaEvent_t prof_a = g_prof_loss_start.exchange(nullptr), prof_b = g_prof_loss_stop.exchange(nullptr);
+    const bool prof = prof_a && prof_b;
+    if (prof) cudaEventRecord(prof_a, st);
     if (p->input_form == BG_LOSS_RAW_SPLIT) {
         // class / box planes: cleared by memset (adjacent planes are cleared by one call), objectness plane by a kernel
         struct Run { unsigned char *p; size_t n; } runs[6];
@@ -923,10 +931,27 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
         loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
         BG_LAUNCH_CHECK();
     }
-    if (prof) { cudaEventRecord(g_prof_loss_stop, st); g_prof_loss_start = g_prof_loss_stop = nullptr; }
+    if (prof) cudaEventRecord(prof_b, st);
     if (p->nt == 0) return BG_OK;
     if (k.C == 80) return launch_after(loss_bwd_rows_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
     return launch_after(loss_bwd_rows_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
+}
+
+int bg_loss_pack(const double *scalars, const int64_t *cells3, int32_t C, double *pack15, void *stream)
+{
+    if (!scalars || !cells3 || !pack15 || C <= 0) return BG_ERR_INVALID;
+    loss_pack_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scalars, (double)cells3[0], (double)cells3[1], (double)cells3[2], (double)C, pack15);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+int bg_loss_combine(const double *pack15, const bg_loss_params *p, double *out_loss, void *stream)
+{
+    if (!pack15 || !p || !out_loss || p->C <= 0) return BG_ERR_INVALID;
+    loss_combine_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pack15, p->box_w, p->conf_w, p->class_w, p->scale_w[0], p->scale_w[1],
+                                                     p->scale_w[2], (double)p->C, out_loss);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
 }
 
 // ------------------------------------------------------------------------------------------ a13

@@ -235,10 +235,16 @@ class DetectPlan:
         p.throughput = 1 if throughput else 0
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
-        self.out_boxes = torch.empty(n, 6, dtype=torch.float32, device=device)
+        # counts and rows share one device allocation ([counts | pad | rows]) so that result_host() can bring both to the
+        # host with ONE copy
+        self._hdr_bytes = ((2 + 2 * B) * 4 + 255) // 256 * 256
+        self._packed = torch.empty(self._hdr_bytes + n * 24, dtype=torch.uint8, device=device)
+        self.out_boxes = self._packed[self._hdr_bytes:].view(torch.float32).view(n, 6)
+        self._host_packed = None
+        self._rows_guess = 256
         self.out_img = torch.empty(n, dtype=torch.int64, device=device)
         self.out_keep = torch.empty(n, dtype=torch.int64, device=device)
-        self.counts = torch.empty(2 + 2 * B, dtype=torch.int32, device=device)
+        self.counts = self._packed[: (2 + 2 * B) * 4].view(torch.int32)
         self.key = (device.index, "detect")
         self.ws_tag = "detect"   # plans that run concurrently on different streams need distinct scratch: set a distinct tag
         self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
@@ -317,6 +323,67 @@ class DetectPlan:
             k = int(h[0])
             return Detections(self.out_boxes[:k], self.out_img[:k], self.out_keep[:k], h[2: 2 + B].clone(),
                               h[2 + B: 2 + 2 * B].clone())
+
+
+    # ---- the step after the path (inference_det.py:100-129) ----------------------------------------
+    def enqueue_host_copy(self) -> None:
+        """Queue ONE device->host copy of [counts | rows] behind the kernels of the last ``enqueue`` (pinned buffer;
+        sized for the row count of recent batches plus head room, the rare overflow is fetched by ``result_host``)."""
+        if self._host_packed is None:
+            self._host_packed = torch.empty(self._packed.numel(), dtype=torch.uint8).pin_memory()
+        n = min(self._packed.numel(), self._hdr_bytes + self._rows_guess * 24)
+        with _on(self.dev):
+            self._host_packed[:n].copy_(self._packed[:n], non_blocking=True)
+        self._copied_rows = (n - self._hdr_bytes) // 24
+
+    def result_host(self) -> "HostDetections":
+        """Rows of the last batch on the HOST, image by image, without ``.unique()``, per-image masks or per-image
+        ``.cpu()`` calls: what the reference's host loop builds at inference_det.py:100-129 (``boxes.detach().cpu().numpy()``
+        per image, after the tracked-class filter), from one pinned buffer filled by one asynchronous copy."""
+        import numpy as np
+        if getattr(self, "_copied_rows", None) is None:
+            self.enqueue_host_copy()
+        B = self.B
+        with _on(self.dev):
+            torch.cuda.current_stream(self.dev).synchronize()
+            hdr = self._host_packed[: (2 + 2 * B) * 4].view(torch.int32)
+            if int(hdr[1]) & (_lib.STATUS_NEED_GENERAL | _lib.STATUS_MASK_SPACE):
+                self._result()              # re-runs on the right engine (rare); then copy again
+                self._copied_rows = None
+                self.enqueue_host_copy()
+                torch.cuda.current_stream(self.dev).synchronize()
+                hdr = self._host_packed[: (2 + 2 * B) * 4].view(torch.int32)
+            k = int(hdr[0])
+            if k > self._copied_rows:       # more rows than the optimistic copy covered: fetch the rest
+                lo, hi = self._hdr_bytes + self._copied_rows * 24, self._hdr_bytes + k * 24
+                self._host_packed[lo:hi].copy_(self._packed[lo:hi], non_blocking=True)
+                torch.cuda.current_stream(self.dev).synchronize()
+        self._rows_guess = max(256, k + k // 4)
+        self._copied_rows = None
+        rows = self._host_packed[self._hdr_bytes: self._hdr_bytes + k * 24].view(torch.float32).view(k, 6).numpy()
+        counts = hdr[2: 2 + B].numpy().astype(np.int64)
+        offsets = np.zeros(B + 1, np.int64)
+        np.cumsum(counts, out=offsets[1:])
+        if self.params.order != 0:
+            raise RuntimeError("result_host: needs order='image' (rows grouped by image)")
+        return HostDetections(rows, offsets)
+
+
+@dataclass
+class HostDetections:
+    """``rows [K, 6]`` float32 on the host = (score, class, x1, y1, x2, y2), image-major and score-descending inside an
+    image; ``offsets [B+1]``: rows of image b are ``rows[offsets[b]:offsets[b+1]]`` (CSR).  The arrays are views of
+    the plan's pinned buffer: consume them before the plan's next ``result_host``."""
+    rows: "object"
+    offsets: "object"
+
+    def per_image(self):
+        """Yields ``(image index, boxes [k, 6])`` for the images that kept at least one row -- the iteration of
+        inference_det.py:100-113 (``sample_idxs.unique()`` + mask + tracked-class filter + ``.cpu().numpy()``)."""
+        for b in range(len(self.offsets) - 1):
+            lo, hi = int(self.offsets[b]), int(self.offsets[b + 1])
+            if hi > lo:
+                yield b, self.rows[lo:hi]
 
 
 class DetectPipeline:
@@ -669,6 +736,39 @@ class _DetLoss(torch.autograd.Function):
             check(L.bg_loss_bwd(_head_ptrs(tensors, split), C.byref(params), go.data_ptr(), 1.0, _head_ptrs(grads, split),
                                 ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "bg_loss_bwd")
         return (None, None, None, None, None, *grads)
+
+
+_combine_param_cache: Dict[tuple, LossParams] = {}
+
+
+def loss_terms_pack(scalars: torch.Tensor, cells: Sequence[int], num_classes: int) -> torch.Tensor:
+    """``[3, 5]`` float64 per scale ``{lbox*M, lconf*cells, lcls*M*C, M, cells}`` from the ``[3, 8]`` scalar block of
+    :func:`detection_loss` on this rank's image shard: the sums that add up over shards (one tiny kernel)."""
+    sc = _req(scalars, "scalars", torch.float64)
+    pack = torch.empty(3, 5, dtype=torch.float64, device=sc.device)
+    c3 = (C.c_int64 * 3)(*(int(c) for c in cells))
+    with _on(sc.device):
+        check(_lib.lib().bg_loss_pack(sc.data_ptr(), c3, int(num_classes), pack.data_ptr(), _stream(sc.device)), "bg_loss_pack")
+    return pack
+
+
+def loss_terms_combine(pack: torch.Tensor, cfg: dict, num_classes: int) -> torch.Tensor:
+    """The loss of the concatenated batch (modules/detection_loss.py:107-110 with global means) from the summed
+    terms; 0-d float64 tensor on the device."""
+    pk = _req(pack, "pack", torch.float64)
+    sw = tuple(cfg.get("scale_w") or [4.0, 2.0, 1.0])
+    key = (int(num_classes), cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), sw)
+    p = _combine_param_cache.get(key)
+    if p is None:
+        p = _combine_param_cache[key] = LossParams()
+        p.C = int(num_classes)
+        p.box_w, p.conf_w, p.class_w = float(key[1]), float(key[2]), float(key[3])
+        for s in range(3):
+            p.scale_w[s] = float(sw[s])
+    out = torch.empty(1, dtype=torch.float64, device=pk.device)
+    with _on(pk.device):
+        check(_lib.lib().bg_loss_combine(pk.data_ptr(), C.byref(p), out.data_ptr(), _stream(pk.device)), "bg_loss_combine")
+    return out.reshape(())
 
 
 def _macro_metrics(hist: torch.Tensor, M: int) -> Dict[str, float]:

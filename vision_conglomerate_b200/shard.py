@@ -6,7 +6,7 @@ data-path collective**; this is exactly what the reference's ``DistributedSample
 (train_det.py:83-84).  The reference does not all-reduce any loss normaliser (each rank normalises by
 its local match count and DDP averages gradients), so :func:`allreduce_loss_terms` is an *optional
 extension*, off by default: it makes a P-rank run report the loss of the single-GPU big-batch run by
-summing the per-scale numerators and normalisers (one tiny all-reduce, 24 doubles).
+summing the per-scale numerators and normalisers (one tiny all-reduce, 15 doubles).
 """
 from __future__ import annotations
 
@@ -45,9 +45,17 @@ def allreduce_loss_terms(scalars: torch.Tensor, cells: Sequence[int], cfg: dict,
     Returns the big-batch loss: means over the *global* match / cell counts (modules/detection_loss.py:107-110
     evaluated on the concatenated batch)."""
     import torch.distributed as dist
+    C_cls = float(cfg["num_classes"])
+    if scalars.is_cuda:
+        # two tiny kernels around the one collective: no host synchronisation, ~3 launches per step
+        from . import ops
+        pack = ops.loss_terms_pack(scalars, cells, int(C_cls))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+        return ops.loss_terms_combine(pack, cfg, int(C_cls))
+    # host tensors (the gloo tests of the sharding logic): the same arithmetic with torch ops
     M = scalars[:, 6]
     c = torch.as_tensor(list(cells), dtype=torch.float64, device=scalars.device)
-    C_cls = float(cfg["num_classes"])
     pack = torch.stack([scalars[:, 0] * M, scalars[:, 1] * c, scalars[:, 2] * M * C_cls, M, c], dim=1).contiguous()
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
