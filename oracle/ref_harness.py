@@ -71,6 +71,7 @@ def load():
         sv.ByteTrack = type("ByteTrack", (), {"__init__": lambda s, *a, **k: None})
         sys.modules["supervision"] = sv
     from modules.detection import DetectionNet
+    from modules.common import EffiDecHead
     from modules.detection_loss import DetectionLoss
     from dataset.detection_dataset import DetectionDataset
     import inference_det
@@ -96,7 +97,7 @@ def load():
         _bbox_to_size = DetectionNet._bbox_to_size
         _make_2dgrid = DetectionNet._make_2dgrid
 
-    ns = types.SimpleNamespace(DetectionNet=DetectionNet, DetectionLoss=DetectionLoss,
+    ns = types.SimpleNamespace(DetectionNet=DetectionNet, DetectionLoss=DetectionLoss, EffiDecHead=EffiDecHead,
                                DetectionDataset=DetectionDataset, inference_det=inference_det,
                                make_anchors=make_anchors, utils=ref_utils, FakeModel=FakeModel,
                                DecodeOnly=DecodeOnly)

@@ -42,7 +42,8 @@ def main():
         out[form] = {"big": float(big), "combined": float(comb), "local": float(loss), "grad_ok": ok_grad}
     out["current_device"] = torch.cuda.current_device()
     dist.barrier(device_ids=[local])
-    print("MULTIRANK " + json.dumps(out), flush=True)
+    with open(os.path.join(os.environ["BG_MULTIRANK_OUT"], "rank%d.json" % rank), "w") as f:
+        json.dump(out, f)
     dist.destroy_process_group()
 
 

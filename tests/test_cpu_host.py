@@ -151,21 +151,47 @@ def test_lazy_decoded_stand_in_mechanics():
     real = ops.decode_train
     ops.decode_train = ref_decode
     try:
-        z = lazy.LazyDecoded(raw)
+        z = lazy.LazyRows([raw], decode=True)
         assert isinstance(z, torch.Tensor) and z.pending
         assert z.shape == raw.shape and z.shape[0] == 2 and z.dim() == 5 and z.dtype == raw.dtype and z.device == raw.device
         assert z.requires_grad and len(z) == 2 and z.numel() == raw.numel() and z.is_contiguous()
-        assert z.pending and lazy.logits_if_pending((z, z, z))[0] is raw       # none of that materialised it
+        assert z.pending and lazy.loss_inputs_if_pending((z, z, z))[1][0] is raw    # none of that materialised it
         sm, md, lg = (z, z, z)                                                 # tuple packing / unpacking neither
         assert sm.pending
         got = z[..., C + 1:]                                                   # a real consumer: decoded values
-        assert not z.pending and lazy.logits_if_pending((z,)) is None
+        assert not z.pending and lazy.loss_inputs_if_pending((z,)) is None
         assert torch.equal(got, ref_decode(raw)[..., C + 1:]) and type(got) is torch.Tensor
         (z * 1.0).sum().backward()
         exp = torch.autograd.grad(ref_decode(raw).sum(), raw)[0]
         assert torch.allclose(raw.grad, exp)
-        z2 = lazy.LazyDecoded(raw.detach())
+        z2 = lazy.LazyRows([raw.detach()], decode=True)
         assert torch.equal(torch.cat([z2, z2], 0)[:2], ref_decode(raw.detach()))   # functions taking lists see it too
+        # the head's three conv outputs, still apart (EffiDecHead's deferred torch.cat, modules/common.py:919)
+        conv = torch.nn.Conv2d(4, 3 * (5 + C), 1)
+        feat = torch.randn(2, 4, 4, 4)
+
+        def head(x):  # the shape of EffiDecHead.forward's tail
+            y = conv(x)
+            pr = lambda t, d: t.permute(0, 2, 3, 1).reshape(2, 4, 4, 3, d)  # noqa: E731
+            return torch.cat([pr(y[:, :3], 1), pr(y[:, 3:3 + 3 * C], C), pr(y[:, 3 + 3 * C:], 4)], dim=-1)
+
+        ref_rows = head(feat)
+        lz = head(feat.as_subclass(lazy.HeadTrace))
+        assert isinstance(lz, lazy.LazyRows) and lz.pending and not lz.decode and len(lz.parts) == 3
+        assert lz.shape == ref_rows.shape and lz.requires_grad and lz.is_contiguous() and lz.stride() == ref_rows.stride()
+        assert all(type(p) is torch.Tensor for p in lz.parts)
+        dec = lazy.LazyRows(lz.parts, decode=True)
+        kind, tri = lazy.loss_inputs_if_pending((dec, dec, dec))
+        assert kind == "split" and tri[0][1].shape[-1] == C
+        assert torch.equal(dec[..., :], ref_decode(ref_rows))            # materialises: cat, then decode
+        assert torch.equal(lz + 0, ref_rows)
+        conv.zero_grad()
+        (dec * 1.0).sum().backward()
+        g1 = conv.weight.grad.clone()
+        conv.zero_grad()
+        ref_decode(head(feat)).sum().backward()
+        assert torch.allclose(g1, conv.weight.grad)
+        assert lazy.loss_inputs_if_pending((z2, dec)) is None               # mixed kinds are not fused
     finally:
         ops.decode_train = real
 

@@ -16,11 +16,11 @@ def test_sharded_loss_allreduce_nccl():
     port = 29500 + (os.getpid() % 400)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "multirank_worker.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    lines = [l for l in r.stdout.splitlines() if l.startswith("MULTIRANK ")]
-    assert len(lines) == 2, r.stdout[-2000:] + r.stderr[-2000:]
-    res = sorted((json.loads(l[len("MULTIRANK "):]) for l in lines), key=lambda d: d["rank"])
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, BG_MULTIRANK_OUT=tmp))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+        res = [json.load(open(os.path.join(tmp, "rank%d.json" % k))) for k in range(2)]
     assert all(d["current_device"] == 0 for d in res)           # nobody called set_device: ops followed the tensors
     for form in ("decoded", "raw"):
         big = res[0][form]["big"]

@@ -779,6 +779,7 @@ bool loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const bg_hea
     memset(&k, 0, sizeof(k));
     k.B = p->B; k.C = p->C;
     k.raw = p->input_form != BG_LOSS_DECODED;
+    k.keep_l2 = p->backward_follows ? 1 : 0;
     // python: cn = 0.5 * label_smoothing, cp = 1 - cn in double, written into fp32 tensors (detection_loss.py:191-195)
     k.cn = (float)(0.5 * (double)p->label_smoothing);
     k.cp = (float)(1.0 - 0.5 * (double)p->label_smoothing);

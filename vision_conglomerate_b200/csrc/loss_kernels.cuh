@@ -63,6 +63,7 @@ struct Loss3K {
     LossScale s[3];
     int B, C;
     int raw;             // 1: the box values are logits, decode in registers
+    int keep_l2;         // forward: 1 = a backward follows, keep the objectness residuals in L2 for it (evict-last stores)
     float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
     int nblk_match, nblk_dense;
     double box_w, conf_w, class_w;
@@ -315,7 +316,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
             if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
             // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
             // (evict-last), so those reads do not turn into DRAM read/write turnarounds
-            asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
+            if (k.keep_l2) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
+            else S.gobj[c] = __fsub_rn(sg, t);
         }
     }
     pdl_launch_dependents();
@@ -444,6 +446,27 @@ __global__ void __launch_bounds__(256) l2_pin_kernel(const float4 *p, long long 
     if (acc == 1.2345e-30f) asm volatile("trap;");  // keeps the loads alive
 }
 
+// The backward reads each residual exactly once: the load demotes its L2 line to evict-first, so the evict-last
+// lines of one step do not pile up in L2 when the next forward's workspace lies at another address.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float ld_last_use_f32(const float *p, unsigned long long pol)
+{
+    float v;
+    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ float4 ld_last_use_f32x4(const float4 *p, unsigned long long pol)
+{
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 // interleaved rows only (v.g_obj is the gradient tensor, v.so its row length D)
 __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K k)
 {
@@ -470,12 +493,13 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
     // the residuals of the next BWD_AHEAD chunks are kept in flight: a chunk is only ~22 store instructions long,
     // far shorter than the latency of the load that feeds the one after it
     constexpr int BWD_AHEAD = 4;
+    const unsigned long long lu_pol = l2_evict_first_policy();
     float gq[BWD_AHEAD];
 #pragma unroll
     for (int a = 0; a < BWD_AHEAD; ++a) {
         gq[a] = 0.f;
         const long long ga = gw + a * nw;
-        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[a] = k.s[s2].gobj[r2 + lane]; }
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[a] = ld_last_use_f32(k.s[s2].gobj + r2 + lane, lu_pol); }
     }
     for (long long g = gw; g < tot; g += nw) {
         int si; long long row0;
@@ -486,7 +510,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
         for (int a = 0; a + 1 < BWD_AHEAD; ++a) gq[a] = gq[a + 1];
         gq[BWD_AHEAD - 1] = 0.f;
         const long long ga = g + BWD_AHEAD * nw;
-        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[BWD_AHEAD - 1] = k.s[s2].gobj[r2 + lane]; }
+        if (ga < tot) { int s2; long long r2; locate(ga, s2, r2); gq[BWD_AHEAD - 1] = ld_last_use_f32(k.s[s2].gobj + r2 + lane, lu_pol); }
         __syncwarp();
         for (int f = lane; f < chunk_f4; f += 32) __stcs(dst + f, im4[f]);  // shared-memory image -> 512-byte coalesced, evict-first stores
         __syncwarp();
@@ -512,8 +536,9 @@ __global__ void __launch_bounds__(256) loss_bwd_conf_kernel(Loss3K k)
     const long long n4 = S.cells >> 2;
     const float4 *src = reinterpret_cast<const float4 *>(S.gobj);
     float4 *dst = reinterpret_cast<float4 *>(S.v.g_obj);
+    const unsigned long long lu_pol = l2_evict_first_policy();
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
-        float4 v = src[i];
+        float4 v = ld_last_use_f32x4(src + i, lu_pol);
         v.x *= cf; v.y *= cf; v.z *= cf; v.w *= cf;
         dst[i] = v;
     }

@@ -23,7 +23,7 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import ops
-from .lazy import LazyDecoded, logits_if_pending
+from .lazy import HeadTrace, LazyRows, loss_inputs_if_pending
 
 _saved: Dict[str, Any] = {}
 
@@ -82,9 +82,9 @@ def _make_loss_forward(orig):
         # anchors are read from the module at call time: they live in the state dict (detection.py:36-38)
         anchors3 = [model.sm_anchors.data, model.md_anchors.data, model.lg_anchors.data]
         targets = targets.to(preds[0].device, torch.float32)
-        logits = logits_if_pending(preds)
-        if logits is not None:   # straight from the head: the training-mode decode is fused into the loss
-            return ops.detection_loss(logits, targets, anchors3, cfg, input_form="raw")
+        lazy_in = loss_inputs_if_pending(preds)
+        if lazy_in is not None:   # straight from the head: the training-mode decode is fused into the loss
+            return ops.detection_loss(lazy_in[1], targets, anchors3, cfg, input_form=lazy_in[0])
         return ops.detection_loss(preds, targets, anchors3, cfg)
     return forward
 
@@ -109,10 +109,31 @@ def _make_get_scale_pred(orig):
             if _options["fuse_train_decode"]:
                 # stands for the decoded tensor; DetectionLoss.forward takes the logits from it, any other consumer
                 # gets the decoded values (differentiable CUDA decode) on first use
-                return LazyDecoded(scale_pred if scale_pred.is_contiguous() else scale_pred.contiguous())
+                if isinstance(scale_pred, LazyRows):
+                    if scale_pred.pending and not scale_pred.decode:
+                        return LazyRows(scale_pred.parts, decode=True)     # the head's three conv outputs, still apart
+                    scale_pred = scale_pred.materialize()
+                return LazyRows([scale_pred if scale_pred.is_contiguous() else scale_pred.contiguous()], decode=True)
+            if isinstance(scale_pred, LazyRows):
+                scale_pred = scale_pred.materialize()
             return ops.decode_train(scale_pred)
+        if isinstance(scale_pred, LazyRows):
+            scale_pred = scale_pred.materialize()
         return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), inference)
     return _get_scale_pred
+
+
+# ------------------------------------------------------------------------------------------------ f3
+def _make_head_forward(orig):
+    def forward(self, x):
+        if hasattr(self, "masks_layer") or hasattr(self, "keypoints_layer") or not _options["split_head"] \
+                or not (isinstance(x, torch.Tensor) and x.is_cuda):
+            return orig(self, x)
+        # the reference's own forward runs unchanged; only its final torch.cat([conf, cls, bbox], -1) (common.py:919)
+        # is deferred: the three conv outputs stay where they are and the fused loss reads them in place
+        out = orig(self, x.as_subclass(HeadTrace))
+        return out if isinstance(out, LazyRows) else out.as_subclass(torch.Tensor)
+    return forward
 
 
 def _make_bbox_to_size(orig):
@@ -150,18 +171,24 @@ def _make_ratio_metrics(orig, extras: bool):
     return ratio_metrics
 
 
-_options = {"fuse_train_decode": True}
+_options = {"fuse_train_decode": True, "split_head": True}
 
 
 def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True, make_anchors=None,
-            fuse_train_decode: bool = True) -> None:
+            fuse_train_decode: bool = True, EffiDecHead=None, split_head: bool = True) -> None:
     """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
     imported in your process (any subset); ``torchvision_ops=True`` also replaces
     ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time); ``make_anchors`` is the
     reference's ``utils.make_anchors`` module (``ratio_metrics*``).  ``fuse_train_decode=False`` makes the
     training-mode ``_get_scale_pred`` return a real decoded tensor (one CUDA kernel each way) instead of the
-    deferred stand-in."""
+    deferred stand-in.  ``EffiDecHead`` (modules/common.py:852-931): its final ``torch.cat`` is deferred as well, so the
+    loss reads the head's three conv outputs in place (zero-copy when the model runs channels-last,
+    otherwise the pieces are made contiguous -- the copy the concatenation would have been)."""
     _options["fuse_train_decode"] = bool(fuse_train_decode)
+    _options["split_head"] = bool(split_head)
+    if EffiDecHead is not None and "EffiDecHead.forward" not in _saved:
+        _saved["EffiDecHead.forward"] = (EffiDecHead, EffiDecHead.__dict__["forward"])
+        EffiDecHead.forward = _make_head_forward(EffiDecHead.__dict__["forward"])
     from . import _lib
     _lib.lib()  # fail loudly now if the extension is not built
     if DetectionDataset is not None and "build_target_by_scale" not in _saved:
@@ -203,6 +230,9 @@ def uninstall() -> None:
         if name in _saved:
             owner, orig = _saved.pop(name)
             setattr(owner, name, orig)
+    if "EffiDecHead.forward" in _saved:
+        owner, orig = _saved.pop("EffiDecHead.forward")
+        owner.forward = orig
     _saved.pop("DetectionLoss.loss_fn", None)
 
 

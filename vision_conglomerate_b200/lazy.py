@@ -1,24 +1,30 @@
-"""Deferred training-mode decode: how the fused loss reaches the head's logits with zero edits to the host code.
+"""Deferred head concatenation and training-mode decode: how the fused loss reaches the head's logits with zero
+edits to the host code.
 
-In the reference, ``DetectionNet.forward`` (modules/detection.py:58-96) passes each head output through
+In the reference, ``EffiDecHead.forward`` (modules/common.py:908-919) concatenates its three conv outputs into rows
+``[obj, cls*C, tx,ty,tw,th]``, ``DetectionNet.forward`` (modules/detection.py:58-96) passes each head output through
 ``_get_scale_pred(inference=False)`` -- ``xy = 2*sigmoid - 0.5``, ``wh = (2*sigmoid)**2`` (:122,125) over ~15 ATen
 kernels that copy the whole ``[B,ny,nx,na,5+C]`` tensor -- and the trainer hands the three results straight to
 ``DetectionLoss.forward`` (pipeline/detection_trainer.py:178-180).  The CUDA loss applies that decode in registers
-(``BG_LOSS_RAW``), so the decoded tensors never need to exist.
+(``BG_LOSS_RAW``) and can read the three conv outputs where they are (``BG_LOSS_RAW_SPLIT``), so neither the
+concatenated nor the decoded tensors need to exist.
 
-The patched ``_get_scale_pred`` therefore returns a :class:`LazyDecoded`: a ``torch.Tensor`` subclass that *stands
-for* the decoded tensor (same shape, dtype, device, ``requires_grad``) but only remembers the logits.  The patched
-``DetectionLoss.forward`` recognises it and feeds the logits to the fused loss.  Any *other* use -- indexing,
-arithmetic, ``torch.cat``, printing, a different loss -- goes through ``__torch_function__``, which materialises the
-decoded tensor first (once, with the differentiable CUDA decode ``ops.decode_train``) and then runs the requested
-function on it: the values every other consumer sees are exactly the reference's.
+The patched ``EffiDecHead.forward`` / ``_get_scale_pred`` therefore return a :class:`LazyRows`: a ``torch.Tensor``
+subclass that *stands for* the tensor the reference would have built (same shape, dtype, device, ``requires_grad``)
+but only remembers the parts it is made of.  The patched ``DetectionLoss.forward`` recognises it and feeds the parts
+to the fused loss.  Any *other* use -- indexing, arithmetic, ``torch.cat``, printing, a different loss -- goes through
+``__torch_function__``, which materialises the real tensor first (once: ``torch.cat`` of the parts, then the
+differentiable CUDA decode ``ops.decode_train``) and then runs the requested function on it: the values every other
+consumer sees are exactly the reference's.
 """
 from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
 
 import torch
 
 _T = torch.Tensor
-# metadata that the decoded tensor shares with the logits: answered without materialising
+# metadata that the stand-in shares with the tensor it stands for: answered without materialising
 _META = {
     _T.shape.__get__, _T.device.__get__, _T.dtype.__get__, _T.ndim.__get__, _T.is_cuda.__get__, _T.layout.__get__,
     _T.requires_grad.__get__, _T.size, _T.dim, _T.ndimension, _T.numel, _T.nelement, _T.stride, _T.is_contiguous,
@@ -26,40 +32,73 @@ _META = {
 }
 
 
-class LazyDecoded(torch.Tensor):
-    """Stands for ``DetectionNet._get_scale_pred(raw, ..., inference=False)`` without computing it."""
+class LazyRows(torch.Tensor):
+    """Stands for ``torch.cat(parts, -1)`` (``decode=False``: a head output) or for
+    ``DetectionNet._get_scale_pred(torch.cat(parts, -1), ..., inference=False)`` (``decode=True``) without computing
+    it.  ``parts``: one tensor ``[B,ny,nx,na,5+C]`` (rows already interleaved) or the head's three
+    ``(conf [...,1], cls [...,C], bbox [...,4])``."""
 
     @staticmethod
-    def __new__(cls, raw: torch.Tensor):
-        return torch.Tensor._make_subclass(cls, raw.detach(), False)
+    def __new__(cls, parts: Sequence[torch.Tensor], decode: bool):
+        if len(parts) == 1:
+            base = parts[0].detach()
+        else:  # no tensor of the concatenated shape exists: a 4-byte stand-in expanded to that shape carries the metadata
+            shape = tuple(parts[1].shape[:-1]) + (sum(int(p.shape[-1]) for p in parts),)
+            base = torch.empty(1, dtype=parts[1].dtype, device=parts[1].device).expand(shape)
+        return torch.Tensor._make_subclass(cls, base, False)
 
-    def __init__(self, raw: torch.Tensor):
-        self._bg_raw = raw
-        self._bg_dec = None
+    def __init__(self, parts: Sequence[torch.Tensor], decode: bool):
+        self._bg_parts: Tuple[torch.Tensor, ...] = tuple(parts)
+        self._bg_decode = bool(decode)
+        self._bg_real: Optional[torch.Tensor] = None
 
     @property
     def pending(self) -> bool:
-        """True while nobody has asked for the decoded values."""
-        return self._bg_dec is None
+        """True while nobody has asked for the values."""
+        return self._bg_real is None
 
     @property
-    def logits(self) -> torch.Tensor:
-        return self._bg_raw
+    def parts(self) -> Tuple[torch.Tensor, ...]:
+        return self._bg_parts
+
+    @property
+    def decode(self) -> bool:
+        return self._bg_decode
 
     def materialize(self) -> torch.Tensor:
-        if self._bg_dec is None:
-            from . import ops
-            self._bg_dec = ops.decode_train(self._bg_raw)
-        return self._bg_dec
+        if self._bg_real is None:
+            rows = self._bg_parts[0] if len(self._bg_parts) == 1 else torch.cat(self._bg_parts, dim=-1)
+            if self._bg_decode:
+                from . import ops
+                rows = ops.decode_train(rows)
+            self._bg_real = rows
+        return self._bg_real
+
+    def _meta(self, func, args, kwargs):
+        if len(self._bg_parts) == 1:
+            return func(*(a._bg_parts[0] if isinstance(a, LazyRows) else a for a in args), **kwargs)
+        if func == _T.requires_grad.__get__:
+            return any(p.requires_grad for p in self._bg_parts)
+        if func == _T.is_contiguous:
+            return True
+        if func == _T.stride:
+            st, acc = [], 1
+            for n in reversed(tuple(_T.size(self._bg_parts[1])[:-1]) + (sum(int(p.shape[-1]) for p in self._bg_parts),)):
+                st.append(acc)
+                acc *= int(n)
+            st = tuple(reversed(st))
+            return st if len(args) == 1 and not kwargs else st[args[1] if len(args) > 1 else kwargs["dim"]]
+        with torch._C.DisableTorchFunctionSubclass():
+            return func(*args, **kwargs)
 
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):
         kwargs = kwargs or {}
-        if func in _META:
-            return func(*(a._bg_raw if isinstance(a, LazyDecoded) else a for a in args), **kwargs)
+        if func in _META and args and isinstance(args[0], LazyRows):
+            return args[0]._meta(func, args, kwargs)
 
         def real(a):
-            if isinstance(a, LazyDecoded):
+            if isinstance(a, LazyRows):
                 return a.materialize()
             if isinstance(a, (list, tuple)):
                 return type(a)(real(x) for x in a)
@@ -70,8 +109,35 @@ class LazyDecoded(torch.Tensor):
         return func(*real(args), **real(kwargs))
 
 
-def logits_if_pending(preds):
-    """The three logit tensors if every element of ``preds`` is a still-pending :class:`LazyDecoded`, else None."""
-    if all(isinstance(p, LazyDecoded) and p.pending for p in preds):
-        return [p.logits for p in preds]
+LazyDecoded = LazyRows  # (name used by the first version of the drop-in)
+
+
+class HeadTrace(torch.Tensor):
+    """Marks the tensors flowing through ``EffiDecHead.forward`` so that its final
+    ``torch.cat([conf, cls, bbox], dim=-1)`` (modules/common.py:919) can be recognised and deferred; every other
+    function behaves as on a plain tensor."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func is torch.cat and args and isinstance(args[0], (list, tuple)) and len(args[0]) == 3:
+            parts = args[0]
+            dim = kwargs.get("dim", args[1] if len(args) > 1 else 0)
+            if all(isinstance(p, torch.Tensor) and p.dim() == 5 for p in parts) and dim in (-1, 4) \
+                    and int(parts[0].shape[-1]) == 1 and int(parts[2].shape[-1]) == 4 \
+                    and all(p.shape[:-1] == parts[0].shape[:-1] for p in parts):
+                return LazyRows([p.as_subclass(torch.Tensor) for p in parts], decode=False)
+        return super().__torch_function__(func, types, args, kwargs)
+
+
+def loss_inputs_if_pending(preds):
+    """``("raw", [rows x3])`` or ``("split", [(conf, cls, bbox) x3])`` if every element of ``preds`` is a still-pending
+    :class:`LazyRows` awaiting the training-mode decode (all of the same kind), else ``None``."""
+    if not all(isinstance(p, LazyRows) and p.pending and p.decode for p in preds):
+        return None
+    kinds = {len(p.parts) for p in preds}
+    if kinds == {1}:
+        return "raw", [p.parts[0] for p in preds]
+    if kinds == {3}:
+        return "split", [p.parts for p in preds]
     return None
