@@ -745,12 +745,19 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     w.cap = 5ll * p->na * p->nt;
     w.nblk_match = (int)((w.cap + MATCH_CHUNK - 1) / MATCH_CHUNK);
     if (w.cap < 1) w.cap = 1;
-    w.nblk_dense = sms * 8;
     w.cells_total = 0;
+    long long most = 0;
     for (int s = 0; s < 3; ++s) {
         w.cells[s] = (long long)p->B * p->ny[s] * p->nx[s] * p->na;
         w.cell_off[s] = w.cells_total;
         w.cells_total += w.cells[s];
+        most = w.cells[s] > most ? w.cells[s] : most;
+    }
+    {   // blocks of the dense pass per scale: 16 cells per thread on the largest scale, between one and eight CTAs per SM
+        // (small shards: fewer partial sums for the final reduction, no tail of near-empty blocks)
+        long long nb = (most + LOSS_THREADS * 16 - 1) / (LOSS_THREADS * 16);
+        nb = nb < sms ? sms : (nb > sms * 8 ? sms * 8 : nb);
+        w.nblk_dense = (int)nb;
     }
     w.M = b.take<int>(4);
     w.zero_begin = b.off - 4 * sizeof(int);

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];   // [MATCH_CHUNK] MatchRec, then [3*C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
-    __shared__ int s_wcnt[MATCH_PER][LOSS_THREADS / 32];
-    __shared__ int s_base, s_total;
+    __shared__ int s_wcnt[LOSS_THREADS / 32], s_wpre[LOSS_THREADS / 32 + 1];
+    __shared__ int s_base;
     MatchRec *s_rec = reinterpret_cast<MatchRec *>(s_dyn);
     int *s_hist = reinterpret_cast<int *>(s_dyn + sizeof(MatchRec) * MATCH_CHUNK);
     const LossScale &S = k.s[blockIdx.y];
@@ -107,14 +107,16 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
     constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
     for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
 
-    // ---- 1. the block's candidates: slice i = candidates [chunk*CHUNK + i*256, +256), so ballot order = candidate
-    //         order.  Two sweeps (flags, then records) keep one evaluation's registers alive at a time.
+    // ---- 1. the block's candidates.  Warp w owns candidates [chunk*CHUNK + w*128, +128) (slice i = its lanes' i-th
+    //         candidates) and writes the records of the emitted ones, in candidate order, to its own quarter-kilobyte
+    //         region of the staging array: one evaluation per candidate, no block-wide prefix needed for the position.
     const long long c0 = (long long)blockIdx.x * MATCH_CHUNK;
     bool bad = false;
-    u32 fmask = 0;
+    int wcount = 0;  // records this warp has written so far (warp-uniform)
 #pragma unroll
     for (int i = 0; i < MATCH_PER; ++i) {
-        const long long c = c0 + i * LOSS_THREADS + tid;
+        const int lc = wid * (32 * MATCH_PER) + i * 32 + lane;  // local candidate number
+        const long long c = c0 + lc;
         AssignOut o;
         bool f = (c < S.a.ncand) && assign_eval(S.a, c, o);
         if (f && ((unsigned)o.b >= (unsigned)k.B || (unsigned)o.cls >= (unsigned)C)) {
@@ -122,42 +124,39 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
             bad = true;
         }
         const u32 bal = __ballot_sync(0xffffffffu, f);
-        if (lane == 0) s_wcnt[i][wid] = __popc(bal);
-        if (f) fmask |= 1u << i;
+        if (f) {
+            MatchRec r;
+            r.cell = ((o.b * S.a.ny + o.gj) * S.a.nx + o.gi) * S.a.na + o.a;
+            r.cls_a = o.cls | (o.a << 16) | (lc << 20);
+            r.bx = o.bx; r.by = o.by; r.bw = o.bw; r.bh = o.bh;
+            s_rec[wid * (32 * MATCH_PER) + wcount + __popc(bal & lanemask_lt())] = r;
+        }
+        wcount += __popc(bal);
     }
+    if (lane == 0) s_wcnt[wid] = wcount;
     __syncthreads();
     pdl_wait();  // everything above reads only the targets; the counters / match arrays / head words are cleared upstream
     if (bad) atomicOr(k.status, 1);
     if (tid == 0) {
         int tot = 0;
-#pragma unroll
-        for (int i = 0; i < MATCH_PER; ++i)
-            for (int w = 0; w < LOSS_THREADS / 32; ++w) { const int v = s_wcnt[i][w]; s_wcnt[i][w] = tot; tot += v; }
-        s_total = tot;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) { const int v = s_wcnt[w]; s_wpre[w] = tot; tot += v; }
+        s_wpre[LOSS_THREADS / 32] = tot;
         s_base = tot ? atomicAdd(S.M, tot) : 0;
     }
     __syncthreads();
-    const int nloc = s_total, base = s_base;
+    const int nloc = s_wpre[LOSS_THREADS / 32], base = s_base;
+    // dense match number j of the block -> its record: the warp whose range holds j, then the position inside its region
+    auto rec_of = [&](int j) -> const MatchRec & {
+        int w = 0;
 #pragma unroll
-    for (int i = 0; i < MATCH_PER; ++i) {
-        const bool f = (fmask >> i) & 1u;
-        const u32 bal = __ballot_sync(0xffffffffu, f);
-        if (!f) continue;
-        AssignOut o;
-        assign_eval(S.a, c0 + i * LOSS_THREADS + tid, o);
-        const int j = s_wcnt[i][wid] + __popc(bal & lanemask_lt());
-        MatchRec r;
-        r.cell = ((o.b * S.a.ny + o.gj) * S.a.nx + o.gi) * S.a.na + o.a;
-        r.cls_a = o.cls | (o.a << 16) | ((i * LOSS_THREADS + tid) << 20);
-        r.bx = o.bx; r.by = o.by; r.bw = o.bw; r.bh = o.bh;
-        s_rec[j] = r;
-    }
-    __syncthreads();
+        for (int q = 1; q < LOSS_THREADS / 32; ++q) w += (j >= s_wpre[q]) ? 1 : 0;
+        return s_rec[w * (32 * MATCH_PER) + (j - s_wpre[w])];
+    };
 
     // ---- 2. one thread per match: gather, CIoU and its gradient, link into the cell's list; records to global memory
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     for (int j = tid; j < nloc; j += LOSS_THREADS) {
-        const MatchRec r = s_rec[j];
+        const MatchRec r = rec_of(j);
         const int m = base + j, cell = r.cell, an = (r.cls_a >> 16) & 15;
         const float aw = S.a.aw[an], ah = S.a.ah[an];
         const float *bp = S.v.box + (long long)cell * S.v.sb;
@@ -200,8 +199,9 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
         float bsum = 0.f, best = -INFINITY;
         int bi = 0x7fffffff, tc = -1;
         if (valid) {
-            tc = s_rec[j].cls_a & 0xffff;
-            const float *row = S.v.cls + (long long)s_rec[j].cell * S.v.sc;
+            const MatchRec &rr = rec_of(j);
+            tc = rr.cls_a & 0xffff;
+            const float *row = S.v.cls + (long long)rr.cell * S.v.sc;
             float spos = 0.f, sx = 0.f, lsum = 0.f;
             for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
                 float x[ROWS_UNROLL];
@@ -561,15 +561,17 @@ __global__ void __launch_bounds__(LOSS_THREADS) loss_bwd_rows_kernel(Loss3K k)
          mb += (long long)gridDim.x * (LOSS_THREADS / 32) * 4) {
         const long long m = mb + (lane >> 3);
         if (m >= M) continue;
-        if (S.next[m] != -1) continue;  // the first match linked into the cell owns the row
-        const int cell = S.cell[m];
+        // everything addressed by m is fetched at once (one memory round trip), then the ownership test
+        const int nx = S.next[m], cell = S.cell[m], cls_m = S.cls[m];
+        const unsigned char su = S.succ[m];
+        const float4 gq_m = S.gbox[m];
+        if (nx != -1) continue;  // the first match linked into the cell owns the row
         int n = 0, c1 = -1, c2 = -1;
         float gb[4] = {0.f, 0.f, 0.f, 0.f};
         int lhead = (int)m;
-        if (!S.succ[m]) {  // the only match of its cell (the usual case): everything is addressed by m, no list walk
-            const float4 gq = S.gbox[m];
-            gb[0] = gq.x; gb[1] = gq.y; gb[2] = gq.z; gb[3] = gq.w;
-            c1 = S.cls[m];
+        if (!su) {  // the only match of its cell (the usual case): everything is addressed by m, no list walk
+            gb[0] = gq_m.x; gb[1] = gq_m.y; gb[2] = gq_m.z; gb[3] = gq_m.w;
+            c1 = cls_m;
             n = 1;
         } else {           // sums in double: the list order depends on the block schedule, the rounded sum must not
             lhead = S.head[cell] - 1;

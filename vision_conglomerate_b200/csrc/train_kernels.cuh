@@ -222,6 +222,11 @@ __global__ void __launch_bounds__(ASSIGN_THREADS) assign_onepass_kernel(Assign3K
 // CIoU (modules/detection_loss.py:229-264): fp32 forward in the reference's operation order; the
 // gradient w.r.t. the prediction (alpha constant) is evaluated in double from the same quantities.
 // ------------------------------------------------------------------------------------------------
+// division of the gradient arithmetic: exact in double, the fast reciprocal-multiply in float (2 ulp; the fused loss's
+// gradients are held to rtol 1e-4 and its match kernel is instruction-bound)
+__device__ __forceinline__ double gdiv(double a, double b) { return a / b; }
+__device__ __forceinline__ float gdiv(float a, float b) { return __fdividef(a, b); }
+
 template <typename G>  // G = double (stand-alone bg_ciou_bwd) or float (fused loss: rtol 1e-4 against fp32 autograd)
 __device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], float e, G *g /*4 or null*/)
 {
@@ -256,7 +261,8 @@ __device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], f
         const G s_maxx2 = px2 > tx2 ? (G)1 : (px2 == tx2 ? (G)0.5 : (G)0), s_minx1 = px1 < tx1 ? (G)1 : (px1 == tx1 ? (G)0.5 : (G)0);
         const G s_maxy2 = py2 > ty2 ? (G)1 : (py2 == ty2 ? (G)0.5 : (G)0), s_miny1 = py1 < ty1 ? (G)1 : (py1 == ty1 ? (G)0.5 : (G)0);
         const G den = (G)uni + (G)e;
-        const G r = (G)pw / (G)ph;
+        const G r = gdiv((G)pw, (G)ph);
+        const G inv_den = gdiv((G)1, den), inv_c2 = gdiv((G)1, (G)c2), inv_ph = gdiv((G)1, (G)ph), inv_1r2 = gdiv((G)1, (G)1 + r * r);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const G diw = iw_pos ? (s_minx2 * dpx2[q] - s_maxx1 * dpx1[q]) : (G)0;
@@ -264,15 +270,15 @@ __device__ __forceinline__ float ciou_eval(const float p[4], const float t[4], f
             const G dinter = diw * ih + iw * dih;
             const G dpwph = (q == 2 ? (G)ph : (G)0) + (q == 3 ? (G)pw : (G)0);
             const G duni = dpwph - dinter;
-            const G diou = dinter / den - (G)inter * duni / (den * den);
+            const G diou = dinter * inv_den - (G)inter * duni * inv_den * inv_den;
             const G dcw = s_maxx2 * dpx2[q] - s_minx1 * dpx1[q];
             const G dch = s_maxy2 * dpy2[q] - s_miny1 * dpy1[q];
             const G dc2 = (G)2 * cw * dcw + (G)2 * ch * dch;
             const G drho2 = (q == 0 ? (G)2 * dx : (G)0) + (q == 1 ? (G)2 * dy : (G)0);
-            const G dr = (q == 2 ? (G)1 / (G)ph : (G)0) + (q == 3 ? -(G)pw / ((G)ph * ph) : (G)0);
-            const G dv = (G)k4pi2 * (G)2 * (G)dat * (-(dr / ((G)1 + r * r)));
+            const G dr = (q == 2 ? inv_ph : (G)0) + (q == 3 ? -(G)pw * inv_ph * inv_ph : (G)0);
+            const G dv = (G)k4pi2 * (G)2 * (G)dat * (-(dr * inv_1r2));
             const G av = (q >= 2) ? (G)a * dv : (G)0;  // v depends on (w,h) only: a NaN alpha never reaches x,y
-            g[q] = diou - (drho2 / c2 - (G)rho2 * dc2 / ((G)c2 * c2) + av);
+            g[q] = diou - (drho2 * inv_c2 - (G)rho2 * dc2 * inv_c2 * inv_c2 + av);
         }
     }
     return ciou;
