@@ -149,6 +149,14 @@ int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t
                     const float *anchors /*host [na,2]*/, int32_t H, int32_t W, int32_t inference, int32_t og_H,
                     int32_t og_W, void *stream);
 
+/* Rows of DetectionNet.forward(x, inference=True) (modules/detection.py:69-91) for selected candidates only:
+ * out [n, 5+C+extra] = [obj logit, class logits, x, y, w, h, ...] of the flat candidates idx [n] (i64, b*N + i, e.g. the
+ * out_keep of bg_detect), decoded and rescaled exactly as bg_detect does internally (before the box allowance and the
+ * xyxy step).  `p` as for bg_detect.  Lets the reference's own post-processing / host loop (inference_det.py:57-165)
+ * run on the kept candidates only. */
+int bg_decode_rows(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *p /*host*/,
+                   const int64_t *idx, int64_t n, float *out, void *stream);
+
 /* DetectionNet._bbox_to_size (modules/detection.py:175-190) as called at :79-81, in place on decoded rows of D floats
  * (box columns at C+1..C+4): box = (box / from) * to; from4 / to4 are the DEVICE int64[4] tensors [W,H,W,H] /
  * [W0,H0,W0,H0] the reference builds at :77-78 (read on the device: no host sync). */

@@ -73,6 +73,7 @@ def test_dropin_keeps_reference_signatures():
     from vision_conglomerate_b200 import dropin
     import torchvision
     ns = ref_harness.load()
+    before_fns = (ns.DetectionNet.forward, ns.EffiDecHead.forward, ns.inference_det.post_process_preds)
     before = {
         "bts": inspect.signature(ns.DetectionDataset.build_target_by_scale),
         "ciou": inspect.signature(ns.DetectionLoss.compute_ciou),
@@ -83,8 +84,12 @@ def test_dropin_keeps_reference_signatures():
         "rm": inspect.signature(ns.make_anchors.ratio_metrics),
         "rmx": inspect.signature(ns.make_anchors.ratio_metrics_w_extras),
         "nms": inspect.signature(torchvision.ops.batched_nms),
+        "netfwd": inspect.signature(ns.DetectionNet.forward),
+        "headfwd": inspect.signature(ns.EffiDecHead.forward),
+        "ppp": inspect.signature(ns.inference_det.post_process_preds),
     }
-    dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, make_anchors=ns.make_anchors)
+    dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, make_anchors=ns.make_anchors,
+                   EffiDecHead=ns.EffiDecHead, inference_det=ns.inference_det)
     try:
         assert all(dropin.installed().values())
         after = {
@@ -97,6 +102,9 @@ def test_dropin_keeps_reference_signatures():
             "rm": inspect.signature(ns.make_anchors.ratio_metrics),
             "rmx": inspect.signature(ns.make_anchors.ratio_metrics_w_extras),
             "nms": inspect.signature(torchvision.ops.batched_nms),
+            "netfwd": inspect.signature(ns.DetectionNet.forward),
+            "headfwd": inspect.signature(ns.EffiDecHead.forward),
+            "ppp": inspect.signature(ns.inference_det.post_process_preds),
         }
         for k in before:
             assert list(before[k].parameters) == list(after[k].parameters), k
@@ -123,6 +131,8 @@ def test_dropin_keeps_reference_signatures():
     finally:
         dropin.uninstall()
     assert not any(dropin.installed().values())
+    assert ns.DetectionNet.forward is before_fns[0] and ns.EffiDecHead.forward is before_fns[1] \
+        and ns.inference_det.post_process_preds is before_fns[2]
     ref = ns.DetectionDataset.build_target_by_scale(synth.targets(1, 3), (20, 20), synth.anchors_tensor("lg"))
     assert len(ref) == 6
 
@@ -194,6 +204,46 @@ def test_lazy_decoded_stand_in_mechanics():
         assert lazy.loss_inputs_if_pending((z2, dec)) is None               # mixed kinds are not fused
     finally:
         ops.decode_train = real
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference checkout not present")
+def test_lazy_preds_stand_in_mechanics():
+    """lazy.LazyPreds (what the patched _get_scale_pred returns with inference=True): the shape-only steps of
+    DetectionNet.forward (modules/detection.py:76-91: _bbox_to_size bookkeeping, reshape(B,-1,D), cat(dim=1),
+    flatten(1,-2)) keep the stand-in pending; any real consumer gets the reference's tensor.  The CUDA decode is
+    stubbed with the reference's own _get_scale_pred / _bbox_to_size."""
+    from vision_conglomerate_b200 import lazy, ops
+    ns = ref_harness.load()
+    C, B, H, W = 5, 2, 64, 96
+    net = ns.DecodeOnly(C)
+    raws = synth.raw_head_outputs(B, H, W, C, "N", 3)
+    anc = [synth.anchors_tensor(k) for k in synth.SCALES]
+    real_dec, real_b2s = ops.decode_scale, ops.bbox_to_size
+    ops.decode_scale = lambda x, a, ishape, inference, og=None: net._get_scale_pred(x.clone(), a, input_shape=ishape, inference=inference)
+    ops.bbox_to_size = lambda pred, f, t, nc: net._bbox_to_size(pred, f, t)
+    try:
+        og = (100, 130)
+        _from, _to = torch.tensor([W, H, W, H]), torch.tensor([og[1], og[0], og[1], og[0]])
+        ref = ref_harness.ref_decode_inference(raws, anc, H, W, og, C)
+
+        def forward_tail(make):       # the tail of DetectionNet.forward, on stand-ins
+            ps = [make(r, a) for r, a in zip(raws, anc)]
+            ps = [p.with_rescale(_from, _to) for p in ps]
+            ps = [p.reshape(B, -1, C + 5) for p in ps]
+            return torch.cat(ps, dim=1).flatten(start_dim=1, end_dim=-2)
+
+        mk = lambda r, a: lazy.LazyPreds(tuple(r.shape), [dict(raw=r, anchors=a, input_shape=(H, W), rescale=None, og_size=None, num_classes=C)])  # noqa: E731
+        out = forward_tail(mk)
+        assert isinstance(out, lazy.LazyPreds) and out.pending and len(out.scales) == 3
+        assert out.shape == ref.shape and out.dim() == 3 and out.is_contiguous() and out.stride() == ref.stride() and not out.requires_grad
+        assert all(sc["rescale"] is not None for sc in out.scales)
+        got = out[..., :]                                    # a real consumer
+        assert not out.pending and type(got) is torch.Tensor and torch.equal(got, ref)
+        assert torch.equal(torch.sigmoid(forward_tail(mk)[..., :1]), torch.sigmoid(ref[..., :1]))
+        one = mk(raws[0], anc[0])
+        assert torch.equal(one + 0, net._get_scale_pred(raws[0].clone(), anc[0], input_shape=(H, W), inference=True))
+    finally:
+        ops.decode_scale, ops.bbox_to_size = real_dec, real_b2s
 
 
 def test_shard_range_partitions():

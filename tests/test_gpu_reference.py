@@ -182,6 +182,45 @@ def test_inference_patched_equals_unpatched_and_fused(ns):
     assert det.keep_idxs.numel() > 0
 
 
+def test_inference_zero_edit_fused(ns):
+    """install(inference_det=module): the unmodified call sequence of inference_det.evaluate_frames --
+    preds = model(x, inference=True, og_size=...); post_process_preds(imgs, preds, ...) -- runs on the fused decode+NMS
+    kernels with no edit of the reference: the model returns a stand-in, the wrapped post_process_preds runs the fused
+    kernels and then the reference's own function on the kept candidates only.  The per-image box arrays handed to the
+    reference's drawing code must be those of the unpatched run (torch-CUDA + torchvision-CUDA)."""
+    from vision_conglomerate_b200 import _lib, dropin, lazy
+    B, S, C = 3, 256, 80
+    model = _model(ns, C).eval()
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(B, 3, S, S, generator=g).cuda()
+    for og, iou, thr, allow, tracked in (((300, 400), 0.5, 0.2, 4, None), (None, 0.35, 0.24, None, [1, 4, 7, 16, 17]),
+                                         ((256, 400), 0.5, 0.2, 4, None), ((300, 400), 0.5, 0.9, 4, None)):
+        with torch.no_grad():
+            preds_u = model(imgs, inference=True, og_size=og)
+        cap_u = ref_harness.ref_post_process(preds_u, C, iou, thr, allow, tracked)
+        dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, inference_det=ns.inference_det)
+        try:
+            n0 = _lib.launch_count()
+            with torch.no_grad():
+                preds_p = model(imgs, inference=True, og_size=og)
+            assert isinstance(preds_p, lazy.LazyPreds) and preds_p.pending and tuple(preds_p.shape) == tuple(preds_u.shape)
+            assert _lib.launch_count() == n0                       # nothing has been computed yet
+            cap_p = ref_harness.ref_post_process(preds_p, C, iou, thr, allow, tracked)
+            assert preds_p.pending                                 # ... and the decoded [B,N,85] tensor never was
+            assert cap_p["boxes"].shape[0] < preds_u.shape[0] * preds_u.shape[1] // 2   # the reference ran on the kept rows only
+        finally:
+            dropin.uninstall()
+        assert len(cap_p["per_image"]) == len(cap_u["per_image"]), (og, thr)
+        nrows = 0
+        for a, b in zip(cap_p["per_image"], cap_u["per_image"]):
+            assert a.shape == b.shape
+            assert_close(rows_canon(a, np.zeros(len(a))), rows_canon(b, np.zeros(len(b))), rtol=1e-5, atol=2e-5 * 400, what="rows")
+            assert np.array_equal(np.sort(a[:, 1]), np.sort(b[:, 1]))
+            nrows += len(a)
+        print("zero-edit fused inference og=%s thr=%.2f tracked=%s: %d rows over %d images, identical to the unpatched run"
+              % (og, thr, tracked, nrows, len(cap_p["per_image"])))
+
+
 def test_ratio_metrics_patched(ns):
     from vision_conglomerate_b200 import dropin
     g = torch.Generator().manual_seed(31)

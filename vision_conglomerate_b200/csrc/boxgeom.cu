@@ -355,25 +355,10 @@ size_t bg_detect_workspace_bytes(const bg_detect_params *p, size_t mask_bytes)
 
 }  // extern "C"
 
-// shared body of bg_detect (three raw head tensors) and bg_post_process (one decoded [B,N,D] tensor)
-static int detect_impl(const float *raw_sm, const float *raw_md, const float *raw_lg, int predecoded, const bg_detect_params *pp,
-                       float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
-                       size_t workspace_bytes, size_t mask_bytes, void *stream)
+// geometry / decode parameters of the kernel argument block; returns whether the three inputs are 16-byte aligned
+static bool det_fill_geometry(DetectK &k, const float *const raws[3], int predecoded, const bg_detect_params *pp, long long N)
 {
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!det_valid(pp) || !raw_sm || !raw_md || !raw_lg || !out_boxes || !out_img || !out_keep || !out_counts || !workspace)
-        return BG_ERR_INVALID;
-    const long long N = det_candidates(pp);
-    const TilePlan tp = det_tile_plan(pp);
-    const int path = det_nms_path(pp, tp);
-    if (path < 0 || !det_plan_valid(pp, tp)) return BG_ERR_INVALID;
-    DetWs w;
-    if (det_carve((unsigned char *)workspace, pp->B, N, tp.tpi_total, path == 1, pp->order != 0, mask_bytes, w) > workspace_bytes)
-        return BG_ERR_WORKSPACE;
-
-    DetectK k;
     memset(&k, 0, sizeof(k));
-    const float *raws[3] = {raw_sm, raw_md, raw_lg};
     int off = 0;
     bool aligned = true;
     for (int s = 0; s < 3; ++s) {
@@ -401,6 +386,28 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
     k.use_allowance = pp->box_allowance != 0.0f;
     k.allowance = pp->box_allowance;
     k.score_thr = pp->score_threshold;
+    return aligned;
+}
+
+// shared body of bg_detect (three raw head tensors) and bg_post_process (one decoded [B,N,D] tensor)
+static int detect_impl(const float *raw_sm, const float *raw_md, const float *raw_lg, int predecoded, const bg_detect_params *pp,
+                       float *out_boxes, int64_t *out_img, int64_t *out_keep, int32_t *out_counts, void *workspace,
+                       size_t workspace_bytes, size_t mask_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!det_valid(pp) || !raw_sm || !raw_md || !raw_lg || !out_boxes || !out_img || !out_keep || !out_counts || !workspace)
+        return BG_ERR_INVALID;
+    const long long N = det_candidates(pp);
+    const TilePlan tp = det_tile_plan(pp);
+    const int path = det_nms_path(pp, tp);
+    if (path < 0 || !det_plan_valid(pp, tp)) return BG_ERR_INVALID;
+    DetWs w;
+    if (det_carve((unsigned char *)workspace, pp->B, N, tp.tpi_total, path == 1, pp->order != 0, mask_bytes, w) > workspace_bytes)
+        return BG_ERR_WORKSPACE;
+
+    DetectK k;
+    const float *raws[3] = {raw_sm, raw_md, raw_lg};
+    const bool aligned = det_fill_geometry(k, raws, predecoded, pp, N);
     k.keys = w.slot_keys; k.box_slots = w.box_slots; k.cls_slots = w.cls_slots;
     k.box_dense = w.box_dense; k.cls_dense = w.cls_dense;
 
@@ -546,6 +553,21 @@ int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t
     k.fW = (float)W; k.fH = (float)H; k.fW0 = (float)og_W; k.fH0 = (float)og_H;
     if (anchors) for (int a = 0; a < na; ++a) { k.aw[a] = anchors[2 * a]; k.ah[a] = anchors[2 * a + 1]; }
     decode_scale_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+int bg_decode_rows(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *pp, const int64_t *idx,
+                   int64_t n, float *out, void *stream)
+{
+    if (n < 0 || !det_valid(pp)) return BG_ERR_INVALID;
+    if (n == 0) return BG_OK;
+    if (!raw_sm || !raw_md || !raw_lg || !idx || !out) return BG_ERR_INVALID;
+    DetectK k;
+    const float *raws[3] = {raw_sm, raw_md, raw_lg};
+    det_fill_geometry(k, raws, 0, pp, det_candidates(pp));
+    long long blocks = (n * 32 + 255) / 256;  // one warp per row
+    decode_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(k, reinterpret_cast<const long long *>(idx), n, out);
     BG_LAUNCH_CHECK();
     return BG_OK;
 }
@@ -874,7 +896,9 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
 #undef BG_MATCH_LAUNCH
         BG_LAUNCH_CHECK();
     }
-    int rc = launch_after(loss_dense_kernel, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0);
+    static const int dense_occ = []() { const char *e = getenv("BG_DENSE_OCC"); return (e && e[0] == '5') ? 5 : 8; }();
+    int rc = dense_occ == 5 ? launch_after(loss_dense_kernel<5>, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0)
+                            : launch_after(loss_dense_kernel<8>, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0);
     if (rc != BG_OK) return rc;
     rc = launch_after(loss_finalize_kernel, dim3(1), dim3(768), 0, st, k);
     if (rc != BG_OK) return rc;

@@ -569,4 +569,36 @@ __global__ void __launch_bounds__(256) bbox_to_size_kernel(float *pred, long lon
     }
 }
 
+// Rows of DetectionNet.forward(x, inference=True) (modules/detection.py:69-91) for SELECTED candidates only: out[r] =
+// [obj logit, class logits, x, y, w, h (+ trailing columns)] of flat candidate idx[r] = b*N + i, the box decoded (and
+// rescaled to the original frame) by the same arithmetic as decode_xyxy -- before the allowance and the xyxy step,
+// which the caller's post-processing applies itself (inference_det.py:73-76).  One warp per row.
+__global__ void __launch_bounds__(256) decode_rows_kernel(DetectK k, const long long *idx, long long n, float *out)
+{
+    const long long r = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const long long f = idx[r];
+    const int b = (int)(f / k.N);
+    int i = (int)(f - (long long)b * k.N), si = 0;
+    if (i >= k.sc[1].img_off) si = (i >= k.sc[2].img_off) ? 2 : 1;
+    const ScaleDesc &s = k.sc[si];
+    i -= s.img_off;
+    const float *row = s.raw + ((long long)b * s.img_stride + i) * k.D;
+    float *o = out + r * k.D;
+    for (int c = lane; c < k.D; c += 32) {
+        float v = row[c];
+        const int q = c - k.C - 1;
+        if (q >= 0 && q < 4) {
+            const int a = i % k.na, cell = i / k.na;
+            const int x = cell % s.nx, y = cell / s.nx;
+            const float sg = __fmul_rn(sigmoid_acc(v), 2.0f);
+            if (q < 2) v = __fmul_rn(__fadd_rn(__fsub_rn(sg, 0.5f), q == 0 ? (float)x : (float)y), q == 0 ? s.s0 : s.s1);
+            else v = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(sg, sg), q == 2 ? s.aw[a] : s.ah[a]), q == 2 ? s.fnx : s.fny), q == 2 ? s.s0 : s.s1);
+            if (k.rescale) { const bool isx = (q == 0 || q == 2); v = __fmul_rn(__fdiv_rn(v, isx ? k.fW : k.fH), isx ? k.fW0 : k.fH0); }
+        }
+        o[c] = v;
+    }
+}
+
 }  // namespace bg

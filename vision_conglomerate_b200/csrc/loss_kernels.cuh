@@ -97,8 +97,6 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];   // [MATCH_CHUNK] MatchRec, then [3*C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
-    __shared__ int s_wcnt[LOSS_THREADS / 32], s_wpre[LOSS_THREADS / 32 + 1];
-    __shared__ int s_base;
     MatchRec *s_rec = reinterpret_cast<MatchRec *>(s_dyn);
     int *s_hist = reinterpret_cast<int *>(s_dyn + sizeof(MatchRec) * MATCH_CHUNK);
     const LossScale &S = k.s[blockIdx.y];
@@ -106,13 +104,15 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
     const int C = CT ? CT : k.C;
     constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
     for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
+    __syncthreads();
 
-    // ---- 1. the block's candidates.  Warp w owns candidates [chunk*CHUNK + w*128, +128) (slice i = its lanes' i-th
-    //         candidates) and writes the records of the emitted ones, in candidate order, to its own quarter-kilobyte
-    //         region of the staging array: one evaluation per candidate, no block-wide prefix needed for the position.
+    // Every WARP runs the whole pipeline on its own 128 candidates [chunk*CHUNK + w*128, +128) without block barriers:
+    // ---- 1. evaluate the candidates (slice i = the lanes' i-th candidates) and write the records of the emitted ones,
+    //         in candidate order, to the warp's own region of the staging array
     const long long c0 = (long long)blockIdx.x * MATCH_CHUNK;
+    MatchRec *wrec = s_rec + wid * (32 * MATCH_PER);
     bool bad = false;
-    int wcount = 0;  // records this warp has written so far (warp-uniform)
+    int wcount = 0;  // records this warp has written (warp-uniform)
 #pragma unroll
     for (int i = 0; i < MATCH_PER; ++i) {
         const int lc = wid * (32 * MATCH_PER) + i * 32 + lane;  // local candidate number
@@ -129,34 +129,22 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
             r.cell = ((o.b * S.a.ny + o.gj) * S.a.nx + o.gi) * S.a.na + o.a;
             r.cls_a = o.cls | (o.a << 16) | (lc << 20);
             r.bx = o.bx; r.by = o.by; r.bw = o.bw; r.bh = o.bh;
-            s_rec[wid * (32 * MATCH_PER) + wcount + __popc(bal & lanemask_lt())] = r;
+            wrec[wcount + __popc(bal & lanemask_lt())] = r;
         }
         wcount += __popc(bal);
     }
-    if (lane == 0) s_wcnt[wid] = wcount;
-    __syncthreads();
     pdl_wait();  // everything above reads only the targets; the counters / match arrays / head words are cleared upstream
     if (bad) atomicOr(k.status, 1);
-    if (tid == 0) {
-        int tot = 0;
-        for (int w = 0; w < LOSS_THREADS / 32; ++w) { const int v = s_wcnt[w]; s_wpre[w] = tot; tot += v; }
-        s_wpre[LOSS_THREADS / 32] = tot;
-        s_base = tot ? atomicAdd(S.M, tot) : 0;
-    }
-    __syncthreads();
-    const int nloc = s_wpre[LOSS_THREADS / 32], base = s_base;
-    // dense match number j of the block -> its record: the warp whose range holds j, then the position inside its region
-    auto rec_of = [&](int j) -> const MatchRec & {
-        int w = 0;
-#pragma unroll
-        for (int q = 1; q < LOSS_THREADS / 32; ++q) w += (j >= s_wpre[q]) ? 1 : 0;
-        return s_rec[w * (32 * MATCH_PER) + (j - s_wpre[w])];
-    };
+    // the warp's matches get a range of the match arrays with one atomic (the slot order never reaches a result)
+    int base = 0;
+    if (lane == 0 && wcount) base = atomicAdd(S.M, wcount);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
 
-    // ---- 2. one thread per match: gather, CIoU and its gradient, link into the cell's list; records to global memory
+    // ---- 2. one lane per match: gather, CIoU and its gradient, link into the cell's list; records to global memory
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int j = tid; j < nloc; j += LOSS_THREADS) {
-        const MatchRec r = rec_of(j);
+    for (int j = lane; j < wcount; j += 32) {
+        const MatchRec r = wrec[j];
         const int m = base + j, cell = r.cell, an = (r.cls_a >> 16) & 15;
         const float aw = S.a.aw[an], ah = S.a.ah[an];
         const float *bp = S.v.box + (long long)cell * S.v.sb;
@@ -187,11 +175,11 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
         a2 += (double)sigmoid_acc(obj);
     }
 
-    // ---- 3. eight lanes per match (four matches per warp in flight): class BCE, argmax, confusion counters
+    // ---- 3. eight lanes per match (four matches of the warp in flight): class BCE, argmax, confusion counters
     const int gl = lane & 7;
-    for (int jb = wid * 4; jb < nloc; jb += (LOSS_THREADS / 32) * 4) {
+    for (int jb = 0; jb < wcount; jb += 4) {
         const int j = jb + (lane >> 3);
-        const bool valid = j < nloc;
+        const bool valid = j < wcount;
         // sum_c bce(x_c, t_c) = sum_c softplus(x_c) - cn * sum_c x_c - (cp - cn) * x_target, with
         // softplus(x) = max(x, 0) + log(1 + exp(-|x|)); the logs of a lane's classes are taken as ONE log of the
         // product (each factor lies in (1, 2], ten of them stay far from overflow) -- fast exp/log units, |error| of
@@ -199,15 +187,14 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
         float bsum = 0.f, best = -INFINITY;
         int bi = 0x7fffffff, tc = -1;
         if (valid) {
-            const MatchRec &rr = rec_of(j);
-            tc = rr.cls_a & 0xffff;
-            const float *row = S.v.cls + (long long)rr.cell * S.v.sc;
+            tc = wrec[j].cls_a & 0xffff;
+            const float *row = S.v.cls + (long long)wrec[j].cell * S.v.sc;
             float spos = 0.f, sx = 0.f, lsum = 0.f;
             for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
                 float x[ROWS_UNROLL];
 #pragma unroll
                 for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = (kFull || c < C) ? __ldg(row + c) : -INFINITY; }
-                float prod = 1.f;
+                float prod = 1.f, mx = -INFINITY;
 #pragma unroll
                 for (int u = 0; u < ROWS_UNROLL; ++u) {
                     const int c = cb + 8 * u + gl;
@@ -215,10 +202,15 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
                         prod *= 1.0f + __expf(-fabsf(x[u]));
                         spos += fmaxf(x[u], 0.0f);
                         sx += x[u];
-                        if (x[u] > best) { best = x[u]; bi = c; }
+                        mx = fmaxf(mx, x[u]);
                     }
                 }
                 lsum += __logf(prod);
+                if (mx > best) {  // first index holding the batch maximum (the batches ascend in class index)
+                    best = mx;
+#pragma unroll
+                    for (int u = ROWS_UNROLL - 1; u >= 0; --u) if (x[u] == mx) bi = cb + 8 * u + gl;
+                }
             }
             bsum = spos + lsum - k.cn * sx;
             if (gl == 0) bsum -= (k.cp - k.cn) * __ldg(row + tc);
@@ -263,7 +255,8 @@ __device__ __forceinline__ float ld_stride_f32(const float *p)
 }
 
 // dense objectness BCE over every cell
-__global__ void __launch_bounds__(LOSS_THREADS) loss_dense_kernel(Loss3K k)
+template <int OCC>  // CTAs per SM
+__global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_dense_kernel(Loss3K k)
 {
     __shared__ double s_red[LOSS_THREADS / 32][3];
     const LossScale &S = k.s[blockIdx.y];

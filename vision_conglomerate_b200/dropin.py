@@ -13,8 +13,11 @@ re-implementation of ours.  CPU tensors are refused: there is no CPU fallback.
 Training (``train_det.py``): ``_get_scale_pred(inference=False)`` returns a :class:`lazy.LazyDecoded` stand-in and
 ``DetectionLoss.forward`` feeds the head's logits to the fused loss (decode applied in registers, gradient back to
 the logits); nothing else in the reference's step touches the predictions (pipeline/detection_trainer.py:178-184).
-Inference (``inference_det.py``): decode and ``_bbox_to_size`` per scale on the device, ``batched_nms`` on the
-segmented engine.  The fully fused decode+NMS (``ops.detect``) needs the 3-line edit of INTEGRATION.md section 2.
+Inference (``inference_det.py``): with the module passed to ``install(inference_det=...)`` the whole of
+``model(x, inference=True, og_size) -> post_process_preds(...)`` runs on the fused decode+NMS kernels with zero edits
+(the model returns a :class:`lazy.LazyPreds` stand-in; ``post_process_preds`` is wrapped: fused kernels first, then
+the reference's OWN function on the kept candidates only, so its drawing / tracking / CSV code stays its own).
+Without it: decode and ``_bbox_to_size`` per scale on the device, ``batched_nms`` on the segmented engine.
 """
 from __future__ import annotations
 
@@ -23,7 +26,9 @@ from typing import Any, Dict, Optional
 import torch
 
 from . import ops
-from .lazy import HeadTrace, LazyRows, loss_inputs_if_pending
+import threading
+
+from .lazy import HeadTrace, LazyPreds, LazyRows, loss_inputs_if_pending
 
 _saved: Dict[str, Any] = {}
 
@@ -119,8 +124,76 @@ def _make_get_scale_pred(orig):
             return ops.decode_train(scale_pred)
         if isinstance(scale_pred, LazyRows):
             scale_pred = scale_pred.materialize()
-        return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), inference)
+        ishape = tuple(int(v) for v in input_shape)
+        if _options["fuse_inference"] and "post_process_preds" in _saved and scale_pred.shape[-1] == self.num_classes + 5:
+            # stands for the decoded tensor of this scale; the wrapped post_process_preds runs the fused decode+NMS on
+            # the head outputs, any other consumer gets the decoded values on first use
+            raw = scale_pred if scale_pred.is_contiguous() else scale_pred.contiguous()
+            return LazyPreds(tuple(raw.shape), [dict(raw=raw, anchors=anchors, input_shape=ishape, rescale=None, og_size=None,
+                                                     num_classes=self.num_classes)])
+        return ops.decode_scale(scale_pred, anchors, ishape, inference)
     return _get_scale_pred
+
+
+_tls = threading.local()
+
+
+def _make_net_forward(orig):
+    def forward(self, x, inference: bool = False, og_size=None):
+        # remembers og_size for _bbox_to_size, which only receives the derived device tensors (detection.py:77-81)
+        _tls.og_size = tuple(int(v) for v in og_size) if og_size is not None else None
+        try:
+            return orig(self, x, inference, og_size)
+        finally:
+            _tls.og_size = None
+    return forward
+
+
+_detect_plans: Dict[Any, Any] = {}
+
+
+def _make_post_process_preds(orig):
+    def post_process_preds(imgs, preds, num_classes, colormap=None, iou_threshold: float = 0.5, score_threshold: float = 0.1,
+                           vwriter=None, tracker=None, classmap=None, with_summary: bool = False, tracked_classes=None,
+                           start_idx: int = 0, box_allowance=None):
+        rest = dict(colormap=colormap, iou_threshold=iou_threshold, score_threshold=score_threshold, vwriter=vwriter,
+                    tracker=tracker, classmap=classmap, with_summary=with_summary, tracked_classes=tracked_classes,
+                    start_idx=start_idx, box_allowance=box_allowance)
+        sc = preds.scales if isinstance(preds, LazyPreds) and preds.pending else None
+        if sc is None or len(sc) != 3 or preds.dim() != 3 or not (score_threshold >= 0) \
+                or len({(s["rescale"] is None, s["og_size"], s["input_shape"]) for s in sc}) != 1:
+            return orig(imgs, preds, num_classes, **rest)
+        # 1. fused decode + score filter + per-image NMS on the head outputs (lines 57-89 of the reference function)
+        raws = [s["raw"] for s in sc]
+        og = sc[0]["og_size"] if sc[0]["rescale"] is not None else None
+        key = (raws[0].device, tuple(tuple(r.shape) for r in raws), sc[0]["input_shape"], og, float(iou_threshold),
+               float(score_threshold), box_allowance, int(num_classes))
+        plan = _detect_plans.get(key)
+        if plan is None:
+            if len(_detect_plans) > 8:
+                _detect_plans.clear()
+            plan = _detect_plans[key] = ops.DetectPlan([tuple(r.shape) for r in raws], [s["anchors"] for s in sc], sc[0]["input_shape"],
+                                                       int(num_classes), raws[0].device, og, float(iou_threshold),
+                                                       float(score_threshold), box_allowance, None, "image")
+        plan.enqueue(raws)
+        det = plan.result()
+        # 2. the reference's own function on the kept candidates only: their rows of the decoded tensor, image by image,
+        #    padded to a rectangle with rows that can neither pass the score threshold nor suppress anything
+        B, D = int(preds.shape[0]), int(preds.shape[2])
+        counts = det.counts.to(torch.int64)
+        kmax = max(int(counts.max()) if B else 0, 1)
+        small = torch.zeros(B, kmax, D, dtype=torch.float32, device=raws[0].device)
+        small[..., 0] = float("-inf")                                    # sigmoid(-inf) = 0: score 0, ranked last
+        if det.keep_idxs.numel():
+            rows = plan.decode_rows(det.keep_idxs)
+            offs = torch.zeros(B, dtype=torch.int64)
+            offs[1:] = torch.cumsum(counts, 0)[:-1]
+            offs = offs.to(rows.device, non_blocking=True)
+            pos = torch.arange(rows.shape[0], device=rows.device) - offs[det.sample_idxs]
+            small[det.sample_idxs, pos] = rows
+        return orig(imgs, small, num_classes, **rest)
+    return post_process_preds
+
 
 
 # ------------------------------------------------------------------------------------------------ f3
@@ -141,6 +214,13 @@ def _make_bbox_to_size(orig):
         if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
             return orig(self, pred, _from, _to)
         _need_cuda(pred, "_bbox_to_size")
+        if isinstance(pred, LazyPreds) and pred.pending:
+            og = getattr(_tls, "og_size", None)
+            if og is not None:
+                out = pred.with_rescale(_from, _to)
+                for sc in out.scales:
+                    sc["og_size"] = og
+                return out
         return ops.bbox_to_size(pred, _from, _to, self.num_classes)
     return _bbox_to_size
 
@@ -171,11 +251,12 @@ def _make_ratio_metrics(orig, extras: bool):
     return ratio_metrics
 
 
-_options = {"fuse_train_decode": True, "split_head": True}
+_options = {"fuse_train_decode": True, "split_head": True, "fuse_inference": True}
 
 
 def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True, make_anchors=None,
-            fuse_train_decode: bool = True, EffiDecHead=None, split_head: bool = True) -> None:
+            fuse_train_decode: bool = True, EffiDecHead=None, split_head: bool = True, inference_det=None,
+            fuse_inference: bool = True) -> None:
     """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
     imported in your process (any subset); ``torchvision_ops=True`` also replaces
     ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time); ``make_anchors`` is the
@@ -186,6 +267,12 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
     otherwise the pieces are made contiguous -- the copy the concatenation would have been)."""
     _options["fuse_train_decode"] = bool(fuse_train_decode)
     _options["split_head"] = bool(split_head)
+    _options["fuse_inference"] = bool(fuse_inference)
+    if inference_det is not None and "post_process_preds" not in _saved:
+        # ``inference_det`` (the reference's script module): evaluate_frames looks post_process_preds up in the module's
+        # globals at call time (inference_det.py:199-207,229-239)
+        _saved["post_process_preds"] = (inference_det, inference_det.post_process_preds)
+        inference_det.post_process_preds = _make_post_process_preds(inference_det.post_process_preds)
     if EffiDecHead is not None and "EffiDecHead.forward" not in _saved:
         _saved["EffiDecHead.forward"] = (EffiDecHead, EffiDecHead.__dict__["forward"])
         EffiDecHead.forward = _make_head_forward(EffiDecHead.__dict__["forward"])
@@ -204,6 +291,9 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
     if DetectionNet is not None and "_get_scale_pred" not in _saved:
         _saved["_get_scale_pred"] = (DetectionNet, DetectionNet.__dict__["_get_scale_pred"])
         DetectionNet._get_scale_pred = _make_get_scale_pred(DetectionNet.__dict__["_get_scale_pred"])
+        if "forward" in DetectionNet.__dict__:
+            _saved["DetectionNet.forward"] = (DetectionNet, DetectionNet.__dict__["forward"])
+            DetectionNet.forward = _make_net_forward(DetectionNet.__dict__["forward"])
         if "_bbox_to_size" in DetectionNet.__dict__:
             _saved["_bbox_to_size"] = (DetectionNet, DetectionNet.__dict__["_bbox_to_size"])
             DetectionNet._bbox_to_size = _make_bbox_to_size(DetectionNet.__dict__["_bbox_to_size"])
@@ -222,7 +312,7 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
 
 
 _NAMES = ("build_target_by_scale", "compute_ciou", "forward", "_get_scale_pred", "_bbox_to_size", "_make_2dgrid",
-          "batched_nms", "ratio_metrics", "ratio_metrics_w_extras")
+          "batched_nms", "ratio_metrics", "ratio_metrics_w_extras", "post_process_preds")
 
 
 def uninstall() -> None:
@@ -230,9 +320,11 @@ def uninstall() -> None:
         if name in _saved:
             owner, orig = _saved.pop(name)
             setattr(owner, name, orig)
-    if "EffiDecHead.forward" in _saved:
-        owner, orig = _saved.pop("EffiDecHead.forward")
-        owner.forward = orig
+    for key in ("EffiDecHead.forward", "DetectionNet.forward"):
+        if key in _saved:
+            owner, orig = _saved.pop(key)
+            owner.forward = orig
+    _detect_plans.clear()
     _saved.pop("DetectionLoss.loss_fn", None)
 
 

@@ -141,3 +141,97 @@ def loss_inputs_if_pending(preds):
     if kinds == {3}:
         return "split", [p.parts for p in preds]
     return None
+
+
+class LazyPreds(torch.Tensor):
+    """Stands for the inference-mode predictions of ``DetectionNet.forward(x, inference=True, og_size=...)``
+    (modules/detection.py:69-91) -- one scale ``[B,ny,nx,na,D]``, one scale reshaped ``[B,n,D]``, or the concatenated
+    ``[B,N,D]`` -- holding only the head outputs and what the forward would have done to them.  The patched
+    ``inference_det.post_process_preds`` recognises the concatenated form and runs the fused decode+NMS on the head
+    outputs; any other consumer gets the real tensor (CUDA decode per scale, ``_bbox_to_size``, reshape, cat)."""
+
+    @staticmethod
+    def __new__(cls, shape, scales):
+        raw = scales[0]["raw"]
+        base = torch.empty(1, dtype=raw.dtype, device=raw.device).expand(tuple(shape))
+        return torch.Tensor._make_subclass(cls, base, False)
+
+    def __init__(self, shape, scales):
+        self._bg_scales = list(scales)   # per scale: raw, anchors, input_shape, rescale (None or (_from, _to)), num_classes
+        self._bg_real: Optional[torch.Tensor] = None
+
+    @property
+    def pending(self) -> bool:
+        return self._bg_real is None
+
+    @property
+    def scales(self):
+        return self._bg_scales
+
+    def with_rescale(self, _from, _to) -> "LazyPreds":
+        return LazyPreds(tuple(_T.size(self)), [dict(sc, rescale=(_from, _to)) for sc in self._bg_scales])
+
+    def materialize(self) -> torch.Tensor:
+        if self._bg_real is None:
+            from . import ops
+            outs = []
+            for sc in self._bg_scales:
+                d = ops.decode_scale(sc["raw"], sc["anchors"], sc["input_shape"], True)
+                if sc["rescale"] is not None:
+                    d = ops.bbox_to_size(d, sc["rescale"][0], sc["rescale"][1], sc["num_classes"])
+                outs.append(d)
+            shape = tuple(_T.size(self))
+            if len(outs) == 1:
+                real = outs[0].reshape(shape)
+            else:
+                real = torch.cat([o.reshape(shape[0], -1, shape[-1]) for o in outs], dim=1)
+            self._bg_real = real
+        return self._bg_real
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        me = args[0] if args and isinstance(args[0], LazyPreds) else None
+        if me is not None and func in _META:
+            if func == _T.is_contiguous:
+                return True
+            if func == _T.requires_grad.__get__:
+                return False
+            with torch._C.DisableTorchFunctionSubclass():
+                if func == _T.stride:
+                    return func(torch.empty(0, device="meta").new_empty(tuple(_T.size(me))), *args[1:], **kwargs)
+                return func(*args, **kwargs)
+        if me is not None and me.pending:
+            shape = tuple(_T.size(me))
+            # the shape-only steps of DetectionNet.forward keep the stand-in: reshape(B, -1, D), flatten(1, -2) of [B,N,D]
+            if func in (_T.reshape, torch.reshape, _T.view) and len(me._bg_scales) == 1:
+                tgt = args[1] if len(args) == 2 and isinstance(args[1], (tuple, list, torch.Size)) else args[1:]
+                tgt = tuple(int(v) for v in tgt)
+                if len(tgt) == 3 and tgt[0] == shape[0] and tgt[2] == shape[-1] and tgt[1] in (-1, me.numel() // (shape[0] * shape[-1])):
+                    return LazyPreds((shape[0], me.numel() // (shape[0] * shape[-1]), shape[-1]), me._bg_scales)
+            if func in (_T.flatten, torch.flatten) and len(shape) == 3:
+                sd = kwargs.get("start_dim", args[1] if len(args) > 1 else 0)
+                ed = kwargs.get("end_dim", args[2] if len(args) > 2 else -1)
+                if sd == 1 and ed in (-2, 1):
+                    return me
+            if func == _T.contiguous:
+                return me
+        if func is torch.cat and args and isinstance(args[0], (list, tuple)) and len(args[0]) == 3:
+            parts = args[0]
+            dim = kwargs.get("dim", args[1] if len(args) > 1 else 0)
+            if dim == 1 and all(isinstance(p, LazyPreds) and p.pending and len(p._bg_scales) == 1 and p.dim() == 3 for p in parts) \
+                    and len({(p.shape[0], p.shape[2]) for p in parts}) == 1:
+                return LazyPreds((parts[0].shape[0], sum(int(p.shape[1]) for p in parts), parts[0].shape[2]),
+                                 [p._bg_scales[0] for p in parts])
+
+        def real(a):
+            if isinstance(a, (LazyPreds, LazyRows)):
+                return a.materialize()
+            if isinstance(a, (list, tuple)):
+                return type(a)(real(x) for x in a)
+            if isinstance(a, dict):
+                return {k: real(v) for k, v in a.items()}
+            return a
+
+        return func(*real(args), **real(kwargs))
+

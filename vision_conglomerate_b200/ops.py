@@ -325,6 +325,21 @@ class DetectPlan:
                               h[2 + B: 2 + 2 * B].clone())
 
 
+    def decode_rows(self, idx: torch.Tensor) -> torch.Tensor:
+        """``[K, 5+C(+extra)]`` rows ``[obj logit, class logits, x, y, w, h, ...]`` of the flat candidates ``idx`` (e.g.
+        ``Detections.keep_idxs``) of the last enqueued batch: what ``DetectionNet.forward(x, inference=True)`` holds for
+        them (modules/detection.py:69-91), decoded exactly as the fused kernels decode internally."""
+        if self.predecoded:
+            raise RuntimeError("decode_rows: the plan was built on already decoded rows")
+        idx = _req(idx, "idx", torch.int64).reshape(-1)
+        D = self.params.C + 5 + self.params.extra_cols
+        out = torch.empty(idx.numel(), D, dtype=torch.float32, device=self.dev)
+        with _on(self.dev):
+            check(_lib.lib().bg_decode_rows(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(),
+                                            C.byref(self.params), idx.data_ptr(), idx.numel(), out.data_ptr(), _stream(self.dev)),
+                  "bg_decode_rows")
+        return out
+
     # ---- SURVEY 8 f4: the step after the path (inference_det.py:100-129) ----------------------------------------
     def enqueue_host_copy(self) -> None:
         """Queue ONE device->host copy of [counts | rows] behind the kernels of the last ``enqueue`` (pinned buffer;
