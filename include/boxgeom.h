@@ -228,8 +228,6 @@ typedef struct {
     float scale_w[3];
     int64_t nt;
     int32_t input_form;  /* BG_LOSS_DECODED / BG_LOSS_RAW / BG_LOSS_RAW_SPLIT */
-    int32_t backward_follows; /* forward: non-zero = bg_loss_bwd will run on this workspace; the objectness residuals are then
-                          * stored with an L2 evict-last hint (the backward's fill kernel reads them inside a 2 GB write stream) */
     int32_t extra_cols;  /* interleaved forms: columns after the box columns (mask coefficients, keypoints) that the loss
                           * skips; rows are 5 + C + extra_cols floats and their gradient is written as zeros */
 } bg_loss_params;

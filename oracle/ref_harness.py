@@ -170,7 +170,9 @@ def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_all
         B = preds.shape[0]
         imgs = torch.zeros(B, 3, 8, 8, dtype=torch.uint8, device=preds.device)
         with torch.no_grad():
-            inf.post_process_preds(imgs, preds.clone(), num_classes, iou_threshold=iou_threshold,
+            # (the reference adds the box allowance in place on a view of preds: hand it a copy of a real tensor; a
+            # stand-in of the drop-in layer is passed as evaluate_frames passes it -- untouched)
+            inf.post_process_preds(imgs, preds.clone() if type(preds) is torch.Tensor else preds, num_classes, iou_threshold=iou_threshold,
                                    score_threshold=score_threshold, box_allowance=box_allowance,
                                    tracked_classes=list(tracked_classes) if tracked_classes else None)
     finally:

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--form", default="raw")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--iters", type=int, default=12)
+ap.add_argument("--nosync", action="store_true", help="enqueue all iterations back to back (no per-iteration synchronize)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 B, S, C = a.batch, 640, 80
@@ -43,8 +44,11 @@ for i in range(a.iters):
     ev[i][2].record()
     h2 = time.perf_counter()
     host.append(((h1 - h0) * 1e3, (h2 - h1) * 1e3))
-    torch.cuda.synchronize()
+    if not a.nosync:
+        torch.cuda.synchronize()
+torch.cuda.synchronize()
 st1 = torch.cuda.memory_stats()
+print('total GPU span %.3f ms/iter, host enqueue %.3f ms/iter, loadavg %s, cpus %d' % (ev[0][0].elapsed_time(ev[-1][2]) / a.iters, sum(x + y for x, y in host) / a.iters, os.getloadavg(), len(os.sched_getaffinity(0))))
 print("form=%s B=%d env PDL=%s" % (a.form, B, os.environ.get("BG_PDL", "1")))
 for i in range(a.iters):
     print("  it %2d: fwd %.3f ms  bwd %.3f ms | host fwd %.3f bwd %.3f" % (i, ev[i][0].elapsed_time(ev[i][1]), ev[i][1].elapsed_time(ev[i][2]),

@@ -62,7 +62,6 @@ class LossParams(C.Structure):
         ("scale_w", C.c_float * 3),
         ("nt", C.c_int64),
         ("input_form", C.c_int32),
-        ("backward_follows", C.c_int32),
         ("extra_cols", C.c_int32),
     ]
 

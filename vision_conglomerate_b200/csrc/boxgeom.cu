@@ -808,7 +808,6 @@ bool loss_fill(Loss3K &k, const bg_loss_params *p, const LossWs &w, const bg_hea
     memset(&k, 0, sizeof(k));
     k.B = p->B; k.C = p->C;
     k.raw = p->input_form != BG_LOSS_DECODED;
-    k.keep_l2 = p->backward_follows ? 1 : 0;
     // python: cn = 0.5 * label_smoothing, cp = 1 - cn in double, written into fp32 tensors (detection_loss.py:191-195)
     k.cn = (float)(0.5 * (double)p->label_smoothing);
     k.cp = (float)(1.0 - 0.5 * (double)p->label_smoothing);
@@ -896,7 +895,7 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
 #undef BG_MATCH_LAUNCH
         BG_LAUNCH_CHECK();
     }
-    static const int dense_occ = []() { const char *e = getenv("BG_DENSE_OCC"); return (e && e[0] == '5') ? 5 : 8; }();
+    static const int dense_occ = []() { const char *e = getenv("BG_DENSE_OCC"); return (e && e[0] == '8') ? 8 : 5; }();
     int rc = dense_occ == 5 ? launch_after(loss_dense_kernel<5>, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0)
                             : launch_after(loss_dense_kernel<8>, dim3(w.nblk_dense, 3), dim3(LOSS_THREADS), 0, st, k, p->nt > 0);
     if (rc != BG_OK) return rc;
@@ -954,14 +953,14 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
             }
             attr_smem = smem;
         }
-        static const bool pin = []() { const char *e = getenv("BG_L2_PIN"); return e && e[0] == '1'; }();
+        static const bool pin = []() { const char *e = getenv("BG_L2_PIN"); return !(e && e[0] == '0'); }();
         if (pin) {
             l2_pin_kernel<<<sms * 4, 256, 0, st>>>(reinterpret_cast<const float4 *>(w.gobj), w.cells_total / 4);
             BG_LAUNCH_CHECK();
         }
         const int per_sm = smem <= 110 * 1024 ? 2 : 1;
-        loss_bwd_stream_kernel<<<sms * per_sm, BWD_WARPS * 32, smem, st>>>(k);
-        BG_LAUNCH_CHECK();
+        const int rc = launch_after(loss_bwd_stream_kernel, dim3(sms * per_sm), dim3(BWD_WARPS * 32), smem, st, k, pin);
+        if (rc != BG_OK) return rc;
     }
     if (prof) cudaEventRecord(prof_b, st);
     if (p->nt == 0) return BG_OK;

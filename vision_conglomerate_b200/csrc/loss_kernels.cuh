@@ -63,7 +63,6 @@ struct Loss3K {
     LossScale s[3];
     int B, C;
     int raw;             // 1: the box values are logits, decode in registers
-    int keep_l2;         // forward: 1 = a backward follows, keep the objectness residuals in L2 for it (evict-last stores)
     float cn, cp;        // class targets: 0.5*label_smoothing and 1-cn
     int nblk_match, nblk_dense;
     double box_w, conf_w, class_w;
@@ -97,6 +96,8 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];   // [MATCH_CHUNK] MatchRec, then [3*C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
+    __shared__ int s_wcnt[LOSS_THREADS / 32], s_wpre[LOSS_THREADS / 32 + 1];
+    __shared__ int s_base;
     MatchRec *s_rec = reinterpret_cast<MatchRec *>(s_dyn);
     int *s_hist = reinterpret_cast<int *>(s_dyn + sizeof(MatchRec) * MATCH_CHUNK);
     const LossScale &S = k.s[blockIdx.y];
@@ -104,15 +105,13 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
     const int C = CT ? CT : k.C;
     constexpr bool kFull = CT != 0 && CT % (8 * ROWS_UNROLL) == 0;  // every lane's batch lies inside the row
     for (int i = tid; i < 3 * C; i += LOSS_THREADS) s_hist[i] = 0;
-    __syncthreads();
 
-    // Every WARP runs the whole pipeline on its own 128 candidates [chunk*CHUNK + w*128, +128) without block barriers:
-    // ---- 1. evaluate the candidates (slice i = the lanes' i-th candidates) and write the records of the emitted ones,
-    //         in candidate order, to the warp's own region of the staging array
+    // ---- 1. the block's candidates.  Warp w owns candidates [chunk*CHUNK + w*128, +128) (slice i = its lanes' i-th
+    //         candidates) and writes the records of the emitted ones, in candidate order, to its own quarter-kilobyte
+    //         region of the staging array: one evaluation per candidate, no block-wide prefix needed for the position.
     const long long c0 = (long long)blockIdx.x * MATCH_CHUNK;
-    MatchRec *wrec = s_rec + wid * (32 * MATCH_PER);
     bool bad = false;
-    int wcount = 0;  // records this warp has written (warp-uniform)
+    int wcount = 0;  // records this warp has written so far (warp-uniform)
 #pragma unroll
     for (int i = 0; i < MATCH_PER; ++i) {
         const int lc = wid * (32 * MATCH_PER) + i * 32 + lane;  // local candidate number
@@ -129,22 +128,34 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
             r.cell = ((o.b * S.a.ny + o.gj) * S.a.nx + o.gi) * S.a.na + o.a;
             r.cls_a = o.cls | (o.a << 16) | (lc << 20);
             r.bx = o.bx; r.by = o.by; r.bw = o.bw; r.bh = o.bh;
-            wrec[wcount + __popc(bal & lanemask_lt())] = r;
+            s_rec[wid * (32 * MATCH_PER) + wcount + __popc(bal & lanemask_lt())] = r;
         }
         wcount += __popc(bal);
     }
+    if (lane == 0) s_wcnt[wid] = wcount;
+    __syncthreads();
     pdl_wait();  // everything above reads only the targets; the counters / match arrays / head words are cleared upstream
     if (bad) atomicOr(k.status, 1);
-    // the warp's matches get a range of the match arrays with one atomic (the slot order never reaches a result)
-    int base = 0;
-    if (lane == 0 && wcount) base = atomicAdd(S.M, wcount);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < LOSS_THREADS / 32; ++w) { const int v = s_wcnt[w]; s_wpre[w] = tot; tot += v; }
+        s_wpre[LOSS_THREADS / 32] = tot;
+        s_base = tot ? atomicAdd(S.M, tot) : 0;
+    }
+    __syncthreads();
+    const int nloc = s_wpre[LOSS_THREADS / 32], base = s_base;
+    // dense match number j of the block -> its record: the warp whose range holds j, then the position inside its region
+    auto rec_of = [&](int j) -> const MatchRec & {
+        int w = 0;
+#pragma unroll
+        for (int q = 1; q < LOSS_THREADS / 32; ++q) w += (j >= s_wpre[q]) ? 1 : 0;
+        return s_rec[w * (32 * MATCH_PER) + (j - s_wpre[w])];
+    };
 
-    // ---- 2. one lane per match: gather, CIoU and its gradient, link into the cell's list; records to global memory
+    // ---- 2. one thread per match: gather, CIoU and its gradient, link into the cell's list; records to global memory
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int j = lane; j < wcount; j += 32) {
-        const MatchRec r = wrec[j];
+    for (int j = tid; j < nloc; j += LOSS_THREADS) {
+        const MatchRec r = rec_of(j);
         const int m = base + j, cell = r.cell, an = (r.cls_a >> 16) & 15;
         const float aw = S.a.aw[an], ah = S.a.ah[an];
         const float *bp = S.v.box + (long long)cell * S.v.sb;
@@ -175,11 +186,11 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
         a2 += (double)sigmoid_acc(obj);
     }
 
-    // ---- 3. eight lanes per match (four matches of the warp in flight): class BCE, argmax, confusion counters
+    // ---- 3. eight lanes per match (four matches per warp in flight): class BCE, argmax, confusion counters
     const int gl = lane & 7;
-    for (int jb = 0; jb < wcount; jb += 4) {
+    for (int jb = wid * 4; jb < nloc; jb += (LOSS_THREADS / 32) * 4) {
         const int j = jb + (lane >> 3);
-        const bool valid = j < wcount;
+        const bool valid = j < nloc;
         // sum_c bce(x_c, t_c) = sum_c softplus(x_c) - cn * sum_c x_c - (cp - cn) * x_target, with
         // softplus(x) = max(x, 0) + log(1 + exp(-|x|)); the logs of a lane's classes are taken as ONE log of the
         // product (each factor lies in (1, 2], ten of them stay far from overflow) -- fast exp/log units, |error| of
@@ -187,14 +198,15 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
         float bsum = 0.f, best = -INFINITY;
         int bi = 0x7fffffff, tc = -1;
         if (valid) {
-            tc = wrec[j].cls_a & 0xffff;
-            const float *row = S.v.cls + (long long)wrec[j].cell * S.v.sc;
+            const MatchRec &rr = rec_of(j);
+            tc = rr.cls_a & 0xffff;
+            const float *row = S.v.cls + (long long)rr.cell * S.v.sc;
             float spos = 0.f, sx = 0.f, lsum = 0.f;
             for (int cb = 0; cb < C; cb += 8 * ROWS_UNROLL) {
                 float x[ROWS_UNROLL];
 #pragma unroll
                 for (int u = 0; u < ROWS_UNROLL; ++u) { const int c = cb + 8 * u + gl; x[u] = (kFull || c < C) ? __ldg(row + c) : -INFINITY; }
-                float prod = 1.f, mx = -INFINITY;
+                float prod = 1.f;
 #pragma unroll
                 for (int u = 0; u < ROWS_UNROLL; ++u) {
                     const int c = cb + 8 * u + gl;
@@ -202,15 +214,10 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
                         prod *= 1.0f + __expf(-fabsf(x[u]));
                         spos += fmaxf(x[u], 0.0f);
                         sx += x[u];
-                        mx = fmaxf(mx, x[u]);
+                        if (x[u] > best) { best = x[u]; bi = c; }
                     }
                 }
                 lsum += __logf(prod);
-                if (mx > best) {  // first index holding the batch maximum (the batches ascend in class index)
-                    best = mx;
-#pragma unroll
-                    for (int u = ROWS_UNROLL - 1; u >= 0; --u) if (x[u] == mx) bi = cb + 8 * u + gl;
-                }
             }
             bsum = spos + lsum - k.cn * sx;
             if (gl == 0) bsum -= (k.cp - k.cn) * __ldg(row + tc);
@@ -262,8 +269,6 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_dense_kernel(Loss3K k)
     const LossScale &S = k.s[blockIdx.y];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
     constexpr int DENSE_PER = 4;
     const long long stride = (long long)gridDim.x * LOSS_THREADS;
@@ -307,10 +312,7 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_dense_kernel(Loss3K k)
             const float sg = __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
             a0 += (double)(fmaxf(x, 0.0f) - t * x + l);
             if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
-            // the backward's streaming kernel reads this residual in the middle of a 2 GB write stream: keep it in L2
-            // (evict-last), so those reads do not turn into DRAM read/write turnarounds
-            if (k.keep_l2) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(S.gobj + c), "f"(__fsub_rn(sg, t)), "l"(pol) : "memory");
-            else S.gobj[c] = __fsub_rn(sg, t);
+            S.gobj[c] = __fsub_rn(sg, t);
         }
     }
     pdl_launch_dependents();
@@ -423,13 +425,18 @@ __device__ __forceinline__ BwdScales bwd_scales(const Loss3K &k, const LossScale
 constexpr int BWD_WARPS = 8;  // warps per CTA of the streaming kernel (each owns one chunk image)
 
 // Mixing the 26 MB of residual reads into the 2.1 GB write stream costs ~45 us of DRAM read/write turnarounds
-// (measured: the same kernel without the loads runs 352 instead of 396 us).  So the residuals are pulled into L2
-// first, marked evict-last, and the write stream below uses evict-first stores: the streaming kernel's loads hit L2.
+// (measured: the same kernel without the loads runs 352 instead of 396 us).  So the backward first pulls the
+// residuals into L2 marked evict-last (this kernel, ~5 us), the write stream uses evict-first stores, and the streaming
+// kernel's loads -- which hit L2 -- demote each line to evict-first as they go: nothing stays pinned after the call.
+// (Round 1 marked the lines evict-last already when the forward stored them; a forward that is never followed by its
+// backward then leaves 26 MB of high-priority lines behind per call, and several of those starve every later kernel
+// of L2.)
 __global__ void __launch_bounds__(256) l2_pin_kernel(const float4 *p, long long n4)
 {
     float acc = 0.f;
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    pdl_launch_dependents();  // the fill kernel may become resident and prepare its chunk images meanwhile
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
         float4 v;
         asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
@@ -471,6 +478,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) loss_bwd_stream_kernel(Loss3K 
     for (int i = lane; i < chunk_floats; i += 32) im[i] = 0.f;  // only column 0 of a row ever changes
     __syncwarp();
     const float4 *im4 = reinterpret_cast<const float4 *>(im);
+    pdl_wait();  // (launched behind the pinning pass)
 
     long long nch[3], tot = 0;
     for (int s = 0; s < 3; ++s) { nch[s] = k.s[s].cells >> 5; tot += nch[s]; }  // full chunks; remainders below

@@ -656,12 +656,12 @@ _loss_param_cache: Dict[tuple, LossParams] = {}
 _FORMS = {"decoded": _lib.LOSS_DECODED, "raw": _lib.LOSS_RAW, "split": _lib.LOSS_RAW_SPLIT}
 
 
-def _loss_params(shapes, C_cls, extra, nt, anchors3, cfg, form, backward_follows) -> LossParams:
+def _loss_params(shapes, C_cls, extra, nt, anchors3, cfg, form) -> LossParams:
     """The parameter block of bg_loss_fwd / bg_loss_bwd; built once per (shapes, target count, anchors, weights)."""
     akey = tuple(tuple(map(tuple, _anchors_host(a))) for a in anchors3)   # by value
     sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
     key = (shapes, C_cls, extra, nt, akey, cfg.get("anchor_t", 4.0), cfg.get("edge_t", 0.5), cfg.get("label_smoothing", 0.0),
-           cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), tuple(sw), form, backward_follows)
+           cfg.get("box_w", 1.0), cfg.get("conf_w", 1.0), cfg.get("class_w", 1.0), tuple(sw), form)
     hit = _loss_param_cache.get(key)
     if hit is not None:
         return hit
@@ -687,7 +687,6 @@ def _loss_params(shapes, C_cls, extra, nt, anchors3, cfg, form, backward_follows
         p.scale_w[s] = float(sw[s])
     p.nt = nt
     p.input_form = form
-    p.backward_follows = 1 if backward_follows else 0
     p.extra_cols = extra
     return p
 
@@ -849,8 +848,7 @@ def detection_loss(preds3: Sequence, targets: torch.Tensor, anchors3: Sequence, 
     if targets.dim() != 2 or targets.shape[1] != 6:
         raise RuntimeError("detection_loss: keypoint targets are out of scope for the CUDA path")
     dev = _same_device(*tensors, targets)
-    needs_grad = torch.is_grad_enabled() and any(x.requires_grad for x in tensors)
-    params = _loss_params(shapes, Cc, extra, int(targets.shape[0]), anchors3, cfg, form, needs_grad)
+    params = _loss_params(shapes, Cc, extra, int(targets.shape[0]), anchors3, cfg, form)
     scalars = torch.empty(3, 8, dtype=torch.float64, device=dev)
     hist = torch.empty(3, 3, Cc, dtype=torch.int64, device=dev)
     status = torch.empty(1, dtype=torch.int32, device=dev)
