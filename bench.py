@@ -69,7 +69,7 @@ class ClockSampler:
     def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,clocks.mem,clocks.max.mem")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -91,7 +91,7 @@ class ClockSampler:
             self.t.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
+        sm, mx, reasons, mem, mem_mx = [], 0, set(), [], 0
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
@@ -100,11 +100,16 @@ class ClockSampler:
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
+                if len(r) > 8:
+                    mem.append(float(r[7]))
+                    mem_mx = max(mem_mx, float(r[8]))
             except Exception:
                 pass
         sm.sort()
+        mem.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "mem_mhz": mem[len(mem) // 2] if mem else None, "mem_mhz_min": mem[0] if mem else None,
+                "mem_max_mhz": mem_mx or None}
 
 
 def _all_host_threads():

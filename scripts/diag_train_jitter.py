@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--form", default="raw")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--iters", type=int, default=12)
+ap.add_argument("--prelude-fwd", type=int, default=0, help="forward-only calls (graph kept, no backward) before the timed loop, like prof_train.py")
 ap.add_argument("--nosync", action="store_true", help="enqueue all iterations back to back (no per-iteration synchronize)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -29,6 +30,10 @@ for _ in range(3):
     loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False, input_form=a.form)
     loss.backward()
 torch.cuda.synchronize()
+for _ in range(a.prelude_fwd):
+    for p in preds:
+        p.grad = None
+    loss, _ = ops.detection_loss(preds, t, anc, synth.LOSS_CONFIG, with_metrics=False, input_form=a.form)
 st0 = torch.cuda.memory_stats()
 ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.iters)]
 host = []
