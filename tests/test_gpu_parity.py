@@ -682,6 +682,31 @@ def test_loss_forwards_may_precede_their_backwards(ops):
         assert_close(x.grad.cpu().numpy(), r, rtol=1e-4, atol=1e-9, what="grad vs oracle")
 
 
+def test_loss_step_graph_replays_the_eager_step(ops):
+    """ops.LossStepGraph: forward + backward captured in a CUDA graph give, replay after replay and after new values
+    are written into the captured tensors, exactly the eager loss and gradients."""
+    B, H, W, C = 4, 128, 128, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    cfg = dict(synth.LOSS_CONFIG, num_classes=C)
+    t = dev(synth.targets(B, 12, C, 0))
+    stat = [dev(p).requires_grad_(True) for p in synth.train_preds(B, H, W, C, 1)]
+    cells = [x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] for x in stat]
+    gs = ops.LossStepGraph(stat, t, anc, cfg, input_form="raw", cells=cells)
+    for seed in (1, 2, 2, 3):
+        new = [dev(p) for p in synth.train_preds(B, H, W, C, seed)]
+        with torch.no_grad():
+            for s_, n_ in zip(stat, new):
+                s_.copy_(n_)
+        loss_g = float(gs.replay())
+        eager = [n_.clone().requires_grad_(True) for n_ in new]
+        loss_e, _ = ops.detection_loss(eager, t, anc, cfg, with_metrics=False, input_form="raw")
+        loss_e.backward()
+        assert loss_g == float(loss_e)
+        assert_close(float(gs.combined), loss_g, rtol=1e-6, atol=0, what="combined loss, one rank")
+        for s_, e_ in zip(stat, eager):
+            assert torch.equal(s_.grad, e_.grad)
+
+
 def test_loss_rejects_out_of_range_ids(ops):
     """Image ids outside 0..B-1 and class ids outside 0..C-1: the reference raises IndexError (preds[batch_idx, ...],
     t_cls[range, classes]); the CUDA path drops those rows on the device -- no out-of-bounds access -- and raises
