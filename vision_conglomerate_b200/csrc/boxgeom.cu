@@ -744,6 +744,7 @@ struct LossWs {
     long long cap;
     long long cells[3], cell_off[3], cells_total;
     int nblk_match, nblk_dense;
+    int match_small;      // 256 instead of 1,024 candidates per block of the match kernel
 };
 
 bool loss_valid(const bg_loss_params *p)
@@ -766,6 +767,9 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
     const int sms = num_sms();
     w.cap = 5ll * p->na * p->nt;
     w.nblk_match = (int)((w.cap + MATCH_CHUNK - 1) / MATCH_CHUNK);
+    // small shards: 1,024-candidate blocks would leave most SMs idle (three scales x nblk blocks, six resident per SM)
+    w.match_small = 3ll * w.nblk_match < 4ll * sms ? 1 : 0;
+    if (w.match_small) w.nblk_match = (int)((w.cap + MATCH_CHUNK_SMALL - 1) / MATCH_CHUNK_SMALL);
     if (w.cap < 1) w.cap = 1;
     w.cells_total = 0;
     long long most = 0;
@@ -775,9 +779,9 @@ size_t loss_carve(unsigned char *base, const bg_loss_params *p, LossWs &w)
         w.cells_total += w.cells[s];
         most = w.cells[s] > most ? w.cells[s] : most;
     }
-    {   // blocks of the dense pass per scale: 16 cells per thread on the largest scale, between one and eight CTAs per SM
-        // (small shards: fewer partial sums for the final reduction, no tail of near-empty blocks)
-        long long nb = (most + LOSS_THREADS * 16 - 1) / (LOSS_THREADS * 16);
+    {   // blocks of the dense pass per scale: at least two cells per thread on the largest scale, between one and eight
+        // CTAs per SM (the strided objectness loads need every warp the machine holds to hide their latency)
+        long long nb = (most + LOSS_THREADS * 2 - 1) / (LOSS_THREADS * 2);
         nb = nb < sms ? sms : (nb > sms * 8 ? sms * 8 : nb);
         w.nblk_dense = (int)nb;
     }
@@ -879,13 +883,14 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
     if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
     if (p->nt > 0) {
         const dim3 grid(w.nblk_match, 3);
-        const size_t smem = sizeof(MatchRec) * MATCH_CHUNK + 3 * (size_t)p->C * sizeof(int);
+        const size_t smem = sizeof(MatchRec) * (w.match_small ? MATCH_CHUNK_SMALL : MATCH_CHUNK) + 3 * (size_t)p->C * sizeof(int);
         // CTAs per SM of the match kernel: 6 (40 registers, some spills) hides the scattered-row latency better than 4
         static const int occ = []() { const char *e = getenv("BG_MATCH_OCC"); return (e && e[0] == '4') ? 4 : 6; }();
-#define BG_MATCH_LAUNCH(CT, RAW)                                                                   \
-        do {                                                                                       \
-            if (occ == 4) loss_match_kernel<CT, RAW, 4><<<grid, LOSS_THREADS, smem, st>>>(k);      \
-            else loss_match_kernel<CT, RAW, 6><<<grid, LOSS_THREADS, smem, st>>>(k);               \
+#define BG_MATCH_LAUNCH(CT, RAW)                                                                                   \
+        do {                                                                                                       \
+            if (w.match_small) loss_match_kernel<CT, RAW, 6, MATCH_PER_SMALL><<<grid, LOSS_THREADS, smem, st>>>(k); \
+            else if (occ == 4) loss_match_kernel<CT, RAW, 4, MATCH_PER><<<grid, LOSS_THREADS, smem, st>>>(k);      \
+            else loss_match_kernel<CT, RAW, 6, MATCH_PER><<<grid, LOSS_THREADS, smem, st>>>(k);                    \
         } while (0)
         if (p->C == 80) {
             if (k.raw) BG_MATCH_LAUNCH(80, 1); else BG_MATCH_LAUNCH(80, 0);

@@ -84,16 +84,20 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 
 constexpr int LOSS_THREADS = 256;
 constexpr int ROWS_UNROLL = 10;  // 8 lanes x 10 = one 80-class row per batch of loads
-constexpr int MATCH_PER = 4;     // assignment candidates per thread
+constexpr int MATCH_PER = 4;        // assignment candidates per thread (large problems)
+constexpr int MATCH_PER_SMALL = 1;  // ... when the grid would otherwise not fill the GPU (small shards)
 constexpr int MATCH_CHUNK = LOSS_THREADS * MATCH_PER;
+constexpr int MATCH_CHUNK_SMALL = LOSS_THREADS * MATCH_PER_SMALL;
 
 // per-block staging record of a match (shared memory): what the per-match phases need, so that they run on dense
 // lanes and the evaluation's registers are dead by then
 struct MatchRec { int cell; int cls_a; float bx, by, bw, bh; };  // cls_a = cls | anchor << 16 | local candidate number << 20
 
-template <int CT, int RAW, int OCC>  // CT: compile-time class count (80: no bounds predicates in the class loop); 0 = runtime; OCC: CTAs per SM
+template <int CT, int RAW, int OCC, int PER>  // CT: compile-time class count (80: no bounds predicates in the class loop); 0 = runtime;
+                                              // OCC: CTAs per SM; PER: candidates per thread (a block covers 256*PER)
 __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_match_kernel(Loss3K k)
 {
+    constexpr int MATCH_CHUNK = LOSS_THREADS * PER, MATCH_PER = PER;  // (shadow the namespace-level defaults)
     extern __shared__ __align__(16) unsigned char s_dyn[];   // [MATCH_CHUNK] MatchRec, then [3*C] block-local confusion counters
     __shared__ double s_red[LOSS_THREADS / 32][4];
     __shared__ int s_wcnt[LOSS_THREADS / 32], s_wpre[LOSS_THREADS / 32 + 1];

@@ -899,13 +899,25 @@ class LossStepGraph:
         dev = self.leaves[0].device
         self.combined = None
 
+        aux = torch.cuda.Stream(device=dev) if cells is not None else None
+
         def step():
             for p in self.leaves:
                 p.grad = None
             loss, _, sc = detection_loss(self.inputs, self.targets, anchors3, cfg, with_metrics=False, return_scalars=True,
                                          input_form=input_form)
-            loss.backward()
-            comb = shard.allreduce_loss_terms(sc, cells, cfg, group) if cells is not None else None
+            comb = None
+            if cells is not None:
+                # the terms are final after the forward: pack / all-reduce / combine run on a second stream next to the
+                # backward (a fork and a join in the captured graph), so the collective's latency is hidden
+                cur = torch.cuda.current_stream(dev)
+                aux.wait_stream(cur)
+                with torch.cuda.stream(aux):
+                    comb = shard.allreduce_loss_terms(sc, cells, cfg, group)
+                loss.backward()
+                cur.wait_stream(aux)
+            else:
+                loss.backward()
             return loss, comb
 
         with _on(dev):
