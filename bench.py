@@ -22,8 +22,9 @@ Training block (`train`, `roofline_train`, `cpu_baseline_train`, `e2e_train`, `g
 `ops.detection_loss` forward + backward from the head's logits (the form `train_det.py` gets under
 `dropin.install()`), batch 256 sharded by image over the ranks (256/N each, strong scaling), followed by the one
 tiny all-reduce that turns the per-shard terms into the big-batch loss (`shard.allreduce_loss_terms`, NCCL).
-`train.value` replays that whole step from a CUDA graph (`ops.LossStepGraph`, one launch per step); `train.eager`
-is the same step enqueued from Python every time (enqueue-bound for small shards).
+`train.value` is the split form (the head's three conv outputs read in place) replayed from a CUDA graph
+(`ops.LossStepGraph`, one launch per step); `train.forms` lists every input form (split / raw / decoded), each
+enqueued eagerly from Python (enqueue-bound for small shards) and replayed from a graph.
 
 N > 1 (torchrun): one rank per GPU, barrier + synchronize on both sides, max over ranks.
 """
@@ -525,92 +526,12 @@ def train_leg(args, torch, dist, ops, synth, L, devc, world, rank, barrier):
         samples[form] = per
         return min(per), comb, nl
 
-    ms_raw, comb, nl = timed(logits, "raw", K)
-    comb = float(comb)
-    rel = abs(comb - loss_full) / abs(loss_full)
-    if rel > 1e-6:
-        raise RuntimeError("sharded loss %.9f differs from the big-batch loss %.9f (rel %.2e)" % (comb, loss_full, rel))
-    # forward alone
-    for _ in range(3):
-        ops.detection_loss([x.detach() for x in logits], t_loc, anc, cfg, with_metrics=False, input_form="raw")
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(K):
-        ops.detection_loss([x.detach() for x in logits], t_loc, anc, cfg, with_metrics=False, input_form="raw")
-    b.record()
-    barrier()
-    fwd_ms = a.elapsed_time(b) / K
-    # the dense-gradient fill kernel alone (events around it inside bg_loss_bwd)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 10))]
-    for x, y in evs:
-        x.record()
-        y.record()
-    for x, y in evs:
-        for p in logits:
-            p.grad = None
-        loss, _ = ops.detection_loss(logits, t_loc, anc, cfg, with_metrics=False, input_form="raw")
-        L.bg_profile_events_loss(x.cuda_event, y.cuda_event)
-        loss.backward()
-    barrier()
-    L.bg_profile_events_loss(None, None)
-    fill_ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
-    # counts for the algorithmic bytes
-    with torch.no_grad():
-        _, _, sc = ops.detection_loss([x.detach() for x in logits], t_loc, anc, cfg, with_metrics=False, return_scalars=True,
-                                      input_form="raw")
-    M_loc = float(sc[:, 6].sum())
-    N = synth.candidates_per_image(H, W)
-    D = 5 + C
-    # SURVEY 8d, fwd+bwd per shard: objectness plane + matched rows + targets (fwd); dense gradient + residual + matched rows (bwd)
-    alg = Bl * N * 4 + M_loc * D * 4 + t_loc.shape[0] * 24 + Bl * N * D * 4 + Bl * N * 4 + M_loc * D * 4
-    fill_alg = Bl * N * D * 4 + Bl * N * 4
-    peak, peak_src = _peaks()
-    out["train"] = {
-        "metric": "images/s (target-assign + loss fwd+bwd)", "value": Bf / (ms_raw * 1e-3), "unit": "img/s",
-        "ms_per_step": ms_raw, "n_gpus": world, "scaling": "strong", "global_batch": Bf, "per_gpu_batch": Bl,
-        "gt_per_img": G, "input_form": "raw (head logits; training-mode decode fused; what train_det.py gets under dropin.install())",
-        "forward_ms": fwd_ms, "launches_per_step": nl // max(K, 1), "region_ms_per_step": samples.get("raw"),
-        "timing": "best of 3 timed regions of %d steps each (all listed in region_ms_per_step)" % K,
-        "collective": "one all-reduce(SUM) of 15 float64 per step (shard.allreduce_loss_terms, %s)" % ("NCCL" if world > 1 else "world 1: skipped"),
-        "loss_check": {"big_batch_loss": loss_full, "sharded_allreduced_loss": comb, "rel_err": rel, "tol": 1e-6},
-        "workload": "configs[2]: batch %d at %dx%d, %d gt/img, CIoU + objectness/class BCE, image-sharded %d per GPU"
-                    % (Bf, H, W, G, Bl),
-    }
-    out["launches_in_timed_region"] = int(nl)
-    out["roofline_train"] = {
-        "bound": "hbm", "kernel": "whole step (fwd+bwd, %d launches); dominant kernel loss_bwd_stream_kernel" % (nl // max(K, 1)),
-        "achieved": alg / (ms_raw * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms_raw * 1e-3) / 1e9 / peak,
-        "algorithmic_bytes_per_step": int(alg), "algorithmic_bytes_per_image": alg / Bl, "peak_source": peak_src,
-        "traffic": _ncu_traffic("train_step"),
-        "dominant_kernel": {"name": "loss_bwd_stream_kernel", "kernel_ms": fill_ms, "algorithmic_bytes_per_launch": int(fill_alg),
-                            "achieved": fill_alg / (fill_ms * 1e-3) / 1e9, "frac": fill_alg / (fill_ms * 1e-3) / 1e9 / peak,
-                            "traffic": _ncu_traffic("loss_bwd_stream_kernel")},
-        "survey_10.1MB_per_image_frac": Bl * 10.1e6 / (ms_raw * 1e-3) / 1e9 / peak,
-    }
-    # the other input forms on the same shard
-    forms = {}
-    try:
-        dec = [ops.decode_scale(x.detach(), a, (H, W), False).requires_grad_(True) for x, a in zip(logits, anc)]
-        ms_dec, _, _ = timed(dec, "decoded", K)
-        forms["decoded"] = {"ms_per_step": ms_dec, "img_per_s": Bf / (ms_dec * 1e-3),
-                            "what": "the reference's contract: tensors already decoded by _get_scale_pred"}
-        del dec
-        tri = [tuple(y.contiguous().requires_grad_(True) for y in (x.detach()[..., 0], x.detach()[..., 1:1 + C], x.detach()[..., 1 + C:]))
-               for x in logits]
-        ms_sp, comb_s, nl_s = timed(tri, "split", K)
-        forms["split"] = {"ms_per_step": ms_sp, "img_per_s": Bf / (ms_sp * 1e-3), "launches_per_step": nl_s // max(K, 1),
-                          "hbm_frac": alg / (ms_sp * 1e-3) / 1e9 / peak, "loss_rel_err_vs_big_batch": abs(float(comb_s) - loss_full) / abs(loss_full),
-                          "what": "SURVEY 8 f3: the head's three conv outputs (conf / cls / bbox) before EffiDecHead concatenates them"}
-        del tri
-    except Exception as ex:  # noqa: BLE001
-        forms["error"] = repr(ex)
-    out["train"]["other_input_forms"] = forms
-    # ---- the same step captured in a CUDA graph (ops.LossStepGraph: fwd + bwd + pack + NCCL all-reduce + combine in one
-    # launch): small shards are enqueue-bound when run eagerly, the replay is bound by the kernels and the collective
-    try:
-        gs = ops.LossStepGraph([x.detach().clone().requires_grad_(True) for x in logits], t_loc, anc, cfg, input_form="raw",
-                               cells=cells)
+    def graphed(form_inputs, form):
+        """The same step captured in a CUDA graph (ops.LossStepGraph: fwd + bwd + pack + NCCL all-reduce + combine in one
+        launch): small shards are enqueue-bound when run eagerly, the replay is bound by the kernels and the collective."""
+        clones = [tuple(q.detach().clone().requires_grad_(True) for q in p) if isinstance(p, tuple)
+                  else p.detach().clone().requires_grad_(True) for p in form_inputs]
+        gs = ops.LossStepGraph(clones, t_loc, anc, cfg, input_form=form, cells=cells)
         for _ in range(3):
             gs.replay()
         per = []
@@ -626,45 +547,140 @@ def train_leg(args, torch, dist, ops, synth, L, devc, world, rank, barrier):
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             per.append(float(tt.item()) / K)
-        graph_ms = min(per)
         g_rel = abs(float(gs.combined) - loss_full) / abs(loss_full)
         if g_rel > 1e-6:
-            raise RuntimeError("graphed sharded loss differs from the big-batch loss (rel %.2e)" % g_rel)
-        eager = {k: out["train"][k] for k in ("value", "ms_per_step", "region_ms_per_step", "launches_per_step", "timing")}
-        out["train"]["eager"] = dict(eager, hbm_frac=out["roofline_train"]["frac"],
-                                     what="the same step enqueued from Python every time (autograd.Function, 7 launches + all-reduce)")
-        out["train"].update({"value": Bf / (graph_ms * 1e-3), "ms_per_step": graph_ms, "region_ms_per_step": per,
-                             "mode": "cuda_graph: ops.LossStepGraph replays fwd + bwd + loss-term pack + all-reduce + combine "
-                                     "captured once (fixed shapes and addresses); the eager numbers are in train.eager",
-                             "timing": "best of 3 timed regions of %d replays each" % K})
-        out["train"]["loss_check"]["graphed_allreduced_loss"] = float(gs.combined)
-        out["train"]["loss_check"]["graphed_rel_err"] = g_rel
-        rt = out["roofline_train"]
-        rt["achieved"] = alg / (graph_ms * 1e-3) / 1e9
-        rt["frac"] = rt["achieved"] / peak
-        rt["survey_10.1MB_per_image_frac"] = Bl * 10.1e6 / (graph_ms * 1e-3) / 1e9 / peak
-        rt["kernel"] = "whole step (fwd+bwd, graph replay); dominant kernel loss_bwd_stream_kernel"
-        del gs
-    except Exception as ex:  # noqa: BLE001
-        out["train"]["mode"] = "eager (graph capture failed: %r)" % (ex,)
-    # ---- e2e_train: pinned host logits -> H2D -> fwd+bwd -> D2H of the loss, every step
+            raise RuntimeError("graphed sharded loss (%s) differs from the big-batch loss (rel %.2e)" % (form, g_rel))
+        return min(per), per, float(gs.combined), g_rel
+
+    def fill_kernel_ms(form_inputs, form):
+        """The dense-gradient fill alone (events around it inside bg_loss_bwd, bg_profile_events_loss)."""
+        leaves = [q for p in form_inputs for q in (p if isinstance(p, tuple) else (p,))]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(K, 10))]
+        for x, y in evs:
+            x.record()
+            y.record()
+        for x, y in evs:
+            for p in leaves:
+                p.grad = None
+            loss, _ = ops.detection_loss(form_inputs, t_loc, anc, cfg, with_metrics=False, input_form=form)
+            L.bg_profile_events_loss(x.cuda_event, y.cuda_event)
+            loss.backward()
+        barrier()
+        L.bg_profile_events_loss(None, None)
+        return sum(x.elapsed_time(y) for x, y in evs) / len(evs)
+
+    # counts for the algorithmic bytes
+    with torch.no_grad():
+        _, _, sc = ops.detection_loss([x.detach() for x in logits], t_loc, anc, cfg, with_metrics=False, return_scalars=True,
+                                      input_form="raw")
+    M_loc = float(sc[:, 6].sum())
+    N = synth.candidates_per_image(H, W)
+    D = 5 + C
+    # SURVEY 8d, fwd+bwd per shard: objectness plane + matched rows + targets (fwd); dense gradient + residual + matched rows (bwd)
+    alg = Bl * N * 4 + M_loc * D * 4 + t_loc.shape[0] * 24 + Bl * N * D * 4 + Bl * N * 4 + M_loc * D * 4
+    fill_alg = Bl * N * D * 4 + Bl * N * 4
+    peak, peak_src = _peaks()
+
+    # the three input forms on the same shard: eager (3 regions of K steps) and graph replay (3 regions of K replays)
+    what = {"split": "SURVEY 8 f3: the head's three conv outputs (conf / cls / bbox) read in place -- what train_det.py gets under "
+                     "dropin.install(EffiDecHead=...) (zero-copy with a channels-last model)",
+            "raw": "the head's interleaved rows (logits), training-mode decode fused -- dropin.install() without the head patch",
+            "decoded": "the reference's contract: tensors already decoded by _get_scale_pred"}
+    inputs = {"raw": logits,
+              "split": [tuple(y.contiguous().requires_grad_(True) for y in (x.detach()[..., 0], x.detach()[..., 1:1 + C], x.detach()[..., 1 + C:]))
+                        for x in logits],
+              "decoded": [ops.decode_scale(x.detach(), a_, (H, W), False).requires_grad_(True) for x, a_ in zip(logits, anc)]}
+    forms, nl_by = {}, {}
+    for form in ("split", "raw", "decoded"):
+        ent = {"what": what[form]}
+        try:
+            ms_e, comb, nl = timed(inputs[form], form, K)
+            nl_by[form] = nl
+            rel = abs(float(comb) - loss_full) / abs(loss_full) if form != "decoded" else None
+            if rel is not None and rel > 1e-6:
+                raise RuntimeError("sharded loss (%s) %.9f differs from the big-batch loss %.9f (rel %.2e)" % (form, float(comb), loss_full, rel))
+            ent["eager"] = {"ms_per_step": ms_e, "img_per_s": Bf / (ms_e * 1e-3), "hbm_frac": alg / (ms_e * 1e-3) / 1e9 / peak,
+                            "region_ms_per_step": samples[form], "launches_per_step": nl // max(K, 1),
+                            "sharded_allreduced_loss": float(comb), "loss_rel_err_vs_big_batch": rel}
+        except Exception as ex:  # noqa: BLE001
+            ent["eager"] = {"error": repr(ex)}
+        try:
+            ms_g, per_g, comb_g, rel_g = graphed(inputs[form], form) if form != "decoded" else (None, None, None, None)
+            if ms_g is not None:
+                ent["graph"] = {"ms_per_step": ms_g, "img_per_s": Bf / (ms_g * 1e-3), "hbm_frac": alg / (ms_g * 1e-3) / 1e9 / peak,
+                                "region_ms_per_step": per_g, "sharded_allreduced_loss": comb_g, "loss_rel_err_vs_big_batch": rel_g}
+        except Exception as ex:  # noqa: BLE001
+            ent["graph"] = {"error": repr(ex)}
+        forms[form] = ent
+    primary = "split"
+    best = forms[primary].get("graph") if "ms_per_step" in forms[primary].get("graph", {}) else forms[primary]["eager"]
+    mode = "cuda_graph" if best is forms[primary].get("graph") else "eager"
+    ms_best = best["ms_per_step"]
+    # forward alone (eager, primary form)
+    detached = [tuple(q.detach() for q in p) for p in inputs[primary]]
+    for _ in range(3):
+        ops.detection_loss(detached, t_loc, anc, cfg, with_metrics=False, input_form=primary)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        ops.detection_loss(detached, t_loc, anc, cfg, with_metrics=False, input_form=primary)
+    b.record()
+    barrier()
+    fwd_ms = a.elapsed_time(b) / K
+    fill_split, fill_raw = fill_kernel_ms(inputs["split"], "split"), fill_kernel_ms(inputs["raw"], "raw")
+    out["train"] = {
+        "metric": "images/s (target-assign + loss fwd+bwd)", "value": Bf / (ms_best * 1e-3), "unit": "img/s",
+        "ms_per_step": ms_best, "n_gpus": world, "scaling": "strong", "global_batch": Bf, "per_gpu_batch": Bl,
+        "gt_per_img": G, "input_form": primary + ": " + what[primary],
+        "mode": ("cuda_graph: ops.LossStepGraph replays fwd + bwd + loss-term pack + all-reduce + combine captured once (fixed "
+                 "shapes and addresses); the eager numbers of every form are in train.forms") if mode == "cuda_graph" else "eager",
+        "timing": "best of 3 timed regions of %d steps each (all listed in region_ms_per_step)" % K,
+        "region_ms_per_step": best["region_ms_per_step"], "forward_ms_eager": fwd_ms,
+        "launches_per_step_eager": nl_by.get(primary, 0) // max(K, 1),
+        "collective": "one all-reduce(SUM) of 15 float64 per step (shard.allreduce_loss_terms, %s)" % ("NCCL" if world > 1 else "world 1: skipped"),
+        "loss_check": {"big_batch_loss": loss_full, "sharded_allreduced_loss": best["sharded_allreduced_loss"],
+                       "rel_err": best["loss_rel_err_vs_big_batch"], "tol": 1e-6},
+        "workload": "configs[2]: batch %d at %dx%d, %d gt/img, CIoU + objectness/class BCE, image-sharded %d per GPU"
+                    % (Bf, H, W, G, Bl),
+        "forms": forms,
+    }
+    out["launches_in_timed_region"] = int(sum(nl_by.values()))
+    out["roofline_train"] = {
+        "bound": "hbm", "kernel": "whole step (fwd+bwd, %s, %s form); dominant part: the dense-gradient fill" % (mode, primary),
+        "achieved": alg / (ms_best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms_best * 1e-3) / 1e9 / peak,
+        "algorithmic_bytes_per_step": int(alg), "algorithmic_bytes_per_image": alg / Bl, "peak_source": peak_src,
+        "traffic": _ncu_traffic("train_step_split"),
+        "dominant_kernel": {"name": "cudaMemsetAsync of the class / box gradient planes + loss_bwd_conf_kernel (split form)",
+                            "kernel_ms": fill_split, "algorithmic_bytes_per_launch": int(fill_alg),
+                            "achieved": fill_alg / (fill_split * 1e-3) / 1e9, "frac": fill_alg / (fill_split * 1e-3) / 1e9 / peak},
+        "interleaved_fill_kernel": {"name": "l2_pin_kernel + loss_bwd_stream_kernel (raw / decoded forms)", "kernel_ms": fill_raw,
+                                    "algorithmic_bytes_per_launch": int(fill_alg), "achieved": fill_alg / (fill_raw * 1e-3) / 1e9,
+                                    "frac": fill_alg / (fill_raw * 1e-3) / 1e9 / peak, "traffic": _ncu_traffic("loss_bwd_stream_kernel")},
+        "survey_10.1MB_per_image_frac": Bl * 10.1e6 / (ms_best * 1e-3) / 1e9 / peak,
+        "interleaved_forms_frac": {f: forms[f].get("graph", forms[f]["eager"]).get("hbm_frac") for f in ("raw", "decoded")},
+    }
+    del inputs["decoded"]
+    # ---- e2e_train: pinned host conv outputs -> H2D -> fwd+bwd -> D2H of the loss, every step (primary form)
     try:
-        host = [x.detach().cpu().pin_memory() for x in logits]
+        host = [tuple(q.detach().cpu().pin_memory() for q in p) for p in inputs[primary]]
         th = t_loc.cpu().pin_memory()
-        stage = [torch.empty_like(x).requires_grad_(True) for x in logits]
+        stage = [tuple(torch.empty_like(q).requires_grad_(True) for q in p) for p in inputs[primary]]
         tdev = torch.empty_like(t_loc)
         Ke = max(2, min(K, 5))
 
         def e2e_step():
             with torch.no_grad():
-                for sbuf, h in zip(stage, host):
-                    sbuf.copy_(h, non_blocking=True)
+                for sp, hp in zip(stage, host):
+                    for sbuf, h in zip(sp, hp):
+                        sbuf.copy_(h, non_blocking=True)
                 tdev.copy_(th, non_blocking=True)
-            for p in stage:
-                p.grad = None
-            loss, _ = ops.detection_loss(stage, tdev, anc, cfg, with_metrics=False, input_form="raw")
+            for sp in stage:
+                for q in sp:
+                    q.grad = None
+            loss, _ = ops.detection_loss(stage, tdev, anc, cfg, with_metrics=False, input_form=primary)
             loss.backward()
-            return float(loss)         # D2H of the step's result
+            return float(loss.detach())         # D2H of the step's result
 
         e2e_step()
         barrier()
@@ -678,11 +694,11 @@ def train_leg(args, torch, dist, ops, synth, L, devc, world, rank, barrier):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e = float(t.item()) / Ke
-        h2d = sum(x.numel() * 4 for x in host) + th.numel() * 4
+        h2d = sum(q.numel() * 4 for p in host for q in p) + th.numel() * 4
         out["e2e_train"] = {"value": Bf / (ms_e * 1e-3), "unit": "img/s", "ms_per_step": ms_e, "h2d_bytes_per_step": int(h2d),
                             "d2h_bytes_per_step": 4, "steps": Ke,
-                            "bound": "host link (%.1f GB/s H2D per GPU); under train_det.py the logits are produced on the "
-                                     "device by the head, so this is the worst case" % (h2d / (ms_e * 1e-3) / 1e9)}
+                            "bound": "host link (%.1f GB/s H2D per GPU); under train_det.py the head's outputs are produced on the "
+                                     "device, so this is the worst case" % (h2d / (ms_e * 1e-3) / 1e9)}
     except Exception as ex:  # noqa: BLE001
         out["e2e_train"] = {"error": repr(ex)}
     return out
