@@ -266,6 +266,25 @@ __device__ __forceinline__ float ld_stride_f32(const float *p)
 }
 
 // dense objectness BCE over every cell
+// One cell of the dense pass: the objectness BCE against the CIoU of the cell's last match, the residual for the backward.
+__device__ __forceinline__ float dense_cell(const LossScale &S, float x, int head_m, double &a0, double &a1, double &a2)
+{
+    int w = -1, wk = -1;  // "last match wins": the highest candidate number in the cell's list
+    for (int j = head_m; j >= 0; j = S.next[j]) { const int kj = S.key[j]; if (kj > wk) { wk = kj; w = j; } }
+    const float t = w >= 0 ? S.ciou[w] : 0.0f;
+    // bce(x, t) = (1 - t) x - log_sigmoid(x) = max(x, 0) - t x + log(1 + e), e = exp(-|x|), and
+    // sigmoid(x) = (x >= 0 ? 1 : e) / (1 + e): one fast exponential, one fast logarithm and one fast division
+    // per cell (|error| < 3e-7 absolute on terms of order one -- the mean over millions of cells and the
+    // gradient residual stay far inside rtol 1e-5 / 1e-4); the accurate forms made this kernel issue-bound
+    // on the contiguous (split) objectness plane
+    const float e = __expf(-fabsf(x));
+    const float l = e < 1e-4f ? e * (1.0f - 0.5f * e) : __logf(1.0f + e);
+    const float sg = __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
+    a0 += (double)(fmaxf(x, 0.0f) - t * x + l);
+    if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
+    return __fsub_rn(sg, t);
+}
+
 template <int OCC>  // CTAs per SM
 __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_dense_kernel(Loss3K k)
 {
@@ -273,50 +292,68 @@ __global__ void __launch_bounds__(LOSS_THREADS, OCC) loss_dense_kernel(Loss3K k)
     const LossScale &S = k.s[blockIdx.y];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
-    // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
-    constexpr int DENSE_PER = 4;
     const long long stride = (long long)gridDim.x * LOSS_THREADS;
     const int so = S.v.so;
     const long long first = (long long)blockIdx.x * LOSS_THREADS + threadIdx.x;
-    // the logits do not depend on the upstream kernels: the first batch of loads is issued before the wait
-    float xs[DENSE_PER];
-#pragma unroll
-    for (int u = 0; u < DENSE_PER; ++u) {
-        const long long c = first + u * stride;
-        xs[u] = 0.f;
-        if (c < S.cells) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
-    }
-    pdl_wait();
-    for (long long c0 = first; c0 < S.cells; c0 += DENSE_PER * stride) {
-        int ws[DENSE_PER];
-#pragma unroll
-        for (int u = 0; u < DENSE_PER; ++u) {
-            const long long c = c0 + u * stride;
-            ws[u] = -1;
-            if (c < S.cells) {
-                if (c0 != first) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
-                ws[u] = S.head[c] - 1;
+    if (so == 1 && (((unsigned long long)S.head | (unsigned long long)S.gobj | (unsigned long long)S.v.obj) & 15) == 0) {
+        // contiguous objectness plane (split form): four consecutive cells per thread, 16-byte loads and stores
+        const long long n4 = S.cells >> 2;
+        const float4 *x4p = reinterpret_cast<const float4 *>(S.v.obj);
+        const int4 *h4p = reinterpret_cast<const int4 *>(S.head);
+        float4 *g4p = reinterpret_cast<float4 *>(S.gobj);
+        float4 xa = make_float4(0.f, 0.f, 0.f, 0.f), xb = xa;
+        if (first < n4) xa = __ldg(x4p + first);                     // the logits do not depend on the upstream kernels
+        if (first + stride < n4) xb = __ldg(x4p + first + stride);
+        pdl_wait();
+        for (long long g = first; g < n4; g += 2 * stride) {
+            const bool two = g + stride < n4;
+            if (g != first) { xa = __ldg(x4p + g); if (two) xb = __ldg(x4p + g + stride); }
+            const int4 ha = h4p[g];
+            int4 hb = make_int4(0, 0, 0, 0);
+            if (two) hb = h4p[g + stride];
+            float4 r;
+            r.x = dense_cell(S, xa.x, ha.x - 1, a0, a1, a2); r.y = dense_cell(S, xa.y, ha.y - 1, a0, a1, a2);
+            r.z = dense_cell(S, xa.z, ha.z - 1, a0, a1, a2); r.w = dense_cell(S, xa.w, ha.w - 1, a0, a1, a2);
+            g4p[g] = r;
+            if (two) {
+                r.x = dense_cell(S, xb.x, hb.x - 1, a0, a1, a2); r.y = dense_cell(S, xb.y, hb.y - 1, a0, a1, a2);
+                r.z = dense_cell(S, xb.z, hb.z - 1, a0, a1, a2); r.w = dense_cell(S, xb.w, hb.w - 1, a0, a1, a2);
+                g4p[g + stride] = r;
             }
         }
+        if (blockIdx.x == 0 && threadIdx.x < (int)(S.cells & 3)) {   // cells beyond the last group of four
+            const long long c = (n4 << 2) + threadIdx.x;
+            S.gobj[c] = dense_cell(S, __ldg(S.v.obj + c), S.head[c] - 1, a0, a1, a2);
+        }
+    } else {
+        // four cells per thread and pass, their strided loads in flight together (same per-thread order of the sums)
+        constexpr int DENSE_PER = 4;
+        // the logits do not depend on the upstream kernels: the first batch of loads is issued before the wait
+        float xs[DENSE_PER];
 #pragma unroll
         for (int u = 0; u < DENSE_PER; ++u) {
-            const long long c = c0 + u * stride;
-            if (c >= S.cells) break;
-            const float x = xs[u];
-            int w = -1, wk = -1;  // "last match wins": the highest candidate number in the cell's list
-            for (int j = ws[u]; j >= 0; j = S.next[j]) { const int kj = S.key[j]; if (kj > wk) { wk = kj; w = j; } }
-            const float t = w >= 0 ? S.ciou[w] : 0.0f;
-            // bce(x, t) = (1 - t) x - log_sigmoid(x) = max(x, 0) - t x + log(1 + e), e = exp(-|x|), and
-            // sigmoid(x) = (x >= 0 ? 1 : e) / (1 + e): one fast exponential, one fast logarithm and one fast division
-            // per cell (|error| < 3e-7 absolute on terms of order one -- the mean over millions of cells and the
-            // gradient residual stay far inside rtol 1e-5 / 1e-4); the accurate forms made this kernel issue-bound
-            // on the contiguous (split) objectness plane
-            const float e = __expf(-fabsf(x));
-            const float l = e < 1e-4f ? e * (1.0f - 0.5f * e) : __logf(1.0f + e);
-            const float sg = __fdividef(x >= 0.0f ? 1.0f : e, 1.0f + e);
-            a0 += (double)(fmaxf(x, 0.0f) - t * x + l);
-            if (t == 0.0f) { a1 += (double)sg; a2 += 1.0; }
-            S.gobj[c] = __fsub_rn(sg, t);
+            const long long c = first + u * stride;
+            xs[u] = 0.f;
+            if (c < S.cells) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
+        }
+        pdl_wait();
+        for (long long c0 = first; c0 < S.cells; c0 += DENSE_PER * stride) {
+            int ws[DENSE_PER];
+#pragma unroll
+            for (int u = 0; u < DENSE_PER; ++u) {
+                const long long c = c0 + u * stride;
+                ws[u] = -1;
+                if (c < S.cells) {
+                    if (c0 != first) xs[u] = so == 1 ? __ldg(S.v.obj + c) : ld_stride_f32(S.v.obj + c * so);
+                    ws[u] = S.head[c] - 1;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < DENSE_PER; ++u) {
+                const long long c = c0 + u * stride;
+                if (c >= S.cells) break;
+                S.gobj[c] = dense_cell(S, xs[u], ws[u], a0, a1, a2);
+            }
         }
     }
     pdl_launch_dependents();
