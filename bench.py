@@ -645,7 +645,10 @@ def train_leg(args, torch, dist, ops, synth, L, devc, world, rank, barrier):
                     % (Bf, H, W, G, Bl),
         "forms": forms,
     }
-    out["launches_in_timed_region"] = int(sum(nl_by.values()))
+    # kernels of ours inside the timed regions of this block: the last eager region of every form (host-side counter) plus
+    # the graph replays (3 regions x K replays x the launches one step holds; replays do not pass through the host counter)
+    replayed = sum(3 * K * (nl_by.get(f, 0) // max(K, 1)) for f in ("split", "raw") if "ms_per_step" in forms[f].get("graph", {}))
+    out["launches_in_timed_region"] = int(sum(nl_by.values()) + replayed)
     out["roofline_train"] = {
         "bound": "hbm", "kernel": "whole step (fwd+bwd, %s, %s form); dominant part: the dense-gradient fill" % (mode, primary),
         "achieved": alg / (ms_best * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms_best * 1e-3) / 1e9 / peak,
