@@ -126,6 +126,49 @@ def test_train_step_patched_equals_unpatched(ns):
         assert tot_err / tot_den < 1e-4 and worst < 5e-4, worst_name
 
 
+def test_split_head_is_zero_copy_under_channels_last(ns):
+    """With the model in channels-last memory format the head's `permute(0,2,3,1).reshape(...)` views of its three conv
+    outputs (modules/common.py:912-918) are contiguous: the fused loss reads them where cuDNN wrote them (no copy in
+    `_req`) -- and loss / gradients still equal the unpatched run of the same channels-last model."""
+    from vision_conglomerate_b200 import dropin, ops
+    B, S, C = 2, 256, 80
+    model = _model(ns, C).train().to(memory_format=torch.channels_last)
+    loss_mod = ns.DetectionLoss(model, **synth.LOSS_CONFIG)
+    g = torch.Generator().manual_seed(9)
+    imgs = torch.rand(B, 3, S, S, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    t = torch.tensor([[b, 3 + b, 0.3 + 0.2 * b, 0.4, 0.15, 0.35] for b in range(B)], dtype=torch.float32).cuda()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        preds = model(imgs)
+        loss, _ = loss_mod(preds, t)
+        loss.backward()
+        return float(loss), _param_grads(model)
+
+    loss_u, grads_u = step()
+    seen = []
+    real = ops.detection_loss
+
+    def spy(preds3, *a, **k):
+        if k.get("input_form") == "split":
+            seen.append(all(x.is_contiguous() for tri in preds3 for x in tri))
+        return real(preds3, *a, **k)
+
+    dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, EffiDecHead=ns.EffiDecHead)
+    ops.detection_loss = spy
+    try:
+        loss_p, grads_p = step()
+    finally:
+        ops.detection_loss = real
+        dropin.uninstall()
+    assert seen == [True], seen          # the pieces reached the loss contiguous: nothing was copied
+    assert_close(loss_p, loss_u, rtol=1e-5, atol=0, what="loss")
+    err = sum(float((grads_p[n].double() - grads_u[n].double()).pow(2).sum()) for n in grads_u) ** 0.5
+    den = sum(float(grads_u[n].double().pow(2).sum()) for n in grads_u) ** 0.5
+    print("channels-last split head: loss %.7f vs %.7f, global relative L2 error of the parameter gradients %.2e" % (loss_p, loss_u, err / den))
+    assert err / den < 1e-4
+
+
 def test_inference_patched_equals_unpatched_and_fused(ns):
     """inference_det.py's own flow (model(x, inference=True, og_size) -> post_process_preds) on the real classes:
     unpatched (ATen decode + torchvision-CUDA batched_nms), patched with install() only (zero edits: CUDA decode,
