@@ -886,18 +886,29 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
         const size_t smem = sizeof(MatchRec) * (w.match_small ? MATCH_CHUNK_SMALL : MATCH_CHUNK) + 3 * (size_t)p->C * sizeof(int);
         // CTAs per SM of the match kernel: 6 (40 registers, some spills) hides the scattered-row latency better than 4
         static const int occ = []() { const char *e = getenv("BG_MATCH_OCC"); return (e && e[0] == '4') ? 4 : 6; }();
-#define BG_MATCH_LAUNCH(CT, RAW)                                                                                   \
-        do {                                                                                                       \
-            if (w.match_small) loss_match_kernel<CT, RAW, 6, MATCH_PER_SMALL><<<grid, LOSS_THREADS, smem, st>>>(k); \
-            else if (occ == 4) loss_match_kernel<CT, RAW, 4, MATCH_PER><<<grid, LOSS_THREADS, smem, st>>>(k);      \
-            else loss_match_kernel<CT, RAW, 6, MATCH_PER><<<grid, LOSS_THREADS, smem, st>>>(k);                    \
+        // split form with C % 4 == 0: the class rows are 16-byte aligned -- vector loads, four lanes per match
+        static const bool match_vec_env = []() { const char *e = getenv("BG_MATCH_VEC"); return !(e && e[0] == '0'); }();
+        const bool vec = match_vec_env && p->input_form == BG_LOSS_RAW_SPLIT && (p->C & 3) == 0;
+#define BG_MATCH_LAUNCH(CT, RAW)                                                                                       \
+        do {                                                                                                           \
+            if (w.match_small) loss_match_kernel<CT, RAW, 6, MATCH_PER_SMALL, 0><<<grid, LOSS_THREADS, smem, st>>>(k);  \
+            else if (occ == 4) loss_match_kernel<CT, RAW, 4, MATCH_PER, 0><<<grid, LOSS_THREADS, smem, st>>>(k);       \
+            else loss_match_kernel<CT, RAW, 6, MATCH_PER, 0><<<grid, LOSS_THREADS, smem, st>>>(k);                     \
         } while (0)
-        if (p->C == 80) {
+#define BG_MATCH_LAUNCH_VEC(CT)                                                                                        \
+        do {                                                                                                           \
+            if (w.match_small) loss_match_kernel<CT, 1, 6, MATCH_PER_SMALL, 1><<<grid, LOSS_THREADS, smem, st>>>(k);    \
+            else loss_match_kernel<CT, 1, 6, MATCH_PER, 1><<<grid, LOSS_THREADS, smem, st>>>(k);                       \
+        } while (0)
+        if (vec) {
+            if (p->C == 80) BG_MATCH_LAUNCH_VEC(80); else BG_MATCH_LAUNCH_VEC(0);
+        } else if (p->C == 80) {
             if (k.raw) BG_MATCH_LAUNCH(80, 1); else BG_MATCH_LAUNCH(80, 0);
         } else {
             if (k.raw) BG_MATCH_LAUNCH(0, 1); else BG_MATCH_LAUNCH(0, 0);
         }
 #undef BG_MATCH_LAUNCH
+#undef BG_MATCH_LAUNCH_VEC
         BG_LAUNCH_CHECK();
     }
     static const int dense_occ = []() { const char *e = getenv("BG_DENSE_OCC"); return (e && e[0] == '8') ? 8 : 5; }();
@@ -969,6 +980,11 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
     }
     if (prof) cudaEventRecord(prof_b, st);
     if (p->nt == 0) return BG_OK;
+    static const bool rows_vec = []() { const char *e = getenv("BG_ROWS_VEC"); return !(e && e[0] == '0'); }();
+    if (rows_vec && p->input_form == BG_LOSS_RAW_SPLIT && (k.C & 3) == 0 && k.C <= 128) {  // 16-byte rows: four lanes per match
+        if (k.C == 80) return launch_after(loss_bwd_rows_vec_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
+        return launch_after(loss_bwd_rows_vec_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
+    }
     if (k.C == 80) return launch_after(loss_bwd_rows_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
     return launch_after(loss_bwd_rows_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
 }
