@@ -253,10 +253,18 @@ int bg_loss_fwd(const bg_head_ptrs in[3] /*host*/, const float *targets, const b
                 size_t workspace_bytes, void *stream);
 /*   grads[3]: d(grad_out * loss)/d in, same form and shapes as `in`, every element written (BG_LOSS_RAW*: the
  *   gradient with respect to the logits).  The upstream gradient is read from device memory (grad_out_dev [1] f32)
- *   when non-NULL -- no host sync in loss.backward() -- else grad_out_host is used. */
+ *   when non-NULL -- no host sync in loss.backward() -- else grad_out_host is used.
+ *   flags: BG_LOSS_BWD_PRECLEARED (split form) = the class / box planes of `grads` are already zero (see
+ *   bg_loss_clear_grads); the call then only writes the objectness plane and the matched rows. */
+#define BG_LOSS_BWD_PRECLEARED 1
 int bg_loss_bwd(const bg_head_ptrs in[3] /*host*/, const bg_loss_params *p /*host*/, const float *grad_out_dev,
-                float grad_out_host, const bg_head_grads grads[3] /*host*/, void *workspace, size_t workspace_bytes,
-                void *stream);
+                float grad_out_host, const bg_head_grads grads[3] /*host*/, int32_t flags, void *workspace,
+                size_t workspace_bytes, void *stream);
+/* BG_LOSS_RAW_SPLIT: clears the class / box planes of the gradient tensors (adjacent planes with one cudaMemsetAsync).
+ * The 2 GB of zeros do not depend on the forward: a caller that allocates the gradients up front can issue this on a
+ * second stream NEXT TO bg_loss_fwd (whose kernels are latency- and issue-bound and leave most of the bandwidth free)
+ * and pass BG_LOSS_BWD_PRECLEARED to bg_loss_bwd after joining the streams. */
+int bg_loss_clear_grads(const bg_loss_params *p /*host*/, const bg_head_grads grads[3] /*host*/, void *stream);
 
 /* Image-sharded training: per-shard sums that add up over the shards, and the big-batch loss from the
  * summed terms.  pack15 [3,5] f64 per scale = {lbox*M, lconf*cells, lcls*M*C, M, cells}; the caller all-reduces (SUM)

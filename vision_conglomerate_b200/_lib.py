@@ -27,7 +27,7 @@ SYMBOLS = (
     "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd",
     "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
-    "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_pack", "bg_loss_combine",
+    "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine",
     "bg_ratio_metrics",
 )
 
@@ -67,6 +67,7 @@ class LossParams(C.Structure):
 
 
 LOSS_DECODED, LOSS_RAW, LOSS_RAW_SPLIT = 0, 1, 2
+LOSS_BWD_PRECLEARED = 1
 
 
 class HeadPtrs(C.Structure):
@@ -140,12 +141,13 @@ def lib() -> C.CDLL:
     L.bg_loss_workspace_bytes.argtypes = [C.POINTER(LossParams)]
     L.bg_loss_workspace_bytes.restype = sz
     L.bg_loss_fwd.argtypes = [C.POINTER(HeadPtrs), vp, C.POINTER(LossParams), vp, vp, vp, vp, vp, sz, vp]
-    L.bg_loss_bwd.argtypes = [C.POINTER(HeadPtrs), C.POINTER(LossParams), vp, f32, C.POINTER(HeadPtrs), vp, sz, vp]
+    L.bg_loss_bwd.argtypes = [C.POINTER(HeadPtrs), C.POINTER(LossParams), vp, f32, C.POINTER(HeadPtrs), i32, vp, sz, vp]
+    L.bg_loss_clear_grads.argtypes = [C.POINTER(LossParams), C.POINTER(HeadPtrs), vp]
     L.bg_loss_pack.argtypes = [vp, C.POINTER(i64), i32, vp, vp]
     L.bg_loss_combine.argtypes = [vp, C.POINTER(LossParams), vp, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
-                 "bg_loss_fwd", "bg_loss_bwd", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics"):
+                 "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

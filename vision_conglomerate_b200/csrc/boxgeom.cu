@@ -271,7 +271,7 @@ const char *bg_strerror(int code)
     }
 }
 
-int bg_version(void) { return 200; }  // 200: bg_loss_* take the input form (decoded / raw / raw split) and per-scale pointer triples
+int bg_version(void) { return 201; }  // 200: bg_loss_* take the input form (decoded / raw / raw split) and per-scale pointer triples
 
 uint64_t bg_launch_count(void) { return g_launches; }
 void bg_profile_events(void *start, void *stop) { g_prof_start = (cudaEvent_t)start; g_prof_stop = (cudaEvent_t)stop; }
@@ -921,8 +921,39 @@ int bg_loss_fwd(const bg_head_ptrs in[3], const float *targets, const bg_loss_pa
     return BG_OK;
 }
 
+// split form: the class / box planes of the gradient are zeros except for the matched rows: cleared by memset
+// (adjacent planes by one call)
+static int loss_clear_planes(const bg_loss_params *p, const bg_head_grads grads[3], cudaStream_t st)
+{
+    struct Run { unsigned char *p; size_t n; } runs[6];
+    int nr = 0;
+    for (int s = 0; s < 3; ++s) {
+        const size_t cells = (size_t)p->B * p->ny[s] * p->nx[s] * p->na;
+        if (!grads[s].cls || !grads[s].box) return BG_ERR_INVALID;
+        runs[nr++] = Run{(unsigned char *)grads[s].cls, cells * p->C * sizeof(float)};
+        runs[nr++] = Run{(unsigned char *)grads[s].box, cells * 4 * sizeof(float)};
+    }
+    for (int i = 1; i < nr; ++i)  // insertion sort by address
+        for (int j = i; j > 0 && runs[j].p < runs[j - 1].p; --j) { const Run t = runs[j]; runs[j] = runs[j - 1]; runs[j - 1] = t; }
+    for (int i = 0; i < nr;) {
+        unsigned char *b0 = runs[i].p;
+        size_t n = runs[i].n;
+        int j = i + 1;
+        while (j < nr && runs[j].p == b0 + n) { n += runs[j].n; ++j; }
+        if (cudaMemsetAsync(b0, 0, n, st) != cudaSuccess) return BG_ERR_LAUNCH;
+        i = j;
+    }
+    return BG_OK;
+}
+
+int bg_loss_clear_grads(const bg_loss_params *p, const bg_head_grads grads[3], void *stream)
+{
+    if (!loss_valid(p) || !grads || p->input_form != BG_LOSS_RAW_SPLIT) return BG_ERR_INVALID;
+    return loss_clear_planes(p, grads, (cudaStream_t)stream);
+}
+
 int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *grad_out_dev, float grad_out_host,
-                const bg_head_grads grads[3], void *workspace, size_t workspace_bytes, void *stream)
+                const bg_head_grads grads[3], int32_t flags, void *workspace, size_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     if (!loss_valid(p) || !in || !grads || !workspace) return BG_ERR_INVALID;
@@ -937,22 +968,11 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
     const bool prof = prof_a && prof_b;
     if (prof) cudaEventRecord(prof_a, st);
     if (p->input_form == BG_LOSS_RAW_SPLIT) {
-        // class / box planes: cleared by memset (adjacent planes are cleared by one call), objectness plane by a kernel
-        struct Run { unsigned char *p; size_t n; } runs[6];
-        int nr = 0;
-        for (int s = 0; s < 3; ++s) {
-            runs[nr++] = Run{(unsigned char *)grads[s].cls, (size_t)w.cells[s] * p->C * sizeof(float)};
-            runs[nr++] = Run{(unsigned char *)grads[s].box, (size_t)w.cells[s] * 4 * sizeof(float)};
-        }
-        for (int i = 1; i < nr; ++i)  // insertion sort by address
-            for (int j = i; j > 0 && runs[j].p < runs[j - 1].p; --j) { const Run t = runs[j]; runs[j] = runs[j - 1]; runs[j - 1] = t; }
-        for (int i = 0; i < nr;) {
-            unsigned char *b0 = runs[i].p;
-            size_t n = runs[i].n;
-            int j = i + 1;
-            while (j < nr && runs[j].p == b0 + n) { n += runs[j].n; ++j; }
-            if (cudaMemsetAsync(b0, 0, n, st) != cudaSuccess) return BG_ERR_LAUNCH;
-            i = j;
+        // class / box planes: cleared by memset unless the caller did so already (BG_LOSS_BWD_PRECLEARED: next to the
+        // forward, on another stream); objectness plane by a kernel
+        if (!(flags & BG_LOSS_BWD_PRECLEARED)) {
+            const int rc = loss_clear_planes(p, grads, st);
+            if (rc != BG_OK) return rc;
         }
         loss_bwd_conf_kernel<<<dim3(sms * 2, 3), 256, 0, st>>>(k);
         BG_LAUNCH_CHECK();

@@ -703,19 +703,60 @@ def _head_ptrs(tensors, split: bool):
     return arr
 
 
+_side_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _side_streams.get(idx)
+    if st is None:
+        st = _side_streams[idx] = torch.cuda.Stream(device=dev)
+    return st
+
+
+def _split_grad_buffers(tensors, dev):
+    """Gradient tensors of the split form: the class / box planes of the three scales share one buffer (one memset
+    clears them all), the objectness planes are separate."""
+    big = [t for i, t in enumerate(tensors) if i % 3]
+    flat = torch.empty(sum(t.numel() for t in big), dtype=torch.float32, device=dev)
+    grads, off = [], 0
+    for i, t in enumerate(tensors):
+        if i % 3 == 0:
+            grads.append(torch.empty_like(t))
+        else:
+            grads.append(flat[off: off + t.numel()].view(t.shape))
+            off += t.numel()
+    return grads, flat
+
+
 class _DetLoss(torch.autograd.Function):
     """Forward: assignment + gather + CIoU + objectness/class BCE for the three scales and the combined loss,
     all on the device, no host sync.  Backward: dense gradients written once per scale; the upstream
     gradient stays on the device.  Everything the backward needs lives in a workspace allocated per forward and
     owned by ``ctx`` -- any number of forwards may precede their backwards (gradient accumulation, several
-    loss modules, a validation loss in between)."""
+    loss modules, a validation loss in between).
+
+    Split form with gradients required: the 2 GB of zeros of the class / box gradient planes do not depend on the
+    forward, whose kernels are latency- and issue-bound.  The gradient tensors are therefore allocated already in the
+    forward and cleared on a second stream NEXT TO the forward kernels; the backward joins that stream and only
+    writes the objectness plane and the matched rows."""
 
     @staticmethod
     def forward(ctx, targets, params: LossParams, scalars, hist, status, *tensors):
         L = _lib.lib()
         dev = tensors[0].device
         split = params.input_form == _lib.LOSS_RAW_SPLIT
+        ctx.pre = None
         with _on(dev):
+            if split and PRECLEAR_SPLIT_GRADS and any(ctx.needs_input_grad[5:]):
+                # (needs_input_grad says whether a backward can follow)
+                cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                grads, flat = _split_grad_buffers(tensors, dev)
+                side.wait_stream(cur)        # the buffers may be recycled memory of work queued on this stream
+                check(L.bg_loss_clear_grads(C.byref(params), _head_ptrs(grads, True), side.cuda_stream), "bg_loss_clear_grads")
+                if not torch.cuda.is_current_stream_capturing():
+                    flat.record_stream(side)   # (if the node dies without its backward, the memory waits for the clear)
+                ctx.pre = (grads, flat, side)
             ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
             loss = torch.empty(1, dtype=torch.float32, device=dev)
             check(L.bg_loss_fwd(_head_ptrs(tensors, split), targets.data_ptr() if targets.numel() else None,
@@ -732,25 +773,26 @@ class _DetLoss(torch.autograd.Function):
         params = ctx.params
         dev = tensors[0].device
         split = params.input_form == _lib.LOSS_RAW_SPLIT
+        flags = 0
         with _on(dev):
-            if split:
-                # class / box gradients of the three scales share one buffer: one memset clears them all
-                big = [t for i, t in enumerate(tensors) if i % 3]
-                flat = torch.empty(sum(t.numel() for t in big), dtype=torch.float32, device=dev)
-                grads, off = [], 0
-                for i, t in enumerate(tensors):
-                    if i % 3 == 0:
-                        grads.append(torch.empty_like(t))
-                    else:
-                        grads.append(flat[off: off + t.numel()].view(t.shape))
-                        off += t.numel()
+            if ctx.pre is not None:
+                grads, _flat, side = ctx.pre
+                torch.cuda.current_stream(dev).wait_stream(side)   # the planes are zero from here on
+                flags = _lib.LOSS_BWD_PRECLEARED
+                ctx.pre = None                                     # (a second backward through the same node is refused by autograd anyway)
+            elif split:
+                grads, _flat = _split_grad_buffers(tensors, dev)
             else:
                 grads = [torch.empty_like(x) for x in tensors]
             if go.dtype != torch.float32 or not go.is_contiguous():
                 go = go.to(torch.float32).contiguous()
-            check(L.bg_loss_bwd(_head_ptrs(tensors, split), C.byref(params), go.data_ptr(), 1.0, _head_ptrs(grads, split),
+            check(L.bg_loss_bwd(_head_ptrs(tensors, split), C.byref(params), go.data_ptr(), 1.0, _head_ptrs(grads, split), flags,
                                 ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "bg_loss_bwd")
         return (None, None, None, None, None, *grads)
+
+
+# split form: clear the class / box gradient planes next to the forward (see _DetLoss); False = inside the backward
+PRECLEAR_SPLIT_GRADS = True
 
 
 _combine_param_cache: Dict[tuple, LossParams] = {}
