@@ -260,10 +260,11 @@ int bg_loss_fwd(const bg_head_ptrs in[3] /*host*/, const float *targets, const b
 int bg_loss_bwd(const bg_head_ptrs in[3] /*host*/, const bg_loss_params *p /*host*/, const float *grad_out_dev,
                 float grad_out_host, const bg_head_grads grads[3] /*host*/, int32_t flags, void *workspace,
                 size_t workspace_bytes, void *stream);
-/* BG_LOSS_RAW_SPLIT: clears the class / box planes of the gradient tensors (adjacent planes with one cudaMemsetAsync).
- * The 2 GB of zeros do not depend on the forward: a caller that allocates the gradients up front can issue this on a
- * second stream NEXT TO bg_loss_fwd (whose kernels are latency- and issue-bound and leave most of the bandwidth free)
- * and pass BG_LOSS_BWD_PRECLEARED to bg_loss_bwd after joining the streams. */
+/* BG_LOSS_RAW_SPLIT: clears the class / box planes of the gradient tensors (adjacent planes with one cudaMemsetAsync),
+ * for callers that allocate the gradients up front and want the 2 GB of zeros -- which do not depend on the forward --
+ * written elsewhere in their schedule; bg_loss_bwd then takes BG_LOSS_BWD_PRECLEARED.  (Measured on B200: running the
+ * clear on a second stream NEXT TO bg_loss_fwd gains nothing -- a memset fills every thread slot of the machine and
+ * the forward kernels queue behind it, a fill kernel small enough to leave them room writes at 1-2 TB/s) */
 int bg_loss_clear_grads(const bg_loss_params *p /*host*/, const bg_head_grads grads[3] /*host*/, void *stream);
 
 /* Image-sharded training: per-shard sums that add up over the shards, and the big-batch loss from the

@@ -708,6 +708,37 @@ def test_loss_step_graph_replays_the_eager_step(ops):
             assert torch.equal(s_.grad, e_.grad)
 
 
+def test_loss_split_gradients_cleared_ahead(ops):
+    """bg_loss_clear_grads + BG_LOSS_BWD_PRECLEARED (ops.PRECLEAR_SPLIT_GRADS): the class / box gradient planes cleared on
+    a second stream next to the forward give the gradients of the default path bit for bit, eagerly and from a graph."""
+    B, H, W, C = 4, 128, 128, 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    cfg = dict(synth.LOSS_CONFIG, num_classes=C)
+    t = dev(synth.targets(B, 12, C, 0))
+    raws = synth.train_preds(B, H, W, C, 1)
+
+    def run(graph):
+        tri = [tuple(x.requires_grad_(True) for x in _split(dev(p), C)) for p in raws]
+        if graph:
+            gs = ops.LossStepGraph(tri, t, anc, cfg, input_form="split")
+            loss = gs.replay()
+        else:
+            loss, _ = ops.detection_loss(tri, t, anc, cfg, with_metrics=False, input_form="split")
+            loss.backward()
+        torch.cuda.synchronize()
+        return float(loss), [x.grad.clone() for p in tri for x in p]
+
+    base = run(False)
+    ops.PRECLEAR_SPLIT_GRADS = True
+    try:
+        for graph in (False, True):
+            got = run(graph)
+            assert got[0] == base[0]
+            assert all(torch.equal(a, b) for a, b in zip(got[1], base[1]))
+    finally:
+        ops.PRECLEAR_SPLIT_GRADS = False
+
+
 def test_loss_rejects_out_of_range_ids(ops):
     """Image ids outside 0..B-1 and class ids outside 0..C-1: the reference raises IndexError (preds[batch_idx, ...],
     t_cls[range, classes]); the CUDA path drops those rows on the device -- no out-of-bounds access -- and raises
