@@ -40,7 +40,7 @@ extern "C" {
 #define BG_STATUS_MASK_SPACE 2  /* suppression scratch (mask_bytes) exhausted: neither the overlap-edge list nor the dense
                                  * bit matrix fits; retry with a larger mask_bytes */
 #define BG_STATUS_NEED_GENERAL 4 /* bg_detect, per-image NMS path: an image has too many survivors (out_counts[2+B+b]) or overlaps;
-                                   * retry with nms_path = 4 (up to 8,192 survivors) or 1 */
+                                   * retry with nms_path = 2 (after 5), 4 (up to 8,192 survivors) or 1 */
 
 #define BG_MAX_ANCHORS 8
 #define BG_MAX_TRACKED 64
@@ -95,7 +95,9 @@ typedef struct {
     int32_t variant;            /* decode kernel tile loads: 0 auto, 1 plain loads, 2 TMA bulk pipeline (needs 16-byte aligned inputs) */
     int32_t nms_path;           /* 0 auto (per-image CTAs, up to 4,096 score survivors per image), 1 general segmented engine,
                                  * 2 = 0 but an error instead of the general engine when the threshold rules it out,
-                                 * 3 = 2 with one CTA per image (no helper CTA), 4 per-image CTAs for up to 8,192 survivors */
+                                 * 3 = 2 with one CTA per image (no helper CTA), 4 per-image CTAs for up to 8,192 survivors,
+                                 * 5 lean per-image CTAs (512 threads, 46 KB: up to 2,048 survivors per image) that fit on an SM
+                                 * next to the decode CTAs of batches in flight on other streams */
     int32_t extra_cols;         /* columns per row after the four box columns that the kernels skip (mask coefficients and
                                  * keypoints of the segmentation / keypoint heads, inference_seg.py:66-68): rows are
                                  * 5 + C + extra_cols floats; the caller gathers them by out_keep */

@@ -239,7 +239,7 @@ def test_seg_post_process_golden(ops, name, nms_path):
     assert torch.equal(plain.pred_boxes, rows) and torch.equal(plain.keep_idxs, keep)
 
 
-@pytest.mark.parametrize("nms_path", ["auto", "general", "per_image_single"])
+@pytest.mark.parametrize("nms_path", ["auto", "general", "per_image_single", "per_image_lean"])
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("B,H,W,C,dist,og,iou,thr,allow,tracked,order", [
     (2, 96, 64, 3, "N", (120, 100), 0.5, 0.2, 4, None, "image"),        # non-square, rescale, even row length (D=8)
@@ -308,10 +308,36 @@ def test_detect_paths_agree_exactly(ops):
     for iou in (0.65, 0.3, 0.1):
         a = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="auto")
         a = [t.clone() for t in (a.pred_boxes, a.sample_idxs, a.keep_idxs, a.counts)]
-        for path in ("general", "per_image_single"):
+        for path in ("general", "per_image_single", "per_image_lean"):
             g = ops.detect(raws, anc, (H, W), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path=path)
             for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
                 assert torch.equal(x, y), (iou, path)
+
+
+def test_detect_lean_kernel_steps_up(ops):
+    """Throughput plans start on the lean per-image kernel (512 threads, 46 KB, up to 2,048 survivors: it shares an SM
+    with the decode CTAs of other batches).  Rows are bitwise those of the general engine; an image with more survivors
+    moves the plan to the 1024-thread kernel (and the configuration's hint with it), heavy overlap spills the lean
+    kernel's 4,096-edge shared-memory list to the global list."""
+    C = 80
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    dv = torch.device("cuda", 0)
+    for H, dist, iou, expect_path in ((640, "T", 0.65, 5), (160, "R", 0.5, 5), (224, "R", 0.5, 2)):
+        B = 3
+        raws = [dev(r) for r in synth.raw_head_outputs(B, H, H, C, dist, seed=5)]
+        ops._nms_path_hint.clear()
+        plan = ops.DetectPlan([tuple(r.shape) for r in raws], anc, (H, H), C, dv, None, iou, 0.001, 4, throughput=True)
+        assert plan.params.nms_path == 5
+        plan.enqueue(raws)
+        d = plan.result()
+        assert plan.params.nms_path == expect_path, (H, dist, int(d.candidates.max()))
+        a = [t.clone() for t in (d.pred_boxes, d.sample_idxs, d.keep_idxs, d.counts)]
+        again = ops.DetectPlan([tuple(r.shape) for r in raws], anc, (H, H), C, dv, None, iou, 0.001, 4, throughput=True)
+        assert again.params.nms_path == expect_path          # the hint is remembered per configuration
+        g = ops.detect(raws, anc, (H, H), C, iou_threshold=iou, score_threshold=0.001, box_allowance=4, nms_path="general")
+        for x, y in zip(a, (g.pred_boxes, g.sample_idxs, g.keep_idxs, g.counts)):
+            assert torch.equal(x, y), (H, dist)
+    ops._nms_path_hint.clear()
 
 
 @pytest.mark.parametrize("depth", [1, 3])

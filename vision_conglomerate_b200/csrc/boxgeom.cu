@@ -154,6 +154,8 @@ struct DetWs {
     u32 *gspill;
     u64 *gsorted;
     float4 *gboxp;
+    u64 *gkeyp;           // lean per-image kernel: keys / classes by survivor number
+    u32 *gclsp;
     u64 *f_emit_key;      // globally ordered output only
     float4 *f_emit_box;
     int *f_emit_cls;
@@ -183,6 +185,8 @@ static size_t det_carve(unsigned char *base, int B, long long N, int tiles_per_i
         w.gspill = b.take<u32>((size_t)B * DET_SPILL_EDGES);
         w.gsorted = b.take<u64>((size_t)B * INMS_CAP_MAX);
         w.gboxp = b.take<float4>((size_t)B * INMS_CAP_MAX);
+        w.gkeyp = b.take<u64>((size_t)B * InmsLean::CAP);
+        w.gclsp = b.take<u32>((size_t)B * InmsLean::CAP);
     }
     w.stride = (long long)next_pow2((u32)N);
     if (general) {
@@ -245,7 +249,7 @@ static int det_nms_path(const bg_detect_params *p, const TilePlan &tp)
     const IouThr t = make_iou_thr(p->iou_threshold);
     const bool ok = t.fast_ok && !t.zero_suppresses && t.tdn >= 0.05f && t.tdn < 1.0f && tp.tpi_total < INMS_MAXT &&
                     det_candidates(p) <= InmsLarge::MAX_N && p->C <= 65535;
-    if (p->nms_path >= 2 && p->nms_path <= 4) return ok ? 0 : -1;
+    if (p->nms_path >= 2 && p->nms_path <= 5) return ok ? 0 : -1;
     return ok ? 0 : 1;
 }
 
@@ -418,7 +422,12 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         if (cudaFuncSetAttribute(decode_filter_kernel<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(decode_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_STAGES * DEC_TILE_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(image_nms_kernel<InmsSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsSmall>)) != cudaSuccess ||
-            cudaFuncSetAttribute(image_nms_kernel<InmsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsLarge>)) != cudaSuccess) {
+            cudaFuncSetAttribute(image_nms_kernel<InmsLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ImgNmsSmem<InmsLarge>)) != cudaSuccess ||
+            // the lean NMS CTA shares an SM with two decode CTAs only if the SM keeps its full 228 KB of shared memory:
+            // a smaller carve-out chosen for the decode kernel alone (196 KB) could not be changed while its CTAs run
+            cudaFuncSetAttribute(decode_filter_kernel<80>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaFuncSetAttribute(decode_filter_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess ||
+            cudaFuncSetAttribute(image_nms_kernel<InmsLean>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
             (void)cudaGetLastError();
             return BG_ERR_LAUNCH;
         }
@@ -463,23 +472,31 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         q.stamps = g_prof_stamps;
         {   // two CTAs per image (helper + main) while every CTA of the grid can be resident at once
             static const int split_env = []() { const char *e = getenv("BG_NMS_SPLIT"); return e ? atoi(e) : -1; }();
-            q.split = (pp->nms_path == 3 || pp->throughput) ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
+            // (throughput mode, 1024-thread kernel: less total SM time matters more than latency; the lean kernel runs next
+            // to the decode CTAs either way, and a shorter NMS shortens what is left when the last batch's decode ends)
+            const bool can_split = pp->nms_path != 3 && (!pp->throughput || pp->nms_path == 5);
+            q.split = !can_split ? 0 : (split_env >= 0 ? (split_env != 0) : (2 * pp->B <= sms ? 1 : 0));
         }
         q.gflag = w.gflag; q.gedges = w.gedges; q.gsorted = w.gsorted; q.gspill = w.gspill; q.gcap = DET_SPILL_EDGES;
-        q.gboxp = w.gboxp;
+        q.gboxp = w.gboxp; q.gkeyp = w.gkeyp; q.gclsp = w.gclsp;
         const bool large = pp->nms_path == 4;  // up to 8,192 survivors per image, boxes in L2 instead of shared memory
+        // up to 2,048 survivors; a CTA small enough to run next to the decode CTAs of other streams (one tile count per thread)
+        const bool lean = pp->nms_path == 5 && tp.tpi_total < InmsLean::MAXT;
         {   // programmatic dependent launch: the CTAs become resident while the decode kernel drains
             static const bool pdl = []() { const char *e = getenv("BG_PDL"); return !(e && e[0] == '0'); }();
             cudaLaunchConfig_t cfg;
             memset(&cfg, 0, sizeof(cfg));
-            cfg.gridDim = dim3(pp->B * (q.split ? 2 : 1)); cfg.blockDim = dim3(INMS_THREADS);
-            cfg.dynamicSmemBytes = large ? sizeof(ImgNmsSmem<InmsLarge>) : sizeof(ImgNmsSmem<InmsSmall>); cfg.stream = st;
+            cfg.gridDim = dim3(pp->B * (q.split ? 2 : 1)); cfg.blockDim = dim3(lean ? InmsLean::THREADS : INMS_THREADS);
+            cfg.dynamicSmemBytes = lean ? sizeof(ImgNmsSmem<InmsLean>) : large ? sizeof(ImgNmsSmem<InmsLarge>) : sizeof(ImgNmsSmem<InmsSmall>);
+            cfg.stream = st;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             // (throughput mode: CTAs resident early would hold SMs the other streams' decode kernels can use)
             cfg.attrs = at; cfg.numAttrs = (pdl && !pp->throughput) ? 1 : 0;
-            const cudaError_t le = large ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLarge>, q) : cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsSmall>, q);
+            const cudaError_t le = lean    ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLean>, q)
+                                   : large ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLarge>, q)
+                                           : cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsSmall>, q);
             if (le != cudaSuccess) { (void)cudaGetLastError(); return BG_ERR_LAUNCH; }
             ++g_launches;
         }

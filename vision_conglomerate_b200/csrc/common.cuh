@@ -76,15 +76,15 @@ struct IouThr {
 };
 IouThr make_iou_thr(double thr);
 
-// Ascending bitonic sort of s[0..P), P = E * 1024 keys (callers pad with ~0), by 1024 threads.  Thread t holds
-// the E consecutive keys t*E..t*E+E-1 in registers: strides below E are register compare-exchanges, strides
-// below 32*E are warp shuffles with lane ^ (j/E), and only the larger strides go through shared memory
-// (staged key-index-major, s[e*1024 + t], so the exchange reads are conflict-free).
-template <int E>
+// Ascending bitonic sort of s[0..P), P = E * NT keys (callers pad with ~0), by NT threads (1024, or 512 in the lean
+// per-image NMS).  Thread t holds the E consecutive keys t*E..t*E+E-1 in registers: strides below E are register
+// compare-exchanges, strides below 32*E are warp shuffles with lane ^ (j/E), and only the larger strides go through
+// shared memory (staged key-index-major, s[e*NT + t], so the exchange reads are conflict-free).
+template <int E, int NT = 1024>
 __device__ __forceinline__ void sort_reg_1024(u64 *s, int k_start = 2)  // k_start = P: only the last merge (input bitonic)
 {
     const int t = threadIdx.x;
-    constexpr int P = E * 1024;
+    constexpr int P = E * NT;
     u64 v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) v[e] = s[t * E + e];
@@ -93,13 +93,13 @@ __device__ __forceinline__ void sort_reg_1024(u64 *s, int k_start = 2)  // k_sta
         for (int j = k >> 1; j > 0; j >>= 1) {
             if (j >= 32 * E) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) s[e * 1024 + t] = v[e];
+                for (int e = 0; e < E; ++e) s[e * NT + t] = v[e];
                 __syncthreads();
                 const int pt = t ^ (j / E);
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = t * E + e;
-                    const u64 o = s[e * 1024 + pt];
+                    const u64 o = s[e * NT + pt];
                     const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
                     v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
                 }
@@ -113,7 +113,7 @@ __device__ __forceinline__ void sort_reg_1024(u64 *s, int k_start = 2)  // k_sta
                     v[e] = keep_min ? (o < v[e] ? o : v[e]) : (o > v[e] ? o : v[e]);
                 }
             } else {
-                // register compare-exchange; j is 1 (E >= 2) or 2 (E == 4): static indices keep v[] in registers
+                // register compare-exchange; j is 1 (E >= 2), 2 (E >= 4) or 4 (E == 8): static indices keep v[] in registers
 #pragma unroll
                 for (int jj = 1; jj < E; jj <<= 1) {
                     if (jj != j) continue;

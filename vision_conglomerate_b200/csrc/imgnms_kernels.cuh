@@ -31,21 +31,34 @@ constexpr int INMS_MAXT = 1024;      // tiles per image
 constexpr int INMS_GMAX = 64;        // grid cells per axis
 constexpr int INMS_HELPER_SHARE_32 = 7;  // the helper takes 7/32 of the pair-test items (it also does the sort)
 
-// Two sizes of the kernel.  Small: up to 4 096 survivors per image, boxes in shared memory (the headline case).
+// Three sizes of the kernel.  Small: up to 4 096 survivors per image, boxes in shared memory (the latency case).
 // Large: up to 8 192 survivors; the boxes no longer fit next to the keys, so they live in a compact global
 // array (L2-resident) and only the bf16 extents used by the pre-filter stay in shared memory.
-template <int CAP_, bool BOX_SMEM_>
+// Lean (throughput mode, several batches in flight): up to 2 048 survivors, 512 threads, <= 56 registers and 46 KB of
+// shared memory, so that a CTA fits on an SM NEXT TO the two resident CTAs of the next batch's decode kernel
+// (2 x 90.7 KB, 2 x 128 threads x 144 registers) instead of waiting for -- or taking -- a whole SM.  Boxes, classes and
+// (until the sort) the keys live in the image's L2-resident scratch; the keys' shared-memory home is shared with the
+// arrays of the pair-test stage.
+template <int CAP_, bool BOX_SMEM_, int THREADS_ = 1024, bool LEAN_ = false>
 struct InmsCfg {
     static constexpr int CAP = CAP_;                 // survivors per image
     static constexpr bool BOX_SMEM = BOX_SMEM_;
-    static constexpr int PBITS = CAP_ == 4096 ? 12 : 13;   // bits of p inside the sort key
-    static constexpr int ECAP = BOX_SMEM_ ? 12288 : 8192;  // overlap edges in shared memory (more spill to global)
+    static constexpr int THREADS = THREADS_;
+    static constexpr bool LEAN = LEAN_;
+    static constexpr int PBITS = CAP_ == 2048 ? 11 : (CAP_ == 4096 ? 12 : 13);   // bits of p inside the sort key
+    static constexpr int ECAP = LEAN_ ? 4096 : (BOX_SMEM_ ? 12288 : 8192);  // overlap edges in shared memory (more spill to global)
     static constexpr int ITEMS = 2 * CAP_;           // (box, grid row) work items per pass
-    static constexpr int PER = CAP_ / INMS_THREADS;  // boxes / sort keys per thread
+    static constexpr int PER = CAP_ / THREADS_;      // boxes / sort keys per thread
     static constexpr int MAX_N = 1 << (32 - PBITS);  // candidates per image (key = score | idx | p)
+    static constexpr int GMAX = LEAN_ ? 32 : INMS_GMAX;  // grid cells per axis (2 (G+1)^2 <= K bounds G by 31 at 2 048)
+    static constexpr int MAXT = THREADS_;            // tiles per image (one tile count per thread in stage 1)
+    // split mode: the helper CTA takes this many 32nds of the pair-test items (it also does the sort; with 512 threads
+    // the pair tests are 3.5x the sort, with 1024 threads 1.7x)
+    static constexpr int HELPER_SHARE_32 = LEAN_ ? 11 : INMS_HELPER_SHARE_32;
 };
 typedef InmsCfg<4096, true> InmsSmall;
 typedef InmsCfg<8192, false> InmsLarge;
+typedef InmsCfg<2048, false, 512, true> InmsLean;
 constexpr int INMS_CAP_MAX = InmsLarge::CAP;
 constexpr int INMS_HCAP = 12288;     // edges a helper CTA hands over from its shared-memory list (>= any ECAP)
 
@@ -79,7 +92,9 @@ struct ImgNmsK {
     u32 *gspill;               // [B, gcap] edges that did not fit a CTA's shared-memory list (main and helper)
     int gcap;
     u64 *gsorted;              // [B, INMS_CAP_MAX]
-    float4 *gboxp;             // [B, INMS_CAP_MAX] large variant: boxes in survivor (p) order
+    float4 *gboxp;             // [B, INMS_CAP_MAX] large / lean variant: boxes in survivor (p) order
+    u64 *gkeyp;                // [B, InmsLean::CAP] lean variant: keys in survivor order (until the sort)
+    u32 *gclsp;                // [B, InmsLean::CAP] lean variant: classes in survivor order
 };
 constexpr int INMS_STAMPS = 10;
 
@@ -91,7 +106,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #define INMS_STAMP(i) do { if (k.stamps && tid == 0 && role == 1) k.stamps[(long long)b * INMS_STAMPS + (i)] = globaltimer_ns(); } while (0)
 
-template <class Cfg>
+template <class Cfg, bool LEAN = Cfg::LEAN>
 struct ImgNmsSmem {
     u64 keys[Cfg::CAP];                          // (~score | idx | p); indexed by p until the sort
     float4 box[Cfg::BOX_SMEM ? Cfg::CAP : 1];    // by p (small variant only)
@@ -118,9 +133,44 @@ struct ImgNmsSmem {
     int img;
     long long base;
 };
+// lean layout: the keys are parked in global memory from stage 1 to the sort and share their home with the
+// stage 2..3 arrays; classes stay in global memory
+template <class Cfg>
+struct ImgNmsSmem<Cfg, true> {
+    union {
+        u64 keys[Cfg::CAP];                      // stage 5..6
+        struct {
+            u32 whc[Cfg::CAP];                   // stage 2..3
+            union {
+                struct { unsigned short cell_of[Cfg::CAP], rank_in_cell[Cfg::CAP]; };  // stage 2
+                unsigned short item_owner[Cfg::ITEMS];                                 // stage 3
+            };
+        };
+    };
+    u32 edges[Cfg::ECAP];
+    int cell_start[Cfg::GMAX * Cfg::GMAX + 1];
+    union {
+        int tile_pref[Cfg::MAXT + 1];            // stage 1
+        unsigned short cellord[Cfg::CAP];        // stage 2..3
+    };
+    union {
+        unsigned char item_row[Cfg::ITEMS];                                    // stage 3
+        struct { unsigned char state[Cfg::CAP], blocked[Cfg::CAP]; };          // stage 4..6
+    };
+    int wsum[33];
+    float red[4][32];
+    int n_edges;
+    int next_item;
+    int img;
+    long long base;
+};
 static_assert(sizeof(ImgNmsSmem<InmsSmall>) <= 227 * 1024 && sizeof(ImgNmsSmem<InmsLarge>) <= 227 * 1024,
               "per-image NMS state must fit one SM's shared memory");
+// 228 KB per SM - 2 x (87 040 B ring + 3 712 B static and reserved) of the decode CTAs - 1 KB reserved for this CTA
+static_assert(sizeof(ImgNmsSmem<InmsLean>) <= 233472 - 2 * (2 * 43520 + 3712) - 1024,
+              "the lean per-image NMS must fit next to two decode CTAs");
 
+template <int NT>
 __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, int &total)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -133,7 +183,7 @@ __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, i
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        const int w = wsum[lane];
+        const int w = lane < NT / 32 ? wsum[lane] : 0;
         int winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -150,18 +200,19 @@ __device__ __forceinline__ int inms_block_excl_scan(int v, int *wsum /*[33]*/, i
     return r;
 }
 
-// pads keys[K..P) with ~0 and sorts keys[0..P), P = the smallest of 1024, 2048, 4096 (, 8192) >= K
+// pads keys[K..P) with ~0 and sorts keys[0..P), P = the smallest of 1, 2, 4 (, 8) x THREADS >= K
 template <class Cfg>
 __device__ __forceinline__ void inms_sort_keys(u64 *keys, int K)
 {
-    int P = INMS_THREADS;
+    constexpr int NT = Cfg::THREADS;
+    int P = NT;
     while (P < K) P <<= 1;
-    for (int j = K + threadIdx.x; j < P; j += INMS_THREADS) keys[j] = ~0ull;
+    for (int j = K + threadIdx.x; j < P; j += NT) keys[j] = ~0ull;
     __syncthreads();
-    if (P == INMS_THREADS) sort_reg_1024<1>(keys);
-    else if (P == 2 * INMS_THREADS) sort_reg_1024<2>(keys);
-    else if (P == 4 * INMS_THREADS || Cfg::CAP <= 4 * INMS_THREADS) sort_reg_1024<4>(keys);
-    else sort_reg_1024<8>(keys);
+    if (P == NT) sort_reg_1024<1, NT>(keys);
+    else if (P == 2 * NT) sort_reg_1024<2, NT>(keys);
+    else if (P == 4 * NT || Cfg::CAP <= 4 * NT) sort_reg_1024<4, NT>(keys);
+    else sort_reg_1024<8, NT>(keys);
 }
 
 __device__ __forceinline__ bool inms_tracked(const ImgNmsK &k, int c)
@@ -187,12 +238,13 @@ __device__ __forceinline__ bool inms_box_valid(const float4 bx, float &w, float 
 }
 
 template <class Cfg>
-__global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
+// (lean: bounds of 2 x 576 threads cap the kernel at 56 registers -- 512 x 56 is what two decode CTAs leave of an SM's file)
+__global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 : 1) image_nms_kernel(ImgNmsK k)
 {
     extern __shared__ __align__(16) unsigned char inms_raw[];
     ImgNmsSmem<Cfg> &S = *reinterpret_cast<ImgNmsSmem<Cfg> *>(inms_raw);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int CAP = Cfg::CAP, PER = Cfg::PER;
+    constexpr int CAP = Cfg::CAP, PER = Cfg::PER, INMS_THREADS = Cfg::THREADS, INMS_GMAX = Cfg::GMAX;
 
     // launched with programmatic stream serialization: the CTA may become resident while the decode kernel
     // drains; everything it reads is produced by that kernel, so wait for it here
@@ -208,14 +260,20 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     // boxes by survivor number p: shared memory (small variant) or the image's compact global array (large variant;
     // both CTAs of an image write identical values there, then read their own writes)
     float4 *gbx = k.gboxp + (long long)b * INMS_CAP_MAX;
-    auto box_at = [&](int i) -> float4 { return Cfg::BOX_SMEM ? S.box[i] : gbx[i]; };
+    auto box_at = [&](int i) -> float4 { if constexpr (Cfg::BOX_SMEM) return S.box[i]; else return gbx[i]; };
+    // lean variant: keys (until the sort) and classes by survivor number in the image's global scratch (both CTAs of
+    // an image write identical values there, then read their own writes)
+    u64 *gkey = k.gkeyp + (long long)b * InmsLean::CAP;
+    u32 *gcls = k.gclsp + (long long)b * InmsLean::CAP;
+    auto key_at = [&](int i) -> u64 { if constexpr (Cfg::LEAN) return gkey[i]; else return S.keys[i]; };
+    auto cls_at = [&](int i) -> int { if constexpr (Cfg::LEAN) return (int)gcls[i]; else return (int)S.cls[i]; };
     INMS_STAMP(0);
 
     // ---- 1. tile counts -> prefix; keys, boxes, classes into shared memory (slot order = candidate order) ----
     int K;
     {
         const int c = (tid < k.tpi_total) ? k.tile_count[(long long)b * k.tpi_total + tid] : 0;
-        const int ex = inms_block_excl_scan(c, S.wsum, K);
+        const int ex = inms_block_excl_scan<INMS_THREADS>(c, S.wsum, K);
         if (tid <= k.tpi_total) S.tile_pref[tid] = ex;  // tid == tpi_total holds the total (c = 0 there)
         if (tid == 0) S.n_edges = 0;
     }
@@ -236,13 +294,13 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         const u64 key = k.keys[slot];
         const float4 bx = k.box_slots[slot];
         const int cl = k.cls_slots[slot];
-        S.keys[j] = (key & 0xffffffff00000000ull) | ((u64)key_id(key) << Cfg::PBITS) | (u64)j;
-        if (Cfg::BOX_SMEM) S.box[j] = bx; else gbx[j] = bx;
-        S.cls[j] = (unsigned short)cl;
+        const u64 pkey = (key & 0xffffffff00000000ull) | ((u64)key_id(key) << Cfg::PBITS) | (u64)j;
+        if constexpr (Cfg::LEAN) { gkey[j] = pkey; gcls[j] = (u32)cl; } else { S.keys[j] = pkey; S.cls[j] = (unsigned short)cl; }
+        if constexpr (Cfg::BOX_SMEM) S.box[j] = bx; else gbx[j] = bx;
         float w, h, cx, cy;
         if (inms_box_valid(bx, w, h, cx, cy)) { mnx = fminf(mnx, cx); mxx = fmaxf(mxx, cx); mny = fminf(mny, cy); mxy = fmaxf(mxy, cy); }
     }
-    if (!Cfg::BOX_SMEM) __syncthreads();  // the global box array is complete (block-scope visibility)
+    if (!Cfg::BOX_SMEM) __syncthreads();  // the global box (key, class) arrays are complete (block-scope visibility)
     INMS_STAMP(1);
 
     // ---- 2. grid over the valid centres, counting sort by cell --------------------------------------------------
@@ -253,7 +311,11 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
     }
     if (lane == 0) { S.red[0][wid] = mnx; S.red[1][wid] = mxx; S.red[2][wid] = mny; S.red[3][wid] = mxy; }
     __syncthreads();  // also: every thread is done with tile_pref (aliases cellord)
-    mnx = S.red[0][lane]; mxx = S.red[1][lane]; mny = S.red[2][lane]; mxy = S.red[3][lane];
+    {   // (only THREADS / 32 entries were written)
+        const bool w = lane < INMS_THREADS / 32;
+        mnx = w ? S.red[0][lane] : INFINITY; mxx = w ? S.red[1][lane] : -INFINITY;
+        mny = w ? S.red[2][lane] : INFINITY; mxy = w ? S.red[3][lane] : -INFINITY;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
@@ -288,7 +350,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) { v[q] = (c0 + q < ncell) ? S.cell_start[c0 + q] : 0; sum += v[q]; }
         int tot;
-        int ex = inms_block_excl_scan(sum, S.wsum, tot);
+        int ex = inms_block_excl_scan<INMS_THREADS>(sum, S.wsum, tot);
 #pragma unroll
         for (int q = 0; q < 4; ++q) { if (c0 + q < ncell) S.cell_start[c0 + q] = ex; ex += v[q]; }
         if (tid == 0) S.cell_start[ncell] = tot;
@@ -322,12 +384,12 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         items += nrow[q];
     }
     int T;
-    const int item0 = inms_block_excl_scan(items, S.wsum, T);  // (its barriers also publish cellord)
+    const int item0 = inms_block_excl_scan<INMS_THREADS>(items, S.wsum, T);  // (its barriers also publish cellord)
     INMS_STAMP(2);
 
     // ---- 3. pair tests, item-parallel ------------------------------------------------------------------------
     const IouThr thr = k.thr;
-    const int T_helper = k.split ? (int)(((long long)T * INMS_HELPER_SHARE_32) >> 5) : 0;
+    const int T_helper = k.split ? (int)(((long long)T * Cfg::HELPER_SHARE_32) >> 5) : 0;
     const int it_lo = role == 1 ? T_helper : 0, it_hi = role == 1 ? T : T_helper;
     for (int c0 = it_lo; c0 < it_hi; c0 += Cfg::ITEMS) {
         const int nit = min(Cfg::ITEMS, it_hi - c0);
@@ -384,7 +446,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
                     const float4 c = box_at(j);
                     const float ac = __fmul_rn(__fsub_rn(c.z, c.x), __fsub_rn(c.w, c.y));
                     if (iou_suppresses(a, aa, c, ac, thr)) {
-                        const bool i_first = S.keys[i] < S.keys[j];  // earlier in (score desc, index asc) order
+                        const bool i_first = key_at(i) < key_at(j);  // earlier in (score desc, index asc) order
                         const u32 ed = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
                         const int e = atomicAdd(&S.n_edges, 1);
                         if (e < Cfg::ECAP) S.edges[e] = ed;
@@ -406,6 +468,9 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         __threadfence();
         __syncthreads();
         if (tid == 0) ((volatile u32 *)k.gflag)[4 * b] = (u32)ne + 1u;
+        if constexpr (Cfg::LEAN) {   // the keys come home (their place held the pair-test arrays)
+            for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = gkey[j];
+        }
         inms_sort_keys<Cfg>(S.keys, K);
         u64 *gs = k.gsorted + (long long)b * INMS_CAP_MAX;
         for (int j = tid; j < K; j += INMS_THREADS) gs[j] = S.keys[j];
@@ -468,6 +533,9 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = __ldcg(gs + j);
         __syncthreads();
     } else {
+        if constexpr (Cfg::LEAN) {   // the keys come home (their place held the pair-test arrays)
+            for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = gkey[j];
+        }
         inms_sort_keys<Cfg>(S.keys, K);
     }
     INMS_STAMP(5);
@@ -483,7 +551,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         if (i < K) {
             const u64 key = S.keys[i];
             const int p = (int)(key & (CAP - 1));
-            if (S.state[p] == 1 && (k.n_tracked == 0 || inms_tracked(k, S.cls[p]))) {
+            if (S.state[p] == 1 && (k.n_tracked == 0 || inms_tracked(k, cls_at(p)))) {
                 mykeys[q] = key;
                 flags |= 1 << q;
                 ++cnt;
@@ -491,7 +559,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         }
     }
     int total;
-    int rank = inms_block_excl_scan(cnt, S.wsum, total);
+    int rank = inms_block_excl_scan<INMS_THREADS>(cnt, S.wsum, total);
     // rows of image b start after the rows of images < b: decoupled look-back over the per-image words
     // (CHAIN_AGG | own count, later CHAIN_PREFIX | inclusive prefix); predecessors hold earlier tickets, so
     // they are running or done and the wait cannot deadlock
@@ -540,7 +608,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         if (k.order == 0) {
             const long long dst = base + rank;
             float2 *o = reinterpret_cast<float2 *>(k.out_boxes + dst * 6);  // rows are 24 bytes: 8-byte aligned
-            o[0] = make_float2(score, (float)S.cls[p]);
+            o[0] = make_float2(score, (float)cls_at(p));
             o[1] = make_float2(bx.x, bx.y);
             o[2] = make_float2(bx.z, bx.w);
             k.out_img[dst] = b;
@@ -548,7 +616,7 @@ __global__ void __launch_bounds__(INMS_THREADS, 1) image_nms_kernel(ImgNmsK k)
         } else {
             k.emit_key[ibase + rank] = (key & 0xffffffff00000000ull) | (u64)id;
             k.emit_box[ibase + rank] = bx;
-            k.emit_cls[ibase + rank] = (int)S.cls[p];
+            k.emit_cls[ibase + rank] = cls_at(p);
         }
         ++rank;
     }

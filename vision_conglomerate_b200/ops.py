@@ -29,6 +29,8 @@ DEFAULT_MASK_BYTES = 64 << 20
 _nms_path_hint: Dict[Tuple, int] = {}
 PER_IMAGE_NMS_CAP = 4096        # InmsSmall::CAP of csrc/imgnms_kernels.cuh
 PER_IMAGE_NMS_CAP_LARGE = 8192  # InmsLarge::CAP
+PER_IMAGE_NMS_CAP_LEAN = 2048   # InmsLean::CAP (throughput mode: a CTA that runs next to the decode CTAs of other streams)
+LEAN_NMS = True                 # throughput plans start on the lean kernel (False: the 1024-thread kernel, one CTA per image)
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -228,10 +230,10 @@ class DetectPlan:
         hint = _nms_path_hint.get(self.hint_key, 0)
         if nms_path == "general":
             p.nms_path = 1
-        elif nms_path in ("per_image", "per_image_single", "per_image_large"):
-            p.nms_path = {"per_image": 2, "per_image_single": 3, "per_image_large": 4}[nms_path]
+        elif nms_path in ("per_image", "per_image_single", "per_image_large", "per_image_lean"):
+            p.nms_path = {"per_image": 2, "per_image_single": 3, "per_image_large": 4, "per_image_lean": 5}[nms_path]
         else:
-            p.nms_path = {0: 0, 4: 4}.get(hint, 1)
+            p.nms_path = self._auto_path(hint, bool(throughput))
         p.throughput = 1 if throughput else 0
         self.shapes = [tuple(sh) for sh in shapes]
         n = B * self.N
@@ -248,6 +250,16 @@ class DetectPlan:
         self.key = (device.index, "detect")
         self.ws_tag = "detect"   # plans that run concurrently on different streams need distinct scratch: set a distinct tag
         self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
+
+    def _auto_path(self, hint: int, throughput: bool) -> int:
+        """``bg_detect_params.nms_path`` for what earlier batches of this configuration needed (``_nms_path_hint``): 0 nothing
+        known / sparse, 2 more than the lean kernel holds, 4 more than the 4 096-survivor kernel holds, else general."""
+        lean_ok = throughput and LEAN_NMS   # (the library steps to the 1024-thread kernel when an image has >= 512 tiles)
+        if hint == 0:
+            return 5 if lean_ok else 0
+        if hint == 2:
+            return 2 if throughput else 0
+        return 4 if hint == 4 else 1
 
     def enqueue(self, raws) -> None:
         """``raws``: the three head tensors, or (``predecoded`` plans) the one decoded ``[B, N, 5+C]`` tensor."""
@@ -294,21 +306,25 @@ class DetectPlan:
                 # an image exceeded what the one-CTA-per-image NMS holds: run again through the general engine
                 # and remember it (survivor overflow is re-evaluated from the counts, edge overflow is kept)
                 most = int(h[2 + B: 2 + 2 * B].max())
-                if most > PER_IMAGE_NMS_CAP and most <= PER_IMAGE_NMS_CAP_LARGE and self.params.nms_path != 4:
+                if self.params.nms_path == 5 and PER_IMAGE_NMS_CAP_LEAN < most <= PER_IMAGE_NMS_CAP:
+                    nxt = 2       # more than the lean kernel holds: the 1024-thread kernel
+                elif most > PER_IMAGE_NMS_CAP and most <= PER_IMAGE_NMS_CAP_LARGE and self.params.nms_path != 4:
                     nxt = 4       # the larger per-image kernel holds it
                 elif most > PER_IMAGE_NMS_CAP_LARGE:
                     nxt = 1       # general engine while the images are this crowded
                 else:
                     nxt = 3       # overlap-edge overflow: general engine for good
                 _nms_path_hint[self.hint_key] = nxt
-                self.params.nms_path = 4 if nxt == 4 else 1
+                self.params.nms_path = {2: 2, 4: 4}.get(nxt, 1)
                 self._enqueue(self.raws)
                 continue
-            if _nms_path_hint.get(self.hint_key) in (1, 4):   # crowded earlier; step back down when it is sparse again
+            if _nms_path_hint.get(self.hint_key) in (1, 2, 4):   # crowded earlier; step back down when it is sparse again
                 most = int(h[2 + B: 2 + 2 * B].max())
                 if self.params.nms_path == 1 and most <= PER_IMAGE_NMS_CAP_LARGE // 2:
                     _nms_path_hint[self.hint_key] = 4 if most > PER_IMAGE_NMS_CAP // 2 else 0
                 elif self.params.nms_path == 4 and most <= PER_IMAGE_NMS_CAP // 2:
+                    _nms_path_hint.pop(self.hint_key, None)
+                elif self.params.nms_path == 2 and _nms_path_hint.get(self.hint_key) == 2 and most <= PER_IMAGE_NMS_CAP_LEAN // 2:
                     _nms_path_hint.pop(self.hint_key, None)
             if int(h[1]) & _lib.STATUS_MASK_SPACE:
                 # neither the overlap-edge list nor the dense bit matrix fitted.  The per-image survivor counts are
