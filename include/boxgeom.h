@@ -104,6 +104,12 @@ typedef struct {
     int32_t throughput;         /* 0: tuned for the latency of one batch (helper CTA per image while the GPU has room, the NMS
                                  * kernel launched programmatically behind the decode kernel); 1: tuned for several batches in
                                  * flight on different streams (one NMS CTA per image, plain stream-ordered launches) */
+    void *nms_stream;           /* optional (NULL = everything on `stream`): a second stream of the caller for the NMS kernels,
+                                 * normally one of higher priority, so that the block scheduler places the few NMS CTAs of a
+                                 * batch ahead of the pending decode CTAs of the batches behind it.  The library orders the two
+                                 * with nms_event: decode on `stream` -> event -> NMS on nms_stream -> event -> `stream` (which
+                                 * therefore still sees the finished batch; no host synchronisation) */
+    void *nms_event;            /* cudaEvent_t of the caller (timing disabled is fine), required with nms_stream */
 } bg_detect_params;
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);

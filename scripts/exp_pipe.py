@@ -17,6 +17,7 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--size", type=int, default=640)
 ap.add_argument("--lean", default="0,1")
 ap.add_argument("--stages", type=int, default=1)
+ap.add_argument("--prio", default="1")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 B, S, C = args.batch, args.size, 80
@@ -30,8 +31,8 @@ for raws in sets:
 print("survivors/img %.0f max %d, kept %d" % (float(d.candidates.float().mean()), int(d.candidates.max()), ref[1][0].shape[0]))
 for lean in [bool(int(x)) for x in args.lean.split(",")]:
     ops.LEAN_NMS = lean
-    for depth in [int(x) for x in args.depths.split(",")]:
-        pipe = ops.DetectPipeline(shapes, anc, (S, S), C, dev, None, 0.65, 0.001, 4, None, depth=depth)
+    for prio, depth in [(bool(int(p)), int(x)) for p in args.prio.split(",") for x in args.depths.split(",")]:
+        pipe = ops.DetectPipeline(shapes, anc, (S, S), C, dev, None, 0.65, 0.001, 4, None, depth=depth, nms_priority=prio)
         for it in range(3):
             for _ in range(depth):
                 pipe.submit(sets[it & 1])
@@ -46,7 +47,7 @@ for lean in [bool(int(x)) for x in args.lean.split(",")]:
         torch.cuda.synchronize()
         out = []
         for K in [int(x) for x in args.steps.split(",")]:
-            best = 1e9
+            best, tot = 1e9, 0.0
             for _r in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
@@ -57,8 +58,9 @@ for lean in [bool(int(x)) for x in args.lean.split(",")]:
                 e1.record()
                 torch.cuda.synchronize()
                 best = min(best, e0.elapsed_time(e1) / K)
-            out.append("K=%d: %.1f us" % (K, best * 1e3))
-        print("lean=%d path=%d depth=%d  %s" % (lean, pipe.plans[0].params.nms_path, depth, "  ".join(out)), flush=True)
+                tot += e0.elapsed_time(e1) / K / 3
+            out.append("K=%d: best %.1f mean %.1f us" % (K, best * 1e3, tot * 1e3))
+        print("lean=%d prio=%d path=%d depth=%d  %s" % (lean, prio, pipe.plans[0].params.nms_path, depth, "  ".join(out)), flush=True)
 
 if not args.stages:
     sys.exit(0)

@@ -340,10 +340,11 @@ def test_detect_lean_kernel_steps_up(ops):
     ops._nms_path_hint.clear()
 
 
-@pytest.mark.parametrize("depth", [1, 3])
-def test_detect_pipeline_matches_single_stream(ops, depth):
-    """ops.DetectPipeline (batches in flight on several streams, own scratch each) returns, batch by batch,
-    exactly the rows of a single-stream plan -- also when a slot is reused and when inputs differ per batch."""
+@pytest.mark.parametrize("depth,prio", [(1, True), (3, True), (3, False)])
+def test_detect_pipeline_matches_single_stream(ops, depth, prio):
+    """ops.DetectPipeline (batches in flight on several streams, own scratch each; the lean NMS kernel, on a second,
+    higher-priority stream per slot when `prio`) returns, batch by batch, exactly the rows of a single-stream plan --
+    also when a slot is reused and when inputs differ per batch."""
     B, H, W, C = 8, 640, 640, 80
     anc = [synth.anchors_tensor(s) for s in synth.SCALES]
     batches = [[dev(r) for r in synth.raw_head_outputs(B, H, W, C, "T", seed=20 + i)] for i in range(5)]
@@ -352,7 +353,10 @@ def test_detect_pipeline_matches_single_stream(ops, depth):
     for raws in batches:
         d = ops.detect(raws, anc, (H, W), C, iou_threshold=0.65, score_threshold=0.001, box_allowance=4, tracked_classes=[0, 3, 17])
         ref.append([t.clone() for t in (d.pred_boxes, d.sample_idxs, d.keep_idxs, d.counts)])
-    pipe = ops.DetectPipeline(shapes, anc, (H, W), C, torch.device("cuda", 0), None, 0.65, 0.001, 4, [0, 3, 17], depth=depth)
+    pipe = ops.DetectPipeline(shapes, anc, (H, W), C, torch.device("cuda", 0), None, 0.65, 0.001, 4, [0, 3, 17], depth=depth,
+                              nms_priority=prio)
+    assert (pipe.plans[0].params.nms_stream is not None) == (prio and depth > 1)
+    assert pipe.plans[0].params.nms_path == (5 if depth > 1 else 0)
     slots = {}
     for i, raws in enumerate(batches):
         slot = pipe.submitted % pipe.depth

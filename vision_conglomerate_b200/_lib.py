@@ -49,6 +49,8 @@ class DetectParams(C.Structure):
         ("nms_path", C.c_int32),
         ("extra_cols", C.c_int32),
         ("throughput", C.c_int32),
+        ("nms_stream", C.c_void_p),
+        ("nms_event", C.c_void_p),
     ]
 
 

@@ -453,6 +453,27 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
     }
     if (prof) { cudaEventRecord(g_prof_stop, st); g_prof_start = g_prof_stop = nullptr; }
 
+    // the NMS kernels on the caller's second (higher-priority) stream, ordered behind the decode by the caller's event
+    cudaStream_t st_dec = st;
+    const bool two_streams = pp->nms_stream != nullptr && pp->nms_event != nullptr;
+    if (two_streams) {
+        if (cudaEventRecord((cudaEvent_t)pp->nms_event, st) != cudaSuccess ||
+            cudaStreamWaitEvent((cudaStream_t)pp->nms_stream, (cudaEvent_t)pp->nms_event, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return BG_ERR_LAUNCH;
+        }
+        st = (cudaStream_t)pp->nms_stream;
+    }
+    auto rejoin = [&]() -> int {   // `stream` continues behind the NMS kernels
+        if (!two_streams) return BG_OK;
+        if (cudaEventRecord((cudaEvent_t)pp->nms_event, st) != cudaSuccess ||
+            cudaStreamWaitEvent(st_dec, (cudaEvent_t)pp->nms_event, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return BG_ERR_LAUNCH;
+        }
+        return BG_OK;
+    };
+
     if (path == 0) {
         // ---- one CTA per image: sort, grid-pruned pair tests, greedy resolution, rows ----
         ImgNmsK q;
@@ -493,7 +514,8 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             // (throughput mode: CTAs resident early would hold SMs the other streams' decode kernels can use)
-            cfg.attrs = at; cfg.numAttrs = (pdl && !pp->throughput) ? 1 : 0;
+            static const bool lean_pdl = []() { const char *e = getenv("BG_LEAN_PDL"); return e && e[0] == '1'; }();
+            cfg.attrs = at; cfg.numAttrs = (pdl && !two_streams && (!pp->throughput || (lean && lean_pdl))) ? 1 : 0;
             const cudaError_t le = lean    ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLean>, q)
                                    : large ? cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsLarge>, q)
                                            : cudaLaunchKernelEx(&cfg, image_nms_kernel<InmsSmall>, q);
@@ -509,7 +531,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
                                                                            reinterpret_cast<long long *>(out_keep), out_counts);
             BG_LAUNCH_CHECK();
         }
-        return BG_OK;
+        return rejoin();
     }
 
     // ---- general path: segmented engine over the compacted survivor lists ----
@@ -529,7 +551,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
     detect_output_kernel<<<dim3(pp->B > 256 ? 1 : 8, go), 256, 0, st>>>(p, k, pp->order, p.seg_count, nullptr, nullptr, out_boxes, reinterpret_cast<long long *>(out_img),
                                                                    reinterpret_cast<long long *>(out_keep), out_counts);
     BG_LAUNCH_CHECK();
-    return BG_OK;
+    return rejoin();
 }
 
 extern "C" {

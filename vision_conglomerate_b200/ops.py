@@ -261,6 +261,19 @@ class DetectPlan:
             return 2 if throughput else 0
         return 4 if hint == 4 else 1
 
+    def use_nms_stream(self, stream: Optional["torch.cuda.Stream"]) -> None:
+        """Run the NMS kernels on ``stream`` (normally one of higher priority than the stream ``enqueue`` is called on),
+        ordered behind the decode kernel and in front of whatever follows on the enqueueing stream by an event of the
+        plan (``bg_detect_params.nms_stream`` / ``nms_event``).  ``None`` switches it off."""
+        if stream is None:
+            self.params.nms_stream, self.params.nms_event, self._nms_keep = None, None, None
+            return
+        ev = torch.cuda.Event()
+        with torch.cuda.device(self.dev):
+            ev.record(stream)            # torch creates the cudaEvent lazily
+        self._nms_keep = (stream, ev)
+        self.params.nms_stream, self.params.nms_event = stream.cuda_stream, ev.cuda_event
+
     def enqueue(self, raws) -> None:
         """``raws``: the three head tensors, or (``predecoded`` plans) the one decoded ``[B, N, 5+C]`` tensor."""
         with _on(self.dev):
@@ -428,17 +441,22 @@ class DetectPipeline:
 
     def __init__(self, shapes, anchors3, input_shape, num_classes, device, og_size=None, iou_threshold=0.5,
                  score_threshold=0.1, box_allowance=None, tracked_classes=None, order="image", variant=0,
-                 depth: int = 4):
+                 depth: int = 4, nms_priority: bool = True):
         if depth < 1:
             raise RuntimeError("DetectPipeline: depth must be at least 1")
         self.depth = int(depth)
         self.plans = []
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.depth)]
+        # the NMS kernels of a batch go to a second, higher-priority stream: the block scheduler then places the batch's few
+        # NMS CTAs (which fit next to resident decode CTAs) ahead of the pending decode CTAs of the batches behind it
+        self.nms_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in range(self.depth)] if nms_priority and self.depth > 1 else []
         for i in range(self.depth):
             pl = DetectPlan(shapes, anchors3, input_shape, num_classes, device, og_size, iou_threshold, score_threshold,
                             box_allowance, tracked_classes, order, variant, "auto", False, throughput=self.depth > 1)
             pl.ws_tag = "detect/pipe%d" % i
+            if self.nms_streams:
+                pl.use_nms_stream(self.nms_streams[i])
             self.plans.append(pl)
-        self.streams = [torch.cuda.Stream(device=device) for _ in range(self.depth)]
         self.submitted = 0
 
     def submit(self, raws) -> int:
