@@ -275,6 +275,45 @@ int bg_loss_bwd(const bg_head_ptrs in[3] /*host*/, const bg_loss_params *p /*hos
  * the forward kernels queue behind it, a fill kernel small enough to leave them room writes at 1-2 TB/s) */
 int bg_loss_clear_grads(const bg_loss_params *p /*host*/, const bg_head_grads grads[3] /*host*/, void *stream);
 
+/* ------------------------------------------------------------------ f2
+ * The mask term of SegmentationLoss (modules/segmentation_loss.py:26-75,147-171,208-231) for overlap_masks=True and
+ * BCEWithLogits, added to the detection terms that bg_loss_fwd / bg_loss_bwd compute from the same prediction tensors
+ * (BG_LOSS_DECODED with extra_cols >= K: the mask coefficients are the first K columns after the box columns):
+ *     loss = detection loss + seg_w * sum_s scale_w[s] * seg_loss_s      (:57-58)
+ * seg_loss_s / dice_score_s as in :147-171 with segmentation_metrics (:208-231), compute_dice_score and crop_section
+ * (utils/utils.py:130-172); the masks are nearest-resized to the protos' size like F.interpolate (:152-153).
+ * Call order: bg_loss_fwd, then bg_seg_loss_fwd with the same out_loss (it adds its term); bg_loss_bwd, then
+ * bg_seg_loss_bwd with the same gradient tensors (it adds to their coefficient columns) -- all on one stream.
+ */
+typedef struct {
+    int32_t B, C, na, K;        /* K mask coefficients: 8, 16 or 32 */
+    int32_t extra_cols;         /* rows are 5 + C + extra_cols floats, extra_cols >= K */
+    int32_t ny[3], nx[3];
+    float anchors[3][BG_MAX_ANCHORS][2];
+    float anchor_t, edge_t;
+    int32_t Hp, Wp;             /* protos [B, K, Hp, Wp] */
+    int32_t Hm, Wm;             /* target_masks [B, Hm, Wm] f32: 1 + position of the covering object inside its image */
+    float scale_w[3];
+    float seg_w;
+    int64_t nt;
+} bg_seg_params;
+
+size_t bg_sizeof_seg_params(void);
+size_t bg_seg_loss_workspace_bytes(const bg_seg_params *p /*host*/);
+/*   preds[3] (host array of device pointers) [B,ny,nx,na,5+C+extra]; targets [nt,6]; protos; target_masks.
+ *   inout_loss [1] f32: the detection loss on entry, the segmentation loss on return.
+ *   out_scalars [3,2] f64: (seg_loss, dice_score) per scale.  out_status [1] i32: 1 if the per-image target counts for
+ *   image ids 0..B-1 do not add up to nt (the reference raises, detection_dataset.py:151-157).
+ *   The workspace keeps what bg_seg_loss_bwd needs.  Nine launches, no host synchronisation. */
+int bg_seg_loss_fwd(const float *const preds[3] /*host*/, const float *targets, const float *protos, const float *target_masks,
+                    const bg_seg_params *p /*host*/, float *inout_loss, double *out_scalars, int32_t *out_status,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/*   grad_preds[3]: the dense gradients bg_loss_bwd has written (zeros in the extra columns): the mask term's
+ *   d loss / d coefficients is ADDED to the matched rows.  grad_protos [B,K,Hp,Wp]: every element written. */
+int bg_seg_loss_bwd(const float *const preds[3] /*host*/, const float *protos, const float *target_masks,
+                    const bg_seg_params *p /*host*/, const float *grad_out_dev, float *const grad_preds[3] /*host*/,
+                    float *grad_protos, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Image-sharded training: per-shard sums that add up over the shards, and the big-batch loss from the
  * summed terms.  pack15 [3,5] f64 per scale = {lbox*M, lconf*cells, lcls*M*C, M, cells}; the caller all-reduces (SUM)
  * the 15 doubles between the two calls (NCCL).  cells3: host int64[3], this shard's B*ny*nx*na per scale.

@@ -289,6 +289,42 @@ def gen_ratio(ns):
     save("ratio", wh=wh.numpy(), anchors=anc.numpy(), score=np.array(s1), extras=np.array(s2), extras_x3_t2=np.array(s3))
 
 
+SEG_LOSS_CASES = {
+    # name: (B, H, W, C, K, G, seed, mask_div, fixed)
+    "segloss_sq64": (2, 64, 64, 5, 8, 6, 3, 1, False),        # masks 64x64 -> nearest-resized to the 32x32 protos
+    "segloss_rect": (3, 96, 64, 80, 32, 4, 5, 2, False),      # masks already at the protos' size, 32 coefficients
+    "segloss_128": (2, 128, 128, 80, 32, 12, 7, 1, True),
+    "segloss_empty_img": (3, 64, 64, 5, 8, 3, 9, 1, False),   # (image 1 loses its targets below)
+}
+
+
+def gen_seg_loss(ns):
+    """``SegmentationLoss.forward`` + backward (modules/segmentation_loss.py:26-231, overlap_masks=True, BCE) on seeded
+    inputs: loss, the metrics dict, and the gradients with respect to the three prediction tensors and the protos."""
+    torch.set_num_threads(1)
+    cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+    for name, (B, H, W, C, K, G, seed, mdiv, fixed) in SEG_LOSS_CASES.items():
+        preds, protos, t, masks = synth.seg_inputs(B, H, W, C, K, G, seed, mdiv, fixed)
+        if name == "segloss_empty_img":
+            keep = t[:, 0] != 1
+            t = t[keep].contiguous()
+        preds = [p.requires_grad_(True) for p in preds]
+        protos.requires_grad_(True)
+        mod = ns.SegmentationLoss(ns.FakeSegModel(C, synth.ANCHORS, K), overlap_masks=True, **cfg)
+        if name == "segloss_empty_img":
+            # the reference numbers the overlapped masks by the per-image counts for ids 0..B-1 (detection_dataset.py:151-154)
+            pass
+        loss, metrics = mod(tuple(preds), t.clone(), protos, masks.clone())
+        loss.backward()
+        kw = dict(params=np.array([B, H, W, C, K, G, seed, mdiv, int(fixed)]), in_digest=np.array(digest(t, protos, masks, *preds)),
+                  loss=np.array(loss.item(), np.float64), metric_keys=np.array(list(metrics.keys())),
+                  metric_vals=np.array([float(v) for v in metrics.values()], np.float64),
+                  grad_protos=protos.grad.numpy())
+        for sc, p in zip(synth.SCALES, preds):
+            kw["grad_" + sc] = p.grad.numpy()
+        save(name, **kw)
+
+
 if __name__ == "__main__":
     ns = ref_harness.load()
     gen_decode_post(ns)
@@ -300,4 +336,5 @@ if __name__ == "__main__":
     gen_loss(ns)
     gen_loss(ns, raw=True)
     gen_ratio(ns)
+    gen_seg_loss(ns)
     print("torch", torch.__version__, "torchvision", torchvision.__version__)

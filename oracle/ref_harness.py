@@ -97,7 +97,17 @@ def load():
         _bbox_to_size = DetectionNet._bbox_to_size
         _make_2dgrid = DetectionNet._make_2dgrid
 
-    ns = types.SimpleNamespace(DetectionNet=DetectionNet, DetectionLoss=DetectionLoss, EffiDecHead=EffiDecHead,
+    from modules.segmentation_loss import SegmentationLoss
+
+    class FakeSegModel(FakeModel):
+        """What SegmentationLoss reads from its model on top of FakeModel: proto_seg_module.out_channels
+        (modules/segmentation_loss.py:101)."""
+        def __init__(self, num_classes, anchors, num_masks):
+            super().__init__(num_classes, anchors)
+            self.proto_seg_module = types.SimpleNamespace(out_channels=num_masks)
+
+    ns = types.SimpleNamespace(SegmentationLoss=SegmentationLoss, FakeSegModel=FakeSegModel,
+                               DetectionNet=DetectionNet, DetectionLoss=DetectionLoss, EffiDecHead=EffiDecHead,
                                DetectionDataset=DetectionDataset, inference_det=inference_det,
                                make_anchors=make_anchors, utils=ref_utils, FakeModel=FakeModel,
                                DecodeOnly=DecodeOnly)

@@ -971,3 +971,70 @@ def test_ratio_metrics(ops):
     assert_close(np.array(s), g["extras"], rtol=1e-5)
     assert_close(ops.ratio_metrics(g["anchors"], dev(g["wh"]), 4.0), float(g["score"]), rtol=1e-5)
     assert_close(np.array(ops.ratio_metrics_w_extras(g["anchors"], dev(g["wh"]) * 3.0, 2.0)), g["extras_x3_t2"], rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ f2: SegmentationLoss
+def _seg_case(ops, preds, protos, t, masks, C, K, cfg):
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    gp = [dev(p).requires_grad_(True) for p in preds]
+    pr = dev(protos).requires_grad_(True)
+    loss, metrics = ops.segmentation_loss(gp, dev(t), pr, dev(masks), anc, cfg, C, K)
+    loss.backward()
+    return loss, metrics, [p.grad.cpu().numpy() for p in gp], pr.grad.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["segloss_sq64", "segloss_rect", "segloss_128", "segloss_empty_img"])
+def test_segmentation_loss_golden(ops, name):
+    """SegmentationLoss.forward + backward on the CUDA path (fused detection terms + the mask-term kernels)
+    against the UNMODIFIED reference (modules/segmentation_loss.py:26-231, overlap_masks=True): loss rtol 1e-5, the twelve
+    metrics, gradients with respect to the three prediction tensors and the protos rtol 1e-4."""
+    from tests.util import seg_loss_case
+    g = golden(name)
+    preds, protos, t, masks, C, K = seg_loss_case(name, g)
+    cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+    loss, metrics, grads, gpr = _seg_case(ops, preds, protos, t, masks, C, K, cfg)
+    assert_close(float(loss), float(g["loss"]), rtol=1e-5, atol=0, what="loss vs reference")
+    ref_m = dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"]))
+    assert set(metrics) == set(ref_m)
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for sc, gr in zip(synth.SCALES, grads):
+        assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
+    assert_close(gpr, g["grad_protos"], rtol=1e-4, atol=1e-8, what="grad protos")
+
+
+@pytest.mark.parametrize("B,S,C,K,G,mdiv,seg_w", [(4, 256, 80, 32, 10, 1, 1.0), (5, 160, 7, 16, 40, 2, 0.7), (16, 320, 80, 32, 20, 1, 1.0)])
+def test_segmentation_loss_vs_oracle(ops, B, S, C, K, G, mdiv, seg_w):
+    """Larger shapes against the oracle (oracle/seg_oracle.py, itself pinned to the reference by the fixtures): several
+    match groups per image (more than 32 matches), pixel counts that are not multiples of the tile, 16 coefficients, a
+    weight other than 1, duplicate cells."""
+    from oracle import seg_oracle as SO
+    preds, protos, t, masks = synth.seg_inputs(B, S, S, C, K, G, seed=21, mask_div=mdiv)
+    cfg = dict(synth.LOSS_CONFIG, seg_w=seg_w, scale_w=[5.0, 2.0, 1.0])
+    anc = [synth.anchors_tensor(s).numpy() for s in synth.SCALES]
+    ref_loss, ref_m, ref_g, ref_gp = SO.segmentation_loss([p.numpy() for p in preds], t.numpy(), protos.numpy(), masks.numpy(),
+                                                          anc, cfg, C, K, with_grad=True)
+    loss, metrics, grads, gpr = _seg_case(ops, preds, protos, t, masks, C, K, cfg)
+    assert_close(float(loss), ref_loss, rtol=1e-5, atol=0, what="loss")
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for a, b in zip(grads, ref_g):
+        assert_close(a, b, rtol=1e-4, atol=1e-8, what="grad preds")
+    assert_close(gpr, ref_gp, rtol=1e-4, atol=1e-9, what="grad protos")
+
+
+def test_segmentation_loss_twice_and_scaled(ops):
+    """Two forwards before their backwards (own workspaces), and an upstream gradient other than 1."""
+    from tests.util import seg_loss_case
+    g = golden("segloss_sq64")
+    preds, protos, t, masks, C, K = seg_loss_case("segloss_sq64", g)
+    cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    gp = [dev(p).requires_grad_(True) for p in preds]
+    pr = dev(protos).requires_grad_(True)
+    l1, _ = ops.segmentation_loss(gp, dev(t), pr, dev(masks), anc, cfg, C, K, with_metrics=False)
+    l2, _ = ops.segmentation_loss([p * 1.0 for p in gp], dev(t), pr * 1.0, dev(masks), anc, cfg, C, K, with_metrics=False)
+    (l1 * 0.5 + l2 * 1.5).backward()
+    for sc, p in zip(synth.SCALES, gp):
+        assert_close(p.grad.cpu().numpy(), 2.0 * g["grad_" + sc], rtol=1e-4, atol=2e-7, what="grad " + sc)
+    assert_close(pr.grad.cpu().numpy(), 2.0 * g["grad_protos"], rtol=1e-4, atol=2e-8, what="grad protos")

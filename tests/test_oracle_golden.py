@@ -189,3 +189,26 @@ def test_ratio_metrics():
     assert_close(s[0], float(g["score"]), rtol=1e-5)
     assert_close(np.array(s), g["extras"], rtol=1e-5)
     assert_close(np.array(O.ratio_metrics(g["anchors"], g["wh"] * 3.0, 2.0)), g["extras_x3_t2"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["segloss_sq64", "segloss_rect", "segloss_128", "segloss_empty_img"])
+def test_segmentation_loss(name):
+    """the numpy restatement of SegmentationLoss.forward (oracle/seg_oracle.py: detection terms from the C
+    oracle + the mask term) against the unmodified reference's loss, metrics and gradients with respect to the three
+    prediction tensors and the protos (modules/segmentation_loss.py:26-231, overlap_masks=True)."""
+    from oracle import seg_oracle as SO
+    from tests.util import seg_loss_case
+    g = golden(name)
+    preds, protos, t, masks, C, K = seg_loss_case(name, g)
+    assert digest(t, protos, masks, *preds) == str(g["in_digest"])
+    anc = [synth.anchors_tensor(s).numpy() for s in synth.SCALES]
+    cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+    loss, metrics, grads, gp = SO.segmentation_loss([p.numpy() for p in preds], t.numpy(), protos.numpy(), masks.numpy(), anc, cfg,
+                                                    C, K, with_grad=True)
+    assert_close(loss, float(g["loss"]), rtol=1e-5, atol=0, what="loss")
+    ref_m = dict(zip((str(k) for k in g["metric_keys"]), g["metric_vals"]))
+    for k, v in ref_m.items():
+        assert_close(metrics[k], v, rtol=2e-5, atol=1e-7, what=k)
+    for sc, gr in zip(synth.SCALES, grads):
+        assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
+    assert_close(gp, g["grad_protos"], rtol=1e-4, atol=1e-8, what="grad protos")

@@ -75,3 +75,13 @@ def rows_order(rows, img):
     if r.shape[0] == 0:
         return np.zeros(0, dtype=np.int64)
     return np.lexsort((r[:, 5], r[:, 4], r[:, 3], r[:, 2], r[:, 1], -r[:, 0], np.asarray(img)))
+
+
+def seg_loss_case(name, g):
+    """Inputs of a tests/golden/segloss_*.npz case (oracle/make_golden.py gen_seg_loss): preds, protos, targets, masks, C, K."""
+    from vision_conglomerate_b200 import synth
+    B, H, W, C, K, G, seed, mdiv, fixed = (int(v) for v in g["params"])
+    preds, protos, t, masks = synth.seg_inputs(B, H, W, C, K, G, seed, mdiv, bool(fixed))
+    if name == "segloss_empty_img":
+        t = t[t[:, 0] != 1].contiguous()
+    return preds, protos, t, masks, C, K

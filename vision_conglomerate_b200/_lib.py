@@ -29,6 +29,7 @@ SYMBOLS = (
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine",
     "bg_ratio_metrics",
+    "bg_seg_loss_workspace_bytes", "bg_seg_loss_fwd", "bg_seg_loss_bwd", "bg_sizeof_seg_params",
 )
 
 
@@ -67,6 +68,23 @@ class LossParams(C.Structure):
         ("extra_cols", C.c_int32),
     ]
 
+
+class SegParams(C.Structure):
+    """bg_seg_params: the mask term of SegmentationLoss on top of the fused detection loss."""
+    _fields_ = [
+        ("B", C.c_int32), ("C", C.c_int32), ("na", C.c_int32), ("K", C.c_int32),
+        ("extra_cols", C.c_int32),
+        ("ny", C.c_int32 * 3), ("nx", C.c_int32 * 3),
+        ("anchors", ((C.c_float * 2) * BG_MAX_ANCHORS) * 3),
+        ("anchor_t", C.c_float), ("edge_t", C.c_float),
+        ("Hp", C.c_int32), ("Wp", C.c_int32), ("Hm", C.c_int32), ("Wm", C.c_int32),
+        ("scale_w", C.c_float * 3),
+        ("seg_w", C.c_float),
+        ("nt", C.c_int64),
+    ]
+
+
+Ptr3 = C.c_void_p * 3
 
 LOSS_DECODED, LOSS_RAW, LOSS_RAW_SPLIT = 0, 1, 2
 LOSS_BWD_PRECLEARED = 1
@@ -148,8 +166,16 @@ def lib() -> C.CDLL:
     L.bg_loss_pack.argtypes = [vp, C.POINTER(i64), i32, vp, vp]
     L.bg_loss_combine.argtypes = [vp, C.POINTER(LossParams), vp, vp]
     L.bg_ratio_metrics.argtypes = [vp, i64, C.POINTER(f32), i32, f32, vp, vp]
+    L.bg_sizeof_seg_params.restype = sz
+    if L.bg_sizeof_seg_params() != C.sizeof(SegParams):
+        raise RuntimeError("libboxgeom.so: bg_seg_params layout differs from the ctypes binding (stale build?)")
+    L.bg_seg_loss_workspace_bytes.argtypes = [C.POINTER(SegParams)]
+    L.bg_seg_loss_workspace_bytes.restype = sz
+    L.bg_seg_loss_fwd.argtypes = [C.POINTER(vp), vp, vp, vp, C.POINTER(SegParams), vp, vp, vp, vp, sz, vp]
+    L.bg_seg_loss_bwd.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(SegParams), vp, C.POINTER(vp), vp, vp, sz, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
-                 "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics"):
+                 "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics",
+                 "bg_seg_loss_fwd", "bg_seg_loss_bwd"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

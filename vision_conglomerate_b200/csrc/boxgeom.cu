@@ -12,6 +12,7 @@
 #include "imgnms_kernels.cuh"
 #include "train_kernels.cuh"
 #include "loss_kernels.cuh"
+#include "seg_kernels.cuh"
 
 namespace bg {
 
@@ -285,6 +286,7 @@ void bg_profile_decode_cycles(void *dev_buf) { g_prof_cycles = (unsigned long lo
 int bg_profile_stamps_per_image(void) { return INMS_STAMPS; }
 size_t bg_sizeof_detect_params(void) { return sizeof(bg_detect_params); }
 size_t bg_sizeof_loss_params(void) { return sizeof(bg_loss_params); }
+size_t bg_sizeof_seg_params(void) { return sizeof(bg_seg_params); }
 
 // ------------------------------------------------------------------------------------------ B4
 size_t bg_batched_nms_workspace_bytes(int64_t n, int64_t max_groups, size_t mask_bytes)
@@ -1046,6 +1048,189 @@ int bg_loss_bwd(const bg_head_ptrs in[3], const bg_loss_params *p, const float *
     }
     if (k.C == 80) return launch_after(loss_bwd_rows_kernel<80>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
     return launch_after(loss_bwd_rows_kernel<0>, dim3(sms * 8, 3), dim3(LOSS_THREADS), 0, st, k);
+}
+
+// ------------------------------------------------------------------------------------------ f2: mask term of SegmentationLoss
+}  // extern "C" (templates below)
+namespace {
+
+struct SegWs {
+    u64 *chain[3];
+    int *tmask_of_target, *block_start;
+    int *count;          // [3] matches per scale, [3] = status of the mask numbering
+    int *cell[3];
+    float4 *box[3];
+    long long *tmask[3];
+    int *cnt, *off;
+    SegEntry *list;
+    float4 *mstat;
+    double *img_s;
+    float *part;
+    size_t zero_begin, zero_bytes;
+    int G;
+    long long cap_s, cap;
+};
+
+bool seg_valid(const bg_seg_params *p)
+{
+    if (!p || p->B <= 0 || p->C <= 0 || p->na <= 0 || p->na > BG_MAX_ANCHORS || p->nt < 0) return false;
+    if (p->K != 8 && p->K != 16 && p->K != 32) return false;
+    if (p->extra_cols < p->K || p->extra_cols > 4096) return false;
+    if (p->Hp <= 0 || p->Wp <= 0 || p->Hm <= 0 || p->Wm <= 0 || (long long)p->Hp * p->Wp >= (1ll << 30)) return false;
+    if (15ll * p->na * p->nt >= (1ll << 31)) return false;
+    for (int s = 0; s < 3; ++s) {
+        if (p->ny[s] <= 0 || p->nx[s] <= 0) return false;
+        if ((long long)p->B * p->ny[s] * p->nx[s] * p->na >= (1ll << 31)) return false;
+    }
+    return true;
+}
+
+size_t seg_carve(unsigned char *base, const bg_seg_params *p, SegWs &w)
+{
+    Bump b{base, 0};
+    memset(&w, 0, sizeof(w));
+    w.cap_s = 5ll * p->na * p->nt;
+    w.cap = 3 * w.cap_s;
+    const size_t words = assign_chain_words(p->nt, p->na);
+    w.zero_begin = align_up(b.off, 256);
+    for (int s = 0; s < 3; ++s) w.chain[s] = b.take<u64>(words);
+    w.count = b.take<int>(4);
+    w.zero_bytes = b.off - w.zero_begin;
+    w.tmask_of_target = b.take<int>((size_t)p->nt + 1);
+    w.block_start = b.take<int>((size_t)p->B + 2);
+    for (int s = 0; s < 3; ++s) {
+        w.cell[s] = b.take<int>((size_t)w.cap_s + 1);
+        w.box[s] = b.take<float4>((size_t)w.cap_s + 1);
+        w.tmask[s] = b.take<long long>((size_t)w.cap_s + 1);
+    }
+    w.cnt = b.take<int>(4 * (size_t)p->B);
+    w.off = b.take<int>((size_t)p->B + 1);
+    w.list = b.take<SegEntry>((size_t)w.cap + 1);
+    w.mstat = b.take<float4>((size_t)w.cap + 1);
+    w.img_s = b.take<double>(6 * (size_t)p->B);
+    // pixel groups per image: enough CTAs for two waves of the GPU, bounded by the tiles there are and by 64 MB of partials
+    const int tiles = (int)(((long long)p->Hp * p->Wp + SEG_THREADS - 1) / SEG_THREADS);
+    int G = (2 * num_sms() + p->B - 1) / p->B;
+    G = G < 1 ? 1 : (G > tiles ? tiles : G);
+    while (G > 1 && (size_t)G * w.cap * p->K * 4 > ((size_t)64 << 20)) --G;
+    w.G = G;
+    w.part = b.take<float>((size_t)G * (w.cap + 1) * (p->K > SEG_FWD_Q ? p->K : SEG_FWD_Q));
+    return align_up(b.off, 256);
+}
+
+void seg_fill_k(SegK &k, const bg_seg_params *p, const SegWs &w, const float *const preds[3], const float *protos, const float *masks)
+{
+    memset(&k, 0, sizeof(k));
+    k.B = p->B; k.K = p->K; k.D = 5 + p->C + p->extra_cols; k.coef_off = 5 + p->C;
+    k.Hp = p->Hp; k.Wp = p->Wp; k.HW = p->Hp * p->Wp; k.Hm = p->Hm; k.Wm = p->Wm;
+    k.sy = (float)p->Hm / (float)p->Hp; k.sx = (float)p->Wm / (float)p->Wp;
+    for (int s = 0; s < 3; ++s) {
+        k.preds[s] = preds[s];
+        k.cells_per_img[s] = p->ny[s] * p->nx[s] * p->na;
+        k.cell[s] = w.cell[s]; k.box[s] = w.box[s]; k.tmask[s] = w.tmask[s]; k.count[s] = w.count + s;
+        k.scale_w[s] = p->scale_w[s];
+    }
+    k.seg_w = p->seg_w;
+    k.protos = protos; k.masks = masks;
+    k.cap_s = (int)w.cap_s; k.cap = (int)w.cap; k.G = w.G;
+    k.cnt = w.cnt; k.off = w.off; k.list = w.list; k.mstat = w.mstat; k.img_s = w.img_s; k.part = w.part;
+}
+
+template <int K>
+int seg_launch_fwd(const SegK &k, cudaStream_t st)
+{
+    seg_fwd_kernel<K><<<dim3(k.G, k.B), SEG_THREADS, SegTile<K>::BYTES, st>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+template <int K>
+int seg_launch_bwd(const SegK &k, cudaStream_t st)
+{
+    seg_bwd_coef_kernel<K><<<dim3(k.G, k.B), SEG_THREADS, SegTile<K>::BYTES, st>>>(k);
+    BG_LAUNCH_CHECK();
+    seg_bwd_protos_kernel<K><<<dim3((k.HW + SEG_THREADS - 1) / SEG_THREADS, k.B), SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+}  // namespace
+extern "C" {
+
+size_t bg_seg_loss_workspace_bytes(const bg_seg_params *p)
+{
+    if (!seg_valid(p)) return 0;
+    SegWs w;
+    return seg_carve(nullptr, p, w);
+}
+
+int bg_seg_loss_fwd(const float *const preds[3], const float *targets, const float *protos, const float *target_masks,
+                    const bg_seg_params *p, float *inout_loss, double *out_scalars, int32_t *out_status, void *workspace,
+                    size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!seg_valid(p) || !preds || !preds[0] || !preds[1] || !preds[2] || !protos || !target_masks || !inout_loss ||
+        !out_scalars || !out_status || !workspace)
+        return BG_ERR_INVALID;
+    if (p->nt > 0 && !targets) return BG_ERR_INVALID;
+    SegWs w;
+    if (seg_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
+    if (cudaMemsetAsync((unsigned char *)workspace + w.zero_begin, 0, w.zero_bytes, st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (cudaMemsetAsync(out_status, 0, sizeof(int32_t), st) != cudaSuccess) return BG_ERR_LAUNCH;
+    if (p->nt > 0) {
+        // mask numbering of the targets (detection_dataset.py:146-157), then the three scales' matches in one launch
+        assign_tmask_kernel<<<1, 1024, 0, st>>>(targets, 6, p->nt, 1, p->B, w.tmask_of_target, w.block_start, out_status);
+        BG_LAUNCH_CHECK();
+        Assign3K kk;
+        for (int s = 0; s < 3; ++s) {
+            AssignK &a = kk.a[s];
+            assign_fill(a, targets, p->nt, p->ny[s], p->nx[s], &p->anchors[s][0][0], p->na, p->anchor_t, p->edge_t);
+            a.chain = w.chain[s];
+            a.cap = w.cap_s; a.count = w.count + s;
+            a.cell = w.cell[s]; a.box = reinterpret_cast<float *>(w.box[s]);
+            a.tmask_of_target = w.tmask_of_target; a.tmask64 = w.tmask[s];
+        }
+        const int rc = assign_launch(kk, 3, st);
+        if (rc != BG_OK) return rc;
+    }
+    SegK k;
+    seg_fill_k(k, p, w, preds, protos, target_masks);
+    k.scalars = out_scalars; k.loss = inout_loss;
+    seg_count_kernel<<<p->B, SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    seg_fill_kernel<<<p->B, SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    const int rc = p->K == 32 ? seg_launch_fwd<32>(k, st) : p->K == 16 ? seg_launch_fwd<16>(k, st) : seg_launch_fwd<8>(k, st);
+    if (rc != BG_OK) return rc;
+    seg_reduce_kernel<<<p->B, SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    seg_final_kernel<<<1, SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
+int bg_seg_loss_bwd(const float *const preds[3], const float *protos, const float *target_masks, const bg_seg_params *p,
+                    const float *grad_out_dev, float *const grad_preds[3], float *grad_protos, void *workspace,
+                    size_t workspace_bytes, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!seg_valid(p) || !preds || !preds[0] || !preds[1] || !preds[2] || !protos || !target_masks || !grad_preds ||
+        !grad_preds[0] || !grad_preds[1] || !grad_preds[2] || !grad_protos || !workspace)
+        return BG_ERR_INVALID;
+    SegWs w;
+    if (seg_carve((unsigned char *)workspace, p, w) > workspace_bytes) return BG_ERR_WORKSPACE;
+    SegK k;
+    seg_fill_k(k, p, w, preds, protos, target_masks);
+    for (int s = 0; s < 3; ++s) k.gpreds[s] = grad_preds[s];
+    k.gprotos = grad_protos;
+    k.go_dev = grad_out_dev;
+    const int rc = p->K == 32 ? seg_launch_bwd<32>(k, st) : p->K == 16 ? seg_launch_bwd<16>(k, st) : seg_launch_bwd<8>(k, st);
+    if (rc != BG_OK) return rc;
+    const long long work = (long long)w.cap * p->K;
+    const int blocks = (int)(work / SEG_THREADS + 1 < 4ll * num_sms() ? work / SEG_THREADS + 1 : 4ll * num_sms());
+    seg_bwd_scatter_kernel<<<blocks, SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
 }
 
 int bg_loss_pack(const double *scalars, const int64_t *cells3, int32_t C, double *pack15, void *stream)

@@ -957,6 +957,145 @@ def detection_loss(preds3: Sequence, targets: torch.Tensor, anchors3: Sequence, 
     return (loss, metrics, scalars) if return_scalars else (loss, metrics)
 
 
+# ---------------------------------------------------------------------------------------------- f2: SegmentationLoss
+SEG_METRIC_KEYS = ("mean_ciou", "conf_loss", "seg_loss", "dice_score", "avg_pos_conf", "avg_neg_conf", "class_loss", "accuracy",
+                   "f1", "precision", "recall")
+
+
+def _seg_params(shapes, C_cls, K, extra, nt, anchors3, cfg, protos_shape, masks_shape) -> "_lib.SegParams":
+    p = _lib.SegParams()
+    B, _, _, na = shapes[0]
+    p.B, p.C, p.na, p.K, p.extra_cols = B, C_cls, na, K, extra
+    for s, sh in enumerate(shapes):
+        p.ny[s], p.nx[s] = sh[1], sh[2]
+        for a, (w, h) in enumerate(_anchors_host(anchors3[s])):
+            p.anchors[s][a][0] = w
+            p.anchors[s][a][1] = h
+    p.anchor_t, p.edge_t = float(cfg.get("anchor_t", 4.0)), float(cfg.get("edge_t", 0.5))
+    p.Hp, p.Wp = int(protos_shape[2]), int(protos_shape[3])
+    p.Hm, p.Wm = int(masks_shape[1]), int(masks_shape[2])
+    sw = cfg.get("scale_w") or [4.0, 2.0, 1.0]
+    for s in range(3):
+        p.scale_w[s] = float(sw[s])
+    p.seg_w = float(cfg.get("seg_w", 1.0))
+    p.nt = nt
+    return p
+
+
+def _ptr3(tensors) -> "C.Array":
+    return _lib.Ptr3(*(t.data_ptr() for t in tensors))
+
+
+class _SegLoss(torch.autograd.Function):
+    """``SegmentationLoss.forward`` (modules/segmentation_loss.py:26-75) on the device: the fused detection loss on the
+    prediction tensors (mask coefficients ride along as extra columns) followed by the mask term, which adds
+    ``seg_w * sum_s scale_w[s] * seg_loss_s`` to the loss.  Backward: the detection backward writes the dense gradients
+    (zeros in the coefficient columns), the mask backward adds the coefficient gradients of the matched rows and writes
+    the gradient of the protos.  Both workspaces are allocated per forward and owned by ``ctx``."""
+
+    @staticmethod
+    def forward(ctx, targets, params, sparams, scalars, hist, status, seg_scalars, seg_status, protos, masks, *tensors):
+        L = _lib.lib()
+        dev = tensors[0].device
+        with _on(dev):
+            ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
+            wss = torch.empty(L.bg_seg_loss_workspace_bytes(C.byref(sparams)), dtype=torch.uint8, device=dev)
+            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            tp = targets.data_ptr() if targets.numel() else None
+            check(L.bg_loss_fwd(_head_ptrs(tensors, False), tp, C.byref(params), scalars.data_ptr(), hist.data_ptr(),
+                                loss.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "bg_loss_fwd")
+            check(L.bg_seg_loss_fwd(_ptr3(tensors), tp, protos.data_ptr(), masks.data_ptr(), C.byref(sparams), loss.data_ptr(),
+                                    seg_scalars.data_ptr(), seg_status.data_ptr(), wss.data_ptr(), wss.numel(), _stream(dev)),
+                  "bg_seg_loss_fwd")
+        ctx.save_for_backward(protos, masks, *tensors)
+        ctx.params, ctx.sparams, ctx.ws, ctx.wss = params, sparams, ws, wss
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, go):
+        protos, masks, *tensors = ctx.saved_tensors
+        L = _lib.lib()
+        dev = tensors[0].device
+        with _on(dev):
+            grads = [torch.empty_like(x) for x in tensors]
+            gprotos = torch.empty_like(protos)
+            if go.dtype != torch.float32 or not go.is_contiguous():
+                go = go.to(torch.float32).contiguous()
+            check(L.bg_loss_bwd(_head_ptrs(tensors, False), C.byref(ctx.params), go.data_ptr(), 1.0, _head_ptrs(grads, False), 0,
+                                ctx.ws.data_ptr(), ctx.ws.numel(), _stream(dev)), "bg_loss_bwd")
+            check(L.bg_seg_loss_bwd(_ptr3(tensors), protos.data_ptr(), masks.data_ptr(), C.byref(ctx.sparams), go.data_ptr(),
+                                    _ptr3(grads), gprotos.data_ptr(), ctx.wss.data_ptr(), ctx.wss.numel(), _stream(dev)),
+                  "bg_seg_loss_bwd")
+        return (None, None, None, None, None, None, None, None, gprotos, None, *grads)
+
+
+def segmentation_loss(preds3: Sequence[torch.Tensor], targets: torch.Tensor, protos: torch.Tensor, target_masks: torch.Tensor,
+                      anchors3: Sequence, cfg: dict, num_classes: int, num_masks: int, with_metrics: bool = True):
+    """``SegmentationLoss.forward`` (modules/segmentation_loss.py:26-75) for ``overlap_masks=True``, BCE losses and no
+    keypoints.  ``preds3``: the training-mode tensors ``[B, ny, nx, na, 5 + C + K (+ more)]`` of ``SegmentationNet``;
+    ``protos [B, K, Hp, Wp]``; ``target_masks [B, Hm, Wm]`` (pixel = 1 + position of the covering object inside its image,
+    any real dtype).  Returns ``(loss, metrics_dict)`` with the reference's twelve metric keys; ``loss`` is attached to
+    autograd through ``preds3`` and ``protos``."""
+    tensors = [_req(x, f"preds[{i}]") for i, x in enumerate(preds3)]
+    if len(tensors) != 3 or any(x.dim() != 5 for x in tensors):
+        raise RuntimeError("segmentation_loss: expected three [B, ny, nx, na, 5+C+K] tensors")
+    Cc, K = int(num_classes), int(num_masks)
+    D = int(tensors[0].shape[4])
+    extra = D - 5 - Cc
+    if extra < K or any(int(x.shape[4]) != D for x in tensors):
+        raise RuntimeError("segmentation_loss: rows must hold 5 + num_classes + num_masks columns")
+    if K not in (8, 16, 32):
+        raise RuntimeError("segmentation_loss: the CUDA path handles 8, 16 or 32 mask coefficients")
+    shapes = tuple(tuple(x.shape[:4]) for x in tensors)
+    B = shapes[0][0]
+    targets = _req(targets, "targets")
+    if targets.dim() != 2 or targets.shape[1] != 6:
+        raise RuntimeError("segmentation_loss: keypoint targets are out of scope for the CUDA path")
+    protos = _req(protos, "protos")
+    if protos.dim() != 4 or protos.shape[0] != B or protos.shape[1] != K:
+        raise RuntimeError("segmentation_loss: protos must be [B, num_masks, Hp, Wp]")
+    masks = target_masks
+    if not (masks.is_cuda and masks.dim() == 3 and masks.shape[0] == B):
+        raise RuntimeError("segmentation_loss: target_masks must be a CUDA tensor [B, Hm, Wm] (overlap_masks=True)")
+    if masks.dtype != torch.float32 or not masks.is_contiguous():
+        masks = masks.to(torch.float32).contiguous()
+    dev = _same_device(*tensors, targets, protos, masks)
+    nt = int(targets.shape[0])
+    params = _loss_params(shapes, Cc, extra, nt, anchors3, cfg, _lib.LOSS_DECODED)
+    sparams = _seg_params(shapes, Cc, K, extra, nt, anchors3, cfg, protos.shape, masks.shape)
+    scalars = torch.empty(3, 8, dtype=torch.float64, device=dev)
+    hist = torch.empty(3, 3, Cc, dtype=torch.int64, device=dev)
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    seg_scalars = torch.empty(3, 2, dtype=torch.float64, device=dev)
+    seg_status = torch.empty(1, dtype=torch.int32, device=dev)
+    loss = _SegLoss.apply(targets, params, sparams, scalars, hist, status, seg_scalars, seg_status, protos, masks, *tensors)
+    if not with_metrics:
+        return loss, {}
+    host = torch.cat([scalars.reshape(-1), hist.reshape(-1).double(), seg_scalars.reshape(-1), loss.detach().double().reshape(1),
+                      status.double(), seg_status.double()]).cpu()
+    if int(host[-1]):
+        raise RuntimeError("segmentation_loss: per-image target counts do not add up to the number of targets "
+                           "(image ids outside 0..batch_size-1)")
+    if int(host[-2]):
+        raise IndexError("segmentation_loss: a target row names an image outside the batch or a class outside "
+                         "0..num_classes-1 (index out of range)")
+    sc = host[:24].reshape(3, 8)
+    hh = host[24:24 + 9 * Cc].reshape(3, 3, Cc).long()
+    ss = host[24 + 9 * Cc: 30 + 9 * Cc].reshape(3, 2)
+    rows = []
+    for s in range(3):
+        M = int(sc[s, 6])
+        m = dict(mean_ciou=float(sc[s, 3]), conf_loss=float(sc[s, 1]), seg_loss=float(ss[s, 0]), dice_score=float(ss[s, 1]),
+                 avg_pos_conf=float(sc[s, 4]), avg_neg_conf=float(sc[s, 5]), class_loss=float(sc[s, 2]) if M else float("nan"))
+        m.update(_macro_metrics(hh[s], M))
+        rows.append(m)
+    metrics = {"aggregate_loss": float(host[-3])}
+    for k in SEG_METRIC_KEYS:
+        vals = [r[k] for r in rows if r[k] == r[k]]
+        metrics[k] = sum(vals) / len(vals) if vals else float("nan")
+    return loss, metrics
+
+
 class LossStepGraph:
     """The training-loss step -- :func:`detection_loss` forward + backward, and for image-sharded runs the per-shard
     terms, their all-reduce and the big-batch loss (``shard.allreduce_loss_terms``) -- captured once in a CUDA graph

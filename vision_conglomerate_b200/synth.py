@@ -132,6 +132,33 @@ def train_preds(B: int, H: int, W: int, C: int = 80, seed: int = 1, na: int = 3)
     return [torch.randn(B, ny, nx, na, 5 + C, generator=g, dtype=torch.float32) for ny, nx in fmap_shapes(H, W)]
 
 
+def seg_inputs(B: int, H: int, W: int, C: int, K: int, G: int, seed: int = 3, mask_div: int = 1, fixed: bool = False):
+    """Seeded inputs of ``SegmentationLoss.forward`` (modules/segmentation_loss.py:26-75) with ``overlap_masks=True``:
+    training-mode prediction tensors with ``K`` mask-coefficient columns (``tanh``-ranged, detection.py:131-134),
+    ``protos [B, K, H/2, W/2]`` (modules/segmentation.py:21), targets, and the overlapped target masks
+    ``[B, H/mask_div, W/mask_div]`` whose pixels hold 1 + the position of the covering object inside its image
+    (later objects drawn over earlier ones; utils/utils.py polygons_2_overlapped_mask), here the objects' boxes."""
+    g = torch.Generator().manual_seed(seed)
+    preds = []
+    for ny, nx in fmap_shapes(H, W):
+        p = torch.randn(B, ny, nx, 3, 5 + C + K, generator=g, dtype=torch.float32)
+        p[..., 5 + C:] = torch.tanh(p[..., 5 + C:])
+        preds.append(p.contiguous())
+    protos = torch.randn(B, K, H // 2, W // 2, generator=g, dtype=torch.float32)
+    t = targets(B, G, C, seed + 1, fixed)
+    Hm, Wm = H // mask_div, W // mask_div
+    masks = torch.zeros(B, Hm, Wm, dtype=torch.float32)
+    pos = {}
+    for row in t.tolist():
+        b = int(row[0])
+        pos[b] = pos.get(b, 0) + 1
+        x, y, w, h = row[2:6]
+        x1, x2 = int(max(0.0, x - w / 2) * Wm), int(min(1.0, x + w / 2) * Wm) + 1
+        y1, y2 = int(max(0.0, y - h / 2) * Hm), int(min(1.0, y + h / 2) * Hm) + 1
+        masks[b, y1:y2, x1:x2] = float(pos[b])
+    return preds, protos, t, masks
+
+
 def nms_boxes(n: int, groups: int, seed: int = 3, extent: float = 640.0, ties: bool = False
               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Random xyxy boxes, scores and int64 group ids for stand-alone NMS tests."""
