@@ -98,6 +98,7 @@ def load():
         _make_2dgrid = DetectionNet._make_2dgrid
 
     from modules.segmentation_loss import SegmentationLoss
+    from modules.segmentation import SegmentationNet
 
     class FakeSegModel(FakeModel):
         """What SegmentationLoss reads from its model on top of FakeModel: proto_seg_module.out_channels
@@ -106,7 +107,7 @@ def load():
             super().__init__(num_classes, anchors)
             self.proto_seg_module = types.SimpleNamespace(out_channels=num_masks)
 
-    ns = types.SimpleNamespace(SegmentationLoss=SegmentationLoss, FakeSegModel=FakeSegModel,
+    ns = types.SimpleNamespace(SegmentationLoss=SegmentationLoss, FakeSegModel=FakeSegModel, SegmentationNet=SegmentationNet,
                                DetectionNet=DetectionNet, DetectionLoss=DetectionLoss, EffiDecHead=EffiDecHead,
                                DetectionDataset=DetectionDataset, inference_det=inference_det,
                                make_anchors=make_anchors, utils=ref_utils, FakeModel=FakeModel,
@@ -115,10 +116,10 @@ def load():
     return ns
 
 
-def model_config() -> dict:
-    """``model_config`` of the reference's config/detection/config.yaml (CSPBackBone + RepBiPAN + EffiDecHead)."""
+def model_config(task: str = "detection") -> dict:
+    """``model_config`` of the reference's config/{detection,segmentation}/config.yaml (CSPBackBone + RepBiPAN + EffiDecHead)."""
     import yaml
-    with open(os.path.join(REF, "config", "detection", "config.yaml")) as f:
+    with open(os.path.join(REF, "config", task, "config.yaml")) as f:
         return yaml.safe_load(f)["model_config"]
 
 

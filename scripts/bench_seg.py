@@ -1,0 +1,70 @@
+#!/usr/bin/env python
+"""SegmentationLoss forward + backward: the CUDA path (fused detection terms + mask-term kernels) against the
+unmodified reference on torch-CUDA on the same GPU (baseline/_ref), same seeded inputs.  Prints one JSON line per case."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from vision_conglomerate_b200 import _lib, ops, synth  # noqa: E402
+
+dev = torch.device("cuda", 0)
+torch.backends.cuda.matmul.allow_tf32 = False
+anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+for B, S, C, K, G in ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20)):
+    preds, protos, t, masks = synth.seg_inputs(B, S, S, C, K, G, seed=11)
+    preds = [p.to(dev).requires_grad_(True) for p in preds]
+    protos = protos.to(dev).requires_grad_(True)
+    t, masks = t.to(dev), masks.to(dev)
+
+    def ours():
+        for p in preds:
+            p.grad = None
+        protos.grad = None
+        loss, _ = ops.segmentation_loss(preds, t, protos, masks, anc, cfg, C, K, with_metrics=False)
+        loss.backward()
+        return loss
+
+    l0 = _lib.launch_count()
+    loss = ours()
+    launches = _lib.launch_count() - l0
+    ms = timed(ours, 20)
+    out = {"case": "SegmentationLoss fwd+bwd B=%d %dx%d C=%d K=%d, <=%d gt/img, protos %dx%d" % (B, S, S, C, K, G, S // 2, S // 2),
+           "ours_ms": ms, "ours_img_s": B / ms * 1e3, "loss": float(loss), "kernels_per_step": int(launches)}
+    try:
+        from oracle import ref_harness
+        ns = ref_harness.load()
+        mod = ns.SegmentationLoss(ns.FakeSegModel(C, synth.ANCHORS, K).to(dev), overlap_masks=True, **cfg)
+
+        def ref():
+            for p in preds:
+                p.grad = None
+            protos.grad = None
+            loss, _ = mod(tuple(preds), t, protos, masks)
+            loss.backward()
+            return loss
+
+        rl = float(ref())
+        rms = timed(ref, 3)
+        out.update(reference_torch_cuda_ms=rms, reference_loss=rl, speedup=rms / ms)
+    except Exception as e:  # noqa: BLE001
+        out["reference"] = repr(e)[:200]
+    print(json.dumps(out), flush=True)

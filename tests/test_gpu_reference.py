@@ -279,3 +279,58 @@ def test_ratio_metrics_patched(ns):
     assert_close(np.array(got[0], dtype=np.float64), np.array([float(v) for v in ref[0]]), rtol=1e-5)
     assert_close(float(got[1]), float(ref[1]), rtol=1e-5)
     assert float(host) == float(ref[1])
+
+
+def test_segmentation_train_step_patched_equals_unpatched(ns):
+    """SURVEY 8 f2 on the REAL classes: one training step of the unmodified SegmentationNet (19 M parameters,
+    config/segmentation/config.yaml) + SegmentationLoss (pipeline/segmentation_trainer.py:42-48) -- model forward, loss,
+    backward -- with ``dropin.install(SegmentationLoss=...)`` against the unpatched torch-CUDA run: loss, the twelve metrics,
+    every parameter gradient."""
+    from vision_conglomerate_b200 import dropin, ops
+    B, S, C = 4, 256, 5
+    torch.manual_seed(42)
+    model = ns.SegmentationNet(3, C, ref_harness.model_config("segmentation"), synth.ANCHORS, num_keypoints=0).cuda().train()
+    K = model.proto_seg_module.out_channels
+    loss_mod = ns.SegmentationLoss(model, overlap_masks=True, **dict(synth.LOSS_CONFIG, seg_w=1.0))
+    g = torch.Generator().manual_seed(3)
+    imgs = torch.rand(B, 3, S, S, generator=g).cuda()
+    # two targets per image, far apart (no duplicate cells: the reference's duplicate-index scatter on CUDA is not deterministic)
+    rows = []
+    for b in range(B):
+        rows += [[b, (2 * b) % C, 0.2 + 0.1 * b, 0.25, 0.14, 0.3], [b, (2 * b + 1) % C, 0.7, 0.6 + 0.05 * b, 0.2, 0.25]]
+    t = torch.tensor(rows, dtype=torch.float32).cuda()
+    masks = torch.zeros(B, S, S)
+    for b in range(B):
+        for j, r in enumerate(rows[2 * b: 2 * b + 2]):
+            x, y, w, h = r[2:]
+            masks[b, int((y - h / 2) * S): int((y + h / 2) * S), int((x - w / 2) * S): int((x + w / 2) * S)] = j + 1
+    masks = masks.cuda()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        (sm, md, lg), protos = model(imgs)
+        loss, metrics = loss_mod((sm, md, lg), t, protos, masks)
+        loss.backward()
+        return float(loss), metrics, _param_grads(model)
+
+    loss_u, met_u, grads_u = step()
+    calls = []
+    orig = ops.segmentation_loss
+    ops.segmentation_loss = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    dropin.install(SegmentationLoss=ns.SegmentationLoss, torchvision_ops=False)
+    try:
+        loss_p, met_p, grads_p = step()
+    finally:
+        dropin.uninstall()
+        ops.segmentation_loss = orig
+    assert calls, "the CUDA segmentation loss did not run"
+    assert K == 32
+    assert_close(loss_p, loss_u, rtol=1e-5, atol=0, what="loss")
+    assert set(met_p) == set(met_u)
+    for k in met_u:
+        assert_close(met_p[k], met_u[k], rtol=5e-5, atol=1e-6, what=k)
+    assert set(grads_p) == set(grads_u)
+    num = sum(float((grads_p[n].double() - grads_u[n].double()).pow(2).sum()) for n in grads_u)
+    den = sum(float(grads_u[n].double().pow(2).sum()) for n in grads_u)
+    print("segmentation train step: %d parameter gradients, global relative L2 error %.2e" % (len(grads_u), (num / den) ** 0.5))
+    assert (num / den) ** 0.5 < 2e-5

@@ -94,6 +94,33 @@ def _make_loss_forward(orig):
     return forward
 
 
+# ------------------------------------------------------------------------------------------------ f2
+def _make_seg_loss_forward(orig):
+    def forward(self, preds, targets, protos, target_masks):
+        """SegmentationLoss.forward (modules/segmentation_loss.py:26-75): the CUDA path covers overlap_masks=True with the
+        BCE losses and no keypoints; everything else goes to the reference's own code."""
+        model = self.model
+        K = int(getattr(getattr(model, "proto_seg_module", None), "out_channels", 0) or 0)
+        out_of_scope = (
+            (self.alpha and self.gamma) or bool(getattr(model, "num_keypoints", None)) or not self.overlap_masks
+            or self.batch_scale_loss or len(preds) != 3 or K not in (8, 16, 32)
+            or not (isinstance(targets, torch.Tensor) and targets.dim() == 2 and targets.shape[1] == 6)
+            or not all(_is_cuda_f32(p) for p in preds) or not _is_cuda_f32(protos)
+            or not (isinstance(target_masks, torch.Tensor) and target_masks.dim() == 3 and target_masks.shape[0] == preds[0].shape[0])
+            or type(self).loss_fn is not _saved.get("SegmentationLoss.loss_fn", type(self).loss_fn)
+        )
+        if out_of_scope:
+            return orig(self, preds, targets, protos, target_masks)
+        cfg = dict(anchor_t=self.anchor_t, edge_t=self.edge_t, box_w=self.box_w, conf_w=self.conf_w, class_w=self.class_w,
+                   label_smoothing=self.label_smoothing, scale_w=self.scale_w, seg_w=self.seg_w)
+        anchors3 = [model.sm_anchors.data, model.md_anchors.data, model.lg_anchors.data]
+        dev = preds[0].device
+        return ops.segmentation_loss([p if p.is_contiguous() else p.contiguous() for p in preds],
+                                     targets.to(dev, torch.float32), protos if protos.is_contiguous() else protos.contiguous(),
+                                     target_masks.to(dev), anchors3, cfg, model.num_classes, K)
+    return forward
+
+
 # ------------------------------------------------------------------------------------------------ B4
 def _make_batched_nms(orig):
     def batched_nms(boxes, scores, idxs, iou_threshold):
@@ -256,7 +283,7 @@ _options = {"fuse_train_decode": True, "split_head": True, "fuse_inference": Tru
 
 def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True, make_anchors=None,
             fuse_train_decode: bool = True, EffiDecHead=None, split_head: bool = True, inference_det=None,
-            fuse_inference: bool = True) -> None:
+            fuse_inference: bool = True, SegmentationLoss=None) -> None:
     """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
     imported in your process (any subset); ``torchvision_ops=True`` also replaces
     ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time); ``make_anchors`` is the
@@ -264,7 +291,9 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
     training-mode ``_get_scale_pred`` return a real decoded tensor (one CUDA kernel each way) instead of the
     deferred stand-in.  ``EffiDecHead`` (modules/common.py:852-931): its final ``torch.cat`` is deferred as well, so the
     loss reads the head's three conv outputs in place (zero-copy when the model runs channels-last,
-    otherwise the pieces are made contiguous -- the copy the concatenation would have been)."""
+    otherwise the pieces are made contiguous -- the copy the concatenation would have been).  ``SegmentationLoss``
+    (modules/segmentation_loss.py): its ``forward`` runs the fused detection terms plus the mask-term kernels
+    (overlap_masks=True, BCE, no keypoints -- other configurations keep the reference's code)."""
     _options["fuse_train_decode"] = bool(fuse_train_decode)
     _options["split_head"] = bool(split_head)
     _options["fuse_inference"] = bool(fuse_inference)
@@ -300,6 +329,10 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
         if "_make_2dgrid" in DetectionNet.__dict__:
             _saved["_make_2dgrid"] = (DetectionNet, DetectionNet.__dict__["_make_2dgrid"])
             DetectionNet._make_2dgrid = _make_2dgrid(DetectionNet.__dict__["_make_2dgrid"])
+    if SegmentationLoss is not None and "SegmentationLoss.forward" not in _saved:
+        _saved["SegmentationLoss.forward"] = (SegmentationLoss, SegmentationLoss.__dict__["forward"])
+        _saved["SegmentationLoss.loss_fn"] = SegmentationLoss.__dict__["loss_fn"]
+        SegmentationLoss.forward = _make_seg_loss_forward(SegmentationLoss.__dict__["forward"])
     if make_anchors is not None and "ratio_metrics" not in _saved:
         _saved["ratio_metrics"] = (make_anchors, make_anchors.ratio_metrics)
         _saved["ratio_metrics_w_extras"] = (make_anchors, make_anchors.ratio_metrics_w_extras)
@@ -320,12 +353,13 @@ def uninstall() -> None:
         if name in _saved:
             owner, orig = _saved.pop(name)
             setattr(owner, name, orig)
-    for key in ("EffiDecHead.forward", "DetectionNet.forward"):
+    for key in ("EffiDecHead.forward", "DetectionNet.forward", "SegmentationLoss.forward"):
         if key in _saved:
             owner, orig = _saved.pop(key)
             owner.forward = orig
     _detect_plans.clear()
     _saved.pop("DetectionLoss.loss_fn", None)
+    _saved.pop("SegmentationLoss.loss_fn", None)
 
 
 def installed() -> Dict[str, bool]:
