@@ -19,7 +19,7 @@ for B in (32, 64, 256):
     raw = [torch.randn(B, ny, nx, 3, 5 + C, generator=g, device=dev) for ny, nx in synth.fmap_shapes(640, 640)]
     cells = [x.shape[0] * x.shape[1] * x.shape[2] * x.shape[3] for x in raw]
     for form in ("split", "raw"):
-        for pre in ((True, False) if form == "split" else (False,)):
+        for pre in (("priority", True, False) if form == "split" else (False,)):
             ops.PRECLEAR_SPLIT_GRADS = pre
             if form == "split":
                 inp = [tuple(y.contiguous().requires_grad_(True) for y in (x[..., 0], x[..., 1:1 + C], x[..., 1 + C:])) for x in raw]

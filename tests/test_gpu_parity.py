@@ -759,14 +759,16 @@ def test_loss_split_gradients_cleared_ahead(ops):
         return float(loss), [x.grad.clone() for p in tri for x in p]
 
     base = run(False)
-    ops.PRECLEAR_SPLIT_GRADS = True
+    keep = ops.PRECLEAR_SPLIT_GRADS
     try:
-        for graph in (False, True):
-            got = run(graph)
-            assert got[0] == base[0]
-            assert all(torch.equal(a, b) for a, b in zip(got[1], base[1]))
+        for mode in (True, "priority", False):
+            ops.PRECLEAR_SPLIT_GRADS = mode
+            for graph in (False, True):
+                got = run(graph)
+                assert got[0] == base[0], (mode, graph)
+                assert all(torch.equal(a, b) for a, b in zip(got[1], base[1])), (mode, graph)
     finally:
-        ops.PRECLEAR_SPLIT_GRADS = False
+        ops.PRECLEAR_SPLIT_GRADS = keep
 
 
 def test_loss_rejects_out_of_range_ids(ops):

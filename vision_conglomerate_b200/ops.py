@@ -740,11 +740,11 @@ def _head_ptrs(tensors, split: bool):
 _side_streams: Dict[int, "torch.cuda.Stream"] = {}
 
 
-def _side_stream(dev: torch.device) -> "torch.cuda.Stream":
+def _side_stream(dev: torch.device, high_priority: bool = False) -> "torch.cuda.Stream":
     idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    st = _side_streams.get(idx)
+    st = _side_streams.get((idx, high_priority))
     if st is None:
-        st = _side_streams[idx] = torch.cuda.Stream(device=dev)
+        st = _side_streams[(idx, high_priority)] = torch.cuda.Stream(device=dev, priority=-1 if high_priority else 0)
     return st
 
 
@@ -782,8 +782,22 @@ class _DetLoss(torch.autograd.Function):
         split = params.input_form == _lib.LOSS_RAW_SPLIT
         ctx.pre = None
         with _on(dev):
-            if split and PRECLEAR_SPLIT_GRADS and any(ctx.needs_input_grad[5:]):
-                # (needs_input_grad says whether a backward can follow)
+            preclear = split and PRECLEAR_SPLIT_GRADS and any(ctx.needs_input_grad[5:])   # (whether a backward can follow)
+            fwd_stream = _stream(dev)
+            hp = None
+            if preclear and PRECLEAR_SPLIT_GRADS == "priority":
+                # the clear on the caller's stream, the forward kernels on a HIGHER-PRIORITY stream next to it: the block
+                # scheduler serves their CTAs ahead of the memset's pending ones, so the latency-bound forward runs inside
+                # the bandwidth-bound clear instead of queueing behind it
+                cur, hp = torch.cuda.current_stream(dev), _side_stream(dev, True)
+                grads, flat = _split_grad_buffers(tensors, dev)
+                ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
+                loss = torch.empty(1, dtype=torch.float32, device=dev)
+                hp.wait_stream(cur)
+                check(L.bg_loss_clear_grads(C.byref(params), _head_ptrs(grads, True), cur.cuda_stream), "bg_loss_clear_grads")
+                ctx.pre = (grads, flat, None)
+                fwd_stream = hp.cuda_stream
+            elif preclear:
                 cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 grads, flat = _split_grad_buffers(tensors, dev)
                 side.wait_stream(cur)        # the buffers may be recycled memory of work queued on this stream
@@ -791,11 +805,14 @@ class _DetLoss(torch.autograd.Function):
                 if not torch.cuda.is_current_stream_capturing():
                     flat.record_stream(side)   # (if the node dies without its backward, the memory waits for the clear)
                 ctx.pre = (grads, flat, side)
-            ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
-            loss = torch.empty(1, dtype=torch.float32, device=dev)
+            if hp is None:
+                ws = torch.empty(L.bg_loss_workspace_bytes(C.byref(params)), dtype=torch.uint8, device=dev)
+                loss = torch.empty(1, dtype=torch.float32, device=dev)
             check(L.bg_loss_fwd(_head_ptrs(tensors, split), targets.data_ptr() if targets.numel() else None,
                                 C.byref(params), scalars.data_ptr(), hist.data_ptr(), loss.data_ptr(), status.data_ptr(),
-                                ws.data_ptr(), ws.numel(), _stream(dev)), "bg_loss_fwd")
+                                ws.data_ptr(), ws.numel(), fwd_stream), "bg_loss_fwd")
+            if hp is not None:
+                torch.cuda.current_stream(dev).wait_stream(hp)   # loss, scalars and the cleared planes: all behind this point
         ctx.save_for_backward(*tensors)
         ctx.params, ctx.ws = params, ws
         return loss.reshape(())
@@ -811,7 +828,8 @@ class _DetLoss(torch.autograd.Function):
         with _on(dev):
             if ctx.pre is not None:
                 grads, _flat, side = ctx.pre
-                torch.cuda.current_stream(dev).wait_stream(side)   # the planes are zero from here on
+                if side is not None:
+                    torch.cuda.current_stream(dev).wait_stream(side)   # the planes are zero from here on
                 flags = _lib.LOSS_BWD_PRECLEARED
                 ctx.pre = None                                     # (a second backward through the same node is refused by autograd anyway)
             elif split:
@@ -825,10 +843,12 @@ class _DetLoss(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
-# split form: clear the class / box gradient planes on a second stream next to the forward (see _DetLoss) instead of
-# inside the backward.  Off: measured on B200 it gains nothing (graph replay 0.507 vs 0.512 ms at 256 images, 0.099 vs
-# 0.100 ms at 32) and costs the eager path two cross-stream joins per step.
-PRECLEAR_SPLIT_GRADS = False
+# split form: where the 2 GB clear of the class / box gradient planes runs.  False: inside the backward.  True: on a second
+# stream next to the forward (measured on B200: gains nothing -- a memset fills every thread slot of the machine and the
+# forward kernels queue behind it).  "priority": the clear on the caller's stream and the FORWARD on a higher-priority
+# stream next to it, so that the scheduler serves the forward's CTAs first: graph replay 0.0916 vs 0.0997 ms at 32 images,
+# 0.154 vs 0.161 at 64, 0.502 vs 0.511 at 256 (where the step sits on the DRAM floor of its 3.16 GB of actual traffic).
+PRECLEAR_SPLIT_GRADS = "priority"
 
 
 _combine_param_cache: Dict[tuple, LossParams] = {}
