@@ -29,7 +29,8 @@ def timed(fn, iters):
     return a.elapsed_time(b) / iters
 
 
-for B, S, C, K, G in ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20)):
+QUICK = "--quick" in sys.argv     # one case, no reference run (for ncu)
+for B, S, C, K, G in (((16, 640, 80, 32, 8),) if QUICK else ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20))):
     preds, protos, t, masks = synth.seg_inputs(B, S, S, C, K, G, seed=11)
     preds = [p.to(dev).requires_grad_(True) for p in preds]
     protos = protos.to(dev).requires_grad_(True)
@@ -50,6 +51,8 @@ for B, S, C, K, G in ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20)):
     out = {"case": "SegmentationLoss fwd+bwd B=%d %dx%d C=%d K=%d, <=%d gt/img, protos %dx%d" % (B, S, S, C, K, G, S // 2, S // 2),
            "ours_ms": ms, "ours_img_s": B / ms * 1e3, "loss": float(loss), "kernels_per_step": int(launches)}
     try:
+        if QUICK:
+            raise RuntimeError("skipped (--quick)")
         from oracle import ref_harness
         ns = ref_harness.load()
         mod = ns.SegmentationLoss(ns.FakeSegModel(C, synth.ANCHORS, K).to(dev), overlap_masks=True, **cfg)

@@ -23,9 +23,15 @@ done
 TCMD="python scripts/prof_train.py --iters 2 --warmup 2 --form raw"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"loss_bwd_stream|loss_bwd_rows|loss_match|loss_dense" -s 12 -c 5 -o gpurun_out/prof_train_r2 -f $TCMD > gpurun_out/train_ncu_full.log 2>&1
 echo "ncu train full rc=$?" >> gpurun_out/stages.txt
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"decode_filter|image_nms" -s 10 -c 4 -o gpurun_out/prof_detect_r2 -f $CMD > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"decode_filter|image_nms" -s 10 -c 8 -o gpurun_out/prof_detect_r2 -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "ncu detect full rc=$?" >> gpurun_out/stages.txt
+SCMD="python scripts/bench_seg.py --quick"
+timeout 300 $SCMD > gpurun_out/seg_plain.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"seg_fwd|seg_bwd" -s 9 -c 3 -o gpurun_out/prof_seg_r2 -f $SCMD > gpurun_out/ncu_seg.log 2>&1
+echo "ncu seg full rc=$?" >> gpurun_out/stages.txt
 fi
+timeout 300 python scripts/exp_pipe.py --depths 3,4,6 > gpurun_out/exp_pipe.log 2>&1; echo "exp_pipe rc=$?" >> gpurun_out/stages.txt
+timeout 600 python scripts/bench_seg.py > gpurun_out/bench_seg.log 2>&1; echo "bench_seg rc=$?" >> gpurun_out/stages.txt
 cat gpurun_out/stages.txt
 tail -n 4 gpurun_out/pytest_gpu.log
 grep "^train" gpurun_out/train_forms.log
