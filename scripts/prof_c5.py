@@ -26,6 +26,24 @@ for f in range(500):
 med = lambda v: sorted(v)[len(v) // 2]
 print("p50 us: host enqueue (incl. 2 event records) %.1f, result() %.1f, total %.1f; GPU span of the two kernels %.1f; rows %d"
       % (med(enq), med(res), med(tot), med(gpu), int(r.pred_boxes.shape[0])))
+# the same with the rows brought to the HOST by one pinned copy queued behind the kernels (what the reference's
+# per-image loop needs, inference_det.py:100-129)
+tot3 = []
+for f in range(500):
+    t0 = time.perf_counter()
+    plan.enqueue(frames[f % 32])
+    plan.enqueue_host_copy()
+    h = plan.result_host()
+    tot3.append((time.perf_counter() - t0) * 1e6)
+print("enqueue + one pinned copy of [counts | rows] + result_host(): p50 %.1f us, p99 %.1f us, rows on the host %d"
+      % (med(tot3), sorted(tot3)[int(len(tot3) * 0.99)], int(h.rows.shape[0])))
+tot4 = []
+for f in range(500):
+    t0 = time.perf_counter()
+    plan.enqueue(frames[f % 32])
+    r = plan.result()
+    tot4.append((time.perf_counter() - t0) * 1e6)
+print("enqueue + result() (rows stay on the device): p50 %.1f us, p99 %.1f us" % (med(tot4), sorted(tot4)[int(len(tot4) * 0.99)]))
 # CUDA graph replay of the same two launches from a static input
 static = [t.clone() for t in frames[0]]
 plan.enqueue(static); plan.result()

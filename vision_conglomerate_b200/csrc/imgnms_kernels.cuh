@@ -29,6 +29,7 @@ namespace bg {
 constexpr int INMS_THREADS = 1024;
 constexpr int INMS_MAXT = 1024;      // tiles per image
 constexpr int INMS_GMAX = 64;        // grid cells per axis
+constexpr int INMS_TINY_K = 128;     // images with at most this many survivors: all pairs, rank by counting, no helper (video frames)
 constexpr int INMS_HELPER_SHARE_32 = 7;  // the helper takes 7/32 of the pair-test items (it also does the sort)
 
 // Three sizes of the kernel.  Small: up to 4 096 survivors per image, boxes in shared memory (the latency case).
@@ -302,6 +303,36 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
     }
     if (!Cfg::BOX_SMEM) __syncthreads();  // the global box (key, class) arrays are complete (block-scope visibility)
     INMS_STAMP(1);
+    // A few dozen survivors (batch-1 video frames with a real score threshold): the grid, the work items and the
+    // 1024-key sorting network are all fixed cost there.  Test all pairs, rank the keys by counting, skip the helper
+    // (both CTAs of an image see the same K, so the main CTA knows not to wait).
+    const bool tiny = K <= INMS_TINY_K;
+    if (tiny && role == 0) return;
+    const IouThr thr = k.thr;
+    if (tiny) {
+        __syncthreads();  // keys / boxes of stage 1 are in place
+        for (int t = tid; t < K * K; t += INMS_THREADS) {
+            const int i = t / K, j = t - i * K;
+            if (i >= j) continue;
+            const float4 a = box_at(i), c = box_at(j);
+            float w, h, cx, cy;
+            if (!inms_box_valid(a, w, h, cx, cy)) continue;
+            const float aa = __fmul_rn(w, h);
+            if (!inms_box_valid(c, w, h, cx, cy)) continue;
+            if (iou_suppresses(a, aa, c, __fmul_rn(w, h), thr)) {
+                const bool i_first = key_at(i) < key_at(j);
+                const u32 ed = i_first ? (((u32)i << 16) | (u32)j) : (((u32)j << 16) | (u32)i);
+                const int e = atomicAdd(&S.n_edges, 1);
+                if (e < Cfg::ECAP) S.edges[e] = ed;
+                else {
+                    const u32 o = atomicAdd(&k.gflag[4 * b + 2], 1u);
+                    if (o < (u32)k.gcap) k.gspill[(long long)b * k.gcap + o] = ed;
+                }
+            }
+        }
+        __syncthreads();
+        INMS_STAMP(2);
+    } else {
 
     // ---- 2. grid over the valid centres, counting sort by cell --------------------------------------------------
 #pragma unroll
@@ -388,7 +419,6 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
     INMS_STAMP(2);
 
     // ---- 3. pair tests, item-parallel ------------------------------------------------------------------------
-    const IouThr thr = k.thr;
     const int T_helper = k.split ? (int)(((long long)T * Cfg::HELPER_SHARE_32) >> 5) : 0;
     const int it_lo = role == 1 ? T_helper : 0, it_hi = role == 1 ? T : T_helper;
     for (int c0 = it_lo; c0 < it_hi; c0 += Cfg::ITEMS) {
@@ -460,6 +490,7 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
         }
         __syncthreads();
     }
+    }  // !tiny
     int ne = min(S.n_edges, Cfg::ECAP);  // edges in this CTA's shared-memory list (the rest were spilled)
     if (role == 0) {
         // ---- helper: hand the edges over, sort the keys, hand them over, done ----
@@ -480,7 +511,7 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
         return;
     }
     int nh = 0;  // edges in the helper's list
-    if (k.split) {
+    if (k.split && !tiny) {
         if (tid == 0) {
             u32 v;
             do { v = ((volatile u32 *)k.gflag)[4 * b]; } while (v == 0u);
@@ -525,7 +556,21 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
     INMS_STAMP(4);
 
     // ---- 5. sort ------------------------------------------------------------------------------------------------------
-    if (k.split) {   // the helper sorted the keys meanwhile
+    if (tiny) {      // rank by counting: the keys are distinct (they end in the survivor number)
+        if constexpr (Cfg::LEAN) {
+            for (int j = tid; j < K; j += INMS_THREADS) S.keys[j] = gkey[j];
+            __syncthreads();
+        }
+        u64 mine = 0;
+        int r = 0;
+        if (tid < K) {
+            mine = S.keys[tid];
+            for (int j = 0; j < K; ++j) r += S.keys[j] < mine ? 1 : 0;
+        }
+        __syncthreads();
+        if (tid < K) S.keys[r] = mine;
+        __syncthreads();
+    } else if (k.split) {   // the helper sorted the keys meanwhile
         if (tid == 0) { while (((volatile u32 *)k.gflag)[4 * b + 1] == 0u) { } }
         __syncthreads();
         __threadfence();
