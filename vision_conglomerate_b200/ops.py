@@ -250,6 +250,8 @@ class DetectPlan:
         self.key = (device.index, "detect")
         self.ws_tag = "detect"   # plans that run concurrently on different streams need distinct scratch: set a distinct tag
         self.input_bytes = sum(4 * B * sh[1] * sh[2] * na * D for sh in shapes)
+        self._need_key, self._need = None, 0
+        self._out_ptrs = (self.out_boxes.data_ptr(), self.out_img.data_ptr(), self.out_keep.data_ptr(), self.counts.data_ptr())
 
     def _auto_path(self, hint: int, throughput: bool) -> int:
         """``bg_detect_params.nms_path`` for what earlier batches of this configuration needed (``_nms_path_hint``): 0 nothing
@@ -294,7 +296,11 @@ class DetectPlan:
         if any(r.device != self.dev for r in self.raws):
             raise RuntimeError(f"detect: the plan lives on {self.dev}, the inputs on {self.raws[0].device}")
         self.mask_bytes = _mask_budget.get(self.key, DEFAULT_MASK_BYTES)
-        need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
+        nk = (self.mask_bytes, p.nms_path)
+        if self._need_key != nk:     # (the size query is a host-side carve: remembered per scratch budget / engine)
+            self._need = L.bg_detect_workspace_bytes(C.byref(p), self.mask_bytes)
+            self._need_key = nk
+        need = self._need
         if need == 0:
             raise RuntimeError("detect: invalid parameters")
         ws = _workspace(self.dev, self.ws_tag, need)
@@ -303,9 +309,10 @@ class DetectPlan:
                                     self.out_keep.data_ptr(), self.counts.data_ptr(), ws.data_ptr(), ws.numel(),
                                     self.mask_bytes, _stream(self.dev)), "bg_post_process")
             return
-        check(L.bg_detect(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(), C.byref(p),
-                          self.out_boxes.data_ptr(), self.out_img.data_ptr(), self.out_keep.data_ptr(),
-                          self.counts.data_ptr(), ws.data_ptr(), ws.numel(), self.mask_bytes, _stream(self.dev)), "bg_detect")
+        rc = L.bg_detect(self.raws[0].data_ptr(), self.raws[1].data_ptr(), self.raws[2].data_ptr(), C.byref(p),
+                         *self._out_ptrs, ws.data_ptr(), ws.numel(), self.mask_bytes, _stream(self.dev))
+        if rc:
+            check(rc, "bg_detect")
 
     def result(self) -> Detections:
         with _on(self.dev):
@@ -315,7 +322,12 @@ class DetectPlan:
         B = self.B
         while True:
             h = _read_counts(self.counts, "detect")
-            if int(h[1]) & _lib.STATUS_NEED_GENERAL:
+            status = int(h[1])
+            if not status and not _nms_path_hint:   # the common case, with as few tensor operations as possible (batch-1 latency)
+                hc = h.clone()
+                k = int(hc[0])
+                return Detections(self.out_boxes[:k], self.out_img[:k], self.out_keep[:k], hc[2: 2 + B], hc[2 + B: 2 + 2 * B])
+            if status & _lib.STATUS_NEED_GENERAL:
                 # an image exceeded what the one-CTA-per-image NMS holds: run again through the general engine
                 # and remember it (survivor overflow is re-evaluated from the counts, edge overflow is kept)
                 most = int(h[2 + B: 2 + 2 * B].max())
