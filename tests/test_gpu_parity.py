@@ -1040,3 +1040,22 @@ def test_segmentation_loss_twice_and_scaled(ops):
     for sc, p in zip(synth.SCALES, gp):
         assert_close(p.grad.cpu().numpy(), 2.0 * g["grad_" + sc], rtol=1e-4, atol=2e-7, what="grad " + sc)
     assert_close(pr.grad.cpu().numpy(), 2.0 * g["grad_protos"], rtol=1e-4, atol=2e-8, what="grad protos")
+
+
+def test_segmentation_loss_without_targets(ops):
+    """No target at all: the mask term is zero (the reference's loop over batch_idx.unique() is empty), the protos get a
+    zero gradient, the detection terms are those of the detection loss."""
+    from oracle import seg_oracle as SO
+    B, S, C, K = 2, 64, 5, 8
+    preds, protos, t, masks = synth.seg_inputs(B, S, S, C, K, 0, seed=4, fixed=True)
+    assert t.shape == (0, 6)
+    cfg = dict(synth.LOSS_CONFIG, seg_w=1.0)
+    anc = [synth.anchors_tensor(s).numpy() for s in synth.SCALES]
+    ref_loss, ref_m, ref_g, _ = SO.segmentation_loss([p.numpy() for p in preds], t.numpy(), protos.numpy(), masks.numpy(), anc, cfg,
+                                                     C, K, with_grad=True)
+    loss, metrics, grads, gpr = _seg_case(ops, preds, protos, t, masks, C, K, cfg)
+    assert_close(float(loss), ref_loss, rtol=1e-5, atol=0, what="loss")
+    assert metrics["seg_loss"] == 0.0 and metrics["dice_score"] == 0.0
+    for a, b in zip(grads, ref_g):
+        assert_close(a, b, rtol=1e-4, atol=1e-8, what="grad preds")
+    assert not gpr.any()
