@@ -27,6 +27,7 @@ def test_library_exports_every_declared_symbol():
     assert L.bg_strerror(0) == b"ok" and b"workspace" in L.bg_strerror(2)
     assert L.bg_sizeof_detect_params() == __import__("ctypes").sizeof(_lib.DetectParams)
     assert L.bg_sizeof_loss_params() == __import__("ctypes").sizeof(_lib.LossParams)
+    assert L.bg_sizeof_seg_params() == __import__("ctypes").sizeof(_lib.SegParams)
 
 
 def test_workspace_queries_run_on_host():
