@@ -314,6 +314,14 @@ int bg_seg_loss_bwd(const float *const preds[3] /*host*/, const float *protos, c
                     const bg_seg_params *p /*host*/, const float *grad_out_dev, float *const grad_preds[3] /*host*/,
                     float *grad_protos, void *workspace, size_t workspace_bytes, void *stream);
 
+/* inference_seg.post_process_preds lines 115-117: for the kept rows of every image,
+ *     masks = sigmoid(coefs @ protos_i) -> F.interpolate(size=(H, W), mode="bilinear", align_corners=False) -> > 0.5.
+ *   coefs [n, K] f32: the mask coefficients of the kept rows, image by image; row_offsets [B+1] i32 (device): rows of
+ *   image i are row_offsets[i] .. row_offsets[i+1]-1; protos [B, K, Hp, Wp]; scratch [n, Hp*Wp] f32 (caller's);
+ *   out_masks [n, H, W] u8 (0 / 1, i.e. torch.bool), 4-byte aligned.  K <= 64.  Two launches. */
+int bg_seg_masks(const float *coefs, const int32_t *row_offsets, const float *protos, int32_t B, int32_t K, int32_t Hp,
+                 int32_t Wp, int64_t n, int32_t H, int32_t W, float *scratch, uint8_t *out_masks, void *stream);
+
 /* Image-sharded training: per-shard sums that add up over the shards, and the big-batch loss from the
  * summed terms.  pack15 [3,5] f64 per scale = {lbox*M, lconf*cells, lcls*M*C, M, cells}; the caller all-reduces (SUM)
  * the 15 doubles between the two calls (NCCL).  cells3: host int64[3], this shard's B*ny*nx*na per scale.

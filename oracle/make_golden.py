@@ -131,6 +131,35 @@ def gen_seg_post(ns):
              keypoint_rows=np.array([k.reshape(-1, 3).shape[0] for k in kps], dtype=np.int64))
 
 
+SEG_MASK_CASES = {
+    # name: (decode case, iou, score_thr, box_allowance, tracked, protos (Hp, Wp), image (H, W))
+    "segmask_T128": ("dec_T128", 0.35, 0.3, 4, None, (32, 32), (128, 128)),          # x4 bilinear
+    "segmask_T128_odd": ("dec_T128", 0.35, 0.3, 4, (1, 4, 7, 16, 17), (24, 40), (90, 100)),  # non-integer scales, class filter
+}
+
+
+def gen_seg_masks(ns):
+    """inference_seg.post_process_preds lines 115-117 (f2): masks = sigmoid(coefs @ protos) -> bilinear resize to the image
+    -> > 0.5, captured from the unmodified function for every surviving image (boolean, bit-packed in the fixture)."""
+    for name, (dname, iou, thr, allow, tracked, psz, isz) in SEG_MASK_CASES.items():
+        B, H, W, C, dist, seed, og = DECODE_CASES[dname]
+        raws = synth.raw_head_outputs(B, H, W, C, dist, seed)
+        anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+        base = ref_harness.ref_decode_inference(raws, anc, H, W, og, C)
+        extra = seg_extra_columns(B, base.shape[1], 0, 500 + seed)
+        preds = torch.cat([base, extra], dim=-1).contiguous()
+        protos = torch.randn(B, SEG_MASKS, psz[0], psz[1], generator=torch.Generator().manual_seed(900 + seed)).contiguous()
+        cap = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, allow, tracked, img_size=isz)
+        per, masks = cap["per_image"], cap["masks"]
+        allm = np.concatenate([m.reshape(m.shape[0], -1) for m in masks], 0) if masks else np.zeros((0, isz[0] * isz[1]), bool)
+        save(name, decode_case=np.array(dname), iou=np.array(iou), thr=np.array(thr), allow=np.array(-1 if allow is None else allow),
+             extra_seed=np.array(500 + seed), proto_seed=np.array(900 + seed), psz=np.array(psz), isz=np.array(isz),
+             tracked=np.array(tracked if tracked else [], dtype=np.int64),
+             per_image=np.concatenate(per, 0) if per else np.zeros((0, 6), np.float32),
+             per_image_counts=np.array([p.shape[0] for p in per], dtype=np.int64),
+             masks_packed=np.packbits(allm.astype(np.uint8), axis=1), mask_rows=np.array(allm.shape[0]))
+
+
 def gen_nms():
     cases = {}
     b, s, g = synth.nms_boxes(3000, 4, seed=3)
@@ -337,4 +366,5 @@ if __name__ == "__main__":
     gen_loss(ns, raw=True)
     gen_ratio(ns)
     gen_seg_loss(ns)
+    gen_seg_masks(ns)
     print("torch", torch.__version__, "torchvision", torchvision.__version__)

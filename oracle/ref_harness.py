@@ -194,7 +194,7 @@ def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_all
 
 
 def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_threshold, box_allowance=None,
-                         tracked_classes=None):
+                         tracked_classes=None, img_size=None):
     """Calls the reference's inference_seg.post_process_preds unmodified (inference_seg.py:40-175) and captures the
     arguments / result of its torchvision.ops.batched_nms call and, per surviving image, the box array, the boolean
     masks and the keypoint array it hands to the drawing code."""
@@ -241,7 +241,9 @@ def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_thresh
         inf.Image = _NullImg
         inf.STORAGE_PATH = tmp
         B = preds.shape[0]
-        imgs = torch.zeros(B, 3, protos.shape[2], protos.shape[3], dtype=torch.uint8)  # same size as the protos: the resize is the identity
+        # same size as the protos (the bilinear resize of inference_seg.py:116 is then the identity) unless img_size is given
+        ih, iw = img_size if img_size is not None else (protos.shape[2], protos.shape[3])
+        imgs = torch.zeros(B, 3, ih, iw, dtype=torch.uint8)
         with torch.no_grad():
             inf.post_process_preds(imgs, preds.clone(), protos.clone(), num_classes, iou_threshold=iou_threshold,
                                    score_threshold=score_threshold, box_allowance=box_allowance,

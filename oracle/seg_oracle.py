@@ -136,3 +136,37 @@ def segmentation_loss(preds3: Sequence, targets, protos, target_masks, anchors3:
     loss = loss + cfg.get("seg_w", 1.0) * lseg
     metrics = dict(metrics, aggregate_loss=float(loss), seg_loss=float(np.mean(seg_rows)), dice_score=float(np.mean(dice_rows)))
     return float(loss), metrics, (grads if with_grad else None), gp
+
+
+def seg_masks(coefs, row_counts, protos, H: int, W: int):
+    """inference_seg.post_process_preds lines 115-117: per image, ``masks = sigmoid(coefs @ protos_i)`` on the protos'
+    grid, ``F.interpolate(mode="bilinear", align_corners=False)`` to ``(H, W)``, ``> 0.5``.  ``coefs [n, K]`` are the kept
+    rows' coefficients image by image (``row_counts [B]``).  Returns (bool [n, H, W], the interpolated values fp32).
+    ATen's bilinear kernel: src = scale * (dst + 0.5) - 0.5 clamped at 0, scale = in / out in fp32, i0 = trunc(src),
+    i1 = i0 + (i0 < in - 1), value = h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)."""
+    coefs = np.asarray(coefs, np.float32)
+    protos = np.asarray(protos, np.float32)
+    B, K, Hp, Wp = protos.shape
+    n = coefs.shape[0]
+    vals = np.zeros((n, H, W), np.float32)
+
+    def axis(n_in, n_out):
+        scale = np.float32(n_in) / np.float32(n_out)
+        src = np.maximum(scale * (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) - np.float32(0.5), np.float32(0))
+        i0 = src.astype(np.int64)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        return i0, i1, (np.float32(1) - l1).astype(np.float32), l1
+
+    y0, y1, hy0, hy1 = axis(Hp, H)
+    x0, x1, wx0, wx1 = axis(Wp, W)
+    r = 0
+    for i, c in enumerate(np.asarray(row_counts, np.int64)):
+        if c == 0:
+            continue
+        low = _sigmoid((coefs[r:r + c] @ protos[i].reshape(K, -1)).astype(np.float32)).reshape(c, Hp, Wp)
+        top = wx0[None, None, :] * low[:, y0][:, :, x0] + wx1[None, None, :] * low[:, y0][:, :, x1]
+        bot = wx0[None, None, :] * low[:, y1][:, :, x0] + wx1[None, None, :] * low[:, y1][:, :, x1]
+        vals[r:r + c] = hy0[None, :, None] * top + hy1[None, :, None] * bot
+        r += c
+    return vals > np.float32(0.5), vals

@@ -71,3 +71,44 @@ for B, S, C, K, G in (((16, 640, 80, 32, 8),) if QUICK else ((16, 640, 80, 32, 8
     except Exception as e:  # noqa: BLE001
         out["reference"] = repr(e)[:200]
     print(json.dumps(out), flush=True)
+
+# inference side (inference_seg.py:115-117): masks of the kept rows, ours vs the same torch calls per image
+B, K, Hp, Wp, H, W = 8, 32, 160, 160, 640, 640
+g = torch.Generator().manual_seed(5)
+counts = torch.full((B,), 25)
+coefs = torch.tanh(torch.randn(int(counts.sum()), K, generator=g)).to(dev)
+protos = torch.randn(B, K, Hp, Wp, generator=g).to(dev)
+
+
+def ours_masks():
+    return ops.seg_masks(coefs, counts, protos, (H, W))
+
+
+def torch_masks():
+    r, outs = 0, []
+    for i, c in enumerate(counts.tolist()):
+        m = (coefs[r:r + c] @ protos[i].reshape(K, -1)).reshape(-1, Hp, Wp).sigmoid()
+        m = torch.nn.functional.interpolate(m.unsqueeze(0), size=(H, W), mode="bilinear", align_corners=False)
+        outs.append(torch.gt(m, 0.5).squeeze(0))
+        r += c
+    return outs
+
+
+if not QUICK:
+    a, b = timed(ours_masks, 20), timed(torch_masks, 20)
+    print(json.dumps({"case": "masks of 200 kept rows (8 images x 25), K=32, protos 160x160 -> 640x640 bool", "ours_ms": a,
+                      "torch_cuda_ms": b, "speedup": b / a, "output_MB": 200 * H * W / 1e6}), flush=True)
+
+if not QUICK:   # the two kernels alone (no Python, no offsets copy)
+    from vision_conglomerate_b200.ops import _stream
+    L = _lib.lib()
+    n = int(counts.sum())
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(counts, 0)
+    off = off.to(dev)
+    low = torch.empty(n, Hp * Wp, device=dev)
+    out = torch.empty(n, H, W, dtype=torch.uint8, device=dev)
+    kms = timed(lambda: L.bg_seg_masks(coefs.data_ptr(), off.data_ptr(), protos.data_ptr(), B, K, Hp, Wp, n, H, W, low.data_ptr(),
+                                       out.data_ptr(), _stream(dev)), 50)
+    byts = n * H * W + 2 * n * Hp * Wp * 4 + B * K * Hp * Wp * 4
+    print(json.dumps({"case": "bg_seg_masks kernels only", "ms": kms, "algorithmic_MB": byts / 1e6, "GB_per_s": byts / kms / 1e6}), flush=True)

@@ -1059,3 +1059,58 @@ def test_segmentation_loss_without_targets(ops):
     for a, b in zip(grads, ref_g):
         assert_close(a, b, rtol=1e-4, atol=1e-8, what="grad preds")
     assert not gpr.any()
+
+
+@pytest.mark.parametrize("name", ["segmask_T128", "segmask_T128_odd"])
+def test_seg_masks_golden(ops, name):
+    """inference_seg.post_process_preds lines 62-117 end to end on the device: rows by ops.post_process, the
+    coefficients of the kept rows by ops.extra_columns, the masks by ops.seg_masks -- against the boolean masks the
+    UNMODIFIED function hands to its drawing code (pixels may differ only where the interpolated value is within 2e-5 of 0.5)."""
+    from oracle import seg_oracle as SO
+    from tests.util import assert_masks_match, seg_mask_case
+    g = golden(name)
+    raws, (B, H, W, C, og), protos, isz, ref_masks = seg_mask_case(g)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    base = torch.cat([ops.decode_scale(dev(r), a, (H, W), True, og).reshape(B, -1, C + 5) for r, a in zip(raws, anc)], 1)
+    extra = seg_extra_columns(B, base.shape[1], 4, int(g["extra_seed"]))
+    preds = torch.cat([base, dev(extra)], dim=-1).contiguous()
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    det = ops.post_process(preds, (H, W), C, float(g["iou"]), float(g["thr"]), allow, tracked, order="image")
+    coefs = ops.extra_columns(preds, det, C)[:, :4].contiguous()
+    masks = ops.seg_masks(coefs, det.counts, dev(protos), isz)
+    assert masks.dtype == torch.bool and tuple(masks.shape) == (det.pred_boxes.shape[0], isz[0], isz[1])
+    counts = g["per_image_counts"]
+    ref_img = np.repeat(np.arange(len(counts)), counts)
+    rows = det.pred_boxes.cpu().numpy()
+    got_img = np.unique(det.sample_idxs.cpu().numpy(), return_inverse=True)[1]
+    po, pr = rows_order(rows, got_img), rows_order(g["per_image"], ref_img)
+    assert_close(rows[po], g["per_image"][pr], rtol=1e-5, atol=2e-5 * max(H, W), what="rows vs reference")
+    _, vals = SO.seg_masks(coefs.cpu().numpy(), det.counts.numpy(), protos.numpy(), isz[0], isz[1])
+    nd = assert_masks_match(masks.cpu().numpy()[po], ref_masks[pr], vals[po])
+    print("%s: %d masks of %dx%d, %d pixels differ from the reference (all on the threshold)" % (name, masks.shape[0], isz[0], isz[1], nd))
+
+
+def test_seg_masks_vs_oracle_and_torch(ops):
+    """32 coefficients, 160x160 protos to 640x640, images without rows: against the oracle and against the same three torch
+    calls on the device (what inference_seg.py runs per image)."""
+    from oracle import seg_oracle as SO
+    from tests.util import assert_masks_match
+    B, K, Hp, Wp, H, W = 4, 32, 160, 160, 640, 640
+    g = torch.Generator().manual_seed(5)
+    counts = torch.tensor([7, 0, 19, 3])
+    coefs = torch.tanh(torch.randn(int(counts.sum()), K, generator=g))
+    protos = torch.randn(B, K, Hp, Wp, generator=g)
+    masks = ops.seg_masks(dev(coefs), counts, dev(protos), (H, W)).cpu().numpy()
+    ref, vals = SO.seg_masks(coefs.numpy(), counts.numpy(), protos.numpy(), H, W)
+    nd = assert_masks_match(masks, ref, vals)
+    r, outs = 0, []
+    for i, c in enumerate(counts.tolist()):
+        if c:
+            m = (dev(coefs[r:r + c]) @ dev(protos[i]).reshape(K, -1)).reshape(-1, Hp, Wp).sigmoid()
+            m = torch.nn.functional.interpolate(m.unsqueeze(0), size=(H, W), mode="bilinear", align_corners=False)
+            outs.append(torch.gt(m, 0.5).squeeze(0).cpu().numpy())
+        r += c
+    nt = assert_masks_match(masks, np.concatenate(outs, 0), vals, what="masks vs torch-CUDA", band=5e-5)
+    print("seg_masks 29 x 640x640: %d pixels differ from the oracle, %d from torch-CUDA (all on the threshold)" % (nd, nt))
+    assert ops.seg_masks(dev(coefs[:0]), torch.zeros(B, dtype=torch.int64), dev(protos), (H, W)).shape == (0, H, W)

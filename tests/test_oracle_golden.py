@@ -212,3 +212,32 @@ def test_segmentation_loss(name):
     for sc, gr in zip(synth.SCALES, grads):
         assert_close(gr, g["grad_" + sc], rtol=1e-4, atol=1e-7, what="grad " + sc)
     assert_close(gp, g["grad_protos"], rtol=1e-4, atol=1e-8, what="grad protos")
+
+
+@pytest.mark.parametrize("name", ["segmask_T128", "segmask_T128_odd"])
+def test_seg_masks(name):
+    """inference_seg.post_process_preds lines 115-117: sigmoid(coefs @ protos) -> bilinear resize -> > 0.5, the
+    numpy restatement against the boolean masks the unmodified function hands to its drawing code."""
+    from oracle import seg_oracle as SO
+    from tests.util import assert_masks_match, seg_mask_case
+    g = golden(name)
+    raws, (B, H, W, C, og), protos, isz, ref_masks = seg_mask_case(g)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    preds = O.decode_inference(raws, anc, H, W, og)
+    extra = seg_extra_columns(B, preds.shape[1], 4, int(g["extra_seed"])).numpy()
+    allow = None if int(g["allow"]) < 0 else int(g["allow"])
+    tracked = [int(v) for v in g["tracked"]] or None
+    out = O.post_process(preds, float(g["iou"]), float(g["thr"]), allow, tracked)
+    counts = g["per_image_counts"]
+    got, ref_rows = out["pred_boxes"], g["per_image"]
+    assert got.shape[0] == counts.sum() == ref_masks.shape[0]
+    ref_img = np.repeat(np.arange(len(counts)), counts)
+    got_img = np.unique(out["sample_idxs"], return_inverse=True)[1] if len(got) else out["sample_idxs"]
+    po, pr = rows_order(got, got_img), rows_order(ref_rows, ref_img)
+    # image-major rows for the restatement, then back to the reference's order
+    img_full = out["sample_idxs"][po]
+    coefs = extra.reshape(-1, 4)[out["keep"]][po]
+    per_img = np.bincount(img_full, minlength=B)
+    m, vals = SO.seg_masks(coefs, per_img, protos.numpy(), isz[0], isz[1])
+    nd = assert_masks_match(m, ref_masks[pr], vals)
+    print("%s: %d rows, %d of %d pixels differ (all within 2e-5 of the threshold)" % (name, m.shape[0], nd, m.size))

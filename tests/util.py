@@ -85,3 +85,29 @@ def seg_loss_case(name, g):
     if name == "segloss_empty_img":
         t = t[t[:, 0] != 1].contiguous()
     return preds, protos, t, masks, C, K
+
+
+def seg_mask_case(g):
+    """Inputs of a tests/golden/segmask_*.npz case (oracle/make_golden.py gen_seg_masks): raw head outputs, decode
+    parameters, the K = 4 extra columns' seed, the protos, the image size and the reference's per-image rows / masks."""
+    import torch
+    from vision_conglomerate_b200 import synth
+    gd = golden(str(g["decode_case"]))
+    B, H, W, C, seed, og0, og1 = (int(v) for v in gd["params"])
+    raws = synth.raw_head_outputs(B, H, W, C, str(gd["dist"]), seed)
+    psz, isz = [int(v) for v in g["psz"]], [int(v) for v in g["isz"]]
+    protos = torch.randn(B, 4, psz[0], psz[1], generator=torch.Generator().manual_seed(int(g["proto_seed"]))).contiguous()
+    nrow = int(g["mask_rows"])
+    masks = np.unpackbits(g["masks_packed"], axis=1)[:, : isz[0] * isz[1]].reshape(nrow, isz[0], isz[1]).astype(bool)
+    return raws, (B, H, W, C, None if og0 < 0 else (og0, og1)), protos, isz, masks
+
+
+def assert_masks_match(got, ref, vals, what="masks", band=2e-5):
+    """Boolean masks must agree except where the interpolated value sits on the 0.5 threshold to within `band`
+    (cuBLAS / ATen and the restatement add the K products and the four bilinear terms in different orders)."""
+    got, ref = np.asarray(got, bool), np.asarray(ref, bool)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    diff = got != ref
+    marginal = np.abs(np.asarray(vals, np.float64) - 0.5) < band
+    assert not (diff & ~marginal).any(), f"{what}: {int((diff & ~marginal).sum())} pixels differ away from the threshold"
+    return int(diff.sum())

@@ -29,7 +29,7 @@ SYMBOLS = (
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine",
     "bg_ratio_metrics",
-    "bg_seg_loss_workspace_bytes", "bg_seg_loss_fwd", "bg_seg_loss_bwd", "bg_sizeof_seg_params",
+    "bg_seg_loss_workspace_bytes", "bg_seg_loss_fwd", "bg_seg_loss_bwd", "bg_sizeof_seg_params", "bg_seg_masks",
 )
 
 
@@ -173,9 +173,10 @@ def lib() -> C.CDLL:
     L.bg_seg_loss_workspace_bytes.restype = sz
     L.bg_seg_loss_fwd.argtypes = [C.POINTER(vp), vp, vp, vp, C.POINTER(SegParams), vp, vp, vp, vp, sz, vp]
     L.bg_seg_loss_bwd.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(SegParams), vp, C.POINTER(vp), vp, vp, sz, vp]
+    L.bg_seg_masks.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, vp, vp]
     for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics",
-                 "bg_seg_loss_fwd", "bg_seg_loss_bwd"):
+                 "bg_seg_loss_fwd", "bg_seg_loss_bwd", "bg_seg_masks"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L

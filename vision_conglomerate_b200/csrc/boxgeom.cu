@@ -1233,6 +1233,32 @@ int bg_seg_loss_bwd(const float *const preds[3], const float *protos, const floa
     return BG_OK;
 }
 
+int bg_seg_masks(const float *coefs, const int32_t *row_offsets, const float *protos, int32_t B, int32_t K, int32_t Hp,
+                 int32_t Wp, int64_t n, int32_t H, int32_t W, float *scratch, uint8_t *out_masks, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B <= 0 || K <= 0 || K > SEGM_KMAX || Hp <= 0 || Wp <= 0 || H <= 0 || W <= 0 || n < 0 || !row_offsets || !protos) return BG_ERR_INVALID;
+    if ((long long)Hp * Wp >= (1ll << 30) || n * (long long)H * W >= (1ll << 40)) return BG_ERR_INVALID;
+    if (n == 0) return BG_OK;
+    if (!coefs || !scratch || !out_masks || ((uintptr_t)out_masks & 3)) return BG_ERR_INVALID;
+    SegMaskK k;
+    memset(&k, 0, sizeof(k));
+    k.B = B; k.K = K; k.Hp = Hp; k.Wp = Wp; k.HW = Hp * Wp; k.H = H; k.W = W; k.n = n;
+    k.coefs = coefs; k.row_off = row_offsets; k.protos = protos; k.low = scratch; k.out = out_masks;
+    k.ry = (float)Hp / (float)H; k.rx = (float)Wp / (float)W;
+    seg_lowres_kernel<<<dim3((k.HW + SEG_THREADS - 1) / SEG_THREADS, B), SEG_THREADS, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    const bool vec = (W & 3) == 0;
+    const long long blocks = n * ((H + SEGM_YCHUNK - 1) / SEGM_YCHUNK);   // one block per (row, 16 output lines)
+    if (blocks >= (1ll << 31)) return BG_ERR_INVALID;
+    const int wv = vec ? W / 4 : W;
+    const int threads = wv >= SEG_THREADS ? SEG_THREADS : ((wv + 31) / 32) * 32;   // no idle warps when a line is short
+    if (vec) seg_upsample_kernel<4><<<(unsigned)blocks, threads, 0, st>>>(k);
+    else seg_upsample_kernel<1><<<(unsigned)blocks, threads, 0, st>>>(k);
+    BG_LAUNCH_CHECK();
+    return BG_OK;
+}
+
 int bg_loss_pack(const double *scalars, const int64_t *cells3, int32_t C, double *pack15, void *stream)
 {
     if (!scalars || !cells3 || !pack15 || C <= 0) return BG_ERR_INVALID;

@@ -448,4 +448,114 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_bwd_protos_kernel(SegK k)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// inference_seg.post_process_preds lines 115-117: masks = sigmoid(coefs @ protos_i) on the protos' grid, bilinear resize
+// (align_corners=False) to the image, > 0.5.  Rows are the kept detections, image by image (row_off [B+1]).
+//   seg_lowres_kernel     thread = proto pixel, eight rows at a time (coefficients broadcast from shared memory, each
+//                         proto value read once per eight rows), accurate sigmoid -> low [n, Hp*Wp]
+//   seg_upsample_kernel   thread = output pixel (four of a row where the width allows): ATen's source index and weights
+//                         (upsample_bilinear2d: src = scale*(dst+0.5)-0.5 clamped at 0, scale = in/out in fp32), threshold,
+//                         one byte per pixel
+// ------------------------------------------------------------------------------------------------
+struct SegMaskK {
+    int B, K, Hp, Wp, HW, H, W;
+    long long n;
+    const float *coefs;        // [n, K]
+    const int *row_off;        // [B+1]
+    const float *protos;       // [B, K, HW]
+    float *low;                // [n, HW]
+    unsigned char *out;        // [n, H, W] 0 / 1
+    float ry, rx;              // Hp / H, Wp / W in fp32
+};
+constexpr int SEGM_ROWS = 8;
+constexpr int SEGM_KMAX = 64;
+
+__global__ void __launch_bounds__(SEG_THREADS) seg_lowres_kernel(SegMaskK k)
+{
+    __shared__ float cs[SEGM_ROWS][SEGM_KMAX];
+    const int i = blockIdx.y, tid = threadIdx.x;
+    const int px = blockIdx.x * SEG_THREADS + tid;
+    const int r0 = k.row_off[i], r1 = k.row_off[i + 1];
+    const float *P = k.protos + (long long)i * k.K * k.HW;
+    for (int r = r0; r < r1; r += SEGM_ROWS) {
+        const int nr = min(SEGM_ROWS, r1 - r);
+        __syncthreads();
+        for (int idx = tid; idx < SEGM_ROWS * k.K; idx += SEG_THREADS) {
+            const int rr = idx / k.K, kk = idx - rr * k.K;
+            cs[rr][kk] = rr < nr ? k.coefs[(long long)(r + rr) * k.K + kk] : 0.0f;
+        }
+        __syncthreads();
+        if (px < k.HW) {
+            float acc[SEGM_ROWS];
+#pragma unroll
+            for (int rr = 0; rr < SEGM_ROWS; ++rr) acc[rr] = 0.0f;
+            for (int kk = 0; kk < k.K; ++kk) {
+                const float p = P[(long long)kk * k.HW + px];
+#pragma unroll
+                for (int rr = 0; rr < SEGM_ROWS; ++rr) acc[rr] = __fmaf_rn(cs[rr][kk], p, acc[rr]);
+            }
+#pragma unroll
+            for (int rr = 0; rr < SEGM_ROWS; ++rr)
+                if (rr < nr) k.low[(long long)(r + rr) * k.HW + px] = sigmoid_acc(acc[rr]);
+        }
+    }
+}
+
+__device__ __forceinline__ void segm_axis(float scale, int dst, int n_in, int &i0, int &i1, float &l0, float &l1)
+{
+    const float src = fmaxf(__fsub_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), 0.5f), 0.0f);
+    i0 = (int)src;
+    i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+    l1 = __fsub_rn(src, (float)i0);
+    l0 = __fsub_rn(1.0f, l1);
+}
+
+constexpr int SEGM_YCHUNK = 16;      // output lines per block: a thread keeps the x-axis indices / weights of its pixels for all of them
+constexpr int SEGM_STAGE = 8192;     // floats of the low-resolution lines a block stages in shared memory (else it reads them through L1)
+
+template <int VEC>  // output pixels per thread along x (4 when W % 4 == 0: one 32-bit store)
+__global__ void __launch_bounds__(SEG_THREADS) seg_upsample_kernel(SegMaskK k)
+{
+    __shared__ float s_low[SEGM_STAGE];
+    const int WV = k.W / VEC;
+    const int ychunks = (k.H + SEGM_YCHUNK - 1) / SEGM_YCHUNK;
+    const long long r = blockIdx.x / ychunks;
+    const int oy0 = (int)(blockIdx.x - r * ychunks) * SEGM_YCHUNK, oy1 = min(oy0 + SEGM_YCHUNK, k.H);
+    const float *L = k.low + r * k.HW;
+    // the low-resolution lines this block's output lines interpolate between (the source index is monotone in the line)
+    int ylo, yhi, t0, t1;
+    float u0, u1;
+    segm_axis(k.ry, oy0, k.Hp, ylo, t1, u0, u1);
+    segm_axis(k.ry, oy1 - 1, k.Hp, t0, yhi, u0, u1);
+    const bool staged = (yhi - ylo + 1) * k.Wp <= SEGM_STAGE;
+    if (staged) {
+        const int cnt = (yhi - ylo + 1) * k.Wp;
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_low[i] = L[(long long)ylo * k.Wp + i];
+        __syncthreads();
+        L = s_low - (long long)ylo * k.Wp;   // (only ever indexed at lines ylo..yhi)
+    }
+    for (int xv = threadIdx.x; xv < WV; xv += blockDim.x) {
+        int x0[VEC], x1[VEC];
+        float w0[VEC], w1[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) segm_axis(k.rx, xv * VEC + v, k.Wp, x0[v], x1[v], w0[v], w1[v]);
+        for (int oy = oy0; oy < oy1; ++oy) {
+            int y0, y1;
+            float h0, h1;
+            segm_axis(k.ry, oy, k.Hp, y0, y1, h0, h1);
+            const float *L0 = L + (long long)y0 * k.Wp, *L1 = L + (long long)y1 * k.Wp;
+            unsigned char b[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const float top = __fadd_rn(__fmul_rn(w0[v], L0[x0[v]]), __fmul_rn(w1[v], L0[x1[v]]));
+                const float bot = __fadd_rn(__fmul_rn(w0[v], L1[x0[v]]), __fmul_rn(w1[v], L1[x1[v]]));
+                b[v] = __fadd_rn(__fmul_rn(h0, top), __fmul_rn(h1, bot)) > 0.5f ? 1 : 0;
+            }
+            unsigned char *o = k.out + (r * k.H + oy) * k.W + (long long)xv * VEC;
+            if (VEC == 4) *reinterpret_cast<uchar4 *>(o) = make_uchar4(b[0], b[1], b[2], b[3]);
+            else o[0] = b[0];
+        }
+    }
+}
+
 }  // namespace bg

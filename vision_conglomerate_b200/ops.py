@@ -513,6 +513,34 @@ def extra_columns(preds: torch.Tensor, det: Detections, num_classes: int) -> tor
     return flat[det.keep_idxs, 5 + num_classes:]
 
 
+def seg_masks(coefs: torch.Tensor, counts, protos: torch.Tensor, out_size: Tuple[int, int]) -> torch.Tensor:
+    """``inference_seg.post_process_preds`` lines 115-117 for every kept row at once: ``sigmoid(coefs @ protos_i)`` on the
+    protos' grid, bilinear resize (``align_corners=False``) to ``out_size``, ``> 0.5``.  ``coefs [n, K]``: the coefficient
+    columns of the kept rows, image by image (``extra_columns(...)[:, :K]`` of an ``order="image"`` result); ``counts [B]``:
+    rows per image (``Detections.counts``); ``protos [B, K, Hp, Wp]``.  Returns ``bool [n, H, W]`` on the device."""
+    coefs = _req(coefs, "coefs")
+    protos = _req(protos, "protos")
+    if coefs.dim() != 2 or protos.dim() != 4 or coefs.shape[1] != protos.shape[1]:
+        raise RuntimeError("seg_masks: coefs [n, K] and protos [B, K, Hp, Wp] do not fit")
+    dev = _same_device(coefs, protos)
+    B, K, Hp, Wp = (int(v) for v in protos.shape)
+    n, (H, W) = int(coefs.shape[0]), (int(out_size[0]), int(out_size[1]))
+    cnt = torch.as_tensor(counts, dtype=torch.int64).reshape(-1).cpu()
+    if cnt.numel() != B or int(cnt.sum()) != n:
+        raise RuntimeError("seg_masks: counts must hold the rows of each of the B images")
+    off = torch.zeros(B + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(cnt, 0)
+    out = torch.empty(n, H, W, dtype=torch.uint8, device=dev)
+    if n == 0:
+        return out.view(torch.bool)
+    with _on(dev):
+        off_d = off.to(dev, non_blocking=True)
+        low = torch.empty(n, Hp * Wp, dtype=torch.float32, device=dev)
+        check(_lib.lib().bg_seg_masks(coefs.data_ptr(), off_d.data_ptr(), protos.data_ptr(), B, K, Hp, Wp, n, H, W, low.data_ptr(),
+                                      out.data_ptr(), _stream(dev)), "bg_seg_masks")
+    return out.view(torch.bool)
+
+
 def post_process(preds: torch.Tensor, input_shape: Tuple[int, int], num_classes: int, iou_threshold: float = 0.5,
                  score_threshold: float = 0.1, box_allowance: Optional[float] = None,
                  tracked_classes: Optional[Sequence[int]] = None, order: str = "global", na: int = 3,
