@@ -194,7 +194,7 @@ def ref_post_process(preds, num_classes, iou_threshold, score_threshold, box_all
 
 
 def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_threshold, box_allowance=None,
-                         tracked_classes=None, img_size=None):
+                         tracked_classes=None, img_size=None, capture_values=False):
     """Calls the reference's inference_seg.post_process_preds unmodified (inference_seg.py:40-175) and captures the
     arguments / result of its torchvision.ops.batched_nms call and, per surviving image, the box array, the boolean
     masks and the keypoint array it hands to the drawing code."""
@@ -203,7 +203,7 @@ def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_thresh
     import torchvision
     load()
     import inference_seg as inf
-    inf.device = "cpu"  # module-global only defined under __main__, read by the tracked-class filter
+    inf.device = preds.device  # module-global only defined under __main__, read by the tracked-class filter
     cap = {"per_image": [], "masks": [], "keypoints": []}
     real_nms = torchvision.ops.batched_nms
 
@@ -232,6 +232,15 @@ def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_thresh
                     pass
             return _I()
 
+    old_F = inf.F
+    if capture_values:  # the interpolated values behind the boolean masks (inference_seg.py:116), for threshold-band checks
+        cap["values"] = []
+
+        def spy_interpolate(x, *a, **k):
+            out = old_F.interpolate(x, *a, **k)
+            cap["values"].append(out[0].detach().cpu().numpy())
+            return out
+        inf.F = types.SimpleNamespace(interpolate=spy_interpolate)
     old = (torchvision.ops.batched_nms, inf.apply_bboxes, inf.apply_segments, inf.apply_keypoints, inf.Image, inf.STORAGE_PATH)
     import tempfile
     tmp = tempfile.mkdtemp()
@@ -250,6 +259,7 @@ def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_thresh
                                    tracked_classes=list(tracked_classes) if tracked_classes else None)
     finally:
         (torchvision.ops.batched_nms, inf.apply_bboxes, inf.apply_segments, inf.apply_keypoints, inf.Image, inf.STORAGE_PATH) = old
+        inf.F = old_F
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
     return cap

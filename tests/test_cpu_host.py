@@ -304,3 +304,41 @@ def test_image_sharded_loss_matches_big_batch_gloo():
     for rank, loss, same in res:
         assert same, "sharded assignment differs"
         assert abs(loss - ref) <= 1e-9 * abs(ref), (rank, loss, ref)
+
+
+def test_lazy_masks_recognise_the_reference_chain(monkeypatch):
+    """lazy.ProtoTrace / lazy.LazyMasks (inference_seg.py:115-117): the reference's chain
+    ``sigmoid((coefs @ protos[i].reshape(K, -1)).reshape(-1, Hp, Wp))`` -> ``F.interpolate`` -> ``torch.gt(0.5)`` reaches
+    ops.seg_masks with the image's prototypes and the output size, nothing is computed before; any other chain or
+    consumer sees the values ATen would have produced.  (Host logic only: the kernel call is replaced by a recorder.)"""
+    import torch
+    import torch.nn.functional as F
+    from vision_conglomerate_b200 import lazy, ops
+    calls = []
+
+    def fake(coefs, counts, protos, size):
+        calls.append((tuple(coefs.shape), list(counts), tuple(protos.shape), tuple(size)))
+        m = (coefs @ protos[0].reshape(protos.shape[1], -1)).reshape(-1, *protos.shape[2:]).sigmoid()
+        return F.interpolate(m.unsqueeze(0), size=size, mode="bilinear", align_corners=False)[0] > 0.5
+
+    monkeypatch.setattr(lazy, "_on_gpu", lambda t: True)
+    monkeypatch.setattr(ops, "seg_masks", fake)
+    g = torch.Generator().manual_seed(0)
+    protos, coefs, i = torch.randn(3, 8, 6, 10, generator=g), torch.randn(5, 8, generator=g), torch.tensor(1)
+    p = protos.as_subclass(lazy.ProtoTrace)
+
+    def chain(pr, mode="bilinear"):
+        m = (coefs @ pr[i].reshape(pr.shape[1], -1)).reshape(-1, *pr.shape[2:]).sigmoid()
+        kw = dict(align_corners=False) if mode == "bilinear" else {}
+        return F.interpolate(m.unsqueeze(dim=0), size=torch.Size([24, 30]), mode=mode, **kw)
+
+    lz = chain(p)
+    assert isinstance(lz, lazy.LazyMasks) and lz.pending and tuple(lz.shape) == (1, 5, 24, 30) and not calls
+    out = torch.gt(lz, other=0.5).squeeze(dim=0).detach().cpu().numpy()
+    assert calls == [((5, 8), [5], (1, 8, 6, 10), (24, 30))]
+    assert (out == torch.gt(chain(protos), other=0.5)[0].numpy()).all()
+    # another consumer / another chain: the reference's values, no kernel call
+    assert torch.equal(chain(p).sum(), chain(protos).sum())
+    assert torch.equal(chain(p, "nearest") > 0.5, chain(protos, "nearest") > 0.5) and len(calls) == 1
+    assert torch.equal(torch.gt(chain(p), other=0.25), torch.gt(chain(protos), other=0.25)) and len(calls) == 1
+    assert type(p[0]) is lazy.ProtoTrace and type(p * 2) is torch.Tensor and type(p.sum()) is torch.Tensor

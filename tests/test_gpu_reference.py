@@ -334,3 +334,48 @@ def test_segmentation_train_step_patched_equals_unpatched(ns):
     den = sum(float(grads_u[n].double().pow(2).sum()) for n in grads_u)
     print("segmentation train step: %d parameter gradients, global relative L2 error %.2e" % (len(grads_u), (num / den) ** 0.5))
     assert (num / den) ** 0.5 < 2e-5
+
+
+def test_segmentation_inference_zero_edit(ns):
+    """SURVEY 8 f2, inference side, on the REAL classes: the unmodified call sequence of inference_seg.evaluate_frames --
+    ``preds, protos = model(x, inference=True, og_size=...)``; ``post_process_preds(imgs, preds, protos, ...)`` -- with
+    ``dropin.install(inference_seg=module)``: NMS by bg_batched_nms, the per-image boolean masks of lines 115-117 by the
+    two mask kernels (recognised through lazy.ProtoTrace / lazy.LazyMasks).  Box arrays and masks handed to the
+    reference's drawing code against the unpatched torch-CUDA run; a mask pixel may differ only where the unpatched
+    run's interpolated value is within 5e-5 of 0.5."""
+    import inference_seg
+    from vision_conglomerate_b200 import _lib, dropin, ops
+    B, S, C = 3, 128, 5       # (a random-init model keeps hundreds of rows per image: small frames keep the mask arrays small)
+    torch.manual_seed(42)
+    model = ns.SegmentationNet(3, C, ref_harness.model_config("segmentation"), synth.ANCHORS, num_keypoints=0).cuda().eval()
+    imgs = torch.rand(B, 3, S, S, generator=torch.Generator().manual_seed(5)).cuda()
+    for og, iou, thr, tracked in (((150, 200), 0.5, 0.2, None), ((128, 128), 0.35, 0.24, [0, 2, 3])):
+        with torch.no_grad():
+            preds, protos = model(imgs, inference=True, og_size=og)
+        cap_u = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og, capture_values=True)
+        calls = []
+        orig = ops.seg_masks
+        ops.seg_masks = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+        dropin.install(inference_seg=inference_seg)
+        try:
+            n0 = _lib.launch_count()
+            cap_p = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og)
+            launches = _lib.launch_count() - n0
+        finally:
+            dropin.uninstall()
+            ops.seg_masks = orig
+        assert len(cap_u["masks"]) > 0 and len(calls) == len(cap_u["masks"]), (len(calls), len(cap_u["masks"]))
+        assert len(cap_p["per_image"]) == len(cap_u["per_image"]) and len(cap_p["masks"]) == len(cap_u["masks"])
+        assert np.array_equal(np.sort(cap_p["keep"].cpu().numpy()), np.sort(cap_u["keep"].cpu().numpy()))
+        nd = npx = bad = 0
+        for a, b, ma, mb, v in zip(cap_p["per_image"], cap_u["per_image"], cap_p["masks"], cap_u["masks"], cap_u["values"]):
+            assert a.shape == b.shape and ma.shape == mb.shape == v.shape and ma.dtype == np.bool_
+            oa, ob = np.lexsort((a[:, 2], a[:, 1], -a[:, 0])), np.lexsort((b[:, 2], b[:, 1], -b[:, 0]))
+            assert_close(a[oa], b[ob], rtol=1e-5, atol=2e-5 * 400, what="rows")
+            diff = ma[oa] != mb[ob]
+            nd += int(diff.sum())
+            npx += diff.size
+            bad += int((diff & (np.abs(v[ob].astype(np.float64) - 0.5) >= 5e-5)).sum())
+        assert bad == 0, "%d mask pixels differ away from the threshold" % bad
+        print("zero-edit segmentation inference og=%s tracked=%s: %d images, %d masks, %d of %d pixels differ (all on the "
+              "threshold), %d launches of ours" % (og, tracked, len(cap_u["masks"]), sum(len(m) for m in cap_u["masks"]), nd, npx, launches))

@@ -28,7 +28,7 @@ import torch
 from . import ops
 import threading
 
-from .lazy import HeadTrace, LazyPreds, LazyRows, loss_inputs_if_pending
+from .lazy import HeadTrace, LazyPreds, LazyRows, ProtoTrace, loss_inputs_if_pending
 
 _saved: Dict[str, Any] = {}
 
@@ -222,6 +222,17 @@ def _make_post_process_preds(orig):
     return post_process_preds
 
 
+def _make_seg_post_process_preds(orig):
+    def post_process_preds(imgs, preds, protos, num_classes, *args, **kwargs):
+        # lines 62-97 run as written (their torchvision.ops.batched_nms is the re-pointed one); the prototypes are marked
+        # so that the host loop's per-image ``sigmoid(coefs @ protos[i]) -> F.interpolate -> torch.gt(0.5)`` (lines 115-117)
+        # is recognised and runs on the two mask kernels (lazy.ProtoTrace / lazy.LazyMasks)
+        if isinstance(protos, torch.Tensor) and protos.is_cuda and protos.dtype == torch.float32 and protos.dim() == 4 \
+                and not protos.requires_grad and int(protos.shape[1]) <= 64:
+            protos = protos.contiguous().as_subclass(ProtoTrace)
+        return orig(imgs, preds, protos, num_classes, *args, **kwargs)
+    return post_process_preds
+
 
 # ------------------------------------------------------------------------------------------------ f3
 def _make_head_forward(orig):
@@ -283,7 +294,7 @@ _options = {"fuse_train_decode": True, "split_head": True, "fuse_inference": Tru
 
 def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchvision_ops=True, make_anchors=None,
             fuse_train_decode: bool = True, EffiDecHead=None, split_head: bool = True, inference_det=None,
-            fuse_inference: bool = True, SegmentationLoss=None) -> None:
+            fuse_inference: bool = True, SegmentationLoss=None, inference_seg=None) -> None:
     """Re-point the reference's call sites at the CUDA operators.  Pass the reference classes that are
     imported in your process (any subset); ``torchvision_ops=True`` also replaces
     ``torchvision.ops.batched_nms`` (what ``inference_det.py:77`` looks up at call time); ``make_anchors`` is the
@@ -293,7 +304,9 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
     loss reads the head's three conv outputs in place (zero-copy when the model runs channels-last,
     otherwise the pieces are made contiguous -- the copy the concatenation would have been).  ``SegmentationLoss``
     (modules/segmentation_loss.py): its ``forward`` runs the fused detection terms plus the mask-term kernels
-    (overlap_masks=True, BCE, no keypoints -- other configurations keep the reference's code)."""
+    (overlap_masks=True, BCE, no keypoints -- other configurations keep the reference's code).
+    ``inference_seg`` (the reference's script module): its ``post_process_preds`` builds the boolean masks of the kept rows
+    with the mask kernels (inference_seg.py:115-117)."""
     _options["fuse_train_decode"] = bool(fuse_train_decode)
     _options["split_head"] = bool(split_head)
     _options["fuse_inference"] = bool(fuse_inference)
@@ -302,6 +315,9 @@ def install(DetectionDataset=None, DetectionLoss=None, DetectionNet=None, torchv
         # globals at call time (inference_det.py:199-207,229-239)
         _saved["post_process_preds"] = (inference_det, inference_det.post_process_preds)
         inference_det.post_process_preds = _make_post_process_preds(inference_det.post_process_preds)
+    if inference_seg is not None and "inference_seg.post_process_preds" not in _saved:
+        _saved["inference_seg.post_process_preds"] = (inference_seg, inference_seg.post_process_preds)
+        inference_seg.post_process_preds = _make_seg_post_process_preds(inference_seg.post_process_preds)
     if EffiDecHead is not None and "EffiDecHead.forward" not in _saved:
         _saved["EffiDecHead.forward"] = (EffiDecHead, EffiDecHead.__dict__["forward"])
         EffiDecHead.forward = _make_head_forward(EffiDecHead.__dict__["forward"])
@@ -357,6 +373,9 @@ def uninstall() -> None:
         if key in _saved:
             owner, orig = _saved.pop(key)
             owner.forward = orig
+    if "inference_seg.post_process_preds" in _saved:
+        owner, orig = _saved.pop("inference_seg.post_process_preds")
+        owner.post_process_preds = orig
     _detect_plans.clear()
     _saved.pop("DetectionLoss.loss_fn", None)
     _saved.pop("SegmentationLoss.loss_fn", None)

@@ -235,3 +235,135 @@ class LazyPreds(torch.Tensor):
 
         return func(*real(args), **real(kwargs))
 
+
+
+# ------------------------------------------------------------------------------------------------ f2: inference masks
+def _on_gpu(t: torch.Tensor) -> bool:
+    return t.is_cuda
+
+
+class ProtoTrace(torch.Tensor):
+    """Marks the prototype tensor ``protos [B, K, Hp, Wp]`` handed to ``inference_seg.post_process_preds`` so that the
+    per-image chain of its host loop (inference_seg.py:115-117)
+
+        masks = (coefs @ protos[i].reshape(num_masks, -1)).reshape(-1, *protos.shape[2:]).sigmoid()
+        masks = F.interpolate(masks.unsqueeze(dim=0), size=img.shape[1:], mode="bilinear", align_corners=False)
+        masks = torch.gt(masks, other=0.5)
+
+    can be recognised: indexing and reshaping keep the mark (the data is the real data), the matrix product with the
+    kept rows' coefficients returns a :class:`LazyMasks`.  Every other function behaves as on a plain tensor."""
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in (torch.matmul, _T.matmul, _T.__matmul__, _T.__rmatmul__) and len(args) == 2 and not kwargs:
+            a, b = (args[1], args[0]) if func is _T.__rmatmul__ else args
+            if isinstance(b, ProtoTrace) and isinstance(a, torch.Tensor) and not isinstance(a, ProtoTrace) \
+                    and a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[0] and _on_gpu(a) and _on_gpu(b) \
+                    and a.dtype == torch.float32 and b.dtype == torch.float32 and _T.is_contiguous(b) \
+                    and not a.requires_grad and not b.requires_grad:
+                return LazyMasks(a.as_subclass(torch.Tensor), b.as_subclass(torch.Tensor), ())
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **kwargs)
+        # only views of the prototypes stay marked (indexing, reshape); anything computed from them is a plain tensor
+        if isinstance(out, torch.Tensor) and func in (_T.__getitem__, _T.reshape, torch.reshape, _T.view, _T.contiguous,
+                                                      _T.select, torch.select, _T.flatten, torch.flatten):
+            return out.as_subclass(ProtoTrace)
+        if isinstance(out, torch.Tensor):
+            return out.as_subclass(torch.Tensor)
+        return out
+
+
+class LazyMasks(torch.Tensor):
+    """Stands for ``coefs @ proto`` (``coefs [n, K]``, ``proto [K, Hp*Wp]`` of one image) and for what
+    ``inference_seg.post_process_preds`` does to it next -- reshape to ``[n, Hp, Wp]``, ``sigmoid``, ``unsqueeze(0)``,
+    ``F.interpolate(size, "bilinear", align_corners=False)`` -- remembering the steps instead of running them.  The closing
+    ``torch.gt(masks, other=0.5)`` runs the two mask kernels (``ops.seg_masks``: one byte per output pixel instead of five
+    ATen passes with an ``[n, H, W]`` fp32 intermediate).  Any other step, or any other consumer, gets the reference's
+    values: the recorded chain is replayed with ATen first."""
+
+    @staticmethod
+    def __new__(cls, coefs, proto, log, shape=None):
+        shape = (int(coefs.shape[0]), int(proto.shape[1])) if shape is None else tuple(shape)
+        base = torch.empty(1, dtype=coefs.dtype, device=coefs.device).expand(shape)
+        return torch.Tensor._make_subclass(cls, base, False)
+
+    def __init__(self, coefs, proto, log, shape=None):
+        self._bg_coefs, self._bg_proto, self._bg_log = coefs, proto, tuple(log)
+        self._bg_real: Optional[torch.Tensor] = None
+
+    @property
+    def pending(self) -> bool:
+        return self._bg_real is None
+
+    def materialize(self) -> torch.Tensor:
+        if self._bg_real is None:
+            x = self._bg_coefs @ self._bg_proto
+            for func, rest, kw in self._bg_log:
+                x = func(x, *rest, **kw)
+            self._bg_real = x
+        return self._bg_real
+
+    def _then(self, func, rest, kw) -> "LazyMasks":
+        with torch._C.DisableTorchFunctionSubclass():
+            shape = func(torch.empty(tuple(_T.size(self)), device="meta"), *rest, **kw).shape
+        return LazyMasks(self._bg_coefs, self._bg_proto, self._bg_log + ((func, tuple(rest), dict(kw)),), shape)
+
+    def _fused_size(self):
+        """``(Hp, Wp, H, W)`` if the recorded steps are exactly the reference's chain, else ``None``."""
+        import torch.nn.functional as F
+        log = self._bg_log
+        if len(log) != 4 or log[0][0] not in (_T.reshape, torch.reshape, _T.view) or log[1][0] not in (_T.sigmoid, torch.sigmoid) \
+                or log[2][0] not in (_T.unsqueeze, torch.unsqueeze) or log[3][0] is not F.interpolate:
+            return None
+        n, HW = int(self._bg_coefs.shape[0]), int(self._bg_proto.shape[1])
+        with torch._C.DisableTorchFunctionSubclass():
+            s1 = tuple(log[0][0](torch.empty(n, HW, device="meta"), *log[0][1], **log[0][2]).shape)
+        dim = log[2][2].get("dim", log[2][1][0] if log[2][1] else None)
+        kw = dict(log[3][2])
+        size = kw.pop("size", log[3][1][0] if log[3][1] else None)
+        if len(s1) != 3 or s1[0] != n or dim != 0 or len(log[3][1]) > 1 or size is None or len(tuple(size)) != 2 \
+                or kw.pop("mode", "nearest") != "bilinear" or kw.pop("align_corners", None) is not False \
+                or kw.pop("antialias", False) or any(v is not None for v in kw.values()):
+            return None
+        return s1[1], s1[2], int(size[0]), int(size[1])
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        import torch.nn.functional as F
+        kwargs = kwargs or {}
+        me = args[0] if args and isinstance(args[0], LazyMasks) else None
+        if me is not None and func in _META:
+            if func == _T.is_contiguous:
+                return True
+            if func == _T.requires_grad.__get__:
+                return False
+            with torch._C.DisableTorchFunctionSubclass():
+                if func == _T.stride:
+                    return func(torch.empty(tuple(_T.size(me)), device="meta"), *args[1:], **kwargs)
+                return func(*args, **kwargs)
+        if me is not None and me.pending and not any(isinstance(a, torch.Tensor) for a in list(args[1:]) + list(kwargs.values())):
+            if func in (_T.reshape, torch.reshape, _T.view, _T.sigmoid, torch.sigmoid, _T.unsqueeze, torch.unsqueeze, F.interpolate):
+                return me._then(func, args[1:], kwargs)
+            if func in (torch.gt, _T.gt, _T.__gt__):
+                other = kwargs.get("other", args[1] if len(args) > 1 else None)
+                fs = me._fused_size()
+                if fs is not None and isinstance(other, float) and other == 0.5 and fs[0] * fs[1] == int(me._bg_proto.shape[1]) \
+                        and int(me._bg_coefs.shape[1]) <= 64:
+                    from . import ops
+                    Hp, Wp, H, W = fs
+                    n, K = (int(v) for v in me._bg_coefs.shape)
+                    return ops.seg_masks(me._bg_coefs.contiguous(), [n], me._bg_proto.view(1, K, Hp, Wp), (H, W)).unsqueeze(0)
+
+        def real(a):
+            if isinstance(a, LazyMasks):
+                return a.materialize()
+            if isinstance(a, ProtoTrace):
+                return a.as_subclass(torch.Tensor)
+            if isinstance(a, (list, tuple)):
+                return type(a)(real(x) for x in a)
+            if isinstance(a, dict):
+                return {k: real(v) for k, v in a.items()}
+            return a
+
+        return func(*real(args), **real(kwargs))
