@@ -110,7 +110,20 @@ typedef struct {
                                  * with nms_event: decode on `stream` -> event -> NMS on nms_stream -> event -> `stream` (which
                                  * therefore still sees the finished batch; no host synchronisation) */
     void *nms_event;            /* cudaEvent_t of the caller (timing disabled is fine), required with nms_stream */
+    void *host_flag;            /* optional (NULL = off): a 32-bit word in page-locked HOST memory that the device can address
+                                 * (cudaHostAlloc / cudaHostRegister; bg_host_mapped_ptr checks it).  The last kernel of the call
+                                 * stores host_flag_value there once every output of the call is visible to the host, so a caller
+                                 * that ALSO placed out_boxes / out_img / out_keep / out_counts in such memory (batch-1 video
+                                 * frames: a few dozen rows) gets the rows without a device->host copy and without a stream
+                                 * synchronisation: it polls the word (BASELINE config 5; the kernels write through PCIe, which is
+                                 * only sensible for small outputs) */
+    int32_t host_flag_value;    /* value to store (use a fresh value per call, e.g. a sequence number) */
+    int32_t reserved0;
 } bg_detect_params;
+
+/* The device address of page-locked host memory `host_ptr` for the current device, NULL if the device cannot address it
+ * (cudaHostGetDevicePointer); under unified addressing it equals host_ptr. */
+void *bg_host_mapped_ptr(void *host_ptr);
 
 size_t bg_detect_workspace_bytes(const bg_detect_params *p /*host*/, size_t mask_bytes);
 /*   raw_* [B,ny,nx,na,5+C] f32 contiguous, channels [obj, cls*C, tx,ty,tw,th] (common.py:912-931)

@@ -96,6 +96,21 @@ lat = sorted(lat[32:])
 out["c5_batch1_latency_us"] = {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "mean": sum(lat) / len(lat), "frames": len(lat),
                                "rows_last_frame": int(r.pred_boxes.shape[0]), "note": "enqueue + one D2H count read + sync per frame, wall clock"}
 
+# the same with the rows on the HOST every frame: the kernels write into page-locked host memory and store a flag last
+# (DetectPlan(host_result=True), bg_detect_params.host_flag); no device->host copy, no stream synchronisation
+hplan = ops.DetectPlan([tuple(r.shape) for r in frames[0]], anc, (640, 640), 80, dev, (720, 1280), 0.35, 0.3, 4, synth.tracked_classes_default(),
+                       host_result=True)
+lat = []
+for f in range(1032):
+    t0 = time.perf_counter()
+    hplan.enqueue(frames[f % 32])
+    h = hplan.result_host()
+    lat.append((time.perf_counter() - t0) * 1e6)
+lat = sorted(lat[32:])
+out["c5_batch1_latency_host_rows_us"] = {"p50": lat[len(lat) // 2], "p99": lat[int(len(lat) * 0.99)], "mean": sum(lat) / len(lat), "frames": len(lat),
+                                         "rows_last_frame": int(h.rows.shape[0]),
+                                         "note": "enqueue + poll of the flag the last kernel stores in page-locked host memory; rows [k, 6] on the host, wall clock"}
+
 # torchvision-CUDA on the same candidates: decode with our kernel, then its batched_nms over ALL candidates (the reference path)
 try:
     import torchvision

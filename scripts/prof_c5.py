@@ -44,6 +44,20 @@ for f in range(500):
     r = plan.result()
     tot4.append((time.perf_counter() - t0) * 1e6)
 print("enqueue + result() (rows stay on the device): p50 %.1f us, p99 %.1f us" % (med(tot4), sorted(tot4)[int(len(tot4) * 0.99)]))
+# host-result plan: the kernels write rows / counts into page-locked host memory and store a flag last; the host polls it
+hplan = ops.DetectPlan([tuple(r.shape) for r in frames[0]], anc, (640, 640), 80, dev, (720, 1280), 0.35, 0.3, 4, synth.tracked_classes_default(),
+                       host_result=True)
+for f in range(64):
+    hplan.enqueue(frames[f % 32]); hplan.result_host()
+tot5, enq5 = [], []
+for f in range(1000):
+    t0 = time.perf_counter()
+    hplan.enqueue(frames[f % 32])
+    t1 = time.perf_counter()
+    h = hplan.result_host()
+    tot5.append((time.perf_counter() - t0) * 1e6); enq5.append((t1 - t0) * 1e6)
+print("host-result plan (no copy, no sync; poll the flag): p50 %.1f us, p99 %.1f us (enqueue %.1f), rows on the host %d"
+      % (med(tot5), sorted(tot5)[int(len(tot5) * 0.99)], med(enq5), int(h.rows.shape[0])))
 # CUDA graph replay of the same two launches from a static input
 static = [t.clone() for t in frames[0]]
 plan.enqueue(static); plan.result()

@@ -456,6 +456,51 @@ def test_detect_config5_video_frames(ops):
     assert got.size > 0
 
 
+def test_detect_host_result_plan(ops):
+    """``DetectPlan(host_result=True)`` (bg_detect_params.host_flag): the kernels write rows and counts into page-locked host
+    memory and store a sequence number last; the host polls it instead of copying and synchronising.  Rows, image
+    offsets and candidate indices must be bitwise those of the ordinary plan: batch-1 frames of config 5 (the per-image
+    kernel stores the flag itself), a small batch in the reference's global row order and on the general engine (the
+    flag is stored by a one-thread kernel behind them)."""
+    H, W, C = 640, 640, 80
+    tracked = list(synth.tracked_classes_default())
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    d0 = torch.device("cuda", 0)
+    frames = [[dev(r) for r in synth.raw_head_outputs(1, H, W, C, "TP", seed=7 + f)] for f in range(12)]
+    shapes = [tuple(r.shape) for r in frames[0]]
+    a = ops.DetectPlan(shapes, anc, (H, W), C, d0, (720, 1280), 0.35, 0.3, 4, tracked)
+    b = ops.DetectPlan(shapes, anc, (H, W), C, d0, (720, 1280), 0.35, 0.3, 4, tracked, host_result=True)
+    rows = 0
+    for fr in frames * 3:
+        a.enqueue(fr)
+        da = a.result()
+        b.enqueue(fr)
+        hb = b.result_host()
+        assert np.array_equal(hb.rows.view(np.uint32), da.pred_boxes.cpu().numpy().view(np.uint32))
+        assert list(hb.offsets) == [0, int(da.counts[0])]
+        b.enqueue(fr)
+        db = b.result()                                     # the Detections form of the same buffers (host tensors)
+        assert not db.pred_boxes.is_cuda and torch.equal(db.keep_idxs, da.keep_idxs.cpu()) and torch.equal(db.counts, da.counts)
+        rows += hb.rows.shape[0]
+    assert rows > 0
+    B = 4
+    raws = [dev(r) for r in synth.raw_head_outputs(B, 256, 256, C, "T", seed=3)]
+    shapes = [tuple(r.shape) for r in raws]
+    for order, path in (("image", "auto"), ("global", "auto"), ("image", "general"), ("global", "general")):
+        a = ops.DetectPlan(shapes, anc, (256, 256), C, d0, None, 0.65, 0.001, 4, None, order, 0, path)
+        b = ops.DetectPlan(shapes, anc, (256, 256), C, d0, None, 0.65, 0.001, 4, None, order, 0, path, host_result=True)
+        for _ in range(3):
+            a.enqueue(raws)
+            da = a.result()
+            b.enqueue(raws)
+            db = b.result()
+            assert da.pred_boxes.shape[0] > 0
+            assert torch.equal(db.pred_boxes.view(torch.int32), da.pred_boxes.cpu().view(torch.int32)), (order, path)
+            assert torch.equal(db.keep_idxs, da.keep_idxs.cpu()) and torch.equal(db.sample_idxs, da.sample_idxs.cpu())
+            assert torch.equal(db.counts, da.counts) and torch.equal(db.candidates, da.candidates)
+    print("host-result plan: %d rows over 36 batch-1 frames and 12 small batches, bitwise those of the ordinary plan" % rows)
+
+
 @pytest.mark.parametrize("name", ["dec_sq64", "dec_rect_rescale", "dec_rect_norescale", "dec_T128"])
 def test_decode_scale_golden(ops, name):
     g = golden(name)

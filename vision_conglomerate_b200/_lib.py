@@ -24,7 +24,7 @@ SYMBOLS = (
     "bg_strerror", "bg_version", "bg_launch_count", "bg_sizeof_detect_params", "bg_sizeof_loss_params", "bg_profile_events", "bg_profile_events_loss",
     "bg_profile_stamps", "bg_profile_stamps_per_image", "bg_profile_decode_cycles",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
-    "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd",
+    "bg_host_mapped_ptr", "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd",
     "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine",
@@ -52,6 +52,9 @@ class DetectParams(C.Structure):
         ("throughput", C.c_int32),
         ("nms_stream", C.c_void_p),
         ("nms_event", C.c_void_p),
+        ("host_flag", C.c_void_p),
+        ("host_flag_value", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 
@@ -141,6 +144,8 @@ def lib() -> C.CDLL:
     L.bg_batched_nms_workspace_bytes.argtypes = [i64, i64, sz]
     L.bg_batched_nms_workspace_bytes.restype = sz
     L.bg_batched_nms.argtypes = [vp, vp, vp, i64, f64, i64, vp, vp, vp, sz, sz, vp]
+    L.bg_host_mapped_ptr.argtypes = [vp]
+    L.bg_host_mapped_ptr.restype = vp
     L.bg_detect_workspace_bytes.argtypes = [C.POINTER(DetectParams), sz]
     L.bg_detect_workspace_bytes.restype = sz
     L.bg_detect.argtypes = [vp, vp, vp, C.POINTER(DetectParams), vp, vp, vp, vp, vp, sz, sz, vp]

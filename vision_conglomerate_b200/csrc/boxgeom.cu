@@ -285,6 +285,12 @@ void bg_profile_stamps(void *dev_buf) { g_prof_stamps = (unsigned long long *)de
 void bg_profile_decode_cycles(void *dev_buf) { g_prof_cycles = (unsigned long long *)dev_buf; }
 int bg_profile_stamps_per_image(void) { return INMS_STAMPS; }
 size_t bg_sizeof_detect_params(void) { return sizeof(bg_detect_params); }
+void *bg_host_mapped_ptr(void *host_ptr)
+{
+    void *d = nullptr;
+    if (!host_ptr || cudaHostGetDevicePointer(&d, host_ptr, 0) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return d;
+}
 size_t bg_sizeof_loss_params(void) { return sizeof(bg_loss_params); }
 size_t bg_sizeof_seg_params(void) { return sizeof(bg_seg_params); }
 
@@ -466,7 +472,11 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         }
         st = (cudaStream_t)pp->nms_stream;
     }
-    auto rejoin = [&]() -> int {   // `stream` continues behind the NMS kernels
+    auto rejoin = [&](bool flag_written = false) -> int {   // `stream` continues behind the NMS kernels
+        if (pp->host_flag && !flag_written) {   // (the per-image kernel in image order stores the flag itself)
+            host_flag_kernel<<<1, 1, 0, st>>>((int32_t *)pp->host_flag, pp->host_flag_value);
+            BG_LAUNCH_CHECK();
+        }
         if (!two_streams) return BG_OK;
         if (cudaEventRecord((cudaEvent_t)pp->nms_event, st) != cudaSuccess ||
             cudaStreamWaitEvent(st_dec, (cudaEvent_t)pp->nms_event, 0) != cudaSuccess) {
@@ -493,6 +503,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
         q.out_boxes = out_boxes; q.out_img = reinterpret_cast<long long *>(out_img);
         q.out_keep = reinterpret_cast<long long *>(out_keep); q.out_counts = out_counts;
         q.stamps = g_prof_stamps;
+        q.host_flag = (int32_t *)pp->host_flag; q.host_flag_value = pp->host_flag_value;
         {   // two CTAs per image (helper + main) while every CTA of the grid can be resident at once
             static const int split_env = []() { const char *e = getenv("BG_NMS_SPLIT"); return e ? atoi(e) : -1; }();
             // (throughput mode, 1024-thread kernel: less total SM time matters more than latency; the lean kernel runs next
@@ -533,7 +544,7 @@ static int detect_impl(const float *raw_sm, const float *raw_md, const float *ra
                                                                            reinterpret_cast<long long *>(out_keep), out_counts);
             BG_LAUNCH_CHECK();
         }
-        return rejoin();
+        return rejoin(pp->order == 0);
     }
 
     // ---- general path: segmented engine over the compacted survivor lists ----

@@ -418,6 +418,14 @@ __global__ void __launch_bounds__(256) detect_output_kernel(SegNms p, DetectK k,
 
 // general NMS path: gather the tile slots of every image into the segment layout of the segmented NMS
 // engine (keys of image b compacted at seg_off[b] = b * seg_stride) and initialise its header.
+// bg_detect_params.host_flag for the paths whose last kernel has no single last writer: everything the stream did before
+// this launch is complete; make it visible to the host and tell the polling thread
+__global__ void host_flag_kernel(int32_t *flag, int value)
+{
+    __threadfence_system();
+    *((volatile int32_t *)flag) = value;
+}
+
 __global__ void __launch_bounds__(1024) detect_compact_kernel(SegNms p, DetectK k, TilePlan tp, const int *tile_count,
                                                               long long seg_stride, int32_t *out_counts)
 {

@@ -85,6 +85,8 @@ struct ImgNmsK {
     float *out_boxes;
     long long *out_img, *out_keep;
     int32_t *out_counts;
+    int32_t *host_flag;   // optional: word in mapped host memory, written last (bg_detect_params.host_flag)
+    int host_flag_value;
     unsigned long long *stamps;  // optional [B, INMS_STAMPS] globaltimer (ns) at the stage boundaries (profiling hook)
     // split mode (two CTAs per image when the GPU has room): the helper tests a share of the pairs and sorts the keys
     int split;
@@ -668,7 +670,8 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
     INMS_STAMP(7);
 
     // last image to finish: totals and status
-    __threadfence();
+    if (k.host_flag) __threadfence_system();   // (the outputs may live in mapped host memory)
+    else __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned d = atomicAdd(&k.hdr->done, 1u);
@@ -677,6 +680,10 @@ __global__ void __launch_bounds__(Cfg::LEAN ? 576 : Cfg::THREADS, Cfg::LEAN ? 2 
             const u64 v = *((volatile u64 *)(k.chain + k.B));
             k.out_counts[0] = (int)(v & CHAIN_VALUE);
             k.out_counts[1] = *((volatile int *)&k.hdr->status);
+            if (k.host_flag && k.order == 0) {   // everything of this call is written: tell the polling host thread
+                __threadfence_system();
+                *((volatile int32_t *)k.host_flag) = k.host_flag_value;
+            }
         }
     }
 }

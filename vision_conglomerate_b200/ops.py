@@ -184,14 +184,19 @@ class DetectPlan:
     batches of the same shape.  ``enqueue`` launches the kernels on the current stream without any host
     synchronisation; ``result`` performs the single device->host read the reference signature forces.
     ``throughput=True`` tunes the launches for several batches in flight (see :class:`DetectPipeline`): one NMS CTA
-    per image instead of main + helper, no programmatic dependent launch."""
+    per image instead of main + helper, no programmatic dependent launch.
+    ``host_result=True`` (batch-1 video frames, BASELINE config 5): the output buffers live in page-locked host memory
+    that the kernels write directly, and the last kernel stores a sequence number there (``bg_detect_params.host_flag``);
+    ``result_host`` then polls that word -- no device->host copy, no stream synchronisation.  Meant for outputs of a few
+    hundred rows: every row crosses PCIe as the kernel writes it."""
 
     def __init__(self, shapes: Sequence[Tuple[int, ...]], anchors3: Sequence, input_shape: Tuple[int, int],
                  num_classes: int, device: torch.device, og_size: Optional[Tuple[int, int]] = None,
                  iou_threshold: float = 0.5, score_threshold: float = 0.1, box_allowance: Optional[float] = None,
                  tracked_classes: Optional[Sequence[int]] = None, order: str = "image", variant: int = 0,
-                 nms_path: str = "auto", predecoded: bool = False, throughput: bool = False):
+                 nms_path: str = "auto", predecoded: bool = False, throughput: bool = False, host_result: bool = False):
         self.predecoded = bool(predecoded)
+        self.host_result = bool(host_result)
         if len(shapes) != 3 or any(len(sh) != 5 for sh in shapes):
             raise RuntimeError("detect: expected three [B, ny, nx, na, 5+C] head outputs")
         B, _, _, na, D = shapes[0]
@@ -239,13 +244,29 @@ class DetectPlan:
         n = B * self.N
         # counts and rows share one device allocation ([counts | pad | rows]) so that result_host() can bring both to the
         # host with ONE copy
-        self._hdr_bytes = ((2 + 2 * B) * 4 + 255) // 256 * 256
-        self._packed = torch.empty(self._hdr_bytes + n * 24, dtype=torch.uint8, device=device)
-        self.out_boxes = self._packed[self._hdr_bytes:].view(torch.float32).view(n, 6)
+        self._hdr_bytes = ((3 + 2 * B) * 4 + 255) // 256 * 256        # (one more word: the host flag of host_result plans)
         self._host_packed = None
         self._rows_guess = 256
-        self.out_img = torch.empty(n, dtype=torch.int64, device=device)
-        self.out_keep = torch.empty(n, dtype=torch.int64, device=device)
+        if self.host_result:
+            # [counts | flag | pad | rows], the image and candidate index of every row: page-locked host memory, written by
+            # the kernels through the device's mapping of it (under unified addressing the same address)
+            self._packed = torch.empty(self._hdr_bytes + n * 24, dtype=torch.uint8).pin_memory()
+            self.out_img = torch.empty(n, dtype=torch.int64).pin_memory()
+            self.out_keep = torch.empty(n, dtype=torch.int64).pin_memory()
+            with _on(device):
+                for t in (self._packed, self.out_img, self.out_keep):
+                    if _lib.lib().bg_host_mapped_ptr(t.data_ptr()) != t.data_ptr():
+                        raise RuntimeError("detect: page-locked host memory is not addressable by the device at its own address")
+            self._np_hdr = self._packed[: self._hdr_bytes].view(torch.int32).numpy()
+            self._np_rows = self._packed[self._hdr_bytes:].view(torch.float32).view(n, 6).numpy()
+            self._flag_idx, self._seq = 2 + 2 * B, 0
+            self._np_hdr[self._flag_idx] = 0
+            p.host_flag = self._packed.data_ptr() + 4 * self._flag_idx
+        else:
+            self._packed = torch.empty(self._hdr_bytes + n * 24, dtype=torch.uint8, device=device)
+            self.out_img = torch.empty(n, dtype=torch.int64, device=device)
+            self.out_keep = torch.empty(n, dtype=torch.int64, device=device)
+        self.out_boxes = self._packed[self._hdr_bytes:].view(torch.float32).view(n, 6)
         self.counts = self._packed[: (2 + 2 * B) * 4].view(torch.int32)
         self.key = (device.index, "detect")
         self.ws_tag = "detect"   # plans that run concurrently on different streams need distinct scratch: set a distinct tag
@@ -304,6 +325,9 @@ class DetectPlan:
         if need == 0:
             raise RuntimeError("detect: invalid parameters")
         ws = _workspace(self.dev, self.ws_tag, need)
+        if self.host_result:
+            self._seq = self._seq % 0x7fffffff + 1      # a fresh value per call: the word still holds the previous one
+            p.host_flag_value = self._seq
         if self.predecoded:
             check(L.bg_post_process(self.raws[0].data_ptr(), C.byref(p), self.out_boxes.data_ptr(), self.out_img.data_ptr(),
                                     self.out_keep.data_ptr(), self.counts.data_ptr(), ws.data_ptr(), ws.numel(),
@@ -318,10 +342,26 @@ class DetectPlan:
         with _on(self.dev):
             return self._result()
 
+    def _wait_host_flag(self) -> None:
+        """Spin on the word the last kernel of the call stores in page-locked host memory (no CUDA call on the way);
+        every ~2 ms make sure the stream has not finished without it (a failed launch)."""
+        hdr, i, seq = self._np_hdr, self._flag_idx, self._seq
+        spins = 0
+        while hdr[i] != seq:
+            spins += 1
+            if spins % 20000 == 0 and torch.cuda.current_stream(self.dev).query() and hdr[i] != seq:
+                torch.cuda.current_stream(self.dev).synchronize()
+                if hdr[i] != seq:
+                    raise RuntimeError("detect: the kernels finished without storing the host flag")
+
     def _result(self) -> Detections:
         B = self.B
         while True:
-            h = _read_counts(self.counts, "detect")
+            if self.host_result:
+                self._wait_host_flag()
+                h = self.counts
+            else:
+                h = _read_counts(self.counts, "detect")
             status = int(h[1])
             if not status and not _nms_path_hint:   # the common case, with as few tensor operations as possible (batch-1 latency)
                 hc = h.clone()
@@ -385,6 +425,8 @@ class DetectPlan:
     def enqueue_host_copy(self) -> None:
         """Queue ONE device->host copy of [counts | rows] behind the kernels of the last ``enqueue`` (pinned buffer;
         sized for the row count of recent batches plus head room, the rare overflow is fetched by ``result_host``)."""
+        if self.host_result:
+            return                              # the kernels write the host buffer themselves
         if self._host_packed is None:
             self._host_packed = torch.empty(self._packed.numel(), dtype=torch.uint8).pin_memory()
         n = min(self._packed.numel(), self._hdr_bytes + self._rows_guess * 24)
@@ -397,9 +439,21 @@ class DetectPlan:
         ``.cpu()`` calls: what the reference's host loop builds at inference_det.py:100-129 (``boxes.detach().cpu().numpy()``
         per image, after the tracked-class filter), from one pinned buffer filled by one asynchronous copy."""
         import numpy as np
+        B = self.B
+        if self.host_result:
+            if self.params.order != 0:
+                raise RuntimeError("result_host: needs order='image' (rows grouped by image)")
+            self._wait_host_flag()
+            hdr = self._np_hdr
+            if hdr[1]:                      # a status bit (rare): the general route re-runs on the right engine
+                with _on(self.dev):
+                    self._result()
+            k = int(hdr[0])
+            offsets = np.zeros(B + 1, np.int64)
+            np.cumsum(hdr[2: 2 + B], out=offsets[1:])
+            return HostDetections(self._np_rows[:k], offsets)
         if getattr(self, "_copied_rows", None) is None:
             self.enqueue_host_copy()
-        B = self.B
         with _on(self.dev):
             torch.cuda.current_stream(self.dev).synchronize()
             hdr = self._host_packed[: (2 + 2 * B) * 4].view(torch.int32)
