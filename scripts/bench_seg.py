@@ -30,7 +30,8 @@ def timed(fn, iters):
 
 
 QUICK = "--quick" in sys.argv     # one case, no reference run (for ncu)
-for B, S, C, K, G in (((16, 640, 80, 32, 8),) if QUICK else ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20))):
+MASKS_ONLY = "--masks-only" in sys.argv
+for B, S, C, K, G in (() if MASKS_ONLY else ((16, 640, 80, 32, 8),) if QUICK else ((16, 640, 80, 32, 8), (64, 640, 80, 32, 20))):
     preds, protos, t, masks = synth.seg_inputs(B, S, S, C, K, G, seed=11)
     preds = [p.to(dev).requires_grad_(True) for p in preds]
     protos = protos.to(dev).requires_grad_(True)

@@ -467,32 +467,41 @@ struct SegMaskK {
     unsigned char *out;        // [n, H, W] 0 / 1
     float ry, rx;              // Hp / H, Wp / W in fp32
 };
-constexpr int SEGM_ROWS = 8;
+constexpr int SEGM_ROWS = 16;
 constexpr int SEGM_KMAX = 64;
 
 __global__ void __launch_bounds__(SEG_THREADS) seg_lowres_kernel(SegMaskK k)
 {
-    __shared__ float cs[SEGM_ROWS][SEGM_KMAX];
+    __shared__ __align__(16) float cs[SEGM_ROWS][SEGM_KMAX];   // the coefficients of 16 rows, zero-padded to a multiple of four
     const int i = blockIdx.y, tid = threadIdx.x;
     const int px = blockIdx.x * SEG_THREADS + tid;
     const int r0 = k.row_off[i], r1 = k.row_off[i + 1];
     const float *P = k.protos + (long long)i * k.K * k.HW;
+    const int K4 = (k.K + 3) & ~3;
     for (int r = r0; r < r1; r += SEGM_ROWS) {
         const int nr = min(SEGM_ROWS, r1 - r);
         __syncthreads();
-        for (int idx = tid; idx < SEGM_ROWS * k.K; idx += SEG_THREADS) {
-            const int rr = idx / k.K, kk = idx - rr * k.K;
-            cs[rr][kk] = rr < nr ? k.coefs[(long long)(r + rr) * k.K + kk] : 0.0f;
+        for (int idx = tid; idx < SEGM_ROWS * K4; idx += SEG_THREADS) {
+            const int rr = idx / K4, kk = idx - rr * K4;
+            cs[rr][kk] = (rr < nr && kk < k.K) ? k.coefs[(long long)(r + rr) * k.K + kk] : 0.0f;
         }
         __syncthreads();
         if (px < k.HW) {
             float acc[SEGM_ROWS];
 #pragma unroll
             for (int rr = 0; rr < SEGM_ROWS; ++rr) acc[rr] = 0.0f;
-            for (int kk = 0; kk < k.K; ++kk) {
-                const float p = P[(long long)kk * k.HW + px];
+            for (int kk = 0; kk < K4; kk += 4) {   // products added in ascending k, as a row-times-matrix product does
+                float p[4];
 #pragma unroll
-                for (int rr = 0; rr < SEGM_ROWS; ++rr) acc[rr] = __fmaf_rn(cs[rr][kk], p, acc[rr]);
+                for (int j = 0; j < 4; ++j) p[j] = kk + j < k.K ? P[(long long)(kk + j) * k.HW + px] : 0.0f;
+#pragma unroll
+                for (int rr = 0; rr < SEGM_ROWS; ++rr) {
+                    const float4 c = *reinterpret_cast<const float4 *>(&cs[rr][kk]);   // one broadcast load per four products
+                    acc[rr] = __fmaf_rn(c.x, p[0], acc[rr]);
+                    acc[rr] = __fmaf_rn(c.y, p[1], acc[rr]);
+                    acc[rr] = __fmaf_rn(c.z, p[2], acc[rr]);
+                    acc[rr] = __fmaf_rn(c.w, p[3], acc[rr]);
+                }
             }
 #pragma unroll
             for (int rr = 0; rr < SEGM_ROWS; ++rr)
@@ -511,13 +520,70 @@ __device__ __forceinline__ void segm_axis(float scale, int dst, int n_in, int &i
 }
 
 constexpr int SEGM_YCHUNK = 16;      // output lines per block: a thread keeps the x-axis indices / weights of its pixels for all of them
-constexpr int SEGM_STAGE = 8192;     // floats of the low-resolution lines a block stages in shared memory (else it reads them through L1)
+constexpr int SEGM_STAGE = 2560;     // floats of the low-resolution lines a block stages in shared memory (else it reads them through L1)
+
+// the lines of one block: VEC output pixels per thread along x; the low-resolution lines come from the block's
+// shared-memory window (32-bit shared addresses) or, when the window does not fit, from the global array
+template <int VEC, bool STAGED>
+__device__ __forceinline__ void segm_lines(const SegMaskK &k, const float *__restrict__ L, const float *s_low, int ylo,
+                                           const int4 *s_y, int nl, unsigned char *out0)
+{
+    const int WV = k.W / VEC;
+    for (int xv = threadIdx.x; xv < WV; xv += blockDim.x) {
+        int x0[VEC], x1[VEC];
+        float w0[VEC], w1[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            segm_axis(k.rx, xv * VEC + v, k.Wp, x0[v], x1[v], w0[v], w1[v]);
+            asm volatile("" : "+r"(x0[v]), "+r"(x1[v]));   // keep the indices (else they are recomputed from the floats per use)
+        }
+        // the horizontal interpolation of a source line serves every output line between the same two source lines
+        // (four of them when the masks are enlarged four times): kept in registers, and a line that was the lower one
+        // becomes the upper one without being read again.  Same operations in the same order for every pixel.
+        float top[VEC], bot[VEC];
+        int py0 = -1, py1 = -1;
+        unsigned char *o = out0 + (long long)xv * VEC;
+        for (int l = 0; l < nl; ++l, o += k.W) {
+            const int4 yy = s_y[l];
+            const int y0 = yy.x, y1 = yy.y;
+            const float h0 = __int_as_float(yy.z), h1 = __int_as_float(yy.w);
+            if (y0 != py0) {
+                if (y0 == py1) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) top[v] = bot[v];
+                } else {
+                    const float *L0 = STAGED ? s_low + (y0 - ylo) * k.Wp : L + (long long)y0 * k.Wp;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) top[v] = __fadd_rn(__fmul_rn(w0[v], L0[x0[v]]), __fmul_rn(w1[v], L0[x1[v]]));
+                }
+                py0 = y0;
+            }
+            if (y1 != py1) {
+                if (y1 == y0) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) bot[v] = top[v];
+                } else {
+                    const float *L1 = STAGED ? s_low + (y1 - ylo) * k.Wp : L + (long long)y1 * k.Wp;
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) bot[v] = __fadd_rn(__fmul_rn(w0[v], L1[x0[v]]), __fmul_rn(w1[v], L1[x1[v]]));
+                }
+                py1 = y1;
+            }
+            unsigned word = 0;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+                word |= (__fadd_rn(__fmul_rn(h0, top[v]), __fmul_rn(h1, bot[v])) > 0.5f ? 1u : 0u) << (8 * v);
+            if (VEC == 4) *reinterpret_cast<unsigned *>(o) = word;
+            else o[0] = (unsigned char)word;
+        }
+    }
+}
 
 template <int VEC>  // output pixels per thread along x (4 when W % 4 == 0: one 32-bit store)
 __global__ void __launch_bounds__(SEG_THREADS) seg_upsample_kernel(SegMaskK k)
 {
     __shared__ float s_low[SEGM_STAGE];
-    const int WV = k.W / VEC;
+    __shared__ int4 s_y[SEGM_YCHUNK];   // per output line of the block: the two source lines and their weights, worked out once
     const int ychunks = (k.H + SEGM_YCHUNK - 1) / SEGM_YCHUNK;
     const long long r = blockIdx.x / ychunks;
     const int oy0 = (int)(blockIdx.x - r * ychunks) * SEGM_YCHUNK, oy1 = min(oy0 + SEGM_YCHUNK, k.H);
@@ -531,31 +597,17 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_upsample_kernel(SegMaskK k)
     if (staged) {
         const int cnt = (yhi - ylo + 1) * k.Wp;
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_low[i] = L[(long long)ylo * k.Wp + i];
-        __syncthreads();
-        L = s_low - (long long)ylo * k.Wp;   // (only ever indexed at lines ylo..yhi)
     }
-    for (int xv = threadIdx.x; xv < WV; xv += blockDim.x) {
-        int x0[VEC], x1[VEC];
-        float w0[VEC], w1[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) segm_axis(k.rx, xv * VEC + v, k.Wp, x0[v], x1[v], w0[v], w1[v]);
-        for (int oy = oy0; oy < oy1; ++oy) {
-            int y0, y1;
-            float h0, h1;
-            segm_axis(k.ry, oy, k.Hp, y0, y1, h0, h1);
-            const float *L0 = L + (long long)y0 * k.Wp, *L1 = L + (long long)y1 * k.Wp;
-            unsigned char b[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const float top = __fadd_rn(__fmul_rn(w0[v], L0[x0[v]]), __fmul_rn(w1[v], L0[x1[v]]));
-                const float bot = __fadd_rn(__fmul_rn(w0[v], L1[x0[v]]), __fmul_rn(w1[v], L1[x1[v]]));
-                b[v] = __fadd_rn(__fmul_rn(h0, top), __fmul_rn(h1, bot)) > 0.5f ? 1 : 0;
-            }
-            unsigned char *o = k.out + (r * k.H + oy) * k.W + (long long)xv * VEC;
-            if (VEC == 4) *reinterpret_cast<uchar4 *>(o) = make_uchar4(b[0], b[1], b[2], b[3]);
-            else o[0] = b[0];
-        }
+    if (threadIdx.x < oy1 - oy0) {
+        int y0, y1;
+        float h0, h1;
+        segm_axis(k.ry, oy0 + threadIdx.x, k.Hp, y0, y1, h0, h1);
+        s_y[threadIdx.x] = make_int4(y0, y1, __float_as_int(h0), __float_as_int(h1));
     }
+    __syncthreads();
+    unsigned char *out0 = k.out + (r * k.H + oy0) * k.W;
+    if (staged) segm_lines<VEC, true>(k, L, s_low, ylo, s_y, oy1 - oy0, out0);
+    else segm_lines<VEC, false>(k, L, s_low, ylo, s_y, oy1 - oy0, out0);
 }
 
 }  // namespace bg
