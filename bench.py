@@ -700,6 +700,46 @@ def train_leg(args, torch, dist, ops, synth, L, devc, world, rank, barrier):
         "interleaved_forms_frac": {f: forms[f].get("graph", forms[f]["eager"]).get("hbm_frac") for f in ("raw", "decoded")},
     }
     del inputs["decoded"]
+    # ---- weak scaling of the same step (N > 1): every rank runs a FULL batch of its own (per-GPU work fixed as N grows),
+    #      same captured step incl. the NCCL all-reduce of the loss terms; the strong-scaling numbers above are configs[2]
+    if world > 1:
+        try:
+            gw = torch.Generator(device=devc).manual_seed(w["pseed"] + 1000 + rank)
+            t_w = synth.targets(Bf, G, C, w["tseed"] + rank).to(devc)
+            split_w = []
+            for ny, nx in synth.fmap_shapes(H, W):
+                split_w.append(tuple(torch.randn(Bf, ny, nx, 3, n_, generator=gw, device=devc).squeeze(-1).contiguous().requires_grad_(True)
+                                     if n_ == 1 else torch.randn(Bf, ny, nx, 3, n_, generator=gw, device=devc).requires_grad_(True)
+                                     for n_ in (1, C, 4)))
+            cells_w = [Bf * ny * nx * 3 for ny, nx in synth.fmap_shapes(H, W)]
+            gsw = ops.LossStepGraph(split_w, t_w, anc, cfg, input_form="split", cells=cells_w)
+            for _ in range(3):
+                gsw.replay()
+            per = []
+            for _r in range(3):
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(K):
+                    gsw.replay()
+                b.record()
+                barrier()
+                tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=devc)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                per.append(float(tt.item()) / K)
+            ms_w = min(per)
+            lw = float(gsw.combined)
+            if not (lw == lw and abs(lw) < 1e6):
+                raise RuntimeError("weak-scaling step: combined loss %r" % lw)
+            out["train"]["weak_scaling"] = {
+                "value": world * Bf / (ms_w * 1e-3), "unit": "img/s", "ms_per_step": ms_w, "per_gpu_batch": Bf, "global_batch": world * Bf,
+                "scaling": "weak", "region_ms_per_step": per, "combined_loss_of_the_global_batch": lw,
+                "what": "every rank runs its own batch of %d images (split form, CUDA-graph replay incl. the NCCL all-reduce of the "
+                        "15 loss terms); max over ranks" % Bf}
+            del gsw, split_w
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            out["train"]["weak_scaling"] = {"error": repr(ex)}
     # ---- e2e_train: pinned host conv outputs -> H2D -> fwd+bwd -> D2H of the loss, every step (primary form)
     try:
         host = [tuple(q.detach().cpu().pin_memory() for q in p) for p in inputs[primary]]
