@@ -126,9 +126,10 @@ def test_dropin_keeps_reference_signatures():
         # the cell grid stays the reference's own (cached per shape)
         net = ns.DecodeOnly(80)
         assert torch.equal(ns.DetectionNet._make_2dgrid(net, 5, 4), _saved_grid(dropin)(net, 5, 4))
-        # out-of-scope variants are delegated to the reference's original callable (broadcasting CIoU form)
+        # the broadcasting CIoU form (detection_loss.py:231-234) is served by the CUDA operator too: no CPU fallback
         p4 = torch.rand(2, 5, 4) + 0.1
-        assert ns.DetectionLoss.compute_ciou(p4, p4[:, 0]).shape[:2] == (2, 5)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            ns.DetectionLoss.compute_ciou(p4, p4[:, 0])
     finally:
         dropin.uninstall()
     assert not any(dropin.installed().values())

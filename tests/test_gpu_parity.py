@@ -590,6 +590,17 @@ def test_ciou(ops):
     assert_close(p.grad.cpu().numpy(), g["grad"], rtol=1e-4, atol=1e-5, what="ciou grad vs reference autograd")
     oc, og = O.compute_ciou(g["p"], g["t"], with_grad=True)
     assert_close(c.detach().cpu().numpy(), oc, rtol=1e-5, atol=1e-6, what="ciou vs oracle")
+    # the broadcasting form (detection_loss.py:231-234): targets [m, 4] against preds [m, A, 4]
+    m, A = g["p"].shape[0] // 5, 5
+    pb = dev(g["p"][: m * A]).reshape(m, A, 4).clone().requires_grad_(True)
+    tb = dev(g["t"][:m])
+    cb = ops.compute_ciou(pb, tb)
+    assert tuple(cb.shape) == (m, A)
+    cb.sum().backward()
+    te = np.repeat(g["t"][:m], A, axis=0)
+    oc2, og2 = O.compute_ciou(g["p"][: m * A], te, with_grad=True)
+    assert_close(cb.detach().cpu().numpy().reshape(-1), oc2, rtol=1e-5, atol=1e-6, what="broadcast ciou vs oracle")
+    assert_close(pb.grad.cpu().numpy().reshape(-1, 4), og2, rtol=1e-4, atol=1e-5, what="broadcast ciou grad vs oracle")
 
 
 # -------------------------------------------------------------------------------------- loss (B3)

@@ -58,8 +58,8 @@ def _make_build_target_by_scale(orig):
 # ------------------------------------------------------------------------------------------------ B2
 def _make_compute_ciou(orig):
     def compute_ciou(preds_xywh, targets_xywh, e: float = 1e-7):
-        if preds_xywh.shape != targets_xywh.shape:  # broadcasting form, unused by the repo (detection_loss.py:231-234)
-            return orig(preds_xywh, targets_xywh, e)
+        if targets_xywh.requires_grad and preds_xywh.shape != targets_xywh.shape:
+            return orig(preds_xywh, targets_xywh, e)   # (gradient to broadcast targets: never asked for by the reference)
         _need_cuda(preds_xywh, "compute_ciou")
         return ops.compute_ciou(preds_xywh, targets_xywh.to(preds_xywh.dtype), e)
     return compute_ciou

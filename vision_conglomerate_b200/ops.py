@@ -767,11 +767,20 @@ class _CIoU(torch.autograd.Function):
 
 
 def compute_ciou(preds_xywh: torch.Tensor, targets_xywh: torch.Tensor, e: float = 1e-7) -> torch.Tensor:
-    """``DetectionLoss.compute_ciou`` (modules/detection_loss.py:229-264), element-wise form, differentiable
-    w.r.t. ``preds_xywh`` (alpha held constant as under the reference's ``no_grad``)."""
+    """``DetectionLoss.compute_ciou`` (modules/detection_loss.py:229-264), differentiable w.r.t. ``preds_xywh`` (alpha held
+    constant as under the reference's ``no_grad``).  Element-wise form, or the broadcasting form of :231-234
+    (``preds [..., A, 4]`` against ``targets [..., 4]``: every target against the ``A`` boxes of its row)."""
+    if preds_xywh.dim() == targets_xywh.dim() + 1:
+        targets_xywh = targets_xywh.unsqueeze(-2)
+    if preds_xywh.dim() != targets_xywh.dim() or preds_xywh.shape[-1] != 4 or targets_xywh.shape[-1] != 4:
+        raise RuntimeError("compute_ciou: expected preds [..., 4] and targets of the same rank or one dimension less")
     if preds_xywh.shape != targets_xywh.shape:
-        raise RuntimeError("compute_ciou: the broadcasting form (preds.ndim == targets.ndim + 1) is unused by the "
-                           "reference and not provided")
+        if targets_xywh.requires_grad:
+            raise RuntimeError("compute_ciou: gradients flow to preds_xywh only; detach the broadcast targets")
+        shape = torch.broadcast_shapes(preds_xywh.shape, targets_xywh.shape)
+        if tuple(shape) != tuple(preds_xywh.shape):
+            preds_xywh = preds_xywh.expand(shape)
+        targets_xywh = targets_xywh.expand(shape)
     return _CIoU.apply(preds_xywh, targets_xywh, e)
 
 
