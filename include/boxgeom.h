@@ -169,6 +169,12 @@ void bg_profile_decode_cycles(void *dev_buf);
 int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
                     const float *anchors /*host [na,2]*/, int32_t H, int32_t W, int32_t inference, int32_t og_H,
                     int32_t og_W, void *stream);
+/* The same for the heads whose rows carry extra_cols more columns behind the box: rows are
+ * 5 + C + extra_cols floats; the first tanh_cols of the extra columns are the mask coefficients of the segmentation
+ * head, which _get_scale_pred passes through tanh (modules/detection.py:131-134); the rest is copied. */
+int bg_decode_scale_ex(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
+                       int32_t extra_cols, int32_t tanh_cols, const float *anchors /*host [na,2]*/, int32_t H, int32_t W,
+                       int32_t inference, int32_t og_H, int32_t og_W, void *stream);
 
 /* Rows of DetectionNet.forward(x, inference=True) (modules/detection.py:69-91) for selected candidates only:
  * out [n, 5+C+extra] = [obj logit, class logits, x, y, w, h, ...] of the flat candidates idx [n] (i64, b*N + i, e.g. the

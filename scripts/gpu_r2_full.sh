@@ -30,6 +30,14 @@ timeout 300 $SCMD > gpurun_out/seg_plain.log 2>&1 && \
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"seg_fwd|seg_bwd" -s 9 -c 3 -o gpurun_out/prof_seg_r2 -f $SCMD > gpurun_out/ncu_seg.log 2>&1
 echo "ncu seg full rc=$?" >> gpurun_out/stages.txt
 fi
+MCMD="python scripts/bench_seg.py --masks-only"
+if [ "$1" = "ncu" ]; then
+timeout 300 $MCMD > gpurun_out/segmask_plain.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"seg_lowres|seg_upsample" -s 8 -c 2 -o gpurun_out/prof_segmask_r2 -f $MCMD > gpurun_out/ncu_segmask.log 2>&1
+echo "ncu segmask full rc=$?" >> gpurun_out/stages.txt
+fi
+timeout 600 python scripts/bench_configs.py > gpurun_out/bench_configs.json 2> gpurun_out/bench_configs.err; echo "bench_configs rc=$?" >> gpurun_out/stages.txt
+timeout 300 python scripts/prof_c5.py > gpurun_out/prof_c5.log 2>&1; echo "prof_c5 rc=$?" >> gpurun_out/stages.txt
 timeout 300 python scripts/exp_pipe.py --depths 3,4,6 > gpurun_out/exp_pipe.log 2>&1; echo "exp_pipe rc=$?" >> gpurun_out/stages.txt
 timeout 600 python scripts/bench_seg.py > gpurun_out/bench_seg.log 2>&1; echo "bench_seg rc=$?" >> gpurun_out/stages.txt
 cat gpurun_out/stages.txt

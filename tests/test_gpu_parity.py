@@ -516,6 +516,24 @@ def test_decode_scale_golden(ops, name):
     assert_close(tr[..., C + 1:], g["train_sm_boxes"], rtol=1e-5, atol=1e-6, what="training decode")
 
 
+def test_decode_scale_segmentation_rows(ops):
+    """_get_scale_pred of the segmentation head (modules/detection.py:126-134,164-167): rows [obj, cls, box, K mask
+    coefficients, further columns] -- the box decodes as in the detection rows (bitwise the same kernel arithmetic), the
+    coefficients go through tanh (fp32, rtol 1e-5 against numpy), anything behind them is copied."""
+    B, H, W, C, K, X = 2, 128, 160, 7, 8, 3
+    g = torch.Generator().manual_seed(11)
+    a = synth.anchors_tensor("md")
+    raw = torch.randn(B, H // 16, W // 16, 3, 5 + C + K + X, generator=g) * 2.0
+    out = ops.decode_scale(dev(raw), a, (H, W), True, (200, 300), num_classes=C, tanh_cols=K).cpu()
+    base = ops.decode_scale(dev(raw[..., : 5 + C].contiguous()), a, (H, W), True, (200, 300)).cpu()
+    assert torch.equal(out[..., : 5 + C], base)
+    assert_close(out[..., 5 + C: 5 + C + K].numpy(), np.tanh(raw[..., 5 + C: 5 + C + K].numpy().astype(np.float64)), rtol=1e-5, atol=1e-7,
+                 what="tanh of the mask coefficients")
+    assert torch.equal(out[..., 5 + C + K:], raw[..., 5 + C + K:])
+    with pytest.raises(RuntimeError):
+        ops.decode_scale(dev(raw), a, (H, W), True, None, num_classes=C, tanh_cols=K + X + 1)
+
+
 # -------------------------------------------------------------------------- target assignment (B1)
 def _assign_check(ops, t, ny, nx, sc):
     anc = synth.anchors_tensor(sc)

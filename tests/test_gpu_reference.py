@@ -352,6 +352,18 @@ def test_segmentation_inference_zero_edit(ns):
     for og, iou, thr, tracked in (((150, 200), 0.5, 0.2, None), ((128, 128), 0.35, 0.24, [0, 2, 3])):
         with torch.no_grad():
             preds, protos = model(imgs, inference=True, og_size=og)
+        # the model's own inference decode (three scales: _get_scale_pred with tanh on the mask coefficients, _bbox_to_size)
+        # on the decode kernels: install(DetectionNet=...) patches the methods SegmentationNet inherits
+        dropin.install(DetectionNet=ns.DetectionNet, torchvision_ops=False)
+        try:
+            n0 = _lib.launch_count()
+            with torch.no_grad():
+                preds_p, protos_p = model(imgs, inference=True, og_size=og)
+            dec_launches = _lib.launch_count() - n0
+        finally:
+            dropin.uninstall()
+        assert dec_launches >= 3 and tuple(preds_p.shape) == tuple(preds.shape) and torch.equal(protos_p, protos)
+        assert_close(preds_p.cpu().numpy(), preds.cpu().numpy(), rtol=1e-5, atol=2e-5 * max(og), what="segmentation decode")
         cap_u = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og, capture_values=True)
         calls = []
         orig = ops.seg_masks

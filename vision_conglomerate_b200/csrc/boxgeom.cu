@@ -587,17 +587,19 @@ int bg_post_process(const float *preds, const bg_detect_params *pp, float *out_b
                        workspace_bytes, mask_bytes, stream);
 }
 
-int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
-                    const float *anchors, int32_t H, int32_t W, int32_t inference, int32_t og_H, int32_t og_W,
-                    void *stream)
+int bg_decode_scale_ex(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
+                       int32_t extra_cols, int32_t tanh_cols, const float *anchors, int32_t H, int32_t W, int32_t inference,
+                       int32_t og_H, int32_t og_W, void *stream)
 {
     if (!raw || !out || B <= 0 || ny <= 0 || nx <= 0 || na <= 0 || na > BG_MAX_ANCHORS || C <= 0) return BG_ERR_INVALID;
+    if (extra_cols < 0 || tanh_cols < 0 || tanh_cols > extra_cols) return BG_ERR_INVALID;
     if (inference && !anchors) return BG_ERR_INVALID;
     DecodeK k;
     memset(&k, 0, sizeof(k));
     k.raw = raw; k.out = out;
     k.rows = (long long)B * ny * nx * na;
-    k.ny = ny; k.nx = nx; k.na = na; k.C = C; k.D = C + 5;
+    k.ny = ny; k.nx = nx; k.na = na; k.C = C; k.D = C + 5 + extra_cols;
+    k.tanh_cols = tanh_cols;
     k.inference = inference;
     k.rescale = (og_H > 0 && og_W > 0 && og_H != H && og_W != W) ? 1 : 0;
     k.s0 = (float)H / (float)ny; k.s1 = (float)W / (float)nx;
@@ -607,6 +609,13 @@ int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t
     decode_scale_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(k);
     BG_LAUNCH_CHECK();
     return BG_OK;
+}
+
+int bg_decode_scale(const float *raw, float *out, int32_t B, int32_t ny, int32_t nx, int32_t na, int32_t C,
+                    const float *anchors, int32_t H, int32_t W, int32_t inference, int32_t og_H, int32_t og_W,
+                    void *stream)
+{
+    return bg_decode_scale_ex(raw, out, B, ny, nx, na, C, 0, 0, anchors, H, W, inference, og_H, og_W, stream);
 }
 
 int bg_decode_rows(const float *raw_sm, const float *raw_md, const float *raw_lg, const bg_detect_params *pp, const int64_t *idx,

@@ -505,6 +505,7 @@ struct DecodeK {
     long long rows;
     int ny, nx, na, C, D;
     int inference, rescale;
+    int tanh_cols;   // the first tanh_cols columns behind the box go through tanh (mask coefficients, detection.py:131-134)
     float s0, s1, fnx, fny, fW, fH, fW0, fH0;
     float aw[BG_MAX_ANCHORS], ah[BG_MAX_ANCHORS];
 };
@@ -517,7 +518,9 @@ __global__ void __launch_bounds__(256) decode_scale_kernel(DecodeK k)
         const long long row = e / k.D;
         const int c = (int)(e - row * k.D);
         float v = __ldg(k.raw + e);
-        if (c > k.C) {
+        if (c > k.C + 4) {
+            if (c - k.C - 5 < k.tanh_cols) v = tanhf(v);
+        } else if (c > k.C) {
             const int q = c - k.C - 1;  // 0:x 1:y 2:w 3:h
             const int rl = (int)(row % ((long long)k.ny * k.nx * k.na));
             const int a = rl % k.na;

@@ -132,8 +132,17 @@ def _make_batched_nms(orig):
 # ------------------------------------------------------------------------------------------------ B5
 def _make_get_scale_pred(orig):
     def _get_scale_pred(self, scale_pred, anchors, input_shape, inference: bool = False):
-        if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
+        if self.num_keypoints is not None and self.num_keypoints > 0:
             return orig(self, scale_pred, anchors, input_shape, inference)
+        if hasattr(self, "proto_seg_module"):
+            # segmentation head: the detection decode plus tanh on the mask coefficients (detection.py:131-134);
+            # the inference form runs on the decode kernel, the training form (autograd) stays the reference's
+            K = int(self.proto_seg_module.out_channels)
+            if not inference or scale_pred.requires_grad and torch.is_grad_enabled() \
+                    or scale_pred.shape[-1] != self.num_classes + 5 + K:
+                return orig(self, scale_pred, anchors, input_shape, inference)
+            _need_cuda(scale_pred, "_get_scale_pred")
+            return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), True, None, self.num_classes, K)
         _need_cuda(scale_pred, "_get_scale_pred")
         if not inference:
             if scale_pred.shape[-1] != self.num_classes + 5:
@@ -249,8 +258,8 @@ def _make_head_forward(orig):
 
 def _make_bbox_to_size(orig):
     def _bbox_to_size(self, pred, _from, _to):
-        if hasattr(self, "proto_seg_module") or (self.num_keypoints is not None and self.num_keypoints > 0):
-            return orig(self, pred, _from, _to)
+        if self.num_keypoints is not None and self.num_keypoints > 0:
+            return orig(self, pred, _from, _to)      # (keypoints are rescaled too, detection.py:186-189)
         _need_cuda(pred, "_bbox_to_size")
         if isinstance(pred, LazyPreds) and pred.pending:
             og = getattr(_tls, "og_size", None)

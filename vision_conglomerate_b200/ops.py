@@ -622,17 +622,23 @@ def post_process(preds: torch.Tensor, input_shape: Tuple[int, int], num_classes:
 
 
 def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int], inference: bool = False,
-                 og_size: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                 og_size: Optional[Tuple[int, int]] = None, num_classes: Optional[int] = None, tanh_cols: int = 0) -> torch.Tensor:
     """``DetectionNet._get_scale_pred`` (modules/detection.py:98-173), optionally followed by
-    ``_bbox_to_size`` (:175-190, guard of :76 applied inside)."""
+    ``_bbox_to_size`` (:175-190, guard of :76 applied inside).  ``num_classes`` (default: row length - 5) tells where the
+    box sits when the rows carry more columns behind it; the first ``tanh_cols`` of those are the segmentation head's mask
+    coefficients, which the reference passes through ``tanh`` (:131-134)."""
     x = _req(scale_pred, "scale_pred")
     B, ny, nx, na, D = x.shape
+    Cc = D - 5 if num_classes is None else int(num_classes)
+    extra = D - 5 - Cc
+    if Cc <= 0 or extra < 0 or not 0 <= tanh_cols <= extra:
+        raise RuntimeError("decode_scale: rows of %d columns do not hold 5 + %d columns (+ %d through tanh)" % (D, Cc, tanh_cols))
     out = torch.empty_like(x)
     og = (int(og_size[0]), int(og_size[1])) if og_size is not None else (-1, -1)
     with _on(x.device):
-        check(_lib.lib().bg_decode_scale(x.data_ptr(), out.data_ptr(), B, ny, nx, na, D - 5, _anchor_array(anchors),
-                                         int(input_shape[0]), int(input_shape[1]), int(bool(inference)), og[0], og[1],
-                                         _stream(x.device)), "bg_decode_scale")
+        check(_lib.lib().bg_decode_scale_ex(x.data_ptr(), out.data_ptr(), B, ny, nx, na, Cc, extra, int(tanh_cols),
+                                            _anchor_array(anchors), int(input_shape[0]), int(input_shape[1]),
+                                            int(bool(inference)), og[0], og[1], _stream(x.device)), "bg_decode_scale")
     return out
 
 
