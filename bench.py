@@ -229,7 +229,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import ref_harness
-    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, min(args.warmup, 8))   # (every step costs ~4 s per image; reported as run)
     if ref_harness.available():
         sample = 1 if steps * 4 > 40 else 2        # ~4 s per image: keep the whole run within a few minutes
         ips, threads, t, kept = cpu_reference_detect(sample, steps=steps, warmup=warmup)
