@@ -254,7 +254,9 @@ def ref_seg_post_process(preds, protos, num_classes, iou_threshold, score_thresh
         ih, iw = img_size if img_size is not None else (protos.shape[2], protos.shape[3])
         imgs = torch.zeros(B, 3, ih, iw, dtype=torch.uint8)
         with torch.no_grad():
-            inf.post_process_preds(imgs, preds.clone(), protos.clone(), num_classes, iou_threshold=iou_threshold,
+            # (the reference adds the box allowance in place; a stand-in of the drop-in is handed over as it is)
+            inf.post_process_preds(imgs, preds.clone() if type(preds) is torch.Tensor else preds, protos.clone(), num_classes,
+                                   iou_threshold=iou_threshold,
                                    score_threshold=score_threshold, box_allowance=box_allowance,
                                    tracked_classes=list(tracked_classes) if tracked_classes else None)
     finally:

@@ -74,8 +74,13 @@ def test_dropin_keeps_reference_signatures():
     from vision_conglomerate_b200 import dropin
     import torchvision
     ns = ref_harness.load()
+    import inference_seg
+    from modules.segmentation_loss import SegmentationLoss
     before_fns = (ns.DetectionNet.forward, ns.EffiDecHead.forward, ns.inference_det.post_process_preds)
+    before_seg = (inference_seg.post_process_preds, SegmentationLoss.forward)
     before = {
+        "sppp": inspect.signature(inference_seg.post_process_preds),
+        "segfwd": inspect.signature(SegmentationLoss.forward),
         "bts": inspect.signature(ns.DetectionDataset.build_target_by_scale),
         "ciou": inspect.signature(ns.DetectionLoss.compute_ciou),
         "fwd": inspect.signature(ns.DetectionLoss.forward),
@@ -90,10 +95,14 @@ def test_dropin_keeps_reference_signatures():
         "ppp": inspect.signature(ns.inference_det.post_process_preds),
     }
     dropin.install(ns.DetectionDataset, ns.DetectionLoss, ns.DetectionNet, make_anchors=ns.make_anchors,
-                   EffiDecHead=ns.EffiDecHead, inference_det=ns.inference_det)
+                   EffiDecHead=ns.EffiDecHead, inference_det=ns.inference_det, inference_seg=inference_seg,
+                   SegmentationLoss=SegmentationLoss)
     try:
         assert all(dropin.installed().values())
+        assert inference_seg.post_process_preds is not before_seg[0] and SegmentationLoss.forward is not before_seg[1]
         after = {
+            "sppp": inspect.signature(inference_seg.post_process_preds),
+            "segfwd": inspect.signature(SegmentationLoss.forward),
             "bts": inspect.signature(ns.DetectionDataset.build_target_by_scale),
             "ciou": inspect.signature(ns.DetectionLoss.compute_ciou),
             "fwd": inspect.signature(ns.DetectionLoss.forward),
@@ -135,6 +144,7 @@ def test_dropin_keeps_reference_signatures():
     assert not any(dropin.installed().values())
     assert ns.DetectionNet.forward is before_fns[0] and ns.EffiDecHead.forward is before_fns[1] \
         and ns.inference_det.post_process_preds is before_fns[2]
+    assert inference_seg.post_process_preds is before_seg[0] and SegmentationLoss.forward is before_seg[1]
     ref = ns.DetectionDataset.build_target_by_scale(synth.targets(1, 3), (20, 20), synth.anchors_tensor("lg"))
     assert len(ref) == 6
 
@@ -221,7 +231,7 @@ def test_lazy_preds_stand_in_mechanics():
     raws = synth.raw_head_outputs(B, H, W, C, "N", 3)
     anc = [synth.anchors_tensor(k) for k in synth.SCALES]
     real_dec, real_b2s = ops.decode_scale, ops.bbox_to_size
-    ops.decode_scale = lambda x, a, ishape, inference, og=None: net._get_scale_pred(x.clone(), a, input_shape=ishape, inference=inference)
+    ops.decode_scale = lambda x, a, ishape, inference, og=None, num_classes=None, tanh_cols=0: net._get_scale_pred(x.clone(), a, input_shape=ishape, inference=inference)
     ops.bbox_to_size = lambda pred, f, t, nc: net._bbox_to_size(pred, f, t)
     try:
         og = (100, 130)

@@ -344,7 +344,7 @@ def test_segmentation_inference_zero_edit(ns):
     reference's drawing code against the unpatched torch-CUDA run; a mask pixel may differ only where the unpatched
     run's interpolated value is within 5e-5 of 0.5."""
     import inference_seg
-    from vision_conglomerate_b200 import _lib, dropin, ops
+    from vision_conglomerate_b200 import _lib, dropin, lazy, ops
     B, S, C = 3, 128, 5       # (a random-init model keeps hundreds of rows per image: small frames keep the mask arrays small)
     torch.manual_seed(42)
     model = ns.SegmentationNet(3, C, ref_harness.model_config("segmentation"), synth.ANCHORS, num_keypoints=0).cuda().eval()
@@ -365,29 +365,46 @@ def test_segmentation_inference_zero_edit(ns):
         assert dec_launches >= 3 and tuple(preds_p.shape) == tuple(preds.shape) and torch.equal(protos_p, protos)
         assert_close(preds_p.cpu().numpy(), preds.cpu().numpy(), rtol=1e-5, atol=2e-5 * max(og), what="segmentation decode")
         cap_u = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og, capture_values=True)
-        calls = []
-        orig = ops.seg_masks
-        ops.seg_masks = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
-        dropin.install(inference_seg=inference_seg)
-        try:
-            n0 = _lib.launch_count()
-            cap_p = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og)
-            launches = _lib.launch_count() - n0
-        finally:
-            dropin.uninstall()
-            ops.seg_masks = orig
-        assert len(cap_u["masks"]) > 0 and len(calls) == len(cap_u["masks"]), (len(calls), len(cap_u["masks"]))
-        assert len(cap_p["per_image"]) == len(cap_u["per_image"]) and len(cap_p["masks"]) == len(cap_u["masks"])
-        assert np.array_equal(np.sort(cap_p["keep"].cpu().numpy()), np.sort(cap_u["keep"].cpu().numpy()))
-        nd = npx = bad = 0
-        for a, b, ma, mb, v in zip(cap_p["per_image"], cap_u["per_image"], cap_p["masks"], cap_u["masks"], cap_u["values"]):
-            assert a.shape == b.shape and ma.shape == mb.shape == v.shape and ma.dtype == np.bool_
-            oa, ob = np.lexsort((a[:, 2], a[:, 1], -a[:, 0])), np.lexsort((b[:, 2], b[:, 1], -b[:, 0]))
-            assert_close(a[oa], b[ob], rtol=1e-5, atol=2e-5 * 400, what="rows")
-            diff = ma[oa] != mb[ob]
-            nd += int(diff.sum())
-            npx += diff.size
-            bad += int((diff & (np.abs(v[ob].astype(np.float64) - 0.5) >= 5e-5)).sum())
-        assert bad == 0, "%d mask pixels differ away from the threshold" % bad
-        print("zero-edit segmentation inference og=%s tracked=%s: %d images, %d masks, %d of %d pixels differ (all on the "
-              "threshold), %d launches of ours" % (og, tracked, len(cap_u["masks"]), sum(len(m) for m in cap_u["masks"]), nd, npx, launches))
+        for mode in ("masks", "fused"):
+            calls = []
+            orig = ops.seg_masks
+            ops.seg_masks = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+            # "masks": post_process_preds on the decoded tensor (NMS by bg_batched_nms over all candidates, masks by the mask
+            # kernels); "fused": the model hands over a stand-in, the wrapped function runs the fused decode+NMS on the head
+            # outputs and the reference's code on the kept rows only
+            if mode == "masks":
+                dropin.install(inference_seg=inference_seg)
+            else:
+                dropin.install(DetectionNet=ns.DetectionNet, inference_seg=inference_seg)
+            try:
+                n0 = _lib.launch_count()
+                if mode == "fused":
+                    with torch.no_grad():
+                        preds_l, protos_l = model(imgs, inference=True, og_size=og)
+                    assert isinstance(preds_l, lazy.LazyPreds) and preds_l.pending and tuple(preds_l.shape) == tuple(preds.shape)
+                    assert _lib.launch_count() == n0                   # nothing decoded yet
+                    cap_p = ref_harness.ref_seg_post_process(preds_l, protos_l, C, iou, thr, 4, tracked, img_size=og)
+                    assert preds_l.pending                             # ... and the decoded [B, N, D] tensor never was
+                    assert cap_p["boxes"].shape[0] < preds.shape[0] * preds.shape[1]   # the reference ran on the kept rows only
+                else:
+                    cap_p = ref_harness.ref_seg_post_process(preds, protos, C, iou, thr, 4, tracked, img_size=og)
+                launches = _lib.launch_count() - n0
+            finally:
+                dropin.uninstall()
+                ops.seg_masks = orig
+            assert len(cap_u["masks"]) > 0 and len(calls) == len(cap_u["masks"]), (len(calls), len(cap_u["masks"]))
+            assert len(cap_p["per_image"]) == len(cap_u["per_image"]) and len(cap_p["masks"]) == len(cap_u["masks"])
+            if mode == "masks":
+                assert np.array_equal(np.sort(cap_p["keep"].cpu().numpy()), np.sort(cap_u["keep"].cpu().numpy()))
+            nd = npx = bad = 0
+            for a, b, ma, mb, v in zip(cap_p["per_image"], cap_u["per_image"], cap_p["masks"], cap_u["masks"], cap_u["values"]):
+                assert a.shape == b.shape and ma.shape == mb.shape == v.shape and ma.dtype == np.bool_
+                oa, ob = np.lexsort((a[:, 2], a[:, 1], -a[:, 0])), np.lexsort((b[:, 2], b[:, 1], -b[:, 0]))
+                assert_close(a[oa], b[ob], rtol=1e-5, atol=2e-5 * 400, what="rows")
+                diff = ma[oa] != mb[ob]
+                nd += int(diff.sum())
+                npx += diff.size
+                bad += int((diff & (np.abs(v[ob].astype(np.float64) - 0.5) >= 5e-5)).sum())
+            assert bad == 0, "%d mask pixels differ away from the threshold" % bad
+            print("zero-edit segmentation inference (%s) og=%s tracked=%s: %d images, %d masks, %d of %d pixels differ (all on the "
+                  "threshold), %d launches of ours" % (mode, og, tracked, len(cap_u["masks"]), sum(len(m) for m in cap_u["masks"]), nd, npx, launches))

@@ -142,7 +142,14 @@ def _make_get_scale_pred(orig):
                     or scale_pred.shape[-1] != self.num_classes + 5 + K:
                 return orig(self, scale_pred, anchors, input_shape, inference)
             _need_cuda(scale_pred, "_get_scale_pred")
-            return ops.decode_scale(scale_pred, anchors, tuple(int(v) for v in input_shape), True, None, self.num_classes, K)
+            ishape = tuple(int(v) for v in input_shape)
+            if _options["fuse_inference"] and "inference_seg.post_process_preds" in _saved:
+                # stands for the decoded tensor of this scale (as for the detection model below); the wrapped
+                # inference_seg.post_process_preds runs the fused decode+NMS on the head outputs
+                raw = scale_pred if scale_pred.is_contiguous() else scale_pred.contiguous()
+                return LazyPreds(tuple(raw.shape), [dict(raw=raw, anchors=anchors, input_shape=ishape, rescale=None, og_size=None,
+                                                         num_classes=self.num_classes, tanh_cols=K)])
+            return ops.decode_scale(scale_pred, anchors, ishape, True, None, self.num_classes, K)
         _need_cuda(scale_pred, "_get_scale_pred")
         if not inference:
             if scale_pred.shape[-1] != self.num_classes + 5:
@@ -195,51 +202,73 @@ def _make_post_process_preds(orig):
         rest = dict(colormap=colormap, iou_threshold=iou_threshold, score_threshold=score_threshold, vwriter=vwriter,
                     tracker=tracker, classmap=classmap, with_summary=with_summary, tracked_classes=tracked_classes,
                     start_idx=start_idx, box_allowance=box_allowance)
-        sc = preds.scales if isinstance(preds, LazyPreds) and preds.pending else None
-        if sc is None or len(sc) != 3 or preds.dim() != 3 or not (score_threshold >= 0) \
-                or len({(s["rescale"] is None, s["og_size"], s["input_shape"]) for s in sc}) != 1:
+        # 1. fused decode + score filter + per-image NMS on the head outputs (lines 57-89 of the reference function);
+        # 2. the reference's own function on the kept candidates only
+        small = _fused_rows(preds, int(num_classes), iou_threshold, score_threshold, box_allowance)
+        if small is None:
             return orig(imgs, preds, num_classes, **rest)
-        # 1. fused decode + score filter + per-image NMS on the head outputs (lines 57-89 of the reference function)
-        raws = [s["raw"] for s in sc]
-        og = sc[0]["og_size"] if sc[0]["rescale"] is not None else None
-        key = (raws[0].device, tuple(tuple(r.shape) for r in raws), sc[0]["input_shape"], og, float(iou_threshold),
-               float(score_threshold), box_allowance, int(num_classes))
-        plan = _detect_plans.get(key)
-        if plan is None:
-            if len(_detect_plans) > 8:
-                _detect_plans.clear()
-            plan = _detect_plans[key] = ops.DetectPlan([tuple(r.shape) for r in raws], [s["anchors"] for s in sc], sc[0]["input_shape"],
-                                                       int(num_classes), raws[0].device, og, float(iou_threshold),
-                                                       float(score_threshold), box_allowance, None, "image")
-        plan.enqueue(raws)
-        det = plan.result()
-        # 2. the reference's own function on the kept candidates only: their rows of the decoded tensor, image by image,
-        #    padded to a rectangle with rows that can neither pass the score threshold nor suppress anything
-        B, D = int(preds.shape[0]), int(preds.shape[2])
-        counts = det.counts.to(torch.int64)
-        kmax = max(int(counts.max()) if B else 0, 1)
-        small = torch.zeros(B, kmax, D, dtype=torch.float32, device=raws[0].device)
-        small[..., 0] = float("-inf")                                    # sigmoid(-inf) = 0: score 0, ranked last
-        if det.keep_idxs.numel():
-            rows = plan.decode_rows(det.keep_idxs)
-            offs = torch.zeros(B, dtype=torch.int64)
-            offs[1:] = torch.cumsum(counts, 0)[:-1]
-            offs = offs.to(rows.device, non_blocking=True)
-            pos = torch.arange(rows.shape[0], device=rows.device) - offs[det.sample_idxs]
-            small[det.sample_idxs, pos] = rows
         return orig(imgs, small, num_classes, **rest)
     return post_process_preds
 
 
+def _fused_rows(preds, num_classes, iou_threshold, score_threshold, box_allowance):
+    """Lines 57-89 of the reference's post_process_preds on the head outputs a pending LazyPreds stands for: fused decode +
+    score filter + per-image NMS, then the kept candidates' rows of the decoded tensor, image by image, padded to a
+    rectangle ``[B, kmax, D]`` with rows that can neither pass the score threshold nor suppress anything.  ``None`` if
+    ``preds`` is not such a stand-in (the caller then runs the reference's function on what it was given)."""
+    sc = preds.scales if isinstance(preds, LazyPreds) and preds.pending else None
+    if sc is None or len(sc) != 3 or preds.dim() != 3 or not (score_threshold >= 0) \
+            or len({(s["rescale"] is None, s["og_size"], s["input_shape"]) for s in sc}) != 1:
+        return None
+    raws = [s["raw"] for s in sc]
+    og = sc[0]["og_size"] if sc[0]["rescale"] is not None else None
+    key = (raws[0].device, tuple(tuple(r.shape) for r in raws), sc[0]["input_shape"], og, float(iou_threshold),
+           float(score_threshold), box_allowance, int(num_classes))
+    plan = _detect_plans.get(key)
+    if plan is None:
+        if len(_detect_plans) > 8:
+            _detect_plans.clear()
+        plan = _detect_plans[key] = ops.DetectPlan([tuple(r.shape) for r in raws], [s["anchors"] for s in sc], sc[0]["input_shape"],
+                                                   int(num_classes), raws[0].device, og, float(iou_threshold),
+                                                   float(score_threshold), box_allowance, None, "image")
+    plan.enqueue(raws)
+    det = plan.result()
+    B, D = int(preds.shape[0]), int(preds.shape[2])
+    counts = det.counts.to(torch.int64)
+    kmax = max(int(counts.max()) if B else 0, 1)
+    small = torch.zeros(B, kmax, D, dtype=torch.float32, device=raws[0].device)
+    small[..., 0] = float("-inf")                                    # sigmoid(-inf) = 0: score 0, ranked last
+    if det.keep_idxs.numel():
+        rows = plan.decode_rows(det.keep_idxs)
+        tc = int(sc[0].get("tanh_cols", 0))
+        if tc:                                                       # the mask coefficients (detection.py:131-134)
+            rows[:, 5 + num_classes: 5 + num_classes + tc].tanh_()
+        offs = torch.zeros(B, dtype=torch.int64)
+        offs[1:] = torch.cumsum(counts, 0)[:-1]
+        offs = offs.to(rows.device, non_blocking=True)
+        pos = torch.arange(rows.shape[0], device=rows.device) - offs[det.sample_idxs]
+        small[det.sample_idxs, pos] = rows
+    return small
+
+
 def _make_seg_post_process_preds(orig):
-    def post_process_preds(imgs, preds, protos, num_classes, *args, **kwargs):
-        # lines 62-97 run as written (their torchvision.ops.batched_nms is the re-pointed one); the prototypes are marked
-        # so that the host loop's per-image ``sigmoid(coefs @ protos[i]) -> F.interpolate -> torch.gt(0.5)`` (lines 115-117)
-        # is recognised and runs on the two mask kernels (lazy.ProtoTrace / lazy.LazyMasks)
+    def post_process_preds(imgs, preds, protos, num_classes, colormap=None, iou_threshold: float = 0.5,
+                           score_threshold: float = 0.1, vwriter=None, tracker=None, classmap=None, with_summary: bool = False,
+                           tracked_classes=None, start_idx: int = 0, box_allowance=None):
+        rest = dict(colormap=colormap, iou_threshold=iou_threshold, score_threshold=score_threshold, vwriter=vwriter,
+                    tracker=tracker, classmap=classmap, with_summary=with_summary, tracked_classes=tracked_classes,
+                    start_idx=start_idx, box_allowance=box_allowance)
+        # 1. lines 57-89 fused on the head outputs when the model handed over a stand-in (install(DetectionNet=...,
+        #    inference_seg=...)); otherwise they run as written (their torchvision.ops.batched_nms is the re-pointed one)
+        small = _fused_rows(preds, int(num_classes), iou_threshold, score_threshold, box_allowance)
+        if small is not None:
+            preds = small
+        # 2. the prototypes are marked so that the host loop's per-image ``sigmoid(coefs @ protos[i]) -> F.interpolate ->
+        #    torch.gt(0.5)`` (lines 115-117) is recognised and runs on the two mask kernels (lazy.ProtoTrace / LazyMasks)
         if isinstance(protos, torch.Tensor) and protos.is_cuda and protos.dtype == torch.float32 and protos.dim() == 4 \
                 and not protos.requires_grad and int(protos.shape[1]) <= 64:
             protos = protos.contiguous().as_subclass(ProtoTrace)
-        return orig(imgs, preds, protos, num_classes, *args, **kwargs)
+        return orig(imgs, preds, protos, num_classes, **rest)
     return post_process_preds
 
 

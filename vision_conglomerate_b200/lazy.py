@@ -176,7 +176,7 @@ class LazyPreds(torch.Tensor):
             from . import ops
             outs = []
             for sc in self._bg_scales:
-                d = ops.decode_scale(sc["raw"], sc["anchors"], sc["input_shape"], True)
+                d = ops.decode_scale(sc["raw"], sc["anchors"], sc["input_shape"], True, None, sc["num_classes"], sc.get("tanh_cols", 0))
                 if sc["rescale"] is not None:
                     d = ops.bbox_to_size(d, sc["rescale"][0], sc["rescale"][1], sc["num_classes"])
                 outs.append(d)
