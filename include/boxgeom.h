@@ -194,6 +194,10 @@ int bg_bbox_to_size(float *pred, int64_t rows, int32_t C, int32_t D, const int64
  * s = sigmoid(raw).  Makes DetectionNet._get_scale_pred differentiable on the CUDA path when its result is consumed
  * by something other than the fused loss (which takes the logits directly, BG_LOSS_RAW). */
 int bg_decode_train_bwd(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, void *stream);
+/* The same for rows of 5 + C + extra_cols floats whose first tanh_cols extra columns went through tanh (bg_decode_scale_ex,
+ * the segmentation head: modules/detection.py:131-134): grad_out * (1 - tanh(raw)^2) there, grad_out on the rest. */
+int bg_decode_train_bwd_ex(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, int32_t extra_cols,
+                           int32_t tanh_cols, void *stream);
 
 /* ------------------------------------------------------------------ B1
  * DetectionDataset.build_target_by_scale (dataset/detection_dataset.py:90-246), detection branch.

@@ -317,12 +317,19 @@ def test_segmentation_train_step_patched_equals_unpatched(ns):
     calls = []
     orig = ops.segmentation_loss
     ops.segmentation_loss = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
-    dropin.install(SegmentationLoss=ns.SegmentationLoss, torchvision_ops=False)
+    dec_calls = []
+    orig_dec = ops.decode_train
+    ops.decode_train = lambda *a, **k: (dec_calls.append(1), orig_dec(*a, **k))[1]
+    # (DetectionNet: SegmentationNet inherits _get_scale_pred -- its training-mode decode, tanh on the coefficients included,
+    #  runs as one differentiable CUDA kernel per scale and direction)
+    dropin.install(SegmentationLoss=ns.SegmentationLoss, DetectionNet=ns.DetectionNet, torchvision_ops=False)
     try:
         loss_p, met_p, grads_p = step()
+        assert len(dec_calls) == 3, dec_calls
     finally:
         dropin.uninstall()
         ops.segmentation_loss = orig
+        ops.decode_train = orig_dec
     assert calls, "the CUDA segmentation loss did not run"
     assert K == 32
     assert_close(loss_p, loss_u, rtol=1e-5, atol=0, what="loss")

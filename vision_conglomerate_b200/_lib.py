@@ -24,7 +24,7 @@ SYMBOLS = (
     "bg_strerror", "bg_version", "bg_launch_count", "bg_sizeof_detect_params", "bg_sizeof_loss_params", "bg_profile_events", "bg_profile_events_loss",
     "bg_profile_stamps", "bg_profile_stamps_per_image", "bg_profile_decode_cycles",
     "bg_batched_nms_workspace_bytes", "bg_batched_nms",
-    "bg_host_mapped_ptr", "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_scale_ex", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd",
+    "bg_host_mapped_ptr", "bg_detect_workspace_bytes", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_scale_ex", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_decode_train_bwd_ex",
     "bg_assign_workspace_bytes", "bg_assign_targets", "bg_assign_ex_workspace_bytes", "bg_assign_targets_ex",
     "bg_ciou_fwd", "bg_ciou_bwd",
     "bg_loss_workspace_bytes", "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine",
@@ -153,6 +153,7 @@ def lib() -> C.CDLL:
     L.bg_decode_scale.argtypes = [vp, vp, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, i32, i32, i32, vp]
     L.bg_decode_scale_ex.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), i32, i32, i32, i32, i32, vp]
     L.bg_decode_train_bwd.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.bg_decode_train_bwd_ex.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     L.bg_bbox_to_size.argtypes = [vp, i64, i32, i32, vp, vp, vp]
     L.bg_decode_rows.argtypes = [vp, vp, vp, C.POINTER(DetectParams), vp, i64, vp, vp]
     L.bg_assign_workspace_bytes.argtypes = [i64, i32]
@@ -180,7 +181,7 @@ def lib() -> C.CDLL:
     L.bg_seg_loss_fwd.argtypes = [C.POINTER(vp), vp, vp, vp, C.POINTER(SegParams), vp, vp, vp, vp, sz, vp]
     L.bg_seg_loss_bwd.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(SegParams), vp, C.POINTER(vp), vp, vp, sz, vp]
     L.bg_seg_masks.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i32, i32, vp, vp, vp]
-    for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_scale_ex", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
+    for name in ("bg_batched_nms", "bg_detect", "bg_post_process", "bg_decode_scale", "bg_decode_scale_ex", "bg_decode_rows", "bg_bbox_to_size", "bg_decode_train_bwd", "bg_decode_train_bwd_ex", "bg_assign_targets", "bg_assign_targets_ex", "bg_ciou_fwd", "bg_ciou_bwd",
                  "bg_loss_fwd", "bg_loss_bwd", "bg_loss_clear_grads", "bg_loss_pack", "bg_loss_combine", "bg_ratio_metrics",
                  "bg_seg_loss_fwd", "bg_seg_loss_bwd", "bg_seg_masks"):
         getattr(L, name).restype = C.c_int

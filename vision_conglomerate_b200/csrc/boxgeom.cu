@@ -646,14 +646,20 @@ int bg_bbox_to_size(float *pred, int64_t rows, int32_t C, int32_t D, const int64
     return BG_OK;
 }
 
-int bg_decode_train_bwd(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, void *stream)
+int bg_decode_train_bwd_ex(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, int32_t extra_cols,
+                           int32_t tanh_cols, void *stream)
 {
-    if (rows < 0 || C <= 0) return BG_ERR_INVALID;
+    if (rows < 0 || C <= 0 || extra_cols < 0 || tanh_cols < 0 || tanh_cols > extra_cols) return BG_ERR_INVALID;
     if (rows == 0) return BG_OK;
     if (!raw || !grad_out || !grad_raw) return BG_ERR_INVALID;
-    decode_train_bwd_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(raw, grad_out, grad_raw, rows, C);
+    decode_train_bwd_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(raw, grad_out, grad_raw, rows, C, extra_cols, tanh_cols);
     BG_LAUNCH_CHECK();
     return BG_OK;
+}
+
+int bg_decode_train_bwd(const float *raw, const float *grad_out, float *grad_raw, int64_t rows, int32_t C, void *stream)
+{
+    return bg_decode_train_bwd_ex(raw, grad_out, grad_raw, rows, C, 0, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------ B1

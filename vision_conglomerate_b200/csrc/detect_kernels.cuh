@@ -549,15 +549,21 @@ __global__ void __launch_bounds__(256) decode_scale_kernel(DecodeK k)
 
 // Backward of the training-mode decode (modules/detection.py:122,125): grad_raw = grad_out on the objectness / class
 // columns, grad_out * 2s(1-s) on x, y and grad_out * 8s^2(1-s) on w, h, with s = sigmoid(raw).
-__global__ void __launch_bounds__(256) decode_train_bwd_kernel(const float *raw, const float *go, float *gr, long long rows, int C)
+__global__ void __launch_bounds__(256) decode_train_bwd_kernel(const float *raw, const float *go, float *gr, long long rows, int C,
+                                                               int extra_cols, int tanh_cols)
 {
-    const int D = C + 5;
+    const int D = C + 5 + extra_cols;
     const long long total = rows * D;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(e % D);
         float g = __ldg(go + e);
-        if (c > C) {
+        if (c > C + 4) {
+            if (c - C - 5 < tanh_cols) {                                         // d tanh = 1 - tanh^2 (mask coefficients)
+                const float t = tanhf(__ldg(raw + e));
+                g = __fmul_rn(g, __fsub_rn(1.0f, __fmul_rn(t, t)));
+            }
+        } else if (c > C) {
             const float s = sigmoid_acc(__ldg(raw + e));
             const float t = __fmul_rn(s, __fsub_rn(1.0f, s));                    // sigmoid'
             g = (c - C - 1 < 2) ? __fmul_rn(__fmul_rn(g, 2.0f), t)              // d(2s - 0.5)

@@ -135,13 +135,13 @@ def _make_get_scale_pred(orig):
         if self.num_keypoints is not None and self.num_keypoints > 0:
             return orig(self, scale_pred, anchors, input_shape, inference)
         if hasattr(self, "proto_seg_module"):
-            # segmentation head: the detection decode plus tanh on the mask coefficients (detection.py:131-134);
-            # the inference form runs on the decode kernel, the training form (autograd) stays the reference's
+            # segmentation head: the detection decode plus tanh on the mask coefficients (detection.py:131-134)
             K = int(self.proto_seg_module.out_channels)
-            if not inference or scale_pred.requires_grad and torch.is_grad_enabled() \
-                    or scale_pred.shape[-1] != self.num_classes + 5 + K:
+            if scale_pred.shape[-1] != self.num_classes + 5 + K or (inference and scale_pred.requires_grad and torch.is_grad_enabled()):
                 return orig(self, scale_pred, anchors, input_shape, inference)
             _need_cuda(scale_pred, "_get_scale_pred")
+            if not inference:     # training mode: one differentiable kernel each way (SegmentationLoss takes decoded rows)
+                return ops.decode_train(scale_pred, self.num_classes, K)
             ishape = tuple(int(v) for v in input_shape)
             if _options["fuse_inference"] and "inference_seg.post_process_preds" in _saved:
                 # stands for the decoded tensor of this scale (as for the detection model below); the wrapped

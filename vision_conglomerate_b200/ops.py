@@ -644,26 +644,32 @@ def decode_scale(scale_pred: torch.Tensor, anchors, input_shape: Tuple[int, int]
 
 class _TrainDecode(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, num_classes, tanh_cols):
         ctx.save_for_backward(x)
-        return decode_scale(x, [[1.0, 1.0]] * x.shape[3], (1, 1), False)
+        ctx.cfg = (num_classes, tanh_cols)
+        return decode_scale(x, [[1.0, 1.0]] * x.shape[3], (1, 1), False, None, num_classes, tanh_cols)
 
     @staticmethod
     def backward(ctx, go):
         (x,) = ctx.saved_tensors
+        Cc, tc = ctx.cfg
         go = go.contiguous() if go.dtype == torch.float32 else go.float().contiguous()
         gr = torch.empty_like(x)
         with _on(x.device):
-            check(_lib.lib().bg_decode_train_bwd(x.data_ptr(), go.data_ptr(), gr.data_ptr(), x.numel() // x.shape[-1],
-                                                 x.shape[-1] - 5, _stream(x.device)), "bg_decode_train_bwd")
-        return gr
+            check(_lib.lib().bg_decode_train_bwd_ex(x.data_ptr(), go.data_ptr(), gr.data_ptr(), x.numel() // x.shape[-1],
+                                                    Cc, x.shape[-1] - 5 - Cc, tc, _stream(x.device)), "bg_decode_train_bwd")
+        return gr, None, None
 
 
-def decode_train(scale_pred: torch.Tensor) -> torch.Tensor:
+def decode_train(scale_pred: torch.Tensor, num_classes: Optional[int] = None, tanh_cols: int = 0) -> torch.Tensor:
     """``DetectionNet._get_scale_pred(..., inference=False)`` (modules/detection.py:98-173), differentiable: one CUDA
     kernel each way instead of ~15 ATen kernels and their autograd graph.  (The fused loss does not need it -- it
-    takes the logits, ``detection_loss(..., input_form="raw")``; this is for every other consumer.)"""
-    return _TrainDecode.apply(_req(scale_pred, "scale_pred"))
+    takes the logits, ``detection_loss(..., input_form="raw")``; this is for every other consumer.)  ``num_classes`` /
+    ``tanh_cols``: rows with more columns behind the box, the first ``tanh_cols`` of them through ``tanh`` (the segmentation
+    head's mask coefficients, :131-134)."""
+    x = _req(scale_pred, "scale_pred")
+    Cc = x.shape[-1] - 5 if num_classes is None else int(num_classes)
+    return _TrainDecode.apply(x, Cc, int(tanh_cols))
 
 
 def bbox_to_size(pred: torch.Tensor, _from: torch.Tensor, _to: torch.Tensor, num_classes: int) -> torch.Tensor:
