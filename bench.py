@@ -934,6 +934,121 @@ def extras(torch, ops, synth, devc):
                                                                   "(25,200 survivors per image exceed the per-image kernels)"}
     except Exception as e:  # noqa: BLE001
         out["stress_error"] = repr(e)
+    anc = [synth.anchors_tensor(s) for s in synth.SCALES]
+    # ---- BASELINE configs[4]: batch-1 video frames at 640^2, IoU 0.35 / score 0.3, tracked classes, og (720, 1280); wall clock
+    try:
+        frames = [[r.to(devc) for r in synth.raw_head_outputs(1, 640, 640, 80, "TP", 7 + f)] for f in range(16)]
+        shapes = [tuple(r.shape) for r in frames[0]]
+        tr = synth.tracked_classes_default()
+        res = {}
+        for name, host in (("device_rows_count_read_and_sync", False), ("host_rows_polled_flag", True)):
+            plan = ops.DetectPlan(shapes, anc, (640, 640), 80, devc, (720, 1280), 0.35, 0.3, 4, tr, host_result=host)
+            lat, rows = [], 0
+            for f in range(332):
+                t0 = time.perf_counter()
+                plan.enqueue(frames[f % 16])
+                rows = plan.result_host().rows.shape[0] if host else plan.result().pred_boxes.shape[0]
+                lat.append((time.perf_counter() - t0) * 1e6)
+            lat = sorted(lat[32:])
+            res[name] = {"p50_us": lat[len(lat) // 2], "p99_us": lat[int(len(lat) * 0.99)], "frames": len(lat), "rows_last_frame": int(rows)}
+        res["what"] = ("per frame: enqueue the two kernels + get the result, wall clock; host_rows_polled_flag = DetectPlan(host_result=True): "
+                       "the kernels write rows / counts into page-locked host memory and store a flag last (no copy, no stream sync)")
+        out["c5_batch1_latency"] = res
+    except Exception as e:  # noqa: BLE001
+        out["c5_error"] = repr(e)
+    # ---- BASELINE configs[3]: 1280^2 (100,800 candidates/img), batch 32: decode+NMS (trained-like logits drawn on the device) and
+    #      assignment + loss fwd+bwd with 300 gt/img
+    try:
+        B, S, C = 32, 1280, 80
+        g = torch.Generator(device=devc).manual_seed(9)
+        raws = []
+        for ny, nx in synth.fmap_shapes(S, S):
+            z = torch.randn(B, ny, nx, 3, 5 + C, generator=g, device=devc)
+            z[..., 0] = -9.0 + 2.0 * z[..., 0]
+            z[..., 1:1 + C] = -4.0 + 1.5 * z[..., 1:1 + C]
+            raws.append(z.contiguous())
+        shapes = [tuple(r.shape) for r in raws]
+        plan = ops.DetectPlan(shapes, anc, (S, S), C, devc, None, 0.65, 0.001, 4)
+        plan.enqueue(raws)
+        r = plan.result()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            plan.enqueue(raws)
+        e1.record()
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / 5
+        pipe = ops.DetectPipeline(shapes, anc, (S, S), C, devc, None, 0.65, 0.001, 4, None, depth=4)
+        for _ in range(2):
+            for _d in range(4):
+                pipe.submit(raws)
+            for d in range(4):
+                pipe.result(d)
+        pipe.join()
+        e0.record()
+        for _ in range(16):
+            pipe.submit(raws)
+        pipe.join()
+        e1.record()
+        torch.cuda.synchronize()
+        msp = e0.elapsed_time(e1) / 16
+        peak, _src = _peaks()
+        out["c4_detect_1280_b32"] = {"ms_per_batch": ms1, "img_per_s": B / (ms1 * 1e-3), "ms_per_batch_4_in_flight": msp,
+                                     "img_per_s_4_in_flight": B / (msp * 1e-3), "hbm_frac_4_in_flight": plan.input_bytes / (msp * 1e-3) / 1e9 / peak,
+                                     "survivors_per_image": float(r.candidates.float().mean()), "kept_rows": int(r.pred_boxes.shape[0])}
+        del raws, plan, pipe
+        torch.cuda.empty_cache()
+        t = synth.targets(B, 300, C, 0).to(devc)
+        parts = [tuple(torch.randn(B, ny, nx, 3, n_, generator=g, device=devc).squeeze(-1).contiguous().requires_grad_(True) if n_ == 1
+                       else torch.randn(B, ny, nx, 3, n_, generator=g, device=devc).requires_grad_(True) for n_ in (1, C, 4))
+                 for ny, nx in synth.fmap_shapes(S, S)]
+        cfg = dict(synth.LOSS_CONFIG, num_classes=C)
+        gs = ops.LossStepGraph(parts, t, anc, cfg, input_form="split")
+        for _ in range(3):
+            gs.replay()
+        e0.record()
+        for _ in range(10):
+            gs.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        mst = e0.elapsed_time(e1) / 10
+        N4 = synth.candidates_per_image(S, S)
+        out["c4_train_1280_b32_300gt"] = {"ms_per_step": mst, "img_per_s": B / (mst * 1e-3), "form": "split, CUDA-graph replay",
+                                          "hbm_frac_dense_gradient_only": B * N4 * (5 + C) * 4 / (mst * 1e-3) / 1e9 / peak}
+        del gs, parts
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001
+        out["c4_error"] = repr(e)
+    # ---- SURVEY 8 f2, inference side: boolean masks of 200 kept rows, protos 160^2 -> 640^2 (inference_seg.py:115-117)
+    try:
+        Bm, K, Hp, Wp, H, W = 8, 32, 160, 160, 640, 640
+        g = torch.Generator(device=devc).manual_seed(5)
+        counts = torch.full((Bm,), 25)
+        coefs = torch.tanh(torch.randn(int(counts.sum()), K, generator=g, device=devc))
+        protos = torch.randn(Bm, K, Hp, Wp, generator=g, device=devc)
+
+        def torch_masks():
+            r0 = 0
+            for i, c in enumerate(counts.tolist()):
+                m = (coefs[r0:r0 + c] @ protos[i].reshape(K, -1)).reshape(-1, Hp, Wp).sigmoid()
+                m = torch.nn.functional.interpolate(m.unsqueeze(0), size=(H, W), mode="bilinear", align_corners=False)
+                torch.gt(m, 0.5)
+                r0 += c
+
+        def timed(fn, n=20):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        a, b = timed(lambda: ops.seg_masks(coefs, counts, protos, (H, W))), timed(torch_masks)
+        out["seg_masks_200x640x640"] = {"ours_ms": a, "same_torch_calls_ms": b, "speedup": b / a, "output_MB": 200 * H * W / 1e6}
+    except Exception as e:  # noqa: BLE001
+        out["seg_masks_error"] = repr(e)
     return out
 
 
