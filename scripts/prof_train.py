@@ -67,3 +67,21 @@ torch.cuda.synchronize()
 fwd = e[0].elapsed_time(e[1]) / a.iters
 both = e[1].elapsed_time(e[2]) / a.iters
 print("train form=%s B=%d gt=%d S=%d: fwd %.3f ms, fwd+bwd %.3f ms (%.0f img/s), loss %.6f" % (a.form, B, a.gt, S, fwd, both, B / both * 1e3, float(loss)))
+
+if a.form != "decoded" and os.environ.get("BG_GRAPH", "1") == "1":   # the same step replayed from a CUDA graph (ops.LossStepGraph)
+    cfg = dict(synth.LOSS_CONFIG, num_classes=C)
+    clones = [tuple(q.detach().clone().requires_grad_(True) for q in p) if isinstance(p, tuple) else p.detach().clone().requires_grad_(True)
+              for p in preds]
+    gs = ops.LossStepGraph(clones, t, anc, cfg, input_form=a.form)
+    for _ in range(3):
+        gs.replay()
+    best = 1e9
+    for _r in range(3):
+        x, y = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x.record()
+        for _ in range(20):
+            gs.replay()
+        y.record()
+        torch.cuda.synchronize()
+        best = min(best, x.elapsed_time(y) / 20)
+    print("train form=%s B=%d graph replay: %.4f ms per step (%.0f img/s)" % (a.form, B, best, B / best * 1e3))

@@ -9,6 +9,8 @@ reference root).
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import weakref
 from dataclasses import dataclass
