@@ -9,8 +9,6 @@ reference root).
 """
 from __future__ import annotations
 
-import os
-
 import ctypes as C
 import weakref
 from dataclasses import dataclass
