@@ -1188,3 +1188,29 @@ def test_seg_masks_vs_oracle_and_torch(ops):
     nt = assert_masks_match(masks, np.concatenate(outs, 0), vals, what="masks vs torch-CUDA", band=5e-5)
     print("seg_masks 29 x 640x640: %d pixels differ from the oracle, %d from torch-CUDA (all on the threshold)" % (nd, nt))
     assert ops.seg_masks(dev(coefs[:0]), torch.zeros(B, dtype=torch.int64), dev(protos), (H, W)).shape == (0, H, W)
+
+
+@pytest.mark.parametrize("K,Hp,Wp,H,W,counts", [
+    (5, 7, 9, 21, 30, [3, 0, 2]),            # W % 4 != 0: one pixel per thread; K not a multiple of four
+    (64, 40, 40, 20, 20, [4, 1]),            # masks made smaller: source lines are skipped; the largest K
+    (8, 100, 300, 110, 304, [2, 5]),         # a block's source lines exceed the shared-memory window: read from global memory
+    (16, 33, 17, 257, 131, [1]),             # odd everything, enlargement by non-integer factors, a single row
+    (3, 2, 2, 9, 8, [0, 0, 6, 0]),           # tiny prototypes (every output line interpolates the same two source lines), empty images
+])
+def test_seg_masks_shapes(ops, K, Hp, Wp, H, W, counts):
+    """bg_seg_masks on the code paths the goldens do not reach: against the numpy restatement of inference_seg.py:115-117
+    (a pixel may differ only where the interpolated value is within 2e-5 of 0.5)."""
+    from oracle import seg_oracle as SO
+    from tests.util import assert_masks_match
+    g = torch.Generator().manual_seed(K * 1000 + H)
+    counts = torch.tensor(counts)
+    B = counts.numel()
+    coefs = torch.tanh(torch.randn(int(counts.sum()), K, generator=g))
+    protos = torch.randn(B, K, Hp, Wp, generator=g)
+    masks = ops.seg_masks(dev(coefs), counts, dev(protos), (H, W))
+    assert masks.dtype == torch.bool and tuple(masks.shape) == (int(counts.sum()), H, W)
+    ref, vals = SO.seg_masks(coefs.numpy(), counts.numpy(), protos.numpy(), H, W)
+    nd = assert_masks_match(masks.cpu().numpy(), ref, vals)
+    frac = float(ref.mean())
+    assert 0.05 < frac < 0.95                                      # (the case is not trivially all-false / all-true)
+    print("seg_masks K=%d %dx%d -> %dx%d rows %s: %d pixels differ (all on the threshold)" % (K, Hp, Wp, H, W, counts.tolist(), nd))
