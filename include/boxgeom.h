@@ -110,7 +110,8 @@ typedef struct {
                                  * with nms_event: decode on `stream` -> event -> NMS on nms_stream -> event -> `stream` (which
                                  * therefore still sees the finished batch; no host synchronisation) */
     void *nms_event;            /* cudaEvent_t of the caller (timing disabled is fine), required with nms_stream */
-    void *host_flag;            /* optional (NULL = off): a 32-bit word in page-locked HOST memory that the device can address
+    void *host_flag;            /* optional (NULL = off; replaces the per-image `boxes.detach().cpu().numpy()` of the reference's host
+                                 * loop, inference_det.py:116-118): a 32-bit word in page-locked HOST memory that the device can address
                                  * (cudaHostAlloc / cudaHostRegister; bg_host_mapped_ptr checks it).  The last kernel of the call
                                  * stores host_flag_value there once every output of the call is visible to the host, so a caller
                                  * that ALSO placed out_boxes / out_img / out_keep / out_counts in such memory (batch-1 video
