@@ -30,6 +30,36 @@ def test_library_exports_every_declared_symbol():
     assert L.bg_sizeof_seg_params() == __import__("ctypes").sizeof(_lib.SegParams)
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/boxgeom.h is the drop-in boundary: it must compile as strict C99 (no C++-isms, no torch types) and a C
+    program must link against libboxgeom.so and call it -- here only entry points that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include "boxgeom.h"\n#include <stdio.h>\n#include <string.h>\n'
+        "int main(void) {\n"
+        "    bg_detect_params p; bg_loss_params q; bg_seg_params r;\n"
+        "    memset(&p, 0, sizeof p); memset(&q, 0, sizeof q); memset(&r, 0, sizeof r);\n"
+        "    p.B = 64; p.C = 80; p.na = 3; p.H = 640; p.W = 640;\n"
+        "    for (int s = 0; s < 3; ++s) { p.ny[s] = p.nx[s] = 80 >> s; }\n"
+        '    printf("%d %s %zu %zu %zu %zu %d\\n", bg_version(), bg_strerror(0), bg_sizeof_detect_params(), sizeof p,\n'
+        "           bg_sizeof_loss_params() - sizeof q + bg_sizeof_seg_params() - sizeof r, bg_detect_workspace_bytes(&p, 0),\n"
+        "           bg_batched_nms(NULL, NULL, NULL, -1, 0.5, 16, NULL, NULL, NULL, 0, 0, NULL));\n"
+        "    return 0;\n}\n")
+    libdir = os.path.join(ROOT, "vision_conglomerate_b200", "csrc")
+    exe = tmp_path / "abi"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", libdir, "-lboxgeom", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    ver, ok, sz_lib, sz_c, diff, ws, rc = out.stdout.split()
+    assert int(ver) >= 100 and ok == "ok" and sz_lib == sz_c and int(diff) == 0 and int(ws) > 0 and int(rc) == 1
+
+
 def test_workspace_queries_run_on_host():
     import ctypes as C
     L = _lib.lib()
