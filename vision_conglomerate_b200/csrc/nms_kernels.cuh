@@ -99,6 +99,7 @@ __device__ __forceinline__ ScanPair block_excl_scan_1024(ScanPair v, ScanPair *s
 // kernel T: per-segment prefix tables (one CTA)
 // ------------------------------------------------------------------------------------------------
 constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_LONG = 24;      // cell-order entries of one (box, grid row) from which the warp shares the run out
 
 __global__ void __launch_bounds__(1024) seg_tables_kernel(SegNms p)
 {
@@ -378,43 +379,79 @@ __global__ void __launch_bounds__(PAIR_THREADS) nms_grid_pairs_kernel(SegNms p)
         const int seg = lo;
         const SegGrid gr = p.grid[seg];
         const int q = (item - p.item_prefix[seg]) * PAIR_THREADS + threadIdx.x;
-        if (q >= gr.nvalid) continue;
+        const bool live = q < gr.nvalid;      // (idle lanes stay in the loop: the warp shares out long cell runs below)
         const long long off = p.seg_off[seg];
         const u64 *bk = p.bkeys + off;
         const u32 *wh = p.bwh + off;
         const int *cs = p.cell_start + p.cell_off[seg];
         const int G = gr.G;
-        const u64 key = bk[q];
+        const u64 key = live ? bk[q] : 0ull;
         const u32 cell = (u32)(key >> 32), pos = (u32)key;
-        const float4 a = p.bbox[off + q];
-        const float aa = p.barea[off + q];
+        const float4 a = live ? p.bbox[off + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float aa = live ? p.barea[off + q] : 0.f;
         const float w = __fsub_rn(a.z, a.x), h = __fsub_rn(a.w, a.y);
         const float cx = 0.5f * a.x + 0.5f * a.z, cy = 0.5f * a.y + 0.5f * a.w;
         const float rx = p.reach * w + gr.pad, ry = p.reach * h + gr.pad;
         const int ay = (int)cell / G, ax = (int)cell - ay * G;
-        const int y1 = seg_cell_y(gr, cy + ry), xl = seg_cell_x(gr, cx - rx), x1 = seg_cell_x(gr, cx + rx);
-        // IoU > t needs both extent ratios above t: conservative reject on the bf16 extents (1 % slack for the fp32
-        // rounding of the exact test, 2^-7 for the truncation) before the partner's box is touched
-        const float wlo = 0.99f * thr.tdn * w, hlo = 0.99f * thr.tdn * h, tsc = 0.99f * thr.tdn;
+        const int y1 = live ? seg_cell_y(gr, cy + ry) : -1, xl = seg_cell_x(gr, cx - rx), x1 = seg_cell_x(gr, cx + rx);
         u64 *edges = p.mask + p.edge_off[seg];
         const unsigned long long ecap = (unsigned long long)(p.edge_off[seg + 1] - p.edge_off[seg]);
-        for (int gy = ay; gy <= y1; ++gy) {
-            const bool own_row = gy == ay;
-            const int x0 = own_row ? ax : xl;
-            int qa = cs[gy * G + x0];
-            const int qb = cs[gy * G + x1 + 1];
-            if (own_row) qa = max(qa, q + 1);  // own cell: only the boxes after this one in cell order
-            for (int q2 = qa; q2 < qb; ++q2) {
-                const u32 v = wh[q2];
-                const float wt = __uint_as_float(v << 16), ht = __uint_as_float(v & 0xffff0000u);
-                if (wt * 1.008f < wlo || ht * 1.008f < hlo || tsc * wt > w || tsc * ht > h) continue;
-                if (!iou_suppresses(a, aa, p.bbox[off + q2], p.barea[off + q2], thr)) continue;
-                const u32 pos2 = (u32)bk[q2];
-                const u64 ed = pos < pos2 ? (((u64)pos << 32) | pos2) : (((u64)pos2 << 32) | pos);
-                const unsigned long long e = atomicAdd(&p.edge_count[seg], 1ull);
-                if (e < ecap) edges[e] = ed;
-                else if (e == ecap) atomicOr(&p.hdr->overflow, 1);
+        // IoU > t needs both extent ratios above t: conservative reject on the bf16 extents (1 % slack for the fp32
+        // rounding of the exact test, 2^-7 for the truncation) before the partner's box is touched
+        auto test = [&](const float4 ba, float baa, float bw, float bh, u32 bpos, int q2) {
+            const float wlo = 0.99f * thr.tdn * bw, hlo = 0.99f * thr.tdn * bh, tsc = 0.99f * thr.tdn;
+            const u32 v = wh[q2];
+            const float wt = __uint_as_float(v << 16), ht = __uint_as_float(v & 0xffff0000u);
+            if (wt * 1.008f < wlo || ht * 1.008f < hlo || tsc * wt > bw || tsc * ht > bh) return;
+            if (!iou_suppresses(ba, baa, p.bbox[off + q2], p.barea[off + q2], thr)) return;
+            const u32 pos2 = (u32)bk[q2];
+            const u64 ed = bpos < pos2 ? (((u64)bpos << 32) | pos2) : (((u64)pos2 << 32) | bpos);
+            // one atomic per group of lanes that arrive here together (every lane of the warp appends to the same
+            // segment's counter: crowded segments would otherwise serialise millions of atomics on one address)
+            const u32 am = __activemask();
+            const int leader = __ffs(am) - 1;
+            unsigned long long base = 0;
+            if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&p.edge_count[seg], (unsigned long long)__popc(am));
+            base = __shfl_sync(am, base, leader);
+            const unsigned long long e = base + (unsigned long long)__popc(am & lanemask_lt());
+            if (e < ecap) edges[e] = ed;
+            else if (e == ecap) atomicOr(&p.hdr->overflow, 1);
+        };
+        // Row by row.  The runs of cell-order entries a box has to look at differ by orders of magnitude (a large box
+        // reaches hundreds of cells of a row, a small one a handful), and the 32 boxes of a warp are neighbours in cell
+        // order, not in size: long runs are shared out over the lanes of the warp, the others are scanned by their own lane.
+        const int lane = threadIdx.x & 31;
+        for (int gy = ay; __any_sync(0xffffffffu, gy <= y1); ++gy) {
+            const bool mine = gy <= y1;
+            int qa = 0, qb = 0;
+            if (mine) {
+                const bool own_row = gy == ay;
+                qa = cs[gy * G + (own_row ? ax : xl)];
+                qb = cs[gy * G + x1 + 1];
+                if (own_row) qa = max(qa, q + 1);  // own cell: only the boxes after this one in cell order
             }
+            // shared out: the runs of the lowest length class (24 / 96 / 384 entries and more) that at most eight lanes
+            // reach -- when most lanes have long runs they are busy in parallel anyway, and one lane per run is cheaper
+            const int len = qb - qa;
+            u32 lm = __ballot_sync(0xffffffffu, len >= PAIR_LONG);
+            if (__popc(lm) > 8) lm = __ballot_sync(0xffffffffu, len >= 4 * PAIR_LONG);
+            if (__popc(lm) > 8) lm = __ballot_sync(0xffffffffu, len >= 16 * PAIR_LONG);
+            if (__popc(lm) > 8) lm = 0u;
+            const bool is_long = (lm >> lane) & 1u;
+            while (lm) {
+                const int src = __ffs(lm) - 1;
+                lm &= lm - 1;
+                float4 ba;
+                ba.x = __shfl_sync(0xffffffffu, a.x, src); ba.y = __shfl_sync(0xffffffffu, a.y, src);
+                ba.z = __shfl_sync(0xffffffffu, a.z, src); ba.w = __shfl_sync(0xffffffffu, a.w, src);
+                const float baa = __shfl_sync(0xffffffffu, aa, src);
+                const u32 bpos = __shfl_sync(0xffffffffu, pos, src);
+                const int ba_q = __shfl_sync(0xffffffffu, qa, src), bb_q = __shfl_sync(0xffffffffu, qb, src);
+                const float bw = __fsub_rn(ba.z, ba.x), bh = __fsub_rn(ba.w, ba.y);
+                for (int q2 = ba_q + lane; q2 < bb_q; q2 += 32) test(ba, baa, bw, bh, bpos, q2);
+            }
+            if (!is_long)
+                for (int q2 = qa; q2 < qb; ++q2) test(a, aa, w, h, pos, q2);
         }
     }
 }
