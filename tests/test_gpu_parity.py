@@ -905,6 +905,24 @@ def test_ops_follow_the_tensors_device(ops):
     idx0 = ops.build_target_by_scale(t.cuda(0), (16, 16), anc[0])
     idx1 = ops.build_target_by_scale(t.to(d1), (16, 16), anc[0])
     assert idx1[1].device == d1 and torch.equal(torch.stack(idx0[0]).cpu(), torch.stack(idx1[0]).cpu())
+    # the operators added late in round 2: mask assembly, the segmentation head's decode, the host-result plan
+    gq = torch.Generator().manual_seed(3)
+    coefs, protos, cnt = torch.tanh(torch.randn(5, 8, generator=gq)), torch.randn(2, 8, 16, 16, generator=gq), torch.tensor([2, 3])
+    m0 = ops.seg_masks(coefs.cuda(0), cnt, protos.cuda(0), (40, 48))
+    m1 = ops.seg_masks(coefs.to(d1), cnt, protos.to(d1), (40, 48))
+    assert m1.device == d1 and torch.equal(m0.cpu(), m1.cpu())
+    rs = torch.randn(2, 8, 8, 3, 5 + 7 + 4, generator=gq)
+    s0 = ops.decode_scale(rs.cuda(0), anc[1], (128, 128), True, None, num_classes=7, tanh_cols=4)
+    s1 = ops.decode_scale(rs.to(d1), anc[1], (128, 128), True, None, num_classes=7, tanh_cols=4)
+    assert s1.device == d1 and torch.equal(s0.cpu(), s1.cpu())
+    one = [r[:1].contiguous() for r in raws]
+    shapes = [tuple(r.shape) for r in one]
+    h0 = ops.DetectPlan(shapes, anc, (H, W), C, torch.device("cuda", 0), None, 0.5, 0.01, 4, host_result=True)
+    h1 = ops.DetectPlan(shapes, anc, (H, W), C, d1, None, 0.5, 0.01, 4, host_result=True)
+    h0.enqueue([r.cuda(0) for r in one])
+    h1.enqueue([r.to(d1) for r in one])
+    r0, r1 = h0.result_host(), h1.result_host()
+    assert r0.rows.shape[0] > 0 and np.array_equal(r0.rows.view(np.uint32), r1.rows.view(np.uint32))
     assert torch.cuda.current_device() == 0
     with pytest.raises(RuntimeError, match="one device"):
         ops.detection_loss(p0, t.to(d1), anc, synth.LOSS_CONFIG)
