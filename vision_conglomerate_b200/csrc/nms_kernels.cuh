@@ -99,6 +99,7 @@ __device__ __forceinline__ ScanPair block_excl_scan_1024(ScanPair v, ScanPair *s
 // kernel T: per-segment prefix tables (one CTA)
 // ------------------------------------------------------------------------------------------------
 constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_CTAS_PER_SM = 12;   // resident CTAs of the pair kernel per SM (<= 42 registers per thread)
 constexpr int PAIR_LONG = 24;      // cell-order entries of one (box, grid row) from which the warp shares the run out
 
 __global__ void __launch_bounds__(1024) seg_tables_kernel(SegNms p)
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) seg_sort_kernel(SegNms p)
 // order.  A pair in different cells is tested by the box whose cell comes first in row-major order, a pair inside
 // one cell by the box that is earlier in cell order (each box of an overlapping pair lies in the other's reach).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PAIR_THREADS) nms_grid_pairs_kernel(SegNms p)
+__global__ void __launch_bounds__(PAIR_THREADS, PAIR_CTAS_PER_SM) nms_grid_pairs_kernel(SegNms p)
 {
     __shared__ int s_item;
     if (p.hdr->status & (BG_STATUS_MASK_SPACE | BG_STATUS_GROUP_RANGE)) return;
@@ -856,7 +857,7 @@ static int segnms_run(const SegNms &p, int S_launch, int32_t *out_counts, int co
     seg_sort_kernel<<<g, SORT_THREADS, segnms_sort_smem(), st>>>(p);
     BG_LAUNCH_CHECK();
     if (p.sparse) {
-        nms_grid_pairs_kernel<<<num_sms * 8, PAIR_THREADS, 0, st>>>(p);
+        nms_grid_pairs_kernel<<<num_sms * PAIR_CTAS_PER_SM, PAIR_THREADS, 0, st>>>(p);
         BG_LAUNCH_CHECK();
     }
     nms_mask_kernel<<<num_sms * 8, MASK_THREADS, 0, st>>>(p);
