@@ -741,7 +741,7 @@ __global__ void __launch_bounds__(REDUCE_THREADS) nms_reduce_kernel(SegNms p, in
 // so every round decides at least one box, and a box is decided only from decided predecessors: the result is
 // the sequential greedy scan's.  Then the same emission as the dense path.
 // ------------------------------------------------------------------------------------------------
-constexpr int RESOLVE_THREADS = 512;
+constexpr int RESOLVE_THREADS = 1024;
 constexpr int RESOLVE_SMEM_BOXES = 32768;  // segments up to this size keep their state in shared memory (2 x 32 KB)
 
 __global__ void __launch_bounds__(RESOLVE_THREADS) nms_resolve_kernel(SegNms p, int32_t *out_counts, int counts_per_seg)
@@ -765,13 +765,23 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) nms_resolve_kernel(SegNms p, 
         for (int i = threadIdx.x; i < K; i += RESOLVE_THREADS) { state[i] = 0; blocked[i] = 0; }
         __syncthreads();
         while (ne > 0) {
-            for (long long e = threadIdx.x; e < ne; e += RESOLVE_THREADS) {
-                const u64 ed = __ldcg(edges + e);
-                const u32 i = (u32)(ed >> 32), j = (u32)ed;
-                if (state[j] == 0) {
-                    const unsigned char si = state[i];
-                    if (si == 1) state[j] = 2;
-                    else if (si == 0) blocked[j] = 1;
+            // (four edges per thread in flight: the list lives in L2 and every round sweeps all of it)
+            for (long long e = threadIdx.x; e < ne; e += 4 * RESOLVE_THREADS) {
+                u64 ed[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const long long eu = e + (long long)u * RESOLVE_THREADS;
+                    ed[u] = eu < ne ? __ldcg(edges + eu) : ~0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ed[u] == ~0ull) continue;
+                    const u32 i = (u32)(ed[u] >> 32), j = (u32)ed[u];
+                    if (state[j] == 0) {
+                        const unsigned char si = state[i];
+                        if (si == 1) state[j] = 2;
+                        else if (si == 0) blocked[j] = 1;
+                    }
                 }
             }
             __syncthreads();
