@@ -764,26 +764,34 @@ __global__ void __launch_bounds__(RESOLVE_THREADS) nms_resolve_kernel(SegNms p, 
         const long long ne = bad ? 0 : (long long)p.edge_count[seg];
         for (int i = threadIdx.x; i < K; i += RESOLVE_THREADS) { state[i] = 0; blocked[i] = 0; }
         __syncthreads();
+        // Thread t owns the edges t, t + NT, t + 2 NT, ... and keeps only the live ones, packed to the front of its own
+        // positions: an edge i -> j is dead for good once j is decided or i is suppressed, so later rounds sweep a fraction
+        // of the list (crowded segments need dozens of rounds).  Eight edges per thread are in flight: the list lives in L2.
+        u64 *ew = const_cast<u64 *>(edges);
+        long long mine = ne > (long long)threadIdx.x ? (ne - threadIdx.x + RESOLVE_THREADS - 1) / RESOLVE_THREADS : 0;
         while (ne > 0) {
-            // (four edges per thread in flight: the list lives in L2 and every round sweeps all of it)
-            for (long long e = threadIdx.x; e < ne; e += 4 * RESOLVE_THREADS) {
-                u64 ed[4];
+            long long w = 0;
+            for (long long k0 = 0; k0 < mine; k0 += 8) {
+                u64 ed[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const long long eu = e + (long long)u * RESOLVE_THREADS;
-                    ed[u] = eu < ne ? __ldcg(edges + eu) : ~0ull;
-                }
+                for (int u = 0; u < 8; ++u)
+                    ed[u] = k0 + u < mine ? __ldcg(edges + threadIdx.x + (k0 + u) * RESOLVE_THREADS) : ~0ull;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     if (ed[u] == ~0ull) continue;
                     const u32 i = (u32)(ed[u] >> 32), j = (u32)ed[u];
                     if (state[j] == 0) {
                         const unsigned char si = state[i];
                         if (si == 1) state[j] = 2;
-                        else if (si == 0) blocked[j] = 1;
+                        else if (si == 0) {
+                            blocked[j] = 1;
+                            ew[threadIdx.x + w * RESOLVE_THREADS] = ed[u];   // (w <= k0 + u: never ahead of the reads)
+                            ++w;
+                        }
                     }
                 }
             }
+            mine = w;
             __syncthreads();
             int pending = 0;
             for (int j = threadIdx.x; j < K; j += RESOLVE_THREADS) {
